@@ -1,0 +1,172 @@
+/*
+ * svt_hevc_b200.h -- C ABI of libsvthevc_b200.so, the B200 (sm_100a) implementation of the
+ * SVT-HEVC per-CTU data-parallel hot path.
+ *
+ * This library takes the place of the reference's ASM_TYPES function-pointer dispatch
+ * (Source/Lib/Codec/EbDefinitions.h:350-364, tables in EbComputeSAD.h:95-175,
+ * EbMeSadCalculation.h:106-121, EbMcp.h/EbMcpTables.c, EbTransforms.h:271-510,
+ * EbIntraPrediction.h:470-642, EbDeblockingFilter.h:245-268, EbSampleAdaptiveOffset.h:171-335,
+ * EbPackUnPack.h:27-164).  Two kinds of entry points:
+ *
+ *   (1) leaf entry points `svtb200_<ReferenceName>`: the EXACT prototype of the reference
+ *       typedef they replace (host pointers, by-value scalars).  One call = one H2D copy,
+ *       one kernel, one D2H copy.  They exist so that every kernel can be unit-compared 1:1
+ *       with the reference's C/SIMD rows and dropped into a table row for debugging.
+ *   (2) batched / picture-level entry points: one call processes every CTU (or every job)
+ *       of a picture.  These are what MotionEstimationKernel (EbMotionEstimationProcess.c:603)
+ *       and EncDecKernel (EbEncDecProcess.c:2630) call through the shim.
+ *       Each has a `_dev` twin that takes device pointers + a CUDA stream so a caller that
+ *       keeps pictures resident in HBM pays no copies.
+ *
+ * Conventions: plain C types only; all sizes in samples unless noted; every function returns
+ * SVTB200_OK (0) or a negative error.  There is NO CPU fallback: without a CUDA device every
+ * compute entry point returns SVTB200_ERR_NO_DEVICE.
+ */
+#ifndef SVT_HEVC_B200_H
+#define SVT_HEVC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVTB200_OK               0
+#define SVTB200_ERR_NO_DEVICE   -1   /* maps to EB_ErrorInsufficientResources at EbInitEncoder */
+#define SVTB200_ERR_CUDA        -2
+#define SVTB200_ERR_BAD_ARG     -3   /* maps to EB_ErrorBadParameter */
+#define SVTB200_ERR_UNSUPPORTED -4
+
+#define SVTB200_ME_PU_COUNT 85      /* MAX_ME_PU_COUNT, EbDefinitions.h */
+#define SVTB200_LCU_SIZE    64      /* MAX_LCU_SIZE,   EbDefinitions.h:827 */
+
+/* ---------------------------------------------------------------------------------------
+ * Library lifetime (hook: EbInitEncoder right after ASM_TYPES is set, EbEncHandle.c:702-707)
+ * ------------------------------------------------------------------------------------- */
+int         svtb200_init(int device_ordinal);      /* creates context, streams, staging pools */
+void        svtb200_shutdown(void);
+int         svtb200_device_count(void);            /* 0 when no CUDA device is visible        */
+const char *svtb200_version(void);
+const char *svtb200_last_error(void);
+/* number of kernel launches issued by this library since load (bench.py "gpu_launches") */
+uint64_t    svtb200_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Plane descriptor: mirror of the luma part of EbPictureBufferDesc_t
+ * (EbPictureBufferDesc.h:26-70): buf points at the top-left of the PADDED allocation,
+ * the visible picture starts at (origin_x, origin_y), row pitch is `stride` samples.
+ * Indices computed by the reference (origin + x + (origin + y) * stride) are valid as-is.
+ * ------------------------------------------------------------------------------------- */
+typedef struct svtb200_plane {
+    uint8_t *buf;        /* host pointer (plain API) or device pointer (_dev API) */
+    uint32_t stride;
+    uint16_t origin_x;
+    uint16_t origin_y;
+    uint16_t width;
+    uint16_t height;
+} svtb200_plane;
+
+/* =======================================================================================
+ *  A. Motion estimation
+ * ===================================================================================== */
+
+/* a1: leaf, prototype of EB_SADLOOPKERNELNxM_TYPE (EbComputeSAD.h:36-48);
+ *     semantics of SadLoopKernel (C_DEFAULT/EbComputeSAD_C.c:165). The caller passes the size
+ *     of the readable reference region so the host->device copy is bounded:
+ *     the kernel reads ref[x + y*refStride + sy*srcStrideRaw] for x < width+searchAreaWidth-1. */
+int svtb200_SadLoopKernel(
+    const uint8_t *src, uint32_t srcStride,
+    const uint8_t *ref, uint32_t refStride,
+    uint32_t height, uint32_t width,
+    uint64_t *bestSad, int16_t *xSearchCenter, int16_t *ySearchCenter,
+    uint32_t srcStrideRaw, int16_t searchAreaWidth, int16_t searchAreaHeight);
+
+/* a4: leaf, EB_SADKERNELNxM_TYPE (EbComputeSAD.h:26-32), FastLoop_NxMSadKernel
+ *     (C_DEFAULT/EbComputeSAD_C.c:141).  Returns the SAD through *sad. */
+int svtb200_NxMSadKernel(
+    const uint8_t *src, uint32_t srcStride, const uint8_t *ref, uint32_t refStride,
+    uint32_t height, uint32_t width, uint32_t *sad);
+
+/* a5: leaf, CombinedAveragingSAD (C_DEFAULT/EbComputeSAD_C.c:14). */
+int svtb200_CombinedAveragingSAD(
+    const uint8_t *src, uint32_t srcStride, const uint8_t *ref1, uint32_t ref1Stride,
+    const uint8_t *ref2, uint32_t ref2Stride, uint32_t height, uint32_t width, uint32_t *sad);
+
+/* a2+a3: leaf, one call of FullPelSearch_LCU (EbMotionEstimation.c:586) over a
+ *     searchAreaWidth x searchAreaHeight window: the 8-position path
+ *     (GetEightHorizontalSearchPointResults_8x8_16x16_PU / _32x32_64x64,
+ *     C_DEFAULT/EbComputeSAD_C.c:244,355) for the multiple-of-8 part and the single-position
+ *     path (SadCalculation_8x8_16x16 / _32x32_64x64, C_DEFAULT/EbMeSadCalculation_C.c:16,73)
+ *     for the remainder.  best_sad/best_mv are the 85-entry pLcuBestSad/pLcuBestMV arrays
+ *     (n-order: 64x64, 4x32x32, 16x16x16, 64x8x8 in the reference's tab order,
+ *     EbMotionEstimationContext.h:352-360); they are READ (running best) and UPDATED.
+ *     src = 64x64 LCU (stride srcStride); ref points at the top-left search position. */
+int svtb200_FullPelSearch_LCU(
+    const uint8_t *src, uint32_t srcStride, const uint8_t *ref, uint32_t refStride,
+    int16_t xSearchAreaOrigin, int16_t ySearchAreaOrigin,
+    uint32_t searchAreaWidth, uint32_t searchAreaHeight,
+    uint32_t best_sad[SVTB200_ME_PU_COUNT], uint32_t best_mv[SVTB200_ME_PU_COUNT]);
+
+/* Per-picture ME configuration: the fields MotionEstimateLcu (EbMotionEstimation.c:3671)
+ * reads from MeContext_t (EbMotionEstimationContext.h:309-464), PictureParentControlSet_t and
+ * SequenceControlSet_t after SignalDerivationMeKernelOq (EbMotionEstimationProcess.c:308) has run. */
+typedef struct svtb200_me_config {
+    uint16_t pic_width, pic_height;        /* lumaWidth / lumaHeight                           */
+    uint8_t  num_lists;                    /* 1 = P picture (list 0), 2 = B picture            */
+    uint8_t  temporal_layer;               /* temporalLayerIndex                               */
+    uint8_t  hierarchical_levels;          /* hierarchicalLevels (row of the multiplier table) */
+    uint8_t  enable_hme;                   /* enableHmeFlag                                    */
+    uint8_t  enable_hme_l0, enable_hme_l1, enable_hme_l2;
+    uint8_t  one_quadrant_hme;             /* oneQuadrantHME                                   */
+    uint8_t  update_hme_search_center;     /* updateHmeSearchCenter (TRUE for >576p, tune 1)   */
+    uint8_t  n_hme_regions_w, n_hme_regions_h;   /* numberHmeSearchRegionInWidth/Height (<=2)  */
+    uint16_t hme_l0_total_w, hme_l0_total_h;
+    uint16_t hme_l0_w[2], hme_l0_h[2];
+    uint16_t hme_l1_w[2], hme_l1_h[2];
+    uint16_t hme_l2_w[2], hme_l2_h[2];
+    uint8_t  search_area_w, search_area_h; /* searchAreaWidth / searchAreaHeight               */
+    uint8_t  fractional_search_model;      /* 0 all, 1 selective, 2 off (integer-pel only)     */
+    uint8_t  cu8x8_mode, cu16x16_mode;     /* CU_8x8_MODE_x / CU_16x16_MODE_x                  */
+    uint8_t  rate_control_mode;            /* staticConfig.rateControlMode                     */
+    uint32_t lambda;                       /* MeContext_t::lambda                              */
+    uint32_t mvd_bits[12];                 /* MeContext_t::mvdBitsArray[NUMBER_OF_MVD_CASES]   */
+    uint64_t ref_poc[2];                   /* refPicPocArray                                   */
+} svtb200_me_config;
+
+/* Per-PU output record: the information MotionEstimateLcu writes into MeCuResults_t
+ * (EbMotionEstimationLcuResults.h:50-74, written at EbMotionEstimation.c:4348-4438),
+ * without C bitfields so the layout is ABI-stable. 24 bytes. */
+typedef struct svtb200_me_pu_result {
+    int16_t  x_mv_l0, y_mv_l0, x_mv_l1, y_mv_l1;  /* quarter-pel units */
+    uint32_t distortion[3];
+    uint8_t  direction[3];                          /* 0 = L0, 1 = L1, 2 = BI */
+    uint8_t  total_me_candidates;
+} svtb200_me_pu_result;
+
+/* Source ("picture analysis") pictures used by ME: full, 1/4 and 1/16 resolution luma
+ * (EbPaReferenceObject_t: inputPaddedPicturePtr, quarterDecimatedPicturePtr,
+ * sixteenthDecimatedPicturePtr, EbReferenceObject.c:182-195). */
+typedef struct svtb200_pa_picture {
+    svtb200_plane full, quarter, sixteenth;
+} svtb200_pa_picture;
+
+/* a6: picture-level ME: every LCU of the picture, every list.
+ *   results        [n_lcu][85] in PU order (0 = 64x64, 1-4 = 32x32, 5-20 = 16x16, 21-84 = 8x8 raster)
+ *   lcu_best_sad/mv optional [n_lcu][2][85] raw per-list pLcuBestSad/pLcuBestMV (n-order); may be NULL
+ *   rc_me_distortion optional [n_lcu] (rcMEdistortion), may be NULL
+ * Host variant copies the planes in and the results out (e2e); _dev variant takes device
+ * pointers in every svtb200_plane::buf and output pointer, and launches on `cuda_stream`. */
+int svtb200_me_picture(const svtb200_me_config *cfg, const svtb200_pa_picture *src,
+                       const svtb200_pa_picture *ref_l0, const svtb200_pa_picture *ref_l1,
+                       svtb200_me_pu_result *results, uint32_t *lcu_best_sad, uint32_t *lcu_best_mv,
+                       uint32_t *rc_me_distortion);
+int svtb200_me_picture_dev(const svtb200_me_config *cfg, const svtb200_pa_picture *src,
+                           const svtb200_pa_picture *ref_l0, const svtb200_pa_picture *ref_l1,
+                           svtb200_me_pu_result *results, uint32_t *lcu_best_sad, uint32_t *lcu_best_mv,
+                           uint32_t *rc_me_distortion, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVT_HEVC_B200_H */

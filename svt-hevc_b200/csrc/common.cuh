@@ -1,0 +1,86 @@
+// common.cuh -- shared host/device plumbing for libsvthevc_b200.so (sm_100a only).
+//
+// Threading model mirrors the reference's: leaf kernels are called concurrently and lock-free
+// from many EncDec / ME pthreads (SURVEY §8b "Threading").  Every calling thread gets its own
+// CUDA stream and its own grow-only device scratch arena + pinned staging block (thread_local),
+// so no entry point takes a lock after first use.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "svt_hevc_b200.h"
+
+namespace svtb200 {
+
+extern std::atomic<uint64_t> g_launches;
+void set_error(const char *fmt, ...);
+int  ensure_device();   // SVTB200_OK or SVTB200_ERR_NO_DEVICE; selects the device for this thread
+
+#define SVTB200_CUDA_TRY(expr)                                                                  \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            ::svtb200::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+            return SVTB200_ERR_CUDA;                                                            \
+        }                                                                                       \
+    } while (0)
+
+// Per-thread execution context.
+struct ThreadCtx {
+    cudaStream_t stream = nullptr;
+    uint8_t *dev = nullptr;   size_t dev_cap = 0,  dev_used = 0;
+    uint8_t *pin = nullptr;   size_t pin_cap = 0,  pin_used = 0;
+    int init();
+    void reset() { dev_used = 0; pin_used = 0; }
+    // bump allocators; pointers stay valid until the next reset(); grow = sync + realloc
+    int dev_alloc(size_t bytes, void **out);
+    int pin_alloc(size_t bytes, void **out);
+    // reserve the total up front so later dev_alloc() calls never move the block
+    int dev_reserve(size_t bytes);
+    int pin_reserve(size_t bytes);
+};
+ThreadCtx *tls_ctx();
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+#define SVTB200_COUNT_LAUNCH() (::svtb200::g_launches.fetch_add(1, std::memory_order_relaxed))
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+// 4 consecutive bytes starting at an arbitrary byte address (global or shared): two aligned
+// 32-bit loads + one funnel shift (SASS: SHF.R.W).
+__device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t *p)
+{
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    const uint32_t lo = w[0];
+    if (sh == 0) return lo;
+    return __funnelshift_r(lo, w[1], sh);
+}
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t < v ? t : v;
+    }
+    return v;
+}
+#endif
+
+}  // namespace svtb200

@@ -1,0 +1,930 @@
+// me.cu -- motion estimation on B200: hierarchical ME block SAD search (HME level 0/1/2),
+// 85-PU full-pel search, integer-pel bi-prediction SAD and MeCuResults assembly.
+//
+// Replaces:
+//   SadLoopKernel*                       C_DEFAULT/EbComputeSAD_C.c:165, ASM_AVX2/EbComputeSAD_Intrinsic_AVX2.c:28,
+//                                        ASM_AVX2/EbComputeSAD_SadLoopKernel_AVX512.c:59,1121
+//   GetEightHorizontalSearchPointResults_8x8_16x16_PU / _32x32_64x64   C_DEFAULT/EbComputeSAD_C.c:244,355
+//   SadCalculation_8x8_16x16 / _32x32_64x64                            C_DEFAULT/EbMeSadCalculation_C.c:16,73
+//   FastLoop_NxMSadKernel / CombinedAveragingSAD                       C_DEFAULT/EbComputeSAD_C.c:141,14
+//   MotionEstimateLcu + helpers (driver logic)                         Codec/EbMotionEstimation.c:3671 (and :586,
+//                                        :1847,:2012,:2194,:2315,:2946,:3363,:2742,:2870,:4321-4438)
+//
+// Design: ONE CTA PER LCU for the whole picture (grid = #LCUs, 256 threads).  The CTA stages the 64x64 source
+// block and each reference search window in shared memory exactly once (every reference byte is read from
+// HBM/L2 once per LCU), evaluates search positions with VABSDIFF4 (__vsadu4: 4 byte-SADs per lane-op) on
+// funnel-shifted words, and reduces candidates with warp shuffles.  The reference's sequential tie-break rules
+// are kept by encoding the raster index in the reduction key (first minimum wins) and by replaying the 85-PU
+// best-update scan position by position in scan order.  No tensor-core work exists on this path.
+#include "common.cuh"
+
+namespace svtb200 {
+
+constexpr int NT = 256;                 // threads per CTA
+constexpr int CHUNK = 64;               // full-pel search positions evaluated per pass
+constexpr uint32_t MAX_SAD_INIT = 64 * 64 * 255;   // MAX_SAD_VALUE, EbMotionEstimation.c:99
+
+struct PlaneD {
+    const uint8_t *buf;
+    int stride, ox, oy, w, h;
+};
+struct MeArgs {
+    svtb200_me_config cfg;
+    PlaneD src[3];        // full, quarter, sixteenth
+    PlaneD ref[2][3];
+    svtb200_me_pu_result *results;
+    uint32_t *best_sad, *best_mv, *rc;
+    int cols, rows;
+    int win_bytes;        // bytes reserved for the window region of dynamic shared memory
+};
+
+__device__ __forceinline__ const uint8_t *pat(const PlaneD &p, int x, int y)
+{
+    return p.buf + (ptrdiff_t)(p.oy + y) * p.stride + (p.ox + x);
+}
+
+// ---- block-wide reductions ---------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void block_sum(uint32_t (&v)[N], uint32_t *s_red /* [8*N] */)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
+    __syncthreads();
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < N; ++i) s_red[wid * N + i] = v[i];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) t += s_red[w * N + i];
+        v[i] = t;
+    }
+}
+__device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v, unsigned long long *s_red /* [8] */)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_min_u64(v);
+    __syncthreads();
+    if (lane == 0) s_red[wid] = v;
+    __syncthreads();
+    unsigned long long t = s_red[0];
+#pragma unroll
+    for (int w = 1; w < NT / 32; ++w) t = s_red[w] < t ? s_red[w] : t;
+    return t;
+}
+
+// ---- window staging ------------------------------------------------------------------------
+// Copies `rows` rows of `wbytes` bytes starting at global address g (row pitch gstride) into shared memory
+// with row pitch wp (multiple of 4, >= wbytes + 8).  Word-granular and coalesced when the plane pitch is a
+// multiple of 4: the global byte misalignment `a` (0..3) is preserved, i.e. window byte x lives at column a + x.
+__device__ __forceinline__ int load_window(uint8_t *s_win, int wp, const uint8_t *g, int gstride, int wbytes, int rows)
+{
+    if ((gstride & 3) == 0) {
+        const int a = (int)((uintptr_t)g & 3);
+        const uint32_t *gw = (const uint32_t *)(g - a);
+        const int nW = (a + wbytes + 3) >> 2, gs4 = gstride >> 2, wp4 = wp >> 2;
+        uint32_t *sw = (uint32_t *)s_win;
+        for (int i = threadIdx.x; i < rows * nW; i += NT) {
+            const int r = i / nW, c = i - r * nW;
+            sw[r * wp4 + c] = __ldg(gw + (ptrdiff_t)r * gs4 + c);
+        }
+        return a;
+    }
+    for (int i = threadIdx.x; i < rows * wbytes; i += NT) {
+        const int r = i / wbytes, c = i - r * wbytes;
+        s_win[r * wp + c] = __ldg(g + (ptrdiff_t)r * gstride + c);
+    }
+    return 0;
+}
+__device__ __host__ __forceinline__ int win_pitch(int wbytes) { return ((wbytes + 3 + 3) & ~3) + 4; }
+
+// ---- exhaustive block search (semantics of SadLoopKernel, C_DEFAULT/EbComputeSAD_C.c:165) -----------------
+// s_blk: bw x bh source block in shared memory (pitch bp, multiple of 4); window staged by load_window().
+// Block row r is compared with window row y + r*row_step.  Returns min SAD (start value 0xffffff) and the
+// FIRST raster position attaining it; x/y are left untouched when no position qualifies.
+__device__ void sad_search(const uint8_t *s_blk, int bp, int bw, int bh, const uint8_t *s_win, int wp, int a,
+                           int row_step, int saw, int sah, unsigned long long *s_red64,
+                           uint32_t &best_sad, int &best_x, int &best_y)
+{
+    const int P = saw * sah;
+    // split block rows over RS lanes when there are few positions (HME level 1/2 windows)
+    int rs_log = 0;
+    while ((P << rs_log) < NT && (1 << (rs_log + 1)) <= bh && rs_log < 5) ++rs_log;
+    const int RS = 1 << rs_log;
+    const int rows_per = (bh + RS - 1) >> rs_log;
+    const int nw = (bw + 3) >> 2;
+    const uint32_t tail_mask = (bw & 3) ? ((1u << ((bw & 3) * 8)) - 1u) : 0xffffffffu;
+    const uint32_t *blk32 = (const uint32_t *)s_blk;
+    const int bp4 = bp >> 2;
+    unsigned long long best = ~0ull;
+    const int total = P << rs_log;
+    for (int base = 0; base < total; base += NT) {
+        const int i = base + threadIdx.x;
+        const bool active = i < total;
+        const int p = active ? (i >> rs_log) : 0, rsub = i & (RS - 1);
+        const int y = p / saw, x = p - y * saw;
+        uint32_t sad = 0;
+        if (active) {
+            const int r0 = rsub * rows_per, r1 = min(bh, r0 + rows_per);
+            const int col = a + x, wi = col >> 2, sh = (col & 3) * 8;
+            for (int r = r0; r < r1; ++r) {
+                const uint32_t *row = (const uint32_t *)(s_win + (y + r * row_step) * wp) + wi;
+                uint32_t lo = row[0];
+                for (int j = 0; j < nw; ++j) {
+                    const uint32_t hi = row[j + 1];
+                    uint32_t v = __funnelshift_r(lo, hi, sh);
+                    uint32_t s = blk32[r * bp4 + j];
+                    if (j == nw - 1) { v &= tail_mask; s &= tail_mask; }
+                    sad += __vsadu4(v, s);
+                    lo = hi;
+                }
+            }
+        }
+        for (int o = 1; o < RS; o <<= 1) sad += __shfl_xor_sync(0xffffffffu, sad, o);
+        if (active && rsub == 0 && sad < 0xffffffu) {
+            const unsigned long long key = ((unsigned long long)sad << 32) | (uint32_t)p;
+            best = key < best ? key : best;
+        }
+    }
+    best = block_min_u64(best, s_red64);
+    if (best != ~0ull) {
+        const int p = (int)(uint32_t)best;
+        best_sad = (uint32_t)(best >> 32);
+        best_y = p / saw;
+        best_x = p - best_y * saw;
+    } else {
+        best_sad = 0xffffffu;
+    }
+}
+
+// ---- LCU-sized row-subsampled SADs straight from global memory (centre tests) ----------------------------
+// N candidate displacements; SAD over lw x (lh/2) on every other row, doubled (subsampleSad = 1 calls in
+// TestSearchAreaBounds :3397 and EbHevcCheckZeroZeroCenter :2964).
+template <int N>
+__device__ void lcu_sads(const uint8_t *s_src, const PlaneD &rF, int ox, int oy, int lw, int lh,
+                         const int (&dx)[N], const int (&dy)[N], int ncand, uint32_t *s_red32, uint32_t (&out)[N])
+{
+    uint32_t acc[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc[k] = 0;
+    const int rows = lh >> 1, nw = lw >> 2;   // lw is a multiple of 8 (minimum CU size)
+    for (int i = threadIdx.x; i < rows * nw; i += NT) {
+        const int r = i / nw, j = i - r * nw;
+        const uint32_t s = ((const uint32_t *)s_src)[(2 * r) * 16 + j];
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+            if (k < ncand) acc[k] += __vsadu4(s, ld_u32_unaligned(pat(rF, ox + dx[k] + 4 * j, oy + dy[k] + 2 * r)));
+    }
+    block_sum<N>(acc, s_red32);
+#pragma unroll
+    for (int k = 0; k < N; ++k) out[k] = acc[k] << 1;
+}
+
+// the four-sided window clamp repeated through EbMotionEstimation.c (e.g. :1892-1930)
+__device__ __forceinline__ void clamp_window(int org, int pad, int limit, int &o, int &len)
+{
+    // left/top: the reference moves the origin first and then re-tests the SAME condition with the moved origin
+    // (e.g. :1892-1900), so the window is shifted but never shortened on this side
+    if (org + o < -pad) o = -pad - org;
+    if (org + o > limit - 1) o -= (org + o) - (limit - 1);
+    if (org + o + len > limit) { const int l = len - ((org + o + len) - limit); len = l < 1 ? 1 : l; }
+}
+__device__ __forceinline__ int clamp_center(int org, int c, int pad, int limit)
+{
+    if (org + c < -pad) c = -pad - org;
+    if (org + c > limit - 1) c -= (org + c) - (limit - 1);
+    return c;
+}
+__device__ __forceinline__ int s16(int v) { return (int)(short)v; }
+
+// MeEbHevcGetMvdFractionBits, Codec/EbMdRateEstimation.c:172
+__device__ uint32_t egk1_bits(int sym)
+{
+    uint32_t k = 1, n = 0;
+    while (sym >= (int)(1u << k)) { sym -= (1 << k); ++k; ++n; }
+    return n + 1 + k;
+}
+__device__ uint32_t mvd_bits(int mx, int my, const uint32_t *t)
+{
+    const uint32_t ax = (uint32_t)abs(mx), ay = (uint32_t)abs(my);
+    const uint32_t xn = ax != 0, yn = ay != 0, xg = ax > 1, yg = ay > 1;
+    uint32_t b = t[xn] + t[yn + (2u << xn)];
+    if (xn) b += t[xg + 6];
+    if (yn) b += t[yg + 6 + (2u << xg)];
+    if (xn) b += (xg ? egk1_bits((int)ax - 2) * 32768u : 0u) + 32768u;
+    if (yn) b += (yg ? egk1_bits((int)ay - 2) * 32768u : 0u) + 32768u;
+    return b;
+}
+
+__constant__ int c_hme_mult[6][6] = {   // HME_LEVEL_0_SEARCH_AREA_MULTIPLIER_X/_Y, EbDefinitions.h:1322-1340
+    {100, 0, 0, 0, 0, 0}, {100, 100, 0, 0, 0, 0}, {100, 100, 100, 0, 0, 0},
+    {200, 140, 100, 70, 0, 0}, {350, 200, 100, 100, 100, 0}, {525, 350, 200, 100, 100, 100}};
+__constant__ uint8_t c_tab32[16] = {0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 11, 14, 15};   // tab32x32, EbMotionEstimation.c:101
+__constant__ uint8_t c_tab8[64] = {0, 1, 4, 5, 16, 17, 20, 21, 2, 3, 6, 7, 18, 19, 22, 23, 8, 9, 12, 13, 24, 25, 28, 29,
+                                   10, 11, 14, 15, 26, 27, 30, 31, 32, 33, 36, 37, 48, 49, 52, 53, 34, 35, 38, 39, 50, 51, 54, 55,
+                                   40, 41, 44, 45, 56, 57, 60, 61, 42, 43, 46, 47, 58, 59, 62, 63};    // tab8x8, :102
+
+// geometry of PU n (n-order of pLcuBestSad: 64x64, 32x32 raster, 16x16 z-order, 8x8 four per 16x16)
+__device__ __forceinline__ void pu_geom(int n, int &px, int &py, int &sz)
+{
+    if (n == 0) { px = 0; py = 0; sz = 64; return; }
+    if (n < 5) { px = ((n - 1) & 1) * 32; py = ((n - 1) >> 1) * 32; sz = 32; return; }
+    int z, q = 0;
+    if (n < 21) { z = n - 5; sz = 16; } else { z = (n - 21) >> 2; q = (n - 21) & 3; sz = 8; }
+    const int Q = z >> 2, s = z & 3;
+    const int X = (Q & 1) * 2 + (s & 1), Y = (Q >> 1) * 2 + (s >> 1);
+    px = X * 16 + (q & 1) * 8;
+    py = Y * 16 + (q >> 1) * 8;
+}
+
+// ---- 85-PU full-pel search (FullPelSearch_LCU, EbMotionEstimation.c:586) ---------------------------------
+// s_src: 64x64 source (pitch 64).  Window (saw+63) x (sah+63) staged in s_win (pitch wp, misalignment a).
+// s_bsad/s_bmv: running best (n-order), updated with the reference's scan-order semantics:
+//   positions with x < (saw & ~7) follow the 8-position path (u16 16x16 partials, 64x64 uses '<='),
+//   the remainder follows the single-position path (strict '<' everywhere).
+__device__ void fullpel_search(const uint8_t *s_src, const uint8_t *s_win, int wp, int a, int sox, int soy,
+                               int saw, int sah, uint16_t *s_sad8 /*[CHUNK][64]*/, uint32_t *s_sum /*[CHUNK][21]*/,
+                               uint32_t *s_bsad, uint32_t *s_bmv)
+{
+    const int P = saw * sah, w8 = saw & ~7;
+    const uint32_t *src32 = (const uint32_t *)s_src;
+    for (int c0 = 0; c0 < P; c0 += CHUNK) {
+        const int cn = min(CHUNK, P - c0);
+        // (1) 8x8 SADs on rows 0,2,4,6 (Subsad8x8, C_DEFAULT/EbComputeSAD_C.c:214)
+        for (int i = threadIdx.x; i < cn * 64; i += NT) {
+            const int pc = i >> 6, b = i & 63, bx = b & 7, by = b >> 3;
+            const int p = c0 + pc, y = p / saw, x = p - y * saw;
+            const int col = a + x + bx * 8, wi = col >> 2, sh = (col & 3) * 8;
+            uint32_t sad = 0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const uint32_t *row = (const uint32_t *)(s_win + (y + by * 8 + 2 * r) * wp) + wi;
+                const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];
+                const uint32_t *s = src32 + (by * 8 + 2 * r) * 16 + bx * 2;
+                sad += __vsadu4(__funnelshift_r(w0, w1, sh), s[0]);
+                sad += __vsadu4(__funnelshift_r(w1, w2, sh), s[1]);
+            }
+            s_sad8[pc * 64 + b] = (uint16_t)sad;
+        }
+        __syncthreads();
+        // (2) 16x16 partial sums in n-order
+        for (int i = threadIdx.x; i < cn * 16; i += NT) {
+            const int pc = i >> 4, z = i & 15, Q = z >> 2, s = z & 3;
+            const int X = (Q & 1) * 2 + (s & 1), Y = (Q >> 1) * 2 + (s >> 1);
+            const uint16_t *q = s_sad8 + pc * 64 + (Y * 2) * 8 + X * 2;
+            uint32_t t = (uint32_t)q[0] + q[1] + q[8] + q[9];
+            const int p = c0 + pc, x = p % saw;
+            if (x < w8) t = (uint16_t)t;     // EB_U16 sad16x16, C_DEFAULT/EbComputeSAD_C.c:259,337
+            s_sum[pc * 21 + 5 + z] = t;
+        }
+        __syncthreads();
+        // (3) 32x32 and 64x64
+        for (int i = threadIdx.x; i < cn * 4; i += NT) {
+            const int pc = i >> 2, k = i & 3;
+            const uint32_t *q = s_sum + pc * 21 + 5 + 4 * k;
+            s_sum[pc * 21 + 1 + k] = q[0] + q[1] + q[2] + q[3];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < cn; i += NT) {
+            const uint32_t *q = s_sum + i * 21 + 1;
+            s_sum[i * 21] = q[0] + q[1] + q[2] + q[3];
+        }
+        __syncthreads();
+        // (4) replay the best-update scan in order, one thread per PU
+        if (threadIdx.x < 85) {
+            const int n = threadIdx.x;
+            uint32_t bs = s_bsad[n], bm = s_bmv[n];
+            int b8 = 0;
+            if (n >= 21) {
+                int px, py, sz;
+                pu_geom(n, px, py, sz);
+                b8 = (py >> 3) * 8 + (px >> 3);
+            }
+            for (int pc = 0; pc < cn; ++pc) {
+                const int p = c0 + pc, y = p / saw, x = p - y * saw;
+                const uint32_t v = 2u * (n >= 21 ? (uint32_t)s_sad8[pc * 64 + b8] : s_sum[pc * 21 + n]);
+                const bool take = (n == 0 && x < w8) ? (v <= bs) : (v < bs);
+                if (take) {
+                    bs = v;
+                    bm = ((uint32_t)(uint16_t)((y + soy) * 4) << 16) | (uint16_t)((x + sox) * 4);
+                }
+            }
+            s_bsad[n] = bs;
+            s_bmv[n] = bm;
+        }
+        __syncthreads();
+    }
+}
+
+struct HmeRes { uint32_t sad; int x, y; };   // sad already doubled may exceed 24 bits -> keep 32
+
+// ============================================================================================
+// Picture kernel: one CTA per LCU
+// ============================================================================================
+__global__ void __launch_bounds__(NT) me_picture_kernel(const __grid_constant__ MeArgs A)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *s_src = smem;                                   // 64*64
+    uint8_t *s_q = s_src + 4096;                             // quarter-res block 32x32 (pitch 64 like the reference's stride*2 view)
+    uint8_t *s_s16 = s_q + 2048;                             // sixteenth-res block, every other row, pitch 16
+    uint16_t *s_sad8 = (uint16_t *)(s_s16 + 128);            // [CHUNK][64]
+    uint32_t *s_sum = (uint32_t *)(s_sad8 + CHUNK * 64);     // [CHUNK][21]
+    uint32_t *s_bsad = s_sum + CHUNK * 21;                   // [2][85]
+    uint32_t *s_bmv = s_bsad + 170;                          // [2][85]
+    uint32_t *s_bi = s_bmv + 170;                            // [85]
+    uint32_t *s_red32 = s_bi + 85 + 1;                       // [8*6]
+    unsigned long long *s_red64 = (unsigned long long *)(s_red32 + 48);   // [8]
+    uint8_t *s_win = (uint8_t *)(s_red64 + 8);
+
+    const svtb200_me_config &cfg = A.cfg;
+    const int lcu = blockIdx.x, lx = lcu % A.cols, ly = lcu / A.cols;
+    const int ox = lx * 64, oy = ly * 64;
+    const int W = cfg.pic_width, H = cfg.pic_height;
+    const int lw = min(64, W - ox), lh = min(64, H - oy);
+    const int nl = cfg.num_lists;
+    const int mult = c_hme_mult[cfg.hierarchical_levels][cfg.temporal_layer];
+    const PlaneD &sF = A.src[0];
+
+    // stage the source blocks (full 64x64 always: the 85-PU search reads the padded picture beyond lw/lh)
+    for (int i = threadIdx.x; i < 64 * 16; i += NT) {
+        const int r = i >> 4, j = i & 15;
+        ((uint32_t *)s_src)[i] = ld_u32_unaligned(pat(sF, ox + 4 * j, oy + r));
+    }
+    for (int i = threadIdx.x; i < 170; i += NT) { s_bsad[i] = 0; s_bmv[i] = 0; }
+    if (threadIdx.x < 86) s_bi[threadIdx.x] = 0;
+    if (cfg.enable_hme_l1) {
+        for (int i = threadIdx.x; i < 32 * 32; i += NT) {
+            const int r = i >> 5, c = i & 31;
+            s_q[r * 32 + c] = (r < (lh >> 1) && c < (lw >> 1)) ? *pat(A.src[1], (ox >> 1) + c, (oy >> 1) + r) : 0;
+        }
+    }
+    if (cfg.enable_hme_l0 && threadIdx.x < 128) {
+        const int r = threadIdx.x >> 4, c = threadIdx.x & 15;
+        s_s16[threadIdx.x] = (2 * r < (lh >> 2) && c < (lw >> 2)) ? *pat(A.src[2], (ox >> 2) + c, (oy >> 2) + 2 * r) : 0;
+    }
+    __syncthreads();
+
+    int sa_w[2] = {0, 0};
+    for (int li = 0; li < nl; ++li) {
+        const PlaneD &rF = A.ref[li][0], &rQ = A.ref[li][1], &rS = A.ref[li][2];
+        int cx = 0, cy = 0;
+        if (cfg.temporal_layer > 0 || li == 0) {
+            if (cfg.update_hme_search_center) {
+                // TestSearchAreaBounds, EbMotionEstimation.c:3363-3665: zero, A, B, C, [direct], D; SAD at the clamped
+                // vector, unclamped vector returned; ties resolve zero,A,B,C,direct,D.
+                const int tw = cfg.hme_l0_total_w, th = cfg.hme_l0_total_h;
+                int cxv[6] = {0, -tw, tw, 0, 0, 0}, cyv[6] = {0, 0, 0, -th, 0, th};
+                if (li == 1) {
+                    cxv[4] = 0 - (s16(s_bmv[0] & 0xffff) >> 2);
+                    cyv[4] = 0 - (s16(s_bmv[0] >> 16) >> 2);
+                }
+                int dx[6], dy[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    dx[k] = k ? clamp_center(ox, cxv[k], 63, rF.w) : 0;
+                    dy[k] = k ? clamp_center(oy, cyv[k], 63, rF.h) : 0;
+                }
+                uint32_t sad[6];
+                lcu_sads<6>(s_src, rF, ox, oy, lw, lh, dx, dy, 6, s_red32, sad);
+                int best = 0;
+#pragma unroll
+                for (int k = 1; k < 6; ++k) {
+                    if (k == 4 && li == 0) continue;
+                    if (sad[k] < sad[best]) best = k;
+                }
+                cx = cxv[best];
+                cy = cyv[best];
+            }
+            if (cfg.enable_hme && lh == 64) {
+                HmeRes l0[2][2], l1[2][2], l2[2][2];
+                const int nw = min((int)cfg.n_hme_regions_w, 2), nh = min((int)cfg.n_hme_regions_h, 2);
+                const int sh0 = cfg.update_hme_search_center ? 2 : 0, sh1 = cfg.update_hme_search_center ? 1 : 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    HmeRes &a0 = l0[q & 1][q >> 1], &a1 = l1[q & 1][q >> 1], &a2 = l2[q & 1][q >> 1];
+                    a0.sad = a1.sad = a2.sad = 0;
+                    a0.x = s16(cx >> sh0); a0.y = s16(cy >> sh0);
+                    a1.x = s16(cx >> sh1); a1.y = s16(cy >> sh1);
+                    a2.x = s16(cx); a2.y = s16(cy);
+                }
+                if (cfg.enable_hme_l0) {
+                    const bool one = cfg.one_quadrant_hme && !cfg.enable_hme_l1 && !cfg.enable_hme_l2;
+                    const int o4x = ox >> 2, o4y = oy >> 2;
+                    for (int qy = 0; qy < (one ? 1 : nh); ++qy)
+                        for (int qx = 0; qx < (one ? 1 : nw); ++qx) {
+                            int saw, sah, sox, soy;
+                            if (one) {   // EbHevcHmeOneQuadrantLevel0 :1847
+                                saw = (cfg.hme_l0_total_w * mult) / 100;
+                                sah = (cfg.hme_l0_total_h * mult) / 100;
+                                sox = -(saw >> 1) + (cx >> 2);
+                                soy = -(sah >> 1) + (cy >> 2);
+                            } else {     // EbHevcHmeLevel0 :2012
+                                saw = (cfg.hme_l0_w[qx] * mult) / 100;
+                                sah = (cfg.hme_l0_h[qy] * mult) / 100;
+                                int ddx = cx >> 2, ddy = cy >> 2;
+                                for (int k = 0; k < qx; ++k) ddx += (cfg.hme_l0_w[k] * mult) / 100;
+                                for (int k = 0; k < qy; ++k) ddy += (cfg.hme_l0_h[k] * mult) / 100;
+                                sox = -(((cfg.hme_l0_total_w * mult) / 100) >> 1) + ddx;
+                                soy = -(((cfg.hme_l0_total_h * mult) / 100) >> 1) + ddy;
+                            }
+                            sox = s16(sox); soy = s16(soy);
+                            clamp_window(o4x, rS.ox - 1, rS.w, sox, saw);
+                            clamp_window(o4y, rS.oy - 1, rS.h, soy, sah);
+                            if (one && (saw & 15)) saw = (saw >> 4) << 4;   // :1933-1936
+                            const int bw = lw >> 2, bh = (lh >> 2) >> 1;
+                            HmeRes &o = l0[qx][qy];
+                            uint32_t bs = 0xffffffu;
+                            int bx = o.x, by = o.y;
+                            if (saw > 0 && sah > 0) {
+                                const int wbytes = saw + bw - 1, wrows = sah + (bh - 1) * 2, wp = win_pitch(wbytes);
+                                __syncthreads();
+                                const int a = load_window(s_win, wp, pat(rS, o4x + sox, o4y + soy), rS.stride, wbytes, wrows);
+                                __syncthreads();
+                                sad_search(s_s16, 16, bw, bh, s_win, wp, a, 2, saw, sah, s_red64, bs, bx, by);
+                            }
+                            o.sad = bs * 2;
+                            o.x = s16(s16(bx + sox) * 4);
+                            o.y = s16(s16(by + soy) * 4);
+                        }
+                }
+                if (cfg.enable_hme_l1) {
+                    const int o2x = ox >> 1, o2y = oy >> 1;
+                    for (int qy = 0; qy < nh; ++qy)
+                        for (int qx = 0; qx < nw; ++qx) {   // EbHevcHmeLevel1 :2194
+                            const int w1 = cfg.hme_l1_w[qx];
+                            int saw = w1 < 8 ? 8 : (w1 & 7) ? w1 + (w1 - ((w1 >> 3) << 3)) : w1, sah = cfg.hme_l1_h[qy];
+                            int sox = s16(-(saw >> 1) + (l0[qx][qy].x >> 1)), soy = s16(-(sah >> 1) + (l0[qx][qy].y >> 1));
+                            clamp_window(o2x, rQ.ox - 1, rQ.w, sox, saw);
+                            clamp_window(o2y, rQ.oy - 1, rQ.h, soy, sah);
+                            const int bw = lw >> 1, bh = (lh >> 1) >> 1;
+                            HmeRes &o = l1[qx][qy];
+                            uint32_t bs = 0xffffffu;
+                            int bx = o.x, by = o.y;
+                            if (saw > 0 && sah > 0) {
+                                const int wbytes = saw + bw - 1, wrows = sah + (bh - 1) * 2, wp = win_pitch(wbytes);
+                                __syncthreads();
+                                const int a = load_window(s_win, wp, pat(rQ, o2x + sox, o2y + soy), rQ.stride, wbytes, wrows);
+                                __syncthreads();
+                                // the reference passes quarterLcuBufferStride*2 = 64 as block pitch: rows 0,2,4,.. of the 32-pitch block
+                                sad_search(s_q, 64, bw, bh, s_win, wp, a, 2, saw, sah, s_red64, bs, bx, by);
+                            }
+                            o.sad = bs * 2;
+                            o.x = s16(s16(bx + sox) * 2);
+                            o.y = s16(s16(by + soy) * 2);
+                        }
+                }
+                if (cfg.enable_hme_l2) {
+                    for (int qy = 0; qy < nh; ++qy)
+                        for (int qx = 0; qx < nw; ++qx) {   // EbHevcHmeLevel2 :2315
+                            const int w2 = cfg.hme_l2_w[qx];
+                            int saw = w2 < 8 ? 8 : (w2 & 7) ? w2 + (w2 - ((w2 >> 3) << 3)) : w2, sah = cfg.hme_l2_h[qy];
+                            int sox = s16(-(saw >> 1) + l1[qx][qy].x), soy = s16(-(sah >> 1) + l1[qx][qy].y);
+                            clamp_window(ox, 63, rF.w, sox, saw);
+                            clamp_window(oy, 63, rF.h, soy, sah);
+                            const int bw = lw, bh = lh >> 1;
+                            HmeRes &o = l2[qx][qy];
+                            uint32_t bs = 0xffffffu;
+                            int bx = o.x, by = o.y;
+                            if (saw > 0 && sah > 0) {
+                                const int wbytes = saw + bw - 1, wrows = sah + (bh - 1) * 2, wp = win_pitch(wbytes);
+                                __syncthreads();
+                                const int a = load_window(s_win, wp, pat(rF, ox + sox, oy + soy), rF.stride, wbytes, wrows);
+                                __syncthreads();
+                                sad_search(s_src, 128, bw, bh, s_win, wp, a, 2, saw, sah, s_red64, bs, bx, by);
+                            }
+                            o.sad = bs * 2;
+                            o.x = s16(bx + sox);
+                            o.y = s16(by + soy);
+                        }
+                }
+                // best region of the last enabled level; first minimum in width-fastest order (:3959-4030)
+                HmeRes(*lvl)[2] = cfg.enable_hme_l2 ? l2 : cfg.enable_hme_l1 ? l1 : l0;
+                if (cfg.enable_hme_l0 || cfg.enable_hme_l1 || cfg.enable_hme_l2) {
+                    uint32_t bsd = lvl[0][0].sad;
+                    int hx = lvl[0][0].x, hy = lvl[0][0].y;
+                    const bool onlyone = (!cfg.enable_hme_l1 && !cfg.enable_hme_l2) && cfg.one_quadrant_hme;
+                    if (!onlyone)
+                        for (int qy = 0; qy < nh; ++qy)
+                            for (int qx = (qy == 0 ? 1 : 0); qx < nw; ++qx)
+                                if (lvl[qx][qy].sad < bsd) { bsd = lvl[qx][qy].sad; hx = lvl[qx][qy].x; hy = lvl[qx][qy].y; }
+                    if (cfg.enable_hme_l2 && cfg.ref_poc[0] == cfg.ref_poc[1] && li == 1 && nw * nh > 1) {
+                        // same-POC second list: second-best region after the reference's selection sort, whose
+                        // [q / nw][q % nw] indexing is kept as is (:4032-4060)
+                        const int nq = nw * nh;
+                        for (int p = 0; p < nq - 1; ++p)
+                            for (int q = p + 1; q < nq; ++q)
+                                if (l2[p / nw][p % nw].sad > l2[q / nw][q % nw].sad) {
+                                    HmeRes t = l2[p / nw][p % nw]; l2[p / nw][p % nw] = l2[q / nw][q % nw]; l2[q / nw][q % nw] = t;
+                                }
+                        hx = l2[0][1].x; hy = l2[0][1].y;
+                    }
+                    cx = hx; cy = hy;
+                } else { cx = 0; cy = 0; }
+            }
+        }
+        int saw = min((int)cfg.search_area_w, 127), sah = min((int)cfg.search_area_h, 127);
+        if (cx != 0 || cy != 0) {   // EbHevcCheckZeroZeroCenter :2946
+            if (cfg.update_hme_search_center) { cx = clamp_center(ox, cx, 63, rF.w); cy = clamp_center(oy, cy, 63, rF.h); }
+            const int dx[2] = {0, cx}, dy[2] = {0, cy};
+            uint32_t sad[2];
+            lcu_sads<2>(s_src, rF, ox, oy, lw, lh, dx, dy, 2, s_red32, sad);
+            const uint32_t rate = mvd_bits(s16(cx) << 2, s16(cy) << 2, cfg.mvd_bits);
+            const unsigned long long zc = (unsigned long long)sad[0] << 8;
+            const unsigned long long hc = ((unsigned long long)sad[1] << 8) + (((unsigned long long)cfg.lambda * rate + (1u << 22)) >> 23);
+            if (zc <= hc) { cx = 0; cy = 0; }
+        }
+        int sox = s16(cx - (saw >> 1)), soy = s16(cy - (sah >> 1));
+        clamp_window(ox, 63, W, sox, saw);
+        clamp_window(oy, 63, H, soy, sah);
+        sa_w[li] = saw;
+        // full-pel 85-PU search
+        {
+            const int wbytes = saw + 63, wrows = sah + 63, wp = win_pitch(wbytes);
+            __syncthreads();
+            for (int i = threadIdx.x; i < 85; i += NT) s_bsad[li * 85 + i] = MAX_SAD_INIT;
+            const int a = load_window(s_win, wp, pat(rF, ox + sox, oy + soy), rF.stride, wbytes, wrows);
+            __syncthreads();
+            fullpel_search(s_src, s_win, wp, a, sox, soy, saw, sah, s_sad8, s_sum, s_bsad + li * 85, s_bmv + li * 85);
+        }
+    }
+    (void)sa_w;
+    __syncthreads();
+
+    // integer-pel bi-prediction SAD (EbHevcBiPredictionCompensation :2742 -> EbHevcBiPredAverging :2600, SUB_SAD_SEARCH):
+    // SAD(src, avg(ref0 @mv0, ref1 @mv1)) on every other row, doubled.  One warp per PU.
+    if (nl == 2) {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        const int npu = cfg.cu16x16_mode ? 5 : (cfg.cu8x8_mode ? 21 : 85);
+        for (int n = wid; n < npu; n += NT / 32) {
+            int px, py, sz;
+            pu_geom(n, px, py, sz);
+            const int x0 = s16(s_bmv[n] & 0xffff) >> 2, y0 = s16(s_bmv[n] >> 16) >> 2;
+            const int x1 = s16(s_bmv[85 + n] & 0xffff) >> 2, y1 = s16(s_bmv[85 + n] >> 16) >> 2;
+            const int nw = sz >> 2, items = (sz >> 1) * nw;
+            uint32_t acc = 0;
+            for (int i = lane; i < items; i += 32) {
+                const int r = i / nw, j = i - r * nw;
+                const uint32_t s = ((const uint32_t *)s_src)[(py + 2 * r) * 16 + (px >> 2) + j];
+                const uint32_t p0 = ld_u32_unaligned(pat(A.ref[0][0], ox + px + x0 + 4 * j, oy + py + y0 + 2 * r));
+                const uint32_t p1 = ld_u32_unaligned(pat(A.ref[1][0], ox + px + x1 + 4 * j, oy + py + y1 + 2 * r));
+                acc += __vsadu4(s, __vavgu4(p0, p1));
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) s_bi[n] = acc << 1;
+        }
+    }
+    __syncthreads();
+
+    // MeCuResults assembly, EbMotionEstimation.c:4321-4438
+    if (threadIdx.x < 85) {
+        const int pu = threadIdx.x;
+        const int n = pu > 20 ? c_tab8[pu - 21] + 21 : pu > 4 ? c_tab32[pu - 5] + 5 : pu;
+        int total = nl;
+        if (nl == 2 && (cfg.cu8x8_mode == 0 || pu < 21) && (cfg.cu16x16_mode == 0 || pu < 5)) total = 3;
+        const uint32_t a = s_bsad[n], b = s_bsad[85 + n], c = s_bi[n];
+        uint32_t d[3] = {0, 0, 0};
+        uint8_t dir[3] = {0, 0, 0};
+        if (total == 3) {   // Sort3Elements :2919
+            if (a <= b && a <= c) { d[0] = a; dir[0] = 0; if (b <= c) { d[1] = b; dir[1] = 1; d[2] = c; dir[2] = 2; } else { d[1] = c; dir[1] = 2; d[2] = b; dir[2] = 1; } }
+            else if (b <= a && b <= c) { d[0] = b; dir[0] = 1; if (a <= c) { d[1] = a; dir[1] = 0; d[2] = c; dir[2] = 2; } else { d[1] = c; dir[1] = 2; d[2] = a; dir[2] = 0; } }
+            else if (a <= b) { d[0] = c; dir[0] = 2; d[1] = a; dir[1] = 0; d[2] = b; dir[2] = 1; }
+            else { d[0] = c; dir[0] = 2; d[1] = b; dir[1] = 1; d[2] = a; dir[2] = 0; }
+        } else if (total == 2) {
+            if (a <= b) { d[0] = a; dir[0] = 0; d[1] = b; dir[1] = 1; } else { d[0] = b; dir[0] = 1; d[1] = a; dir[1] = 0; }
+        } else { d[0] = a; dir[0] = 0; }
+        svtb200_me_pu_result r;
+        r.x_mv_l0 = (int16_t)(s_bmv[n] & 0xffff); r.y_mv_l0 = (int16_t)(s_bmv[n] >> 16);
+        r.x_mv_l1 = (int16_t)(s_bmv[85 + n] & 0xffff); r.y_mv_l1 = (int16_t)(s_bmv[85 + n] >> 16);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { r.distortion[k] = d[k]; r.direction[k] = dir[k]; }
+        r.total_me_candidates = (uint8_t)total;
+        A.results[(size_t)lcu * 85 + pu] = r;
+        s_sum[pu] = d[0];
+    }
+    if (A.best_sad || A.best_mv)
+        for (int i = threadIdx.x; i < 170; i += NT) {
+            if (A.best_sad) A.best_sad[(size_t)lcu * 170 + i] = s_bsad[i];
+            if (A.best_mv) A.best_mv[(size_t)lcu * 170 + i] = s_bmv[i];
+        }
+    if (A.rc) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+            if (cfg.rate_control_mode) for (int i = 0; i < 16; ++i) t += s_sum[5 + i];
+            A.rc[lcu] = t;
+        }
+    }
+}
+
+static size_t me_fixed_smem()
+{
+    return 4096 + 2048 + 128 + CHUNK * 64 * 2 + CHUNK * 21 * 4 + 170 * 4 * 2 + 86 * 4 + 48 * 4 + 8 * 8;
+}
+
+// worst-case window bytes over every search this configuration can issue
+static int me_window_bytes(const svtb200_me_config &c)
+{
+    static const int mult_tab[6][6] = {{100}, {100, 100}, {100, 100, 100}, {200, 140, 100, 70}, {350, 200, 100, 100, 100}, {525, 350, 200, 100, 100, 100}};
+    const int mult = mult_tab[c.hierarchical_levels][c.temporal_layer];
+    int best = 0;
+    auto upd = [&](int saw, int sah, int bw, int bh_rows_span) {
+        const int wb = saw + bw - 1, rows = sah + bh_rows_span;
+        const int wp = ((wb + 6) & ~3) + 4;
+        if (wp * rows > best) best = wp * rows;
+    };
+    if (c.enable_hme && c.enable_hme_l0) {
+        int w = (c.hme_l0_total_w * mult) / 100, h = (c.hme_l0_total_h * mult) / 100;
+        for (int q = 0; q < 2; ++q) { w = std::max(w, (c.hme_l0_w[q] * mult) / 100); h = std::max(h, (c.hme_l0_h[q] * mult) / 100); }
+        upd(w, h, 16, 14);
+    }
+    auto rnd8 = [](int w) { return w < 8 ? 8 : (w & 7) ? w + (w - ((w >> 3) << 3)) : w; };
+    if (c.enable_hme && c.enable_hme_l1) upd(rnd8(std::max(c.hme_l1_w[0], c.hme_l1_w[1])), std::max(c.hme_l1_h[0], c.hme_l1_h[1]), 32, 30);
+    if (c.enable_hme && c.enable_hme_l2) upd(rnd8(std::max(c.hme_l2_w[0], c.hme_l2_w[1])), std::max(c.hme_l2_h[0], c.hme_l2_h[1]), 64, 62);
+    upd(std::min<int>(c.search_area_w, 127), std::min<int>(c.search_area_h, 127), 64, 63);
+    return (best + 15) & ~15;
+}
+
+static int validate_cfg(const svtb200_me_config *c)
+{
+    if (!c || c->pic_width < 8 || c->pic_height < 8) { set_error("me: bad picture size"); return SVTB200_ERR_BAD_ARG; }
+    if (c->num_lists < 1 || c->num_lists > 2 || c->hierarchical_levels > 5 || c->temporal_layer > c->hierarchical_levels) { set_error("me: bad list/layer configuration"); return SVTB200_ERR_BAD_ARG; }
+    if (c->fractional_search_model != 2) { set_error("me: sub-pel refinement (fractional_search_model != 2) not built yet"); return SVTB200_ERR_UNSUPPORTED; }
+    if (c->n_hme_regions_w > 2 || c->n_hme_regions_h > 2 || c->search_area_w == 0 || c->search_area_h == 0) { set_error("me: bad search configuration"); return SVTB200_ERR_BAD_ARG; }
+    return SVTB200_OK;
+}
+
+static PlaneD to_dev_plane(const svtb200_plane &p, const uint8_t *dbuf)
+{
+    PlaneD d = {dbuf, (int)p.stride, p.origin_x, p.origin_y, p.width, p.height};
+    return d;
+}
+
+static int launch_me(const svtb200_me_config *cfg, const PlaneD src[3], const PlaneD ref[2][3], svtb200_me_pu_result *results,
+                     uint32_t *bs, uint32_t *bm, uint32_t *rc, cudaStream_t st)
+{
+    MeArgs A;
+    memset(&A, 0, sizeof A);
+    A.cfg = *cfg;
+    for (int i = 0; i < 3; ++i) { A.src[i] = src[i]; A.ref[0][i] = ref[0][i]; A.ref[1][i] = ref[1][i]; }
+    A.results = results; A.best_sad = bs; A.best_mv = bm; A.rc = rc;
+    A.cols = (cfg->pic_width + 63) / 64; A.rows = (cfg->pic_height + 63) / 64;
+    A.win_bytes = me_window_bytes(*cfg);
+    const size_t smem = me_fixed_smem() + (size_t)A.win_bytes + 64;
+    if (smem > 227 * 1024) { set_error("me: search window needs %zu B of shared memory (> 227 KB)", smem); return SVTB200_ERR_UNSUPPORTED; }
+    static thread_local size_t smem_set = 0;
+    if (smem > smem_set) {
+        SVTB200_CUDA_TRY(cudaFuncSetAttribute(me_picture_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+        smem_set = smem;
+    }
+    me_picture_kernel<<<A.cols * A.rows, NT, smem, st>>>(A);
+    SVTB200_COUNT_LAUNCH();
+    SVTB200_CUDA_TRY(cudaGetLastError());
+    return SVTB200_OK;
+}
+
+static size_t plane_bytes(const svtb200_plane &p) { return (size_t)p.stride * (p.height + 2 * p.origin_y); }
+
+// ---- leaf kernels --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) sad_loop_leaf_kernel(const uint8_t *src, int sstride, const uint8_t *ref, int rstride,
+                                                           int h, int w, int raw, int saw, int sah, int row_step, uint32_t *out /*[3]*/)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    unsigned long long *s_red64 = (unsigned long long *)smem;
+    uint8_t *s_blk = smem + 64;
+    const int bp = (w + 3 + 3) & ~3;
+    uint8_t *s_win = s_blk + ((bp * h + 15) & ~15);
+    for (int i = threadIdx.x; i < bp * h; i += NT) { const int r = i / bp, c = i - r * bp; s_blk[i] = c < w ? src[r * sstride + c] : 0; }
+    const int wbytes = saw + w - 1, wrows = sah + (h - 1) * row_step, wp = win_pitch(wbytes);
+    const int a = load_window(s_win, wp, ref, raw, wbytes, wrows);
+    __syncthreads();
+    uint32_t bs;
+    int bx = (int)out[1], by = (int)out[2];
+    sad_search(s_blk, bp, w, h, s_win, wp, a, row_step, saw, sah, s_red64, bs, bx, by);
+    if (threadIdx.x == 0) { out[0] = bs; out[1] = (uint32_t)bx; out[2] = (uint32_t)by; }
+}
+
+__global__ void __launch_bounds__(NT) sad_nxm_leaf_kernel(const uint8_t *src, int ss, const uint8_t *r1, int r1s, const uint8_t *r2, int r2s,
+                                                          int h, int w, uint32_t *out)
+{
+    __shared__ uint32_t s_red[8];
+    uint32_t acc[1] = {0};
+    for (int i = threadIdx.x; i < h * w; i += NT) {
+        const int r = i / w, c = i - r * w;
+        int p = r1[r * r1s + c];
+        if (r2) p = (p + r2[r * r2s + c] + 1) >> 1;
+        acc[0] += (uint32_t)abs((int)src[r * ss + c] - p);
+    }
+    block_sum<1>(acc, s_red);
+    if (threadIdx.x == 0) *out = acc[0];
+}
+
+__global__ void __launch_bounds__(NT) fullpel_leaf_kernel(const uint8_t *src, int ss, const uint8_t *ref, int rs, int sox, int soy,
+                                                          int saw, int sah, uint32_t *bsad, uint32_t *bmv)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *s_src = smem;
+    uint16_t *s_sad8 = (uint16_t *)(s_src + 4096);
+    uint32_t *s_sum = (uint32_t *)(s_sad8 + CHUNK * 64);
+    uint32_t *s_bsad = s_sum + CHUNK * 21;
+    uint32_t *s_bmv = s_bsad + 85;
+    uint8_t *s_win = (uint8_t *)(s_bmv + 85 + 2);
+    for (int i = threadIdx.x; i < 4096; i += NT) s_src[i] = src[(i >> 6) * ss + (i & 63)];
+    if (threadIdx.x < 85) { s_bsad[threadIdx.x] = bsad[threadIdx.x]; s_bmv[threadIdx.x] = bmv[threadIdx.x]; }
+    const int wbytes = saw + 63, wrows = sah + 63, wp = win_pitch(wbytes);
+    const int a = load_window(s_win, wp, ref, rs, wbytes, wrows);
+    __syncthreads();
+    fullpel_search(s_src, s_win, wp, a, sox, soy, saw, sah, s_sad8, s_sum, s_bsad, s_bmv);
+    if (threadIdx.x < 85) { bsad[threadIdx.x] = s_bsad[threadIdx.x]; bmv[threadIdx.x] = s_bmv[threadIdx.x]; }
+}
+
+}  // namespace svtb200
+
+using namespace svtb200;
+
+extern "C" {
+
+int svtb200_me_picture_dev(const svtb200_me_config *cfg, const svtb200_pa_picture *src, const svtb200_pa_picture *ref_l0,
+                           const svtb200_pa_picture *ref_l1, svtb200_me_pu_result *results, uint32_t *lcu_best_sad,
+                           uint32_t *lcu_best_mv, uint32_t *rc_me_distortion, void *cuda_stream)
+{
+    int rc = validate_cfg(cfg);
+    if (rc) return rc;
+    if (!src || !ref_l0 || !results || (cfg->num_lists == 2 && !ref_l1)) { set_error("me: null picture/result pointer"); return SVTB200_ERR_BAD_ARG; }
+    if ((rc = ensure_device())) return rc;
+    const svtb200_pa_picture *r1 = ref_l1 ? ref_l1 : ref_l0;
+    PlaneD s[3] = {to_dev_plane(src->full, src->full.buf), to_dev_plane(src->quarter, src->quarter.buf), to_dev_plane(src->sixteenth, src->sixteenth.buf)};
+    PlaneD r[2][3] = {{to_dev_plane(ref_l0->full, ref_l0->full.buf), to_dev_plane(ref_l0->quarter, ref_l0->quarter.buf), to_dev_plane(ref_l0->sixteenth, ref_l0->sixteenth.buf)},
+                      {to_dev_plane(r1->full, r1->full.buf), to_dev_plane(r1->quarter, r1->quarter.buf), to_dev_plane(r1->sixteenth, r1->sixteenth.buf)}};
+    return launch_me(cfg, s, r, results, lcu_best_sad, lcu_best_mv, rc_me_distortion, (cudaStream_t)cuda_stream);
+}
+
+int svtb200_me_picture(const svtb200_me_config *cfg, const svtb200_pa_picture *src, const svtb200_pa_picture *ref_l0,
+                       const svtb200_pa_picture *ref_l1, svtb200_me_pu_result *results, uint32_t *lcu_best_sad,
+                       uint32_t *lcu_best_mv, uint32_t *rc_me_distortion)
+{
+    int rc = validate_cfg(cfg);
+    if (rc) return rc;
+    if (!src || !ref_l0 || !results || (cfg->num_lists == 2 && !ref_l1)) { set_error("me: null picture/result pointer"); return SVTB200_ERR_BAD_ARG; }
+    ThreadCtx *c = tls_ctx();
+    if ((rc = c->init())) return rc;
+    c->reset();
+    const int nl = cfg->num_lists;
+    const svtb200_pa_picture *pics[3] = {src, ref_l0, nl == 2 ? ref_l1 : nullptr};
+    const bool same_ref = nl == 2 && ref_l1->full.buf == ref_l0->full.buf && ref_l1->quarter.buf == ref_l0->quarter.buf && ref_l1->sixteenth.buf == ref_l0->sixteenth.buf;
+    const size_t n_lcu = (size_t)((cfg->pic_width + 63) / 64) * ((cfg->pic_height + 63) / 64);
+    size_t need = 0;
+    for (int p = 0; p < 3; ++p) {
+        if (!pics[p] || (p == 2 && same_ref)) continue;
+        need += align_up(plane_bytes(pics[p]->full), 256) + align_up(plane_bytes(pics[p]->quarter), 256) + align_up(plane_bytes(pics[p]->sixteenth), 256);
+    }
+    const size_t res_bytes = n_lcu * 85 * sizeof(svtb200_me_pu_result), arr_bytes = n_lcu * 170 * 4, rc_bytes = n_lcu * 4;
+    need += align_up(res_bytes, 256) + 2 * align_up(arr_bytes, 256) + align_up(rc_bytes, 256) + 1024;
+    if ((rc = c->dev_reserve(need))) return rc;
+    PlaneD dp[3][3];
+    for (int p = 0; p < 3; ++p) {
+        if (!pics[p]) continue;
+        if (p == 2 && same_ref) { for (int k = 0; k < 3; ++k) dp[2][k] = dp[1][k]; continue; }
+        const svtb200_plane *pl[3] = {&pics[p]->full, &pics[p]->quarter, &pics[p]->sixteenth};
+        for (int k = 0; k < 3; ++k) {
+            const bool used = k == 0 || (k == 1 && cfg->enable_hme && cfg->enable_hme_l1) || (k == 2 && cfg->enable_hme && cfg->enable_hme_l0);
+            void *d = nullptr;
+            if (used) {
+                if (!pl[k]->buf) { set_error("me: plane %d of picture %d is null", k, p); return SVTB200_ERR_BAD_ARG; }
+                if ((rc = c->dev_alloc(plane_bytes(*pl[k]), &d))) return rc;
+                SVTB200_CUDA_TRY(cudaMemcpyAsync(d, pl[k]->buf, plane_bytes(*pl[k]), cudaMemcpyHostToDevice, c->stream));
+            }
+            dp[p][k] = to_dev_plane(*pl[k], (const uint8_t *)d);
+        }
+    }
+    if (nl == 1) for (int k = 0; k < 3; ++k) dp[2][k] = dp[1][k];
+    void *d_res, *d_bs, *d_bm, *d_rc;
+    if ((rc = c->dev_alloc(res_bytes, &d_res)) || (rc = c->dev_alloc(arr_bytes, &d_bs)) || (rc = c->dev_alloc(arr_bytes, &d_bm)) || (rc = c->dev_alloc(rc_bytes, &d_rc))) return rc;
+    PlaneD refs[2][3];
+    for (int k = 0; k < 3; ++k) { refs[0][k] = dp[1][k]; refs[1][k] = dp[2][k]; }
+    if ((rc = launch_me(cfg, dp[0], refs, (svtb200_me_pu_result *)d_res, lcu_best_sad ? (uint32_t *)d_bs : nullptr,
+                        lcu_best_mv ? (uint32_t *)d_bm : nullptr, rc_me_distortion ? (uint32_t *)d_rc : nullptr, c->stream))) return rc;
+    SVTB200_CUDA_TRY(cudaMemcpyAsync(results, d_res, res_bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (lcu_best_sad) SVTB200_CUDA_TRY(cudaMemcpyAsync(lcu_best_sad, d_bs, arr_bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (lcu_best_mv) SVTB200_CUDA_TRY(cudaMemcpyAsync(lcu_best_mv, d_bm, arr_bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (rc_me_distortion) SVTB200_CUDA_TRY(cudaMemcpyAsync(rc_me_distortion, d_rc, rc_bytes, cudaMemcpyDeviceToHost, c->stream));
+    SVTB200_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SVTB200_OK;
+}
+
+int svtb200_SadLoopKernel(const uint8_t *src, uint32_t srcStride, const uint8_t *ref, uint32_t refStride, uint32_t height, uint32_t width,
+                          uint64_t *bestSad, int16_t *xSearchCenter, int16_t *ySearchCenter, uint32_t srcStrideRaw,
+                          int16_t searchAreaWidth, int16_t searchAreaHeight)
+{
+    if (!src || !ref || !bestSad || !xSearchCenter || !ySearchCenter || width == 0 || height == 0 || width > 64 || height > 64) { set_error("SadLoopKernel: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    if (srcStrideRaw == 0 || refStride % srcStrideRaw) { set_error("SadLoopKernel: refStride must be a multiple of srcStrideRaw"); return SVTB200_ERR_UNSUPPORTED; }
+    ThreadCtx *c = tls_ctx();
+    int rc;
+    if ((rc = c->init())) return rc;
+    c->reset();
+    const int saw = searchAreaWidth > 0 ? searchAreaWidth : 0, sah = searchAreaHeight > 0 ? searchAreaHeight : 0;
+    if (saw == 0 || sah == 0) { *bestSad = 0xffffff; return SVTB200_OK; }
+    const int row_step = (int)(refStride / srcStrideRaw);
+    const size_t src_bytes = (size_t)(height - 1) * srcStride + width;
+    const int wrows = sah + (int)(height - 1) * row_step;
+    const size_t ref_bytes = (size_t)(wrows - 1) * srcStrideRaw + saw + width - 1;
+    const int wp = win_pitch(saw + (int)width - 1), bp = ((int)width + 6) & ~3;
+    const size_t smem = 64 + (((size_t)bp * height + 15) & ~15) + (size_t)wp * wrows + 16;
+    if (smem > 227 * 1024) { set_error("SadLoopKernel: window of %zu B exceeds shared memory", smem); return SVTB200_ERR_UNSUPPORTED; }
+    void *d_src, *d_ref, *d_out, *h_out;
+    // keep the reference region's byte alignment so that the window loader's word path is exercised as in the picture kernel
+    const size_t mis = (uintptr_t)ref & 3;
+    if ((rc = c->dev_reserve(src_bytes + ref_bytes + 4096)) || (rc = c->dev_alloc(src_bytes, &d_src)) || (rc = c->dev_alloc(ref_bytes + 8, &d_ref)) ||
+        (rc = c->dev_alloc(16, &d_out)) || (rc = c->pin_alloc(16, &h_out))) return rc;
+    uint32_t *ho = (uint32_t *)h_out;
+    ho[0] = 0; ho[1] = (uint32_t)(int)*xSearchCenter; ho[2] = (uint32_t)(int)*ySearchCenter;
+    SVTB200_CUDA_TRY(cudaMemcpyAsync(d_src, src, src_bytes, cudaMemcpyHostToDevice, c->stream));
+    SVTB200_CUDA_TRY(cudaMemcpyAsync((uint8_t *)d_ref + mis, ref, ref_bytes, cudaMemcpyHostToDevice, c->stream));
+    SVTB200_CUDA_TRY(cudaMemcpyAsync(d_out, ho, 12, cudaMemcpyHostToDevice, c->stream));
+    static thread_local size_t smem_set = 48 * 1024;
+    if (smem > smem_set) { SVTB200_CUDA_TRY(cudaFuncSetAttribute(sad_loop_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
+    sad_loop_leaf_kernel<<<1, NT, smem, c->stream>>>((const uint8_t *)d_src, (int)srcStride, (const uint8_t *)d_ref + mis, (int)refStride, (int)height,
+                                                      (int)width, (int)srcStrideRaw, saw, sah, row_step, (uint32_t *)d_out);
+    SVTB200_COUNT_LAUNCH();
+    SVTB200_CUDA_TRY(cudaGetLastError());
+    SVTB200_CUDA_TRY(cudaMemcpyAsync(ho, d_out, 12, cudaMemcpyDeviceToHost, c->stream));
+    SVTB200_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *bestSad = ho[0];
+    *xSearchCenter = (int16_t)(int)ho[1];
+    *ySearchCenter = (int16_t)(int)ho[2];
+    return SVTB200_OK;
+}
+
+static int sad_leaf(const uint8_t *src, uint32_t ss, const uint8_t *r1, uint32_t r1s, const uint8_t *r2, uint32_t r2s, uint32_t h, uint32_t w, uint32_t *sad)
+{
+    if (!src || !r1 || !sad || h == 0 || w == 0) { set_error("sad: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    ThreadCtx *c = tls_ctx();
+    int rc;
+    if ((rc = c->init())) return rc;
+    c->reset();
+    const size_t sb = (size_t)(h - 1) * ss + w, b1 = (size_t)(h - 1) * r1s + w, b2 = r2 ? (size_t)(h - 1) * r2s + w : 0;
+    void *d_s, *d_1, *d_2 = nullptr, *d_o, *h_o;
+    if ((rc = c->dev_reserve(sb + b1 + b2 + 4096)) || (rc = c->dev_alloc(sb, &d_s)) || (rc = c->dev_alloc(b1, &d_1)) || (rc = c->dev_alloc(b2 + 4, &d_2)) ||
+        (rc = c->dev_alloc(4, &d_o)) || (rc = c->pin_alloc(4, &h_o))) return rc;
+    SVTB200_CUDA_TRY(cudaMemcpyAsync(d_s, src, sb, cudaMemcpyHostToDevice, c->stream));
+    SVTB200_CUDA_TRY(cudaMemcpyAsync(d_1, r1, b1, cudaMemcpyHostToDevice, c->stream));
+    if (r2) SVTB200_CUDA_TRY(cudaMemcpyAsync(d_2, r2, b2, cudaMemcpyHostToDevice, c->stream));
+    sad_nxm_leaf_kernel<<<1, NT, 0, c->stream>>>((const uint8_t *)d_s, (int)ss, (const uint8_t *)d_1, (int)r1s, r2 ? (const uint8_t *)d_2 : nullptr, (int)r2s, (int)h, (int)w, (uint32_t *)d_o);
+    SVTB200_COUNT_LAUNCH();
+    SVTB200_CUDA_TRY(cudaGetLastError());
+    SVTB200_CUDA_TRY(cudaMemcpyAsync(h_o, d_o, 4, cudaMemcpyDeviceToHost, c->stream));
+    SVTB200_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *sad = *(uint32_t *)h_o;
+    return SVTB200_OK;
+}
+
+int svtb200_NxMSadKernel(const uint8_t *src, uint32_t srcStride, const uint8_t *ref, uint32_t refStride, uint32_t height, uint32_t width, uint32_t *sad)
+{
+    return sad_leaf(src, srcStride, ref, refStride, nullptr, 0, height, width, sad);
+}
+
+int svtb200_CombinedAveragingSAD(const uint8_t *src, uint32_t srcStride, const uint8_t *ref1, uint32_t ref1Stride, const uint8_t *ref2,
+                                 uint32_t ref2Stride, uint32_t height, uint32_t width, uint32_t *sad)
+{
+    if (!ref2) { set_error("CombinedAveragingSAD: ref2 is null"); return SVTB200_ERR_BAD_ARG; }
+    return sad_leaf(src, srcStride, ref1, ref1Stride, ref2, ref2Stride, height, width, sad);
+}
+
+int svtb200_FullPelSearch_LCU(const uint8_t *src, uint32_t srcStride, const uint8_t *ref, uint32_t refStride, int16_t xSearchAreaOrigin,
+                              int16_t ySearchAreaOrigin, uint32_t searchAreaWidth, uint32_t searchAreaHeight, uint32_t best_sad[SVTB200_ME_PU_COUNT],
+                              uint32_t best_mv[SVTB200_ME_PU_COUNT])
+{
+    if (!src || !ref || !best_sad || !best_mv || searchAreaWidth == 0 || searchAreaHeight == 0 || searchAreaWidth > 127 || searchAreaHeight > 127) { set_error("FullPelSearch_LCU: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    ThreadCtx *c = tls_ctx();
+    int rc;
+    if ((rc = c->init())) return rc;
+    c->reset();
+    const int saw = (int)searchAreaWidth, sah = (int)searchAreaHeight;
+    const size_t sb = (size_t)63 * srcStride + 64, rb = (size_t)(sah + 62) * refStride + saw + 63;
+    const size_t mis = (uintptr_t)ref & 3;
+    void *d_s, *d_r, *d_bs, *d_bm, *h_b;
+    if ((rc = c->dev_reserve(sb + rb + 8192)) || (rc = c->dev_alloc(sb, &d_s)) || (rc = c->dev_alloc(rb + 8, &d_r)) || (rc = c->dev_alloc(85 * 4, &d_bs)) ||
+        (rc = c->dev_alloc(85 * 4, &d_bm)) || (rc = c->pin_alloc(170 * 4, &h_b))) return rc;
+    uint32_t *hb = (uint32_t *)h_b;
+    memcpy(hb, best_sad, 85 * 4); memcpy(hb + 85, best_mv, 85 * 4);
+    SVTB200_CUDA_TRY(cudaMemcpyAsync(d_s, src, sb, cudaMemcpyHostToDevice, c->stream));
+    SVTB200_CUDA_TRY(cudaMemcpyAsync((uint8_t *)d_r + mis, ref, rb, cudaMemcpyHostToDevice, c->stream));
+    SVTB200_CUDA_TRY(cudaMemcpyAsync(d_bs, hb, 85 * 4, cudaMemcpyHostToDevice, c->stream));
+    SVTB200_CUDA_TRY(cudaMemcpyAsync(d_bm, hb + 85, 85 * 4, cudaMemcpyHostToDevice, c->stream));
+    const size_t smem = 4096 + CHUNK * 64 * 2 + CHUNK * 21 * 4 + 172 * 4 + (size_t)win_pitch(saw + 63) * (sah + 63) + 16;
+    static thread_local size_t smem_set = 48 * 1024;
+    if (smem > smem_set) { SVTB200_CUDA_TRY(cudaFuncSetAttribute(fullpel_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
+    fullpel_leaf_kernel<<<1, NT, smem, c->stream>>>((const uint8_t *)d_s, (int)srcStride, (const uint8_t *)d_r + mis, (int)refStride, (int)xSearchAreaOrigin,
+                                                     (int)ySearchAreaOrigin, saw, sah, (uint32_t *)d_bs, (uint32_t *)d_bm);
+    SVTB200_COUNT_LAUNCH();
+    SVTB200_CUDA_TRY(cudaGetLastError());
+    SVTB200_CUDA_TRY(cudaMemcpyAsync(hb, d_bs, 85 * 4, cudaMemcpyDeviceToHost, c->stream));
+    SVTB200_CUDA_TRY(cudaMemcpyAsync(hb + 85, d_bm, 85 * 4, cudaMemcpyDeviceToHost, c->stream));
+    SVTB200_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(best_sad, hb, 85 * 4); memcpy(best_mv, hb + 85, 85 * 4);
+    return SVTB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,203 @@
+"""ctypes binding of libsvthevc_b200.so (include/svt_hevc_b200.h) + host-side mirrors of the
+reference's per-picture parameter derivation for the hot path.
+
+This module is the product's host side for Python callers (tests, bench.py).  It never imports
+anything from oracle/ and raises if the CUDA library is missing: there is no CPU fallback.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsvthevc_b200.so")
+
+ME_PU_COUNT = 85
+
+
+class Plane(C.Structure):
+    """svtb200_plane == luma view of EbPictureBufferDesc_t (EbPictureBufferDesc.h:26-70)."""
+    _fields_ = [("buf", C.c_void_p), ("stride", C.c_uint32), ("origin_x", C.c_uint16),
+                ("origin_y", C.c_uint16), ("width", C.c_uint16), ("height", C.c_uint16)]
+
+
+class PaPicture(C.Structure):
+    _fields_ = [("full", Plane), ("quarter", Plane), ("sixteenth", Plane)]
+
+
+class MeConfig(C.Structure):
+    _fields_ = [("pic_width", C.c_uint16), ("pic_height", C.c_uint16),
+                ("num_lists", C.c_uint8), ("temporal_layer", C.c_uint8), ("hierarchical_levels", C.c_uint8),
+                ("enable_hme", C.c_uint8), ("enable_hme_l0", C.c_uint8), ("enable_hme_l1", C.c_uint8),
+                ("enable_hme_l2", C.c_uint8), ("one_quadrant_hme", C.c_uint8),
+                ("update_hme_search_center", C.c_uint8),
+                ("n_hme_regions_w", C.c_uint8), ("n_hme_regions_h", C.c_uint8),
+                ("hme_l0_total_w", C.c_uint16), ("hme_l0_total_h", C.c_uint16),
+                ("hme_l0_w", C.c_uint16 * 2), ("hme_l0_h", C.c_uint16 * 2),
+                ("hme_l1_w", C.c_uint16 * 2), ("hme_l1_h", C.c_uint16 * 2),
+                ("hme_l2_w", C.c_uint16 * 2), ("hme_l2_h", C.c_uint16 * 2),
+                ("search_area_w", C.c_uint8), ("search_area_h", C.c_uint8),
+                ("fractional_search_model", C.c_uint8),
+                ("cu8x8_mode", C.c_uint8), ("cu16x16_mode", C.c_uint8), ("rate_control_mode", C.c_uint8),
+                ("lambda_", C.c_uint32), ("mvd_bits", C.c_uint32 * 12), ("ref_poc", C.c_uint64 * 2)]
+
+
+ME_PU_RESULT_DTYPE = np.dtype([("x_mv_l0", "<i2"), ("y_mv_l0", "<i2"), ("x_mv_l1", "<i2"), ("y_mv_l1", "<i2"),
+                               ("distortion", "<u4", 3), ("direction", "u1", 3), ("total_me_candidates", "u1")])
+assert ME_PU_RESULT_DTYPE.itemsize == 24
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; fail loudly if it is absent (no CPU fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(the B200 path has no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.svtb200_version.restype = C.c_char_p
+        _lib.svtb200_last_error.restype = C.c_char_p
+        _lib.svtb200_launch_count.restype = C.c_uint64
+    return _lib
+
+
+class Svtb200Error(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise Svtb200Error(f"svtb200 error {rc}: {lib().svtb200_last_error().decode()}")
+
+
+def _u8p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ------------------------------------------------------------------------------------------------
+# picture helpers (host side of PictureAnalysis: pad + point-decimate, EbPictureAnalysisProcess.c:173,4139)
+# ------------------------------------------------------------------------------------------------
+class HostPaPicture:
+    """Padded full / quarter / sixteenth luma planes in host memory with the reference's geometry:
+    full-resolution pad 68 (EbEncHandle.c:901-903), 1/4 pad 32 (:912-914), 1/16 pad 16 (:923-925)."""
+
+    def __init__(self, luma, pads=(68, 32, 16)):
+        luma = np.ascontiguousarray(luma, dtype=np.uint8)
+        self.height, self.width = luma.shape
+        self.planes = []
+        for step, pad in zip((1, 2, 4), pads):
+            dec = luma[::step, ::step]
+            self.planes.append((np.ascontiguousarray(np.pad(dec, pad, mode="edge")), pad, dec.shape[1], dec.shape[0]))
+        self.struct = PaPicture()
+        for name, (arr, pad, w, h) in zip(("full", "quarter", "sixteenth"), self.planes):
+            p = getattr(self.struct, name)
+            p.buf = arr.ctypes.data
+            p.stride = arr.shape[1]
+            p.origin_x = pad
+            p.origin_y = pad
+            p.width = w
+            p.height = h
+
+
+# ------------------------------------------------------------------------------------------------
+# preset -> ME parameters.  Mirror of SetMeHmeParamsOq / SignalDerivationMeKernelOq
+# (EbMotionEstimationProcess.c:53-124, :308-423) + the tables in EbDefinitions.h:1666-1806 for the
+# resolution classes / presets BASELINE.json names (4K and 1080p, M7 and M10).
+# ------------------------------------------------------------------------------------------------
+_ME_TABLE = {
+    # (res_class, enc_mode): (l0_total_w, l0_total_h, l0_w, l0_h, en_l1, l1_w, l1_h, en_l2, l2_w, l2_h, sa_w, sa_h)
+    ("4k", 10): (64, 32, 32, 16, 0, 0, 0, 0, 0, 0, 8, 7),
+    ("4k", 7): (64, 32, 32, 16, 1, 4, 4, 0, 0, 0, 16, 9),
+    ("1080p", 10): (48, 40, 24, 20, 1, 4, 4, 0, 0, 0, 8, 7),
+    ("1080p", 7): (64, 48, 32, 24, 1, 4, 4, 1, 4, 2, 16, 9),
+}
+# plausible CABAC bit-fraction estimates (1 bit = 32768) standing in for mdRateEstimationArray->mvdBits;
+# the same numbers are handed to the reference harness, the port and the CUDA path.
+DEFAULT_MVD_BITS = (24000, 43000, 26000, 40000, 21000, 47000, 30000, 36000, 33000, 33000, 29000, 38000)
+# lambdaModeDecisionRaSad{Base,RefNonBase,NonRef}[qp] are data tables of the encoder's rate control; tests only need a
+# the qp-32 entries
+DEFAULT_LAMBDA = {"base": 439162, "ref": 717148, "nonref": 824850}  # EbLambdaRateTables.h:249,280 at qp 32
+
+
+def me_config(width, height, enc_mode=10, temporal_layer=0, num_lists=1, hierarchical_levels=3,
+              frame_rate=60, lambda_=None, mvd_bits=DEFAULT_MVD_BITS, ref_poc=(0, 16), rate_control_mode=0):
+    res = "4k" if width * height > 1920 * 1088 else "1080p"
+    t = _ME_TABLE[(res, enc_mode)]
+    c = MeConfig()
+    c.pic_width, c.pic_height = width, height
+    c.num_lists, c.temporal_layer, c.hierarchical_levels = num_lists, temporal_layer, hierarchical_levels
+    c.enable_hme, c.enable_hme_l0, c.enable_hme_l1, c.enable_hme_l2 = 1, 1, t[4], t[7]
+    c.one_quadrant_hme = 1 if (enc_mode >= 8 and res == "4k") else 0
+    c.update_hme_search_center = 1
+    c.n_hme_regions_w = c.n_hme_regions_h = 2
+    l0tw, l0th, l0w, l0h = t[0], t[1], t[2], t[3]
+    if res == "4k" and frame_rate <= 30:   # low frame-rate bump, EbMotionEstimationProcess.c:98-117
+        if enc_mode in (6, 7):
+            l0tw, l0th, l0w, l0h = max(96, l0tw), max(64, l0th), max(48, l0w), max(32, l0h)
+        elif enc_mode >= 8:
+            l0tw, l0th, l0w, l0h = max(64, l0tw), max(48, l0th), max(32, l0w), max(24, l0h)
+    c.hme_l0_total_w, c.hme_l0_total_h = l0tw, l0th
+    for i in range(2):
+        c.hme_l0_w[i], c.hme_l0_h[i] = l0w, l0h
+        c.hme_l1_w[i], c.hme_l1_h[i] = t[5], t[6]
+        c.hme_l2_w[i], c.hme_l2_h[i] = t[8], t[9]
+    c.search_area_w, c.search_area_h = t[10], t[11]
+    c.fractional_search_model = 2        # integer-pel (useSubpelFlag == 0 pictures; sub-pel: later round)
+    c.cu8x8_mode, c.cu16x16_mode = 1, 0  # CU_8x8_MODE_1 at M>=? (EbPictureDecisionProcess.c:447-449)
+    c.rate_control_mode = rate_control_mode
+    c.lambda_ = lambda_ if lambda_ is not None else DEFAULT_LAMBDA["base" if temporal_layer == 0 else "ref"]
+    for i, v in enumerate(mvd_bits):
+        c.mvd_bits[i] = v
+    c.ref_poc[0], c.ref_poc[1] = ref_poc
+    return c
+
+
+# ------------------------------------------------------------------------------------------------
+# entry points
+# ------------------------------------------------------------------------------------------------
+def device_count():
+    return lib().svtb200_device_count()
+
+
+def me_picture(cfg, src, ref0, ref1=None, want_raw=False, want_rc=False):
+    """Host-buffer picture ME (copies in, one kernel, copies out). src/ref*: HostPaPicture."""
+    n_lcu = ((cfg.pic_width + 63) // 64) * ((cfg.pic_height + 63) // 64)
+    res = np.zeros((n_lcu, ME_PU_COUNT), dtype=ME_PU_RESULT_DTYPE)
+    bs = np.zeros((n_lcu, 2, 85), dtype=np.uint32) if want_raw else None
+    bm = np.zeros((n_lcu, 2, 85), dtype=np.uint32) if want_raw else None
+    rc = np.zeros(n_lcu, dtype=np.uint32) if want_rc else None
+    check(lib().svtb200_me_picture(C.byref(cfg), C.byref(src.struct), C.byref(ref0.struct),
+                                   C.byref(ref1.struct) if ref1 is not None else None,
+                                   _u8p(res), _u8p(bs) if want_raw else None, _u8p(bm) if want_raw else None,
+                                   _u8p(rc) if want_rc else None))
+    return res, bs, bm, rc
+
+
+def sad_loop_kernel(src, src_stride, ref, ref_off, ref_stride, height, width, raw_stride, saw, sah, x0=0, y0=0):
+    best = C.c_uint64(0)
+    xs, ys = C.c_int16(x0), C.c_int16(y0)
+    check(lib().svtb200_SadLoopKernel(_u8p(src), C.c_uint32(src_stride), C.c_void_p(ref.ctypes.data + ref_off),
+                                      C.c_uint32(ref_stride), C.c_uint32(height), C.c_uint32(width),
+                                      C.byref(best), C.byref(xs), C.byref(ys), C.c_uint32(raw_stride),
+                                      C.c_int16(saw), C.c_int16(sah)))
+    return best.value, xs.value, ys.value
+
+
+def nxm_sad(src, ss, ref, rs, h, w):
+    out = C.c_uint32(0)
+    check(lib().svtb200_NxMSadKernel(_u8p(src), C.c_uint32(ss), _u8p(ref), C.c_uint32(rs), C.c_uint32(h), C.c_uint32(w), C.byref(out)))
+    return out.value
+
+
+def combined_averaging_sad(src, ss, r1, r1s, r2, r2s, h, w):
+    out = C.c_uint32(0)
+    check(lib().svtb200_CombinedAveragingSAD(_u8p(src), C.c_uint32(ss), _u8p(r1), C.c_uint32(r1s), _u8p(r2), C.c_uint32(r2s),
+                                             C.c_uint32(h), C.c_uint32(w), C.byref(out)))
+    return out.value
+
+
+def fullpel_search_lcu(src, ss, ref, ref_off, rs, xo, yo, saw, sah, best_sad, best_mv):
+    check(lib().svtb200_FullPelSearch_LCU(_u8p(src), C.c_uint32(ss), C.c_void_p(ref.ctypes.data + ref_off), C.c_uint32(rs),
+                                          C.c_int16(xo), C.c_int16(yo), C.c_uint32(saw), C.c_uint32(sah),
+                                          _u8p(best_sad), _u8p(best_mv)))
