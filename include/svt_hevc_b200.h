@@ -166,6 +166,24 @@ int svtb200_me_picture_dev(const svtb200_me_config *cfg, const svtb200_pa_pictur
                            svtb200_me_pu_result *results, uint32_t *lcu_best_sad, uint32_t *lcu_best_mv,
                            uint32_t *rc_me_distortion, void *cuda_stream);
 
+
+/* ---------------------------------------------------------------------------------------
+ * Device-resident source pictures (the PictureAnalysis feeders).
+ * svtb200_pa_picture_create allocates padded full / quarter / sixteenth luma planes in HBM with the
+ * reference's geometry (pads 68 / 32 / 16: EbEncHandle.c:901-925); svtb200_pa_picture_upload copies an
+ * UNPADDED host luma plane into the full plane and runs, on the device, what PictureAnalysisKernel does
+ * on the host: edge padding (GeneratePadding, EbMcp.c:1017) and point decimation by 2 and 4
+ * (Decimation2D, EbPictureAnalysisProcess.c:173; DecimateInputPicture :4139).  The resulting
+ * svtb200_pa_picture holds DEVICE pointers and is what the *_dev entry points take, so a source frame
+ * crosses PCIe once and is reused as a reference by later pictures without further copies.
+ * ------------------------------------------------------------------------------------- */
+int svtb200_pa_picture_create(uint16_t width, uint16_t height, svtb200_pa_picture *out_dev);
+int svtb200_pa_picture_upload(const svtb200_pa_picture *dev, const uint8_t *host_luma, uint32_t host_stride, void *cuda_stream);
+/* same, source already in device memory (unpadded, pitch dev_stride) */
+int svtb200_pa_picture_build_dev(const svtb200_pa_picture *dev, const uint8_t *dev_luma, uint32_t dev_stride, void *cuda_stream);
+int svtb200_pa_picture_download(const svtb200_pa_picture *dev, const svtb200_pa_picture *host_out);
+void svtb200_pa_picture_destroy(svtb200_pa_picture *dev);
+
 #ifdef __cplusplus
 }
 #endif

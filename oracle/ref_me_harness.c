@@ -41,10 +41,12 @@ static void fill_desc(EbPictureBufferDesc_t *d, const svtb200_plane *p)
 }
 
 /* asm_mode: 0 = C rows (ASM_TYPES = 0), 1 = best SIMD the CPU supports (EbHevcGetCpuAsmType). */
-int svtref_me_picture(const svtb200_me_config *cfg, const svtb200_pa_picture *src,
-                      const svtb200_pa_picture *ref_l0, const svtb200_pa_picture *ref_l1,
-                      svtb200_me_pu_result *results, uint32_t *lcu_best_sad, uint32_t *lcu_best_mv,
-                      uint32_t *rc_me_distortion, int asm_mode)
+/* LCU rows [row_begin, row_end): lets bench.py spread one picture over all host threads the way the reference's
+ * own ME segments do (EbMotionEstimationProcess.c:679-683).  Re-entrant: every call builds its own contexts. */
+int svtref_me_picture_rows(const svtb200_me_config *cfg, const svtb200_pa_picture *src,
+                           const svtb200_pa_picture *ref_l0, const svtb200_pa_picture *ref_l1,
+                           svtb200_me_pu_result *results, uint32_t *lcu_best_sad, uint32_t *lcu_best_mv,
+                           uint32_t *rc_me_distortion, int asm_mode, int row_begin, int row_end)
 {
     ASM_TYPES = asm_mode ? EbHevcGetCpuAsmType() : 0;
 
@@ -126,7 +128,7 @@ int svtref_me_picture(const svtb200_me_config *cfg, const svtb200_pa_picture *sr
     for (int i = 0; i < 12; ++i) me->mvdBitsArray[i] = cfg->mvd_bits[i];
 
     const EbPictureBufferDesc_t *in = &srcDesc[0], *q = &srcDesc[1], *s = &srcDesc[2];
-    for (EB_U32 ly = 0; ly < lcuRows; ++ly) {
+    for (EB_U32 ly = (EB_U32)row_begin; ly < lcuRows && ly < (EB_U32)row_end; ++ly) {
         for (EB_U32 lx = 0; lx < lcuCols; ++lx) {
             const EB_U32 lcuIndex = lx + ly * lcuCols;
             const EB_U32 ox = lx * 64, oy = ly * 64;
@@ -181,4 +183,12 @@ int svtref_me_picture(const svtb200_me_config *cfg, const svtb200_pa_picture *sr
     if (me->dctor) me->dctor(me);
     free(me); free(pcs); free(scs);
     return 0;
+}
+
+int svtref_me_picture(const svtb200_me_config *cfg, const svtb200_pa_picture *src,
+                      const svtb200_pa_picture *ref_l0, const svtb200_pa_picture *ref_l1,
+                      svtb200_me_pu_result *results, uint32_t *lcu_best_sad, uint32_t *lcu_best_mv,
+                      uint32_t *rc_me_distortion, int asm_mode)
+{
+    return svtref_me_picture_rows(cfg, src, ref_l0, ref_l1, results, lcu_best_sad, lcu_best_mv, rc_me_distortion, asm_mode, 0, 1 << 30);
 }

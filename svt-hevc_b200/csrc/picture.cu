@@ -1,0 +1,131 @@
+// picture.cu -- device-resident source pictures: edge padding + point decimation on the GPU.
+// Replaces the host-side feeders of ME: GeneratePadding (Codec/EbMcp.c:1017),
+// Decimation2D (Codec/EbPictureAnalysisProcess.c:173), DecimateInputPicture (:4139).
+#include "common.cuh"
+
+namespace svtb200 {
+
+// out(x,y) over the PADDED extent of a plane whose interior is (w x h) at pad; value = full-res interior sample
+// at (clamp(x - pad) * step, clamp(y - pad) * step): decimation followed by edge replication in one pass.
+__global__ void __launch_bounds__(256) decim_pad_kernel(const uint8_t *full, int fstride, int fpad, uint8_t *out, int ostride,
+                                                        int opad, int w, int h, int step, int skip_interior)
+{
+    const int tw = w + 2 * opad, th = h + 2 * opad;
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+    if (x4 >= tw || y >= th) return;
+    const int sy = min(max(y - opad, 0), h - 1) * step;
+    const uint8_t *srow = full + (size_t)(fpad + sy) * fstride + fpad;
+    const bool row_in = (y >= opad && y < opad + h);
+    uint8_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int x = x4 + k;
+        const int sx = min(max(x - opad, 0), w - 1) * step;
+        v[k] = srow[sx];
+    }
+    uint8_t *o = out + (size_t)y * ostride + x4;
+    if (skip_interior && row_in && x4 >= opad && x4 + 3 < opad + w) return;   // in-place full plane: interior untouched
+    if (x4 + 3 < tw && (((uintptr_t)o) & 3) == 0 && !(skip_interior && row_in)) {
+        *(uint32_t *)o = v[0] | (v[1] << 8) | (v[2] << 16) | ((uint32_t)v[3] << 24);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int x = x4 + k;
+            if (x >= tw) break;
+            if (skip_interior && row_in && x >= opad && x < opad + w) continue;
+            o[k] = v[k];
+        }
+    }
+}
+
+static int build_planes(const svtb200_pa_picture *d, cudaStream_t st)
+{
+    const svtb200_plane *pl[3] = {&d->full, &d->quarter, &d->sixteenth};
+    const int steps[3] = {1, 2, 4};
+    // decimated planes first (they read the full-plane interior only), then the full plane's own border
+    for (int k = 2; k >= 0; --k) {
+        const svtb200_plane &p = *pl[k];
+        if (!p.buf) continue;
+        const int tw = p.width + 2 * p.origin_x, th = p.height + 2 * p.origin_y;
+        dim3 grid((tw / 4 + 255) / 256 + ((tw / 4) % 256 ? 0 : 0) + 1, th);
+        grid.x = ((tw + 3) / 4 + 255) / 256;
+        decim_pad_kernel<<<grid, 256, 0, st>>>(d->full.buf, (int)d->full.stride, d->full.origin_x, p.buf, (int)p.stride, p.origin_x, p.width,
+                                               p.height, steps[k], k == 0);
+        SVTB200_COUNT_LAUNCH();
+    }
+    SVTB200_CUDA_TRY(cudaGetLastError());
+    return SVTB200_OK;
+}
+
+}  // namespace svtb200
+using namespace svtb200;
+
+extern "C" {
+
+int svtb200_pa_picture_create(uint16_t width, uint16_t height, svtb200_pa_picture *out)
+{
+    if (!out || width < 8 || height < 8) { set_error("pa_picture_create: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    int rc = ensure_device();
+    if (rc) return rc;
+    memset(out, 0, sizeof *out);
+    svtb200_plane *pl[3] = {&out->full, &out->quarter, &out->sixteenth};
+    const int pads[3] = {68, 32, 16}, sh[3] = {0, 1, 2};
+    for (int k = 0; k < 3; ++k) {
+        svtb200_plane &p = *pl[k];
+        p.width = (uint16_t)((width + (1 << sh[k]) - 1) >> sh[k]);
+        p.height = (uint16_t)((height + (1 << sh[k]) - 1) >> sh[k]);
+        p.origin_x = p.origin_y = (uint16_t)pads[k];
+        p.stride = (uint32_t)align_up((size_t)p.width + 2 * pads[k], 4);
+        void *d = nullptr;
+        SVTB200_CUDA_TRY(cudaMalloc(&d, (size_t)p.stride * (p.height + 2 * pads[k]) + 64));
+        p.buf = (uint8_t *)d;
+    }
+    return SVTB200_OK;
+}
+
+int svtb200_pa_picture_build_dev(const svtb200_pa_picture *dev, const uint8_t *dev_luma, uint32_t dev_stride, void *cuda_stream)
+{
+    if (!dev || !dev->full.buf || !dev_luma) { set_error("pa_picture_build_dev: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    int rc = ensure_device();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const svtb200_plane &f = dev->full;
+    SVTB200_CUDA_TRY(cudaMemcpy2DAsync(f.buf + (size_t)f.origin_y * f.stride + f.origin_x, f.stride, dev_luma, dev_stride, f.width, f.height,
+                                       cudaMemcpyDeviceToDevice, st));
+    return build_planes(dev, st);
+}
+
+int svtb200_pa_picture_upload(const svtb200_pa_picture *dev, const uint8_t *host_luma, uint32_t host_stride, void *cuda_stream)
+{
+    if (!dev || !dev->full.buf || !host_luma) { set_error("pa_picture_upload: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    int rc = ensure_device();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const svtb200_plane &f = dev->full;
+    SVTB200_CUDA_TRY(cudaMemcpy2DAsync(f.buf + (size_t)f.origin_y * f.stride + f.origin_x, f.stride, host_luma, host_stride, f.width, f.height,
+                                       cudaMemcpyHostToDevice, st));
+    return build_planes(dev, st);
+}
+
+int svtb200_pa_picture_download(const svtb200_pa_picture *dev, const svtb200_pa_picture *host)
+{
+    if (!dev || !host) { set_error("pa_picture_download: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    const svtb200_plane *d[3] = {&dev->full, &dev->quarter, &dev->sixteenth}, *h[3] = {&host->full, &host->quarter, &host->sixteenth};
+    SVTB200_CUDA_TRY(cudaDeviceSynchronize());
+    for (int k = 0; k < 3; ++k) {
+        if (!h[k]->buf || !d[k]->buf) continue;
+        const int tw = d[k]->width + 2 * d[k]->origin_x, th = d[k]->height + 2 * d[k]->origin_y;
+        if (h[k]->width != d[k]->width || h[k]->height != d[k]->height || h[k]->origin_x != d[k]->origin_x) { set_error("pa_picture_download: geometry mismatch"); return SVTB200_ERR_BAD_ARG; }
+        SVTB200_CUDA_TRY(cudaMemcpy2D(h[k]->buf, h[k]->stride, d[k]->buf, d[k]->stride, tw, th, cudaMemcpyDeviceToHost));
+    }
+    return SVTB200_OK;
+}
+
+void svtb200_pa_picture_destroy(svtb200_pa_picture *dev)
+{
+    if (!dev) return;
+    svtb200_plane *pl[3] = {&dev->full, &dev->quarter, &dev->sixteenth};
+    for (int k = 0; k < 3; ++k) if (pl[k]->buf) { cudaFree(pl[k]->buf); pl[k]->buf = nullptr; }
+}
+
+}  // extern "C"

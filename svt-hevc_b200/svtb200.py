@@ -201,3 +201,44 @@ def fullpel_search_lcu(src, ss, ref, ref_off, rs, xo, yo, saw, sah, best_sad, be
     check(lib().svtb200_FullPelSearch_LCU(_u8p(src), C.c_uint32(ss), C.c_void_p(ref.ctypes.data + ref_off), C.c_uint32(rs),
                                           C.c_int16(xo), C.c_int16(yo), C.c_uint32(saw), C.c_uint32(sah),
                                           _u8p(best_sad), _u8p(best_mv)))
+
+
+class DevPaPicture:
+    """Device-resident padded full / quarter / sixteenth luma (svtb200_pa_picture_create / _upload)."""
+
+    def __init__(self, width, height):
+        self.width, self.height = width, height
+        self.struct = PaPicture()
+        check(lib().svtb200_pa_picture_create(C.c_uint16(width), C.c_uint16(height), C.byref(self.struct)))
+
+    def upload(self, luma, stream=0):
+        """luma: contiguous (pinned) host uint8 array HxW, or an integer host address with stride == width."""
+        ptr = luma if isinstance(luma, int) else luma.ctypes.data
+        check(lib().svtb200_pa_picture_upload(C.byref(self.struct), C.c_void_p(ptr), C.c_uint32(self.width), C.c_void_p(stream)))
+
+    def build_from_device(self, dev_ptr, dev_stride, stream=0):
+        check(lib().svtb200_pa_picture_build_dev(C.byref(self.struct), C.c_void_p(dev_ptr), C.c_uint32(dev_stride), C.c_void_p(stream)))
+
+    def download(self):
+        """-> HostPaPicture-shaped numpy planes (for tests)."""
+        host = HostPaPicture(np.zeros((self.height, self.width), np.uint8))
+        check(lib().svtb200_pa_picture_download(C.byref(self.struct), C.byref(host.struct)))
+        return host
+
+    def destroy(self):
+        if self.struct.full.buf:
+            lib().svtb200_pa_picture_destroy(C.byref(self.struct))
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def me_picture_dev(cfg, src, ref0, ref1, results_ptr, stream=0, best_sad_ptr=None, best_mv_ptr=None, rc_ptr=None):
+    """Device-resident picture ME: src/ref*: DevPaPicture; results_ptr: device address of [n_lcu][85] records."""
+    check(lib().svtb200_me_picture_dev(C.byref(cfg), C.byref(src.struct), C.byref(ref0.struct),
+                                       C.byref(ref1.struct) if ref1 is not None else None,
+                                       C.c_void_p(results_ptr), C.c_void_p(best_sad_ptr), C.c_void_p(best_mv_ptr),
+                                       C.c_void_p(rc_ptr), C.c_void_p(stream)))

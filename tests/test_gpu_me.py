@@ -108,3 +108,36 @@ def test_me_picture_4k_m10_full_size(tl, nl):
     else:
         want = common.oracle_me_picture(port, "port_me_picture", cfg, src, r0, r1)
     common.assert_me_equal(got, want, nl, "4K M10 CUDA vs oracle")
+
+
+@pytest.mark.parametrize("wh", [(448, 256), (328, 200), (72, 40)])
+def test_device_picture_build_matches_host_pad_and_decimation(wh):
+    w, h = wh
+    luma = common.SynthVideo(w, h, seed=3).luma(2)
+    host = S.HostPaPicture(luma)
+    dev = S.DevPaPicture(w, h)
+    dev.upload(luma)
+    got = dev.download()
+    for (a, pad, pw, ph), (b, _, _, _) in zip(host.planes, got.planes):
+        assert np.array_equal(a, b[:, :a.shape[1]])
+    dev.destroy()
+
+
+def test_me_picture_dev_resident_matches_host_api():
+    import torch
+    w, h = 448, 256
+    v = common.SynthVideo(w, h, seed=9)
+    lum = [v.luma(n) for n in (4, 0, 8)]
+    hp = [S.HostPaPicture(l) for l in lum]
+    dp = [S.DevPaPicture(w, h) for _ in lum]
+    for d, l in zip(dp, lum):
+        d.upload(l)
+    cfg = S.me_config(3840, 2160, enc_mode=10, temporal_layer=2, num_lists=2)
+    cfg.pic_width, cfg.pic_height = w, h
+    n_lcu = 7 * 4
+    out = torch.zeros(n_lcu * 85 * 24, dtype=torch.uint8, device="cuda")
+    S.me_picture_dev(cfg, dp[0], dp[1], dp[2], out.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().view(S.ME_PU_RESULT_DTYPE).reshape(n_lcu, 85)
+    want = S.me_picture(cfg, hp[0], hp[1], hp[2])[0]
+    assert np.array_equal(got, want)
