@@ -167,6 +167,55 @@ int svtb200_me_picture_dev(const svtb200_me_config *cfg, const svtb200_pa_pictur
                            uint32_t *rc_me_distortion, void *cuda_stream);
 
 
+/* =======================================================================================
+ *  B. Motion-compensated prediction
+ * ===================================================================================== */
+
+/* Three-plane 8-bit 4:2:0 picture: mirror of EbPictureBufferDesc_t (bufferY/Cb/Cr, strideY/Cb/Cr,
+ * originX/originY; the chroma planes carry half the luma padding, EbPictureBufferDesc.c). */
+typedef struct svtb200_yuv_picture {
+    svtb200_plane y, cb, cr;
+} svtb200_yuv_picture;
+
+/* One 2Nx2N prediction unit: the arguments of EncodePassInterPrediction
+ * (Codec/EbInterPrediction.c:761): MvUnit_t {mv[2], predDirection}, puOrigin, puWidth/Height,
+ * plus which reference picture each list points at (index into the refs[] array of the batch). */
+typedef struct svtb200_mc_job {
+    uint16_t x, y;          /* PU origin, luma samples, picture coordinates          */
+    uint8_t  w, h;          /* PU size in luma samples: 8, 16, 32 or 64              */
+    uint8_t  dir;           /* 0 = UNI_PRED_LIST_0, 1 = UNI_PRED_LIST_1, 2 = BI_PRED */
+    uint8_t  ref_idx[2];    /* refs[] index used by list 0 / list 1                  */
+    uint8_t  reserved;
+    int16_t  mv[2][2];      /* [list][x,y], quarter-pel                              */
+} svtb200_mc_job;
+
+/* Batched HEVC inter prediction of luma + both chroma planes for n_jobs PUs into `dst` at each PU's own
+ * position (what EncodePassInterPrediction writes into the prediction picture): position clamp
+ * (EbInterPrediction.c:794-808), 8-tap luma / 4-tap chroma separable interpolation, uni-pred rounding or
+ * bi-pred averaging (EncodeUniPredInterpolation Codec/EbMcp.c:175, EncodeBiPredInterpolation :562,
+ * kernels C_DEFAULT/EbMcp_C.c).  Host variant: refs/dst are host pictures (copied in/out);
+ * _dev variant: device pictures + device job array. */
+int svtb200_mc_batch(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs, int n_jobs,
+                     const svtb200_yuv_picture *dst);
+int svtb200_mc_batch_dev(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs_dev, int n_jobs,
+                         const svtb200_yuv_picture *dst, void *cuda_stream);
+
+/* Leaf entry points with the reference's kernel prototypes.  The reference selects one of 16 (luma) / 64
+ * (chroma) functions by fractional position (uniPredLumaIFFunctionPtrArrayNew[2][16], EbMcpTables.c:28;
+ * uniPredChromaIFFunctionPtrArrayNew[2][64], :195); here the position is an argument.
+ * frac = fracPosx + (fracPosy << 2) for luma; chroma takes fracPosx, fracPosy in 1/8 units.
+ * refPic points at the integer sample of the block's top-left (the kernels read 3 left/above, 4 right/below). */
+int svtb200_LumaInterpolationFilterNew(uint32_t frac, const uint8_t *refPic, uint32_t srcStride, uint8_t *dst,
+                                       uint32_t dstStride, uint32_t puWidth, uint32_t puHeight);
+int svtb200_ChromaInterpolationFilterNew(uint32_t fracPosx, uint32_t fracPosy, const uint8_t *refPic, uint32_t srcStride,
+                                         uint8_t *dst, uint32_t dstStride, uint32_t puWidth, uint32_t puHeight);
+/* bi-pred: raw 14-bit intermediates of both lists (biPred*IFFunctionPtrArrayNew) + BiPredClipping (C_DEFAULT/EbMcp_C.c:21) */
+int svtb200_LumaBiPredInterpolation(uint32_t frac0, const uint8_t *ref0, uint32_t ref0Stride, uint32_t frac1, const uint8_t *ref1,
+                                    uint32_t ref1Stride, uint8_t *dst, uint32_t dstStride, uint32_t puWidth, uint32_t puHeight);
+int svtb200_ChromaBiPredInterpolation(uint32_t frac0x, uint32_t frac0y, const uint8_t *ref0, uint32_t ref0Stride, uint32_t frac1x,
+                                      uint32_t frac1y, const uint8_t *ref1, uint32_t ref1Stride, uint8_t *dst, uint32_t dstStride,
+                                      uint32_t puWidth, uint32_t puHeight);
+
 /* ---------------------------------------------------------------------------------------
  * Device-resident source pictures (the PictureAnalysis feeders).
  * svtb200_pa_picture_create allocates padded full / quarter / sixteenth luma planes in HBM with the

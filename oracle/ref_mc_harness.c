@@ -1,0 +1,84 @@
+/*
+ * oracle/ref_mc_harness.c -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * Path-level oracle for inter prediction: runs the reference's OWN EncodePassInterPrediction
+ * (Source/Lib/Codec/EbInterPrediction.c:761) -- and through it EncodeUniPredInterpolation /
+ * EncodeBiPredInterpolation (Codec/EbMcp.c:175,562) and the table-dispatched interpolation kernels -- for a
+ * list of PUs described with the product's ABI structs.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "EbDefinitions.h"
+#include "EbPictureControlSet.h"
+#include "EbSequenceControlSet.h"
+#include "EbEncodeContext.h"
+#include "EbInterPrediction.h"
+#include "EbMcp.h"
+#include "EbReferenceObject.h"
+#include "EbSystemResourceManager.h"
+#include "EbPictureBufferDesc.h"
+
+#include "svt_hevc_b200.h"
+
+extern EB_U32 EbHevcGetCpuAsmType(void);
+
+static void fill_yuv(EbPictureBufferDesc_t *d, const svtb200_yuv_picture *p)
+{
+    memset(d, 0, sizeof(*d));
+    d->bufferY = p->y.buf; d->bufferCb = p->cb.buf; d->bufferCr = p->cr.buf;
+    d->strideY = (EB_U16)p->y.stride; d->strideCb = (EB_U16)p->cb.stride; d->strideCr = (EB_U16)p->cr.stride;
+    d->originX = p->y.origin_x; d->originY = p->y.origin_y;
+    d->width = p->y.width; d->height = p->y.height;
+    d->maxWidth = p->y.width; d->maxHeight = p->y.height;
+    d->bitDepth = EB_8BIT;
+    d->colorFormat = EB_YUV420;
+}
+
+static void on_error(EB_PTR handle, EB_U32 code)
+{
+    (void)handle;
+    fprintf(stderr, "ref_mc_harness: reference raised error 0x%x\n", code);
+    abort();
+}
+
+int svtref_mc_batch(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs, int n_jobs,
+                    const svtb200_yuv_picture *dst, int asm_mode)
+{
+    ASM_TYPES = asm_mode ? EbHevcGetCpuAsmType() : 0;
+    EbPictureBufferDesc_t *refDesc = (EbPictureBufferDesc_t *)calloc((size_t)n_refs, sizeof(*refDesc)), dstDesc;
+    EbReferenceObject_t *refObj = (EbReferenceObject_t *)calloc((size_t)n_refs, sizeof(*refObj));
+    EbObjectWrapper_t *refWrap = (EbObjectWrapper_t *)calloc((size_t)n_refs, sizeof(*refWrap));
+    for (int i = 0; i < n_refs; ++i) {
+        fill_yuv(&refDesc[i], &refs[i]);
+        refObj[i].referencePicture = &refDesc[i];
+        refWrap[i].objectPtr = &refObj[i];
+    }
+    fill_yuv(&dstDesc, dst);
+
+    EbCallback_t cb; memset(&cb, 0, sizeof cb); cb.ErrorHandler = on_error;
+    EncodeContext_t *ec = (EncodeContext_t *)calloc(1, sizeof(*ec));
+    ec->appCallbackPtr = &cb;
+    SequenceControlSet_t *scs = (SequenceControlSet_t *)calloc(1, sizeof(*scs));
+    scs->encodeContextPtr = ec;
+    EbObjectWrapper_t scsWrap; memset(&scsWrap, 0, sizeof scsWrap); scsWrap.objectPtr = scs;
+    PictureControlSet_t *pcs = (PictureControlSet_t *)calloc(1, sizeof(*pcs));
+    pcs->sequenceControlSetWrapperPtr = &scsWrap;
+
+    MotionCompensationPredictionContext_t *mcp = (MotionCompensationPredictionContext_t *)calloc(1, sizeof(*mcp));
+    if (MotionCompensationPredictionContextCtor(mcp, 64, 64, EB_FALSE) != EB_ErrorNone) return -1;
+
+    for (int j = 0; j < n_jobs; ++j) {
+        const svtb200_mc_job *q = &jobs[j];
+        MvUnit_t mvu; memset(&mvu, 0, sizeof mvu);
+        mvu.predDirection = q->dir;
+        for (int l = 0; l < 2; ++l) { mvu.mv[l].x = q->mv[l][0]; mvu.mv[l].y = q->mv[l][1]; }
+        pcs->refPicPtrArray[0] = &refWrap[q->ref_idx[0]];
+        pcs->refPicPtrArray[1] = &refWrap[q->ref_idx[1]];
+        EncodePassInterPrediction(&mvu, q->x, q->y, q->w, q->h, pcs, &dstDesc, mcp);
+    }
+    if (mcp->dctor) mcp->dctor(mcp);
+    free(mcp); free(pcs); free(scs); free(ec); free(refWrap); free(refObj); free(refDesc);
+    return 0;
+}

@@ -76,33 +76,8 @@ __device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v
     return t;
 }
 
-// ---- window staging ------------------------------------------------------------------------
-// Copies `rows` rows of `wbytes` bytes starting at global address g (row pitch gstride) into shared memory
-// with row pitch wp (multiple of 4, >= wbytes + 8).  Word-granular and coalesced when the plane pitch is a
-// multiple of 4: the global byte misalignment `a` (0..3) is preserved, i.e. window byte x lives at column a + x.
-__device__ __forceinline__ int load_window(uint8_t *s_win, int wp, const uint8_t *g, int gstride, int wbytes, int rows)
-{
-    if ((gstride & 3) == 0) {
-        const int a = (int)((uintptr_t)g & 3);
-        const uint32_t *gw = (const uint32_t *)(g - a);
-        const int nW = (a + wbytes + 3) >> 2, gs4 = gstride >> 2, wp4 = wp >> 2;
-        uint32_t *sw = (uint32_t *)s_win;
-        for (int i = threadIdx.x; i < rows * nW; i += NT) {
-            const int r = i / nW, c = i - r * nW;
-            sw[r * wp4 + c] = __ldg(gw + (ptrdiff_t)r * gs4 + c);
-        }
-        return a;
-    }
-    for (int i = threadIdx.x; i < rows * wbytes; i += NT) {
-        const int r = i / wbytes, c = i - r * wbytes;
-        s_win[r * wp + c] = __ldg(g + (ptrdiff_t)r * gstride + c);
-    }
-    return 0;
-}
-__device__ __host__ __forceinline__ int win_pitch(int wbytes) { return ((wbytes + 3 + 3) & ~3) + 4; }
-
 // ---- exhaustive block search (semantics of SadLoopKernel, C_DEFAULT/EbComputeSAD_C.c:165) -----------------
-// s_blk: bw x bh source block in shared memory (pitch bp, multiple of 4); window staged by load_window().
+// s_blk: bw x bh source block in shared memory (pitch bp, multiple of 4); window staged by load_window_t<NT>().
 // Block row r is compared with window row y + r*row_step.  Returns min SAD (start value 0xffffff) and the
 // FIRST raster position attaining it; x/y are left untouched when no position qualifies.
 __device__ void sad_search(const uint8_t *s_blk, int bp, int bw, int bh, const uint8_t *s_win, int wp, int a,
@@ -441,7 +416,7 @@ __global__ void __launch_bounds__(NT) me_picture_kernel(const __grid_constant__ 
                             if (saw > 0 && sah > 0) {
                                 const int wbytes = saw + bw - 1, wrows = sah + (bh - 1) * 2, wp = win_pitch(wbytes);
                                 __syncthreads();
-                                const int a = load_window(s_win, wp, pat(rS, o4x + sox, o4y + soy), rS.stride, wbytes, wrows);
+                                const int a = load_window_t<NT>(s_win, wp, pat(rS, o4x + sox, o4y + soy), rS.stride, wbytes, wrows);
                                 __syncthreads();
                                 sad_search(s_s16, 16, bw, bh, s_win, wp, a, 2, saw, sah, s_red64, bs, bx, by);
                             }
@@ -466,7 +441,7 @@ __global__ void __launch_bounds__(NT) me_picture_kernel(const __grid_constant__ 
                             if (saw > 0 && sah > 0) {
                                 const int wbytes = saw + bw - 1, wrows = sah + (bh - 1) * 2, wp = win_pitch(wbytes);
                                 __syncthreads();
-                                const int a = load_window(s_win, wp, pat(rQ, o2x + sox, o2y + soy), rQ.stride, wbytes, wrows);
+                                const int a = load_window_t<NT>(s_win, wp, pat(rQ, o2x + sox, o2y + soy), rQ.stride, wbytes, wrows);
                                 __syncthreads();
                                 // the reference passes quarterLcuBufferStride*2 = 64 as block pitch: rows 0,2,4,.. of the 32-pitch block
                                 sad_search(s_q, 64, bw, bh, s_win, wp, a, 2, saw, sah, s_red64, bs, bx, by);
@@ -491,7 +466,7 @@ __global__ void __launch_bounds__(NT) me_picture_kernel(const __grid_constant__ 
                             if (saw > 0 && sah > 0) {
                                 const int wbytes = saw + bw - 1, wrows = sah + (bh - 1) * 2, wp = win_pitch(wbytes);
                                 __syncthreads();
-                                const int a = load_window(s_win, wp, pat(rF, ox + sox, oy + soy), rF.stride, wbytes, wrows);
+                                const int a = load_window_t<NT>(s_win, wp, pat(rF, ox + sox, oy + soy), rF.stride, wbytes, wrows);
                                 __syncthreads();
                                 sad_search(s_src, 128, bw, bh, s_win, wp, a, 2, saw, sah, s_red64, bs, bx, by);
                             }
@@ -545,7 +520,7 @@ __global__ void __launch_bounds__(NT) me_picture_kernel(const __grid_constant__ 
             const int wbytes = saw + 63, wrows = sah + 63, wp = win_pitch(wbytes);
             __syncthreads();
             for (int i = threadIdx.x; i < 85; i += NT) s_bsad[li * 85 + i] = MAX_SAD_INIT;
-            const int a = load_window(s_win, wp, pat(rF, ox + sox, oy + soy), rF.stride, wbytes, wrows);
+            const int a = load_window_t<NT>(s_win, wp, pat(rF, ox + sox, oy + soy), rF.stride, wbytes, wrows);
             __syncthreads();
             fullpel_search(s_src, s_win, wp, a, sox, soy, saw, sah, s_sad8, s_sum, s_bsad + li * 85, s_bmv + li * 85);
         }
@@ -698,7 +673,7 @@ __global__ void __launch_bounds__(NT) sad_loop_leaf_kernel(const uint8_t *src, i
     uint8_t *s_win = s_blk + ((bp * h + 15) & ~15);
     for (int i = threadIdx.x; i < bp * h; i += NT) { const int r = i / bp, c = i - r * bp; s_blk[i] = c < w ? src[r * sstride + c] : 0; }
     const int wbytes = saw + w - 1, wrows = sah + (h - 1) * row_step, wp = win_pitch(wbytes);
-    const int a = load_window(s_win, wp, ref, raw, wbytes, wrows);
+    const int a = load_window_t<NT>(s_win, wp, ref, raw, wbytes, wrows);
     __syncthreads();
     uint32_t bs;
     int bx = (int)out[1], by = (int)out[2];
@@ -734,7 +709,7 @@ __global__ void __launch_bounds__(NT) fullpel_leaf_kernel(const uint8_t *src, in
     for (int i = threadIdx.x; i < 4096; i += NT) s_src[i] = src[(i >> 6) * ss + (i & 63)];
     if (threadIdx.x < 85) { s_bsad[threadIdx.x] = bsad[threadIdx.x]; s_bmv[threadIdx.x] = bmv[threadIdx.x]; }
     const int wbytes = saw + 63, wrows = sah + 63, wp = win_pitch(wbytes);
-    const int a = load_window(s_win, wp, ref, rs, wbytes, wrows);
+    const int a = load_window_t<NT>(s_win, wp, ref, rs, wbytes, wrows);
     __syncthreads();
     fullpel_search(s_src, s_win, wp, a, sox, soy, saw, sah, s_sad8, s_sum, s_bsad, s_bmv);
     if (threadIdx.x < 85) { bsad[threadIdx.x] = s_bsad[threadIdx.x]; bmv[threadIdx.x] = s_bmv[threadIdx.x]; }

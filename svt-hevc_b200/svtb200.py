@@ -242,3 +242,85 @@ def me_picture_dev(cfg, src, ref0, ref1, results_ptr, stream=0, best_sad_ptr=Non
                                        C.byref(ref1.struct) if ref1 is not None else None,
                                        C.c_void_p(results_ptr), C.c_void_p(best_sad_ptr), C.c_void_p(best_mv_ptr),
                                        C.c_void_p(rc_ptr), C.c_void_p(stream)))
+
+
+# ================================================================================================
+# B. motion-compensated prediction
+# ================================================================================================
+class YuvPicture(C.Structure):
+    _fields_ = [("y", Plane), ("cb", Plane), ("cr", Plane)]
+
+
+class McJob(C.Structure):
+    _fields_ = [("x", C.c_uint16), ("y", C.c_uint16), ("w", C.c_uint8), ("h", C.c_uint8), ("dir", C.c_uint8),
+                ("ref_idx", C.c_uint8 * 2), ("reserved", C.c_uint8), ("mv", (C.c_int16 * 2) * 2)]
+
+
+MC_JOB_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("w", "u1"), ("h", "u1"), ("dir", "u1"), ("ref_idx", "u1", 2),
+                         ("reserved", "u1"), ("mv", "<i2", (2, 2))])
+assert MC_JOB_DTYPE.itemsize == C.sizeof(McJob) == 18
+
+
+class HostYuvPicture:
+    """8-bit 4:2:0 picture with the reference's recon-reference geometry: luma pad 80 = 64 + MCPXPaddingOffset 16
+    (EbEncHandle.c:867-870), chroma pad 40; edge-replicated like GeneratePadding (EbMcp.c:1017)."""
+
+    def __init__(self, y, cb, cr, pad=80, replicate=True):
+        self.height, self.width = y.shape
+        self.pad = pad
+        mode = "edge" if replicate else "constant"
+        self.y = np.ascontiguousarray(np.pad(np.asarray(y, np.uint8), pad, mode=mode))
+        self.cb = np.ascontiguousarray(np.pad(np.asarray(cb, np.uint8), pad // 2, mode=mode))
+        self.cr = np.ascontiguousarray(np.pad(np.asarray(cr, np.uint8), pad // 2, mode=mode))
+        self.struct = YuvPicture()
+        for name, arr, p, w, h in (("y", self.y, pad, self.width, self.height), ("cb", self.cb, pad // 2, self.width // 2, self.height // 2),
+                                   ("cr", self.cr, pad // 2, self.width // 2, self.height // 2)):
+            pl = getattr(self.struct, name)
+            pl.buf, pl.stride, pl.origin_x, pl.origin_y, pl.width, pl.height = arr.ctypes.data, arr.shape[1], p, p, w, h
+
+    def interior(self):
+        p, q = self.pad, self.pad // 2
+        return (self.y[p:p + self.height, p:p + self.width], self.cb[q:q + self.height // 2, q:q + self.width // 2],
+                self.cr[q:q + self.height // 2, q:q + self.width // 2])
+
+
+def yuv_array(pics):
+    arr = (YuvPicture * len(pics))()
+    for i, p in enumerate(pics):
+        arr[i] = p.struct
+    return arr
+
+
+def mc_batch(refs, jobs, dst):
+    """refs: list of HostYuvPicture; jobs: numpy array of MC_JOB_DTYPE; dst: HostYuvPicture (written in place)."""
+    jobs = np.ascontiguousarray(jobs)
+    check(lib().svtb200_mc_batch(yuv_array(refs), C.c_int(len(refs)), _u8p(jobs), C.c_int(len(jobs)), C.byref(dst.struct)))
+
+
+def luma_interp(frac, ref, ref_off, rs, w, h):
+    dst = np.zeros((h, w), np.uint8)
+    check(lib().svtb200_LumaInterpolationFilterNew(C.c_uint32(frac), C.c_void_p(ref.ctypes.data + ref_off), C.c_uint32(rs), _u8p(dst),
+                                                   C.c_uint32(w), C.c_uint32(w), C.c_uint32(h)))
+    return dst
+
+
+def chroma_interp(fx, fy, ref, ref_off, rs, w, h):
+    dst = np.zeros((h, w), np.uint8)
+    check(lib().svtb200_ChromaInterpolationFilterNew(C.c_uint32(fx), C.c_uint32(fy), C.c_void_p(ref.ctypes.data + ref_off), C.c_uint32(rs),
+                                                     _u8p(dst), C.c_uint32(w), C.c_uint32(w), C.c_uint32(h)))
+    return dst
+
+
+def luma_bipred(f0, r0, r0_off, r0s, f1, r1, r1_off, r1s, w, h):
+    dst = np.zeros((h, w), np.uint8)
+    check(lib().svtb200_LumaBiPredInterpolation(C.c_uint32(f0), C.c_void_p(r0.ctypes.data + r0_off), C.c_uint32(r0s), C.c_uint32(f1),
+                                                C.c_void_p(r1.ctypes.data + r1_off), C.c_uint32(r1s), _u8p(dst), C.c_uint32(w), C.c_uint32(w), C.c_uint32(h)))
+    return dst
+
+
+def chroma_bipred(f0x, f0y, r0, r0_off, r0s, f1x, f1y, r1, r1_off, r1s, w, h):
+    dst = np.zeros((h, w), np.uint8)
+    check(lib().svtb200_ChromaBiPredInterpolation(C.c_uint32(f0x), C.c_uint32(f0y), C.c_void_p(r0.ctypes.data + r0_off), C.c_uint32(r0s),
+                                                  C.c_uint32(f1x), C.c_uint32(f1y), C.c_void_p(r1.ctypes.data + r1_off), C.c_uint32(r1s),
+                                                  _u8p(dst), C.c_uint32(w), C.c_uint32(w), C.c_uint32(h)))
+    return dst
