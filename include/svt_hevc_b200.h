@@ -216,6 +216,65 @@ int svtb200_ChromaBiPredInterpolation(uint32_t frac0x, uint32_t frac0y, const ui
                                       uint32_t frac1y, const uint8_t *ref1, uint32_t ref1Stride, uint8_t *dst, uint32_t dstStride,
                                       uint32_t puWidth, uint32_t puHeight);
 
+/* =======================================================================================
+ *  C. Residual -> transform -> quant / dequant -> inverse transform -> reconstruction
+ *     
+ * ===================================================================================== */
+
+#define SVTB200_SHAPE_DEFAULT 0   /* DEFAULT_SHAPE, EbDefinitions.h (EB_TRANS_COEFF_SHAPE) */
+#define SVTB200_SHAPE_N2      1   /* N2_SHAPE: low-frequency N/2 x N/2 quadrant only       */
+#define SVTB200_SHAPE_N4      2   /* N4_SHAPE: low-frequency N/4 x N/4                     */
+#define SVTB200_SHAPE_ONLY_DC 3   /* ONLY_DC_SHAPE                                          */
+
+#define SVTB200_TQ_CLEAN_SPARSE   1u  /* cleanSparseCeoffPfEncDec (EbTransforms.c:3199-3243)              */
+#define SVTB200_TQ_ENABLE_CBF     2u  /* enableCbflag of UpdateQiQCoef (C_DEFAULT/EbTransforms_C.c:209)   */
+#define SVTB200_TQ_CONTOURING     4u  /* enableContouringQCUpdateFlag                                      */
+#define SVTB200_TQ_SKIP_RECON     8u  /* quantise only (MD-style call): do not run the inverse / addition  */
+
+/* One transform unit of one colour plane: what EncodeLoop + EncodeGenerateRecon
+ * (Codec/EbCodingLoop.c:651,1084) do for it on the 8-bit path. */
+typedef struct svtb200_tq_job {
+    uint16_t x, y;          /* TU origin in samples of ITS OWN plane (chroma: already halved)         */
+    uint8_t  plane;         /* 0 = Y, 1 = Cb, 2 = Cr                                                  */
+    uint8_t  size;          /* 4, 8, 16 or 32                                                          */
+    uint8_t  dst4x4;        /* 1: 4x4 DST (intra luma 4x4), EstimateTransform dstTansformFlag          */
+    uint8_t  shape;         /* SVTB200_SHAPE_*                                                         */
+    uint8_t  qp;            /* cu qp (luma) or mapped chroma qp, 0..51                                 */
+    uint8_t  slice_type;    /* 0 = B, 1 = P, 2 = I (EB_B/P/I_PICTURE, EbApi.h:36-38), 3 = IDR          */
+    uint8_t  temporal_layer;
+    uint8_t  flags;         /* SVTB200_TQ_*                                                            */
+    uint32_t dz_offset;     /* dZoffset of UnifiedQuantizeInvQuantize (0 = use the I/P rounding offset) */
+} svtb200_tq_job;
+
+/* Quantised coefficients, picture geometry (no padding): plane p, sample (x,y) at buf[p][y*stride[p] + x].
+ * (The reference keeps them per LCU with pitch 64, EbCodingLoop.c:740; the shim copies rows, INTEGRATION.md.) */
+typedef struct svtb200_coeff_picture {
+    int16_t *buf[3];
+    uint32_t stride[3];
+} svtb200_coeff_picture;
+
+/* Batched encode-pass chain.  For every job: residual = src - pred (PictureResidual), EstimateTransform,
+ * UnifiedQuantizeInvQuantize default path (QuantizeInvQuantize + optional sparse cleaning + UpdateQiQCoef),
+ * PfZeroOutUselessQuadrants, EncodeInvTransform, AdditionKernel.  recon may alias pred (the reference
+ * reconstructs in place).  nz_counts[job] receives countNonZeroCoeffs.  Host and device variants. */
+int svtb200_tq_batch(const svtb200_yuv_picture *src, const svtb200_yuv_picture *pred, const svtb200_yuv_picture *recon,
+                     const svtb200_coeff_picture *coeff, const svtb200_tq_job *jobs, int n_jobs, uint32_t *nz_counts);
+int svtb200_tq_batch_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *pred, const svtb200_yuv_picture *recon,
+                         const svtb200_coeff_picture *coeff, const svtb200_tq_job *jobs_dev, int n_jobs, uint32_t *nz_counts_dev,
+                         void *cuda_stream);
+
+/* Leaf entry points (reference prototypes; host pointers). */
+/* EstimateTransform, Codec/EbTransforms.c:3268 (EB_TRANSFORM_FUNC tables EbTransforms.h:339-472) */
+int svtb200_EstimateTransform(const int16_t *residualBuffer, uint32_t residualStride, int16_t *coeffBuffer, uint32_t coeffStride,
+                              uint32_t transformSize, uint32_t bitIncrement, uint8_t dstTransformFlag, uint8_t transCoeffShape);
+/* EB_QIQ_TYPE (EbTransforms.h:213-225), QuantizeInvQuantize C_DEFAULT/EbTransforms_C.c:89 */
+int svtb200_QuantizeInvQuantize(const int16_t *coeff, uint32_t coeffStride, int16_t *quantCoeff, int16_t *reconCoeff, uint32_t qFunc,
+                                uint32_t q_offset, int32_t shiftedQBits, int32_t shiftedFFunc, int32_t iq_offset, int32_t shiftNum,
+                                uint32_t areaSize, uint32_t *nonzerocoeff);
+/* EncodeInvTransform, Codec/EbTransforms.c:3502 (isOnlyDc gives identical samples, so it is not an argument) */
+int svtb200_EncodeInvTransform(const int16_t *coeffBuffer, uint32_t coeffStride, int16_t *reconBuffer, uint32_t reconStride,
+                               uint32_t transformSize, uint32_t bitIncrement, uint8_t dstTransformFlag);
+
 /* ---------------------------------------------------------------------------------------
  * Device-resident source pictures (the PictureAnalysis feeders).
  * svtb200_pa_picture_create allocates padded full / quarter / sixteenth luma planes in HBM with the

@@ -1,0 +1,474 @@
+// tq.cu -- residual -> forward DCT/DST -> quantise + dequantise -> inverse transform -> reconstruction, fused per TU.
+//
+// Replaces:
+//   Transform4x4 / DstTransform4x4 / Transform8x8 / Transform16x16Estimate / Transform32x32Estimate   C_DEFAULT/EbTransforms_C.c:1634-1889
+//     (+ SIMD rows lowPrecisionTransform{16x16,32x32}_AVX2_INTRIN, Transform8x8_SSE4_1_INTRIN, ..., Pfreq[N4]Transform*), EstimateTransform
+//     Codec/EbTransforms.c:3268
+//   QuantizeInvQuantize C_DEFAULT/EbTransforms_C.c:89 (+ QuantizeInvQuantize{4x4_SSE3,8x8_AVX2,NxN_AVX2}), UnifiedQuantizeInvQuantize default
+//     branch Codec/EbTransforms.c:3094-3261, UpdateQiQCoef C_DEFAULT/EbTransforms_C.c:209
+//   InvTransform{4,8,16,32} / InvDstTransform4x4 C_DEFAULT/EbTransforms_C.c:1910-2119 (+ PFinvTransform*_SSSE3, ...), EncodeInvTransform
+//     Codec/EbTransforms.c:3502
+//   PictureResidual / AdditionKernel / PfZeroOutUselessQuadrants (Codec/EbPictureOperators.h:242,349; EbTransforms.c:3627)
+//
+// Design: one CTA (128 threads) per TU.  The TU never leaves shared memory between the stages, so HBM sees exactly
+// src + pred in, quantised coefficients + reconstruction out (30 720 B per CTU, the algorithmic figure of SURVEY §8d).
+// The 1-D passes are plain integer matrix products against the HEVC core matrix held in __constant__ memory (lanes of a
+// warp share the matrix row -> broadcast); the 16/32-point forward passes fold the first butterfly stage in 16 bits exactly
+// like PartialButterfly{16,32}Estimate.  Only the `active` low-frequency corner is computed for the N2 / N4 shapes, and
+// the inverse skips the zero rows/columns.  No tensor cores: operands are s16 x s8 with a rounding shift per pass.
+#include "common.cuh"
+
+namespace svtb200 {
+
+constexpr int TQ_NT = 128;
+constexpr int TP = 34;   // s16 pitch of the 32x32 tiles: 17 words -> conflict-free column walks
+
+struct YuvW {
+    uint8_t *p[3];
+    int stride[3];
+    int ox[3], oy[3];
+};
+struct TqArgs {
+    YuvW src, pred, recon;
+    int16_t *coeff[3];
+    int cstride[3];
+    const svtb200_tq_job *jobs;
+    int n_jobs;
+    uint32_t *nz;
+};
+
+__constant__ int8_t c_dct32[32][32];    // M32[k][n]; M_N[k][n] = M32[k * 32 / N][n]
+__constant__ int8_t c_dst4[4][4] = {{29, 55, 74, 84}, {74, 74, 0, -74}, {84, -29, -74, 55}, {55, -84, 74, -29}};
+__constant__ uint32_t c_qfunc[6] = {26214, 23302, 20560, 18396, 16384, 14564};   // QFunc, Codec/EbTransforms.h:26
+__constant__ uint32_t c_ffunc[6] = {40, 45, 51, 57, 64, 72};                      // FFunc, :27
+
+static void build_dct32(int8_t m[32][32])
+{
+    static const int T[33] = {64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67, 64, 61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9, 4, 0};
+    for (int k = 0; k < 32; ++k)
+        for (int n = 0; n < 32; ++n) {
+            const int a = (k * (2 * n + 1)) & 127;
+            m[k][n] = (int8_t)(a <= 32 ? T[a] : a <= 64 ? -T[64 - a] : a <= 96 ? -T[a - 64] : T[128 - a]);
+        }
+}
+
+__device__ __forceinline__ int clip16i(int v) { return min(max(v, -32768), 32767); }
+
+// forward 1-D pass: out[k][r] = (s16)((sum_n M[k][n] * in[r][n] + off) >> shift) for k < kmax, r < rows
+__device__ void fwd_pass(const int16_t *in, int16_t *out, int N, int rows, int kmax, int shift, bool dst)
+{
+    const int off = 1 << (shift - 1), kstep = 32 / N;
+    for (int i = threadIdx.x; i < kmax * rows; i += TQ_NT) {
+        const int k = i / rows, r = i - k * rows;
+        const int16_t *x = in + r * TP;
+        int acc = 0;
+        if (dst) {
+#pragma unroll
+            for (int n = 0; n < 4; ++n) acc += c_dst4[k][n] * x[n];
+        } else if (N >= 16) {
+            const int8_t *m = c_dct32[k * kstep];
+            if (k & 1) for (int n = 0; n < N / 2; ++n) acc += m[n] * (int)(short)(x[n] - x[N - 1 - n]);
+            else for (int n = 0; n < N / 2; ++n) acc += m[n] * (int)(short)(x[n] + x[N - 1 - n]);
+        } else {
+            const int8_t *m = c_dct32[k * kstep];
+            for (int n = 0; n < N; ++n) acc += m[n] * x[n];
+        }
+        out[k * TP + r] = (int16_t)((acc + off) >> shift);
+    }
+}
+
+// inverse 1-D pass: out[r][n] = clip16((sum_{k<kact} M[k][n] * in[k][r] + off) >> shift) for r < rmax, n < N
+__device__ void inv_pass(const int16_t *in, int16_t *out, int N, int rmax, int kact, int shift, bool dst)
+{
+    const int off = 1 << (shift - 1), kstep = 32 / N;
+    for (int i = threadIdx.x; i < rmax * N; i += TQ_NT) {
+        const int r = i / N, n = i - r * N;
+        int acc = 0;
+        if (dst) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc += c_dst4[k][n] * in[k * TP + r];
+        } else {
+            for (int k = 0; k < kact; ++k) acc += c_dct32[k * kstep][n] * in[k * TP + r];
+        }
+        out[r * TP + n] = (int16_t)clip16i((acc + off) >> shift);
+    }
+}
+
+__device__ __forceinline__ int ilog2d(int v) { return 31 - __clz(v); }
+
+// The whole chain for one TU held in shared memory.  s_a: residual in (pitch TP); returns nz.
+// On exit s_a holds the reconstructed residual (if nz && want_recon), s_q the quantised coefficients (act x act corner).
+__device__ uint32_t tq_chain(int16_t *s_a, int16_t *s_b, int16_t *s_q, uint32_t *s_cnt, const svtb200_tq_job &t, bool want_recon)
+{
+    const int N = t.size, lg = ilog2d(N);
+    const bool dst = t.dst4x4 != 0;
+    const bool only_dc = t.shape == SVTB200_SHAPE_ONLY_DC;
+    const int act = only_dc ? 1 : (N == 4 ? 4 : (N >> t.shape));
+    if (threadIdx.x == 0) *s_cnt = 0;
+    // ---- forward ----
+    if (only_dc) {
+        // EstimateTransform ONLY_DC branch (Codec/EbTransforms.c:3316-3332): one rounding for both passes
+        int part = 0;
+        for (int i = threadIdx.x; i < N * N; i += TQ_NT) part += s_a[(i / N) * TP + (i % N)];
+        part = (int)warp_sum((uint32_t)part);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) atomicAdd(s_cnt, (uint32_t)part);
+        __syncthreads();
+        const int sum = (int)*s_cnt;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int shift = (lg - 1) + (lg + 6);
+            s_a[0] = (int16_t)((64 * 64 * sum + (1 << (shift - 1))) >> shift);
+            *s_cnt = 0;
+        }
+        __syncthreads();
+    } else {
+        int s1, s2;
+        if (N == 32) { s1 = 6; s2 = 9; } else if (N == 16) { s1 = 4; s2 = 9; } else { s1 = lg - 1; s2 = lg + 6; }
+        fwd_pass(s_a, s_b, N, N, act, s1, dst);     // s_b[k][r]
+        __syncthreads();
+        fwd_pass(s_b, s_a, N, act, act, s2, dst);   // s_a[v][u]
+        __syncthreads();
+    }
+    // ---- quantise / dequantise (UnifiedQuantizeInvQuantize parameter derivation, Codec/EbTransforms.c:3094-3110) ----
+    const int qpRem = t.qp % 6, qpPer = t.qp / 6;
+    const int tshift = 15 - 8 - lg;
+    const int shiftedQBits = 14 + qpPer + tshift;
+    const uint32_t qoff_ip = (uint32_t)(t.slice_type >= 2 ? 171 : 85) << (shiftedQBits - 9);
+    const uint32_t qoff = (!only_dc && t.dz_offset) ? (uint32_t)(t.dz_offset * (1u << shiftedQBits) / 20) : qoff_ip;
+    const int shiftedFFunc = qpPer > 8 ? (int)c_ffunc[qpRem] << (qpPer - 2) : (int)c_ffunc[qpRem] << qpPer;
+    const int shiftNum = qpPer > 8 ? 20 - 14 - tshift - 2 : 20 - 14 - tshift;
+    const int iqoff = 1 << (shiftNum - 1);
+    const uint32_t qf = c_qfunc[qpRem];
+    uint32_t mynz = 0;
+    for (int i = threadIdx.x; i < N * N; i += TQ_NT) {
+        const int y = i / N, x = i - y * N;
+        int16_t qv = 0, rv = 0;
+        if (y < act && x < act) {
+            const int c = s_a[y * TP + x];
+            int a = (int)((uint32_t)abs(c) * qf + qoff);
+            a >>= shiftedQBits;
+            qv = (int16_t)clip16i(c < 0 ? -a : a);
+            rv = (int16_t)clip16i((qv * shiftedFFunc + iqoff) >> shiftNum);
+            mynz += qv != 0;
+        }
+        s_q[y * TP + x] = qv;
+        s_b[y * TP + x] = rv;     // dequantised; zero outside the active corner (PfZeroOutUselessQuadrants)
+    }
+    mynz = warp_sum(mynz);
+    if ((threadIdx.x & 31) == 0 && mynz) atomicAdd(s_cnt, mynz);
+    __syncthreads();
+    if (!only_dc) {
+        if ((t.flags & SVTB200_TQ_CLEAN_SPARSE) && N >= 8 && *s_cnt && t.slice_type != 2 && act >= 4) {
+            // isolated-coefficient cleaning, Codec/EbTransforms.c:3199-3243: one thread per 4x4 group
+            __syncthreads();
+            const int g = act / 4;
+            for (int b = threadIdx.x; b < g * g; b += TQ_NT) {
+                const int by = b / g, bx = b - by * g;
+                int cnt = 0, loc = 0;
+                for (int y = 0; y < 4; ++y)
+                    for (int x = 0; x < 4; ++x)
+                        if (s_q[(by * 4 + y) * TP + bx * 4 + x]) { ++cnt; loc = (by * 4 + y) * TP + bx * 4 + x; }
+                if (cnt == 1 && loc != 0) { s_q[loc] = 0; s_b[loc] = 0; atomicSub(s_cnt, 1u); }
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            // UpdateQiQCoef, C_DEFAULT/EbTransforms_C.c:209 -- the (EB_S16) cast binds before the shift there
+            uint32_t nz = *s_cnt;
+            const int16_t forced = (int16_t)((int16_t)(shiftedFFunc + iqoff) >> shiftNum);
+            if (nz < 10 && (t.flags & SVTB200_TQ_CONTOURING) && t.slice_type == 2 && t.temporal_layer == 0 && t.plane == 0) {
+                const int loc = (act - 1) * TP + (act - 1);
+                if (s_q[loc] == 0) { ++nz; s_q[loc] = 1; s_b[loc] = forced; }
+            }
+            if (nz == 0 && (t.flags & SVTB200_TQ_ENABLE_CBF)) {
+                const int loc = (act - 2) * TP + (act - 1);
+                nz = 1; s_q[loc] = 1; s_b[loc] = forced;
+            }
+            *s_cnt = nz;
+        }
+        __syncthreads();
+    }
+    const uint32_t nz = *s_cnt;
+    if (nz && want_recon) {
+        inv_pass(s_b, s_a, N, dst ? 4 : act, act, 7, dst);     // s_a[r][n], rows r >= act would be all zero
+        __syncthreads();
+        if (!dst && act < N) {   // zero rows act..N-1 of the intermediate so the second pass may stop at act as well
+            for (int i = threadIdx.x; i < (N - act) * N; i += TQ_NT) s_a[(act + i / N) * TP + (i % N)] = 0;
+            __syncthreads();
+        }
+        inv_pass(s_a, s_b, N, N, dst ? 4 : act, 12, dst);      // s_b[y][x] residual
+        __syncthreads();
+    }
+    return nz;
+}
+
+__global__ void __launch_bounds__(TQ_NT) tq_batch_kernel(const __grid_constant__ TqArgs A)
+{
+    __shared__ __align__(16) int16_t s_a[32 * TP], s_b[32 * TP], s_q[32 * TP];
+    __shared__ uint32_t s_cnt;
+    const int j = blockIdx.x;
+    if (j >= A.n_jobs) return;
+    const svtb200_tq_job t = A.jobs[j];
+    const int N = t.size, pl = t.plane;
+    const uint8_t *s = A.src.p[pl] + (size_t)(A.src.oy[pl] + t.y) * A.src.stride[pl] + A.src.ox[pl] + t.x;
+    const uint8_t *p = A.pred.p[pl] + (size_t)(A.pred.oy[pl] + t.y) * A.pred.stride[pl] + A.pred.ox[pl] + t.x;
+    uint8_t *r = A.recon.p[pl] + (size_t)(A.recon.oy[pl] + t.y) * A.recon.stride[pl] + A.recon.ox[pl] + t.x;
+    for (int i = threadIdx.x; i < N * N; i += TQ_NT) {
+        const int y = i / N, x = i - y * N;
+        s_a[y * TP + x] = (int16_t)((int)s[(size_t)y * A.src.stride[pl] + x] - (int)p[(size_t)y * A.pred.stride[pl] + x]);
+    }
+    __syncthreads();
+    const bool want_recon = !(t.flags & SVTB200_TQ_SKIP_RECON);
+    const uint32_t nz = tq_chain(s_a, s_b, s_q, &s_cnt, t, want_recon);
+    if (threadIdx.x == 0) A.nz[j] = nz;
+    int16_t *co = A.coeff[pl] + (size_t)t.y * A.cstride[pl] + t.x;
+    for (int i = threadIdx.x; i < N * N; i += TQ_NT) {
+        const int y = i / N, x = i - y * N;
+        co[(size_t)y * A.cstride[pl] + x] = s_q[y * TP + x];
+        if (want_recon) {
+            const int pv = p[(size_t)y * A.pred.stride[pl] + x];
+            const int v = nz ? min(max(pv + s_b[y * TP + x], 0), 255) : pv;
+            if (nz || r != p) r[(size_t)y * A.recon.stride[pl] + x] = (uint8_t)v;
+        }
+    }
+}
+
+// leaf kernels: mode 0 forward (EstimateTransform), 1 QiQ with explicit parameters, 2 inverse
+struct LeafArgs {
+    const int16_t *in; int16_t *out, *out2; uint32_t *nz;
+    int istride, ostride, N, bit_inc, dst, shape, mode;
+    uint32_t qFunc, q_offset; int shiftedQBits, shiftedFFunc, iq_offset, shiftNum, area;
+};
+__global__ void __launch_bounds__(TQ_NT) tq_leaf_kernel(const LeafArgs L)
+{
+    __shared__ __align__(16) int16_t s_a[32 * TP], s_b[32 * TP];
+    __shared__ uint32_t s_cnt;
+    const int N = L.N, lg = ilog2d(N);
+    if (L.mode == 1) {
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        uint32_t mynz = 0;
+        for (int i = threadIdx.x; i < L.area * L.area; i += TQ_NT) {
+            const int y = i / L.area, x = i - y * L.area;
+            const int c = L.in[y * L.istride + x];
+            int a = (int)((uint32_t)abs(c) * L.qFunc + L.q_offset);
+            a >>= L.shiftedQBits;
+            const int16_t qv = (int16_t)clip16i(c < 0 ? -a : a);
+            L.out[y * L.istride + x] = qv;
+            L.out2[y * L.istride + x] = (int16_t)clip16i((qv * L.shiftedFFunc + L.iq_offset) >> L.shiftNum);
+            mynz += qv != 0;
+        }
+        mynz = warp_sum(mynz);
+        if ((threadIdx.x & 31) == 0 && mynz) atomicAdd(&s_cnt, mynz);
+        __syncthreads();
+        if (threadIdx.x == 0) *L.nz = s_cnt;
+        return;
+    }
+    for (int i = threadIdx.x; i < N * N; i += TQ_NT) s_a[(i / N) * TP + (i % N)] = L.in[(i / N) * L.istride + (i % N)];
+    __syncthreads();
+    if (L.mode == 0) {
+        const bool dst = L.dst != 0;
+        if (L.shape == SVTB200_SHAPE_ONLY_DC) {
+            if (threadIdx.x == 0) {
+                int sum = 0;
+                for (int i = 0; i < N * N; ++i) sum += s_a[(i / N) * TP + (i % N)];
+                const int shift = (lg - 1 + L.bit_inc) + (lg + 6);
+                L.out[0] = (int16_t)((64 * 64 * sum + (1 << (shift - 1))) >> shift);
+            }
+            return;
+        }
+        const int act = N == 4 ? 4 : (N >> L.shape);
+        int s1, s2;
+        if (N == 32) { s1 = 6 + L.bit_inc; s2 = 9; } else if (N == 16) { s1 = 4 + L.bit_inc; s2 = 9; } else { s1 = lg - 1 + L.bit_inc; s2 = lg + 6; }
+        fwd_pass(s_a, s_b, N, N, act, s1, dst);
+        __syncthreads();
+        fwd_pass(s_b, s_a, N, act, act, s2, dst);
+        __syncthreads();
+        for (int i = threadIdx.x; i < act * act; i += TQ_NT) L.out[(i / act) * L.ostride + (i % act)] = s_a[(i / act) * TP + (i % act)];
+    } else {
+        const bool dst = L.dst != 0;
+        inv_pass(s_a, s_b, N, N, N, 7, dst);
+        __syncthreads();
+        inv_pass(s_b, s_a, N, N, N, 12 - L.bit_inc, dst);
+        __syncthreads();
+        for (int i = threadIdx.x; i < N * N; i += TQ_NT) L.out[(i / N) * L.ostride + (i % N)] = s_a[(i / N) * TP + (i % N)];
+    }
+}
+
+static int ensure_tables()
+{
+    static thread_local bool done = false;   // per thread: cheap and avoids a lock; the copy is idempotent
+    if (done) return SVTB200_OK;
+    int8_t m[32][32];
+    build_dct32(m);
+    SVTB200_CUDA_TRY(cudaMemcpyToSymbol(c_dct32, m, sizeof m));
+    done = true;
+    return SVTB200_OK;
+}
+
+static YuvW to_yuvw(const svtb200_yuv_picture &p, uint8_t *y, uint8_t *cb, uint8_t *cr)
+{
+    YuvW w;
+    w.p[0] = y; w.p[1] = cb; w.p[2] = cr;
+    const svtb200_plane *pl[3] = {&p.y, &p.cb, &p.cr};
+    for (int k = 0; k < 3; ++k) { w.stride[k] = (int)pl[k]->stride; w.ox[k] = pl[k]->origin_x; w.oy[k] = pl[k]->origin_y; }
+    return w;
+}
+static size_t pbytes(const svtb200_plane &p) { return (size_t)p.stride * (p.height + 2 * p.origin_y); }
+
+static int check_jobs(const svtb200_tq_job *jobs, int n, const svtb200_yuv_picture &pic)
+{
+    for (int j = 0; j < n; ++j) {
+        const svtb200_tq_job &t = jobs[j];
+        const svtb200_plane &pl = t.plane == 0 ? pic.y : t.plane == 1 ? pic.cb : pic.cr;
+        const bool ok = t.plane <= 2 && (t.size == 4 || t.size == 8 || t.size == 16 || t.size == 32) && t.shape <= 3 && t.qp <= 51 && t.slice_type <= 3 &&
+                        (!t.dst4x4 || t.size == 4) && (t.size > 4 || t.shape == 0) && !(t.size == 8 && t.shape == SVTB200_SHAPE_N4) &&
+                        t.x + t.size <= pl.width + 2 * pl.origin_x && t.y + t.size <= pl.height + 2 * pl.origin_y;
+        if (!ok) { set_error("tq_batch: job %d malformed (size/shape/qp/plane out of range, or 8x8 with N4 which the reference leaves undefined)", j); return SVTB200_ERR_BAD_ARG; }
+    }
+    return SVTB200_OK;
+}
+
+}  // namespace svtb200
+using namespace svtb200;
+
+extern "C" {
+
+int svtb200_tq_batch_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *pred, const svtb200_yuv_picture *recon,
+                         const svtb200_coeff_picture *coeff, const svtb200_tq_job *jobs_dev, int n_jobs, uint32_t *nz_counts_dev, void *cuda_stream)
+{
+    if (!src || !pred || !recon || !coeff || (!jobs_dev && n_jobs) || n_jobs < 0 || !nz_counts_dev) { set_error("tq_batch_dev: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    int rc = ensure_device();
+    if (rc || (rc = ensure_tables())) return rc;
+    if (n_jobs == 0) return SVTB200_OK;
+    TqArgs A;
+    A.src = to_yuvw(*src, src->y.buf, src->cb.buf, src->cr.buf);
+    A.pred = to_yuvw(*pred, pred->y.buf, pred->cb.buf, pred->cr.buf);
+    A.recon = to_yuvw(*recon, recon->y.buf, recon->cb.buf, recon->cr.buf);
+    for (int k = 0; k < 3; ++k) { A.coeff[k] = coeff->buf[k]; A.cstride[k] = (int)coeff->stride[k]; }
+    A.jobs = jobs_dev; A.n_jobs = n_jobs; A.nz = nz_counts_dev;
+    tq_batch_kernel<<<n_jobs, TQ_NT, 0, (cudaStream_t)cuda_stream>>>(A);
+    SVTB200_COUNT_LAUNCH();
+    SVTB200_CUDA_TRY(cudaGetLastError());
+    return SVTB200_OK;
+}
+
+int svtb200_tq_batch(const svtb200_yuv_picture *src, const svtb200_yuv_picture *pred, const svtb200_yuv_picture *recon,
+                     const svtb200_coeff_picture *coeff, const svtb200_tq_job *jobs, int n_jobs, uint32_t *nz_counts)
+{
+    if (!src || !pred || !recon || !coeff || (!jobs && n_jobs) || n_jobs < 0 || !nz_counts) { set_error("tq_batch: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    int rc = check_jobs(jobs, n_jobs, *src);
+    if (rc) return rc;
+    ThreadCtx *c = tls_ctx();
+    if ((rc = c->init()) || (rc = ensure_tables())) return rc;
+    c->reset();
+    const bool in_place = recon->y.buf == pred->y.buf && recon->cb.buf == pred->cb.buf && recon->cr.buf == pred->cr.buf;
+    const svtb200_yuv_picture *pics[3] = {src, pred, recon};
+    const size_t cw = src->y.width, chh = src->y.height;
+    const size_t cbytes[3] = {(size_t)coeff->stride[0] * chh * 2, (size_t)coeff->stride[1] * (chh / 2) * 2, (size_t)coeff->stride[2] * (chh / 2) * 2};
+    (void)cw;
+    size_t need = 8192 + (size_t)n_jobs * (sizeof(svtb200_tq_job) + 4);
+    for (int i = 0; i < 3; ++i) need += align_up(pbytes(pics[i]->y), 256) + align_up(pbytes(pics[i]->cb), 256) + align_up(pbytes(pics[i]->cr), 256);
+    for (int k = 0; k < 3; ++k) need += align_up(cbytes[k], 256);
+    if ((rc = c->dev_reserve(need))) return rc;
+    uint8_t *dp[3][3];
+    for (int i = 0; i < 3; ++i) {
+        const svtb200_plane *pl[3] = {&pics[i]->y, &pics[i]->cb, &pics[i]->cr};
+        for (int k = 0; k < 3; ++k) {
+            if (i == 2 && in_place) { dp[2][k] = dp[1][k]; continue; }
+            void *d;
+            if ((rc = c->dev_alloc(pbytes(*pl[k]), &d))) return rc;
+            dp[i][k] = (uint8_t *)d;
+            // recon (when separate) is updated only inside TU areas: bring its current content over as well
+            SVTB200_CUDA_TRY(cudaMemcpyAsync(d, pl[k]->buf, pbytes(*pl[k]), cudaMemcpyHostToDevice, c->stream));
+        }
+    }
+    void *dc[3], *d_jobs, *d_nz;
+    for (int k = 0; k < 3; ++k) {
+        if ((rc = c->dev_alloc(cbytes[k], &dc[k]))) return rc;
+        SVTB200_CUDA_TRY(cudaMemcpyAsync(dc[k], coeff->buf[k], cbytes[k], cudaMemcpyHostToDevice, c->stream));
+    }
+    if ((rc = c->dev_alloc(sizeof(svtb200_tq_job) * (size_t)std::max(n_jobs, 1), &d_jobs)) || (rc = c->dev_alloc(4 * (size_t)std::max(n_jobs, 1), &d_nz))) return rc;
+    if (n_jobs) SVTB200_CUDA_TRY(cudaMemcpyAsync(d_jobs, jobs, sizeof(svtb200_tq_job) * (size_t)n_jobs, cudaMemcpyHostToDevice, c->stream));
+    svtb200_yuv_picture ds = *src, dpred = *pred, drec = *recon;
+    ds.y.buf = dp[0][0]; ds.cb.buf = dp[0][1]; ds.cr.buf = dp[0][2];
+    dpred.y.buf = dp[1][0]; dpred.cb.buf = dp[1][1]; dpred.cr.buf = dp[1][2];
+    drec.y.buf = dp[2][0]; drec.cb.buf = dp[2][1]; drec.cr.buf = dp[2][2];
+    svtb200_coeff_picture dcoef = *coeff;
+    for (int k = 0; k < 3; ++k) dcoef.buf[k] = (int16_t *)dc[k];
+    if ((rc = svtb200_tq_batch_dev(&ds, &dpred, &drec, &dcoef, (const svtb200_tq_job *)d_jobs, n_jobs, (uint32_t *)d_nz, c->stream))) return rc;
+    const svtb200_plane *rpl[3] = {&recon->y, &recon->cb, &recon->cr};
+    for (int k = 0; k < 3; ++k) {
+        SVTB200_CUDA_TRY(cudaMemcpyAsync(rpl[k]->buf, dp[2][k], pbytes(*rpl[k]), cudaMemcpyDeviceToHost, c->stream));
+        SVTB200_CUDA_TRY(cudaMemcpyAsync(coeff->buf[k], dc[k], cbytes[k], cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (n_jobs) SVTB200_CUDA_TRY(cudaMemcpyAsync(nz_counts, d_nz, 4 * (size_t)n_jobs, cudaMemcpyDeviceToHost, c->stream));
+    SVTB200_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SVTB200_OK;
+}
+
+static int tq_leaf(LeafArgs L, const int16_t *in, size_t in_elems, int16_t *out, size_t out_elems, int16_t *out2, uint32_t *nz)
+{
+    ThreadCtx *c = tls_ctx();
+    int rc;
+    if ((rc = c->init()) || (rc = ensure_tables())) return rc;
+    c->reset();
+    void *d_in, *d_out, *d_out2, *d_nz, *h;
+    if ((rc = c->dev_reserve((in_elems + 2 * out_elems) * 2 + 8192)) || (rc = c->dev_alloc(in_elems * 2, &d_in)) || (rc = c->dev_alloc(out_elems * 2, &d_out)) ||
+        (rc = c->dev_alloc(out_elems * 2, &d_out2)) || (rc = c->dev_alloc(4, &d_nz)) || (rc = c->pin_alloc(out_elems * 4 + 16, &h))) return rc;
+    SVTB200_CUDA_TRY(cudaMemcpyAsync(d_in, in, in_elems * 2, cudaMemcpyHostToDevice, c->stream));
+    SVTB200_CUDA_TRY(cudaMemsetAsync(d_out, 0, out_elems * 2, c->stream));
+    SVTB200_CUDA_TRY(cudaMemsetAsync(d_out2, 0, out_elems * 2, c->stream));
+    L.in = (const int16_t *)d_in; L.out = (int16_t *)d_out; L.out2 = (int16_t *)d_out2; L.nz = (uint32_t *)d_nz;
+    tq_leaf_kernel<<<1, TQ_NT, 0, c->stream>>>(L);
+    SVTB200_COUNT_LAUNCH();
+    SVTB200_CUDA_TRY(cudaGetLastError());
+    int16_t *h16 = (int16_t *)h;
+    SVTB200_CUDA_TRY(cudaMemcpyAsync(h16, d_out, out_elems * 2, cudaMemcpyDeviceToHost, c->stream));
+    SVTB200_CUDA_TRY(cudaMemcpyAsync(h16 + out_elems, d_out2, out_elems * 2, cudaMemcpyDeviceToHost, c->stream));
+    SVTB200_CUDA_TRY(cudaMemcpyAsync(h16 + 2 * out_elems, d_nz, 4, cudaMemcpyDeviceToHost, c->stream));
+    SVTB200_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const int rows = L.mode == 1 ? L.area : L.N, cols = rows, os = L.mode == 1 ? L.istride : L.ostride;
+    const int keep = (L.mode == 0) ? (L.shape == SVTB200_SHAPE_ONLY_DC ? 1 : (L.N == 4 ? 4 : L.N >> L.shape)) : rows;
+    for (int y = 0; y < keep; ++y)
+        for (int x = 0; x < (L.mode == 0 ? keep : cols); ++x) {
+            out[(size_t)y * os + x] = h16[(size_t)y * os + x];
+            if (out2) out2[(size_t)y * os + x] = h16[out_elems + (size_t)y * os + x];
+        }
+    if (nz) memcpy(nz, h16 + 2 * out_elems, 4);
+    return SVTB200_OK;
+}
+
+int svtb200_EstimateTransform(const int16_t *residualBuffer, uint32_t residualStride, int16_t *coeffBuffer, uint32_t coeffStride, uint32_t transformSize,
+                              uint32_t bitIncrement, uint8_t dstTransformFlag, uint8_t transCoeffShape)
+{
+    const uint32_t N = transformSize;
+    if (!residualBuffer || !coeffBuffer || !(N == 4 || N == 8 || N == 16 || N == 32) || transCoeffShape > 3 || (dstTransformFlag && N != 4) || bitIncrement > 4) { set_error("EstimateTransform: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    LeafArgs L{};
+    L.istride = (int)residualStride; L.ostride = (int)coeffStride; L.N = (int)N; L.bit_inc = (int)bitIncrement; L.dst = dstTransformFlag; L.shape = transCoeffShape; L.mode = 0;
+    return tq_leaf(L, residualBuffer, (size_t)(N - 1) * residualStride + N, coeffBuffer, (size_t)(N - 1) * coeffStride + N, nullptr, nullptr);
+}
+
+int svtb200_QuantizeInvQuantize(const int16_t *coeff, uint32_t coeffStride, int16_t *quantCoeff, int16_t *reconCoeff, uint32_t qFunc, uint32_t q_offset,
+                                int32_t shiftedQBits, int32_t shiftedFFunc, int32_t iq_offset, int32_t shiftNum, uint32_t areaSize, uint32_t *nonzerocoeff)
+{
+    if (!coeff || !quantCoeff || !reconCoeff || !nonzerocoeff || areaSize == 0 || areaSize > 32 || shiftedQBits < 0 || shiftedQBits > 31 || shiftNum < 0 || shiftNum > 31) { set_error("QuantizeInvQuantize: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    LeafArgs L{};
+    L.istride = (int)coeffStride; L.ostride = (int)coeffStride; L.N = (int)areaSize; L.mode = 1; L.area = (int)areaSize;
+    L.qFunc = qFunc; L.q_offset = q_offset; L.shiftedQBits = shiftedQBits; L.shiftedFFunc = shiftedFFunc; L.iq_offset = iq_offset; L.shiftNum = shiftNum;
+    const size_t n = (size_t)(areaSize - 1) * coeffStride + areaSize;
+    return tq_leaf(L, coeff, n, quantCoeff, n, reconCoeff, nonzerocoeff);
+}
+
+int svtb200_EncodeInvTransform(const int16_t *coeffBuffer, uint32_t coeffStride, int16_t *reconBuffer, uint32_t reconStride, uint32_t transformSize,
+                               uint32_t bitIncrement, uint8_t dstTransformFlag)
+{
+    const uint32_t N = transformSize;
+    if (!coeffBuffer || !reconBuffer || !(N == 4 || N == 8 || N == 16 || N == 32) || (dstTransformFlag && N != 4) || bitIncrement > 4) { set_error("EncodeInvTransform: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    LeafArgs L{};
+    L.istride = (int)coeffStride; L.ostride = (int)reconStride; L.N = (int)N; L.bit_inc = (int)bitIncrement; L.dst = dstTransformFlag; L.mode = 2;
+    return tq_leaf(L, coeffBuffer, (size_t)(N - 1) * coeffStride + N, reconBuffer, (size_t)(N - 1) * reconStride + N, nullptr, nullptr);
+}
+
+}  // extern "C"

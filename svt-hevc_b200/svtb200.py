@@ -324,3 +324,62 @@ def chroma_bipred(f0x, f0y, r0, r0_off, r0s, f1x, f1y, r1, r1_off, r1s, w, h):
                                                   C.c_uint32(f1x), C.c_uint32(f1y), C.c_void_p(r1.ctypes.data + r1_off), C.c_uint32(r1s),
                                                   _u8p(dst), C.c_uint32(w), C.c_uint32(w), C.c_uint32(h)))
     return dst
+
+
+# ================================================================================================
+# C. residual / transform / quant / inverse / recon
+# ================================================================================================
+SHAPE_DEFAULT, SHAPE_N2, SHAPE_N4, SHAPE_ONLY_DC = 0, 1, 2, 3
+TQ_CLEAN_SPARSE, TQ_ENABLE_CBF, TQ_CONTOURING, TQ_SKIP_RECON = 1, 2, 4, 8
+
+TQ_JOB_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("plane", "u1"), ("size", "u1"), ("dst4x4", "u1"), ("shape", "u1"), ("qp", "u1"),
+                         ("slice_type", "u1"), ("temporal_layer", "u1"), ("flags", "u1"), ("dz_offset", "<u4")])
+assert TQ_JOB_DTYPE.itemsize == 16
+
+
+class CoeffPicture(C.Structure):
+    _fields_ = [("buf", C.c_void_p * 3), ("stride", C.c_uint32 * 3)]
+
+
+class HostCoeffPicture:
+    def __init__(self, width, height):
+        self.planes = [np.zeros((height, width), np.int16), np.zeros((height // 2, width // 2), np.int16), np.zeros((height // 2, width // 2), np.int16)]
+        self.struct = CoeffPicture()
+        for i, p in enumerate(self.planes):
+            self.struct.buf[i] = p.ctypes.data
+            self.struct.stride[i] = p.shape[1]
+
+
+def tq_batch(src, pred, recon, coeff, jobs):
+    """src/pred/recon: HostYuvPicture (recon may be pred); coeff: HostCoeffPicture; jobs: TQ_JOB_DTYPE array -> nz counts."""
+    jobs = np.ascontiguousarray(jobs)
+    nz = np.zeros(len(jobs), np.uint32)
+    check(lib().svtb200_tq_batch(C.byref(src.struct), C.byref(pred.struct), C.byref(recon.struct), C.byref(coeff.struct), _u8p(jobs),
+                                 C.c_int(len(jobs)), _u8p(nz)))
+    return nz
+
+
+def estimate_transform(res, N, bit_inc=0, dst=0, shape=0):
+    res = np.ascontiguousarray(res, np.int16)
+    out = np.zeros((N, N), np.int16)
+    check(lib().svtb200_EstimateTransform(_u8p(res), C.c_uint32(res.shape[1]), _u8p(out), C.c_uint32(N), C.c_uint32(N), C.c_uint32(bit_inc),
+                                          C.c_uint8(dst), C.c_uint8(shape)))
+    return out
+
+
+def quantize_inv_quantize(coeff, qFunc, q_offset, shiftedQBits, shiftedFFunc, iq_offset, shiftNum, area):
+    coeff = np.ascontiguousarray(coeff, np.int16)
+    q = np.zeros_like(coeff)
+    r = np.zeros_like(coeff)
+    nz = C.c_uint32(0)
+    check(lib().svtb200_QuantizeInvQuantize(_u8p(coeff), C.c_uint32(coeff.shape[1]), _u8p(q), _u8p(r), C.c_uint32(qFunc), C.c_uint32(q_offset),
+                                            C.c_int32(shiftedQBits), C.c_int32(shiftedFFunc), C.c_int32(iq_offset), C.c_int32(shiftNum),
+                                            C.c_uint32(area), C.byref(nz)))
+    return q, r, nz.value
+
+
+def encode_inv_transform(coeff, N, bit_inc=0, dst=0):
+    coeff = np.ascontiguousarray(coeff, np.int16)
+    out = np.zeros((N, N), np.int16)
+    check(lib().svtb200_EncodeInvTransform(_u8p(coeff), C.c_uint32(coeff.shape[1]), _u8p(out), C.c_uint32(N), C.c_uint32(N), C.c_uint32(bit_inc), C.c_uint8(dst)))
+    return out
