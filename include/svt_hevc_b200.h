@@ -275,6 +275,39 @@ int svtb200_QuantizeInvQuantize(const int16_t *coeff, uint32_t coeffStride, int1
 int svtb200_EncodeInvTransform(const int16_t *coeffBuffer, uint32_t coeffStride, int16_t *reconBuffer, uint32_t reconStride,
                                uint32_t transformSize, uint32_t bitIncrement, uint8_t dstTransformFlag);
 
+/* =======================================================================================
+ *  E. In-loop deblocking filter
+ * ===================================================================================== */
+
+/* Picture-level deblocking parameters: the PictureControlSet_t fields the reference's DLF drivers read
+ * (Codec/EbDeblockingFilter.c:2222,2828,3518: qpArrayStride, tcOffset, betaOffset, cbQpOffset, crQpOffset). */
+typedef struct svtb200_dlf_params {
+    uint16_t pic_width, pic_height;   /* luma, multiples of 8                                             */
+    uint16_t qp_array_stride;         /* entries per row of qp_array (one entry per 8x8 luma block)       */
+    int8_t   tc_offset, beta_offset;  /* slice-level offsets (already multiplied by 2, as the PCS stores) */
+    int8_t   cb_qp_offset, cr_qp_offset;
+} svtb200_dlf_params;
+
+/* Deblocks a whole picture in place, HEVC order: every vertical edge of the picture, then every horizontal edge on
+ * the result.  This equals what the reference obtains LCU by LCU with LCUInternalAreaDLFCore + LCUBoundaryDLFCore +
+ * LCUPictureEdgeDLFCore (Codec/EbCodingLoop.c:4604-4635) once all LCUs are done.
+ *   vertical_bs / horizontal_bs : [n_lcu][256] boundary strengths, LCU raster order, entry (x>>2) + (y>>2)*16 inside the
+ *       64x64 LCU (verticalEdgeBSArray / horizontalEdgeBSArray, BLK4X4_ADDR_TO_*_EDGE_BS_ARRAY_IDX EbDeblockingFilter.h:19-20);
+ *       a vertical entry is the strength of the edge on the LEFT side of that 4x4 block, a horizontal one of its TOP side
+ *   qp_array : one qp per 8x8 luma block (SetQpArrayBasedOnCU :50)
+ * Edge filters: Luma4SampleEdgeDLFCore / Chroma2SampleEdgeDLFCore (C_DEFAULT/EbDeblockingFilter_C.c:39,469). */
+int svtb200_dlf_picture(const svtb200_yuv_picture *recon, const uint8_t *vertical_bs, const uint8_t *horizontal_bs,
+                        const uint8_t *qp_array, const svtb200_dlf_params *prm);
+int svtb200_dlf_picture_dev(const svtb200_yuv_picture *recon, const uint8_t *vertical_bs, const uint8_t *horizontal_bs,
+                            const uint8_t *qp_array, const svtb200_dlf_params *prm, void *cuda_stream);
+
+/* Leaf entry points, reference prototypes (EbDeblockingFilter.h:245-273). In-place on host memory; the caller states how
+ * far the plane extends around the edge start via the fixed footprint: 4 samples either side, 4 (luma) / 2 (chroma) along. */
+int svtb200_Luma4SampleEdgeDLFCore(uint8_t *edgeStartFilteredSamplePtr, uint32_t reconLumaPicStride, uint8_t isVerticalEdge,
+                                   int32_t tc, int32_t beta);
+int svtb200_Chroma2SampleEdgeDLFCore(uint8_t *edgeStartSampleCb, uint8_t *edgeStartSampleCr, uint32_t reconChromaPicStride,
+                                     uint8_t isVerticalEdge, uint8_t cbTc, uint8_t crTc);
+
 /* ---------------------------------------------------------------------------------------
  * Device-resident source pictures (the PictureAnalysis feeders).
  * svtb200_pa_picture_create allocates padded full / quarter / sixteenth luma planes in HBM with the

@@ -383,3 +383,25 @@ def encode_inv_transform(coeff, N, bit_inc=0, dst=0):
     out = np.zeros((N, N), np.int16)
     check(lib().svtb200_EncodeInvTransform(_u8p(coeff), C.c_uint32(coeff.shape[1]), _u8p(out), C.c_uint32(N), C.c_uint32(N), C.c_uint32(bit_inc), C.c_uint8(dst)))
     return out
+
+
+# ================================================================================================
+# E. deblocking
+# ================================================================================================
+class DlfParams(C.Structure):
+    _fields_ = [("pic_width", C.c_uint16), ("pic_height", C.c_uint16), ("qp_array_stride", C.c_uint16), ("tc_offset", C.c_int8),
+                ("beta_offset", C.c_int8), ("cb_qp_offset", C.c_int8), ("cr_qp_offset", C.c_int8)]
+
+
+def dlf_picture(recon, vbs, hbs, qp_array, prm):
+    """In-place deblocking of a HostYuvPicture. vbs/hbs: uint8 [n_lcu][256]; qp_array: uint8 [H/8][qp_stride]."""
+    check(lib().svtb200_dlf_picture(C.byref(recon.struct), _u8p(vbs), _u8p(hbs), _u8p(qp_array), C.byref(prm)))
+
+
+def luma_edge_dlf(buf, off, stride, vertical, tc, beta):
+    check(lib().svtb200_Luma4SampleEdgeDLFCore(C.c_void_p(buf.ctypes.data + off), C.c_uint32(stride), C.c_uint8(vertical), C.c_int32(tc), C.c_int32(beta)))
+
+
+def chroma_edge_dlf(cb, cr, off, stride, vertical, cb_tc, cr_tc):
+    check(lib().svtb200_Chroma2SampleEdgeDLFCore(C.c_void_p(cb.ctypes.data + off), C.c_void_p(cr.ctypes.data + off), C.c_uint32(stride),
+                                                 C.c_uint8(vertical), C.c_uint8(cb_tc), C.c_uint8(cr_tc)))
