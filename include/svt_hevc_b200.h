@@ -308,6 +308,43 @@ int svtb200_Luma4SampleEdgeDLFCore(uint8_t *edgeStartFilteredSamplePtr, uint32_t
 int svtb200_Chroma2SampleEdgeDLFCore(uint8_t *edgeStartSampleCb, uint8_t *edgeStartSampleCr, uint32_t reconChromaPicStride,
                                      uint8_t isVerticalEdge, uint8_t cbTc, uint8_t crTc);
 
+/* =======================================================================================
+ *  F. Sample adaptive offset (the RD decision f2 stays on the host)
+ * ===================================================================================== */
+
+/* Per-LCU, per-component statistics: the outputs of GatherSaoStatisticsLcuLossy_62x62
+ * (C_DEFAULT/EbSampleAdaptiveOffset_C.c:125; SaoStats_t in EbSampleAdaptiveOffsetGenerationDecision.h). */
+typedef struct svtb200_sao_stats {
+    int32_t  bo_diff[32];
+    uint16_t bo_count[32];
+    int32_t  eo_diff[4][5];     /* [EO type 0/90/135/45][category], categories already compacted as the reference does */
+    uint16_t eo_count[4][5];
+} svtb200_sao_stats;
+
+/* Statistics of every LCU and component of a picture: out[(lcu * 3 + component)].  `recon` is read as it is -- the
+ * caller decides which deblocking state it holds (the reference gathers them per LCU right after that LCU's DLF,
+ * SURVEY §7 H3 / Codec/EbCodingLoop.c:4692-4748; on pictures whose DLF is off that state is simply the un-deblocked recon). */
+int svtb200_sao_stats_picture(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out);
+int svtb200_sao_stats_picture_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out_dev, void *cuda_stream);
+
+/* Per-LCU SAO parameters: mirror of SaoParameters_t (Codec/EbCodingUnit.h:137-146). */
+typedef struct svtb200_sao_params {
+    uint8_t type[2];            /* saoTypeIndex[luma, chroma]: 0 off, 1 EO-0, 2 EO-90, 3 EO-135, 4 EO-45, 5 BO */
+    uint8_t band_position[3];   /* saoBandPosition[Y, Cb, Cr]                                                   */
+    int8_t  offset[3][4];       /* saoOffset[Y, Cb, Cr][4]                                                      */
+    uint8_t reserved[3];
+} svtb200_sao_params;
+
+/* Applies SAO to a whole picture: out = SAO(in), every sample classified on the UNMODIFIED input (what the reference
+ * achieves in place with its saoUpBuffer / saoLeftBuffer line buffers, ApplySaoOffsetsPicture Codec/EbEncDecProcess.c:522,
+ * ApplySaoOffsetsLcu :215, kernels SAOApplyBO / SAOApplyEO_{0,90,135,45} C_DEFAULT/EbSampleAdaptiveOffset_C.c:394-861).
+ * in and out must be different pictures of identical geometry; picture-border samples of edge classes stay unmodified.
+ * sao_flag[0] / [1]: pictureControlSetPtr->saoFlag (luma / chroma enabled for this picture). */
+int svtb200_sao_apply_picture(const svtb200_yuv_picture *in, const svtb200_yuv_picture *out, const svtb200_sao_params *lcu_params,
+                              const uint8_t sao_flag[2]);
+int svtb200_sao_apply_picture_dev(const svtb200_yuv_picture *in, const svtb200_yuv_picture *out, const svtb200_sao_params *lcu_params_dev,
+                                  const uint8_t sao_flag[2], void *cuda_stream);
+
 /* ---------------------------------------------------------------------------------------
  * Device-resident source pictures (the PictureAnalysis feeders).
  * svtb200_pa_picture_create allocates padded full / quarter / sixteenth luma planes in HBM with the

@@ -26,7 +26,7 @@ mkdir -p "$OUT"
 STAMP="$OUT/.stamp"
 if [ -f "$STAMP" ] && [ -f "$OUT/libsvtref_avx2.so" ] && [ -f "$OUT/libsvtref_avx512.so" ] \
    && [ -f "$OUT/SvtHevcEncApp_avx512" ] && [ "$HERE/build_ref.sh" -ot "$STAMP" ] && [ "$HERE/yasm_shim.c" -ot "$STAMP" ] \
-   && [ -z "$(find "$HERE" -maxdepth 1 -name 'ref_*_harness.c' -newer "$STAMP")" ]; then
+   && [ -z "$(find "$HERE" -maxdepth 1 -name 'ref*_harness.c' -newer "$STAMP")" ]; then
   echo "build_ref.sh: up to date"; exit 0
 fi
 
@@ -53,6 +53,13 @@ build_variant() {  # $1 = variant name, $2 = source root
   done
   xargs -P "$JOBS" -I{} sh -c '{}' < "$OBJ/cmds"
   gcc -shared -o "$OUT/libsvtref_$V.so" "$OBJ"/*.o -lpthread -lm
+  # harnesses that #include a reference .c file (to reach its static functions) live in their own shared object so that the
+  # duplicate external symbols of that file never meet the originals at link time
+  for f in "$HERE"/refinc_*_harness.c; do
+    [ -f "$f" ] || continue
+    n=$(basename "${f%_harness.c}"); n=${n#refinc_}
+    gcc $BASE -I"$HERE/../include" -shared "$f" -o "$OUT/libsvtref_${n}_$V.so" -L"$OUT" -lsvtref_$V -Wl,-rpath,'$ORIGIN' -lpthread -lm
+  done
   if [ "$V" = avx512 ]; then
     gcc -O2 -std=gnu99 -w -D_GNU_SOURCE -I"$OBJ" -I"$SRC/API" "$SRC"/App/*.c -o "$OUT/SvtHevcEncApp_avx512" \
         -L"$OUT" -lsvtref_avx512 -Wl,-rpath,'$ORIGIN' -lpthread -lm

@@ -405,3 +405,25 @@ def luma_edge_dlf(buf, off, stride, vertical, tc, beta):
 def chroma_edge_dlf(cb, cr, off, stride, vertical, cb_tc, cr_tc):
     check(lib().svtb200_Chroma2SampleEdgeDLFCore(C.c_void_p(cb.ctypes.data + off), C.c_void_p(cr.ctypes.data + off), C.c_uint32(stride),
                                                  C.c_uint8(vertical), C.c_uint8(cb_tc), C.c_uint8(cr_tc)))
+
+
+# ================================================================================================
+# F. SAO
+# ================================================================================================
+SAO_STATS_DTYPE = np.dtype([("bo_diff", "<i4", 32), ("bo_count", "<u2", 32), ("eo_diff", "<i4", (4, 5)), ("eo_count", "<u2", (4, 5))])
+assert SAO_STATS_DTYPE.itemsize == 312
+SAO_PARAMS_DTYPE = np.dtype([("type", "u1", 2), ("band_position", "u1", 3), ("offset", "i1", (3, 4)), ("reserved", "u1", 3)])
+assert SAO_PARAMS_DTYPE.itemsize == 20
+
+
+def sao_stats_picture(src, recon):
+    n_lcu = ((recon.width + 63) // 64) * ((recon.height + 63) // 64)
+    out = np.zeros((n_lcu, 3), dtype=SAO_STATS_DTYPE)
+    check(lib().svtb200_sao_stats_picture(C.byref(src.struct), C.byref(recon.struct), _u8p(out)))
+    return out
+
+
+def sao_apply_picture(inp, out, params, sao_flag=(1, 1)):
+    params = np.ascontiguousarray(params)
+    flag = (C.c_uint8 * 2)(*sao_flag)
+    check(lib().svtb200_sao_apply_picture(C.byref(inp.struct), C.byref(out.struct), _u8p(params), flag))
