@@ -1,14 +1,19 @@
 #!/usr/bin/env python
-"""bench.py -- 4Kp60 8-bit preset-M10 hot-path throughput (CTUs/s, fps) on N B200s, next to the
-reference's CPU path on the same box.
+"""bench.py -- 4Kp60 8-bit preset-M10 hot-path throughput (CTUs/s, fps) on N B200s, next to the reference's CPU path
+on the same box.
 
-A "step" = one 3840x2160 frame through the hot path (stages listed in config.stages) with the
-per-picture parameters preset M10 derives for that frame's temporal layer; consecutive steps walk the
-8-frame hierarchical mini-GOP [0,3,2,3,1,3,2,3] (3 hierarchical levels, EbApi.h:222-226).
+A "step" = one 3840x2160 4:2:0 frame through the hot path with the per-picture tool schedule preset M10 derives for that
+frame's temporal layer; consecutive steps walk the 8-frame hierarchical mini-GOP [0,3,2,3,1,3,2,3]:
+    every frame : ME (HME-L0 one quadrant + 85-PU full-pel + bipred, 2 lists) -> MC of the chosen PUs -> residual/T/Q/iQ/iT/recon
+                  -> SAO statistics
+    layer 0 only: + deblocking + SAO application   (M10 switches DLF / SAO-apply off on layers 1-3, EbEncDecProcess.c:2036-2054)
+Mode decision itself (host, out of scope) is replaced by a fixed stand-in: 32x32 PUs / TUs taking each PU's best ME
+candidate; SAO parameters and boundary strengths are fixed per-LCU tables.  Both arms run exactly the same jobs.
   value : frames resident in HBM (16-frame ring > L2), device-timed with CUDA events, max over ranks
-  e2e   : the same step through the C ABI with HOST (pinned) buffers: H2D of the frame, kernels, D2H of results
-N > 1   : independent closed GOPs / streams per GPU -- weak scaling, no data-path collective.
---impl reference : the reference's own CPU implementation of the same stages (oracle/_ref, all host threads).
+  e2e   : the same step through the C ABI from HOST (pinned) buffers: H2D of Y/Cb/Cr, kernels, D2H of ME results,
+          quantised coefficients, nz counts and SAO statistics
+  N > 1 : independent closed GOPs / streams per GPU -- weak scaling, no data-path collective
+  --impl reference : the reference's own CPU implementation of the same stages (oracle/_ref, one frame per host thread)
 """
 import argparse
 import ctypes as C
@@ -26,11 +31,17 @@ for p in (os.path.join(ROOT, "svt-hevc_b200"), os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 W, H = 3840, 2160
-N_LCU = 60 * 34
+COLS, ROWS = 60, 34
+N_LCU = COLS * ROWS
 TL_PATTERN = [0, 3, 2, 3, 1, 3, 2, 3]
 RING = 16
-# algorithmic HBM bytes per CTU per reference list for ME: src Y 4096 + src 1/16 256 + ref Y 4096 + ref 1/16 256 + results 680
-ME_BYTES_PER_CTU_PER_LIST = 9384
+PAD = 80
+METRIC = "4Kp60 8-bit preset-M10 hot-path CTUs/sec (fps = value / 2040)"
+WORKLOAD = ("configs[1]: 3840x2160 8-bit 4:2:0, preset M10 tool schedule, mini-GOP temporal layers [0,3,2,3,1,3,2,3], 2 reference lists, "
+            "fixed 32x32 PU/TU mode-decision stand-in")
+STAGES = ["me_picture", "mc_batch", "tq_batch", "sao_stats_picture", "dlf_picture (layer 0)", "sao_apply_picture (layer 0)"]
+# algorithmic HBM bytes per CTU
+ALG = {"me": 9384 * 2, "mc_uni": 12288, "mc_bi": 18432, "tq": 30720, "dlf": 12864, "sao_stats": 12288 + 3 * 312, "sao_apply": 12288}
 
 
 def peaks():
@@ -46,7 +57,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.samples, self.reasons, self.stop_flag, self.max_mhz = [], set(), False, None
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -74,20 +85,91 @@ class ClockSampler(threading.Thread):
             time.sleep(0.02)
 
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def make_frames(n, seed):
-    import common
-    v = common.SynthVideo(W, H, seed=seed)
-    return [v.luma(i) for i in range(n)]
+# ------------------------------------------------------------------------------------------------
+# the workload: synthetic frames + the fixed decision tables shared by both arms
+# ------------------------------------------------------------------------------------------------
+class Workload:
+    def __init__(self, n_frames, seed):
+        import common
+        import svtb200 as S
+        self.S = S
+        v = common.SynthVideo(W, H, seed=seed)
+        self.luma = [v.luma(i) for i in range(n_frames)]
+        self.chroma = [v.chroma(i) for i in range(n_frames)]
+        self.n = n_frames
+        rng = np.random.default_rng(seed ^ 0xABCD)
+        # TU jobs: 32x32 luma + 16x16 chroma, 16x16 / 8x8 in the 48-row bottom LCUs
+        jobs = []
+        for plane, sh in ((0, 0), (1, 1), (2, 1)):
+            for ly in range(ROWS):
+                n = (32 >> sh) if ly < ROWS - 1 else (16 >> sh)
+                lh = (64 if ly < ROWS - 1 else 48) >> sh
+                for lx in range(COLS):
+                    for yy in range(0, lh, n):
+                        for xx in range(0, 64 >> sh, n):
+                            jobs.append(((lx * 64 >> sh) + xx, (ly * 64 >> sh) + yy, plane, n))
+        tq = np.zeros(len(jobs), dtype=S.TQ_JOB_DTYPE)
+        arr = np.array(jobs)
+        tq["x"], tq["y"], tq["plane"], tq["size"] = arr[:, 0], arr[:, 1], arr[:, 2], arr[:, 3]
+        tq["qp"] = np.where(tq["plane"] == 0, 32, 31)
+        tq["slice_type"] = 0
+        self.tq_jobs = tq
+        # boundary strengths: 1 on every 32x32 (16x16 in the bottom row) PU/TU boundary, none on the picture border
+        vbs = np.zeros((ROWS, COLS, 16, 16), np.uint8)
+        hbs = np.zeros((ROWS, COLS, 16, 16), np.uint8)
+        vbs[:, :, :, 0] = 1; vbs[:, :, :, 8] = 1; hbs[:, :, 0, :] = 1; hbs[:, :, 8, :] = 1
+        vbs[-1, :, :, 4] = 1; vbs[-1, :, :, 12] = 1; hbs[-1, :, 4, :] = 1
+        vbs[:, 0, :, 0] = 0; hbs[0, :, 0, :] = 0
+        self.vbs, self.hbs = vbs.reshape(N_LCU, 256), hbs.reshape(N_LCU, 256)
+        self.qp_array = np.full(((H + 7) // 8, W // 8), 32, np.uint8)
+        self.dlf_prm = S.DlfParams(W, H, W // 8, 0, 0, 0, 0)
+        prm = np.zeros(N_LCU, dtype=S.SAO_PARAMS_DTYPE)
+        prm["type"] = rng.integers(0, 6, (N_LCU, 2))
+        prm["band_position"] = rng.integers(0, 29, (N_LCU, 3))
+        prm["offset"] = rng.integers(-3, 4, (N_LCU, 3, 4))
+        self.sao_prm = prm
 
+    def tl(self, step):
+        return TL_PATTERN[step % 8]
 
-def cfg_for(step, S):
-    tl = TL_PATTERN[step % 8]
-    return S.me_config(W, H, enc_mode=10, temporal_layer=tl, num_lists=2, ref_poc=(0, 16)), tl
+    def me_cfg(self, step):
+        return self.S.me_config(W, H, enc_mode=10, temporal_layer=self.tl(step), num_lists=2, ref_poc=(0, 16))
+
+    def refs(self, step):
+        d = {0: 8, 1: 4, 2: 2, 3: 1}[self.tl(step)]
+        return (step - d) % self.n, (step + d) % self.n
+
+    def mc_jobs(self, me_results):
+        """Mode-decision stand-in: each 32x32 (16x16 in the bottom LCU row) PU takes its best ME candidate."""
+        S = self.S
+        res = me_results.reshape(ROWS, COLS, 85)
+        out = []
+        for ly in range(ROWS):
+            if ly < ROWS - 1:
+                pus = [(1 + k, (k & 1) * 32, (k >> 1) * 32, 32) for k in range(4)]
+            else:
+                pus = [(5 + by * 4 + bx, bx * 16, by * 16, 16) for by in range(3) for bx in range(4)]
+            for (pu, px, py, sz) in pus:
+                r = res[ly, :, pu]
+                j = np.zeros(COLS, dtype=S.MC_JOB_DTYPE)
+                j["x"] = np.arange(COLS) * 64 + px
+                j["y"] = ly * 64 + py
+                j["w"] = j["h"] = sz
+                j["dir"] = r["direction"][:, 0]
+                j["ref_idx"][:, 0], j["ref_idx"][:, 1] = 0, 1
+                j["mv"][:, 0, 0], j["mv"][:, 0, 1] = r["x_mv_l0"], r["y_mv_l0"]
+                j["mv"][:, 1, 0], j["mv"][:, 1, 1] = r["x_mv_l1"], r["y_mv_l1"]
+                out.append(j)
+        return np.concatenate(out)
+
+    @staticmethod
+    def mc_alg_bytes(jobs):
+        px = jobs["w"].astype(np.int64) * jobs["h"] * 3 // 2
+        return int((px * (np.where(jobs["dir"] == 2, 2, 1) + 1)).sum())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -103,38 +185,106 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     S.check(S.lib().svtb200_init(C.c_int(local)))
-    stream = torch.cuda.current_stream().cuda_stream
+    tstream = torch.cuda.current_stream()
+    stream = tstream.cuda_stream
+    wl = Workload(RING, seed=0x5F7C0001 + rank)
+    dev = torch.device("cuda", local)
 
-    lumas = make_frames(RING, seed=0x5F7C0001 + rank)
-    pinned = [torch.from_numpy(l).pin_memory() for l in lumas]
-    ring = [S.DevPaPicture(W, H) for _ in range(RING)]
-    for d, p in zip(ring, pinned):
-        d.upload(p.data_ptr(), stream)
-    res_bytes = N_LCU * 85 * 24
-    d_res = torch.empty(res_bytes, dtype=torch.uint8, device="cuda")
-    h_res = torch.empty(res_bytes, dtype=torch.uint8).pin_memory()
-    e2e_pic = S.DevPaPicture(W, H)
+    def dev_yuv():
+        y = torch.zeros((H + 2 * PAD, W + 2 * PAD), dtype=torch.uint8, device=dev)
+        cb = torch.zeros((H // 2 + PAD, W // 2 + PAD), dtype=torch.uint8, device=dev)
+        cr = torch.zeros((H // 2 + PAD, W // 2 + PAD), dtype=torch.uint8, device=dev)
+        st = S.make_yuv_struct((y.data_ptr(), cb.data_ptr(), cr.data_ptr()), (y.shape[1], cb.shape[1], cr.shape[1]), PAD, W, H)
+        return (y, cb, cr), st
+
+    def fill_yuv(t, y, cb, cr, replicate):
+        """H2D of the three planes into the padded device picture (+ edge replication when it will serve as a reference)."""
+        t[0][PAD:PAD + H, PAD:PAD + W].copy_(y, non_blocking=True)
+        t[1][PAD // 2:PAD // 2 + H // 2, PAD // 2:PAD // 2 + W // 2].copy_(cb, non_blocking=True)
+        t[2][PAD // 2:PAD // 2 + H // 2, PAD // 2:PAD // 2 + W // 2].copy_(cr, non_blocking=True)
+        if replicate:
+            for pl, p in zip(t, (PAD, PAD // 2, PAD // 2)):
+                hh, ww = pl.shape[0] - 2 * p, pl.shape[1] - 2 * p
+                pl[p:p + hh, :p] = pl[p:p + hh, p:p + 1]; pl[p:p + hh, p + ww:] = pl[p:p + hh, p + ww - 1:p + ww]
+                pl[:p, :] = pl[p:p + 1, :]; pl[p + hh:, :] = pl[p + hh - 1:p + hh, :]
+
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_y = [pin(a) for a in wl.luma]
+    h_cb = [pin(c[0]) for c in wl.chroma]
+    h_cr = [pin(c[1]) for c in wl.chroma]
+    ring_pa = [S.DevPaPicture(W, H) for _ in range(RING)]
+    ring_yuv = [dev_yuv() for _ in range(RING)]
+    for i in range(RING):
+        ring_pa[i].upload(h_y[i].data_ptr(), stream)
+        fill_yuv(ring_yuv[i][0], h_y[i], h_cb[i], h_cr[i], True)
+    pred_t, pred = dev_yuv()
+    sao_t, sao_out = dev_yuv()
+    e2e_pa = S.DevPaPicture(W, H)
+    e2e_t, e2e_yuv = dev_yuv()
+    coeff_t = [torch.zeros((H, W), dtype=torch.int16, device=dev), torch.zeros((H // 2, W // 2), dtype=torch.int16, device=dev),
+               torch.zeros((H // 2, W // 2), dtype=torch.int16, device=dev)]
+    coeff = S.CoeffPicture()
+    for k in range(3):
+        coeff.buf[k] = coeff_t[k].data_ptr(); coeff.stride[k] = coeff_t[k].shape[1]
+    d_res = torch.zeros(N_LCU * 85 * 24, dtype=torch.uint8, device=dev)
+    d_tq = torch.from_numpy(wl.tq_jobs.view(np.uint8)).to(dev)
+    d_nz = torch.zeros(len(wl.tq_jobs), dtype=torch.int32, device=dev)
+    d_vbs, d_hbs, d_qp = (torch.from_numpy(a.copy()).to(dev) for a in (wl.vbs, wl.hbs, wl.qp_array))
+    d_sao_prm = torch.from_numpy(wl.sao_prm.view(np.uint8)).to(dev)
+    d_stats = torch.zeros(N_LCU * 3 * 312, dtype=torch.uint8, device=dev)
+    h_res = torch.empty(d_res.shape, dtype=torch.uint8).pin_memory()
+    h_coeff = [torch.empty(t.shape, dtype=torch.int16).pin_memory() for t in coeff_t]
+    h_nz = torch.empty(d_nz.shape, dtype=torch.int32).pin_memory()
+    h_stats = torch.empty(d_stats.shape, dtype=torch.uint8).pin_memory()
+
+    # mode-decision stand-in: one ME pass per (ring frame, layer) pair fixes the MC job lists used by both timed loops
+    d_mc, mc_bytes = [], []
+    for i in range(RING):
+        r0, r1 = wl.refs(i)
+        S.me_picture_dev(wl.me_cfg(i), ring_pa[i], ring_pa[r0], ring_pa[r1], d_res.data_ptr(), stream)
+        torch.cuda.synchronize()
+        jobs = wl.mc_jobs(d_res.cpu().numpy().view(S.ME_PU_RESULT_DTYPE).reshape(N_LCU, 85))
+        d_mc.append((torch.from_numpy(jobs.view(np.uint8)).to(dev), len(jobs)))
+        mc_bytes.append(wl.mc_alg_bytes(jobs))
     torch.cuda.synchronize()
 
-    def refs_for(i):   # mini-GOP style references: nearest earlier / later ring entries by temporal distance
-        tl = TL_PATTERN[i % 8]
-        d = {0: 8, 1: 4, 2: 2, 3: 1}[tl]
-        return ring[(i - d) % RING], ring[(i + d) % RING]
+    names = ["me", "mc", "tq", "dlf", "sao_stats", "sao_apply"]
+
+    def pipeline(i, src_pa, src_yuv, ev=None):
+        """All device stages of frame i.  ev: dict name -> list of (start, end) events."""
+        def timed(name, fn):
+            if ev is None:
+                fn(); return
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            ev[name].append((a, b))
+        r0, r1 = wl.refs(i)
+        k = i % RING
+        tl0 = wl.tl(i) == 0
+        timed("me", lambda: S.me_picture_dev(wl.me_cfg(i), src_pa, ring_pa[r0], ring_pa[r1], d_res.data_ptr(), stream))
+        timed("mc", lambda: S.mc_batch_dev([ring_yuv[r0][1], ring_yuv[r1][1]], d_mc[k][0].data_ptr(), d_mc[k][1], pred, stream))
+        timed("tq", lambda: S.tq_batch_dev(src_yuv, pred, pred, coeff, d_tq.data_ptr(), len(wl.tq_jobs), d_nz.data_ptr(), stream))
+        if tl0:
+            timed("dlf", lambda: S.dlf_picture_dev(pred, d_vbs.data_ptr(), d_hbs.data_ptr(), d_qp.data_ptr(), wl.dlf_prm, stream))
+        timed("sao_stats", lambda: S.sao_stats_picture_dev(src_yuv, pred, d_stats.data_ptr(), stream))
+        if tl0:
+            timed("sao_apply", lambda: S.sao_apply_picture_dev(pred, sao_out, d_sao_prm.data_ptr(), (1, 1), stream))
 
     def step_resident(i, ev=None):
-        cfg, _ = cfg_for(i, S)
-        r0, r1 = refs_for(i)
-        if ev: ev[0].record()
-        S.me_picture_dev(cfg, ring[i % RING], r0, r1, d_res.data_ptr(), stream)
-        if ev: ev[1].record()
+        pipeline(i, ring_pa[i % RING], ring_yuv[i % RING][1], ev)
 
     def step_e2e(i):
-        cfg, _ = cfg_for(i, S)
-        r0, r1 = refs_for(i)
-        e2e_pic.upload(pinned[i % RING].data_ptr(), stream)                      # H2D luma + device pad/decimate
-        S.me_picture_dev(cfg, e2e_pic, r0, r1, d_res.data_ptr(), stream)
-        h_res.copy_(d_res, non_blocking=True)                                    # D2H results
-        torch.cuda.current_stream().synchronize()
+        k = i % RING
+        fill_yuv(e2e_t, h_y[k], h_cb[k], h_cr[k], False)                                   # H2D: Y + Cb + Cr
+        yint = e2e_t[0][PAD:, PAD:]
+        e2e_pa.build_from_device(yint.data_ptr(), e2e_t[0].shape[1], stream)               # pad + decimate on the device
+        pipeline(i, e2e_pa, e2e_yuv)
+        h_res.copy_(d_res, non_blocking=True)                                              # D2H: what the host-side encoder consumes
+        for hc, dc in zip(h_coeff, coeff_t):
+            hc.copy_(dc, non_blocking=True)
+        h_nz.copy_(d_nz, non_blocking=True)
+        h_stats.copy_(d_stats, non_blocking=True)
+        tstream.synchronize()
 
     def barrier():
         torch.cuda.synchronize()
@@ -146,20 +296,19 @@ def run_b200(args):
         step_resident(i)
     launches0 = S.lib().svtb200_launch_count()
     sampler = ClockSampler(local); sampler.start()
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = {n: [] for n in names}
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0.record()
     for i in range(args.steps):
-        step_resident(args.warmup + i, kev[i])
+        step_resident(args.warmup + i, ev)
     t1.record()
     barrier()
     sampler.stop_flag = True
     launches = S.lib().svtb200_launch_count() - launches0
     ms = t0.elapsed_time(t1)
-    kms = [a.elapsed_time(b) for a, b in kev]
+    stage_ms = {n: [a.elapsed_time(b) for a, b in ev[n]] for n in names}
 
-    # e2e: host buffers in, results out, copies inside the timed region
     for i in range(args.warmup):
         step_e2e(i)
     barrier()
@@ -176,84 +325,106 @@ def run_b200(args):
     if rank == 0:
         peak, peak_src = peaks()
         ctus = N_LCU * args.steps * world
-        k_avg_s = float(np.mean(kms)) * 1e-3
-        alg_bytes = ME_BYTES_PER_CTU_PER_LIST * 2 * N_LCU
-        achieved = alg_bytes / k_avg_s / 1e9
+        tot = {n: float(np.sum(v)) for n, v in stage_ms.items()}
+        dom = max(tot, key=tot.get)
+        alg = {"me": ALG["me"] * N_LCU, "mc": float(np.mean(mc_bytes)), "tq": ALG["tq"] * N_LCU, "dlf": ALG["dlf"] * N_LCU,
+               "sao_stats": ALG["sao_stats"] * N_LCU, "sao_apply": ALG["sao_apply"] * N_LCU}
+        per_stage = {n: {"launch_ms_avg": float(np.mean(v)) if v else None, "launches": len(v), "share_of_step": tot[n] / sum(tot.values()),
+                         "achieved_gbs": (alg[n] / (np.mean(v) * 1e-3) / 1e9) if v else None,
+                         "frac_of_hbm_peak": (alg[n] / (np.mean(v) * 1e-3) / 1e9 / peak) if v else None} for n, v in stage_ms.items()}
+        k_avg_s = float(np.mean(stage_ms[dom])) * 1e-3
+        h2d = W * H * 3 // 2
+        d2h = int(d_res.numel() + sum(t.numel() * 2 for t in coeff_t) + d_nz.numel() * 4 + d_stats.numel())
         out = {
-            "metric": "4Kp60 8-bit preset-M10 hot-path CTUs/sec (fps = value / 2040)", "value": ctus / (ms * 1e-3), "unit": "CTU/s",
-            "fps": ctus / (ms * 1e-3) / N_LCU,
+            "metric": METRIC, "value": ctus / (ms * 1e-3), "unit": "CTU/s", "fps": ctus / (ms * 1e-3) / N_LCU,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "configs[1]: 3840x2160 8-bit 4:2:0, preset M10 parameters, mini-GOP temporal layers [0,3,2,3,1,3,2,3], 2 reference lists",
-                       "stages": ["me_picture(HME-L0 one quadrant + 85-PU full-pel + integer bipred)"],
-                       "l2": "16-frame ring of resident 4K pictures (~175 MB of luma planes) > 126 MB L2", "parallelism": f"stream-per-GPU x{world}"},
+            "config": {"workload": WORKLOAD, "stages": STAGES,
+                       "l2": "16-frame ring of resident 4K pictures (> 400 MB of planes) > 126 MB L2", "parallelism": f"stream-per-GPU x{world}"},
             "e2e": {"value": ctus / (e2e_ms * 1e-3), "unit": "CTU/s", "fps": ctus / (e2e_ms * 1e-3) / N_LCU,
-                    "h2d_bytes_per_step": W * H, "d2h_bytes_per_step": res_bytes},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
-            "roofline": {"kernel": "me_picture_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_avg_s * 1e3},
+            "roofline": {"kernel": {"me": "me_picture_kernel", "mc": "mc_batch_kernel", "tq": "tq_batch_kernel", "dlf": "dlf_pass_kernel",
+                                    "sao_stats": "sao_stats_kernel", "sao_apply": "sao_apply_kernel"}[dom],
+                         "bound": "hbm", "achieved": alg[dom] / k_avg_s / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg[dom] / k_avg_s / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg[dom], "avg_launch_ms": k_avg_s * 1e3},
+            "stages": per_stage,
         }
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_reference(steps=8, max_threads=None)
+            out["cpu_baseline"] = cpu_reference(frames=None)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the reference's own MotionEstimateLcu + SIMD kernels, all host threads
+# reference arm / cpu baseline: the reference's own functions (oracle/_ref), one frame per host thread
 # ------------------------------------------------------------------------------------------------
-def cpu_reference(steps, max_threads):
+def cpu_reference(frames):
     import common
     import svtb200 as S
     from concurrent.futures import ThreadPoolExecutor
-    ref = common.load_ref()
-    kind = "reference"
-    fn_name = "svtref_me_picture_rows"
-    lib = ref
+    variant = "avx512" if common.cpu_has("avx512bw") else "avx2"
+    ref = common.load_ref(variant)
     if ref is None:
         raise RuntimeError("oracle/_ref missing: build it with oracle/build_ref.sh where /root/reference exists")
-    nthreads = max_threads or (os.cpu_count() or 1)
-    lumas = make_frames(3, seed=0x5F7C0001)
-    pics = [S.HostPaPicture(l) for l in lumas]
-    fn = getattr(lib, fn_name)
-    fn.restype = C.c_int
-    res = np.zeros((N_LCU, 85), dtype=S.ME_PU_RESULT_DTYPE)
-    rows = 34
-    chunks = [(r, r + 1) for r in range(rows)]
+    refsao = C.CDLL(os.path.join(ROOT, "oracle", "_ref", f"libsvtref_sao_{variant}.so"))
+    nthreads = os.cpu_count() or 1
+    frames = frames or max(8, min(nthreads, 128) // 8 * 8)
+    wl = Workload(RING, seed=0x5F7C0001)
+    pa = [S.HostPaPicture(l) for l in wl.luma]
+    yuv = [S.HostYuvPicture(wl.luma[i], wl.chroma[i][0], wl.chroma[i][1]) for i in range(RING)]
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    for f in (ref.svtref_me_picture_rows, ref.svtref_mc_batch, ref.svtref_tq_batch, ref.svtref_dlf_picture, refsao.svtref_sao_stats_picture,
+              refsao.svtref_sao_apply_picture):
+        f.restype = C.c_int
+    flags = (C.c_uint8 * 2)(1, 1)
 
-    def work(args):
-        cfg, r0, r1 = args
-        return fn(C.byref(cfg), C.byref(pics[1].struct), C.byref(pics[0].struct), C.byref(pics[2].struct), res.ctypes.data_as(C.c_void_p),
-                  None, None, None, C.c_int(1), C.c_int(r0), C.c_int(r1))
+    def frame(i):
+        k = i % RING
+        r0, r1 = wl.refs(i)
+        cfg = wl.me_cfg(i)
+        res = np.zeros((N_LCU, 85), dtype=S.ME_PU_RESULT_DTYPE)
+        assert ref.svtref_me_picture_rows(C.byref(cfg), C.byref(pa[k].struct), C.byref(pa[r0].struct), C.byref(pa[r1].struct), vp(res), None, None, None,
+                                          C.c_int(1), C.c_int(0), C.c_int(ROWS)) == 0
+        jobs = wl.mc_jobs(res)
+        pred = S.HostYuvPicture(np.zeros((H, W), np.uint8), np.zeros((H // 2, W // 2), np.uint8), np.zeros((H // 2, W // 2), np.uint8), replicate=False)
+        assert ref.svtref_mc_batch(S.yuv_array([yuv[r0], yuv[r1]]), C.c_int(2), vp(jobs), C.c_int(len(jobs)), C.byref(pred.struct), C.c_int(1)) == 0
+        coeff = S.HostCoeffPicture(W, H)
+        nz = np.zeros(len(wl.tq_jobs), np.uint32)
+        assert ref.svtref_tq_batch(C.byref(yuv[k].struct), C.byref(pred.struct), C.byref(pred.struct), C.byref(coeff.struct), vp(wl.tq_jobs),
+                                   C.c_int(len(wl.tq_jobs)), vp(nz), C.c_int(1), C.c_int(0), C.c_int(len(wl.tq_jobs))) == 0
+        if wl.tl(i) == 0:
+            assert ref.svtref_dlf_picture(C.byref(pred.struct), vp(wl.vbs), vp(wl.hbs), vp(wl.qp_array), C.byref(wl.dlf_prm), C.c_int(1)) == 0
+        stats = np.zeros((N_LCU, 3), dtype=S.SAO_STATS_DTYPE)
+        assert refsao.svtref_sao_stats_picture(C.byref(yuv[k].struct), C.byref(pred.struct), vp(stats), C.c_int(1)) == 0
+        if wl.tl(i) == 0:
+            assert refsao.svtref_sao_apply_picture(C.byref(pred.struct), vp(wl.sao_prm), flags, C.c_int(1)) == 0
+        return int(nz.sum())
 
     with ThreadPoolExecutor(nthreads) as ex:
-        cfg0, _ = cfg_for(0, S)
-        assert all(r == 0 for r in ex.map(work, [(cfg0, a, b) for a, b in chunks]))          # warm-up frame
-        cfgs = [cfg_for(s, S)[0] for s in range(steps)]
+        list(ex.map(frame, range(min(nthreads, 8))))                      # warm-up (page in libraries, touch buffers)
         t0 = time.perf_counter()
-        rc = list(ex.map(work, [(c, a, b) for c in cfgs for a, b in chunks]))                  # frames pipelined like the reference does
-        t_total = time.perf_counter() - t0
-        assert all(r == 0 for r in rc)
-    v = N_LCU * steps / t_total
-    return {"value": v, "unit": "CTU/s", "fps": v / N_LCU, "cores": min(nthreads, rows * steps), "kind": kind,
-            "sample": f"{steps} full 4K frames (after 1 warm-up) of the same stages: reference MotionEstimateLcu with its AVX2/AVX-512 kernels, one LCU row per task"}
+        list(ex.map(frame, range(frames)))
+        dt = time.perf_counter() - t0
+    v = N_LCU * frames / dt
+    return {"value": v, "unit": "CTU/s", "fps": v / N_LCU, "cores": min(nthreads, frames), "kind": "reference",
+            "sample": f"{frames} full 4K frames of the same stages and jobs through the reference's own functions (MotionEstimateLcu, "
+                      f"EncodePassInterPrediction, EstimateTransform/UnifiedQuantizeInvQuantize/EncodeInvTransform, LCU DLF drivers, SAO gather/apply; "
+                      f"{variant} rows), one frame per host thread, {nthreads} threads"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 16))
     t0 = time.perf_counter()
-    cb = cpu_reference(steps=steps, max_threads=None)
-    out = {"impl": "reference", "metric": "4Kp60 8-bit preset-M10 hot-path CTUs/sec (fps = value / 2040)", "value": cb["value"], "unit": "CTU/s",
-           "fps": cb["fps"], "n_gpus": world, "steps": steps, "warmup": 1, "ms_per_step": 1e3 * N_LCU / cb["value"], "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-           "config": {"workload": "configs[1]: 3840x2160 8-bit 4:2:0, preset M10 parameters, mini-GOP temporal layers [0,3,2,3,1,3,2,3], 2 reference lists",
-                      "stages": ["me_picture(HME-L0 one quadrant + 85-PU full-pel + integer bipred)"]},
+    cb = cpu_reference(frames=None)
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "CTU/s", "fps": cb["fps"], "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * N_LCU / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "u8", "data": "synthetic", "config": {"workload": WORKLOAD, "stages": STAGES},
            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "CTU/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "wall_s": time.perf_counter() - t0}
     print(json.dumps(out))

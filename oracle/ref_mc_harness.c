@@ -46,6 +46,7 @@ static void on_error(EB_PTR handle, EB_U32 code)
 int svtref_mc_batch(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs, int n_jobs,
                     const svtb200_yuv_picture *dst, int asm_mode)
 {
+    /* note: ASM_TYPES is a process global of the reference; concurrent callers must agree on asm_mode */
     ASM_TYPES = asm_mode ? EbHevcGetCpuAsmType() : 0;
     EbPictureBufferDesc_t *refDesc = (EbPictureBufferDesc_t *)calloc((size_t)n_refs, sizeof(*refDesc)), dstDesc;
     EbReferenceObject_t *refObj = (EbReferenceObject_t *)calloc((size_t)n_refs, sizeof(*refObj));

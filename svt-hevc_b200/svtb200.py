@@ -427,3 +427,38 @@ def sao_apply_picture(inp, out, params, sao_flag=(1, 1)):
     params = np.ascontiguousarray(params)
     flag = (C.c_uint8 * 2)(*sao_flag)
     check(lib().svtb200_sao_apply_picture(C.byref(inp.struct), C.byref(out.struct), _u8p(params), flag))
+
+
+# ================================================================================================
+# device-resident (_dev) entry points used by bench.py: every picture struct carries DEVICE pointers
+# ================================================================================================
+def make_yuv_struct(ptrs, strides, pad, width, height):
+    """YuvPicture over caller-owned (device or host) planes: ptrs = (y, cb, cr) addresses of the padded allocations."""
+    s = YuvPicture()
+    for name, ptr, st, p, w, h in (("y", ptrs[0], strides[0], pad, width, height), ("cb", ptrs[1], strides[1], pad // 2, width // 2, height // 2),
+                                   ("cr", ptrs[2], strides[2], pad // 2, width // 2, height // 2)):
+        pl = getattr(s, name)
+        pl.buf, pl.stride, pl.origin_x, pl.origin_y, pl.width, pl.height = ptr, st, p, p, w, h
+    return s
+
+
+def mc_batch_dev(ref_structs, jobs_ptr, n_jobs, dst_struct, stream=0):
+    arr = (YuvPicture * len(ref_structs))(*ref_structs)
+    check(lib().svtb200_mc_batch_dev(arr, C.c_int(len(ref_structs)), C.c_void_p(jobs_ptr), C.c_int(n_jobs), C.byref(dst_struct), C.c_void_p(stream)))
+
+
+def tq_batch_dev(src, pred, recon, coeff_struct, jobs_ptr, n_jobs, nz_ptr, stream=0):
+    check(lib().svtb200_tq_batch_dev(C.byref(src), C.byref(pred), C.byref(recon), C.byref(coeff_struct), C.c_void_p(jobs_ptr), C.c_int(n_jobs),
+                                     C.c_void_p(nz_ptr), C.c_void_p(stream)))
+
+
+def dlf_picture_dev(recon, vbs_ptr, hbs_ptr, qp_ptr, prm, stream=0):
+    check(lib().svtb200_dlf_picture_dev(C.byref(recon), C.c_void_p(vbs_ptr), C.c_void_p(hbs_ptr), C.c_void_p(qp_ptr), C.byref(prm), C.c_void_p(stream)))
+
+
+def sao_stats_picture_dev(src, recon, out_ptr, stream=0):
+    check(lib().svtb200_sao_stats_picture_dev(C.byref(src), C.byref(recon), C.c_void_p(out_ptr), C.c_void_p(stream)))
+
+
+def sao_apply_picture_dev(inp, out, prm_ptr, flags=(1, 1), stream=0):
+    check(lib().svtb200_sao_apply_picture_dev(C.byref(inp), C.byref(out), C.c_void_p(prm_ptr), (C.c_uint8 * 2)(*flags), C.c_void_p(stream)))
