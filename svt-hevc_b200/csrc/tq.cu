@@ -55,7 +55,10 @@ static void build_dct32(int8_t m[32][32])
 __device__ __forceinline__ int clip16i(int v) { return min(max(v, -32768), 32767); }
 
 // forward 1-D pass: out[k][r] = (s16)((sum_n M[k][n] * in[r][n] + off) >> shift) for k < kmax, r < rows
-__device__ void fwd_pass(const int16_t *in, int16_t *out, int N, int rows, int kmax, int shift, bool dst)
+// s_m: the 32x32 core matrix staged in shared memory.  Lanes of a warp either share the matrix row (forward pass: broadcast)
+// or walk along it (inverse pass: consecutive bytes), so neither pass serialises on the matrix the way divergent
+// __constant__ reads would.
+__device__ void fwd_pass(const int8_t *s_m, const int16_t *in, int16_t *out, int N, int rows, int kmax, int shift, bool dst)
 {
     const int off = 1 << (shift - 1), kstep = 32 / N;
     for (int i = threadIdx.x; i < kmax * rows; i += TQ_NT) {
@@ -66,11 +69,11 @@ __device__ void fwd_pass(const int16_t *in, int16_t *out, int N, int rows, int k
 #pragma unroll
             for (int n = 0; n < 4; ++n) acc += c_dst4[k][n] * x[n];
         } else if (N >= 16) {
-            const int8_t *m = c_dct32[k * kstep];
+            const int8_t *m = s_m + k * kstep * 32;
             if (k & 1) for (int n = 0; n < N / 2; ++n) acc += m[n] * (int)(short)(x[n] - x[N - 1 - n]);
             else for (int n = 0; n < N / 2; ++n) acc += m[n] * (int)(short)(x[n] + x[N - 1 - n]);
         } else {
-            const int8_t *m = c_dct32[k * kstep];
+            const int8_t *m = s_m + k * kstep * 32;
             for (int n = 0; n < N; ++n) acc += m[n] * x[n];
         }
         out[k * TP + r] = (int16_t)((acc + off) >> shift);
@@ -78,7 +81,7 @@ __device__ void fwd_pass(const int16_t *in, int16_t *out, int N, int rows, int k
 }
 
 // inverse 1-D pass: out[r][n] = clip16((sum_{k<kact} M[k][n] * in[k][r] + off) >> shift) for r < rmax, n < N
-__device__ void inv_pass(const int16_t *in, int16_t *out, int N, int rmax, int kact, int shift, bool dst)
+__device__ void inv_pass(const int8_t *s_m, const int16_t *in, int16_t *out, int N, int rmax, int kact, int shift, bool dst)
 {
     const int off = 1 << (shift - 1), kstep = 32 / N;
     for (int i = threadIdx.x; i < rmax * N; i += TQ_NT) {
@@ -88,7 +91,7 @@ __device__ void inv_pass(const int16_t *in, int16_t *out, int N, int rmax, int k
 #pragma unroll
             for (int k = 0; k < 4; ++k) acc += c_dst4[k][n] * in[k * TP + r];
         } else {
-            for (int k = 0; k < kact; ++k) acc += c_dct32[k * kstep][n] * in[k * TP + r];
+            for (int k = 0; k < kact; ++k) acc += s_m[k * kstep * 32 + n] * in[k * TP + r];
         }
         out[r * TP + n] = (int16_t)clip16i((acc + off) >> shift);
     }
@@ -98,7 +101,7 @@ __device__ __forceinline__ int ilog2d(int v) { return 31 - __clz(v); }
 
 // The whole chain for one TU held in shared memory.  s_a: residual in (pitch TP); returns nz.
 // On exit s_a holds the reconstructed residual (if nz && want_recon), s_q the quantised coefficients (act x act corner).
-__device__ uint32_t tq_chain(int16_t *s_a, int16_t *s_b, int16_t *s_q, uint32_t *s_cnt, const svtb200_tq_job &t, bool want_recon)
+__device__ uint32_t tq_chain(const int8_t *s_m, int16_t *s_a, int16_t *s_b, int16_t *s_q, uint32_t *s_cnt, const svtb200_tq_job &t, bool want_recon)
 {
     const int N = t.size, lg = ilog2d(N);
     const bool dst = t.dst4x4 != 0;
@@ -125,9 +128,9 @@ __device__ uint32_t tq_chain(int16_t *s_a, int16_t *s_b, int16_t *s_q, uint32_t 
     } else {
         int s1, s2;
         if (N == 32) { s1 = 6; s2 = 9; } else if (N == 16) { s1 = 4; s2 = 9; } else { s1 = lg - 1; s2 = lg + 6; }
-        fwd_pass(s_a, s_b, N, N, act, s1, dst);     // s_b[k][r]
+        fwd_pass(s_m, s_a, s_b, N, N, act, s1, dst);     // s_b[k][r]
         __syncthreads();
-        fwd_pass(s_b, s_a, N, act, act, s2, dst);   // s_a[v][u]
+        fwd_pass(s_m, s_b, s_a, N, act, act, s2, dst);   // s_a[v][u]
         __syncthreads();
     }
     // ---- quantise / dequantise (UnifiedQuantizeInvQuantize parameter derivation, Codec/EbTransforms.c:3094-3110) ----
@@ -191,13 +194,13 @@ __device__ uint32_t tq_chain(int16_t *s_a, int16_t *s_b, int16_t *s_q, uint32_t 
     }
     const uint32_t nz = *s_cnt;
     if (nz && want_recon) {
-        inv_pass(s_b, s_a, N, dst ? 4 : act, act, 7, dst);     // s_a[r][n], rows r >= act would be all zero
+        inv_pass(s_m, s_b, s_a, N, dst ? 4 : act, act, 7, dst);     // s_a[r][n], rows r >= act would be all zero
         __syncthreads();
         if (!dst && act < N) {   // zero rows act..N-1 of the intermediate so the second pass may stop at act as well
             for (int i = threadIdx.x; i < (N - act) * N; i += TQ_NT) s_a[(act + i / N) * TP + (i % N)] = 0;
             __syncthreads();
         }
-        inv_pass(s_a, s_b, N, N, dst ? 4 : act, 12, dst);      // s_b[y][x] residual
+        inv_pass(s_m, s_a, s_b, N, N, dst ? 4 : act, 12, dst);      // s_b[y][x] residual
         __syncthreads();
     }
     return nz;
@@ -207,8 +210,10 @@ __global__ void __launch_bounds__(TQ_NT) tq_batch_kernel(const __grid_constant__
 {
     __shared__ __align__(16) int16_t s_a[32 * TP], s_b[32 * TP], s_q[32 * TP];
     __shared__ uint32_t s_cnt;
+    __shared__ __align__(16) int8_t s_m[32 * 32];
     const int j = blockIdx.x;
     if (j >= A.n_jobs) return;
+    for (int i = threadIdx.x; i < 256; i += TQ_NT) ((uint32_t *)s_m)[i] = ((const uint32_t *)c_dct32)[i];
     const svtb200_tq_job t = A.jobs[j];
     const int N = t.size, pl = t.plane;
     const uint8_t *s = A.src.p[pl] + (size_t)(A.src.oy[pl] + t.y) * A.src.stride[pl] + A.src.ox[pl] + t.x;
@@ -220,7 +225,7 @@ __global__ void __launch_bounds__(TQ_NT) tq_batch_kernel(const __grid_constant__
     }
     __syncthreads();
     const bool want_recon = !(t.flags & SVTB200_TQ_SKIP_RECON);
-    const uint32_t nz = tq_chain(s_a, s_b, s_q, &s_cnt, t, want_recon);
+    const uint32_t nz = tq_chain(s_m, s_a, s_b, s_q, &s_cnt, t, want_recon);
     if (threadIdx.x == 0) A.nz[j] = nz;
     int16_t *co = A.coeff[pl] + (size_t)t.y * A.cstride[pl] + t.x;
     for (int i = threadIdx.x; i < N * N; i += TQ_NT) {
@@ -244,6 +249,8 @@ __global__ void __launch_bounds__(TQ_NT) tq_leaf_kernel(const LeafArgs L)
 {
     __shared__ __align__(16) int16_t s_a[32 * TP], s_b[32 * TP];
     __shared__ uint32_t s_cnt;
+    __shared__ __align__(16) int8_t s_m[32 * 32];
+    for (int i = threadIdx.x; i < 256; i += TQ_NT) ((uint32_t *)s_m)[i] = ((const uint32_t *)c_dct32)[i];
     const int N = L.N, lg = ilog2d(N);
     if (L.mode == 1) {
         if (threadIdx.x == 0) s_cnt = 0;
@@ -281,16 +288,16 @@ __global__ void __launch_bounds__(TQ_NT) tq_leaf_kernel(const LeafArgs L)
         const int act = N == 4 ? 4 : (N >> L.shape);
         int s1, s2;
         if (N == 32) { s1 = 6 + L.bit_inc; s2 = 9; } else if (N == 16) { s1 = 4 + L.bit_inc; s2 = 9; } else { s1 = lg - 1 + L.bit_inc; s2 = lg + 6; }
-        fwd_pass(s_a, s_b, N, N, act, s1, dst);
+        fwd_pass(s_m, s_a, s_b, N, N, act, s1, dst);
         __syncthreads();
-        fwd_pass(s_b, s_a, N, act, act, s2, dst);
+        fwd_pass(s_m, s_b, s_a, N, act, act, s2, dst);
         __syncthreads();
         for (int i = threadIdx.x; i < act * act; i += TQ_NT) L.out[(i / act) * L.ostride + (i % act)] = s_a[(i / act) * TP + (i % act)];
     } else {
         const bool dst = L.dst != 0;
-        inv_pass(s_a, s_b, N, N, N, 7, dst);
+        inv_pass(s_m, s_a, s_b, N, N, N, 7, dst);
         __syncthreads();
-        inv_pass(s_b, s_a, N, N, N, 12 - L.bit_inc, dst);
+        inv_pass(s_m, s_b, s_a, N, N, N, 12 - L.bit_inc, dst);
         __syncthreads();
         for (int i = threadIdx.x; i < N * N; i += TQ_NT) L.out[(i / N) * L.ostride + (i % N)] = s_a[(i / N) * TP + (i % N)];
     }
