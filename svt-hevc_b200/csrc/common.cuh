@@ -88,21 +88,19 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
 template <int NTHREADS>
 __device__ __forceinline__ int load_window_t(uint8_t *s_win, int wp, const uint8_t *g, int gstride, int wbytes, int rows)
 {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if ((gstride & 3) == 0) {
         const int a = (int)((uintptr_t)g & 3);
         const uint32_t *gw = (const uint32_t *)(g - a);
         const int nW = (a + wbytes + 3) >> 2, gs4 = gstride >> 2, wp4 = wp >> 2;
         uint32_t *sw = (uint32_t *)s_win;
-        for (int i = threadIdx.x; i < rows * nW; i += NTHREADS) {
-            const int r = i / nW, c = i - r * nW;
-            sw[r * wp4 + c] = __ldg(gw + (ptrdiff_t)r * gs4 + c);
-        }
+        // one warp per row, lanes along the row: coalesced, no integer division
+        for (int r = wid; r < rows; r += NTHREADS / 32)
+            for (int c = lane; c < nW; c += 32) sw[r * wp4 + c] = __ldg(gw + (ptrdiff_t)r * gs4 + c);
         return a;
     }
-    for (int i = threadIdx.x; i < rows * wbytes; i += NTHREADS) {
-        const int r = i / wbytes, c = i - r * wbytes;
-        s_win[r * wp + c] = __ldg(g + (ptrdiff_t)r * gstride + c);
-    }
+    for (int r = wid; r < rows; r += NTHREADS / 32)
+        for (int c = lane; c < wbytes; c += 32) s_win[r * wp + c] = __ldg(g + (ptrdiff_t)r * gstride + c);
     return 0;
 }
 __device__ __host__ __forceinline__ int win_pitch(int wbytes) { return ((wbytes + 3 + 3) & ~3) + 4; }

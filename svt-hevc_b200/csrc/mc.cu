@@ -151,6 +151,19 @@ template <int TAPS>
 __device__ void predict_tile(const uint8_t *rp0, int s0, int f0x, int f0y, const uint8_t *rp1, int s1, int f1x, int f1y, int tw, int th,
                              uint8_t *out, int ostride, uint8_t *s_win, int16_t *s_tmp, int16_t *s_raw0, int16_t *s_raw1)
 {
+    if ((f0x | f0y) == 0 && (!rp1 || (f1x | f1y) == 0)) {
+        // integer motion vectors (every layer-1..3 picture of M10 runs integer-pel ME): LumaInterpolationCopy (C_DEFAULT/EbMcp_C.c:221) /
+        // BiPredClippingOnTheFly (Codec/EbMcp.c:603): ((p0 << 6) + (p1 << 6) + 64) >> 7 == (p0 + p1 + 1) >> 1
+        for (int i = threadIdx.x; i < th * (tw >> 2); i += MC_NT) {
+            const int y = i / (tw >> 2), x = (i - y * (tw >> 2)) * 4;
+            uint32_t v = ld_u32_unaligned(rp0 + (size_t)y * s0 + x);
+            if (rp1) v = __vavgu4(v, ld_u32_unaligned(rp1 + (size_t)y * s1 + x));
+            uint8_t *o = out + (size_t)y * ostride + x;
+            if (((uintptr_t)o & 3) == 0) *(uint32_t *)o = v;
+            else { o[0] = (uint8_t)v; o[1] = (uint8_t)(v >> 8); o[2] = (uint8_t)(v >> 16); o[3] = (uint8_t)(v >> 24); }
+        }
+        return;
+    }
     if (!rp1) {
         interp_tile<TAPS>(rp0, s0, f0x, f0y, tw, th, s_win, s_tmp, out, ostride, nullptr);
         return;

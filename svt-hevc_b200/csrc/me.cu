@@ -76,6 +76,45 @@ __device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v
     return t;
 }
 
+// Fast path of sad_search for full-width HME level-0 blocks (16 x bh, pitch 16): each thread evaluates FOUR consecutive x
+// positions from one set of window words.  The window's byte misalignment is the same for every group (x0 is a multiple of
+// 4), so it is a template parameter and every funnel shift has a compile-time amount: per block row 6 window words + 4
+// source words feed 16 VABSDIFF4.
+template <int SH>
+__device__ __forceinline__ unsigned long long sad_search4_body(const uint32_t *blk32, int bh, const uint8_t *s_win, int wp, int a, int row_step,
+                                                               int saw, int sah)
+{
+    const int gpr = (saw + 3) >> 2, G = gpr * sah, wp4 = wp >> 2;
+    unsigned long long best = ~0ull;
+    for (int g = threadIdx.x; g < G; g += NT) {
+        const int y = g / gpr, x0 = (g - y * gpr) * 4;
+        const uint32_t *row = (const uint32_t *)(s_win + y * wp) + ((a + x0) >> 2);
+        uint32_t acc[4] = {0, 0, 0, 0};
+        for (int r = 0; r < bh; ++r, row += row_step * wp4) {
+            uint32_t w[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) w[j] = row[j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t s = blk32[r * 4 + j];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int t = SH * 8 + 8 * k, idx = t >> 5, sft = t & 31;
+                    const uint32_t v = sft ? __funnelshift_r(w[j + idx], w[j + idx + 1], sft) : w[j + idx];
+                    acc[k] += __vsadu4(v, s);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (x0 + k < saw && acc[k] < 0xffffffu) {
+                const unsigned long long key = ((unsigned long long)acc[k] << 32) | (uint32_t)(y * saw + x0 + k);
+                best = key < best ? key : best;
+            }
+    }
+    return best;
+}
+
 // ---- exhaustive block search (semantics of SadLoopKernel, C_DEFAULT/EbComputeSAD_C.c:165) -----------------
 // s_blk: bw x bh source block in shared memory (pitch bp, multiple of 4); window staged by load_window_t<NT>().
 // Block row r is compared with window row y + r*row_step.  Returns min SAD (start value 0xffffff) and the
@@ -85,6 +124,19 @@ __device__ void sad_search(const uint8_t *s_blk, int bp, int bw, int bh, const u
                            uint32_t &best_sad, int &best_x, int &best_y)
 {
     const int P = saw * sah;
+    if (bw == 16 && bp == 16 && P >= NT) {
+        unsigned long long b;
+        switch (a & 3) {
+        case 0: b = sad_search4_body<0>((const uint32_t *)s_blk, bh, s_win, wp, a, row_step, saw, sah); break;
+        case 1: b = sad_search4_body<1>((const uint32_t *)s_blk, bh, s_win, wp, a, row_step, saw, sah); break;
+        case 2: b = sad_search4_body<2>((const uint32_t *)s_blk, bh, s_win, wp, a, row_step, saw, sah); break;
+        default: b = sad_search4_body<3>((const uint32_t *)s_blk, bh, s_win, wp, a, row_step, saw, sah); break;
+        }
+        b = block_min_u64(b, s_red64);
+        if (b != ~0ull) { const int p = (int)(uint32_t)b; best_sad = (uint32_t)(b >> 32); best_y = p / saw; best_x = p - best_y * saw; }
+        else best_sad = 0xffffffu;
+        return;
+    }
     // split block rows over RS lanes when there are few positions (HME level 1/2 windows)
     int rs_log = 0;
     while ((P << rs_log) < NT && (1 << (rs_log + 1)) <= bh && rs_log < 5) ++rs_log;
@@ -220,29 +272,58 @@ __device__ __forceinline__ void pu_geom(int n, int &px, int &py, int &sz)
 // s_bsad/s_bmv: running best (n-order), updated with the reference's scan-order semantics:
 //   positions with x < (saw & ~7) follow the 8-position path (u16 16x16 partials, 64x64 uses '<='),
 //   the remainder follows the single-position path (strict '<' everywhere).
+// (1) of fullpel_search: 8x8 SADs (rows 0,2,4,6; Subsad8x8, C_DEFAULT/EbComputeSAD_C.c:214) of one chunk of search positions.
+// A work item = (8x8 block b, search row, group of 8 consecutive x positions): five window words per block row serve all 8
+// positions (the same sharing GetEightHorizontalSearchPointResults_8x8_16x16_PU gets from mpsadbw).  The byte misalignment
+// of the staged window is uniform, hence a template parameter.
+template <int SH>
+__device__ __forceinline__ void fullpel_sad8_chunk(const uint32_t *src32, const uint8_t *s_win, int wp, int a, int y0, int nrows, int xg0, int ngr,
+                                                   int gw, uint16_t *s_sad8)
+{
+    const int n_items = nrows * ngr * 64;
+    for (int i = threadIdx.x; i < n_items; i += NT) {
+        const int b = i & 63, t = i >> 6, yy = t / ngr, xgi = t - yy * ngr;
+        const int bx = b & 7, by = b >> 3;
+        const int x0 = (xg0 + xgi) * 8, y = y0 + yy;
+        uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t *row = (const uint32_t *)(s_win + (y + by * 8 + 2 * r) * wp) + ((a + x0 + bx * 8) >> 2);
+            uint32_t w[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) w[j] = row[j];
+            const uint32_t s0 = src32[(by * 8 + 2 * r) * 16 + bx * 2], s1 = src32[(by * 8 + 2 * r) * 16 + bx * 2 + 1];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int tt = SH * 8 + 8 * k, idx = tt >> 5, sft = tt & 31;
+                const uint32_t v0 = sft ? __funnelshift_r(w[idx], w[idx + 1], sft) : w[idx];
+                const uint32_t v1 = sft ? __funnelshift_r(w[idx + 1], w[idx + 2], sft) : w[idx + 1];
+                acc[k] += __vsadu4(v0, s0) + __vsadu4(v1, s1);
+            }
+        }
+        uint16_t *o = s_sad8 + (yy * gw + xgi * 8) * 64 + b;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k * 64] = (uint16_t)acc[k];
+    }
+}
+
 __device__ void fullpel_search(const uint8_t *s_src, const uint8_t *s_win, int wp, int a, int sox, int soy,
                                int saw, int sah, uint16_t *s_sad8 /*[CHUNK][64]*/, uint32_t *s_sum /*[CHUNK][21]*/,
                                uint32_t *s_bsad, uint32_t *s_bmv)
 {
-    const int P = saw * sah, w8 = saw & ~7;
+    const int w8 = saw & ~7;
     const uint32_t *src32 = (const uint32_t *)s_src;
-    for (int c0 = 0; c0 < P; c0 += CHUNK) {
-        const int cn = min(CHUNK, P - c0);
-        // (1) 8x8 SADs on rows 0,2,4,6 (Subsad8x8, C_DEFAULT/EbComputeSAD_C.c:214)
-        for (int i = threadIdx.x; i < cn * 64; i += NT) {
-            const int pc = i >> 6, b = i & 63, bx = b & 7, by = b >> 3;
-            const int p = c0 + pc, y = p / saw, x = p - y * saw;
-            const int col = a + x + bx * 8, wi = col >> 2, sh = (col & 3) * 8;
-            uint32_t sad = 0;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const uint32_t *row = (const uint32_t *)(s_win + (y + by * 8 + 2 * r) * wp) + wi;
-                const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];
-                const uint32_t *s = src32 + (by * 8 + 2 * r) * 16 + bx * 2;
-                sad += __vsadu4(__funnelshift_r(w0, w1, sh), s[0]);
-                sad += __vsadu4(__funnelshift_r(w1, w2, sh), s[1]);
-            }
-            s_sad8[pc * 64 + b] = (uint16_t)sad;
+    // chunks of <= CHUNK positions in scan order: whole search rows when a row has <= 8 groups of 8, else 8 groups of one row
+    const int ng_total = (saw + 7) >> 3;
+    const int ngr_chunk = ng_total < 8 ? ng_total : 8, rows_chunk = ng_total <= 8 ? max(1, 8 / ng_total) : 1;
+    for (int y0 = 0; y0 < sah; y0 += rows_chunk)
+      for (int xg0 = 0; xg0 < ng_total; xg0 += ngr_chunk) {
+        const int nrows = min(rows_chunk, sah - y0), ngr = min(ngr_chunk, ng_total - xg0), gw = ngr * 8, cn = nrows * gw;
+        switch (a & 3) {
+        case 0: fullpel_sad8_chunk<0>(src32, s_win, wp, a, y0, nrows, xg0, ngr, gw, s_sad8); break;
+        case 1: fullpel_sad8_chunk<1>(src32, s_win, wp, a, y0, nrows, xg0, ngr, gw, s_sad8); break;
+        case 2: fullpel_sad8_chunk<2>(src32, s_win, wp, a, y0, nrows, xg0, ngr, gw, s_sad8); break;
+        default: fullpel_sad8_chunk<3>(src32, s_win, wp, a, y0, nrows, xg0, ngr, gw, s_sad8); break;
         }
         __syncthreads();
         // (2) 16x16 partial sums in n-order
@@ -251,7 +332,7 @@ __device__ void fullpel_search(const uint8_t *s_src, const uint8_t *s_win, int w
             const int X = (Q & 1) * 2 + (s & 1), Y = (Q >> 1) * 2 + (s >> 1);
             const uint16_t *q = s_sad8 + pc * 64 + (Y * 2) * 8 + X * 2;
             uint32_t t = (uint32_t)q[0] + q[1] + q[8] + q[9];
-            const int p = c0 + pc, x = p % saw;
+            const int x = xg0 * 8 + pc % gw;
             if (x < w8) t = (uint16_t)t;     // EB_U16 sad16x16, C_DEFAULT/EbComputeSAD_C.c:259,337
             s_sum[pc * 21 + 5 + z] = t;
         }
@@ -278,20 +359,22 @@ __device__ void fullpel_search(const uint8_t *s_src, const uint8_t *s_win, int w
                 pu_geom(n, px, py, sz);
                 b8 = (py >> 3) * 8 + (px >> 3);
             }
-            for (int pc = 0; pc < cn; ++pc) {
-                const int p = c0 + pc, y = p / saw, x = p - y * saw;
-                const uint32_t v = 2u * (n >= 21 ? (uint32_t)s_sad8[pc * 64 + b8] : s_sum[pc * 21 + n]);
-                const bool take = (n == 0 && x < w8) ? (v <= bs) : (v < bs);
-                if (take) {
-                    bs = v;
-                    bm = ((uint32_t)(uint16_t)((y + soy) * 4) << 16) | (uint16_t)((x + sox) * 4);
+            for (int yy = 0; yy < nrows; ++yy)
+                for (int xx = 0; xx < gw; ++xx) {
+                    const int x = xg0 * 8 + xx, y = y0 + yy, pc = yy * gw + xx;
+                    if (x >= saw) break;
+                    const uint32_t v = 2u * (n >= 21 ? (uint32_t)s_sad8[pc * 64 + b8] : s_sum[pc * 21 + n]);
+                    const bool take = (n == 0 && x < w8) ? (v <= bs) : (v < bs);
+                    if (take) {
+                        bs = v;
+                        bm = ((uint32_t)(uint16_t)((y + soy) * 4) << 16) | (uint16_t)((x + sox) * 4);
+                    }
                 }
-            }
             s_bsad[n] = bs;
             s_bmv[n] = bm;
         }
         __syncthreads();
-    }
+      }
 }
 
 struct HmeRes { uint32_t sad; int x, y; };   // sad already doubled may exceed 24 bits -> keep 32
@@ -299,7 +382,7 @@ struct HmeRes { uint32_t sad; int x, y; };   // sad already doubled may exceed 2
 // ============================================================================================
 // Picture kernel: one CTA per LCU
 // ============================================================================================
-__global__ void __launch_bounds__(NT) me_picture_kernel(const __grid_constant__ MeArgs A)
+__global__ void __launch_bounds__(NT, 3) me_picture_kernel(const __grid_constant__ MeArgs A)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *s_src = smem;                                   // 64*64
@@ -888,7 +971,7 @@ int svtb200_FullPelSearch_LCU(const uint8_t *src, uint32_t srcStride, const uint
     SVTB200_CUDA_TRY(cudaMemcpyAsync((uint8_t *)d_r + mis, ref, rb, cudaMemcpyHostToDevice, c->stream));
     SVTB200_CUDA_TRY(cudaMemcpyAsync(d_bs, hb, 85 * 4, cudaMemcpyHostToDevice, c->stream));
     SVTB200_CUDA_TRY(cudaMemcpyAsync(d_bm, hb + 85, 85 * 4, cudaMemcpyHostToDevice, c->stream));
-    const size_t smem = 4096 + CHUNK * 64 * 2 + CHUNK * 21 * 4 + 172 * 4 + (size_t)win_pitch(saw + 63) * (sah + 63) + 16;
+    const size_t smem = 4096 + CHUNK * 64 * 2 + CHUNK * 21 * 4 + 172 * 4 + (size_t)win_pitch(saw + 63) * (sah + 63) + 64;
     static thread_local size_t smem_set = 48 * 1024;
     if (smem > smem_set) { SVTB200_CUDA_TRY(cudaFuncSetAttribute(fullpel_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
     fullpel_leaf_kernel<<<1, NT, smem, c->stream>>>((const uint8_t *)d_s, (int)srcStride, (const uint8_t *)d_r + mis, (int)refStride, (int)xSearchAreaOrigin,

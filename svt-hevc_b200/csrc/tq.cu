@@ -97,11 +97,64 @@ __device__ void inv_pass(const int8_t *s_m, const int16_t *in, int16_t *out, int
     }
 }
 
+
+__device__ __forceinline__ int dp2a_lo(uint32_t a_s16x2, uint32_t b_s8x4, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_s16x2), "r"(b_s8x4), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi(uint32_t a_s16x2, uint32_t b_s8x4, int c)
+{
+    int d;
+    asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_s16x2), "r"(b_s8x4), "r"(c));
+    return d;
+}
+
+// First butterfly stage of the 16/32-point forward passes, kept in 16 bits like PartialButterfly{16,32}Estimate:
+// out[r][0..N/2) = x[n] + x[N-1-n], out[r][N/2..N) = x[n] - x[N-1-n].
+__device__ void fold_rows(const int16_t *in, int16_t *out, int N, int rows)
+{
+    const int h = N >> 1;
+    for (int i = threadIdx.x; i < rows * h; i += TQ_NT) {
+        const int r = i / h, n = i - r * h;
+        const int a = in[r * TP + n], b = in[r * TP + N - 1 - n];
+        out[r * TP + n] = (int16_t)(a + b);
+        out[r * TP + h + n] = (int16_t)(a - b);
+    }
+}
+
+// Row-by-row dot products on DP2A:  C(i, j) = sum_{n < Nn} A[j][n] * B[i][n]   (A: s8 rows, pitch lda bytes; B: s16 rows, pitch TP)
+//   out[j * osj + i * osi] = CLIP ? clip16((C + off) >> shift) : (s16)((C + off) >> shift)
+// `odd_off`: when != 0, odd j read their B row at +odd_off samples (the odd half of a folded row).
+// Lanes run along i (B rows 17 words apart: conflict-free; the A row is a broadcast); each thread produces outputs j and j + J/2,
+// which share the B words: 4 shared-memory loads feed 4 DP2A = 8 MACs.
+template <bool CLIP>
+__device__ void rowdot(const int8_t *A, int lda, const int16_t *B, int odd_off, int I, int J, int Nn, int off, int shift, int16_t *out, int osi, int osj)
+{
+    const int Jh = J >> 1, n4 = Nn >> 2;
+    for (int it = threadIdx.x; it < I * Jh; it += TQ_NT) {
+        const int j = it / I, i = it - j * I;
+        const uint32_t *b = (const uint32_t *)(B + i * TP + ((j & 1) ? odd_off : 0));
+        const uint32_t *a0 = (const uint32_t *)(A + j * lda), *a1 = (const uint32_t *)(A + (j + Jh) * lda);
+        int c0 = 0, c1 = 0;
+        for (int q = 0; q < n4; ++q) {
+            const uint32_t b0 = b[2 * q], b1 = b[2 * q + 1], w0 = a0[q], w1 = a1[q];
+            c0 = dp2a_lo(b0, w0, c0); c0 = dp2a_hi(b1, w0, c0);
+            c1 = dp2a_lo(b0, w1, c1); c1 = dp2a_hi(b1, w1, c1);
+        }
+        c0 = (c0 + off) >> shift; c1 = (c1 + off) >> shift;
+        if (CLIP) { c0 = clip16i(c0); c1 = clip16i(c1); }
+        out[j * osj + i * osi] = (int16_t)c0;
+        out[(j + Jh) * osj + i * osi] = (int16_t)c1;
+    }
+}
+
 __device__ __forceinline__ int ilog2d(int v) { return 31 - __clz(v); }
 
 // The whole chain for one TU held in shared memory.  s_a: residual in (pitch TP); returns nz.
 // On exit s_a holds the reconstructed residual (if nz && want_recon), s_q the quantised coefficients (act x act corner).
-__device__ uint32_t tq_chain(const int8_t *s_m, int16_t *s_a, int16_t *s_b, int16_t *s_q, uint32_t *s_cnt, const svtb200_tq_job &t, bool want_recon)
+__device__ uint32_t tq_chain(const int8_t *s_m, const int8_t *s_mt, int16_t *s_a, int16_t *s_b, int16_t *s_q, uint32_t *s_cnt, const svtb200_tq_job &t, bool want_recon)
 {
     const int N = t.size, lg = ilog2d(N);
     const bool dst = t.dst4x4 != 0;
@@ -128,10 +181,21 @@ __device__ uint32_t tq_chain(const int8_t *s_m, int16_t *s_a, int16_t *s_b, int1
     } else {
         int s1, s2;
         if (N == 32) { s1 = 6; s2 = 9; } else if (N == 16) { s1 = 4; s2 = 9; } else { s1 = lg - 1; s2 = lg + 6; }
-        fwd_pass(s_m, s_a, s_b, N, N, act, s1, dst);     // s_b[k][r]
-        __syncthreads();
-        fwd_pass(s_m, s_b, s_a, N, act, act, s2, dst);   // s_a[v][u]
-        __syncthreads();
+        if (dst) {
+            fwd_pass(s_m, s_a, s_b, N, N, act, s1, dst);     // s_b[k][r]
+            __syncthreads();
+            fwd_pass(s_m, s_b, s_a, N, act, act, s2, dst);   // s_a[v][u]
+            __syncthreads();
+        } else {
+            const bool fold = N >= 16;
+            const int Nn = fold ? N >> 1 : N, lda = (32 / N) * 32;
+            if (fold) { fold_rows(s_a, s_q, N, N); __syncthreads(); }
+            rowdot<false>(s_m, lda, fold ? s_q : s_a, fold ? Nn : 0, N, act, Nn, 1 << (s1 - 1), s1, s_b, 1, TP);       // s_b[k][r]
+            __syncthreads();
+            if (fold) { fold_rows(s_b, s_q, N, act); __syncthreads(); }
+            rowdot<false>(s_m, lda, fold ? s_q : s_b, fold ? Nn : 0, act, act, Nn, 1 << (s2 - 1), s2, s_a, 1, TP);     // s_a[v][u]
+            __syncthreads();
+        }
     }
     // ---- quantise / dequantise (UnifiedQuantizeInvQuantize parameter derivation, Codec/EbTransforms.c:3094-3110) ----
     const int qpRem = t.qp % 6, qpPer = t.qp / 6;
@@ -144,6 +208,8 @@ __device__ uint32_t tq_chain(const int8_t *s_m, int16_t *s_a, int16_t *s_b, int1
     const int iqoff = 1 << (shiftNum - 1);
     const uint32_t qf = c_qfunc[qpRem];
     uint32_t mynz = 0;
+    const bool fast = !dst && !only_dc;          // DP2A inverse: dequantised coefficients are kept TRANSPOSED (s_b[u][v])
+    const int rsy = fast ? 1 : TP, rsx = fast ? TP : 1;
     for (int i = threadIdx.x; i < N * N; i += TQ_NT) {
         const int y = i / N, x = i - y * N;
         int16_t qv = 0, rv = 0;
@@ -156,7 +222,7 @@ __device__ uint32_t tq_chain(const int8_t *s_m, int16_t *s_a, int16_t *s_b, int1
             mynz += qv != 0;
         }
         s_q[y * TP + x] = qv;
-        s_b[y * TP + x] = rv;     // dequantised; zero outside the active corner (PfZeroOutUselessQuadrants)
+        s_b[y * rsy + x * rsx] = rv;     // dequantised; zero outside the active corner (PfZeroOutUselessQuadrants)
     }
     mynz = warp_sum(mynz);
     if ((threadIdx.x & 31) == 0 && mynz) atomicAdd(s_cnt, mynz);
@@ -168,11 +234,11 @@ __device__ uint32_t tq_chain(const int8_t *s_m, int16_t *s_a, int16_t *s_b, int1
             const int g = act / 4;
             for (int b = threadIdx.x; b < g * g; b += TQ_NT) {
                 const int by = b / g, bx = b - by * g;
-                int cnt = 0, loc = 0;
+                int cnt = 0, loc = 0, locb = 0;
                 for (int y = 0; y < 4; ++y)
                     for (int x = 0; x < 4; ++x)
-                        if (s_q[(by * 4 + y) * TP + bx * 4 + x]) { ++cnt; loc = (by * 4 + y) * TP + bx * 4 + x; }
-                if (cnt == 1 && loc != 0) { s_q[loc] = 0; s_b[loc] = 0; atomicSub(s_cnt, 1u); }
+                        if (s_q[(by * 4 + y) * TP + bx * 4 + x]) { ++cnt; loc = (by * 4 + y) * TP + bx * 4 + x; locb = (by * 4 + y) * rsy + (bx * 4 + x) * rsx; }
+                if (cnt == 1 && loc != 0) { s_q[loc] = 0; s_b[locb] = 0; atomicSub(s_cnt, 1u); }
             }
             __syncthreads();
         }
@@ -182,18 +248,24 @@ __device__ uint32_t tq_chain(const int8_t *s_m, int16_t *s_a, int16_t *s_b, int1
             const int16_t forced = (int16_t)((int16_t)(shiftedFFunc + iqoff) >> shiftNum);
             if (nz < 10 && (t.flags & SVTB200_TQ_CONTOURING) && t.slice_type == 2 && t.temporal_layer == 0 && t.plane == 0) {
                 const int loc = (act - 1) * TP + (act - 1);
-                if (s_q[loc] == 0) { ++nz; s_q[loc] = 1; s_b[loc] = forced; }
+                if (s_q[loc] == 0) { ++nz; s_q[loc] = 1; s_b[(act - 1) * rsy + (act - 1) * rsx] = forced; }
             }
             if (nz == 0 && (t.flags & SVTB200_TQ_ENABLE_CBF)) {
                 const int loc = (act - 2) * TP + (act - 1);
-                nz = 1; s_q[loc] = 1; s_b[loc] = forced;
+                nz = 1; s_q[loc] = 1; s_b[(act - 2) * rsy + (act - 1) * rsx] = forced;
             }
             *s_cnt = nz;
         }
         __syncthreads();
     }
     const uint32_t nz = *s_cnt;
-    if (nz && want_recon) {
+    if (nz && want_recon && fast) {
+        // pass 1: tmp(u, y) = sum_v M[v][y] * deq[v][u], written as s_a[y][u]; pass 2: res(y, x) = sum_u M[u][x] * tmp(u, y) -> s_b[y][x]
+        rowdot<true>(s_mt, 32, s_b, 0, act, N, act, 64, 7, s_a, 1, TP);
+        __syncthreads();
+        rowdot<true>(s_mt, 32, s_a, 0, N, N, act, 2048, 12, s_b, TP, 1);
+        __syncthreads();
+    } else if (nz && want_recon) {
         inv_pass(s_m, s_b, s_a, N, dst ? 4 : act, act, 7, dst);     // s_a[r][n], rows r >= act would be all zero
         __syncthreads();
         if (!dst && act < N) {   // zero rows act..N-1 of the intermediate so the second pass may stop at act as well
@@ -213,8 +285,14 @@ __global__ void __launch_bounds__(TQ_NT) tq_batch_kernel(const __grid_constant__
     __shared__ __align__(16) int8_t s_m[32 * 32];
     const int j = blockIdx.x;
     if (j >= A.n_jobs) return;
+    __shared__ __align__(16) int8_t s_mt[32 * 32];
     for (int i = threadIdx.x; i < 256; i += TQ_NT) ((uint32_t *)s_m)[i] = ((const uint32_t *)c_dct32)[i];
     const svtb200_tq_job t = A.jobs[j];
+    {   // transposed matrix of this TU size: s_mt[n][k] = M_N[k][n] = M32[k * 32 / N][n]
+        const int Nq = t.size, ks = 32 / Nq;
+        __syncthreads();
+        for (int i = threadIdx.x; i < Nq * Nq; i += TQ_NT) { const int k = i / Nq, n = i - k * Nq; s_mt[n * 32 + k] = s_m[k * ks * 32 + n]; }
+    }
     const int N = t.size, pl = t.plane;
     const uint8_t *s = A.src.p[pl] + (size_t)(A.src.oy[pl] + t.y) * A.src.stride[pl] + A.src.ox[pl] + t.x;
     const uint8_t *p = A.pred.p[pl] + (size_t)(A.pred.oy[pl] + t.y) * A.pred.stride[pl] + A.pred.ox[pl] + t.x;
@@ -225,7 +303,7 @@ __global__ void __launch_bounds__(TQ_NT) tq_batch_kernel(const __grid_constant__
     }
     __syncthreads();
     const bool want_recon = !(t.flags & SVTB200_TQ_SKIP_RECON);
-    const uint32_t nz = tq_chain(s_m, s_a, s_b, s_q, &s_cnt, t, want_recon);
+    const uint32_t nz = tq_chain(s_m, s_mt, s_a, s_b, s_q, &s_cnt, t, want_recon);
     if (threadIdx.x == 0) A.nz[j] = nz;
     int16_t *co = A.coeff[pl] + (size_t)t.y * A.cstride[pl] + t.x;
     for (int i = threadIdx.x; i < N * N; i += TQ_NT) {
