@@ -188,12 +188,9 @@ __global__ void __launch_bounds__(MC_NT) mc_batch_kernel(const __grid_constant__
     __shared__ __align__(16) uint8_t s_win[(TILE + 7) * (TILE + 7 + 11 + 4)];
     __shared__ __align__(16) int16_t s_tmp[(TILE + 7) * TILE];
     __shared__ __align__(16) int16_t s_raw[2][TILE * TILE];
-    const int job = blockIdx.x >> 2, tile = blockIdx.x & 3;
+    const int job = blockIdx.x;
     if (job >= A.n_jobs) return;
     const svtb200_mc_job q = A.jobs[job];
-    const int tx0 = (tile & 1) * TILE, ty0 = (tile >> 1) * TILE;
-    if (tx0 >= q.w || ty0 >= q.h) return;
-    const int tw = min(TILE, q.w - tx0), th = min(TILE, q.h - ty0);
     int px[2] = {0, 0}, py[2] = {0, 0};
     const YuvD *r[2] = {nullptr, nullptr};
 #pragma unroll
@@ -204,6 +201,10 @@ __global__ void __launch_bounds__(MC_NT) mc_batch_kernel(const __grid_constant__
         px[l] = (uint16_t)clampi((r[l]->ox - 71) << 2, (r[l]->w + r[l]->ox + 7) << 2, ((q.x + r[l]->ox) << 2) + q.mv[l][0]);
         py[l] = (uint16_t)clampi((r[l]->oy - 71) << 2, (r[l]->h + r[l]->oy + 7) << 2, ((q.y + r[l]->oy) << 2) + q.mv[l][1]);
     }
+  // one CTA per PU; PUs larger than 32x32 are walked tile by tile (an early-exit CTA per absent tile cost more than the copy itself)
+  for (int ty0 = 0; ty0 < q.h; ty0 += TILE)
+   for (int tx0 = 0; tx0 < q.w; tx0 += TILE) {
+    const int tw = min(TILE, q.w - tx0), th = min(TILE, q.h - ty0);
     const bool bi = q.dir == 2;
     const int l0 = bi ? 0 : q.dir, l1 = 1;
     // luma
@@ -225,6 +226,8 @@ __global__ void __launch_bounds__(MC_NT) mc_batch_kernel(const __grid_constant__
         predict_tile<4>(rp0, r[l0]->stride[pl], px[l0] & 7, py[l0] & 7, rp1, bi ? r[l1]->stride[pl] : 0, px[l1] & 7, py[l1] & 7, cw, ch, A.dst[pl] + cidx,
                         A.dstride[pl], s_win, s_tmp, s_raw[0], s_raw[1]);
     }
+    __syncthreads();
+   }
 }
 
 // leaf: one block (w x h, multiples of 4 x 2) through the same tile routine
@@ -271,7 +274,7 @@ static int launch_mc(const YuvD *d_refs, int n_refs, const svtb200_mc_job *d_job
     A.dstride[0] = (int)dst.y.stride; A.dstride[1] = (int)dst.cb.stride; A.dstride[2] = (int)dst.cr.stride;
     A.dox = dst.y.origin_x; A.doy = dst.y.origin_y;
     if (n_jobs == 0) return SVTB200_OK;
-    mc_batch_kernel<<<n_jobs * 4, MC_NT, 0, st>>>(A);
+    mc_batch_kernel<<<n_jobs, MC_NT, 0, st>>>(A);
     SVTB200_COUNT_LAUNCH();
     SVTB200_CUDA_TRY(cudaGetLastError());
     return SVTB200_OK;

@@ -349,29 +349,46 @@ __device__ void fullpel_search(const uint8_t *s_src, const uint8_t *s_win, int w
             s_sum[i * 21] = q[0] + q[1] + q[2] + q[3];
         }
         __syncthreads();
-        // (4) replay the best-update scan in order, one thread per PU
-        if (threadIdx.x < 85) {
-            const int n = threadIdx.x;
-            uint32_t bs = s_bsad[n], bm = s_bmv[n];
-            int b8 = 0;
-            if (n >= 21) {
-                int px, py, sz;
-                pu_geom(n, px, py, sz);
-                b8 = (py >> 3) * 8 + (px >> 3);
-            }
-            for (int yy = 0; yy < nrows; ++yy)
-                for (int xx = 0; xx < gw; ++xx) {
-                    const int x = xg0 * 8 + xx, y = y0 + yy, pc = yy * gw + xx;
-                    if (x >= saw) break;
-                    const uint32_t v = 2u * (n >= 21 ? (uint32_t)s_sad8[pc * 64 + b8] : s_sum[pc * 21 + n]);
-                    const bool take = (n == 0 && x < w8) ? (v <= bs) : (v < bs);
-                    if (take) {
-                        bs = v;
-                        bm = ((uint32_t)(uint16_t)((y + soy) * 4) << 16) | (uint16_t)((x + sox) * 4);
-                    }
+        // (4) best-update with the reference's scan-order semantics, one WARP per PU (lanes = the <= 64 positions of the chunk):
+        //     strict '<' PUs keep the FIRST minimum; the 64x64 PU uses '<=' on 8-position-path positions (x < w8), so among
+        //     positions tied at the minimum the LAST such position wins if it comes after the first tied one -- and it also
+        //     replaces an equal best carried in from earlier chunks (C_DEFAULT/EbComputeSAD_C.c:439 vs EbMeSadCalculation_C.c:109).
+        {
+            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+            for (int n = wid; n < 85; n += NT / 32) {
+                int b8 = 0;
+                if (n >= 21) {
+                    int px, py, sz;
+                    pu_geom(n, px, py, sz);
+                    b8 = (py >> 3) * 8 + (px >> 3);
                 }
-            s_bsad[n] = bs;
-            s_bmv[n] = bm;
+                uint32_t v[2];
+                bool valid[2], le[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int pc = lane + 32 * h, yy = pc / gw, xx = pc - yy * gw, x = xg0 * 8 + xx;
+                    valid[h] = pc < cn && x < saw;
+                    le[h] = valid[h] && n == 0 && x < w8;
+                    v[h] = valid[h] ? 2u * (n >= 21 ? (uint32_t)s_sad8[pc * 64 + b8] : s_sum[pc * 21 + n]) : 0xffffffffu;
+                }
+                const uint32_t m = __reduce_min_sync(0xffffffffu, min(v[0], v[1]));
+                const uint32_t bs = s_bsad[n];
+                const unsigned long long tied = (unsigned long long)__ballot_sync(0xffffffffu, valid[0] && v[0] == m) |
+                                                ((unsigned long long)__ballot_sync(0xffffffffu, valid[1] && v[1] == m) << 32);
+                const unsigned long long tied_le = (unsigned long long)__ballot_sync(0xffffffffu, le[0] && v[0] == m) |
+                                                   ((unsigned long long)__ballot_sync(0xffffffffu, le[1] && v[1] == m) << 32);
+                int win = -1;
+                if (tied) {
+                    const int t1 = __ffsll((long long)tied) - 1, L = tied_le ? 63 - __clzll((long long)tied_le) : -1;
+                    if (m < bs) win = L > t1 ? L : t1;
+                    else if (m == bs && L >= 0) win = L;
+                }
+                if (lane == 0 && win >= 0) {
+                    const int yy = win / gw, x = xg0 * 8 + (win - yy * gw), y = y0 + yy;
+                    s_bsad[n] = m;
+                    s_bmv[n] = ((uint32_t)(uint16_t)((y + soy) * 4) << 16) | (uint16_t)((x + sox) * 4);
+                }
+            }
         }
         __syncthreads();
       }

@@ -25,71 +25,102 @@ struct StatsArgs {
 
 __device__ __forceinline__ int sgn(int a, int b) { return (a > b) - (a < b); }
 
-__global__ void __launch_bounds__(256) sao_stats_kernel(const __grid_constant__ StatsArgs A)
+// sign(v - n) + sign(v - m) + 2 for four packed unsigned bytes: 0..4 per byte
+__device__ __forceinline__ uint32_t edge_idx4(uint32_t v, uint32_t n, uint32_t m)
 {
-    __shared__ __align__(16) uint8_t s_rec[64 * 68];
-    __shared__ int s_bo_diff[32];
-    __shared__ unsigned s_bo_cnt[32];
-    __shared__ int s_eo[8][40];      // per-warp [type][idx] diff (20) + count (20)
+    // __vcmp* give 0xff per true byte (= -1 as s8): sign(v - n) = (v > n) - (v < n) = lt_mask - gt_mask in byte arithmetic
+    const uint32_t sa = __vsub4(__vcmpltu4(v, n), __vcmpgtu4(v, n));
+    const uint32_t sb = __vsub4(__vcmpltu4(v, m), __vcmpgtu4(v, m));
+    return __vadd4(__vadd4(sa, sb), 0x02020202u);
+}
+__device__ __forceinline__ int dp4a_ss(uint32_t a_s8x4, uint32_t b_s8x4, int c)
+{
+    int d;
+    asm("dp4a.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_s8x4), "r"(b_s8x4), "r"(c));
+    return d;
+}
+
+constexpr int ST_NT = 128;
+__global__ void __launch_bounds__(ST_NT) sao_stats_kernel(const __grid_constant__ StatsArgs A)
+{
+    // reconstructed block with a one-word margin on the left (column 4 = block x 0); pitch 72 bytes = 18 words
+    __shared__ __align__(16) uint8_t s_rec[64 * 72];
+    // thread-private band histograms: word = (count << 16) + sum(diff); pitch 33 keeps the 32 lanes of a warp on distinct banks
+    __shared__ int s_bo[ST_NT * 33];
+    __shared__ int s_eo[ST_NT / 32][32];
     const int job = blockIdx.x, lcu = job / 3, c = job - lcu * 3, sh = c ? 1 : 0;
     const int lx = lcu % A.cols, ly = lcu / A.cols;
     const int ox = (lx * 64) >> sh, oy = (ly * 64) >> sh;
     const int lw = min(64, A.W - lx * 64) >> sh, lh = min(64, A.H - ly * 64) >> sh;
     const uint8_t *r = A.rec[c].p + (size_t)oy * A.rec[c].stride + ox, *s = A.src[c].p + (size_t)oy * A.src[c].stride + ox;
-    for (int i = threadIdx.x; i < lh * (lw >> 2); i += 256) {
-        const int y = i / (lw >> 2), x4 = i - y * (lw >> 2);
-        ((uint32_t *)(s_rec + y * 68))[x4] = *(const uint32_t *)(r + (size_t)y * A.rec[c].stride + 4 * x4);   // block origins are 4-aligned
+    const int wpr = lw >> 2;
+    for (int i = threadIdx.x; i < lh * wpr; i += ST_NT) {
+        const int y = i / wpr, x4 = i - y * wpr;
+        ((uint32_t *)(s_rec + y * 72))[1 + x4] = *(const uint32_t *)(r + (size_t)y * A.rec[c].stride + 4 * x4);   // block origins are 4-aligned
     }
-    if (threadIdx.x < 32) { s_bo_diff[threadIdx.x] = 0; s_bo_cnt[threadIdx.x] = 0; }
+    for (int k = 0; k < 33; ++k) s_bo[threadIdx.x * 33 + k] = 0;
     __syncthreads();
-    int ed[4][5], ec[4][5];
+    int ed[4][4], ec[4][4];     // [EO type][category 0,1,3,4 -> 0..3]
 #pragma unroll
     for (int t = 0; t < 4; ++t)
 #pragma unroll
-        for (int k = 0; k < 5; ++k) { ed[t][k] = 0; ec[t][k] = 0; }
-    const int iw = lw - 2, n = iw * (lh - 2);
-    const int iters = (n + 255) / 256;
-    for (int it = 0; it < iters; ++it) {
-        const int i = it * 256 + threadIdx.x;
-        const bool act = i < n;
-        int band = 32, d = 0;   // band 32 = inactive lane: never matches a real band
-        if (act) {
-            const int y = 1 + i / iw, x = 1 + i % iw;
-            const uint8_t *q = s_rec + y * 68 + x;
-            const int v = q[0];
-            d = (int)s[(size_t)y * A.src[c].stride + x] - v;
-            d = min(max(d, -128), 127);                         // clipToSigned8Bit
-            band = v >> 3;
-            const int e[4] = {sgn(v, q[-1]) + sgn(v, q[1]) + 2, sgn(v, q[-68]) + sgn(v, q[68]) + 2, sgn(v, q[-69]) + sgn(v, q[69]) + 2,
-                              sgn(v, q[-67]) + sgn(v, q[67]) + 2};
+        for (int k = 0; k < 4; ++k) { ed[t][k] = 0; ec[t][k] = 0; }
+    int *my_bo = s_bo + threadIdx.x * 33;
+    const int n_items = (lh - 2) * wpr;
+    for (int i = threadIdx.x; i < n_items; i += ST_NT) {
+        const int y = 1 + i / wpr, xw = i % wpr;
+        const uint32_t *row = (const uint32_t *)(s_rec + y * 72) + 1 + xw;
+        const uint32_t up0 = row[-19], up1 = row[-18], up2 = row[-17], c0 = row[-1], v = row[0], c2 = row[1], dn0 = row[17], dn1 = row[18], dn2 = row[19];
+        const uint32_t sv = *(const uint32_t *)(s + (size_t)y * A.src[c].stride + 4 * xw);
+        // valid bytes: the 62x62 interior (GatherSaoStatisticsLcuLossy_62x62 starts at +1,+1 and stops one short)
+        uint32_t vm = 0xffffffffu;
+        if (xw == 0) vm &= 0xffffff00u;
+        if (xw == wpr - 1) vm &= 0x00ffffffu;
+        // diff = clipToSigned8Bit(src - rec), packed s8
+        const uint32_t dpos = __vminu4(__vsubus4(sv, v), 0x7f7f7f7fu), dneg = __vminu4(__vsubus4(v, sv), 0x80808080u);
+        const uint32_t d = __vsub4(dpos, dneg) & vm;
+        const uint32_t L = __funnelshift_r(c0, v, 24), R = __funnelshift_r(v, c2, 8);
+        const uint32_t UL = __funnelshift_r(up0, up1, 24), UR = __funnelshift_r(up1, up2, 8), DL = __funnelshift_r(dn0, dn1, 24), DR = __funnelshift_r(dn1, dn2, 8);
+        const uint32_t e[4] = {edge_idx4(v, L, R), edge_idx4(v, up1, dn1), edge_idx4(v, UL, DR), edge_idx4(v, UR, DL)};   // EO-0, 90, 135, 45
 #pragma unroll
-            for (int t = 0; t < 4; ++t)
+        for (int t = 0; t < 4; ++t)
 #pragma unroll
-                for (int k = 0; k < 5; ++k) { const bool hit = e[t] == k; ed[t][k] += hit ? d : 0; ec[t][k] += hit; }
-        }
-        // warp-aggregated band histogram: one shared-memory atomic per distinct band per warp
-        const unsigned peers = __match_any_sync(0xffffffffu, band);
-        const int sum = __reduce_add_sync(peers, d);
-        if (act && (threadIdx.x & 31) == __ffs(peers) - 1) { atomicAdd(&s_bo_diff[band], sum); atomicAdd(&s_bo_cnt[band], (unsigned)__popc(peers)); }
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t cat = (k < 2 ? k : k + 1) * 0x01010101u;
+                const uint32_t hit = __vcmpeq4(e[t], cat) & vm;
+                ed[t][k] = dp4a_ss(d & hit, 0x01010101u, ed[t][k]);
+                ec[t][k] += __popc(hit) >> 3;
+            }
+        // band offset: private histogram, no atomics
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if ((vm >> (8 * b)) & 1) my_bo[(v >> (8 * b + 3)) & 31] += 65536 + (int)(signed char)(d >> (8 * b));
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
     for (int t = 0; t < 4; ++t)
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
+        for (int k = 0; k < 4; ++k) {
             const int dsum = __reduce_add_sync(0xffffffffu, ed[t][k]), csum = __reduce_add_sync(0xffffffffu, ec[t][k]);
-            if (lane == 0) { s_eo[wid][t * 5 + k] = dsum; s_eo[wid][20 + t * 5 + k] = csum; }
+            if (lane == 0) { s_eo[wid][t * 4 + k] = dsum; s_eo[wid][16 + t * 4 + k] = csum; }
         }
     __syncthreads();
     svtb200_sao_stats *o = A.out + job;
-    if (threadIdx.x < 32) { o->bo_diff[threadIdx.x] = s_bo_diff[threadIdx.x]; o->bo_count[threadIdx.x] = (uint16_t)s_bo_cnt[threadIdx.x]; }
-    if (threadIdx.x < 20) {
-        // categories compacted like the reference: slot 2 <- raw 3, slot 3 <- raw 4, slot 4 scratch (we write 0)
-        const int t = threadIdx.x / 5, k = threadIdx.x % 5;
-        const int rawk = k < 2 ? k : k + 1;
+    if (threadIdx.x < 32) {
+        int dsum = 0, csum = 0;
+        for (int th = 0; th < ST_NT; ++th) {
+            const int w = s_bo[th * 33 + threadIdx.x], dd = (int)(short)(w & 0xffff);   // |sum(diff)| < 2^15 per thread
+            dsum += dd;
+            csum += (w - dd) >> 16;
+        }
+        o->bo_diff[threadIdx.x] = dsum;
+        o->bo_count[threadIdx.x] = (uint16_t)csum;
+    } else if (threadIdx.x < 52) {
+        // categories compacted like the reference: slots 0..3 <- raw 0,1,3,4; slot 4 scratch (we write 0)
+        const int q = threadIdx.x - 32, t = q / 5, k = q % 5;
         int dsum = 0, csum = 0;
         if (k < 4)
-            for (int w = 0; w < 8; ++w) { dsum += s_eo[w][t * 5 + rawk]; csum += s_eo[w][20 + t * 5 + rawk]; }
+            for (int w = 0; w < ST_NT / 32; ++w) { dsum += s_eo[w][t * 4 + k]; csum += s_eo[w][16 + t * 4 + k]; }
         o->eo_diff[t][k] = dsum;
         o->eo_count[t][k] = (uint16_t)csum;
     }
@@ -186,11 +217,11 @@ int svtb200_sao_stats_picture_dev(const svtb200_yuv_picture *src, const svtb200_
         const svtb200_plane *s = plane_of(src, k), *r = plane_of(recon, k);
         A.src[k] = {s->buf + (size_t)s->origin_y * s->stride + s->origin_x, (int)s->stride};
         A.rec[k] = {r->buf + (size_t)r->origin_y * r->stride + r->origin_x, (int)r->stride};
-        if (((uintptr_t)A.rec[k].p) & 3) { set_error("sao_stats_picture: reconstruction interior must be 4-byte aligned"); return SVTB200_ERR_BAD_ARG; }
+        if ((((uintptr_t)A.rec[k].p) & 3) || (((uintptr_t)A.src[k].p) & 3)) { set_error("sao_stats_picture: plane interiors must be 4-byte aligned"); return SVTB200_ERR_BAD_ARG; }
     }
     A.out = out_dev; A.W = recon->y.width; A.H = recon->y.height; A.cols = (A.W + 63) / 64;
     const int n = A.cols * ((A.H + 63) / 64) * 3;
-    sao_stats_kernel<<<n, 256, 0, (cudaStream_t)cuda_stream>>>(A);
+    sao_stats_kernel<<<n, ST_NT, 0, (cudaStream_t)cuda_stream>>>(A);
     SVTB200_COUNT_LAUNCH();
     SVTB200_CUDA_TRY(cudaGetLastError());
     return SVTB200_OK;
