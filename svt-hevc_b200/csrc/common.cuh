@@ -82,28 +82,53 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
     return v;
 }
 // ---- window staging ------------------------------------------------------------------------
-// Copies `rows` rows of `wbytes` bytes starting at global address g (row pitch gstride) into shared memory
-// with row pitch wp (multiple of 4, >= wbytes + 8).  Word-granular and coalesced when the plane pitch is a
-// multiple of 4: the global byte misalignment `a` (0..3) is preserved, i.e. window byte x lives at column a + x.
+// Copies `rows` rows of `wbytes` bytes starting at global address g (row pitch gstride) into shared memory with row pitch
+// wp = win_pitch(wbytes) (s_win 16-byte aligned).  The global byte misalignment `a` is preserved: window byte x lives at
+// column a + x, and a is returned (a & 3 is what the funnel-shift consumers specialise on).
+//   pitch multiple of 16 : 128-bit loads from the 16-byte-aligned start, a in 0..15   (device-resident pictures)
+//   pitch multiple of 4  : 32-bit loads, a in 0..3                                     (host pictures copied as they are)
+//   otherwise            : byte loads, a = 0
+// A warp covers 32 / P rows per pass, P = the power of two >= the vectors per row, so narrow windows still use most lanes.
 template <int NTHREADS>
 __device__ __forceinline__ int load_window_t(uint8_t *s_win, int wp, const uint8_t *g, int gstride, int wbytes, int rows)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if ((gstride & 15) == 0) {
+        const int a = (int)((uintptr_t)g & 15);
+        const uint4 *gv = (const uint4 *)(g - a);
+        const int nV = (a + wbytes + 15) >> 4, gs = gstride >> 4, ws = wp >> 4;
+        int P = 1;
+        while (P < nV) P <<= 1;
+        uint4 *sv = (uint4 *)s_win;
+        if (P <= 32) {
+            const int rpw = 32 / P, sub = lane / P, c = lane & (P - 1);
+            for (int r = wid * rpw + sub; r < rows; r += (NTHREADS / 32) * rpw)
+                if (c < nV) sv[r * ws + c] = __ldg(gv + (ptrdiff_t)r * gs + c);
+        } else {
+            for (int r = wid; r < rows; r += NTHREADS / 32)
+                for (int c = lane; c < nV; c += 32) sv[r * ws + c] = __ldg(gv + (ptrdiff_t)r * gs + c);
+        }
+        return a;
+    }
     if ((gstride & 3) == 0) {
         const int a = (int)((uintptr_t)g & 3);
         const uint32_t *gw = (const uint32_t *)(g - a);
         const int nW = (a + wbytes + 3) >> 2, gs4 = gstride >> 2, wp4 = wp >> 2;
         uint32_t *sw = (uint32_t *)s_win;
-        // one warp per row, lanes along the row: coalesced, no integer division
-        for (int r = wid; r < rows; r += NTHREADS / 32)
-            for (int c = lane; c < nW; c += 32) sw[r * wp4 + c] = __ldg(gw + (ptrdiff_t)r * gs4 + c);
+        int P = 1;
+        while (P < nW && P < 32) P <<= 1;
+        const int rpw = 32 / P, sub = lane / P, c0 = lane & (P - 1);
+        for (int r = wid * rpw + sub; r < rows; r += (NTHREADS / 32) * rpw)
+            for (int c = c0; c < nW; c += P) sw[r * wp4 + c] = __ldg(gw + (ptrdiff_t)r * gs4 + c);
         return a;
     }
     for (int r = wid; r < rows; r += NTHREADS / 32)
         for (int c = lane; c < wbytes; c += 32) s_win[r * wp + c] = __ldg(g + (ptrdiff_t)r * gstride + c);
     return 0;
 }
-__device__ __host__ __forceinline__ int win_pitch(int wbytes) { return ((wbytes + 3 + 3) & ~3) + 4; }
+// row pitch of a staged window: room for the 0..15 byte misalignment, the 16-byte read granularity and the few bytes the
+// funnel-shift consumers read past the last needed byte
+__device__ __host__ __forceinline__ int win_pitch(int wbytes) { return ((wbytes + 15 + 15) & ~15) + 16; }
 #endif
 
 }  // namespace svtb200

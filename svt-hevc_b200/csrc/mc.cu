@@ -185,7 +185,7 @@ __device__ void predict_tile(const uint8_t *rp0, int s0, int f0x, int f0y, const
 
 __global__ void __launch_bounds__(MC_NT) mc_batch_kernel(const __grid_constant__ McArgs A)
 {
-    __shared__ __align__(16) uint8_t s_win[(TILE + 7) * (TILE + 7 + 11 + 4)];
+    __shared__ __align__(16) uint8_t s_win[(TILE + 7) * 96];   // win_pitch(39) = 80
     __shared__ __align__(16) int16_t s_tmp[(TILE + 7) * TILE];
     __shared__ __align__(16) int16_t s_raw[2][TILE * TILE];
     const int job = blockIdx.x;
@@ -235,7 +235,7 @@ template <int TAPS>
 __global__ void __launch_bounds__(MC_NT) mc_leaf_kernel(const uint8_t *r0, int s0, int f0x, int f0y, const uint8_t *r1, int s1, int f1x, int f1y,
                                                         uint8_t *dst, int ds, int w, int h)
 {
-    __shared__ __align__(16) uint8_t s_win[(TILE + 7) * (TILE + 7 + 11 + 4)];
+    __shared__ __align__(16) uint8_t s_win[(TILE + 7) * 96];   // win_pitch(39) = 80
     __shared__ __align__(16) int16_t s_tmp[(TILE + 7) * TILE];
     __shared__ __align__(16) int16_t s_raw[2][TILE * TILE];
     for (int ty0 = 0; ty0 < h; ty0 += TILE)

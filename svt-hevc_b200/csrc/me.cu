@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(NT, 3) me_picture_kernel(const __grid_constant
     uint32_t *s_bi = s_bmv + 170;                            // [85]
     uint32_t *s_red32 = s_bi + 85 + 1;                       // [8*6]
     unsigned long long *s_red64 = (unsigned long long *)(s_red32 + 48);   // [8]
-    uint8_t *s_win = (uint8_t *)(s_red64 + 8);
+    uint8_t *s_win = (uint8_t *)(((uintptr_t)(s_red64 + 8) + 15) & ~(uintptr_t)15);
 
     const svtb200_me_config &cfg = A.cfg;
     const int lcu = blockIdx.x, lx = lcu % A.cols, ly = lcu / A.cols;
@@ -707,7 +707,7 @@ static int me_window_bytes(const svtb200_me_config &c)
     int best = 0;
     auto upd = [&](int saw, int sah, int bw, int bh_rows_span) {
         const int wb = saw + bw - 1, rows = sah + bh_rows_span;
-        const int wp = ((wb + 6) & ~3) + 4;
+        const int wp = win_pitch(wb);
         if (wp * rows > best) best = wp * rows;
     };
     if (c.enable_hme && c.enable_hme_l0) {
@@ -747,7 +747,7 @@ static int launch_me(const svtb200_me_config *cfg, const PlaneD src[3], const Pl
     A.results = results; A.best_sad = bs; A.best_mv = bm; A.rc = rc;
     A.cols = (cfg->pic_width + 63) / 64; A.rows = (cfg->pic_height + 63) / 64;
     A.win_bytes = me_window_bytes(*cfg);
-    const size_t smem = me_fixed_smem() + (size_t)A.win_bytes + 64;
+    const size_t smem = me_fixed_smem() + (size_t)A.win_bytes + 96;
     if (smem > 227 * 1024) { set_error("me: search window needs %zu B of shared memory (> 227 KB)", smem); return SVTB200_ERR_UNSUPPORTED; }
     static thread_local size_t smem_set = 0;
     if (smem > smem_set) {
@@ -770,7 +770,7 @@ __global__ void __launch_bounds__(NT) sad_loop_leaf_kernel(const uint8_t *src, i
     unsigned long long *s_red64 = (unsigned long long *)smem;
     uint8_t *s_blk = smem + 64;
     const int bp = (w + 3 + 3) & ~3;
-    uint8_t *s_win = s_blk + ((bp * h + 15) & ~15);
+    uint8_t *s_win = s_blk + ((bp * h + 15) & ~15);   // smem base and the 64-byte header keep this 16-byte aligned
     for (int i = threadIdx.x; i < bp * h; i += NT) { const int r = i / bp, c = i - r * bp; s_blk[i] = c < w ? src[r * sstride + c] : 0; }
     const int wbytes = saw + w - 1, wrows = sah + (h - 1) * row_step, wp = win_pitch(wbytes);
     const int a = load_window_t<NT>(s_win, wp, ref, raw, wbytes, wrows);
@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(NT) fullpel_leaf_kernel(const uint8_t *src, in
     uint32_t *s_sum = (uint32_t *)(s_sad8 + CHUNK * 64);
     uint32_t *s_bsad = s_sum + CHUNK * 21;
     uint32_t *s_bmv = s_bsad + 85;
-    uint8_t *s_win = (uint8_t *)(s_bmv + 85 + 2);
+    uint8_t *s_win = (uint8_t *)(((uintptr_t)(s_bmv + 85 + 2) + 15) & ~(uintptr_t)15);
     for (int i = threadIdx.x; i < 4096; i += NT) s_src[i] = src[(i >> 6) * ss + (i & 63)];
     if (threadIdx.x < 85) { s_bsad[threadIdx.x] = bsad[threadIdx.x]; s_bmv[threadIdx.x] = bmv[threadIdx.x]; }
     const int wbytes = saw + 63, wrows = sah + 63, wp = win_pitch(wbytes);
@@ -906,7 +906,7 @@ int svtb200_SadLoopKernel(const uint8_t *src, uint32_t srcStride, const uint8_t 
     const int wrows = sah + (int)(height - 1) * row_step;
     const size_t ref_bytes = (size_t)(wrows - 1) * srcStrideRaw + saw + width - 1;
     const int wp = win_pitch(saw + (int)width - 1), bp = ((int)width + 6) & ~3;
-    const size_t smem = 64 + (((size_t)bp * height + 15) & ~15) + (size_t)wp * wrows + 16;
+    const size_t smem = 64 + (((size_t)bp * height + 15) & ~15) + (size_t)wp * wrows + 96;
     if (smem > 227 * 1024) { set_error("SadLoopKernel: window of %zu B exceeds shared memory", smem); return SVTB200_ERR_UNSUPPORTED; }
     void *d_src, *d_ref, *d_out, *h_out;
     // keep the reference region's byte alignment so that the window loader's word path is exercised as in the picture kernel
@@ -988,7 +988,7 @@ int svtb200_FullPelSearch_LCU(const uint8_t *src, uint32_t srcStride, const uint
     SVTB200_CUDA_TRY(cudaMemcpyAsync((uint8_t *)d_r + mis, ref, rb, cudaMemcpyHostToDevice, c->stream));
     SVTB200_CUDA_TRY(cudaMemcpyAsync(d_bs, hb, 85 * 4, cudaMemcpyHostToDevice, c->stream));
     SVTB200_CUDA_TRY(cudaMemcpyAsync(d_bm, hb + 85, 85 * 4, cudaMemcpyHostToDevice, c->stream));
-    const size_t smem = 4096 + CHUNK * 64 * 2 + CHUNK * 21 * 4 + 172 * 4 + (size_t)win_pitch(saw + 63) * (sah + 63) + 64;
+    const size_t smem = 4096 + CHUNK * 64 * 2 + CHUNK * 21 * 4 + 172 * 4 + (size_t)win_pitch(saw + 63) * (sah + 63) + 96;
     static thread_local size_t smem_set = 48 * 1024;
     if (smem > smem_set) { SVTB200_CUDA_TRY(cudaFuncSetAttribute(fullpel_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
     fullpel_leaf_kernel<<<1, NT, smem, c->stream>>>((const uint8_t *)d_s, (int)srcStride, (const uint8_t *)d_r + mis, (int)refStride, (int)xSearchAreaOrigin,

@@ -75,7 +75,7 @@ int svtb200_pa_picture_create(uint16_t width, uint16_t height, svtb200_pa_pictur
         p.width = (uint16_t)((width + (1 << sh[k]) - 1) >> sh[k]);
         p.height = (uint16_t)((height + (1 << sh[k]) - 1) >> sh[k]);
         p.origin_x = p.origin_y = (uint16_t)pads[k];
-        p.stride = (uint32_t)align_up((size_t)p.width + 2 * pads[k], 4);
+        p.stride = (uint32_t)align_up((size_t)p.width + 2 * pads[k], 16);   // 16-byte pitch: windows are staged with 128-bit loads
         void *d = nullptr;
         SVTB200_CUDA_TRY(cudaMalloc(&d, (size_t)p.stride * (p.height + 2 * pads[k]) + 64));
         p.buf = (uint8_t *)d;
