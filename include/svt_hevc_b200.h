@@ -346,6 +346,39 @@ int svtb200_sao_apply_picture_dev(const svtb200_yuv_picture *in, const svtb200_y
                                   const uint8_t sao_flag[2], void *cuda_stream);
 
 /* ---------------------------------------------------------------------------------------
+ * 10-bit sample packing.  Same argument order as the reference typedefs in
+ * Codec/EbPackUnPack.h (EB_ENC_Pack2D_TYPE :17, COMPPack_TYPE :52, EB_ENC_UnPack2D_TYPE :70,
+ * EB_ENC_UnPack8BitData_TYPE :136, EB_ENC_UnpackAvg_TYPE :101); strides in elements; HOST pointers.
+ *   msbPack2D        out16 = (in8 << 2) | ((inn >> 6) & 3)                  C_DEFAULT/EbPackUnPack_C.c:12
+ *   CompressedPackmsb same, inn holds four 2-bit pels per byte, first pel in bits 7:6 (:44); width % 4 == 0
+ *   CPack            unpacked 2-bit plane -> compressed 2-bit plane (:93); width % 4 == 0; localCache unused
+ *   msbUnPack2D      out8 = in16 >> 2, outn = (u8)(in16 << 6) (:130);  UnPack8BitData[SafeSub]: out8 only (:153,203)
+ *   UnpackAvg[SafeSub] dst = ((u8)(l0 >> 2) + (u8)(l1 >> 2) + 1) >> 1 (:174,226)
+ * svtb200_pack_plane_dev runs one of them on DEVICE planes (op = SVTB200_PACK_*; unused planes NULL / 0):
+ *   in0 / in1: the two inputs in the order of the host signature, out0 / out1: the outputs.
+ * ------------------------------------------------------------------------------------- */
+int svtb200_EB_ENC_msbPack2D(const uint8_t *in8BitBuffer, uint32_t in8Stride, const uint8_t *innBitBuffer, uint16_t *out16BitBuffer,
+                             uint32_t innStride, uint32_t outStride, uint32_t width, uint32_t height);
+int svtb200_CompressedPackmsb(const uint8_t *in8BitBuffer, uint32_t in8Stride, const uint8_t *innBitBuffer, uint16_t *out16BitBuffer,
+                              uint32_t innStride, uint32_t outStride, uint32_t width, uint32_t height);
+int svtb200_CPack(const uint8_t *innBitBuffer, uint32_t innStride, uint8_t *inCompnBitBuffer, uint32_t outStride, uint8_t *localCache,
+                  uint32_t width, uint32_t height);
+int svtb200_EB_ENC_msbUnPack2D(const uint16_t *in16BitBuffer, uint32_t inStride, uint8_t *out8BitBuffer, uint8_t *outnBitBuffer,
+                               uint32_t out8Stride, uint32_t outnStride, uint32_t width, uint32_t height);
+int svtb200_UnPack8BitData(const uint16_t *in16BitBuffer, uint32_t inStride, uint8_t *out8BitBuffer, uint32_t out8Stride, uint32_t width,
+                           uint32_t height);
+int svtb200_UnpackAvg(const uint16_t *ref16L0, uint32_t refL0Stride, const uint16_t *ref16L1, uint32_t refL1Stride, uint8_t *dstPtr,
+                      uint32_t dstStride, uint32_t width, uint32_t height);
+#define SVTB200_PACK_MSB 0
+#define SVTB200_PACK_COMPRESSED_MSB 1
+#define SVTB200_PACK_CPACK 2
+#define SVTB200_PACK_UNPACK 3
+#define SVTB200_PACK_UNPACK8 4
+#define SVTB200_PACK_UNPACK_AVG 5
+int svtb200_pack_plane_dev(int op, const void *in0, uint32_t in0_stride, const void *in1, uint32_t in1_stride, void *out0,
+                           uint32_t out0_stride, void *out1, uint32_t out1_stride, uint32_t width, uint32_t height, void *cuda_stream);
+
+/* ---------------------------------------------------------------------------------------
  * Device-resident source pictures (the PictureAnalysis feeders).
  * svtb200_pa_picture_create allocates padded full / quarter / sixteenth luma planes in HBM with the
  * reference's geometry (pads 68 / 32 / 16: EbEncHandle.c:901-925); svtb200_pa_picture_upload copies an

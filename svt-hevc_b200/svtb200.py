@@ -462,3 +462,50 @@ def sao_stats_picture_dev(src, recon, out_ptr, stream=0):
 
 def sao_apply_picture_dev(inp, out, prm_ptr, flags=(1, 1), stream=0):
     check(lib().svtb200_sao_apply_picture_dev(C.byref(inp), C.byref(out), C.c_void_p(prm_ptr), (C.c_uint8 * 2)(*flags), C.c_void_p(stream)))
+
+
+# ---- 10-bit pack / unpack -----------------------------------------------------------
+PACK_MSB, PACK_COMPRESSED_MSB, PACK_CPACK, PACK_UNPACK, PACK_UNPACK8, PACK_UNPACK_AVG = range(6)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def msb_pack2d(in8, inn, compressed=False):
+    """EB_ENC_msbPack2D / CompressedPackmsb on 2-D numpy planes (row strides taken from the arrays)."""
+    h, w = in8.shape
+    out = np.zeros((h, w), np.uint16)
+    f = lib().svtb200_CompressedPackmsb if compressed else lib().svtb200_EB_ENC_msbPack2D
+    check(f(_p(in8), C.c_uint32(in8.strides[0]), _p(inn), _p(out), C.c_uint32(inn.strides[0]), C.c_uint32(w), C.c_uint32(w), C.c_uint32(h)))
+    return out
+
+
+def cpack(inn):
+    h, w = inn.shape
+    out = np.zeros((h, w // 4), np.uint8)
+    check(lib().svtb200_CPack(_p(inn), C.c_uint32(inn.strides[0]), _p(out), C.c_uint32(w // 4), None, C.c_uint32(w), C.c_uint32(h)))
+    return out
+
+
+def msb_unpack2d(in16, want_nbit=True):
+    h, w = in16.shape
+    o8 = np.zeros((h, w), np.uint8)
+    if want_nbit:
+        on = np.zeros((h, w), np.uint8)
+        check(lib().svtb200_EB_ENC_msbUnPack2D(_p(in16), C.c_uint32(in16.strides[0] // 2), _p(o8), _p(on), C.c_uint32(w), C.c_uint32(w), C.c_uint32(w), C.c_uint32(h)))
+        return o8, on
+    check(lib().svtb200_UnPack8BitData(_p(in16), C.c_uint32(in16.strides[0] // 2), _p(o8), C.c_uint32(w), C.c_uint32(w), C.c_uint32(h)))
+    return o8
+
+
+def unpack_avg(l0, l1):
+    h, w = l0.shape
+    o = np.zeros((h, w), np.uint8)
+    check(lib().svtb200_UnpackAvg(_p(l0), C.c_uint32(l0.strides[0] // 2), _p(l1), C.c_uint32(l1.strides[0] // 2), _p(o), C.c_uint32(w), C.c_uint32(w), C.c_uint32(h)))
+    return o
+
+
+def pack_plane_dev(op, in0, s_in0, in1, s_in1, out0, s_out0, out1, s_out1, width, height, stream=0):
+    check(lib().svtb200_pack_plane_dev(C.c_int(op), C.c_void_p(in0), C.c_uint32(s_in0), C.c_void_p(in1), C.c_uint32(s_in1), C.c_void_p(out0), C.c_uint32(s_out0),
+                                       C.c_void_p(out1), C.c_uint32(s_out1), C.c_uint32(width), C.c_uint32(height), C.c_void_p(stream)))
