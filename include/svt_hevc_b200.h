@@ -345,6 +345,74 @@ int svtb200_sao_apply_picture(const svtb200_yuv_picture *in, const svtb200_yuv_p
 int svtb200_sao_apply_picture_dev(const svtb200_yuv_picture *in, const svtb200_yuv_picture *out, const svtb200_sao_params *lcu_params_dev,
                                   const uint8_t sao_flag[2], void *cuda_stream);
 
+/* =======================================================================================
+ *  D. Intra prediction
+ * ===================================================================================== */
+
+/* Leaf: one HEVC intra mode on an explicit reference line -- IntraModePlanar / DCLuma / DCChroma / VerticalLuma|Chroma /
+ * HorizontalLuma|Chroma / Angular_{2,18,34} / Angular_{Vertical,Horizontal}_Kernel behind IntraModeAngular_all
+ * (C_DEFAULT/EbIntraPrediction_C.c:15-1015, Codec/EbIntraPrediction.c:3516).  refSamples holds 4*size+1 samples in the order of
+ * IntraReferenceSamples_t::yIntraReferenceArray: [0] = bottom-most sample of the bottom-left column ... [2*size-1] = left sample of
+ * row 0, [2*size] = top-left, [2*size+1 ...4*size] = top row then top-right.  is_chroma selects the variants without the
+ * DC / horizontal / vertical edge filters.  mode 0 planar, 1 DC, 2..34 angular; size 4/8/16/32. */
+int svtb200_IntraPrediction(uint32_t mode, uint32_t size, int is_chroma, const uint8_t *refSamples, uint8_t *predictionPtr,
+                            uint32_t predictionBufferStride);
+
+/* Encode-pass intra prediction of a batch of mutually independent blocks (one wavefront diagonal):
+ * GenerateIntraReferenceSamplesEncodePass + EncodePassIntraPrediction (Codec/EbIntraPrediction.c:212,4395), 8-bit 4:2:0.
+ * The neighbour samples are read from `recon` (what the reference keeps in its recon neighbour arrays); which of them may be used
+ * is given per 4-luma-sample unit, in the blockIndex order of the reference: left_avail bit i = i-th unit of the left column counted
+ * from the BOTTOM of the bottom-left block (2*size/4 units), top_avail bit i = i-th unit of the top row from the left (top then
+ * top-right).  The caller folds picture/tile/slice boundaries, z-scan order (isBottomLeftAvailable / isUpperRightAvailable,
+ * Codec/EbAvailability.c) and constrained-intra into these bits.  Luma is predicted at `size`, chroma (Cb and Cr) at size/2.
+ * recon and pred may be the same picture (the reference predicts into its recon buffer, EbCodingLoop.c:3336). */
+#define SVTB200_INTRA_SKIP 0xFF               /* luma_mode / chroma_mode: do not predict this component              */
+#define SVTB200_INTRA_TOPLEFT_AVAIL 1         /* flags                                                                */
+#define SVTB200_INTRA_STRONG_SMOOTHING 2      /* flags: sps strong_intra_smoothing_enable_flag                        */
+#define SVTB200_INTRA_CHROMA_PLANAR 0         /* chroma_mode: EB_INTRA_CHROMA_* (Codec/EbSyntaxElements.h:58-62)      */
+#define SVTB200_INTRA_CHROMA_VERTICAL 1
+#define SVTB200_INTRA_CHROMA_HORIZONTAL 2
+#define SVTB200_INTRA_CHROMA_DC 3
+#define SVTB200_INTRA_CHROMA_DM 4
+typedef struct svtb200_intra_job {
+    uint16_t x, y;           /* luma origin of the block, picture coordinates                                         */
+    uint8_t  size;           /* luma size 4/8/16/32 (4 only with chroma_mode = SKIP: the chroma of an NxN CU is one size-8 job) */
+    uint8_t  luma_mode;      /* 0..34 or SVTB200_INTRA_SKIP                                                           */
+    uint8_t  chroma_mode;    /* SVTB200_INTRA_CHROMA_* or SVTB200_INTRA_SKIP                                          */
+    uint8_t  flags;
+    uint16_t left_avail, top_avail;
+} svtb200_intra_job;         /* 12 bytes */
+int svtb200_intra_batch(const svtb200_yuv_picture *recon, const svtb200_yuv_picture *pred, const svtb200_intra_job *jobs, uint32_t n_jobs);
+int svtb200_intra_batch_dev(const svtb200_yuv_picture *recon, const svtb200_yuv_picture *pred, const svtb200_intra_job *jobs_dev,
+                            uint32_t n_jobs, void *cuda_stream);
+
+/* Open-loop intra search of a whole picture: OpenLoopIntraSearchLcu (Codec/EbMotionEstimation.c:5053) for every LCU, with
+ * UpdateNeighborSamplesArrayOpenLoop / IntraPredictionOpenLoop (Codec/EbIntraPrediction.c:5222,5339) and the candidate injection
+ * and sorting helpers (:4458-4960).  Neighbours come from the SOURCE picture, so all LCUs are independent.
+ * Outputs, indexed [lcu * 85 + rasterScanCuIndex] (index 0, the 64x64, is never written):
+ *   total_modes[.]              OisCu32Cu16Results_t / OisCu8Results_t::totalIntraLumaMode
+ *   cand[. * cand_capacity + k] OisCandidate_t packed as the reference's oisResults word: bits 0-19 distortion,
+ *                               bit 20 validDistortion, bits 24-31 intraMode.  Fields the reference leaves unwritten read 0.
+ * cand_capacity >= 18 with ois_kernel_level, >= 9 otherwise (>= 1 suffices with limit_ois_to_dc_mode on non-I pictures).
+ * me_results (the svtb200_me_picture output of the same picture) is read only on non-I pictures without ois_kernel_level and
+ * without limit_ois_to_dc_mode; it may be NULL otherwise. */
+typedef struct svtb200_ois_config {
+    uint16_t pic_width, pic_height;
+    uint8_t  slice_type;                        /* 0 B, 1 P, 2 I (EB_SLICE)                                            */
+    uint8_t  temporal_layer;
+    uint8_t  ois_kernel_level;                  /* MotionEstimationContext_t::oisKernelLevel                           */
+    uint8_t  ois_th_set;                        /* ::oisThSet 0..2                                                     */
+    uint8_t  set_best_ois_distortion_to_valid;  /* ::setBestOisDistortionToValid                                       */
+    uint8_t  limit_ois_to_dc_mode;              /* PictureParentControlSet_t::limitOisToDcModeFlag                     */
+    uint8_t  skip_ois_8x8;                      /* ::skipOis8x8                                                        */
+    uint8_t  cu8x8_mode;                        /* ::cu8x8Mode                                                         */
+} svtb200_ois_config;
+#define SVTB200_OIS_CU_COUNT 85
+int svtb200_ois_picture(const svtb200_ois_config *cfg, const svtb200_plane *src_luma, const svtb200_me_pu_result *me_results,
+                        uint8_t *total_modes, uint32_t *cand, uint32_t cand_capacity);
+int svtb200_ois_picture_dev(const svtb200_ois_config *cfg, const svtb200_plane *src_luma_dev, const svtb200_me_pu_result *me_results_dev,
+                            uint8_t *total_modes_dev, uint32_t *cand_dev, uint32_t cand_capacity, void *cuda_stream);
+
 /* ---------------------------------------------------------------------------------------
  * 10-bit sample packing.  Same argument order as the reference typedefs in
  * Codec/EbPackUnPack.h (EB_ENC_Pack2D_TYPE :17, COMPPack_TYPE :52, EB_ENC_UnPack2D_TYPE :70,

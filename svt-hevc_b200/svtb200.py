@@ -509,3 +509,51 @@ def unpack_avg(l0, l1):
 def pack_plane_dev(op, in0, s_in0, in1, s_in1, out0, s_out0, out1, s_out1, width, height, stream=0):
     check(lib().svtb200_pack_plane_dev(C.c_int(op), C.c_void_p(in0), C.c_uint32(s_in0), C.c_void_p(in1), C.c_uint32(s_in1), C.c_void_p(out0), C.c_uint32(s_out0),
                                        C.c_void_p(out1), C.c_uint32(s_out1), C.c_uint32(width), C.c_uint32(height), C.c_void_p(stream)))
+
+
+# ================================================================================================
+# D. intra prediction
+# ================================================================================================
+INTRA_SKIP, INTRA_TOPLEFT_AVAIL, INTRA_STRONG_SMOOTHING = 0xFF, 1, 2
+INTRA_JOB_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("size", "u1"), ("luma_mode", "u1"), ("chroma_mode", "u1"), ("flags", "u1"),
+                            ("left_avail", "<u2"), ("top_avail", "<u2")])
+assert INTRA_JOB_DTYPE.itemsize == 12
+OIS_CU_COUNT = 85
+
+
+class OisConfig(C.Structure):
+    _fields_ = [("pic_width", C.c_uint16), ("pic_height", C.c_uint16), ("slice_type", C.c_uint8), ("temporal_layer", C.c_uint8),
+                ("ois_kernel_level", C.c_uint8), ("ois_th_set", C.c_uint8), ("set_best_ois_distortion_to_valid", C.c_uint8),
+                ("limit_ois_to_dc_mode", C.c_uint8), ("skip_ois_8x8", C.c_uint8), ("cu8x8_mode", C.c_uint8)]
+
+
+def intra_prediction(mode, size, is_chroma, line):
+    """leaf: one intra mode on an explicit (4*size+1)-sample reference line -> size x size block"""
+    line = np.ascontiguousarray(line, np.uint8)
+    pred = np.zeros((size, size), np.uint8)
+    check(lib().svtb200_IntraPrediction(C.c_uint32(mode), C.c_uint32(size), C.c_int(is_chroma), _u8p(line), _u8p(pred), C.c_uint32(size)))
+    return pred
+
+
+def intra_batch(recon, pred, jobs):
+    """recon / pred: HostYuvPicture (may be the same object); jobs: INTRA_JOB_DTYPE array"""
+    jobs = np.ascontiguousarray(jobs)
+    check(lib().svtb200_intra_batch(C.byref(recon.struct), C.byref(pred.struct), _u8p(jobs), C.c_uint32(len(jobs))))
+
+
+def intra_batch_dev(recon_struct, pred_struct, jobs_ptr, n_jobs, stream=0):
+    check(lib().svtb200_intra_batch_dev(C.byref(recon_struct), C.byref(pred_struct), C.c_void_p(jobs_ptr), C.c_uint32(n_jobs), C.c_void_p(stream)))
+
+
+def ois_picture(cfg, src_plane, me_results, cap):
+    """src_plane: Plane (host luma); me_results: ME_PU_RESULT_DTYPE [n_lcu][85] or None -> (total [n_lcu][85] u8, cand [n_lcu][85][cap] u32)"""
+    n_lcu = ((cfg.pic_width + 63) // 64) * ((cfg.pic_height + 63) // 64)
+    total = np.zeros((n_lcu, OIS_CU_COUNT), np.uint8)
+    cand = np.zeros((n_lcu, OIS_CU_COUNT, cap), np.uint32)
+    check(lib().svtb200_ois_picture(C.byref(cfg), C.byref(src_plane), _u8p(me_results) if me_results is not None else None, _u8p(total), _u8p(cand), C.c_uint32(cap)))
+    return total, cand
+
+
+def ois_picture_dev(cfg, src_plane_dev, me_ptr, total_ptr, cand_ptr, cap, stream=0):
+    check(lib().svtb200_ois_picture_dev(C.byref(cfg), C.byref(src_plane_dev), C.c_void_p(me_ptr), C.c_void_p(total_ptr), C.c_void_p(cand_ptr), C.c_uint32(cap),
+                                        C.c_void_p(stream)))
