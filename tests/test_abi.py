@@ -37,12 +37,13 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(S.McJob) == 18 and S.TQ_JOB_DTYPE.itemsize == 16 and S.ME_PU_RESULT_DTYPE.itemsize == 24
     assert S.SAO_STATS_DTYPE.itemsize == 312 and S.SAO_PARAMS_DTYPE.itemsize == 20 and C.sizeof(S.DlfParams) == 10
     # svtb200_me_config: spot-check a few offsets against the C layout through a tiny compiled probe
-    src = '#include <stddef.h>\n#include <stdio.h>\n#include "svt_hevc_b200.h"\nint main(){printf("%zu %zu %zu %zu",sizeof(svtb200_me_config),offsetof(svtb200_me_config,lambda),offsetof(svtb200_me_config,mvd_bits),offsetof(svtb200_me_config,ref_poc));return 0;}'
+    assert S.INTRA_JOB_DTYPE.itemsize == 12 and C.sizeof(S.OisConfig) == 12
+    src = '#include <stddef.h>\n#include <stdio.h>\n#include "svt_hevc_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu",sizeof(svtb200_me_config),offsetof(svtb200_me_config,lambda),offsetof(svtb200_me_config,mvd_bits),offsetof(svtb200_me_config,ref_poc),sizeof(svtb200_intra_job),sizeof(svtb200_ois_config),offsetof(svtb200_intra_job,left_avail));return 0;}'
     exe = os.path.join(ROOT, "tests", ".abi_probe")
     subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src, text=True, check=True)
     got = [int(v) for v in subprocess.run([exe], capture_output=True, text=True).stdout.split()]
     os.remove(exe)
-    assert got == [C.sizeof(S.MeConfig), S.MeConfig.lambda_.offset, S.MeConfig.mvd_bits.offset, S.MeConfig.ref_poc.offset]
+    assert got == [C.sizeof(S.MeConfig), S.MeConfig.lambda_.offset, S.MeConfig.mvd_bits.offset, S.MeConfig.ref_poc.offset, 12, 12, 8]
 
 
 def test_no_cpu_fallback_without_a_device():
