@@ -129,6 +129,7 @@ typedef struct svtb200_me_config {
     uint8_t  fractional_search_model;      /* 0 all, 1 selective, 2 off (integer-pel only)     */
     uint8_t  cu8x8_mode, cu16x16_mode;     /* CU_8x8_MODE_x / CU_16x16_MODE_x                  */
     uint8_t  rate_control_mode;            /* staticConfig.rateControlMode                     */
+    uint8_t  fractional_search_method;     /* MeContext_t::fractionalSearchMethod: 0 SUB_SAD_SEARCH, 1 FULL_SAD_SEARCH (2 SSD_SEARCH: unsupported) */
     uint32_t lambda;                       /* MeContext_t::lambda                              */
     uint32_t mvd_bits[12];                 /* MeContext_t::mvdBitsArray[NUMBER_OF_MVD_CASES]   */
     uint64_t ref_poc[2];                   /* refPicPocArray                                   */

@@ -124,7 +124,6 @@ void port_fullpel_search_lcu(const uint8_t *src, uint32_t ss, const uint8_t *ref
         }
 }
 
-/* ---- picture driver ------------------------------------------------------------------- */
 
 typedef struct { const uint8_t *buf; int stride, ox, oy, w, h; } plane_t;
 static plane_t mkplane(const svtb200_plane *p)
@@ -133,6 +132,129 @@ static plane_t mkplane(const svtb200_plane *p)
     return q;
 }
 static inline const uint8_t *at(const plane_t *p, int x, int y) { return p->buf + (size_t)(p->oy + y) * p->stride + p->ox + x; }
+
+/* ---- sub-pel refinement --------------------------------------------------------------------
+ * EbHevcInterpolateSearchRegionAVC :645, PU_HalfPelRefinement :733, EbHevcHalfPelSearch_LCU :1036,
+ * SetQuarterPelRefinementInputsOnTheFly :1540, PU_QuarterPelRefinementOnTheFly :1226, QuarterPelSearch_LCU :1623,
+ * SuPelEnable :3035; half-sample filter {-2, 18, 18, -2} (+16) >> 5 of C_DEFAULT/EbAvcStyleMcp_C.c:12-82.
+ * Plane coordinates, relative to the search-area origin O of the list:
+ *   F(x, y) integer sample O + (x, y);  B(c, y) = sample at (c - 1/2, y);  H(x, r) = (x, r - 1/2);  J(c, r) = (c - 1/2, r - 1/2),
+ * J being the vertical filter of the ROUNDED B samples, as in the reference.  Stored with a 2-sample apron. */
+typedef struct { int saw, sah, sox, soy, pitch; uint8_t *F, *B, *H, *J; } subpel_t;
+#define SP_MAX (127 + 63 + 8)
+static inline uint8_t *sp_at(uint8_t *pl, int pitch, int x, int y) { return pl + (size_t)(y + 2) * pitch + (x + 2); }
+static inline int clip255(int v) { return v < 0 ? 0 : v > 255 ? 255 : v; }
+static inline int half4(int a, int b, int c, int d) { return clip255((-2 * a + 18 * b + 18 * c - 2 * d + 16) >> 5); }
+
+static void subpel_build(subpel_t *s, const plane_t *ref, int ox, int oy)
+{
+    const int pw = s->pitch;
+    for (int y = -2; y <= s->sah + 65; ++y)
+        for (int x = -2; x <= s->saw + 65; ++x) *sp_at(s->F, pw, x, y) = *at(ref, ox + s->sox + x, oy + s->soy + y);
+    for (int y = -2; y <= s->sah + 64; ++y)
+        for (int c = 0; c <= s->saw + 64; ++c)
+            *sp_at(s->B, pw, c, y) = (uint8_t)half4(*sp_at(s->F, pw, c - 2, y), *sp_at(s->F, pw, c - 1, y), *sp_at(s->F, pw, c, y), *sp_at(s->F, pw, c + 1, y));
+    for (int r = 0; r <= s->sah + 63; ++r) {
+        for (int x = -1; x <= s->saw + 64; ++x)
+            *sp_at(s->H, pw, x, r) = (uint8_t)half4(*sp_at(s->F, pw, x, r - 2), *sp_at(s->F, pw, x, r - 1), *sp_at(s->F, pw, x, r), *sp_at(s->F, pw, x, r + 1));
+        for (int c = 0; c <= s->saw + 64; ++c)
+            *sp_at(s->J, pw, c, r) = (uint8_t)half4(*sp_at(s->B, pw, c, r - 2), *sp_at(s->B, pw, c, r - 1), *sp_at(s->B, pw, c, r), *sp_at(s->B, pw, c, r + 1));
+    }
+}
+
+/* SAD of the PU against one plane position / the average of two; method 0 = SUB_SAD_SEARCH (even rows, doubled), 1 = FULL_SAD_SEARCH */
+static uint32_t sp_sad(const uint8_t *src, int ss, const uint8_t *p, int ps, int size, int method)
+{
+    return method == 0 ? port_sad_nxm(src, 2 * ss, p, 2 * ps, size >> 1, size) << 1 : port_sad_nxm(src, ss, p, ps, size, size);
+}
+static uint32_t sp_sad_avg(const uint8_t *src, int ss, const uint8_t *p1, const uint8_t *p2, int ps, int size, int method)
+{
+    return method == 0 ? port_sad_avg(src, 2 * ss, p1, 2 * ps, p2, 2 * ps, size >> 1, size) << 1 : port_sad_avg(src, ss, p1, ps, p2, ps, size, size);
+}
+
+enum { DIR_TL = 0, DIR_T = 1, DIR_TR = 2, DIR_R = 3, DIR_BR = 4, DIR_B = 5, DIR_BL = 6, DIR_L = 7 };   /* *_POSITION, EbMotionEstimation.c:68-75 */
+
+static void halfpel_pu(subpel_t *s, const uint8_t *src, int ss, int px, int py, int size, int method, uint32_t *bsad, uint32_t *bmv, uint8_t *dir)
+{
+    const int16_t xmv = (int16_t)(*bmv & 0xffff), ymv = (int16_t)(*bmv >> 16);
+    const int xs = (xmv >> 2) - s->sox + px, ys = (ymv >> 2) - s->soy + py, pw = s->pitch;
+    /* evaluation order of the reference: L R T B TL TR BR BL */
+    const uint8_t *pos[8] = { sp_at(s->B, pw, xs, ys), sp_at(s->B, pw, xs + 1, ys), sp_at(s->H, pw, xs, ys), sp_at(s->H, pw, xs, ys + 1),
+                              sp_at(s->J, pw, xs, ys), sp_at(s->J, pw, xs + 1, ys), sp_at(s->J, pw, xs + 1, ys + 1), sp_at(s->J, pw, xs, ys + 1) };
+    static const int dx[8] = { -2, 2, 0, 0, -2, 2, 2, -2 }, dy[8] = { 0, 0, -2, 2, -2, -2, 2, 2 };
+    uint32_t d[8];
+    for (int k = 0; k < 8; ++k) {
+        d[k] = sp_sad(src, ss, pos[k], pw, size, method);
+        if (d[k] < *bsad) { *bsad = d[k]; *bmv = pack_mv((int16_t)(xmv + dx[k]), (int16_t)(ymv + dy[k])); }
+    }
+    uint32_t best = d[0];
+    for (int k = 1; k < 8; ++k) if (d[k] < best) best = d[k];
+    /* first match in the order L R T B TL TR BL BR (:1000-1023) */
+    static const int order[8] = { 0, 1, 2, 3, 4, 5, 7, 6 };
+    static const uint8_t code[8] = { DIR_L, DIR_R, DIR_T, DIR_B, DIR_TL, DIR_TR, DIR_BR, DIR_BL };
+    for (int k = 0; k < 8; ++k) if (d[order[k]] == best) { *dir = code[order[k]]; break; }
+}
+
+/* the two planes averaged for each of the 8 quarter positions (order L R T B TL TR BR BL), by the kind of the current best MV:
+ * 0 integer, 1 horizontal half, 2 vertical half, 3 diagonal half.  {plane, dx, dy} x 2; planes 0 F, 1 B, 2 H, 3 J. */
+static const int8_t QPEL[4][8][6] = {
+    { {1,0,0, 0,0,0}, {0,0,0, 1,1,0}, {2,0,0, 0,0,0}, {0,0,0, 2,0,1}, {1,0,0, 2,0,0}, {2,0,0, 1,1,0}, {2,0,1, 1,1,0}, {1,0,0, 2,0,1} },
+    { {0,-1,0, 1,0,0}, {1,0,0, 0,0,0}, {3,0,0, 1,0,0}, {1,0,0, 3,0,1}, {2,-1,0, 1,0,0}, {1,0,0, 2,0,0}, {1,0,0, 2,0,1}, {2,-1,1, 1,0,0} },
+    { {3,0,0, 2,0,0}, {2,0,0, 3,1,0}, {0,0,-1, 2,0,0}, {2,0,0, 0,0,0}, {1,0,-1, 2,0,0}, {2,0,0, 1,1,-1}, {2,0,0, 1,1,0}, {1,0,0, 2,0,0} },
+    { {2,-1,0, 3,0,0}, {3,0,0, 2,0,0}, {1,0,-1, 3,0,0}, {3,0,0, 1,0,0}, {2,-1,0, 1,0,-1}, {1,0,-1, 2,0,0}, {1,0,0, 2,0,0}, {2,-1,0, 1,0,0} } };
+
+static void quarterpel_pu(subpel_t *s, const uint8_t *src, int ss, int px, int py, int size, int method, uint32_t *bsad, uint32_t *bmv, uint8_t dir)
+{
+    const int16_t xmv = (int16_t)(*bmv & 0xffff), ymv = (int16_t)(*bmv >> 16);
+    const int xs = ((xmv + 2) >> 2) - s->sox + px, ys = ((ymv + 2) >> 2) - s->soy + py, pw = s->pitch;
+    const int kind = (ymv & 2) + ((xmv & 2) >> 1);
+    uint8_t *pl[4] = { s->F, s->B, s->H, s->J };
+    /* which of the 8 quarter positions lie towards the best half position (:1260-1285): three neighbours of the direction,
+     * mirrored when the current best is itself a half position */
+    static const uint8_t ring[8] = { DIR_TL, DIR_T, DIR_TR, DIR_R, DIR_BR, DIR_B, DIR_BL, DIR_L };
+    static const uint8_t pos_dir[8] = { DIR_L, DIR_R, DIR_T, DIR_B, DIR_TL, DIR_TR, DIR_BR, DIR_BL };
+    static const int dx[8] = { -1, 1, 0, 0, -1, 1, 1, -1 }, dy[8] = { 0, 0, -1, 1, -1, -1, 1, 1 };
+    (void)ring;
+    for (int k = 0; k < 8; ++k) {
+        /* position p is valid when the half-pel direction is p itself or one of its two ring neighbours (integer best),
+         * or the opposite of that (half best) */
+        int want = pos_dir[k];
+        if (kind) want = (want + 4) & 7;
+        const int diff = (dir - want) & 7;
+        if (!(diff == 0 || diff == 1 || diff == 7)) continue;
+        const int8_t *q = QPEL[kind][k];
+        const uint32_t d = sp_sad_avg(src, ss, sp_at(pl[q[0]], pw, xs + q[1], ys + q[2]), sp_at(pl[q[3]], pw, xs + q[4], ys + q[5]), pw, size, method);
+        if (d < *bsad) { *bsad = d; *bmv = pack_mv((int16_t)(xmv + dx[k]), (int16_t)(ymv + dy[k])); }
+    }
+}
+
+/* SuPelEnable :3035: which PU sizes get sub-pel refinement on this LCU / list (fractionalSearchModel 1) */
+static void supel_enable(const uint32_t *bsad, const uint32_t *bmv, int tl, int *e32, int *e16, int *e8)
+{
+    int32_t sx[3] = { 0, 0, 0 }, sy[3] = { 0, 0, 0 };
+    uint32_t sd[3] = { 0, 0, 0 };
+    static const int first[3] = { 1, 5, 21 }, cnt[3] = { 4, 16, 64 }, sh[3] = { 2, 4, 6 };
+    uint32_t mag[3], avg[3];
+    for (int l = 0; l < 3; ++l) {
+        for (int k = 0; k < cnt[l]; ++k) { sx[l] += (int16_t)(bmv[first[l] + k] & 0xffff); sy[l] += (int16_t)(bmv[first[l] + k] >> 16); sd[l] += bsad[first[l] + k]; }
+        const uint32_t ax = (uint32_t)(sx[l] >> sh[l]), ay = (uint32_t)(sy[l] >> sh[l]);
+        mag[l] = ax * ax + ay * ay;
+        avg[l] = sd[l] >> sh[l];
+    }
+    const uint32_t thr = tl == 1 ? 32 * 32 : tl == 2 ? 80 * 80 : 48 * 48;
+    const int m32 = mag[0] < thr, s32 = avg[0] < 32 * 32 * 6, m16 = mag[1] < thr, s16 = avg[1] < 16 * 16 * 2, m8 = mag[2] < thr, s8 = avg[2] < 8 * 8 * 2;
+    /* class = 0 (small MV, small SAD), 1 (small MV, large SAD), 2 (large MV, small SAD), 3 */
+    const int c32 = (m32 ? 0 : 2) + (s32 ? 0 : 1), c16 = (m16 ? 0 : 2) + (s16 ? 0 : 1), c8 = (m8 ? 0 : 2) + (s8 ? 0 : 1);
+    static const uint8_t T32[4][4] = { { 1, 0, 1, 0 }, { 1, 0, 1, 1 }, { 1, 0, 1, 0 }, { 1, 1, 1, 0 } };   /* [layer 0,1,2,other][class] */
+    static const uint8_t T16[4] = { 0, 1, 0, 1 };
+    const int row = tl > 2 ? 3 : tl;
+    *e32 = T32[row][c32];
+    *e16 = T16[c16];
+    *e8 = (row == 3 && c8 == 3) ? 0 : T16[c8];
+}
+
+/* ---- picture driver ------------------------------------------------------------------- */
+
 
 /* MeEbHevcGetMvdFractionBits, EbMdRateEstimation.c:172 (+ ExponentialGolombBits for k=1) */
 static uint32_t egk1_bits(int32_t sym)
@@ -193,7 +315,8 @@ int port_me_picture(const svtb200_me_config *cfg, const svtb200_pa_picture *srcp
     static const int tab8[64] = { 0, 1, 4, 5, 16, 17, 20, 21, 2, 3, 6, 7, 18, 19, 22, 23, 8, 9, 12, 13, 24, 25, 28, 29,
         10, 11, 14, 15, 26, 27, 30, 31, 32, 33, 36, 37, 48, 49, 52, 53, 34, 35, 38, 39, 50, 51, 54, 55,
         40, 41, 44, 45, 56, 57, 60, 61, 42, 43, 46, 47, 58, 59, 62, 63 };                   /* tab8x8, :102 */
-    if (cfg->fractional_search_model != 2) return SVTB200_ERR_UNSUPPORTED;
+    if (cfg->fractional_search_model > 2 || cfg->fractional_search_method > 1) return SVTB200_ERR_UNSUPPORTED;   /* SSD_SEARCH (enc modes <= 4) is not restated */
+    const int subpel = cfg->fractional_search_model != 2, spm = cfg->fractional_search_method;
     const int W = cfg->pic_width, H = cfg->pic_height;
     const int cols = (W + 63) / 64, rows = (H + 63) / 64;
     const plane_t sF = mkplane(&srcp->full), sQ = mkplane(&srcp->quarter), sS = mkplane(&srcp->sixteenth);
@@ -203,6 +326,15 @@ int port_me_picture(const svtb200_me_config *cfg, const svtb200_pa_picture *srcp
     /* per-LCU state persists across LCUs exactly like MeContext_t does (stale list-1 values on P pictures) */
     uint32_t bsad[2][85], bmv[2][85], bisad[85];
     memset(bsad, 0, sizeof bsad); memset(bmv, 0, sizeof bmv); memset(bisad, 0, sizeof bisad);
+    subpel_t sp[2];
+    uint8_t spdir[85];      /* psubPelDirection*: one set shared by both lists, like MeContext_t */
+    memset(spdir, 0, sizeof spdir);
+    memset(sp, 0, sizeof sp);
+    for (int li = 0; li < 2 && subpel; ++li) {
+        sp[li].pitch = SP_MAX;
+        sp[li].F = (uint8_t *)calloc(4, (size_t)SP_MAX * SP_MAX);
+        sp[li].B = sp[li].F + (size_t)SP_MAX * SP_MAX; sp[li].H = sp[li].B + (size_t)SP_MAX * SP_MAX; sp[li].J = sp[li].H + (size_t)SP_MAX * SP_MAX;
+    }
 
     for (int ly = 0; ly < rows; ++ly)
     for (int lx = 0; lx < cols; ++lx) {
@@ -361,6 +493,28 @@ int port_me_picture(const svtb200_me_config *cfg, const svtb200_pa_picture *srcp
             for (int k = 0; k < 85; ++k) bsad[li][k] = MAX_SAD_INIT;
             port_fullpel_search_lcu(at(&sF, ox, oy), (uint32_t)sF.stride, at(&rF, ox + sox, oy + soy), (uint32_t)rF.stride,
                                     (int16_t)sox, (int16_t)soy, (uint32_t)saw, (uint32_t)sah, bsad[li], bmv[li]);
+            if (subpel) {
+                /* MotionEstimateLcu :4242-4316 */
+                int e32 = 1, e16 = 1, e8 = 1;
+                if (cfg->fractional_search_model == 1) supel_enable(bsad[li], bmv[li], cfg->temporal_layer, &e32, &e16, &e8);
+                e16 = e16 && cfg->cu16x16_mode == 0;
+                const int no8 = cfg->cu8x8_mode == 1;
+                subpel_t *S = &sp[li];
+                S->saw = saw; S->sah = sah; S->sox = sox; S->soy = soy;
+                subpel_build(S, &rF, ox, oy);
+                const uint8_t *src = at(&sF, ox, oy);
+                for (int pass = 0; pass < 2; ++pass) {       /* all half-pel refinements, then all quarter-pel ones */
+                    for (int k = 0; k < 84; ++k) {
+                        int size, px, py, n;
+                        if (k < 4) { if (!e32) continue; size = 32; px = (k & 1) * 32; py = (k >> 1) * 32; n = 1 + k; }
+                        else if (k < 20) { if (!e16) continue; const int q = k - 4; size = 16; px = (q & 3) * 16; py = (q >> 2) * 16; n = 5 + tab32[q]; }
+                        else { if (!e8 || no8) continue; const int q = k - 20; size = 8; px = (q & 7) * 8; py = (q >> 3) * 8; n = 21 + tab8[q]; }
+                        const uint8_t *ps = src + (size_t)py * sF.stride + px;
+                        if (pass == 0) halfpel_pu(S, ps, sF.stride, px, py, size, spm, &bsad[li][n], &bmv[li][n], &spdir[n]);
+                        else quarterpel_pu(S, ps, sF.stride, px, py, size, spm, &bsad[li][n], &bmv[li][n], spdir[n]);
+                    }
+                }
+            }
         }
         (void)sa_ox; (void)sa_oy;
 
@@ -376,8 +530,49 @@ int port_me_picture(const svtb200_me_config *cfg, const svtb200_pa_picture *srcp
                 const int px = pu < 21 ? pux21[pu] : ((pu - 21) & 7) * 8, py = pu < 21 ? puy21[pu] : ((pu - 21) >> 3) * 8;
                 const int x0 = (int16_t)(bmv[0][n] & 0xffff) >> 2, y0 = (int16_t)(bmv[0][n] >> 16) >> 2;
                 const int x1 = (int16_t)(bmv[1][n] & 0xffff) >> 2, y1 = (int16_t)(bmv[1][n] >> 16) >> 2;
-                bisad[n] = port_sad_avg(at(&sF, ox + px, oy + py), 2 * sF.stride, at(&rFs[0], ox + px + x0, oy + py + y0), 2 * rFs[0].stride,
-                                        at(&rFs[1], ox + px + x1, oy + py + y1), 2 * rFs[1].stride, (uint32_t)sz >> 1, (uint32_t)sz) << 1;
+                if (!subpel) {
+                    const uint8_t *ps = at(&sF, ox + px, oy + py), *p0 = at(&rFs[0], ox + px + x0, oy + py + y0), *p1 = at(&rFs[1], ox + px + x1, oy + py + y1);
+                    bisad[n] = spm == 0 ? port_sad_avg(ps, 2 * sF.stride, p0, 2 * rFs[0].stride, p1, 2 * rFs[1].stride, (uint32_t)sz >> 1, (uint32_t)sz) << 1
+                                        : port_sad_avg(ps, sF.stride, p0, rFs[0].stride, p1, rFs[1].stride, (uint32_t)sz, (uint32_t)sz);
+                } else {
+                    /* EbHevcBiPredictionCompensation :2742, SelectBuffer :2440, QuarterPelCompensation :2490: each list's prediction is a
+                     * plane or the rounded average of two planes, chosen by the fractional position */
+                    static uint8_t tmp[2][64 * 64];
+                    const uint8_t *pp[2]; int pst[2];
+                    for (int l = 0; l < 2; ++l) {
+                        const int16_t mx = (int16_t)(bmv[l][n] & 0xffff), my = (int16_t)(bmv[l][n] >> 16);
+                        const int ix = (mx >> 2) - sp[l].sox + px, iy = (my >> 2) - sp[l].soy + py, fp = (mx & 3) + ((my & 3) << 2), pw = sp[l].pitch;
+                        uint8_t *F = sp[l].F, *B = sp[l].B, *Hh = sp[l].H, *J = sp[l].J;
+                        const uint8_t *a = NULL, *b = NULL;
+                        switch (fp) {
+                        case 0: a = sp_at(F, pw, ix, iy); break;
+                        case 2: a = sp_at(B, pw, ix + 1, iy); break;
+                        case 8: a = sp_at(Hh, pw, ix, iy + 1); break;
+                        case 10: a = sp_at(J, pw, ix + 1, iy + 1); break;
+                        case 1: a = sp_at(F, pw, ix, iy); b = sp_at(B, pw, ix + 1, iy); break;
+                        case 3: a = sp_at(B, pw, ix + 1, iy); b = sp_at(F, pw, ix + 1, iy); break;
+                        case 4: a = sp_at(F, pw, ix, iy); b = sp_at(Hh, pw, ix, iy + 1); break;
+                        case 5: a = sp_at(B, pw, ix + 1, iy); b = sp_at(Hh, pw, ix, iy + 1); break;
+                        case 6: a = sp_at(B, pw, ix + 1, iy); b = sp_at(J, pw, ix + 1, iy + 1); break;
+                        case 7: a = sp_at(B, pw, ix + 1, iy); b = sp_at(Hh, pw, ix + 1, iy + 1); break;
+                        case 9: a = sp_at(Hh, pw, ix, iy + 1); b = sp_at(J, pw, ix + 1, iy + 1); break;
+                        case 11: a = sp_at(J, pw, ix + 1, iy + 1); b = sp_at(Hh, pw, ix + 1, iy + 1); break;
+                        case 12: a = sp_at(Hh, pw, ix, iy + 1); b = sp_at(F, pw, ix, iy + 1); break;
+                        case 13: a = sp_at(Hh, pw, ix, iy + 1); b = sp_at(B, pw, ix + 1, iy + 1); break;
+                        case 14: a = sp_at(J, pw, ix + 1, iy + 1); b = sp_at(B, pw, ix + 1, iy + 1); break;
+                        default: a = sp_at(Hh, pw, ix + 1, iy + 1); b = sp_at(B, pw, ix + 1, iy + 1); break;
+                        }
+                        if (!b) { pp[l] = a; pst[l] = pw; }
+                        else {
+                            for (int r = 0; r < sz; ++r)
+                                for (int c = 0; c < sz; ++c) tmp[l][r * 64 + c] = (uint8_t)((a[(size_t)r * pw + c] + b[(size_t)r * pw + c] + 1) >> 1);
+                            pp[l] = tmp[l]; pst[l] = 64;
+                        }
+                    }
+                    const uint8_t *ps = at(&sF, ox + px, oy + py);
+                    bisad[n] = spm == 0 ? port_sad_avg(ps, 2 * sF.stride, pp[0], 2 * pst[0], pp[1], 2 * pst[1], (uint32_t)sz >> 1, (uint32_t)sz) << 1
+                                        : port_sad_avg(ps, sF.stride, pp[0], pst[0], pp[1], pst[1], (uint32_t)sz, (uint32_t)sz);
+                }
                 total = 3;
             }
             o->total_me_candidates = (uint8_t)total;
@@ -407,5 +602,6 @@ int port_me_picture(const svtb200_me_config *cfg, const svtb200_pa_picture *srcp
             if (lcu_best_mv) memcpy(&lcu_best_mv[((size_t)lcu * 2 + li) * 85], bmv[li], sizeof bmv[li]);
         }
     }
+    for (int li = 0; li < 2 && subpel; ++li) free(sp[li].F);
     return 0;
 }

@@ -122,7 +122,7 @@ int svtref_me_picture_rows(const svtb200_me_config *cfg, const svtb200_pa_pictur
     me->searchAreaWidth = cfg->search_area_w;
     me->searchAreaHeight = cfg->search_area_h;
     me->fractionalSearchModel = cfg->fractional_search_model;
-    me->fractionalSearchMethod = SUB_SAD_SEARCH;
+    me->fractionalSearchMethod = cfg->fractional_search_method;     /* same numbering: SUB_SAD_SEARCH 0, FULL_SAD_SEARCH 1, SSD_SEARCH 2 */
     me->fractionalSearch64x64 = EB_FALSE;
     me->lambda = cfg->lambda;
     for (int i = 0; i < 12; ++i) me->mvdBitsArray[i] = cfg->mvd_bits[i];

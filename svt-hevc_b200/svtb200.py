@@ -38,6 +38,7 @@ class MeConfig(C.Structure):
                 ("search_area_w", C.c_uint8), ("search_area_h", C.c_uint8),
                 ("fractional_search_model", C.c_uint8),
                 ("cu8x8_mode", C.c_uint8), ("cu16x16_mode", C.c_uint8), ("rate_control_mode", C.c_uint8),
+                ("fractional_search_method", C.c_uint8),
                 ("lambda_", C.c_uint32), ("mvd_bits", C.c_uint32 * 12), ("ref_poc", C.c_uint64 * 2)]
 
 
@@ -121,7 +122,7 @@ DEFAULT_LAMBDA = {"base": 439162, "ref": 717148, "nonref": 824850}  # EbLambdaRa
 
 
 def me_config(width, height, enc_mode=10, temporal_layer=0, num_lists=1, hierarchical_levels=3,
-              frame_rate=60, lambda_=None, mvd_bits=DEFAULT_MVD_BITS, ref_poc=(0, 16), rate_control_mode=0):
+              frame_rate=60, lambda_=None, mvd_bits=DEFAULT_MVD_BITS, ref_poc=(0, 16), rate_control_mode=0, use_subpel=None):
     res = "4k" if width * height > 1920 * 1088 else "1080p"
     t = _ME_TABLE[(res, enc_mode)]
     c = MeConfig()
@@ -143,7 +144,11 @@ def me_config(width, height, enc_mode=10, temporal_layer=0, num_lists=1, hierarc
         c.hme_l1_w[i], c.hme_l1_h[i] = t[5], t[6]
         c.hme_l2_w[i], c.hme_l2_h[i] = t[8], t[9]
     c.search_area_w, c.search_area_h = t[10], t[11]
-    c.fractional_search_model = 2        # integer-pel (useSubpelFlag == 0 pictures; sub-pel: later round)
+    if use_subpel is None:               # useSubpelFlag, EbPictureDecisionProcess.c:330-361: 4K: base layer only; below 4K: M<=9 all, M10 reference pictures
+        use_subpel = (temporal_layer == 0) if res == "4k" else (enc_mode <= 9 or temporal_layer < hierarchical_levels)
+    # fractionalSearchModel, EbMotionEstimationProcess.c:398-420: 0 all PUs (M<=5, M6 below 4K), 1 selective (SuPelEnable), 2 off
+    c.fractional_search_model = 2 if not use_subpel else (0 if (enc_mode <= 5 or (enc_mode == 6 and res != "4k")) else 1)
+    c.fractional_search_method = 0       # SUB_SAD_SEARCH for M>=5 (:340-345)
     c.cu8x8_mode, c.cu16x16_mode = 1, 0  # CU_8x8_MODE_1 at M>=? (EbPictureDecisionProcess.c:447-449)
     c.rate_control_mode = rate_control_mode
     c.lambda_ = lambda_ if lambda_ is not None else DEFAULT_LAMBDA["base" if temporal_layer == 0 else "ref"]

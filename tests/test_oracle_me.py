@@ -101,14 +101,32 @@ def _me_cases():
         ("m10_tiny_64x64", 64, 64, dict(enc_mode=10, temporal_layer=1, num_lists=2, force_res="4k"), "synth"),
         ("m10_partial_lcus_72x40", 72, 40, dict(enc_mode=10, temporal_layer=1, num_lists=2, force_res="4k"), "synth"),
         ("m7_partial_lcus_200x136", 200, 136, dict(enc_mode=7, temporal_layer=1, num_lists=2, force_res="1080p", lambda_=1000), "bigmotion"),
+        # sub-pel refinement (half + quarter pel, fractional bi-prediction): every PU / selective per temporal layer, both SAD methods, 8x8 PUs on
+        ("m7_subpel_all_fullsad_8x8", 256, 192, dict(enc_mode=7, temporal_layer=0, num_lists=2, force_res="4k", frac_model=0, frac_method=1, cu8x8=0), "synth"),
+        ("m10_subpel_sel_8x8_tl0", 320, 192, dict(enc_mode=10, temporal_layer=0, num_lists=2, force_res="1080p", cu8x8=0), "bigmotion"),
+        ("m10_subpel_P_tl0", 256, 128, dict(enc_mode=10, temporal_layer=0, num_lists=1, force_res="4k"), "synth"),
+        ("m7_subpel_sel_tl1", 256, 192, dict(enc_mode=7, temporal_layer=1, num_lists=2, force_res="1080p", use_subpel=True, cu8x8=0), "synth"),
+        ("m7_subpel_sel_tl2", 256, 192, dict(enc_mode=7, temporal_layer=2, num_lists=2, force_res="1080p", use_subpel=True, cu8x8=0), "random"),
+        ("m7_subpel_sel_tl3_noise", 192, 192, dict(enc_mode=7, temporal_layer=3, num_lists=2, force_res="4k", use_subpel=True, cu8x8=0), "noisy"),
+        ("m10_subpel_all_partial_192x136", 192, 136, dict(enc_mode=10, temporal_layer=0, num_lists=2, force_res="4k", frac_model=0, cu16x16=1), "bigmotion"),
+        ("m10_subpel_flat", 128, 128, dict(enc_mode=10, temporal_layer=0, num_lists=2, force_res="4k", frac_model=0, cu8x8=0), "constant"),
     ]
 
 
 def build_me_case(width, height, kw, content):
     kw = dict(kw)
     res = kw.pop("force_res")
+    over = {k: kw.pop(k) for k in ("frac_model", "frac_method", "cu8x8", "cu16x16") if k in kw}
     cfg = S.me_config(3840 if res == "4k" else 1920, 2160 if res == "4k" else 1080, **kw)
     cfg.pic_width, cfg.pic_height = width, height
+    if "frac_model" in over:
+        cfg.fractional_search_model = over["frac_model"]
+    if "frac_method" in over:
+        cfg.fractional_search_method = over["frac_method"]
+    if "cu8x8" in over:
+        cfg.cu8x8_mode = over["cu8x8"]
+    if "cu16x16" in over:
+        cfg.cu16x16_mode = over["cu16x16"]
     if content == "synth":
         v = common.SynthVideo(width, height, seed=1234 + width)
         frames = [v.luma(4), v.luma(0), v.luma(8)]
@@ -117,6 +135,14 @@ def build_me_case(width, height, kw, content):
         big = v.luma(0)
         cut = lambda dx, dy: np.ascontiguousarray(big[128 + dy:128 + dy + height, 128 + dx:128 + dx + width])
         frames = [cut(0, 0), cut(-61, -29), cut(45, 38)]
+    elif content == "noisy":       # sub-pel shifted smooth texture + noise: half / quarter positions win often
+        v = common.SynthVideo(2 * width + 64, 2 * height + 64, seed=5 + width, texture_box=6)
+        big = v.luma(0).astype(np.float64)
+        rng = np.random.default_rng(3)
+        def cut(dx, dy):       # dx, dy in half samples of the 2x oversampled picture = quarter-ish shifts after decimation
+            a = big[16 + dy:16 + dy + 2 * height:2, 16 + dx:16 + dx + 2 * width:2] + big[17 + dy:17 + dy + 2 * height:2, 17 + dx:17 + dx + 2 * width:2]
+            return np.clip(np.rint(a / 2 + rng.normal(0, 1.0, (height, width))), 0, 255).astype(np.uint8)
+        frames = [cut(0, 0), cut(5, 3), cut(-3, 7)]
     else:
         frames = [common.adversarial_luma(content, width, height, seed=s) for s in (1, 2, 3)]
         if content == "random":   # make it a (noisy) translation so that ME finds structure
