@@ -4,9 +4,10 @@ on the same box.
 
 A "step" = one 3840x2160 4:2:0 frame through the hot path with the per-picture tool schedule preset M10 derives for that
 frame's temporal layer; consecutive steps walk the 8-frame hierarchical mini-GOP [0,3,2,3,1,3,2,3]:
-    every frame : ME (HME-L0 one quadrant + 85-PU full-pel + bipred, 2 lists) -> MC of the chosen PUs -> residual/T/Q/iQ/iT/recon
-                  -> SAO statistics
-    layer 0 only: + deblocking + SAO application   (M10 switches DLF / SAO-apply off on layers 1-3, EbEncDecProcess.c:2036-2054)
+    every frame : ME (HME-L0 one quadrant + 85-PU full-pel + bipred, 2 lists) -> open-loop intra search (DC only at M10) -> MC of the chosen PUs
+                  -> residual/T/Q/iQ/iT/recon -> SAO statistics
+    layer 0 only: + selective half/quarter-pel ME refinement (useSubpelFlag, fractionalSearchModel 1) + deblocking + SAO application
+                  (M10 switches sub-pel, DLF and SAO-apply off on layers 1-3: EbPictureDecisionProcess.c:353-361, EbEncDecProcess.c:2036-2054)
 Mode decision itself (host, out of scope) is replaced by a fixed stand-in: 32x32 PUs / TUs taking each PU's best ME
 candidate; SAO parameters and boundary strengths are fixed per-LCU tables.  Both arms run exactly the same jobs.
   value : frames resident in HBM (16-frame ring > L2), device-timed with CUDA events, max over ranks
@@ -39,9 +40,9 @@ PAD = 80
 METRIC = "4Kp60 8-bit preset-M10 hot-path CTUs/sec (fps = value / 2040)"
 WORKLOAD = ("configs[1]: 3840x2160 8-bit 4:2:0, preset M10 tool schedule, mini-GOP temporal layers [0,3,2,3,1,3,2,3], 2 reference lists, "
             "fixed 32x32 PU/TU mode-decision stand-in")
-STAGES = ["me_picture", "mc_batch", "tq_batch", "sao_stats_picture", "dlf_picture (layer 0)", "sao_apply_picture (layer 0)"]
+STAGES = ["me_picture (+ sub-pel on layer 0)", "ois_picture", "mc_batch", "tq_batch", "sao_stats_picture", "dlf_picture (layer 0)", "sao_apply_picture (layer 0)"]
 # algorithmic HBM bytes per CTU
-ALG = {"me": 9384 * 2, "mc_uni": 12288, "mc_bi": 18432, "tq": 30720, "dlf": 12864, "sao_stats": 12288 + 3 * 312, "sao_apply": 12288}
+ALG = {"me": 9384 * 2, "ois": 4096 + 21 * 5, "mc_uni": 12288, "mc_bi": 18432, "tq": 30720, "dlf": 12864, "sao_stats": 12288 + 3 * 312, "sao_apply": 12288}
 
 
 def peaks():
@@ -139,6 +140,13 @@ class Workload:
     def me_cfg(self, step):
         return self.S.me_config(W, H, enc_mode=10, temporal_layer=self.tl(step), num_lists=2, ref_poc=(0, 16))
 
+    def ois_cfg(self):
+        """M10, non-I pictures: limitOisToDcModeFlag (EbPictureDecisionProcess.c:417-422), skipOis8x8 (:455), CU_8x8_MODE_1"""
+        c = self.S.OisConfig()
+        c.pic_width, c.pic_height, c.slice_type, c.temporal_layer = W, H, 0, 0
+        c.limit_ois_to_dc_mode, c.skip_ois_8x8, c.cu8x8_mode = 1, 1, 1
+        return c
+
     def refs(self, step):
         d = {0: 8, 1: 4, 2: 2, 3: 1}[self.tl(step)]
         return (step - d) % self.n, (step + d) % self.n
@@ -232,10 +240,15 @@ def run_b200(args):
     d_vbs, d_hbs, d_qp = (torch.from_numpy(a.copy()).to(dev) for a in (wl.vbs, wl.hbs, wl.qp_array))
     d_sao_prm = torch.from_numpy(wl.sao_prm.view(np.uint8)).to(dev)
     d_stats = torch.zeros(N_LCU * 3 * 312, dtype=torch.uint8, device=dev)
+    d_ois_total = torch.zeros(N_LCU * 85, dtype=torch.uint8, device=dev)
+    d_ois_cand = torch.zeros(N_LCU * 85, dtype=torch.int32, device=dev)
+    ois_cfg = wl.ois_cfg()
     h_res = torch.empty(d_res.shape, dtype=torch.uint8).pin_memory()
     h_coeff = [torch.empty(t.shape, dtype=torch.int16).pin_memory() for t in coeff_t]
     h_nz = torch.empty(d_nz.shape, dtype=torch.int32).pin_memory()
     h_stats = torch.empty(d_stats.shape, dtype=torch.uint8).pin_memory()
+    h_ois_total = torch.empty(d_ois_total.shape, dtype=torch.uint8).pin_memory()
+    h_ois_cand = torch.empty(d_ois_cand.shape, dtype=torch.int32).pin_memory()
 
     # mode-decision stand-in: one ME pass per (ring frame, layer) pair fixes the MC job lists used by both timed loops
     d_mc, mc_bytes = [], []
@@ -248,7 +261,7 @@ def run_b200(args):
         mc_bytes.append(wl.mc_alg_bytes(jobs))
     torch.cuda.synchronize()
 
-    names = ["me", "mc", "tq", "dlf", "sao_stats", "sao_apply"]
+    names = ["me", "ois", "mc", "tq", "dlf", "sao_stats", "sao_apply"]
 
     def pipeline(i, src_pa, src_yuv, ev=None):
         """All device stages of frame i.  ev: dict name -> list of (start, end) events."""
@@ -262,6 +275,7 @@ def run_b200(args):
         k = i % RING
         tl0 = wl.tl(i) == 0
         timed("me", lambda: S.me_picture_dev(wl.me_cfg(i), src_pa, ring_pa[r0], ring_pa[r1], d_res.data_ptr(), stream))
+        timed("ois", lambda: S.ois_picture_dev(ois_cfg, src_pa.struct.full, d_res.data_ptr(), d_ois_total.data_ptr(), d_ois_cand.data_ptr(), 1, stream))
         timed("mc", lambda: S.mc_batch_dev([ring_yuv[r0][1], ring_yuv[r1][1]], d_mc[k][0].data_ptr(), d_mc[k][1], pred, stream))
         timed("tq", lambda: S.tq_batch_dev(src_yuv, pred, pred, coeff, d_tq.data_ptr(), len(wl.tq_jobs), d_nz.data_ptr(), stream))
         if tl0:
@@ -284,6 +298,8 @@ def run_b200(args):
             hc.copy_(dc, non_blocking=True)
         h_nz.copy_(d_nz, non_blocking=True)
         h_stats.copy_(d_stats, non_blocking=True)
+        h_ois_total.copy_(d_ois_total, non_blocking=True)
+        h_ois_cand.copy_(d_ois_cand, non_blocking=True)
         tstream.synchronize()
 
     def barrier():
@@ -327,14 +343,14 @@ def run_b200(args):
         ctus = N_LCU * args.steps * world
         tot = {n: float(np.sum(v)) for n, v in stage_ms.items()}
         dom = max(tot, key=tot.get)
-        alg = {"me": ALG["me"] * N_LCU, "mc": float(np.mean(mc_bytes)), "tq": ALG["tq"] * N_LCU, "dlf": ALG["dlf"] * N_LCU,
+        alg = {"me": ALG["me"] * N_LCU, "ois": ALG["ois"] * N_LCU, "mc": float(np.mean(mc_bytes)), "tq": ALG["tq"] * N_LCU, "dlf": ALG["dlf"] * N_LCU,
                "sao_stats": ALG["sao_stats"] * N_LCU, "sao_apply": ALG["sao_apply"] * N_LCU}
         per_stage = {n: {"launch_ms_avg": float(np.mean(v)) if v else None, "launches": len(v), "share_of_step": tot[n] / sum(tot.values()),
                          "achieved_gbs": (alg[n] / (np.mean(v) * 1e-3) / 1e9) if v else None,
                          "frac_of_hbm_peak": (alg[n] / (np.mean(v) * 1e-3) / 1e9 / peak) if v else None} for n, v in stage_ms.items()}
         k_avg_s = float(np.mean(stage_ms[dom])) * 1e-3
         h2d = W * H * 3 // 2
-        d2h = int(d_res.numel() + sum(t.numel() * 2 for t in coeff_t) + d_nz.numel() * 4 + d_stats.numel())
+        d2h = int(d_res.numel() + sum(t.numel() * 2 for t in coeff_t) + d_nz.numel() * 4 + d_stats.numel() + d_ois_total.numel() + d_ois_cand.numel() * 4)
         out = {
             "metric": METRIC, "value": ctus / (ms * 1e-3), "unit": "CTU/s", "fps": ctus / (ms * 1e-3) / N_LCU,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -345,7 +361,7 @@ def run_b200(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
-            "roofline": {"kernel": {"me": "me_picture_kernel", "mc": "mc_batch_kernel", "tq": "tq_batch_kernel", "dlf": "dlf_pass_kernel",
+            "roofline": {"kernel": {"me": "me_picture_kernel", "ois": "ois_picture_kernel", "mc": "mc_batch_kernel", "tq": "tq_batch_kernel", "dlf": "dlf_pass_kernel",
                                     "sao_stats": "sao_stats_kernel", "sao_apply": "sao_apply_kernel"}[dom],
                          "bound": "hbm", "achieved": alg[dom] / k_avg_s / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg[dom] / k_avg_s / 1e9 / peak, "traffic": None, "peak_source": peak_src,
@@ -377,7 +393,8 @@ def cpu_reference(frames):
     pa = [S.HostPaPicture(l) for l in wl.luma]
     yuv = [S.HostYuvPicture(wl.luma[i], wl.chroma[i][0], wl.chroma[i][1]) for i in range(RING)]
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    for f in (ref.svtref_me_picture_rows, ref.svtref_mc_batch, ref.svtref_tq_batch, ref.svtref_dlf_picture, refsao.svtref_sao_stats_picture,
+    ois_cfg = wl.ois_cfg()
+    for f in (ref.svtref_me_picture_rows, ref.svtref_ois_picture, ref.svtref_mc_batch, ref.svtref_tq_batch, ref.svtref_dlf_picture, refsao.svtref_sao_stats_picture,
               refsao.svtref_sao_apply_picture):
         f.restype = C.c_int
     flags = (C.c_uint8 * 2)(1, 1)
@@ -389,6 +406,8 @@ def cpu_reference(frames):
         res = np.zeros((N_LCU, 85), dtype=S.ME_PU_RESULT_DTYPE)
         assert ref.svtref_me_picture_rows(C.byref(cfg), C.byref(pa[k].struct), C.byref(pa[r0].struct), C.byref(pa[r1].struct), vp(res), None, None, None,
                                           C.c_int(1), C.c_int(0), C.c_int(ROWS)) == 0
+        ois_total, ois_cand = np.zeros((N_LCU, 85), np.uint8), np.zeros((N_LCU, 85, 1), np.uint32)
+        assert ref.svtref_ois_picture(C.byref(ois_cfg), C.byref(pa[k].struct.full), vp(res), vp(ois_total), vp(ois_cand), C.c_uint32(1), C.c_int(1)) == 0
         jobs = wl.mc_jobs(res)
         pred = S.HostYuvPicture(np.zeros((H, W), np.uint8), np.zeros((H // 2, W // 2), np.uint8), np.zeros((H // 2, W // 2), np.uint8), replicate=False)
         assert ref.svtref_mc_batch(S.yuv_array([yuv[r0], yuv[r1]]), C.c_int(2), vp(jobs), C.c_int(len(jobs)), C.byref(pred.struct), C.c_int(1)) == 0
@@ -411,7 +430,7 @@ def cpu_reference(frames):
         dt = time.perf_counter() - t0
     v = N_LCU * frames / dt
     return {"value": v, "unit": "CTU/s", "fps": v / N_LCU, "cores": min(nthreads, frames), "kind": "reference",
-            "sample": f"{frames} full 4K frames of the same stages and jobs through the reference's own functions (MotionEstimateLcu, "
+            "sample": f"{frames} full 4K frames of the same stages and jobs through the reference's own functions (MotionEstimateLcu, OpenLoopIntraSearchLcu, "
                       f"EncodePassInterPrediction, EstimateTransform/UnifiedQuantizeInvQuantize/EncodeInvTransform, LCU DLF drivers, SAO gather/apply; "
                       f"{variant} rows), one frame per host thread, {nthreads} threads"}
 

@@ -30,6 +30,7 @@ struct PlaneD {
 };
 struct MeArgs {
     svtb200_me_config cfg;
+    int sp_fp, sp_sp, sp_f_bytes, sp_p_bytes;   // sub-pel planes: pitches and bytes of the F plane / of each of B, H, J
     PlaneD src[3];        // full, quarter, sixteenth
     PlaneD ref[2][3];
     svtb200_me_pu_result *results;
@@ -394,12 +395,185 @@ __device__ void fullpel_search(const uint8_t *s_src, const uint8_t *s_win, int w
       }
 }
 
+
+// ---- sub-pel refinement --------------------------------------------------------------------------
+// EbHevcInterpolateSearchRegionAVC :645 (AvcStyleLumaInterpolationFilterHorizontal / Vertical, C_DEFAULT/EbAvcStyleMcp_C.c:34,62, half-sample
+// taps {-2, 18, 18, -2}, (+16) >> 5), PU_HalfPelRefinement :733 / EbHevcHalfPelSearch_LCU :1036, SetQuarterPelRefinementInputsOnTheFly :1540,
+// PU_QuarterPelRefinementOnTheFly :1226 / QuarterPelSearch_LCU :1623, SuPelEnable :3035.
+// The reference interpolates three half-sample planes over the whole search region of the LCU and indexes them per PU; here the same
+// planes live in shared memory (per list, kept until bi-prediction).  Plane coordinates relative to the search-area origin O:
+//   F(x, y) integer sample O + (x, y);  B(c, y) = (c - 1/2, y);  H(x, r) = (x, r - 1/2);  J(c, r) = (c - 1/2, r - 1/2) filtered from the ROUNDED B.
+// F is staged by load_window_t (pitch fp, misalignment a); B / H / J share the pitch sp.  All carry a 2-sample apron.
+struct SpList {
+    uint8_t *F, *B, *H, *J;
+    int fp, sp, a;
+    int sox, soy, saw, sah;
+};
+__device__ __forceinline__ const uint8_t *spF(const SpList &L, int x, int y) { return L.F + (y + 2) * L.fp + (x + 2) + L.a; }
+__device__ __forceinline__ const uint8_t *spP(const uint8_t *pl, const SpList &L, int x, int y) { return pl + (y + 2) * L.sp + (x + 2); }
+__device__ __forceinline__ const uint8_t *sp_plane(const SpList &L, int which, int x, int y)
+{
+    return which == 0 ? spF(L, x, y) : spP(which == 1 ? L.B : which == 2 ? L.H : L.J, L, x, y);
+}
+__device__ __forceinline__ int sp_pitch(const SpList &L, int which) { return which == 0 ? L.fp : L.sp; }
+__device__ __forceinline__ uint32_t lds_u32u(const uint8_t *p)
+{
+    const uint32_t *w = (const uint32_t *)((uintptr_t)p & ~(uintptr_t)3);
+    return __funnelshift_r(w[0], w[1], (uint32_t)((uintptr_t)p & 3) * 8);
+}
+__device__ __forceinline__ int half4(int a, int b, int c, int d) { return min(max((-2 * a + 18 * b + 18 * c - 2 * d + 16) >> 5, 0), 255); }
+
+__device__ void sp_build(SpList &L, const PlaneD &rF, int ox, int oy)
+{
+    __syncthreads();
+    const int a = load_window_t<NT>(L.F, L.fp, pat(rF, ox + L.sox - 2, oy + L.soy - 2), rF.stride, L.saw + 68, L.sah + 68);
+    if (threadIdx.x == 0) L.a = a;
+    __syncthreads();
+    const int bw = L.saw + 65, hw = L.saw + 66;
+    for (int i = threadIdx.x; i < (L.sah + 67) * bw; i += NT) {
+        const int r = i / bw, c = i - r * bw, y = r - 2;
+        const uint8_t *f = spF(L, c, y);
+        ((uint8_t *)spP(L.B, L, c, y))[0] = (uint8_t)half4(f[-2], f[-1], f[0], f[1]);
+    }
+    for (int i = threadIdx.x; i < (L.sah + 64) * hw; i += NT) {
+        const int r = i / hw, x = i - r * hw - 1;
+        const uint8_t *f = spF(L, x, r);
+        ((uint8_t *)spP(L.H, L, x, r))[0] = (uint8_t)half4(f[-2 * L.fp], f[-L.fp], f[0], f[L.fp]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (L.sah + 64) * bw; i += NT) {
+        const int r = i / bw, c = i - r * bw;
+        const uint8_t *b = spP(L.B, L, c, r);
+        ((uint8_t *)spP(L.J, L, c, r))[0] = (uint8_t)half4(b[-2 * L.sp], b[-L.sp], b[0], b[L.sp]);
+    }
+    __syncthreads();
+}
+
+// SAD of one PU against a plane position (p2 == nullptr) or the rounded average of two; sub: even rows only, doubled (SUB_SAD_SEARCH)
+__device__ __forceinline__ uint32_t sp_pu_sad(const uint8_t *s_src, int px, int py, int sz, const uint8_t *p1, int pitch1, const uint8_t *p2, int pitch2, bool sub)
+{
+    const int step = sub ? 2 : 1, nw = sz >> 2;
+    uint32_t acc = 0;
+    for (int r = 0; r < sz; r += step)
+        for (int j = 0; j < nw; ++j) {
+            const uint32_t sw = ((const uint32_t *)s_src)[(py + r) * 16 + (px >> 2) + j];
+            uint32_t pw = lds_u32u(p1 + r * pitch1 + 4 * j);
+            if (p2) pw = __vavgu4(pw, lds_u32u(p2 + r * pitch2 + 4 * j));
+            acc = __vsadu4(sw, pw) + acc;
+        }
+    return sub ? acc << 1 : acc;
+}
+
+// the two planes averaged at each of the 8 quarter positions (order L R T B TL TR BR BL) by the kind of the current best MV (0 integer, 1 horizontal
+// half, 2 vertical half, 3 diagonal half): {plane, dx, dy} x 2, planes 0 F, 1 B, 2 H, 3 J  (SetQuarterPelRefinementInputsOnTheFly :1540)
+__constant__ int8_t c_qpel[4][8][6] = {
+    {{1, 0, 0, 0, 0, 0}, {0, 0, 0, 1, 1, 0}, {2, 0, 0, 0, 0, 0}, {0, 0, 0, 2, 0, 1}, {1, 0, 0, 2, 0, 0}, {2, 0, 0, 1, 1, 0}, {2, 0, 1, 1, 1, 0}, {1, 0, 0, 2, 0, 1}},
+    {{0, -1, 0, 1, 0, 0}, {1, 0, 0, 0, 0, 0}, {3, 0, 0, 1, 0, 0}, {1, 0, 0, 3, 0, 1}, {2, -1, 0, 1, 0, 0}, {1, 0, 0, 2, 0, 0}, {1, 0, 0, 2, 0, 1}, {2, -1, 1, 1, 0, 0}},
+    {{3, 0, 0, 2, 0, 0}, {2, 0, 0, 3, 1, 0}, {0, 0, -1, 2, 0, 0}, {2, 0, 0, 0, 0, 0}, {1, 0, -1, 2, 0, 0}, {2, 0, 0, 1, 1, -1}, {2, 0, 0, 1, 1, 0}, {1, 0, 0, 2, 0, 0}},
+    {{2, -1, 0, 3, 0, 0}, {3, 0, 0, 2, 0, 0}, {1, 0, -1, 3, 0, 0}, {3, 0, 0, 1, 0, 0}, {2, -1, 0, 1, 0, -1}, {1, 0, -1, 2, 0, 0}, {1, 0, 0, 2, 0, 0}, {2, -1, 0, 1, 0, 0}}};
+__constant__ int8_t c_sp_dx[8] = {-1, 1, 0, 0, -1, 1, 1, -1}, c_sp_dy[8] = {0, 0, -1, 1, -1, -1, 1, 1};   // L R T B TL TR BR BL
+__constant__ uint8_t c_sp_dir[8] = {7, 3, 1, 5, 0, 2, 4, 6};    // *_POSITION codes of those positions (TL 0, T 1, TR 2, R 3, BR 4, B 5, BL 6, L 7)
+
+// bi-prediction: per fractional position (x & 3) + ((y & 3) << 2) the plane, or the two planes whose rounded average is the list's prediction
+// (SelectBuffer :2440, QuarterPelCompensation :2490); {plane, dx, dy, plane2 or -1, dx2, dy2} relative to the integer part of the MV
+__constant__ int8_t c_bip[16][6] = {{0, 0, 0, -1, 0, 0}, {0, 0, 0, 1, 1, 0}, {1, 1, 0, -1, 0, 0}, {1, 1, 0, 0, 1, 0}, {0, 0, 0, 2, 0, 1}, {1, 1, 0, 2, 0, 1}, {1, 1, 0, 3, 1, 1}, {1, 1, 0, 2, 1, 1},
+                                    {2, 0, 1, -1, 0, 0}, {2, 0, 1, 3, 1, 1}, {3, 1, 1, -1, 0, 0}, {3, 1, 1, 2, 1, 1}, {2, 0, 1, 0, 0, 1}, {2, 0, 1, 1, 1, 1}, {3, 1, 1, 1, 1, 1}, {2, 1, 1, 1, 1, 1}};
+
+// Half- and quarter-pel refinement of the PUs of one list.  s_d: [84][8] scratch, s_dir: psubPelDirection per n-slot, s_en: [3] size enables.
+__device__ void sp_refine(const SpList &L, const uint8_t *s_src, uint32_t *s_bsad, uint32_t *s_bmv, uint32_t *s_d, uint8_t *s_dir, const int *s_en, bool no8, bool sub)
+{
+    for (int pass = 0; pass < 2; ++pass) {
+        // (A) one thread per (PU, position): the distortion
+        for (int t = threadIdx.x; t < 84 * 8; t += NT) {
+            const int n = 1 + (t >> 3), pos = t & 7;
+            int px, py, sz;
+            pu_geom(n, px, py, sz);
+            const bool on = sz == 32 ? s_en[0] : sz == 16 ? s_en[1] : (s_en[2] && !no8);
+            uint32_t d = 0xffffffffu;
+            if (on) {
+                const uint32_t mv = s_bmv[n];
+                const int xmv = s16(mv & 0xffff), ymv = s16(mv >> 16);
+                if (pass == 0) {
+                    const int xs = (xmv >> 2) - L.sox + px, ys = (ymv >> 2) - L.soy + py;
+                    // L R: B(xs), B(xs + 1);  T B: H(ys), H(ys + 1);  TL TR BR BL: J
+                    const uint8_t *p = pos < 2 ? spP(L.B, L, xs + pos, ys) : pos < 4 ? spP(L.H, L, xs, ys + pos - 2)
+                                                : spP(L.J, L, xs + (pos == 5 || pos == 6), ys + (pos >= 6));
+                    d = sp_pu_sad(s_src, px, py, sz, p, L.sp, nullptr, 0, sub);
+                } else {
+                    const int kind = (ymv & 2) + ((xmv & 2) >> 1);
+                    // valid when the half-pel direction is this position or one of its two ring neighbours (integer best), or the opposite three (half best)
+                    const int want = (c_sp_dir[pos] + (kind ? 4 : 0)) & 7, diff = (s_dir[n] - want) & 7;
+                    if (diff == 0 || diff == 1 || diff == 7) {
+                        const int xs = ((xmv + 2) >> 2) - L.sox + px, ys = ((ymv + 2) >> 2) - L.soy + py;
+                        const int8_t *q = c_qpel[kind][pos];
+                        d = sp_pu_sad(s_src, px, py, sz, sp_plane(L, q[0], xs + q[1], ys + q[2]), sp_pitch(L, q[0]), sp_plane(L, q[3], xs + q[4], ys + q[5]), sp_pitch(L, q[3]), sub);
+                    }
+                }
+            }
+            s_d[t] = d;
+        }
+        __syncthreads();
+        // (B) one thread per PU: the reference's sequential update (strict '<', order L R T B TL TR BR BL)
+        for (int n = 1 + threadIdx.x; n < 85; n += NT) {
+            const uint32_t *d = s_d + (n - 1) * 8;
+            if (d[0] == 0xffffffffu && pass == 0) continue;      // size not refined on this LCU
+            uint32_t bs = s_bsad[n], mv = s_bmv[n];
+            const int xmv = s16(mv & 0xffff), ymv = s16(mv >> 16), stepmv = pass == 0 ? 2 : 1;
+            uint32_t best = 0xffffffffu;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (d[k] < bs) { bs = d[k]; mv = ((uint32_t)(uint16_t)(ymv + c_sp_dy[k] * stepmv) << 16) | (uint16_t)(xmv + c_sp_dx[k] * stepmv); }
+                best = min(best, d[k]);
+            }
+            s_bsad[n] = bs; s_bmv[n] = mv;
+            if (pass == 0) {   // first match in the order L R T B TL TR BL BR (:1000-1023)
+                const int order[8] = {0, 1, 2, 3, 4, 5, 7, 6};
+                int dir = 0;
+#pragma unroll
+                for (int k = 7; k >= 0; --k) if (d[order[k]] == best) dir = c_sp_dir[order[k]];
+                s_dir[n] = (uint8_t)dir;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// SuPelEnable :3035 (fractionalSearchModel 1): per-size gates from the LCU means of the full-pel MVs and SADs; warp 0
+__device__ void sp_enables(const uint32_t *s_bsad, const uint32_t *s_bmv, int model, int tl, bool cu16_on, int *s_en)
+{
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    int e[3] = {1, 1, 1};
+    if (model == 1) {
+        uint32_t mag[3], avg[3];
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            const int first = l == 0 ? 1 : l == 1 ? 5 : 21, cnt = l == 0 ? 4 : l == 1 ? 16 : 64, sh = 2 + 2 * l;
+            int sx = 0, sy = 0; uint32_t sd = 0;
+            for (int k = lane; k < cnt; k += 32) { const uint32_t mv = s_bmv[first + k]; sx += s16(mv & 0xffff); sy += s16(mv >> 16); sd += s_bsad[first + k]; }
+            sx = (int)warp_sum((uint32_t)sx); sy = (int)warp_sum((uint32_t)sy); sd = warp_sum(sd);
+            const uint32_t ax = (uint32_t)(sx >> sh), ay = (uint32_t)(sy >> sh);
+            mag[l] = ax * ax + ay * ay;
+            avg[l] = sd >> sh;
+        }
+        const uint32_t thr = tl == 1 ? 32 * 32 : tl == 2 ? 80 * 80 : 48 * 48;
+        const int c32 = (mag[0] < thr ? 0 : 2) + (avg[0] < 32 * 32 * 6 ? 0 : 1), c16 = (mag[1] < thr ? 0 : 2) + (avg[1] < 16 * 16 * 2 ? 0 : 1), c8 = (mag[2] < thr ? 0 : 2) + (avg[2] < 8 * 8 * 2 ? 0 : 1);
+        const int row = tl > 2 ? 3 : tl;
+        // 32x32 gate per temporal layer row {0, 1, 2, other} and class: {1,0,1,0} {1,0,1,1} {1,0,1,0} {1,1,1,0}, bit (row * 4 + class)
+        e[0] = (int)((((0x5u) | (0xDu << 4) | (0x5u << 8) | (0x7u << 12)) >> (row * 4 + c32)) & 1u);
+        e[1] = c16 & 1;
+        e[2] = (row == 3 && c8 == 3) ? 0 : (c8 & 1);
+    }
+    if (lane == 0) { s_en[0] = e[0]; s_en[1] = e[1] && cu16_on; s_en[2] = e[2]; }
+}
+
 struct HmeRes { uint32_t sad; int x, y; };   // sad already doubled may exceed 24 bits -> keep 32
 
 // ============================================================================================
 // Picture kernel: one CTA per LCU
 // ============================================================================================
-__global__ void __launch_bounds__(NT, 3) me_picture_kernel(const __grid_constant__ MeArgs A)
+template <bool SUBPEL>
+__global__ void __launch_bounds__(NT, SUBPEL ? 2 : 3) me_picture_kernel(const __grid_constant__ MeArgs A)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *s_src = smem;                                   // 64*64
@@ -413,6 +587,10 @@ __global__ void __launch_bounds__(NT, 3) me_picture_kernel(const __grid_constant
     uint32_t *s_red32 = s_bi + 85 + 1;                       // [8*6]
     unsigned long long *s_red64 = (unsigned long long *)(s_red32 + 48);   // [8]
     uint8_t *s_win = (uint8_t *)(((uintptr_t)(s_red64 + 8) + 15) & ~(uintptr_t)15);
+    __shared__ SpList s_spl[2];
+    __shared__ int s_en[4];
+    __shared__ uint8_t s_dir[88];
+    uint32_t *s_d = (uint32_t *)(s_win + A.win_bytes);      // [84][8], then the planes of both lists (SUBPEL only)
 
     const svtb200_me_config &cfg = A.cfg;
     const int lcu = blockIdx.x, lx = lcu % A.cols, ly = lcu / A.cols;
@@ -624,6 +802,19 @@ __global__ void __launch_bounds__(NT, 3) me_picture_kernel(const __grid_constant
             __syncthreads();
             fullpel_search(s_src, s_win, wp, a, sox, soy, saw, sah, s_sad8, s_sum, s_bsad + li * 85, s_bmv + li * 85);
         }
+        if (SUBPEL) {   // MotionEstimateLcu :4242-4316
+            __syncthreads();
+            SpList &L = s_spl[li];
+            if (threadIdx.x == 0) {
+                uint8_t *base = (uint8_t *)(s_d + 84 * 8) + (size_t)li * (A.sp_f_bytes + 3 * A.sp_p_bytes);
+                L.F = base; L.B = base + A.sp_f_bytes; L.H = L.B + A.sp_p_bytes; L.J = L.H + A.sp_p_bytes;
+                L.fp = A.sp_fp; L.sp = A.sp_sp; L.a = 0;
+                L.sox = sox; L.soy = soy; L.saw = saw; L.sah = sah;
+            }
+            sp_enables(s_bsad + li * 85, s_bmv + li * 85, cfg.fractional_search_model, cfg.temporal_layer, cfg.cu16x16_mode == 0, s_en);
+            sp_build(L, rF, ox, oy);
+            sp_refine(L, s_src, s_bsad + li * 85, s_bmv + li * 85, s_d, s_dir, s_en, cfg.cu8x8_mode == 1, cfg.fractional_search_method == 0);
+        }
     }
     (void)sa_w;
     __syncthreads();
@@ -633,22 +824,47 @@ __global__ void __launch_bounds__(NT, 3) me_picture_kernel(const __grid_constant
     if (nl == 2) {
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         const int npu = cfg.cu16x16_mode ? 5 : (cfg.cu8x8_mode ? 21 : 85);
+        const bool sub = cfg.fractional_search_method == 0;
         for (int n = wid; n < npu; n += NT / 32) {
             int px, py, sz;
             pu_geom(n, px, py, sz);
-            const int x0 = s16(s_bmv[n] & 0xffff) >> 2, y0 = s16(s_bmv[n] >> 16) >> 2;
-            const int x1 = s16(s_bmv[85 + n] & 0xffff) >> 2, y1 = s16(s_bmv[85 + n] >> 16) >> 2;
-            const int nw = sz >> 2, items = (sz >> 1) * nw;
+            const int nw = sz >> 2, step = sub ? 2 : 1, items = (sz / step) * nw;
             uint32_t acc = 0;
-            for (int i = lane; i < items; i += 32) {
-                const int r = i / nw, j = i - r * nw;
-                const uint32_t s = ((const uint32_t *)s_src)[(py + 2 * r) * 16 + (px >> 2) + j];
-                const uint32_t p0 = ld_u32_unaligned(pat(A.ref[0][0], ox + px + x0 + 4 * j, oy + py + y0 + 2 * r));
-                const uint32_t p1 = ld_u32_unaligned(pat(A.ref[1][0], ox + px + x1 + 4 * j, oy + py + y1 + 2 * r));
-                acc += __vsadu4(s, __vavgu4(p0, p1));
+            if (SUBPEL) {
+                // every list's prediction is one of its planes, or the rounded average of two, chosen by the fractional position
+                const uint8_t *pa[2], *pb[2];
+                int sa[2], sb[2];
+#pragma unroll
+                for (int l = 0; l < 2; ++l) {
+                    const SpList &L = s_spl[l];
+                    const uint32_t mv = s_bmv[l * 85 + n];
+                    const int mx = s16(mv & 0xffff), my = s16(mv >> 16);
+                    const int ix = (mx >> 2) - L.sox + px, iy = (my >> 2) - L.soy + py;
+                    const int8_t *q = c_bip[(mx & 3) + ((my & 3) << 2)];
+                    pa[l] = sp_plane(L, q[0], ix + q[1], iy + q[2]); sa[l] = sp_pitch(L, q[0]);
+                    pb[l] = q[3] < 0 ? nullptr : sp_plane(L, q[3], ix + q[4], iy + q[5]); sb[l] = q[3] < 0 ? 0 : sp_pitch(L, q[3]);
+                }
+                for (int i = lane; i < items; i += 32) {
+                    const int r = (i / nw) * step, j = i - (i / nw) * nw;
+                    const uint32_t sw = ((const uint32_t *)s_src)[(py + r) * 16 + (px >> 2) + j];
+                    uint32_t p0 = lds_u32u(pa[0] + r * sa[0] + 4 * j), p1 = lds_u32u(pa[1] + r * sa[1] + 4 * j);
+                    if (pb[0]) p0 = __vavgu4(p0, lds_u32u(pb[0] + r * sb[0] + 4 * j));
+                    if (pb[1]) p1 = __vavgu4(p1, lds_u32u(pb[1] + r * sb[1] + 4 * j));
+                    acc += __vsadu4(sw, __vavgu4(p0, p1));
+                }
+            } else {
+                const int x0 = s16(s_bmv[n] & 0xffff) >> 2, y0 = s16(s_bmv[n] >> 16) >> 2;
+                const int x1 = s16(s_bmv[85 + n] & 0xffff) >> 2, y1 = s16(s_bmv[85 + n] >> 16) >> 2;
+                for (int i = lane; i < items; i += 32) {
+                    const int r = (i / nw) * step, j = i - (i / nw) * nw;
+                    const uint32_t sw = ((const uint32_t *)s_src)[(py + r) * 16 + (px >> 2) + j];
+                    const uint32_t p0 = ld_u32_unaligned(pat(A.ref[0][0], ox + px + x0 + 4 * j, oy + py + y0 + r));
+                    const uint32_t p1 = ld_u32_unaligned(pat(A.ref[1][0], ox + px + x1 + 4 * j, oy + py + y1 + r));
+                    acc += __vsadu4(sw, __vavgu4(p0, p1));
+                }
             }
             acc = warp_sum(acc);
-            if (lane == 0) s_bi[n] = acc << 1;
+            if (lane == 0) s_bi[n] = sub ? acc << 1 : acc;
         }
     }
     __syncthreads();
@@ -726,7 +942,7 @@ static int validate_cfg(const svtb200_me_config *c)
 {
     if (!c || c->pic_width < 8 || c->pic_height < 8) { set_error("me: bad picture size"); return SVTB200_ERR_BAD_ARG; }
     if (c->num_lists < 1 || c->num_lists > 2 || c->hierarchical_levels > 5 || c->temporal_layer > c->hierarchical_levels) { set_error("me: bad list/layer configuration"); return SVTB200_ERR_BAD_ARG; }
-    if (c->fractional_search_model != 2) { set_error("me: sub-pel refinement (fractional_search_model != 2) not built yet"); return SVTB200_ERR_UNSUPPORTED; }
+    if (c->fractional_search_model > 2 || c->fractional_search_method > 1) { set_error("me: fractional_search_model 0..2; fractional_search_method 0 (SUB_SAD_SEARCH) or 1 (FULL_SAD_SEARCH) -- SSD_SEARCH (enc modes <= 4) is not built"); return SVTB200_ERR_UNSUPPORTED; }
     if (c->n_hme_regions_w > 2 || c->n_hme_regions_h > 2 || c->search_area_w == 0 || c->search_area_h == 0) { set_error("me: bad search configuration"); return SVTB200_ERR_BAD_ARG; }
     return SVTB200_OK;
 }
@@ -747,14 +963,25 @@ static int launch_me(const svtb200_me_config *cfg, const PlaneD src[3], const Pl
     A.results = results; A.best_sad = bs; A.best_mv = bm; A.rc = rc;
     A.cols = (cfg->pic_width + 63) / 64; A.rows = (cfg->pic_height + 63) / 64;
     A.win_bytes = me_window_bytes(*cfg);
-    const size_t smem = me_fixed_smem() + (size_t)A.win_bytes + 96;
-    if (smem > 227 * 1024) { set_error("me: search window needs %zu B of shared memory (> 227 KB)", smem); return SVTB200_ERR_UNSUPPORTED; }
-    static thread_local size_t smem_set = 0;
-    if (smem > smem_set) {
-        SVTB200_CUDA_TRY(cudaFuncSetAttribute(me_picture_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
-        smem_set = smem;
+    const bool subpel = cfg->fractional_search_model != 2;
+    size_t smem = me_fixed_smem() + (size_t)A.win_bytes + 96;
+    if (subpel) {   // [84][8] distortions + per list the integer plane with apron and the three half-sample planes
+        const int saw = std::min<int>(cfg->search_area_w, 127), sah = std::min<int>(cfg->search_area_h, 127);
+        A.sp_fp = win_pitch(saw + 68);
+        A.sp_sp = (saw + 68 + 4 + 3) & ~3;
+        A.sp_f_bytes = (A.sp_fp * (sah + 68) + 15) & ~15;
+        A.sp_p_bytes = (A.sp_sp * (sah + 68) + 15) & ~15;
+        smem += 84 * 8 * 4 + 2 * ((size_t)A.sp_f_bytes + 3 * (size_t)A.sp_p_bytes);
     }
-    me_picture_kernel<<<A.cols * A.rows, NT, smem, st>>>(A);
+    if (smem > 227 * 1024) { set_error("me: this search configuration needs %zu B of shared memory (> 227 KB)", smem); return SVTB200_ERR_UNSUPPORTED; }
+    static thread_local size_t smem_set[2] = {0, 0};
+    if (smem > smem_set[subpel]) {
+        if (subpel) SVTB200_CUDA_TRY(cudaFuncSetAttribute(me_picture_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+        else SVTB200_CUDA_TRY(cudaFuncSetAttribute(me_picture_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+        smem_set[subpel] = smem;
+    }
+    if (subpel) me_picture_kernel<true><<<A.cols * A.rows, NT, smem, st>>>(A);
+    else me_picture_kernel<false><<<A.cols * A.rows, NT, smem, st>>>(A);
     SVTB200_COUNT_LAUNCH();
     SVTB200_CUDA_TRY(cudaGetLastError());
     return SVTB200_OK;
