@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(IN_NT) intra_batch_kernel(const __grid_constan
 
 // ---- open-loop intra search -------------------------------------------------------------------------------------------------
 constexpr int OIS_NT = 256, OIS_NW = OIS_NT / 32;
-constexpr int SRC_P = 100, SRC_R = 97;      // staged source: rows / cols -1 .. 95 relative to the LCU origin
+constexpr int SRC_P = 128, SRC_R = 97;      // staged source: rows / cols -1 .. 95 relative to the LCU origin; pitch = win_pitch(97)
 constexpr int SAD_SLOTS = 36;
 
 struct OisArgs {
@@ -225,6 +225,7 @@ struct OisArgs {
     uint8_t *total;
     uint32_t *cand;
     int cap, lcu_cols;
+    int padded;               // the plane has >= 16 columns of padding left and right and a row above: stage with 128-bit loads
 };
 
 __constant__ uint8_t c_islice_modes[7] = {0, 1, 10, 26, 2, 18, 34};           // iSliceModesArray, EbMotionEstimation.c:148
@@ -249,7 +250,7 @@ __device__ __forceinline__ void cu_geometry(int cu, int &N, int &cx, int &cy)
 }
 
 // SAD of one predicted mode against the staged source, one warp; lanes take 4 horizontally adjacent samples each
-__device__ __forceinline__ uint32_t warp_mode_sad(const uint8_t *line, const ModeSetup &m, const uint8_t *s_src, int cx, int cy)
+__device__ __forceinline__ uint32_t warp_mode_sad(const uint8_t *line, const ModeSetup &m, const uint8_t *s_src, int cx, int cy)   // s_src: sample (-1, -1) of the LCU
 {
     const int N = m.N, q = N >> 2, lane = threadIdx.x & 31;
     uint32_t acc = 0;
@@ -264,7 +265,7 @@ __device__ __forceinline__ uint32_t warp_mode_sad(const uint8_t *line, const Mod
 
 __global__ void __launch_bounds__(OIS_NT) ois_picture_kernel(const __grid_constant__ OisArgs A)
 {
-    __shared__ uint8_t s_src[SRC_R * SRC_P];
+    __shared__ __align__(16) uint8_t s_raw[SRC_R * SRC_P];
     __shared__ uint8_t s_line[OIS_NW][4 * 32 + 4];
     __shared__ uint32_t s_sad[85][SAD_SLOTS];
     __shared__ int s_next;
@@ -276,10 +277,17 @@ __global__ void __launch_bounds__(OIS_NT) ois_picture_kernel(const __grid_consta
     // which mode list this picture runs per CU: 0 I slice, 1 all 35 (kernel level), 2 DC only, 3 DC + the nine stage-1 modes
     const int path = is_i ? 0 : cfg.ois_kernel_level ? 1 : cfg.limit_ois_to_dc_mode ? 2 : 3;
 
-    for (int i = threadIdx.x; i < SRC_R * SRC_R; i += OIS_NT) {
-        const int r = i / SRC_R, c = i - r * SRC_R, gx = ox + c - 1, gy = oy + r - 1;
-        s_src[r * SRC_P + c] = (gx >= 0 && gy >= 0 && gx < W && gy < H) ? __ldg(A.src + (ptrdiff_t)gy * A.stride + gx) : 128;
+    int a0 = 0;
+    if (A.padded) {
+        // only samples inside the picture are ever used (the line builder tests the picture bounds), so stop at its edge
+        a0 = load_window_t<OIS_NT>(s_raw, SRC_P, A.src + (ptrdiff_t)(oy - 1) * A.stride + ox - 1, A.stride, min(SRC_R, W - ox + 1), min(SRC_R, H - oy + 1));
+    } else {
+        for (int i = threadIdx.x; i < SRC_R * SRC_R; i += OIS_NT) {
+            const int r = i / SRC_R, c = i - r * SRC_R, gx = ox + c - 1, gy = oy + r - 1;
+            s_raw[r * SRC_P + c] = (gx >= 0 && gy >= 0 && gx < W && gy < H) ? __ldg(A.src + (ptrdiff_t)gy * A.stride + gx) : 128;
+        }
     }
+    const uint8_t *s_src = s_raw + a0;
     if (threadIdx.x == 0) s_next = 1;
     __syncthreads();
 
@@ -444,11 +452,15 @@ static int ois_check(const svtb200_ois_config *cfg, const svtb200_plane *src, co
     return SVTB200_OK;
 }
 
-static int ois_launch(const svtb200_ois_config &cfg, const uint8_t *src00, int stride, const svtb200_me_pu_result *me, uint8_t *total, uint32_t *cand, uint32_t cap, cudaStream_t st)
+// the staging window starts 1 sample left of / above the LCU and the 128-bit loader rounds rows out to 16 bytes on both sides
+static int ois_padded(const svtb200_plane &p) { return p.origin_x >= 16 && p.origin_y >= 1 && p.stride >= (uint32_t)p.origin_x + p.width + 16; }
+
+static int ois_launch(const svtb200_ois_config &cfg, const uint8_t *src00, int stride, int padded, const svtb200_me_pu_result *me, uint8_t *total, uint32_t *cand, uint32_t cap, cudaStream_t st)
 {
     OisArgs A;
     A.cfg = cfg; A.src = src00; A.stride = stride; A.me = me; A.total = total; A.cand = cand; A.cap = (int)cap;
     A.lcu_cols = (cfg.pic_width + 63) / 64;
+    A.padded = padded;
     const int n_lcu = A.lcu_cols * ((cfg.pic_height + 63) / 64);
     ois_picture_kernel<<<n_lcu, OIS_NT, 0, st>>>(A);
     SVTB200_COUNT_LAUNCH();
@@ -536,7 +548,7 @@ int svtb200_ois_picture_dev(const svtb200_ois_config *cfg, const svtb200_plane *
     if (rc) return rc;
     if ((rc = ensure_device())) return rc;
     const uint8_t *s00 = src_luma_dev->buf + (size_t)src_luma_dev->origin_y * src_luma_dev->stride + src_luma_dev->origin_x;
-    return ois_launch(*cfg, s00, (int)src_luma_dev->stride, me_results_dev, total_modes_dev, cand_dev, cand_capacity, (cudaStream_t)cuda_stream);
+    return ois_launch(*cfg, s00, (int)src_luma_dev->stride, ois_padded(*src_luma_dev), me_results_dev, total_modes_dev, cand_dev, cand_capacity, (cudaStream_t)cuda_stream);
 }
 
 int svtb200_ois_picture(const svtb200_ois_config *cfg, const svtb200_plane *src_luma, const svtb200_me_pu_result *me_results, uint8_t *total_modes, uint32_t *cand,
@@ -556,7 +568,7 @@ int svtb200_ois_picture(const svtb200_ois_config *cfg, const svtb200_plane *src_
     SVTB200_CUDA_TRY(cudaMemcpyAsync(ds, src_luma->buf, sb, cudaMemcpyHostToDevice, c->stream));
     if (mb) SVTB200_CUDA_TRY(cudaMemcpyAsync(dm, me_results, mb, cudaMemcpyHostToDevice, c->stream));
     const uint8_t *s00 = (const uint8_t *)ds + (size_t)src_luma->origin_y * src_luma->stride + src_luma->origin_x;
-    if ((rc = ois_launch(*cfg, s00, (int)src_luma->stride, (const svtb200_me_pu_result *)dm, (uint8_t *)dt, (uint32_t *)dc, cand_capacity, c->stream))) return rc;
+    if ((rc = ois_launch(*cfg, s00, (int)src_luma->stride, ois_padded(*src_luma), (const svtb200_me_pu_result *)dm, (uint8_t *)dt, (uint32_t *)dc, cand_capacity, c->stream))) return rc;
     SVTB200_CUDA_TRY(cudaMemcpyAsync(total_modes, dt, tb, cudaMemcpyDeviceToHost, c->stream));
     SVTB200_CUDA_TRY(cudaMemcpyAsync(cand, dc, cb, cudaMemcpyDeviceToHost, c->stream));
     SVTB200_CUDA_TRY(cudaStreamSynchronize(c->stream));

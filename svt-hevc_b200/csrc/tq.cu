@@ -38,6 +38,9 @@ struct TqArgs {
 };
 
 __constant__ int8_t c_dct32[32][32];    // M32[k][n]; M_N[k][n] = M32[k * 32 / N][n]
+// the same matrix and its per-size transposes T_N[n][k] = M_N[k][n] (pitch 32) in global memory: every CTA stages both with 128-bit loads
+__device__ __align__(16) int8_t g_dct32[32 * 32];
+__device__ __align__(16) int8_t g_dct_t[4][32 * 32];   // [log2 N - 2]
 __constant__ int8_t c_dst4[4][4] = {{29, 55, 74, 84}, {74, 74, 0, -74}, {84, -29, -74, 55}, {55, -84, 74, -29}};
 __constant__ uint32_t c_qfunc[6] = {26214, 23302, 20560, 18396, 16384, 14564};   // QFunc, Codec/EbTransforms.h:26
 __constant__ uint32_t c_ffunc[6] = {40, 45, 51, 57, 64, 72};                      // FFunc, :27
@@ -111,13 +114,16 @@ __device__ __forceinline__ int dp2a_hi(uint32_t a_s16x2, uint32_t b_s8x4, int c)
     return d;
 }
 
+__device__ __forceinline__ int ilog2d(int v) { return 31 - __clz(v); }
+__device__ __forceinline__ uint32_t pack2(int lo, int hi) { return (uint32_t)(uint16_t)lo | ((uint32_t)(uint16_t)hi << 16); }
+
 // First butterfly stage of the 16/32-point forward passes, kept in 16 bits like PartialButterfly{16,32}Estimate:
 // out[r][0..N/2) = x[n] + x[N-1-n], out[r][N/2..N) = x[n] - x[N-1-n].
 __device__ void fold_rows(const int16_t *in, int16_t *out, int N, int rows)
 {
-    const int h = N >> 1;
+    const int h = N >> 1, lgh = ilog2d(h);
     for (int i = threadIdx.x; i < rows * h; i += TQ_NT) {
-        const int r = i / h, n = i - r * h;
+        const int r = i >> lgh, n = i & (h - 1);
         const int a = in[r * TP + n], b = in[r * TP + N - 1 - n];
         out[r * TP + n] = (int16_t)(a + b);
         out[r * TP + h + n] = (int16_t)(a - b);
@@ -132,9 +138,9 @@ __device__ void fold_rows(const int16_t *in, int16_t *out, int N, int rows)
 template <bool CLIP>
 __device__ void rowdot(const int8_t *A, int lda, const int16_t *B, int odd_off, int I, int J, int Nn, int off, int shift, int16_t *out, int osi, int osj)
 {
-    const int Jh = J >> 1, n4 = Nn >> 2;
+    const int Jh = J >> 1, n4 = Nn >> 2, lgI = ilog2d(I);
     for (int it = threadIdx.x; it < I * Jh; it += TQ_NT) {
-        const int j = it / I, i = it - j * I;
+        const int j = it >> lgI, i = it & (I - 1);
         const uint32_t *b = (const uint32_t *)(B + i * TP + ((j & 1) ? odd_off : 0));
         const uint32_t *a0 = (const uint32_t *)(A + j * lda), *a1 = (const uint32_t *)(A + (j + Jh) * lda);
         int c0 = 0, c1 = 0;
@@ -150,11 +156,10 @@ __device__ void rowdot(const int8_t *A, int lda, const int16_t *B, int odd_off, 
     }
 }
 
-__device__ __forceinline__ int ilog2d(int v) { return 31 - __clz(v); }
 
 // The whole chain for one TU held in shared memory.  s_a: residual in (pitch TP); returns nz.
 // On exit s_a holds the reconstructed residual (if nz && want_recon), s_q the quantised coefficients (act x act corner).
-__device__ uint32_t tq_chain(const int8_t *s_m, const int8_t *s_mt, int16_t *s_a, int16_t *s_b, int16_t *s_q, uint32_t *s_cnt, const svtb200_tq_job &t, bool want_recon)
+__device__ uint32_t tq_chain(const int8_t *s_m, const int8_t *s_mt, int16_t *s_a, int16_t *s_b, int16_t *s_q, uint32_t *s_cnt, const svtb200_tq_job &t, bool want_recon, bool prefolded)
 {
     const int N = t.size, lg = ilog2d(N);
     const bool dst = t.dst4x4 != 0;
@@ -189,7 +194,7 @@ __device__ uint32_t tq_chain(const int8_t *s_m, const int8_t *s_mt, int16_t *s_a
         } else {
             const bool fold = N >= 16;
             const int Nn = fold ? N >> 1 : N, lda = (32 / N) * 32;
-            if (fold) { fold_rows(s_a, s_q, N, N); __syncthreads(); }
+            if (fold && !prefolded) { fold_rows(s_a, s_q, N, N); __syncthreads(); }
             rowdot<false>(s_m, lda, fold ? s_q : s_a, fold ? Nn : 0, N, act, Nn, 1 << (s1 - 1), s1, s_b, 1, TP);       // s_b[k][r]
             __syncthreads();
             if (fold) { fold_rows(s_b, s_q, N, act); __syncthreads(); }
@@ -211,7 +216,7 @@ __device__ uint32_t tq_chain(const int8_t *s_m, const int8_t *s_mt, int16_t *s_a
     const bool fast = !dst && !only_dc;          // DP2A inverse: dequantised coefficients are kept TRANSPOSED (s_b[u][v])
     const int rsy = fast ? 1 : TP, rsx = fast ? TP : 1;
     for (int i = threadIdx.x; i < N * N; i += TQ_NT) {
-        const int y = i / N, x = i - y * N;
+        const int y = i >> lg, x = i & (N - 1);
         int16_t qv = 0, rv = 0;
         if (y < act && x < act) {
             const int c = s_a[y * TP + x];
@@ -282,37 +287,86 @@ __global__ void __launch_bounds__(TQ_NT) tq_batch_kernel(const __grid_constant__
 {
     __shared__ __align__(16) int16_t s_a[32 * TP], s_b[32 * TP], s_q[32 * TP];
     __shared__ uint32_t s_cnt;
-    __shared__ __align__(16) int8_t s_m[32 * 32];
+    __shared__ __align__(16) int8_t s_m[32 * 32], s_mt[32 * 32];
     const int j = blockIdx.x;
     if (j >= A.n_jobs) return;
-    __shared__ __align__(16) int8_t s_mt[32 * 32];
-    for (int i = threadIdx.x; i < 256; i += TQ_NT) ((uint32_t *)s_m)[i] = ((const uint32_t *)c_dct32)[i];
     const svtb200_tq_job t = A.jobs[j];
-    {   // transposed matrix of this TU size: s_mt[n][k] = M_N[k][n] = M32[k * 32 / N][n]
-        const int Nq = t.size, ks = 32 / Nq;
-        __syncthreads();
-        for (int i = threadIdx.x; i < Nq * Nq; i += TQ_NT) { const int k = i / Nq, n = i - k * Nq; s_mt[n * 32 + k] = s_m[k * ks * 32 + n]; }
-    }
-    const int N = t.size, pl = t.plane;
-    const uint8_t *s = A.src.p[pl] + (size_t)(A.src.oy[pl] + t.y) * A.src.stride[pl] + A.src.ox[pl] + t.x;
-    const uint8_t *p = A.pred.p[pl] + (size_t)(A.pred.oy[pl] + t.y) * A.pred.stride[pl] + A.pred.ox[pl] + t.x;
-    uint8_t *r = A.recon.p[pl] + (size_t)(A.recon.oy[pl] + t.y) * A.recon.stride[pl] + A.recon.ox[pl] + t.x;
-    for (int i = threadIdx.x; i < N * N; i += TQ_NT) {
-        const int y = i / N, x = i - y * N;
-        s_a[y * TP + x] = (int16_t)((int)s[(size_t)y * A.src.stride[pl] + x] - (int)p[(size_t)y * A.pred.stride[pl] + x]);
+    const int N = t.size, pl = t.plane, lg = ilog2d(N);
+    // core matrix and the transpose of this TU size: 64 + 64 128-bit loads
+    if (threadIdx.x < 64) ((uint4 *)s_m)[threadIdx.x] = ((const uint4 *)g_dct32)[threadIdx.x];
+    else ((uint4 *)s_mt)[threadIdx.x - 64] = ((const uint4 *)g_dct_t[lg - 2])[threadIdx.x - 64];
+    const int ss = A.src.stride[pl], ps = A.pred.stride[pl], rs = A.recon.stride[pl], cs = A.cstride[pl];
+    const uint8_t *s = A.src.p[pl] + (size_t)(A.src.oy[pl] + t.y) * ss + A.src.ox[pl] + t.x;
+    const uint8_t *p = A.pred.p[pl] + (size_t)(A.pred.oy[pl] + t.y) * ps + A.pred.ox[pl] + t.x;
+    uint8_t *r = A.recon.p[pl] + (size_t)(A.recon.oy[pl] + t.y) * rs + A.recon.ox[pl] + t.x;
+    int16_t *co = A.coeff[pl] + (size_t)t.y * cs + t.x;
+    const bool vec_in = ((((uintptr_t)s | (uintptr_t)p) | (uintptr_t)(ss | ps)) & 3) == 0;
+    // residual; for the 16- and 32-point DCT the first butterfly stage (x[n] +- x[N-1-n], kept in 16 bits like
+    // PartialButterfly{16,32}Estimate) is applied on the way in: s_q[r][0..N/2) sums, [N/2..N) differences
+    const bool prefold = vec_in && N >= 16 && !t.dst4x4 && t.shape != SVTB200_SHAPE_ONLY_DC;
+    if (prefold) {
+        const int h = N >> 1, w8 = N >> 3, lw8 = lg - 3;
+        for (int i = threadIdx.x; i < N * w8; i += TQ_NT) {
+            const int y = i >> lw8, q = i & (w8 - 1), xl = 4 * q, xr = N - 4 - 4 * q;
+            const uint32_t sl = *(const uint32_t *)(s + (size_t)y * ss + xl), sr = *(const uint32_t *)(s + (size_t)y * ss + xr);
+            const uint32_t pl_ = *(const uint32_t *)(p + (size_t)y * ps + xl), pr = *(const uint32_t *)(p + (size_t)y * ps + xr);
+            int a[4], b[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                a[e] = (int)((sl >> (8 * e)) & 0xff) - (int)((pl_ >> (8 * e)) & 0xff);
+                b[e] = (int)((sr >> (8 * (3 - e))) & 0xff) - (int)((pr >> (8 * (3 - e))) & 0xff);     // mirror sample N-1-(xl+e)
+            }
+            uint32_t *o = (uint32_t *)(s_q + y * TP);
+            o[(xl >> 1)] = pack2(a[0] + b[0], a[1] + b[1]); o[(xl >> 1) + 1] = pack2(a[2] + b[2], a[3] + b[3]);
+            o[((h + xl) >> 1)] = pack2(a[0] - b[0], a[1] - b[1]); o[((h + xl) >> 1) + 1] = pack2(a[2] - b[2], a[3] - b[3]);
+        }
+    } else if (vec_in) {
+        const int w4 = N >> 2, lw4 = lg - 2;
+        for (int i = threadIdx.x; i < N * w4; i += TQ_NT) {
+            const int y = i >> lw4, x = (i & (w4 - 1)) * 4;
+            const uint32_t sw = *(const uint32_t *)(s + (size_t)y * ss + x), pw = *(const uint32_t *)(p + (size_t)y * ps + x);
+            uint32_t *o = (uint32_t *)(s_a + y * TP + x);
+            o[0] = pack2((int)(sw & 0xff) - (int)(pw & 0xff), (int)((sw >> 8) & 0xff) - (int)((pw >> 8) & 0xff));
+            o[1] = pack2((int)((sw >> 16) & 0xff) - (int)((pw >> 16) & 0xff), (int)(sw >> 24) - (int)(pw >> 24));
+        }
+    } else {
+        for (int i = threadIdx.x; i < N * N; i += TQ_NT) {
+            const int y = i >> lg, x = i & (N - 1);
+            s_a[y * TP + x] = (int16_t)((int)s[(size_t)y * ss + x] - (int)p[(size_t)y * ps + x]);
+        }
     }
     __syncthreads();
     const bool want_recon = !(t.flags & SVTB200_TQ_SKIP_RECON);
-    const uint32_t nz = tq_chain(s_m, s_mt, s_a, s_b, s_q, &s_cnt, t, want_recon);
+    const uint32_t nz = tq_chain(s_m, s_mt, s_a, s_b, s_q, &s_cnt, t, want_recon, prefold);
     if (threadIdx.x == 0) A.nz[j] = nz;
-    int16_t *co = A.coeff[pl] + (size_t)t.y * A.cstride[pl] + t.x;
-    for (int i = threadIdx.x; i < N * N; i += TQ_NT) {
-        const int y = i / N, x = i - y * N;
-        co[(size_t)y * A.cstride[pl] + x] = s_q[y * TP + x];
-        if (want_recon) {
-            const int pv = p[(size_t)y * A.pred.stride[pl] + x];
-            const int v = nz ? min(max(pv + s_b[y * TP + x], 0), 255) : pv;
-            if (nz || r != p) r[(size_t)y * A.recon.stride[pl] + x] = (uint8_t)v;
+    const bool vec_out = vec_in && ((((uintptr_t)r | (uintptr_t)rs) & 3) == 0) && ((((uintptr_t)co | (uintptr_t)(cs * 2)) & 7) == 0);
+    if (vec_out) {
+        const int w4 = N >> 2, lw4 = lg - 2;
+        for (int i = threadIdx.x; i < N * w4; i += TQ_NT) {
+            const int y = i >> lw4, x = (i & (w4 - 1)) * 4;
+            const uint32_t *q = (const uint32_t *)(s_q + y * TP + x);
+            *(uint2 *)(co + (size_t)y * cs + x) = make_uint2(q[0], q[1]);
+            if (want_recon && (nz || r != p)) {
+                uint32_t pw = *(const uint32_t *)(p + (size_t)y * ps + x);
+                if (nz) {
+                    const int16_t *e = s_b + y * TP + x;
+                    uint32_t o = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) o |= (uint32_t)min(max((int)((pw >> (8 * k)) & 0xff) + e[k], 0), 255) << (8 * k);
+                    pw = o;
+                }
+                *(uint32_t *)(r + (size_t)y * rs + x) = pw;
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < N * N; i += TQ_NT) {
+            const int y = i >> lg, x = i & (N - 1);
+            co[(size_t)y * cs + x] = s_q[y * TP + x];
+            if (want_recon) {
+                const int pv = p[(size_t)y * ps + x];
+                const int v = nz ? min(max(pv + s_b[y * TP + x], 0), 255) : pv;
+                if (nz || r != p) r[(size_t)y * rs + x] = (uint8_t)v;
+            }
         }
     }
 }
@@ -388,6 +442,15 @@ static int ensure_tables()
     int8_t m[32][32];
     build_dct32(m);
     SVTB200_CUDA_TRY(cudaMemcpyToSymbol(c_dct32, m, sizeof m));
+    SVTB200_CUDA_TRY(cudaMemcpyToSymbol(g_dct32, m, sizeof m));
+    static int8_t mt[4][32 * 32];
+    memset(mt, 0, sizeof mt);
+    for (int l = 0; l < 4; ++l) {
+        const int N = 4 << l, ks = 32 / N;
+        for (int k = 0; k < N; ++k)
+            for (int n = 0; n < N; ++n) mt[l][n * 32 + k] = m[k * ks][n];
+    }
+    SVTB200_CUDA_TRY(cudaMemcpyToSymbol(g_dct_t, mt, sizeof mt));
     done = true;
     return SVTB200_OK;
 }
