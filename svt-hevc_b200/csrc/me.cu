@@ -356,21 +356,52 @@ __device__ void fullpel_search(const uint8_t *s_src, const uint8_t *s_win, int w
         //     replaces an equal best carried in from earlier chunks (C_DEFAULT/EbComputeSAD_C.c:439 vs EbMeSadCalculation_C.c:109).
         {
             const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-            for (int n = wid; n < 85; n += NT / 32) {
+            // PUs 1..84 (strict '<'): 8 lanes per PU, lane l scans positions l, l + 8, ... keeping (sad, position) as one 64-bit key, so the
+            // minimum key is the FIRST minimum in scan order; three shuffles merge the 8 lanes.  gw is a multiple of 8, so x advances by 8.
+            for (int g = (int)(threadIdx.x >> 3); g < 84; g += NT / 8) {
+                const int n = 1 + g, l = lane & 7;
                 int b8 = 0;
                 if (n >= 21) {
                     int px, py, sz;
                     pu_geom(n, px, py, sz);
                     b8 = (py >> 3) * 8 + (px >> 3);
                 }
+                unsigned long long key = ~0ull;
+                int xx = l;                                  // position pc = l + 8k; xx = pc mod gw (l < 8 <= gw)
+                for (int pc = l; pc < cn; pc += 8) {
+                    if (xg0 * 8 + xx < saw) {
+                        const uint32_t v = 2u * (n >= 21 ? (uint32_t)s_sad8[pc * 64 + b8] : s_sum[pc * 21 + n]);
+                        const unsigned long long k = ((unsigned long long)v << 32) | (uint32_t)pc;
+                        key = k < key ? k : key;
+                    }
+                    xx += 8;
+                    if (xx >= gw) xx -= gw;
+                }
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) {
+                    const unsigned long long t = __shfl_xor_sync(0xffffffffu, key, o);
+                    key = t < key ? t : key;
+                }
+                if (l == 0 && key != ~0ull) {
+                    const uint32_t m = (uint32_t)(key >> 32);
+                    if (m < s_bsad[n]) {
+                        const int win = (int)(uint32_t)key, yy = win / gw, x = xg0 * 8 + (win - yy * gw), y = y0 + yy;
+                        s_bsad[n] = m;
+                        s_bmv[n] = ((uint32_t)(uint16_t)((y + soy) * 4) << 16) | (uint16_t)((x + sox) * 4);
+                    }
+                }
+            }
+            // PU 0 (64x64): '<=' on 8-position-path positions -- one warp, lanes = the <= 64 positions of the chunk
+            if (wid == NT / 32 - 1) {
+                const int n = 0;
                 uint32_t v[2];
                 bool valid[2], le[2];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int pc = lane + 32 * h, yy = pc / gw, xx = pc - yy * gw, x = xg0 * 8 + xx;
                     valid[h] = pc < cn && x < saw;
-                    le[h] = valid[h] && n == 0 && x < w8;
-                    v[h] = valid[h] ? 2u * (n >= 21 ? (uint32_t)s_sad8[pc * 64 + b8] : s_sum[pc * 21 + n]) : 0xffffffffu;
+                    le[h] = valid[h] && x < w8;
+                    v[h] = valid[h] ? 2u * s_sum[pc * 21 + n] : 0xffffffffu;
                 }
                 const uint32_t m = __reduce_min_sync(0xffffffffu, min(v[0], v[1]));
                 const uint32_t bs = s_bsad[n];

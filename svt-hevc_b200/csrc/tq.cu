@@ -157,6 +157,49 @@ __device__ void rowdot(const int8_t *A, int lda, const int16_t *B, int odd_off, 
 }
 
 
+
+// Register-blocked variant for the large passes (I * J >= 1024): every thread owns a 2 (i) x 4 (j) block of outputs, so that per 4 taps
+// 4 + 4 shared-memory words feed 16 DP2A (32 MACs) and a 32x32 pass is exactly one block per thread.  j_m = jq + m * J/4 keeps the parity
+// of jq (J/4 is even whenever the folded passes use this), which is what selects the sum / difference half of a folded row.
+template <bool CLIP>
+__device__ void rowdot24(const int8_t *A, int lda, const int16_t *B, int odd_off, int I, int J, int Nn, int off, int shift, int16_t *out, int osi, int osj)
+{
+    const int Ih = I >> 1, Jq = J >> 2, n4 = Nn >> 2, lgIh = ilog2d(Ih);
+    for (int it = threadIdx.x; it < Ih * Jq; it += TQ_NT) {
+        const int jq = it >> lgIh, i = it & (Ih - 1);
+        const uint32_t *b0p = (const uint32_t *)(B + i * TP + ((jq & 1) ? odd_off : 0)), *b1p = b0p + (Ih * TP) / 2;
+        const uint32_t *ap = (const uint32_t *)(A + jq * lda);
+        const int astep = (Jq * lda) >> 2;
+        int c[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+#pragma unroll 2
+        for (int q = 0; q < n4; ++q) {
+            const uint32_t x0 = b0p[2 * q], x1 = b0p[2 * q + 1], y0 = b1p[2 * q], y1 = b1p[2 * q + 1];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const uint32_t w = ap[m * astep + q];
+                c[0][m] = dp2a_hi(x1, w, dp2a_lo(x0, w, c[0][m]));
+                c[1][m] = dp2a_hi(y1, w, dp2a_lo(y0, w, c[1][m]));
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            int v0 = (c[0][m] + off) >> shift, v1 = (c[1][m] + off) >> shift;
+            if (CLIP) { v0 = clip16i(v0); v1 = clip16i(v1); }
+            const int j = jq + m * Jq;
+            out[j * osj + i * osi] = (int16_t)v0;
+            out[j * osj + (i + Ih) * osi] = (int16_t)v1;
+        }
+    }
+}
+
+// picks the blocking by pass size
+template <bool CLIP>
+__device__ __forceinline__ void rowdot_any(const int8_t *A, int lda, const int16_t *B, int odd_off, int I, int J, int Nn, int off, int shift, int16_t *out, int osi, int osj)
+{
+    if (I * J >= 1024) rowdot24<CLIP>(A, lda, B, odd_off, I, J, Nn, off, shift, out, osi, osj);
+    else rowdot<CLIP>(A, lda, B, odd_off, I, J, Nn, off, shift, out, osi, osj);
+}
+
 // The whole chain for one TU held in shared memory.  s_a: residual in (pitch TP); returns nz.
 // On exit s_a holds the reconstructed residual (if nz && want_recon), s_q the quantised coefficients (act x act corner).
 __device__ uint32_t tq_chain(const int8_t *s_m, const int8_t *s_mt, int16_t *s_a, int16_t *s_b, int16_t *s_q, uint32_t *s_cnt, const svtb200_tq_job &t, bool want_recon, bool prefolded)
@@ -195,10 +238,10 @@ __device__ uint32_t tq_chain(const int8_t *s_m, const int8_t *s_mt, int16_t *s_a
             const bool fold = N >= 16;
             const int Nn = fold ? N >> 1 : N, lda = (32 / N) * 32;
             if (fold && !prefolded) { fold_rows(s_a, s_q, N, N); __syncthreads(); }
-            rowdot<false>(s_m, lda, fold ? s_q : s_a, fold ? Nn : 0, N, act, Nn, 1 << (s1 - 1), s1, s_b, 1, TP);       // s_b[k][r]
+            rowdot_any<false>(s_m, lda, fold ? s_q : s_a, fold ? Nn : 0, N, act, Nn, 1 << (s1 - 1), s1, s_b, 1, TP);       // s_b[k][r]
             __syncthreads();
             if (fold) { fold_rows(s_b, s_q, N, act); __syncthreads(); }
-            rowdot<false>(s_m, lda, fold ? s_q : s_b, fold ? Nn : 0, act, act, Nn, 1 << (s2 - 1), s2, s_a, 1, TP);     // s_a[v][u]
+            rowdot_any<false>(s_m, lda, fold ? s_q : s_b, fold ? Nn : 0, act, act, Nn, 1 << (s2 - 1), s2, s_a, 1, TP);     // s_a[v][u]
             __syncthreads();
         }
     }
@@ -266,9 +309,9 @@ __device__ uint32_t tq_chain(const int8_t *s_m, const int8_t *s_mt, int16_t *s_a
     const uint32_t nz = *s_cnt;
     if (nz && want_recon && fast) {
         // pass 1: tmp(u, y) = sum_v M[v][y] * deq[v][u], written as s_a[y][u]; pass 2: res(y, x) = sum_u M[u][x] * tmp(u, y) -> s_b[y][x]
-        rowdot<true>(s_mt, 32, s_b, 0, act, N, act, 64, 7, s_a, 1, TP);
+        rowdot_any<true>(s_mt, 32, s_b, 0, act, N, act, 64, 7, s_a, 1, TP);
         __syncthreads();
-        rowdot<true>(s_mt, 32, s_a, 0, N, N, act, 2048, 12, s_b, TP, 1);
+        rowdot_any<true>(s_mt, 32, s_a, 0, N, N, act, 2048, 12, s_b, TP, 1);
         __syncthreads();
     } else if (nz && want_recon) {
         inv_pass(s_m, s_b, s_a, N, dst ? 4 : act, act, 7, dst);     // s_a[r][n], rows r >= act would be all zero

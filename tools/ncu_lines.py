@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Per-source-line instruction / stall-sample shares of one kernel: joins `ncu --page source --csv` (SASS order) with
 `nvdisasm -g` line annotations of the same cubin.
-usage: tools/ncu_lines.py <report.ncu-rep> <kernel-substring> <file.cu> [top]"""
+usage: tools/ncu_lines.py <report.ncu-rep> <kernel-substring>[:<mangled-substring>] <file.cu> [top]
+(the second form when the report's demangled name and the cubin's mangled name differ, e.g. template instantiations)"""
 import csv
 import os
 import re
@@ -37,6 +38,8 @@ def sass_lines(kernel, cu):
 
 def main():
     rep, kernel, cu = sys.argv[1:4]
+    kernel, _, mangled = kernel.partition(":")
+    mangled = mangled or kernel
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", f"regex:{kernel}"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
@@ -44,7 +47,7 @@ def main():
     hdr = rows[hi]
     ie, st = hdr.index("Instructions Executed"), hdr.index("# Samples")
     data = [(int(r[ie] or 0), int(r[st] or 0)) for r in rows[hi + 1:] if len(r) > ie and r[0].startswith("0x")]
-    lines = sass_lines(kernel, cu)
+    lines = sass_lines(mangled, cu)
     if len(lines) != len(data):
         print(f"# warning: {len(data)} SASS rows in the report vs {len(lines)} in the cubin (binary changed since the capture?)")
     n = min(len(lines), len(data))
