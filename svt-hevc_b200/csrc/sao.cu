@@ -7,9 +7,9 @@
 // The RD decision (SaoGenerationDecision, Codec/EbSampleAdaptiveOffsetGenerationDecision.c:647) stays on the host: it
 // needs the CABAC rate tables and is a few hundred scalar operations per LCU.
 //
-// Design.  Statistics: one CTA per (LCU, component); the reconstructed block is staged once in shared memory, every
-// thread keeps the 4 x 5 edge-class accumulators in registers (predicated adds, no atomics) and band sums are
-// warp-aggregated with __match_any_sync before touching a shared 32-bin histogram.  Application: out = SAO(in), one
+// Design.  Statistics: one CTA (128 threads) per (LCU, component); the reconstructed block is staged once in shared memory; edge
+// classes are computed SIMD-in-word for 4 samples at a time (edge_idx4: packed compares, no per-sample branches) and accumulated in
+// registers; band statistics go to per-warp private histograms packed as (count << 16) + sum, merged at the end.  Application: out = SAO(in), one
 // thread per 4 samples, neighbours always read from the unmodified input picture, so the reference's line buffers
 // (saoUpBuffer / saoLeftBuffer) have no counterpart.  Both kernels are HBM-bound (18 432 B per CTU).
 #include "common.cuh"
