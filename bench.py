@@ -225,30 +225,34 @@ def run_b200(args):
     for i in range(RING):
         ring_pa[i].upload(h_y[i].data_ptr(), stream)
         fill_yuv(ring_yuv[i][0], h_y[i], h_cb[i], h_cr[i], True)
-    pred_t, pred = dev_yuv()
     sao_t, sao_out = dev_yuv()
-    e2e_pa = S.DevPaPicture(W, H)
-    e2e_t, e2e_yuv = dev_yuv()
-    coeff_t = [torch.zeros((H, W), dtype=torch.int16, device=dev), torch.zeros((H // 2, W // 2), dtype=torch.int16, device=dev),
-               torch.zeros((H // 2, W // 2), dtype=torch.int16, device=dev)]
-    coeff = S.CoeffPicture()
-    for k in range(3):
-        coeff.buf[k] = coeff_t[k].data_ptr(); coeff.stride[k] = coeff_t[k].shape[1]
-    d_res = torch.zeros(N_LCU * 85 * 24, dtype=torch.uint8, device=dev)
+
+    class Slot:
+        """device + pinned host buffers of one frame in flight (the e2e loop keeps two in flight: copies of one overlap the kernels of the other)"""
+        def __init__(self):
+            self.pred_t, self.pred = dev_yuv()
+            self.in_t, self.in_yuv = dev_yuv()
+            self.pa = S.DevPaPicture(W, H)
+            self.coeff_t = [torch.zeros((H, W), dtype=torch.int16, device=dev), torch.zeros((H // 2, W // 2), dtype=torch.int16, device=dev),
+                            torch.zeros((H // 2, W // 2), dtype=torch.int16, device=dev)]
+            self.coeff = S.CoeffPicture()
+            for k in range(3):
+                self.coeff.buf[k] = self.coeff_t[k].data_ptr(); self.coeff.stride[k] = self.coeff_t[k].shape[1]
+            self.d_res = torch.zeros(N_LCU * 85 * 24, dtype=torch.uint8, device=dev)
+            self.d_nz = torch.zeros(len(wl.tq_jobs), dtype=torch.int32, device=dev)
+            self.d_stats = torch.zeros(N_LCU * 3 * 312, dtype=torch.uint8, device=dev)
+            self.d_ois_total = torch.zeros(N_LCU * 85, dtype=torch.uint8, device=dev)
+            self.d_ois_cand = torch.zeros(N_LCU * 85, dtype=torch.int32, device=dev)
+            self.dev_out = [self.d_res, *self.coeff_t, self.d_nz, self.d_stats, self.d_ois_total, self.d_ois_cand]
+            self.host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in self.dev_out]
+            self.ev_in, self.ev_cmp, self.ev_out = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+
+    slots = [Slot(), Slot()]
+    d_res = slots[0].d_res
     d_tq = torch.from_numpy(wl.tq_jobs.view(np.uint8)).to(dev)
-    d_nz = torch.zeros(len(wl.tq_jobs), dtype=torch.int32, device=dev)
     d_vbs, d_hbs, d_qp = (torch.from_numpy(a.copy()).to(dev) for a in (wl.vbs, wl.hbs, wl.qp_array))
     d_sao_prm = torch.from_numpy(wl.sao_prm.view(np.uint8)).to(dev)
-    d_stats = torch.zeros(N_LCU * 3 * 312, dtype=torch.uint8, device=dev)
-    d_ois_total = torch.zeros(N_LCU * 85, dtype=torch.uint8, device=dev)
-    d_ois_cand = torch.zeros(N_LCU * 85, dtype=torch.int32, device=dev)
     ois_cfg = wl.ois_cfg()
-    h_res = torch.empty(d_res.shape, dtype=torch.uint8).pin_memory()
-    h_coeff = [torch.empty(t.shape, dtype=torch.int16).pin_memory() for t in coeff_t]
-    h_nz = torch.empty(d_nz.shape, dtype=torch.int32).pin_memory()
-    h_stats = torch.empty(d_stats.shape, dtype=torch.uint8).pin_memory()
-    h_ois_total = torch.empty(d_ois_total.shape, dtype=torch.uint8).pin_memory()
-    h_ois_cand = torch.empty(d_ois_cand.shape, dtype=torch.int32).pin_memory()
 
     # mode-decision stand-in: one ME pass per (ring frame, layer) pair fixes the MC job lists used by both timed loops
     d_mc, mc_bytes = [], []
@@ -263,8 +267,8 @@ def run_b200(args):
 
     names = ["me", "ois", "mc", "tq", "dlf", "sao_stats", "sao_apply"]
 
-    def pipeline(i, src_pa, src_yuv, ev=None):
-        """All device stages of frame i.  ev: dict name -> list of (start, end) events."""
+    def pipeline(i, src_pa, src_yuv, sl, st, ev=None):
+        """All device stages of frame i into slot sl on CUDA stream st.  ev: dict name -> list of (start, end) events."""
         def timed(name, fn):
             if ev is None:
                 fn(); return
@@ -274,33 +278,42 @@ def run_b200(args):
         r0, r1 = wl.refs(i)
         k = i % RING
         tl0 = wl.tl(i) == 0
-        timed("me", lambda: S.me_picture_dev(wl.me_cfg(i), src_pa, ring_pa[r0], ring_pa[r1], d_res.data_ptr(), stream))
-        timed("ois", lambda: S.ois_picture_dev(ois_cfg, src_pa.struct.full, d_res.data_ptr(), d_ois_total.data_ptr(), d_ois_cand.data_ptr(), 1, stream))
-        timed("mc", lambda: S.mc_batch_dev([ring_yuv[r0][1], ring_yuv[r1][1]], d_mc[k][0].data_ptr(), d_mc[k][1], pred, stream))
-        timed("tq", lambda: S.tq_batch_dev(src_yuv, pred, pred, coeff, d_tq.data_ptr(), len(wl.tq_jobs), d_nz.data_ptr(), stream))
+        pred = sl.pred
+        timed("me", lambda: S.me_picture_dev(wl.me_cfg(i), src_pa, ring_pa[r0], ring_pa[r1], sl.d_res.data_ptr(), st))
+        timed("ois", lambda: S.ois_picture_dev(ois_cfg, src_pa.struct.full, sl.d_res.data_ptr(), sl.d_ois_total.data_ptr(), sl.d_ois_cand.data_ptr(), 1, st))
+        timed("mc", lambda: S.mc_batch_dev([ring_yuv[r0][1], ring_yuv[r1][1]], d_mc[k][0].data_ptr(), d_mc[k][1], pred, st))
+        timed("tq", lambda: S.tq_batch_dev(src_yuv, pred, pred, sl.coeff, d_tq.data_ptr(), len(wl.tq_jobs), sl.d_nz.data_ptr(), st))
         if tl0:
-            timed("dlf", lambda: S.dlf_picture_dev(pred, d_vbs.data_ptr(), d_hbs.data_ptr(), d_qp.data_ptr(), wl.dlf_prm, stream))
-        timed("sao_stats", lambda: S.sao_stats_picture_dev(src_yuv, pred, d_stats.data_ptr(), stream))
+            timed("dlf", lambda: S.dlf_picture_dev(pred, d_vbs.data_ptr(), d_hbs.data_ptr(), d_qp.data_ptr(), wl.dlf_prm, st))
+        timed("sao_stats", lambda: S.sao_stats_picture_dev(src_yuv, pred, sl.d_stats.data_ptr(), st))
         if tl0:
-            timed("sao_apply", lambda: S.sao_apply_picture_dev(pred, sao_out, d_sao_prm.data_ptr(), (1, 1), stream))
+            timed("sao_apply", lambda: S.sao_apply_picture_dev(pred, sao_out, d_sao_prm.data_ptr(), (1, 1), st))
 
     def step_resident(i, ev=None):
-        pipeline(i, ring_pa[i % RING], ring_yuv[i % RING][1], ev)
+        pipeline(i, ring_pa[i % RING], ring_yuv[i % RING][1], slots[0], stream, ev)
+
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
 
     def step_e2e(i):
+        """Frame i from pinned host buffers: H2D on the copy-in stream, kernels on the compute stream, D2H of everything the host-side
+        encoder consumes on the copy-out stream; two frames in flight, every copy inside the timed region."""
         k = i % RING
-        fill_yuv(e2e_t, h_y[k], h_cb[k], h_cr[k], False)                                   # H2D: Y + Cb + Cr
-        yint = e2e_t[0][PAD:, PAD:]
-        e2e_pa.build_from_device(yint.data_ptr(), e2e_t[0].shape[1], stream)               # pad + decimate on the device
-        pipeline(i, e2e_pa, e2e_yuv)
-        h_res.copy_(d_res, non_blocking=True)                                              # D2H: what the host-side encoder consumes
-        for hc, dc in zip(h_coeff, coeff_t):
-            hc.copy_(dc, non_blocking=True)
-        h_nz.copy_(d_nz, non_blocking=True)
-        h_stats.copy_(d_stats, non_blocking=True)
-        h_ois_total.copy_(d_ois_total, non_blocking=True)
-        h_ois_cand.copy_(d_ois_cand, non_blocking=True)
-        tstream.synchronize()
+        sl = slots[i & 1]
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(sl.ev_cmp)                                                     # the kernels that read this slot's inputs are done
+            fill_yuv(sl.in_t, h_y[k], h_cb[k], h_cr[k], False)                             # H2D: Y + Cb + Cr
+            sl.ev_in.record(s_in)
+        tstream.wait_event(sl.ev_in)
+        tstream.wait_event(sl.ev_out)                                                      # this slot's previous results have left the device
+        yint = sl.in_t[0][PAD:, PAD:]
+        sl.pa.build_from_device(yint.data_ptr(), sl.in_t[0].shape[1], stream)              # pad + decimate on the device
+        pipeline(i, sl.pa, sl.in_yuv, sl, stream)
+        sl.ev_cmp.record(tstream)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(sl.ev_cmp)
+            for hb, db in zip(sl.host_out, sl.dev_out):                                    # D2H: ME results, coefficients, nz, SAO stats, OIS
+                hb.copy_(db, non_blocking=True)
+            sl.ev_out.record(s_out)
 
     def barrier():
         torch.cuda.synchronize()
@@ -350,7 +363,7 @@ def run_b200(args):
                          "frac_of_hbm_peak": (alg[n] / (np.mean(v) * 1e-3) / 1e9 / peak) if v else None} for n, v in stage_ms.items()}
         k_avg_s = float(np.mean(stage_ms[dom])) * 1e-3
         h2d = W * H * 3 // 2
-        d2h = int(d_res.numel() + sum(t.numel() * 2 for t in coeff_t) + d_nz.numel() * 4 + d_stats.numel() + d_ois_total.numel() + d_ois_cand.numel() * 4)
+        d2h = int(sum(t.numel() * t.element_size() for t in slots[0].dev_out))
         out = {
             "metric": METRIC, "value": ctus / (ms * 1e-3), "unit": "CTU/s", "fps": ctus / (ms * 1e-3) / N_LCU,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,

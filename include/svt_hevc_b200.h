@@ -200,6 +200,13 @@ int svtb200_mc_batch(const svtb200_yuv_picture *refs, int n_refs, const svtb200_
                      const svtb200_yuv_picture *dst);
 int svtb200_mc_batch_dev(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs_dev, int n_jobs,
                          const svtb200_yuv_picture *dst, void *cuda_stream);
+/* b5: the same batch on 16-bit sample planes (10-bit video): EncodePassInterPrediction16bit (Codec/EbInterPrediction.c:928),
+ * UniPredInterpolation16bit / BiPredInterpolation16bit (Codec/EbMcp.c:249,804), kernels C_DEFAULT/EbMcp_C.c:3121-4861.
+ * svtb200_plane::buf points at uint16_t samples; stride and origins stay in samples (EbReferenceObject_t::referencePicture16bit geometry). */
+int svtb200_mc_batch16(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs, int n_jobs,
+                       const svtb200_yuv_picture *dst);
+int svtb200_mc_batch16_dev(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs_dev, int n_jobs,
+                           const svtb200_yuv_picture *dst, void *cuda_stream);
 
 /* Leaf entry points with the reference's kernel prototypes.  The reference selects one of 16 (luma) / 64
  * (chroma) functions by fractional position (uniPredLumaIFFunctionPtrArrayNew[2][16], EbMcpTables.c:28;

@@ -124,3 +124,85 @@ int port_mc_batch(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_
     }
     return 0;
 }
+
+/* ---- 16-bit samples (10-bit video): SURVEY §8 row b5 -------------------------------------------------------------------
+ * uniPred / biPred ...New16bit / ...OutRaw16bit (C_DEFAULT/EbMcp_C.c:3121-4861), BiPredClipping16bit :3265, integer/integer
+ * shortcut BiPredClippingOnTheFly16bit (Codec/EbMcp.c:847), drivers UniPredInterpolation16bit / BiPredInterpolation16bit
+ * (Codec/EbMcp.c:249,804), EncodePassInterPrediction16bit (Codec/EbInterPrediction.c:928).  Constants Codec/EbDefinitions.h:1041-1059:
+ *   1-D      (S + 32) >> 6                                  raw: (S - 32768) >> 2
+ *   2-D      first (S - 32768) >> 2 (s16), then (S2 + 524800) >> 10      raw: S2 >> 6
+ *   copy     p                                              raw: (p << 4) - 8192
+ *   bi       (a + b + 16400) >> 5, clip to 1023
+ * Written case by case like the reference (no unification), so that it checks the two-pass form the CUDA kernel uses. */
+static inline uint16_t clip10(int v) { return (uint16_t)(v < 0 ? 0 : v > 1023 ? 1023 : v); }
+
+static void interp_block16(const uint16_t *p, int stride, int taps, const int *cx, const int *cy, int fx, int fy, int w, int h, int uni, uint16_t *dst,
+                           int dstride, int16_t *raw)
+{
+    const int half = taps / 2 - 1;
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            int o_uni, o_raw;
+            if (!fx && !fy) { o_uni = p[y * stride + x]; o_raw = (int16_t)(p[y * stride + x] << 4) - 8192; }
+            else if (!fy || !fx) {
+                int s = 0;
+                for (int t = 0; t < taps; ++t) s += !fy ? cx[t] * p[y * stride + x + t - half] : cy[t] * p[(y + t - half) * stride + x];
+                o_uni = clip10((s + 32) >> 6); o_raw = (int16_t)((s - 32768) >> 2);
+            } else {
+                int acc = 0;
+                for (int r = 0; r < taps; ++r) {
+                    int hrow = 0;
+                    for (int t = 0; t < taps; ++t) hrow += cx[t] * p[(y + r - half) * stride + x + t - half];
+                    acc += cy[r] * (int16_t)((hrow - 32768) >> 2);
+                }
+                o_uni = clip10((acc + 524800) >> 10); o_raw = (int16_t)(acc >> 6);
+            }
+            if (uni) dst[y * dstride + x] = (uint16_t)o_uni; else raw[y * w + x] = (int16_t)o_raw;
+        }
+}
+
+static void pred16(const uint16_t *r0, int s0, int f0x, int f0y, const uint16_t *r1, int s1, int f1x, int f1y, int taps, const int (*tab)[8], const int (*tab4)[4],
+                   uint16_t *dst, int ds, int w, int h)
+{
+    const int *c0x = taps == 8 ? tab[f0x] : tab4[f0x], *c0y = taps == 8 ? tab[f0y] : tab4[f0y];
+    if (!r1) { interp_block16(r0, s0, taps, c0x, c0y, f0x, f0y, w, h, 1, dst, ds, NULL); return; }
+    const int *c1x = taps == 8 ? tab[f1x] : tab4[f1x], *c1y = taps == 8 ? tab[f1y] : tab4[f1y];
+    int16_t *a = (int16_t *)malloc((size_t)2 * w * h * sizeof(int16_t)), *b = a + w * h;
+    interp_block16(r0, s0, taps, c0x, c0y, f0x, f0y, w, h, 0, NULL, 0, a);
+    interp_block16(r1, s1, taps, c1x, c1y, f1x, f1y, w, h, 0, NULL, 0, b);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) dst[y * ds + x] = clip10((a[y * w + x] + b[y * w + x] + 16400) >> 5);
+    free(a);
+}
+
+/* planes hold 16-bit samples: svtb200_plane::buf points at them, stride / origins in samples */
+int port_mc_batch16(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs, int n_jobs, const svtb200_yuv_picture *dst)
+{
+    for (int j = 0; j < n_jobs; ++j) {
+        const svtb200_mc_job *q = &jobs[j];
+        int px[2] = { 0, 0 }, py[2] = { 0, 0 };
+        const svtb200_yuv_picture *r[2] = { NULL, NULL };
+        for (int l = 0; l < 2; ++l) {
+            if (!(q->dir == l || q->dir == 2)) continue;
+            if (q->ref_idx[l] >= n_refs) return -1;
+            r[l] = &refs[q->ref_idx[l]];
+            px[l] = (uint16_t)clamp_i((r[l]->y.origin_x - 71) << 2, (r[l]->y.width + r[l]->y.origin_x + 7) << 2, ((q->x + r[l]->y.origin_x) << 2) + q->mv[l][0]);
+            py[l] = (uint16_t)clamp_i((r[l]->y.origin_y - 71) << 2, (r[l]->y.height + r[l]->y.origin_y + 7) << 2, ((q->y + r[l]->y.origin_y) << 2) + q->mv[l][1]);
+        }
+        const int a = q->dir == 1 ? 1 : 0, b = q->dir == 2 ? 1 : -1;
+        uint16_t *dy = (uint16_t *)dst->y.buf + (size_t)(dst->y.origin_y + q->y) * dst->y.stride + dst->y.origin_x + q->x;
+        const size_t cidx = (((size_t)(dst->y.origin_y + q->y) * dst->cb.stride) >> 1) + ((dst->y.origin_x + q->x) >> 1);
+        const uint16_t *ya = (const uint16_t *)r[a]->y.buf + (px[a] >> 2) + (size_t)(py[a] >> 2) * r[a]->y.stride;
+        const uint16_t *yb = b < 0 ? NULL : (const uint16_t *)r[b]->y.buf + (px[b] >> 2) + (size_t)(py[b] >> 2) * r[b]->y.stride;
+        pred16(ya, (int)r[a]->y.stride, px[a] & 3, py[a] & 3, yb, b < 0 ? 0 : (int)r[b]->y.stride, b < 0 ? 0 : px[b] & 3, b < 0 ? 0 : py[b] & 3, 8, LUMA_TAPS, CHROMA_TAPS,
+               dy, (int)dst->y.stride, q->w, q->h);
+        for (int c = 0; c < 2; ++c) {
+            const svtb200_plane *pa = c ? &r[a]->cr : &r[a]->cb, *pb = b < 0 ? NULL : (c ? &r[b]->cr : &r[b]->cb), *pd = c ? &dst->cr : &dst->cb;
+            const uint16_t *ca = (const uint16_t *)pa->buf + (px[a] >> 3) + (size_t)(py[a] >> 3) * pa->stride;
+            const uint16_t *cb = pb ? (const uint16_t *)pb->buf + (px[b] >> 3) + (size_t)(py[b] >> 3) * pb->stride : NULL;
+            pred16(ca, (int)pa->stride, px[a] & 7, py[a] & 7, cb, pb ? (int)pb->stride : 0, pb ? px[b] & 7 : 0, pb ? py[b] & 7 : 0, 4, LUMA_TAPS, CHROMA_TAPS,
+                   (uint16_t *)pd->buf + cidx, (int)pd->stride, q->w >> 1, q->h >> 1);
+        }
+    }
+    return 0;
+}

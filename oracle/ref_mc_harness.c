@@ -83,3 +83,51 @@ int svtref_mc_batch(const svtb200_yuv_picture *refs, int n_refs, const svtb200_m
     free(mcp); free(pcs); free(scs); free(ec); free(refWrap); free(refObj); free(refDesc);
     return 0;
 }
+
+/* 16-bit samples: EncodePassInterPrediction16bit (Codec/EbInterPrediction.c:928) on EbReferenceObject_t::referencePicture16bit.
+ * Planes hold EB_U16 samples (svtb200_plane::buf points at them; strides / origins in samples). */
+int svtref_mc_batch16(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs, int n_jobs, const svtb200_yuv_picture *dst, int asm_mode)
+{
+    ASM_TYPES = asm_mode ? EbHevcGetCpuAsmType() : 0;
+    EbPictureBufferDesc_t *refDesc = (EbPictureBufferDesc_t *)calloc((size_t)n_refs, sizeof(*refDesc)), dstDesc;
+    EbReferenceObject_t *refObj = (EbReferenceObject_t *)calloc((size_t)n_refs, sizeof(*refObj));
+    EbObjectWrapper_t *refWrap = (EbObjectWrapper_t *)calloc((size_t)n_refs, sizeof(*refWrap));
+    for (int i = 0; i < n_refs; ++i) {
+        fill_yuv(&refDesc[i], &refs[i]);
+        refDesc[i].bitDepth = EB_16BIT;
+        refObj[i].referencePicture16bit = &refDesc[i];
+        refWrap[i].objectPtr = &refObj[i];
+    }
+    fill_yuv(&dstDesc, dst);
+    dstDesc.bitDepth = EB_16BIT;
+
+    EbCallback_t cb; memset(&cb, 0, sizeof cb); cb.ErrorHandler = on_error;
+    EncodeContext_t *ec = (EncodeContext_t *)calloc(1, sizeof(*ec));
+    ec->appCallbackPtr = &cb;
+    SequenceControlSet_t *scs = (SequenceControlSet_t *)calloc(1, sizeof(*scs));
+    scs->encodeContextPtr = ec;
+    EbObjectWrapper_t scsWrap; memset(&scsWrap, 0, sizeof scsWrap); scsWrap.objectPtr = scs;
+    PictureControlSet_t *pcs = (PictureControlSet_t *)calloc(1, sizeof(*pcs));
+    pcs->sequenceControlSetWrapperPtr = &scsWrap;
+
+    MotionCompensationPredictionContext_t *mcp = (MotionCompensationPredictionContext_t *)calloc(1, sizeof(*mcp));
+    if (MotionCompensationPredictionContextCtor(mcp, 64, 64, EB_TRUE) != EB_ErrorNone) return -1;
+    /* the 16-bit path re-points the local reference block descriptors into the reference pictures: keep the owned pointers for the dtor */
+    EB_U8 *keep[2][3] = { { mcp->localReferenceBlockL0->bufferY, mcp->localReferenceBlockL0->bufferCb, mcp->localReferenceBlockL0->bufferCr },
+                          { mcp->localReferenceBlockL1->bufferY, mcp->localReferenceBlockL1->bufferCb, mcp->localReferenceBlockL1->bufferCr } };
+
+    for (int j = 0; j < n_jobs; ++j) {
+        const svtb200_mc_job *q = &jobs[j];
+        MvUnit_t mvu; memset(&mvu, 0, sizeof mvu);
+        mvu.predDirection = q->dir;
+        for (int l = 0; l < 2; ++l) { mvu.mv[l].x = q->mv[l][0]; mvu.mv[l].y = q->mv[l][1]; }
+        pcs->refPicPtrArray[0] = &refWrap[q->ref_idx[0]];
+        pcs->refPicPtrArray[1] = &refWrap[q->ref_idx[1]];
+        EncodePassInterPrediction16bit(&mvu, q->x, q->y, q->w, q->h, pcs, &dstDesc, mcp);
+    }
+    mcp->localReferenceBlockL0->bufferY = keep[0][0]; mcp->localReferenceBlockL0->bufferCb = keep[0][1]; mcp->localReferenceBlockL0->bufferCr = keep[0][2];
+    mcp->localReferenceBlockL1->bufferY = keep[1][0]; mcp->localReferenceBlockL1->bufferCb = keep[1][1]; mcp->localReferenceBlockL1->bufferCr = keep[1][2];
+    if (mcp->dctor) mcp->dctor(mcp);
+    free(mcp); free(pcs); free(scs); free(ec); free(refWrap); free(refObj); free(refDesc);
+    return 0;
+}

@@ -28,7 +28,7 @@ struct YuvD {
     int ox, oy, w, h;   // luma origin / size; chroma = half
 };
 struct McArgs {
-    const YuvD *refs;         // device array [n_refs]
+    YuvD refs[16];            // by value: a launch carries its own reference table (no staging buffer to race on between back-to-back launches)
     int n_refs;
     const svtb200_mc_job *jobs;
     int n_jobs;
@@ -64,21 +64,47 @@ __device__ __forceinline__ uint32_t pack4(const int8_t *t) { return (uint8_t)t[0
 //   ref   : integer sample of the tile's top-left in the reference plane
 //   out8  : != nullptr -> uni-pred, final samples written to global memory (pitch ostride)
 //   raw   : != nullptr -> bi-pred, 14-bit intermediates written to shared memory (pitch tw)
-template <int TAPS>
+// HBD: 16-bit samples (10-bit video).  ref / out8 are byte pointers, rstride / ostride are in SAMPLES.  The same two-pass
+// form is exact there as well: first pass (S - 32768) >> 2 kept in 16 bits like LumaInterpolationFilterPos*OutRaw16bit, second pass
+// (S2 + 524800) >> 10 (uni) or S2 >> 6 (bi); with identity taps these reduce to the reference's 1-D (S + 32) >> 6, (S - 32768) >> 2 and copy
+// forms (Codec/EbDefinitions.h:1041-1059).
+template <int TAPS, bool HBD>
 __device__ void interp_tile(const uint8_t *ref, int rstride, int fx, int fy, int tw, int th, uint8_t *s_win, int16_t *s_tmp,
                             uint8_t *out8, int ostride, int16_t *raw)
 {
-    constexpr int HALF = TAPS / 2 - 1;
-    const int wbytes = tw + TAPS - 1, wrows = th + TAPS - 1, wp = win_pitch(wbytes);
+    constexpr int HALF = TAPS / 2 - 1, BPS = HBD ? 2 : 1;
+    const int wbytes = (tw + TAPS - 1) * BPS, wrows = th + TAPS - 1, wp = win_pitch(wbytes);
     __syncthreads();   // previous users of s_win / s_tmp are done
-    const int a = load_window_t<MC_NT>(s_win, wp, ref - HALF * rstride - HALF, rstride, wbytes, wrows);
+    const int a = load_window_t<MC_NT>(s_win, wp, ref - (HALF * rstride + HALF) * BPS, rstride * BPS, wbytes, wrows);
     __syncthreads();
     const int8_t *tx = TAPS == 8 ? c_luma_taps[fx] : c_chroma_taps[fx];
     const int8_t *ty = TAPS == 8 ? c_luma_taps[fy] : c_chroma_taps[fy];
     const uint32_t cx0 = pack4(tx), cx1 = TAPS == 8 ? pack4(tx + 4) : 0u;
     const uint32_t cy0 = pack4(ty), cy1 = TAPS == 8 ? pack4(ty + 4) : 0u;
     // ---- H pass: s_tmp[r][x], r in [0, wrows), pitch tw (s16) ----
-    const int gpr = tw >> 2;
+    if (HBD) {
+        // two adjacent outputs per thread from TAPS/2 + 1 words of s16 pairs; DP2A on (sample, sample) x (tap, tap)
+        const int ppr = tw >> 1;
+        for (int i = threadIdx.x; i < wrows * ppr; i += MC_NT) {
+            const int r = i / ppr, x0 = (i - r * ppr) * 2;
+            const int c0 = (a >> 1) + x0, par = c0 & 1;
+            const uint32_t *row = (const uint32_t *)(s_win + r * wp) + (c0 >> 1);
+            uint32_t w[TAPS / 2 + 1];
+#pragma unroll
+            for (int k = 0; k < TAPS / 2 + 1; ++k) w[k] = row[k];
+            int o0 = 0, o1 = 0;
+#pragma unroll
+            for (int k = 0; k < TAPS / 2; ++k) {
+                const uint32_t sh = __funnelshift_r(w[k], w[k + 1], 16);
+                const uint32_t p0 = par ? sh : w[k], p1 = par ? w[k + 1] : sh;
+                const uint32_t cc = k < 2 ? cx0 : cx1;
+                if ((k & 1) == 0) { o0 = dp2a_lo_ss(p0, cc, o0); o1 = dp2a_lo_ss(p1, cc, o1); }
+                else { o0 = dp2a_hi_ss(p0, cc, o0); o1 = dp2a_hi_ss(p1, cc, o1); }
+            }
+            *(uint32_t *)(s_tmp + r * tw + x0) = (uint32_t)(uint16_t)((o0 - 32768) >> 2) | ((uint32_t)(uint16_t)((o1 - 32768) >> 2) << 16);
+        }
+    }
+    const int gpr = HBD ? 0 : tw >> 2;
     for (int i = threadIdx.x; i < wrows * gpr; i += MC_NT) {
         const int r = i / gpr, x0 = (i - r * gpr) * 4;
         const uint32_t *row = (const uint32_t *)(s_win + r * wp);
@@ -128,7 +154,15 @@ __device__ void interp_tile(const uint8_t *ref, int rstride, int fx, int fy, int
             }
             acc[ry][0] = a0; acc[ry][1] = a1;
         }
-        if (out8) {
+        if (out8 && HBD) {
+#pragma unroll
+            for (int ry = 0; ry < 2; ++ry) {
+                const int v0 = min(max((acc[ry][0] + 524800) >> 10, 0), 1023), v1 = min(max((acc[ry][1] + 524800) >> 10, 0), 1023);
+                uint16_t *o = (uint16_t *)out8 + (size_t)(y + ry) * ostride + x;
+                if (((uintptr_t)o & 3) == 0) *(uint32_t *)o = (uint32_t)v0 | ((uint32_t)v1 << 16);
+                else { o[0] = (uint16_t)v0; o[1] = (uint16_t)v1; }
+            }
+        } else if (out8) {
 #pragma unroll
             for (int ry = 0; ry < 2; ++ry) {
                 const int v0 = min(max((acc[ry][0] + 2048) >> 12, 0), 255), v1 = min(max((acc[ry][1] + 2048) >> 12, 0), 255);
@@ -147,11 +181,23 @@ __device__ void interp_tile(const uint8_t *ref, int rstride, int fx, int fy, int
 __device__ __forceinline__ int clampi(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // uni (rp1 == nullptr) or bi prediction of one tile of one plane
-template <int TAPS>
+template <int TAPS, bool HBD>
 __device__ void predict_tile(const uint8_t *rp0, int s0, int f0x, int f0y, const uint8_t *rp1, int s1, int f1x, int f1y, int tw, int th,
                              uint8_t *out, int ostride, uint8_t *s_win, int16_t *s_tmp, int16_t *s_raw0, int16_t *s_raw1)
 {
-    if ((f0x | f0y) == 0 && (!rp1 || (f1x | f1y) == 0)) {
+    if (HBD && (f0x | f0y) == 0 && (!rp1 || (f1x | f1y) == 0)) {
+        // uniPredCopy16bit (C_DEFAULT/EbMcp_C.c:3827) / BiPredClippingOnTheFly16bit (Codec/EbMcp.c:847): (p0 + p1 + 1) >> 1
+        for (int i = threadIdx.x; i < th * (tw >> 1); i += MC_NT) {
+            const int y = i / (tw >> 1), x = (i - y * (tw >> 1)) * 2;
+            const uint16_t *a = (const uint16_t *)rp0 + (size_t)y * s0 + x;
+            uint32_t v = (uint32_t)a[0] | ((uint32_t)a[1] << 16);
+            if (rp1) { const uint16_t *b = (const uint16_t *)rp1 + (size_t)y * s1 + x; v = __vavgu2(v, (uint32_t)b[0] | ((uint32_t)b[1] << 16)); }
+            uint16_t *o = (uint16_t *)out + (size_t)y * ostride + x;
+            o[0] = (uint16_t)v; o[1] = (uint16_t)(v >> 16);
+        }
+        return;
+    }
+    if (!HBD && (f0x | f0y) == 0 && (!rp1 || (f1x | f1y) == 0)) {
         // integer motion vectors (every layer-1..3 picture of M10 runs integer-pel ME): LumaInterpolationCopy (C_DEFAULT/EbMcp_C.c:221) /
         // BiPredClippingOnTheFly (Codec/EbMcp.c:603): ((p0 << 6) + (p1 << 6) + 64) >> 7 == (p0 + p1 + 1) >> 1
         for (int i = threadIdx.x; i < th * (tw >> 2); i += MC_NT) {
@@ -165,12 +211,22 @@ __device__ void predict_tile(const uint8_t *rp0, int s0, int f0x, int f0y, const
         return;
     }
     if (!rp1) {
-        interp_tile<TAPS>(rp0, s0, f0x, f0y, tw, th, s_win, s_tmp, out, ostride, nullptr);
+        interp_tile<TAPS, HBD>(rp0, s0, f0x, f0y, tw, th, s_win, s_tmp, out, ostride, nullptr);
         return;
     }
-    interp_tile<TAPS>(rp0, s0, f0x, f0y, tw, th, s_win, s_tmp, nullptr, 0, s_raw0);
-    interp_tile<TAPS>(rp1, s1, f1x, f1y, tw, th, s_win, s_tmp, nullptr, 0, s_raw1);
+    interp_tile<TAPS, HBD>(rp0, s0, f0x, f0y, tw, th, s_win, s_tmp, nullptr, 0, s_raw0);
+    interp_tile<TAPS, HBD>(rp1, s1, f1x, f1y, tw, th, s_win, s_tmp, nullptr, 0, s_raw1);
     __syncthreads();
+    if (HBD) {   // BiPredClipping16bit, C_DEFAULT/EbMcp_C.c:3265: (l0 + l1 + 16400) >> 5 (16400 = 2 * 8192 bias + rounding)
+        for (int i = threadIdx.x; i < th * (tw >> 1); i += MC_NT) {
+            const int y = i / (tw >> 1), x = (i - y * (tw >> 1)) * 2;
+            const uint32_t a = *(const uint32_t *)(s_raw0 + y * tw + x), b = *(const uint32_t *)(s_raw1 + y * tw + x);
+            uint16_t *o = (uint16_t *)out + (size_t)y * ostride + x;
+            o[0] = (uint16_t)min(max(((int)(short)(a & 0xffff) + (int)(short)(b & 0xffff) + 16400) >> 5, 0), 1023);
+            o[1] = (uint16_t)min(max((((int)a >> 16) + ((int)b >> 16) + 16400) >> 5, 0), 1023);
+        }
+        return;
+    }
     // BiPredClipping, C_DEFAULT/EbMcp_C.c:21 (the -8192 biases of the reference's raw buffers cancel against Offset5)
     for (int i = threadIdx.x; i < th * (tw >> 1); i += MC_NT) {
         const int y = i / (tw >> 1), x = (i - y * (tw >> 1)) * 2;
@@ -183,9 +239,11 @@ __device__ void predict_tile(const uint8_t *rp0, int s0, int f0x, int f0y, const
     }
 }
 
+template <bool HBD>
 __global__ void __launch_bounds__(MC_NT) mc_batch_kernel(const __grid_constant__ McArgs A)
 {
-    __shared__ __align__(16) uint8_t s_win[(TILE + 7) * 96];   // win_pitch(39) = 80
+    constexpr int BPS = HBD ? 2 : 1;
+    __shared__ __align__(16) uint8_t s_win[(TILE + 7) * (HBD ? 128 : 96)];   // win_pitch(39) = 80, win_pitch(78) = 112
     __shared__ __align__(16) int16_t s_tmp[(TILE + 7) * TILE];
     __shared__ __align__(16) int16_t s_raw[2][TILE * TILE];
     const int job = blockIdx.x;
@@ -196,7 +254,7 @@ __global__ void __launch_bounds__(MC_NT) mc_batch_kernel(const __grid_constant__
 #pragma unroll
     for (int l = 0; l < 2; ++l) {
         if (!(q.dir == l || q.dir == 2)) continue;
-        r[l] = &A.refs[min((int)q.ref_idx[l], A.n_refs - 1)];
+        r[l] = &A.refs[min((int)q.ref_idx[l], A.n_refs - 1)];   // param space
         // absolute quarter-pel position in the padded reference (EB_U16 like the reference); a clamped position has no fraction
         px[l] = (uint16_t)clampi((r[l]->ox - 71) << 2, (r[l]->w + r[l]->ox + 7) << 2, ((q.x + r[l]->ox) << 2) + q.mv[l][0]);
         py[l] = (uint16_t)clampi((r[l]->oy - 71) << 2, (r[l]->h + r[l]->oy + 7) << 2, ((q.y + r[l]->oy) << 2) + q.mv[l][1]);
@@ -209,10 +267,10 @@ __global__ void __launch_bounds__(MC_NT) mc_batch_kernel(const __grid_constant__
     const int l0 = bi ? 0 : q.dir, l1 = 1;
     // luma
     {
-        uint8_t *dy = A.dst[0] + (size_t)(A.doy + q.y + ty0) * A.dstride[0] + A.dox + q.x + tx0;
-        const uint8_t *rp0 = r[l0]->p[0] + (size_t)((py[l0] >> 2) + ty0) * r[l0]->stride[0] + (px[l0] >> 2) + tx0;
-        const uint8_t *rp1 = bi ? r[l1]->p[0] + (size_t)((py[l1] >> 2) + ty0) * r[l1]->stride[0] + (px[l1] >> 2) + tx0 : nullptr;
-        predict_tile<8>(rp0, r[l0]->stride[0], px[l0] & 3, py[l0] & 3, rp1, bi ? r[l1]->stride[0] : 0, px[l1] & 3, py[l1] & 3, tw, th, dy, A.dstride[0],
+        uint8_t *dy = A.dst[0] + ((size_t)(A.doy + q.y + ty0) * A.dstride[0] + A.dox + q.x + tx0) * BPS;
+        const uint8_t *rp0 = r[l0]->p[0] + ((size_t)((py[l0] >> 2) + ty0) * r[l0]->stride[0] + (px[l0] >> 2) + tx0) * BPS;
+        const uint8_t *rp1 = bi ? r[l1]->p[0] + ((size_t)((py[l1] >> 2) + ty0) * r[l1]->stride[0] + (px[l1] >> 2) + tx0) * BPS : nullptr;
+        predict_tile<8, HBD>(rp0, r[l0]->stride[0], px[l0] & 3, py[l0] & 3, rp1, bi ? r[l1]->stride[0] : 0, px[l1] & 3, py[l1] & 3, tw, th, dy, A.dstride[0],
                         s_win, s_tmp, s_raw[0], s_raw[1]);
     }
     // chroma (Cb then Cr): half-size tile, eighth-pel phases
@@ -221,9 +279,9 @@ __global__ void __launch_bounds__(MC_NT) mc_batch_kernel(const __grid_constant__
     const size_t cidx = (((size_t)(A.doy + q.y) * A.dstride[1]) >> 1) + ((A.dox + q.x) >> 1) + (size_t)(ty0 >> 1) * A.dstride[1] + (tx0 >> 1);
 #pragma unroll 1
     for (int pl = 1; pl < 3; ++pl) {
-        const uint8_t *rp0 = r[l0]->p[pl] + (size_t)((py[l0] >> 3) + (ty0 >> 1)) * r[l0]->stride[pl] + (px[l0] >> 3) + (tx0 >> 1);
-        const uint8_t *rp1 = bi ? r[l1]->p[pl] + (size_t)((py[l1] >> 3) + (ty0 >> 1)) * r[l1]->stride[pl] + (px[l1] >> 3) + (tx0 >> 1) : nullptr;
-        predict_tile<4>(rp0, r[l0]->stride[pl], px[l0] & 7, py[l0] & 7, rp1, bi ? r[l1]->stride[pl] : 0, px[l1] & 7, py[l1] & 7, cw, ch, A.dst[pl] + cidx,
+        const uint8_t *rp0 = r[l0]->p[pl] + ((size_t)((py[l0] >> 3) + (ty0 >> 1)) * r[l0]->stride[pl] + (px[l0] >> 3) + (tx0 >> 1)) * BPS;
+        const uint8_t *rp1 = bi ? r[l1]->p[pl] + ((size_t)((py[l1] >> 3) + (ty0 >> 1)) * r[l1]->stride[pl] + (px[l1] >> 3) + (tx0 >> 1)) * BPS : nullptr;
+        predict_tile<4, HBD>(rp0, r[l0]->stride[pl], px[l0] & 7, py[l0] & 7, rp1, bi ? r[l1]->stride[pl] : 0, px[l1] & 7, py[l1] & 7, cw, ch, A.dst[pl] + cidx * BPS,
                         A.dstride[pl], s_win, s_tmp, s_raw[0], s_raw[1]);
     }
     __syncthreads();
@@ -241,7 +299,7 @@ __global__ void __launch_bounds__(MC_NT) mc_leaf_kernel(const uint8_t *r0, int s
     for (int ty0 = 0; ty0 < h; ty0 += TILE)
         for (int tx0 = 0; tx0 < w; tx0 += TILE) {
             const int tw = min(TILE, w - tx0), th = min(TILE, h - ty0);
-            predict_tile<TAPS>(r0 + (size_t)ty0 * s0 + tx0, s0, f0x, f0y, r1 ? r1 + (size_t)ty0 * s1 + tx0 : nullptr, s1, f1x, f1y, tw, th,
+            predict_tile<TAPS, false>(r0 + (size_t)ty0 * s0 + tx0, s0, f0x, f0y, r1 ? r1 + (size_t)ty0 * s1 + tx0 : nullptr, s1, f1x, f1y, tw, th,
                                dst + (size_t)ty0 * ds + tx0, ds, s_win, s_tmp, s_raw[0], s_raw[1]);
         }
 }
@@ -265,16 +323,17 @@ static int check_pic(const svtb200_yuv_picture &p, const char *what)
     return SVTB200_OK;
 }
 
-static int launch_mc(const YuvD *d_refs, int n_refs, const svtb200_mc_job *d_jobs, int n_jobs, const svtb200_yuv_picture &dst,
-                     uint8_t *dy, uint8_t *dcb, uint8_t *dcr, cudaStream_t st)
+static int launch_mc(const YuvD *h_refs, int n_refs, const svtb200_mc_job *d_jobs, int n_jobs, const svtb200_yuv_picture &dst,
+                     uint8_t *dy, uint8_t *dcb, uint8_t *dcr, cudaStream_t st, bool hbd = false)
 {
     McArgs A;
-    A.refs = d_refs; A.n_refs = n_refs; A.jobs = d_jobs; A.n_jobs = n_jobs;
+    for (int i = 0; i < 16; ++i) A.refs[i] = h_refs[i < n_refs ? i : 0];
+    A.n_refs = n_refs; A.jobs = d_jobs; A.n_jobs = n_jobs;
     A.dst[0] = dy; A.dst[1] = dcb; A.dst[2] = dcr;
     A.dstride[0] = (int)dst.y.stride; A.dstride[1] = (int)dst.cb.stride; A.dstride[2] = (int)dst.cr.stride;
     A.dox = dst.y.origin_x; A.doy = dst.y.origin_y;
     if (n_jobs == 0) return SVTB200_OK;
-    mc_batch_kernel<<<n_jobs, MC_NT, 0, st>>>(A);
+    if (hbd) mc_batch_kernel<true><<<n_jobs, MC_NT, 0, st>>>(A); else mc_batch_kernel<false><<<n_jobs, MC_NT, 0, st>>>(A);
     SVTB200_COUNT_LAUNCH();
     SVTB200_CUDA_TRY(cudaGetLastError());
     return SVTB200_OK;
@@ -287,27 +346,22 @@ using namespace svtb200;
 
 extern "C" {
 
-int svtb200_mc_batch_dev(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs_dev, int n_jobs,
-                         const svtb200_yuv_picture *dst, void *cuda_stream)
+static int mc_batch_dev_impl(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs_dev, int n_jobs, const svtb200_yuv_picture *dst, void *cuda_stream, bool hbd)
 {
     if (!refs || n_refs <= 0 || n_refs > 16 || (!jobs_dev && n_jobs) || n_jobs < 0 || !dst) { set_error("mc_batch_dev: bad argument"); return SVTB200_ERR_BAD_ARG; }
     int rc = check_pic(*dst, "destination");
     for (int i = 0; i < n_refs && !rc; ++i) rc = check_pic(refs[i], "reference");
     if (rc) return rc;
-    ThreadCtx *c = tls_ctx();
-    if ((rc = c->init())) return rc;
-    // the small reference-descriptor table travels through this thread's pinned + device arenas
-    c->reset();
-    void *h_tab, *d_tab;
-    if ((rc = c->pin_alloc(sizeof(YuvD) * n_refs, &h_tab)) || (rc = c->dev_alloc(sizeof(YuvD) * n_refs, &d_tab))) return rc;
-    for (int i = 0; i < n_refs; ++i) ((YuvD *)h_tab)[i] = to_yuvd(refs[i], refs[i].y.buf, refs[i].cb.buf, refs[i].cr.buf);
+    if ((rc = ensure_device())) return rc;
+    YuvD tab[16];
+    for (int i = 0; i < n_refs; ++i) tab[i] = to_yuvd(refs[i], refs[i].y.buf, refs[i].cb.buf, refs[i].cr.buf);
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    SVTB200_CUDA_TRY(cudaMemcpyAsync(d_tab, h_tab, sizeof(YuvD) * n_refs, cudaMemcpyHostToDevice, st));
-    return launch_mc((const YuvD *)d_tab, n_refs, jobs_dev, n_jobs, *dst, dst->y.buf, dst->cb.buf, dst->cr.buf, st);
+    return launch_mc(tab, n_refs, jobs_dev, n_jobs, *dst, dst->y.buf, dst->cb.buf, dst->cr.buf, st, hbd);
 }
 
-int svtb200_mc_batch(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs, int n_jobs, const svtb200_yuv_picture *dst)
+static int mc_batch_impl(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs, int n_jobs, const svtb200_yuv_picture *dst, bool hbd)
 {
+    const size_t bps = hbd ? 2 : 1;
     if (!refs || n_refs <= 0 || n_refs > 16 || (!jobs && n_jobs) || n_jobs < 0 || !dst) { set_error("mc_batch: bad argument"); return SVTB200_ERR_BAD_ARG; }
     int rc = check_pic(*dst, "destination");
     for (int i = 0; i < n_refs && !rc; ++i) rc = check_pic(refs[i], "reference");
@@ -323,8 +377,8 @@ int svtb200_mc_batch(const svtb200_yuv_picture *refs, int n_refs, const svtb200_
     if ((rc = c->init())) return rc;
     c->reset();
     size_t need = 4096 + sizeof(YuvD) * n_refs + sizeof(svtb200_mc_job) * (size_t)n_jobs;
-    for (int i = 0; i < n_refs; ++i) need += align_up(pbytes(refs[i].y), 256) + align_up(pbytes(refs[i].cb), 256) + align_up(pbytes(refs[i].cr), 256);
-    need += align_up(pbytes(dst->y), 256) + align_up(pbytes(dst->cb), 256) + align_up(pbytes(dst->cr), 256) + 2048;
+    for (int i = 0; i < n_refs; ++i) need += align_up(bps * pbytes(refs[i].y), 256) + align_up(bps * pbytes(refs[i].cb), 256) + align_up(bps * pbytes(refs[i].cr), 256);
+    need += align_up(bps * pbytes(dst->y), 256) + align_up(bps * pbytes(dst->cb), 256) + align_up(bps * pbytes(dst->cr), 256) + 2048;
     if ((rc = c->dev_reserve(need)) || (rc = c->pin_reserve(sizeof(YuvD) * n_refs + 256))) return rc;
     void *h_tab, *d_tab, *d_jobs;
     if ((rc = c->pin_alloc(sizeof(YuvD) * n_refs, &h_tab)) || (rc = c->dev_alloc(sizeof(YuvD) * n_refs, &d_tab)) ||
@@ -333,25 +387,33 @@ int svtb200_mc_batch(const svtb200_yuv_picture *refs, int n_refs, const svtb200_
         void *p[3];
         const svtb200_plane *pl[3] = {&refs[i].y, &refs[i].cb, &refs[i].cr};
         for (int k = 0; k < 3; ++k) {
-            if ((rc = c->dev_alloc(pbytes(*pl[k]), &p[k]))) return rc;
-            SVTB200_CUDA_TRY(cudaMemcpyAsync(p[k], pl[k]->buf, pbytes(*pl[k]), cudaMemcpyHostToDevice, c->stream));
+            if ((rc = c->dev_alloc(bps * pbytes(*pl[k]), &p[k]))) return rc;
+            SVTB200_CUDA_TRY(cudaMemcpyAsync(p[k], pl[k]->buf, bps * pbytes(*pl[k]), cudaMemcpyHostToDevice, c->stream));
         }
         ((YuvD *)h_tab)[i] = to_yuvd(refs[i], (uint8_t *)p[0], (uint8_t *)p[1], (uint8_t *)p[2]);
     }
     void *dp[3];
     const svtb200_plane *dpl[3] = {&dst->y, &dst->cb, &dst->cr};
     for (int k = 0; k < 3; ++k) {
-        if ((rc = c->dev_alloc(pbytes(*dpl[k]), &dp[k]))) return rc;
+        if ((rc = c->dev_alloc(bps * pbytes(*dpl[k]), &dp[k]))) return rc;
         // the destination is updated in place (only PU areas are written): bring the current content over first
-        SVTB200_CUDA_TRY(cudaMemcpyAsync(dp[k], dpl[k]->buf, pbytes(*dpl[k]), cudaMemcpyHostToDevice, c->stream));
+        SVTB200_CUDA_TRY(cudaMemcpyAsync(dp[k], dpl[k]->buf, bps * pbytes(*dpl[k]), cudaMemcpyHostToDevice, c->stream));
     }
-    SVTB200_CUDA_TRY(cudaMemcpyAsync(d_tab, h_tab, sizeof(YuvD) * n_refs, cudaMemcpyHostToDevice, c->stream));
     if (n_jobs) SVTB200_CUDA_TRY(cudaMemcpyAsync(d_jobs, jobs, sizeof(svtb200_mc_job) * (size_t)n_jobs, cudaMemcpyHostToDevice, c->stream));
-    if ((rc = launch_mc((const YuvD *)d_tab, n_refs, (const svtb200_mc_job *)d_jobs, n_jobs, *dst, (uint8_t *)dp[0], (uint8_t *)dp[1], (uint8_t *)dp[2], c->stream))) return rc;
-    for (int k = 0; k < 3; ++k) SVTB200_CUDA_TRY(cudaMemcpyAsync(dpl[k]->buf, dp[k], pbytes(*dpl[k]), cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = launch_mc((const YuvD *)h_tab, n_refs, (const svtb200_mc_job *)d_jobs, n_jobs, *dst, (uint8_t *)dp[0], (uint8_t *)dp[1], (uint8_t *)dp[2], c->stream, hbd))) return rc;
+    for (int k = 0; k < 3; ++k) SVTB200_CUDA_TRY(cudaMemcpyAsync(dpl[k]->buf, dp[k], bps * pbytes(*dpl[k]), cudaMemcpyDeviceToHost, c->stream));
     SVTB200_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return SVTB200_OK;
 }
+
+int svtb200_mc_batch_dev(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs_dev, int n_jobs, const svtb200_yuv_picture *dst, void *cuda_stream)
+{ return mc_batch_dev_impl(refs, n_refs, jobs_dev, n_jobs, dst, cuda_stream, false); }
+int svtb200_mc_batch(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs, int n_jobs, const svtb200_yuv_picture *dst)
+{ return mc_batch_impl(refs, n_refs, jobs, n_jobs, dst, false); }
+int svtb200_mc_batch16_dev(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs_dev, int n_jobs, const svtb200_yuv_picture *dst, void *cuda_stream)
+{ return mc_batch_dev_impl(refs, n_refs, jobs_dev, n_jobs, dst, cuda_stream, true); }
+int svtb200_mc_batch16(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs, int n_jobs, const svtb200_yuv_picture *dst)
+{ return mc_batch_impl(refs, n_refs, jobs, n_jobs, dst, true); }
 
 // ---- leaf entry points: a single block through the same kernel ----------------------------------------------
 static int mc_leaf(int taps, uint32_t f0x, uint32_t f0y, const uint8_t *ref0, uint32_t r0s, bool bi, uint32_t f1x, uint32_t f1y, const uint8_t *ref1,

@@ -270,13 +270,14 @@ class HostYuvPicture:
     """8-bit 4:2:0 picture with the reference's recon-reference geometry: luma pad 80 = 64 + MCPXPaddingOffset 16
     (EbEncHandle.c:867-870), chroma pad 40; edge-replicated like GeneratePadding (EbMcp.c:1017)."""
 
-    def __init__(self, y, cb, cr, pad=80, replicate=True):
+    def __init__(self, y, cb, cr, pad=80, replicate=True, dtype=np.uint8):
+        """dtype np.uint16: 16-bit sample planes (10-bit video); strides and origins stay in samples"""
         self.height, self.width = y.shape
         self.pad = pad
         mode = "edge" if replicate else "constant"
-        self.y = np.ascontiguousarray(np.pad(np.asarray(y, np.uint8), pad, mode=mode))
-        self.cb = np.ascontiguousarray(np.pad(np.asarray(cb, np.uint8), pad // 2, mode=mode))
-        self.cr = np.ascontiguousarray(np.pad(np.asarray(cr, np.uint8), pad // 2, mode=mode))
+        self.y = np.ascontiguousarray(np.pad(np.asarray(y, dtype), pad, mode=mode))
+        self.cb = np.ascontiguousarray(np.pad(np.asarray(cb, dtype), pad // 2, mode=mode))
+        self.cr = np.ascontiguousarray(np.pad(np.asarray(cr, dtype), pad // 2, mode=mode))
         self.struct = YuvPicture()
         for name, arr, p, w, h in (("y", self.y, pad, self.width, self.height), ("cb", self.cb, pad // 2, self.width // 2, self.height // 2),
                                    ("cr", self.cr, pad // 2, self.width // 2, self.height // 2)):
@@ -300,6 +301,12 @@ def mc_batch(refs, jobs, dst):
     """refs: list of HostYuvPicture; jobs: numpy array of MC_JOB_DTYPE; dst: HostYuvPicture (written in place)."""
     jobs = np.ascontiguousarray(jobs)
     check(lib().svtb200_mc_batch(yuv_array(refs), C.c_int(len(refs)), _u8p(jobs), C.c_int(len(jobs)), C.byref(dst.struct)))
+
+
+def mc_batch16(refs, jobs, dst):
+    """16-bit sample planes (HostYuvPicture(dtype=np.uint16)), 10-bit video"""
+    jobs = np.ascontiguousarray(jobs)
+    check(lib().svtb200_mc_batch16(yuv_array(refs), C.c_int(len(refs)), _u8p(jobs), C.c_int(len(jobs)), C.byref(dst.struct)))
 
 
 def luma_interp(frac, ref, ref_off, rs, w, h):

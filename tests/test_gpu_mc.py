@@ -99,3 +99,35 @@ def test_mc_batch_4k_full_frame():
         want = run_oracle(port, "port_mc_batch", refs, jobs, w, h)
     for a, b, nm in zip(dst.interior(), want.interior(), "Y Cb Cr".split()):
         assert np.array_equal(a, b), f"4K: {nm} differs"
+
+
+# ---- 16-bit samples (10-bit video), SURVEY §8 row b5 ---------------------------------------------------------------------
+@pytest.mark.parametrize("case", MC_CASES, ids=lambda c: c[0])
+def test_mc_batch16_cuda_vs_oracle(case):
+    from test_oracle_mc import make_pictures16, run_oracle16
+    name, w, h, kind, all_fracs, big_mv = case
+    refs = make_pictures16(w, h, seed=w + h, kind=kind)
+    jobs = make_jobs(w, h, len(refs), seed=w, all_fracs=all_fracs, big_mv=big_mv)
+    dst = S.HostYuvPicture(np.zeros((h, w), np.uint16), np.zeros((h // 2, w // 2), np.uint16), np.zeros((h // 2, w // 2), np.uint16), dtype=np.uint16)
+    S.mc_batch16(refs, jobs, dst)
+    want = run_oracle16(port, "port_mc_batch16", refs, jobs, w, h)
+    for a, b, pl in zip(dst.interior(), want.interior(), "y cb cr".split()):
+        assert np.array_equal(a, b), (name, pl, np.argwhere(a != b)[:4])
+    if ref is not None:
+        wr = run_oracle16(ref, "svtref_mc_batch16", refs, jobs, w, h, asm_mode=1 if common.ref_asm_simd_ok() else 0)
+        for a, b in zip(dst.interior(), wr.interior()):
+            assert np.array_equal(a, b), name
+
+
+def test_mc_batch16_integer_mvs_and_alignment():
+    """integer-pel jobs (copy / average shortcut) and pictures whose planes sit at odd sample offsets inside their arrays"""
+    from test_oracle_mc import make_pictures16, run_oracle16
+    w, h = 256, 128
+    refs = make_pictures16(w, h, seed=5, kind="random")
+    jobs = make_jobs(w, h, len(refs), seed=9)
+    jobs["mv"] &= ~3
+    dst = S.HostYuvPicture(np.zeros((h, w), np.uint16), np.zeros((h // 2, w // 2), np.uint16), np.zeros((h // 2, w // 2), np.uint16), dtype=np.uint16)
+    S.mc_batch16(refs, jobs, dst)
+    want = run_oracle16(port, "port_mc_batch16", refs, jobs, w, h)
+    for a, b in zip(dst.interior(), want.interior()):
+        assert np.array_equal(a, b)

@@ -92,3 +92,42 @@ def test_mc_batch_port_vs_reference(case):
         simd = run_oracle(ref, "svtref_mc_batch", refs, jobs, w, h, asm_mode=1)
         for a, b, nm in zip(simd.interior(), want.interior(), "Y Cb Cr".split()):
             assert np.array_equal(a, b), f"{name}: {nm} differs (reference SIMD vs C rows)"
+
+
+# ---- 16-bit samples (10-bit video), SURVEY §8 row b5 ---------------------------------------------------------------------
+def make_pictures16(w, h, seed, n=3, kind="synth"):
+    rng = np.random.default_rng(seed + 1000)
+    out = []
+    for p in make_pictures(w, h, seed, n, kind):
+        planes = []
+        for a in p.interior():
+            if kind == "extremes":
+                planes.append((a.astype(np.uint16) // 255) * 1023)
+            else:
+                planes.append(a.astype(np.uint16) * 4 + rng.integers(0, 4, a.shape, dtype=np.uint16))
+        out.append(S.HostYuvPicture(*planes, dtype=np.uint16))
+    return out
+
+
+def run_oracle16(lib, fn_name, refs, jobs, w, h, asm_mode=None):
+    dst = S.HostYuvPicture(np.zeros((h, w), np.uint16), np.zeros((h // 2, w // 2), np.uint16), np.zeros((h // 2, w // 2), np.uint16), dtype=np.uint16)
+    fn = getattr(lib, fn_name)
+    fn.restype = C.c_int
+    args = [S.yuv_array(refs), C.c_int(len(refs)), jobs.ctypes.data_as(C.c_void_p), C.c_int(len(jobs)), C.byref(dst.struct)]
+    if asm_mode is not None:
+        args.append(C.c_int(asm_mode))
+    assert fn(*args) == 0
+    return dst
+
+
+@needs_ref
+@pytest.mark.parametrize("case", MC_CASES, ids=lambda c: c[0])
+def test_mc_batch16_port_vs_reference(case):
+    name, w, h, kind, all_fracs, big_mv = case
+    refs = make_pictures16(w, h, seed=w + h, kind=kind)
+    jobs = make_jobs(w, h, len(refs), seed=w, all_fracs=all_fracs, big_mv=big_mv)
+    got = run_oracle16(port, "port_mc_batch16", refs, jobs, w, h)
+    for asm in ([0, 1] if common.ref_asm_simd_ok() else [0]):
+        want = run_oracle16(ref, "svtref_mc_batch16", refs, jobs, w, h, asm_mode=asm)
+        for a, b, pl in zip(got.interior(), want.interior(), "y cb cr".split()):
+            assert np.array_equal(a, b), (name, asm, pl, np.argwhere(a != b)[:4])
