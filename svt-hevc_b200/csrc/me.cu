@@ -199,12 +199,18 @@ __device__ void lcu_sads(const uint8_t *s_src, const PlaneD &rF, int ox, int oy,
 #pragma unroll
     for (int k = 0; k < N; ++k) acc[k] = 0;
     const int rows = lh >> 1, nw = lw >> 2;   // lw is a multiple of 8 (minimum CU size)
+    const uint8_t *base[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) base[k] = pat(rF, ox + dx[k < ncand ? k : 0], oy + dy[k < ncand ? k : 0]);
+    const ptrdiff_t rs2 = 2 * (ptrdiff_t)rF.stride;
+#pragma unroll 2
     for (int i = threadIdx.x; i < rows * nw; i += NT) {
         const int r = i / nw, j = i - r * nw;
         const uint32_t s = ((const uint32_t *)s_src)[(2 * r) * 16 + j];
+        const ptrdiff_t off = r * rs2 + 4 * j;
 #pragma unroll
         for (int k = 0; k < N; ++k)
-            if (k < ncand) acc[k] += __vsadu4(s, ld_u32_unaligned(pat(rF, ox + dx[k] + 4 * j, oy + dy[k] + 2 * r)));
+            if (k < ncand) acc[k] += __vsadu4(s, ld_u32_unaligned(base[k] + off));
     }
     block_sum<N>(acc, s_red32);
 #pragma unroll
@@ -598,13 +604,16 @@ __device__ void sp_enables(const uint32_t *s_bsad, const uint32_t *s_bmv, int mo
     if (lane == 0) { s_en[0] = e[0]; s_en[1] = e[1] && cu16_on; s_en[2] = e[2]; }
 }
 
+#ifndef ME_MIN_CTAS
+#define ME_MIN_CTAS 4
+#endif
 struct HmeRes { uint32_t sad; int x, y; };   // sad already doubled may exceed 24 bits -> keep 32
 
 // ============================================================================================
 // Picture kernel: one CTA per LCU
 // ============================================================================================
 template <bool SUBPEL>
-__global__ void __launch_bounds__(NT, SUBPEL ? 2 : 3) me_picture_kernel(const __grid_constant__ MeArgs A)
+__global__ void __launch_bounds__(NT, SUBPEL ? 2 : ME_MIN_CTAS) me_picture_kernel(const __grid_constant__ MeArgs A)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *s_src = smem;                                   // 64*64
@@ -886,11 +895,15 @@ __global__ void __launch_bounds__(NT, SUBPEL ? 2 : 3) me_picture_kernel(const __
             } else {
                 const int x0 = s16(s_bmv[n] & 0xffff) >> 2, y0 = s16(s_bmv[n] >> 16) >> 2;
                 const int x1 = s16(s_bmv[85 + n] & 0xffff) >> 2, y1 = s16(s_bmv[85 + n] >> 16) >> 2;
+                const uint8_t *b0 = pat(A.ref[0][0], ox + px + x0, oy + py + y0), *b1 = pat(A.ref[1][0], ox + px + x1, oy + py + y1);
+                const ptrdiff_t st0 = A.ref[0][0].stride, st1 = A.ref[1][0].stride;
+                const int lgnw = 31 - __clz(nw);
+#pragma unroll 4
                 for (int i = lane; i < items; i += 32) {
-                    const int r = (i / nw) * step, j = i - (i / nw) * nw;
+                    const int r = (i >> lgnw) * step, j = i & (nw - 1);
                     const uint32_t sw = ((const uint32_t *)s_src)[(py + r) * 16 + (px >> 2) + j];
-                    const uint32_t p0 = ld_u32_unaligned(pat(A.ref[0][0], ox + px + x0 + 4 * j, oy + py + y0 + r));
-                    const uint32_t p1 = ld_u32_unaligned(pat(A.ref[1][0], ox + px + x1 + 4 * j, oy + py + y1 + r));
+                    const uint32_t p0 = ld_u32_unaligned(b0 + r * st0 + 4 * j);
+                    const uint32_t p1 = ld_u32_unaligned(b1 + r * st1 + 4 * j);
                     acc += __vsadu4(sw, __vavgu4(p0, p1));
                 }
             }

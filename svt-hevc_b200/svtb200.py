@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsvthevc_b200.so")
+LIB_PATH = os.environ.get("SVTB200_LIB") or os.path.join(_HERE, "libsvthevc_b200.so")   # the override is for A/B builds of the same ABI
 
 ME_PU_COUNT = 85
 
