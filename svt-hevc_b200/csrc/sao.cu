@@ -9,7 +9,8 @@
 //
 // Design.  Statistics: one CTA (128 threads) per (LCU, component); the reconstructed block is staged once in shared memory; edge
 // classes are computed SIMD-in-word for 4 samples at a time (edge_idx4: packed compares, no per-sample branches) and accumulated in
-// registers; band statistics go to per-warp private histograms packed as (count << 16) + sum, merged at the end.  Application: out = SAO(in), one
+// thread-private [row][thread] shared-memory histograms (EO type x edge index, and the 32 bands) packed as (count << 16) + sum -- bank-conflict
+// free by construction, no atomics, column-summed at the end.  Application: out = SAO(in), one
 // thread per 4 samples, neighbours always read from the unmodified input picture, so the reference's line buffers
 // (saoUpBuffer / saoLeftBuffer) have no counterpart.  Both kernels are HBM-bound (18 432 B per CTU).
 #include "common.cuh"
@@ -41,13 +42,14 @@ __device__ __forceinline__ int dp4a_ss(uint32_t a_s8x4, uint32_t b_s8x4, int c)
 }
 
 constexpr int ST_NT = 128;
+constexpr int ST_ROWS = 20 + 32;      // histogram rows: EO type * 5 + edge index (0..4), then the 32 bands
 __global__ void __launch_bounds__(ST_NT) sao_stats_kernel(const __grid_constant__ StatsArgs A)
 {
     // reconstructed block with a one-word margin on the left (column 4 = block x 0); pitch 72 bytes = 18 words
     __shared__ __align__(16) uint8_t s_rec[64 * 72];
-    // thread-private band histograms: word = (count << 16) + sum(diff); pitch 33 keeps the 32 lanes of a warp on distinct banks
-    __shared__ int s_bo[ST_NT * 33];
-    __shared__ int s_eo[ST_NT / 32][32];
+    // thread-private histograms, [row][thread]: a thread only ever touches its own column, so a warp's 32 accesses always fall on 32 different
+    // banks whatever rows they hit -- no atomics, no conflicts.  word = (count << 16) + sum(diff) (both small per thread: <= 31 samples).
+    __shared__ int s_h[ST_ROWS * ST_NT];
     const int job = blockIdx.x, lcu = job / 3, c = job - lcu * 3, sh = c ? 1 : 0;
     const int lx = lcu % A.cols, ly = lcu / A.cols;
     const int ox = (lx * 64) >> sh, oy = (ly * 64) >> sh;
@@ -58,14 +60,10 @@ __global__ void __launch_bounds__(ST_NT) sao_stats_kernel(const __grid_constant_
         const int y = i / wpr, x4 = i - y * wpr;
         ((uint32_t *)(s_rec + y * 72))[1 + x4] = *(const uint32_t *)(r + (size_t)y * A.rec[c].stride + 4 * x4);   // block origins are 4-aligned
     }
-    for (int k = 0; k < 33; ++k) s_bo[threadIdx.x * 33 + k] = 0;
+    int *my = s_h + threadIdx.x;
+#pragma unroll 4
+    for (int k = 0; k < ST_ROWS; ++k) my[k * ST_NT] = 0;
     __syncthreads();
-    int ed[4][4], ec[4][4];     // [EO type][category 0,1,3,4 -> 0..3]
-#pragma unroll
-    for (int t = 0; t < 4; ++t)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { ed[t][k] = 0; ec[t][k] = 0; }
-    int *my_bo = s_bo + threadIdx.x * 33;
     const int n_items = (lh - 2) * wpr;
     for (int i = threadIdx.x; i < n_items; i += ST_NT) {
         const int y = 1 + i / wpr, xw = i % wpr;
@@ -78,51 +76,42 @@ __global__ void __launch_bounds__(ST_NT) sao_stats_kernel(const __grid_constant_
         if (xw == wpr - 1) vm &= 0x00ffffffu;
         // diff = clipToSigned8Bit(src - rec), packed s8
         const uint32_t dpos = __vminu4(__vsubus4(sv, v), 0x7f7f7f7fu), dneg = __vminu4(__vsubus4(v, sv), 0x80808080u);
-        const uint32_t d = __vsub4(dpos, dneg) & vm;
+        const uint32_t d = __vsub4(dpos, dneg);
         const uint32_t L = __funnelshift_r(c0, v, 24), R = __funnelshift_r(v, c2, 8);
         const uint32_t UL = __funnelshift_r(up0, up1, 24), UR = __funnelshift_r(up1, up2, 8), DL = __funnelshift_r(dn0, dn1, 24), DR = __funnelshift_r(dn1, dn2, 8);
         const uint32_t e[4] = {edge_idx4(v, L, R), edge_idx4(v, up1, dn1), edge_idx4(v, UL, DR), edge_idx4(v, UR, DL)};   // EO-0, 90, 135, 45
 #pragma unroll
-        for (int t = 0; t < 4; ++t)
+        for (int b = 0; b < 4; ++b) {
+            if (!((vm >> (8 * b)) & 1)) continue;
+            const int add = 65536 + (int)(signed char)(d >> (8 * b));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t cat = (k < 2 ? k : k + 1) * 0x01010101u;
-                const uint32_t hit = __vcmpeq4(e[t], cat) & vm;
-                ed[t][k] = dp4a_ss(d & hit, 0x01010101u, ed[t][k]);
-                ec[t][k] += __popc(hit) >> 3;
-            }
-        // band offset: private histogram, no atomics
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-            if ((vm >> (8 * b)) & 1) my_bo[(v >> (8 * b + 3)) & 31] += 65536 + (int)(signed char)(d >> (8 * b));
-    }
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-    for (int t = 0; t < 4; ++t)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int dsum = __reduce_add_sync(0xffffffffu, ed[t][k]), csum = __reduce_add_sync(0xffffffffu, ec[t][k]);
-            if (lane == 0) { s_eo[wid][t * 4 + k] = dsum; s_eo[wid][16 + t * 4 + k] = csum; }
+            for (int t = 0; t < 4; ++t) my[(t * 5 + ((e[t] >> (8 * b)) & 7)) * ST_NT] += add;
+            my[(20 + ((v >> (8 * b + 3)) & 31)) * ST_NT] += add;
         }
+    }
     __syncthreads();
+    // column sums: warp w takes rows w, w + 4, ...
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     svtb200_sao_stats *o = A.out + job;
-    if (threadIdx.x < 32) {
+    for (int row = wid; row < ST_ROWS; row += ST_NT / 32) {
         int dsum = 0, csum = 0;
-        for (int th = 0; th < ST_NT; ++th) {
-            const int w = s_bo[th * 33 + threadIdx.x], dd = (int)(short)(w & 0xffff);   // |sum(diff)| < 2^15 per thread
+#pragma unroll
+        for (int q = 0; q < ST_NT / 32; ++q) {
+            const int w = s_h[row * ST_NT + lane + 32 * q], dd = (int)(short)(w & 0xffff);
             dsum += dd;
             csum += (w - dd) >> 16;
         }
-        o->bo_diff[threadIdx.x] = dsum;
-        o->bo_count[threadIdx.x] = (uint16_t)csum;
-    } else if (threadIdx.x < 52) {
-        // categories compacted like the reference: slots 0..3 <- raw 0,1,3,4; slot 4 scratch (we write 0)
-        const int q = threadIdx.x - 32, t = q / 5, k = q % 5;
-        int dsum = 0, csum = 0;
-        if (k < 4)
-            for (int w = 0; w < ST_NT / 32; ++w) { dsum += s_eo[w][t * 4 + k]; csum += s_eo[w][16 + t * 4 + k]; }
-        o->eo_diff[t][k] = dsum;
-        o->eo_count[t][k] = (uint16_t)csum;
+        dsum = __reduce_add_sync(0xffffffffu, dsum);
+        csum = __reduce_add_sync(0xffffffffu, csum);
+        if (lane == 0) {
+            if (row >= 20) { o->bo_diff[row - 20] = dsum; o->bo_count[row - 20] = (uint16_t)csum; }
+            else {
+                // categories compacted like the reference: slots 0..3 <- edge index 0, 1, 3, 4; slot 4 is scratch there (we write 0)
+                const int t = row / 5, k = row - t * 5;
+                if (k == 2) { o->eo_diff[t][4] = 0; o->eo_count[t][4] = 0; }
+                else { const int slot = k < 2 ? k : k - 1; o->eo_diff[t][slot] = dsum; o->eo_count[t][slot] = (uint16_t)csum; }
+            }
+        }
     }
 }
 
