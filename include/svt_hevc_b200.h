@@ -270,6 +270,15 @@ int svtb200_tq_batch(const svtb200_yuv_picture *src, const svtb200_yuv_picture *
 int svtb200_tq_batch_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *pred, const svtb200_yuv_picture *recon,
                          const svtb200_coeff_picture *coeff, const svtb200_tq_job *jobs_dev, int n_jobs, uint32_t *nz_counts_dev,
                          void *cuda_stream);
+/* the same chain on 16-bit sample planes (10-bit video): EncodeLoop16bit / EncodeGenerateRecon16bit (Codec/EbCodingLoop.c:1240,1640) --
+ * PictureResidual16bit, EncodeTransform with BIT_INCREMENT_10BIT (EbTransforms.c:3343), UnifiedQuantizeInvQuantize at EB_10BIT with
+ * qp + QP_BD_OFFSET, EncodeInvTransform, PictureAdditionKernel16bit (clip to 1023).  job.qp stays the 8-bit-scale qp (0..51).
+ * svtb200_plane::buf points at uint16_t samples; strides and origins in samples. */
+int svtb200_tq_batch16(const svtb200_yuv_picture *src, const svtb200_yuv_picture *pred, const svtb200_yuv_picture *recon,
+                       const svtb200_coeff_picture *coeff, const svtb200_tq_job *jobs, int n_jobs, uint32_t *nz_counts);
+int svtb200_tq_batch16_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *pred, const svtb200_yuv_picture *recon,
+                           const svtb200_coeff_picture *coeff, const svtb200_tq_job *jobs_dev, int n_jobs, uint32_t *nz_counts_dev,
+                           void *cuda_stream);
 
 /* Leaf entry points (reference prototypes; host pointers). */
 /* EstimateTransform, Codec/EbTransforms.c:3268 (EB_TRANSFORM_FUNC tables EbTransforms.h:339-472) */
@@ -308,6 +317,12 @@ int svtb200_dlf_picture(const svtb200_yuv_picture *recon, const uint8_t *vertica
                         const uint8_t *qp_array, const svtb200_dlf_params *prm);
 int svtb200_dlf_picture_dev(const svtb200_yuv_picture *recon, const uint8_t *vertical_bs, const uint8_t *horizontal_bs,
                             const uint8_t *qp_array, const svtb200_dlf_params *prm, void *cuda_stream);
+/* the same on 16-bit sample planes (10-bit video): LCUInternalAreaDLFCore16bit / LCUBoundaryDLFCore16bit / LCUPictureEdgeDLFCore16bit
+ * (Codec/EbDeblockingFilter.c:2514,3174,3922), edge cores C_DEFAULT/EbDeblockingFilter_C.c:240,524 -- tc and beta scaled by 4, clip to 1023 */
+int svtb200_dlf_picture16(const svtb200_yuv_picture *recon, const uint8_t *vertical_bs, const uint8_t *horizontal_bs,
+                          const uint8_t *qp_array, const svtb200_dlf_params *prm);
+int svtb200_dlf_picture16_dev(const svtb200_yuv_picture *recon, const uint8_t *vertical_bs, const uint8_t *horizontal_bs,
+                              const uint8_t *qp_array, const svtb200_dlf_params *prm, void *cuda_stream);
 
 /* Leaf entry points, reference prototypes (EbDeblockingFilter.h:245-273). In-place on host memory; the caller states how
  * far the plane extends around the edge start via the fixed footprint: 4 samples either side, 4 (luma) / 2 (chroma) along. */
@@ -393,6 +408,11 @@ typedef struct svtb200_intra_job {
 int svtb200_intra_batch(const svtb200_yuv_picture *recon, const svtb200_yuv_picture *pred, const svtb200_intra_job *jobs, uint32_t n_jobs);
 int svtb200_intra_batch_dev(const svtb200_yuv_picture *recon, const svtb200_yuv_picture *pred, const svtb200_intra_job *jobs_dev,
                             uint32_t n_jobs, void *cuda_stream);
+/* the same on 16-bit sample planes (10-bit video): GenerateIntraReference16bitSamplesEncodePass :1688 + EncodePassIntraPrediction16bit :4676
+ * (midrange 512, SMOOTHING_THRESHOLD_10BIT, edge filters clipped to 1023); svtb200_plane::buf points at uint16_t samples */
+int svtb200_intra_batch16(const svtb200_yuv_picture *recon, const svtb200_yuv_picture *pred, const svtb200_intra_job *jobs, uint32_t n_jobs);
+int svtb200_intra_batch16_dev(const svtb200_yuv_picture *recon, const svtb200_yuv_picture *pred, const svtb200_intra_job *jobs_dev,
+                              uint32_t n_jobs, void *cuda_stream);
 
 /* Open-loop intra search of a whole picture: OpenLoopIntraSearchLcu (Codec/EbMotionEstimation.c:5053) for every LCU, with
  * UpdateNeighborSamplesArrayOpenLoop / IntraPredictionOpenLoop (Codec/EbIntraPrediction.c:5222,5339) and the candidate injection

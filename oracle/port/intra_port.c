@@ -24,21 +24,21 @@ static const int FILT_THR[4] = { 35, 7, 1, 0 };                             /* i
 
 static inline int ilog2(int v) { int l = 0; while (v > 1) { v >>= 1; ++l; } return l; }
 static inline int iabs(int v) { return v < 0 ? -v : v; }
-static inline int clip8(int v) { return v < 0 ? 0 : v > 255 ? 255 : v; }
+static inline int clipv(int v, int maxv) { return v < 0 ? 0 : v > maxv ? maxv : v; }
 
 /* sample m of the "main" reference of an angular mode: m = 0 top-left, m > 0 the main side, m < 0 projected from the other side */
-static inline int main_ref(const uint8_t *line, int N, int vertical, int m, int inv)
+static inline int main_ref(const uint16_t *line, int N, int vertical, int m, int inv)
 {
-    const uint8_t *tl = line + 2 * N;
+    const uint16_t *tl = line + 2 * N;
     if (m >= 0) return vertical ? tl[m] : tl[-m];
     const int j = (128 + (-m) * inv) >> 8;          /* side sample index, 0 = top-left */
     return vertical ? tl[-j] : tl[j];
 }
 
 /* one predicted sample; edge = luma block smaller than 32 (DC / horizontal / vertical boundary smoothing) */
-static int intra_pel(const uint8_t *line, int N, int mode, int x, int y, int edge, int dc)
+static int intra_pel(const uint16_t *line, int N, int mode, int x, int y, int edge, int dc, int maxv)
 {
-    const uint8_t *tl = line + 2 * N;
+    const uint16_t *tl = line + 2 * N;
 #define TOP(i) ((int)tl[1 + (i)])
 #define LEFT(i) ((int)tl[-1 - (i)])
     if (mode == 0) {
@@ -53,8 +53,8 @@ static int intra_pel(const uint8_t *line, int N, int mode, int x, int y, int edg
         }
         return dc;
     }
-    if (mode == 26) return (edge && x == 0) ? clip8(TOP(x) + ((LEFT(y) - (int)tl[0]) >> 1)) : TOP(x);
-    if (mode == 10) return (edge && y == 0) ? clip8(LEFT(y) + ((TOP(x) - (int)tl[0]) >> 1)) : LEFT(y);
+    if (mode == 26) return (edge && x == 0) ? clipv(TOP(x) + ((LEFT(y) - (int)tl[0]) >> 1), maxv) : TOP(x);
+    if (mode == 10) return (edge && y == 0) ? clipv(LEFT(y) + ((TOP(x) - (int)tl[0]) >> 1), maxv) : LEFT(y);
     const int vertical = mode >= 18;
     const int d = vertical ? mode - 26 : 10 - mode;                 /* 2: +8 ... 18: -8 (either family) */
     const int ang = d < 0 ? -ANG[-d] : ANG[d], inv = INV_ANG[iabs(d)];
@@ -68,60 +68,73 @@ static int intra_pel(const uint8_t *line, int N, int mode, int x, int y, int edg
 #undef LEFT
 }
 
-static int dc_value(const uint8_t *line, int N)
+static int dc_value(const uint16_t *line, int N)
 {
     int sum = 0;
     for (int i = 0; i < N; ++i) sum += line[2 * N + 1 + i] + line[2 * N - 1 - i];
-    return (uint8_t)((sum + N) >> (ilog2(N) + 1));
+    return (sum + N) >> (ilog2(N) + 1);
+}
+
+/* block into a scratch int array (pitch N) */
+static void predict_block(int mode, int N, int is_chroma, const uint16_t *line, int maxv, uint16_t *blk)
+{
+    const int edge = !is_chroma && N < 32, dc = mode == 1 ? dc_value(line, N) : 0;
+    for (int y = 0; y < N; ++y)
+        for (int x = 0; x < N; ++x) blk[y * N + x] = (uint16_t)intra_pel(line, N, mode, x, y, edge, dc, maxv);
 }
 
 void port_intra_predict(uint32_t mode, uint32_t size, int is_chroma, const uint8_t *line, uint8_t *pred, uint32_t stride)
 {
-    const int N = (int)size, edge = !is_chroma && N < 32, dc = mode == 1 ? dc_value(line, N) : 0;
+    uint16_t l16[4 * 32 + 1], blk[32 * 32];
+    const int N = (int)size;
+    for (int i = 0; i < 4 * N + 1; ++i) l16[i] = line[i];
+    predict_block((int)mode, N, is_chroma, l16, 255, blk);
     for (int y = 0; y < N; ++y)
-        for (int x = 0; x < N; ++x) pred[(size_t)y * stride + x] = (uint8_t)intra_pel(line, N, (int)mode, x, y, edge, dc);
+        for (int x = 0; x < N; ++x) pred[(size_t)y * stride + x] = (uint8_t)blk[y * N + x];
 }
 
 /* ---- encode pass: reference line from a reconstructed plane with per-unit availability ---------------------------------- */
-/* unit = samples per availability bit in this plane (4 luma, 2 chroma 4:2:0) */
-static void build_line(const uint8_t *plane, uint32_t stride, int x, int y, int N, int unit, uint32_t left_avail, uint32_t top_avail, int tl_avail, uint8_t *line)
+/* unit = samples per availability bit in this plane (4 luma, 2 chroma 4:2:0); bps = bytes per sample (2: 16-bit planes of 10-bit video) */
+static void build_line(const uint8_t *plane, uint32_t stride, int bps, int x, int y, int N, int unit, uint32_t left_avail, uint32_t top_avail, int tl_avail, uint16_t *line)
 {
     const int nu = 2 * N / unit;            /* units per side */
-    const uint8_t *o = plane + (size_t)y * stride + x;
+#define PX(dx, dy) (bps == 2 ? (int)((const uint16_t *)plane)[(ptrdiff_t)(y + (dy)) * (ptrdiff_t)stride + x + (dx)] : (int)plane[(ptrdiff_t)(y + (dy)) * (ptrdiff_t)stride + x + (dx)])
     /* scan order: left units bottom-up, top-left, top units left to right */
-    int have = 0, last = 128;          /* the first available sample in scan order pads everything before it */
+    int have = 0, last = bps == 2 ? 512 : 128;          /* the first available sample in scan order pads everything before it */
     for (int u = 0; u < nu && !have; ++u)
-        if ((left_avail >> u) & 1) { have = 1; last = o[(ptrdiff_t)(2 * N - 1 - u * unit) * (ptrdiff_t)stride - 1]; }
-    if (!have && tl_avail) { have = 1; last = o[-(ptrdiff_t)stride - 1]; }
+        if ((left_avail >> u) & 1) { have = 1; last = PX(-1, 2 * N - 1 - u * unit); }
+    if (!have && tl_avail) { have = 1; last = PX(-1, -1); }
     for (int u = 0; u < nu && !have; ++u)
-        if ((top_avail >> u) & 1) { have = 1; last = o[-(ptrdiff_t)stride + u * unit]; }
-    if (!have) { memset(line, 128, (size_t)4 * N + 1); return; }
+        if ((top_avail >> u) & 1) { have = 1; last = PX(u * unit, -1); }
+    if (!have) { for (int i = 0; i < 4 * N + 1; ++i) line[i] = (uint16_t)last; return; }
     for (int i = 0; i < 2 * N; ++i) {                 /* line[i]: left sample of row 2N-1-i */
-        if ((left_avail >> (i / unit)) & 1) last = o[(ptrdiff_t)(2 * N - 1 - i) * (ptrdiff_t)stride - 1];
-        line[i] = (uint8_t)last;
+        if ((left_avail >> (i / unit)) & 1) last = PX(-1, 2 * N - 1 - i);
+        line[i] = (uint16_t)last;
     }
-    if (tl_avail) last = o[-(ptrdiff_t)stride - 1];
-    line[2 * N] = (uint8_t)last;
+    if (tl_avail) last = PX(-1, -1);
+    line[2 * N] = (uint16_t)last;
     for (int i = 0; i < 2 * N; ++i) {
-        if ((top_avail >> (i / unit)) & 1) last = o[-(ptrdiff_t)stride + i];
-        line[2 * N + 1 + i] = (uint8_t)last;
+        if ((top_avail >> (i / unit)) & 1) last = PX(i, -1);
+        line[2 * N + 1 + i] = (uint16_t)last;
     }
+#undef PX
 }
 
-static void filter_line(const uint8_t *in, int N, int strong_enabled, uint8_t *out)
+/* thr: SMOOTHING_THRESHOLD 8 / SMOOTHING_THRESHOLD_10BIT 32 (Codec/EbIntraPrediction.h:119-120) */
+static void filter_line(const uint16_t *in, int N, int strong_enabled, int thr, uint16_t *out)
 {
     const int bl = in[0], tl = in[2 * N], tr = in[4 * N];
-    if (strong_enabled && N >= 32 && iabs(bl + tl - 2 * in[N]) < 8 && iabs(tl + tr - 2 * in[3 * N]) < 8) {
+    if (strong_enabled && N >= 32 && iabs(bl + tl - 2 * in[N]) < thr && iabs(tl + tr - 2 * in[3 * N]) < thr) {
         const int sh = ilog2(N) + 1;
         out[0] = in[0]; out[2 * N] = in[2 * N]; out[4 * N] = in[4 * N];
         for (int i = 1; i < 2 * N; ++i) {
-            out[i] = (uint8_t)(((2 * N - i) * bl + i * tl + N) >> sh);
-            out[2 * N + i] = (uint8_t)(((2 * N - i) * tl + i * tr + N) >> sh);
+            out[i] = (uint16_t)(((2 * N - i) * bl + i * tl + N) >> sh);
+            out[2 * N + i] = (uint16_t)(((2 * N - i) * tl + i * tr + N) >> sh);
         }
         return;
     }
     out[0] = in[0]; out[4 * N] = in[4 * N];
-    for (int i = 1; i < 4 * N; ++i) out[i] = (uint8_t)((in[i - 1] + 2 * in[i] + in[i + 1] + 2) >> 2);
+    for (int i = 1; i < 4 * N; ++i) out[i] = (uint16_t)((in[i - 1] + 2 * in[i] + in[i + 1] + 2) >> 2);
 }
 
 static int chroma_mode_to_luma(int cm, int luma_mode)
@@ -129,43 +142,48 @@ static int chroma_mode_to_luma(int cm, int luma_mode)
     switch (cm) { case 0: return 0; case 1: return 26; case 2: return 10; case 3: return 1; default: return luma_mode; }
 }
 
-int port_intra_batch(const svtb200_yuv_picture *recon, const svtb200_yuv_picture *pred, const svtb200_intra_job *jobs, uint32_t n_jobs)
+/* hbd: GenerateIntraReference16bitSamplesEncodePass / EncodePassIntraPrediction16bit (Codec/EbIntraPrediction.c:1688,4676): the same process on
+ * 16-bit sample planes, midrange 512, smoothing threshold 32, edge filters clipped to 1023 */
+static int intra_batch_impl(const svtb200_yuv_picture *recon, const svtb200_yuv_picture *pred, const svtb200_intra_job *jobs, uint32_t n_jobs, int hbd)
 {
-    uint8_t line[4 * 32 + 1], filt[4 * 32 + 1], blk[32 * 32];
+    uint16_t line[4 * 32 + 1], filt[4 * 32 + 1], blk[32 * 32];
+    const int bps = hbd ? 2 : 1, maxv = hbd ? 1023 : 255, thr = hbd ? 32 : 8;
     for (uint32_t j = 0; j < n_jobs; ++j) {
         const svtb200_intra_job *t = &jobs[j];
         const int tl = t->flags & SVTB200_INTRA_TOPLEFT_AVAIL, strong = (t->flags & SVTB200_INTRA_STRONG_SMOOTHING) != 0;
-        if (t->luma_mode != SVTB200_INTRA_SKIP) {
-            const int N = t->size, mode = t->luma_mode;
-            const svtb200_plane *rp = &recon->y, *pp = &pred->y;
-            build_line(rp->buf + (size_t)rp->origin_y * rp->stride + rp->origin_x, rp->stride, t->x, t->y, N, 4, t->left_avail, t->top_avail, tl, line);
-            const uint8_t *use = line;
-            const int dmin = iabs(mode - 10) < iabs(mode - 26) ? iabs(mode - 10) : iabs(mode - 26);
-            if (dmin > FILT_THR[ilog2(N) - 2] && mode != 1) { filter_line(line, N, strong, filt); use = filt; }
-            port_intra_predict((uint32_t)mode, (uint32_t)N, 0, use, blk, (uint32_t)N);      /* into a scratch block: pred may alias recon */
-            uint8_t *d = pp->buf + (size_t)(pp->origin_y + t->y) * pp->stride + pp->origin_x + t->x;
-            for (int r = 0; r < N; ++r) memcpy(d + (size_t)r * pp->stride, blk + r * N, (size_t)N);
-        }
-        if (t->chroma_mode != SVTB200_INTRA_SKIP) {
-            const int N = t->size >> 1, mode = chroma_mode_to_luma(t->chroma_mode, t->luma_mode);
-            const svtb200_plane *rps[2] = { &recon->cb, &recon->cr }, *pps[2] = { &pred->cb, &pred->cr };
-            for (int c = 0; c < 2; ++c) {
-                const svtb200_plane *rp = rps[c], *pp = pps[c];
-                build_line(rp->buf + (size_t)rp->origin_y * rp->stride + rp->origin_x, rp->stride, t->x >> 1, t->y >> 1, N, 2, t->left_avail, t->top_avail, tl, line);
-                port_intra_predict((uint32_t)mode, (uint32_t)N, 1, line, blk, (uint32_t)N);
-                uint8_t *d = pp->buf + (size_t)(pp->origin_y + (t->y >> 1)) * pp->stride + pp->origin_x + (t->x >> 1);
-                for (int r = 0; r < N; ++r) memcpy(d + (size_t)r * pp->stride, blk + r * N, (size_t)N);
+        for (int c = 0; c < 3; ++c) {
+            const int luma = c == 0;
+            if (luma ? t->luma_mode == SVTB200_INTRA_SKIP : t->chroma_mode == SVTB200_INTRA_SKIP) continue;
+            const svtb200_plane *rp = c == 0 ? &recon->y : c == 1 ? &recon->cb : &recon->cr, *pp = c == 0 ? &pred->y : c == 1 ? &pred->cb : &pred->cr;
+            const int N = luma ? t->size : t->size >> 1, x = luma ? t->x : t->x >> 1, y = luma ? t->y : t->y >> 1;
+            const int mode = luma ? t->luma_mode : chroma_mode_to_luma(t->chroma_mode, t->luma_mode);
+            build_line(rp->buf + ((size_t)rp->origin_y * rp->stride + rp->origin_x) * bps, rp->stride, bps, x, y, N, luma ? 4 : 2, t->left_avail, t->top_avail, tl, line);
+            const uint16_t *use = line;
+            if (luma) {
+                const int dmin = iabs(mode - 10) < iabs(mode - 26) ? iabs(mode - 10) : iabs(mode - 26);
+                if (dmin > FILT_THR[ilog2(N) - 2] && mode != 1) { filter_line(line, N, strong, thr, filt); use = filt; }
             }
+            predict_block(mode, N, !luma, use, maxv, blk);      /* into a scratch block: pred may alias recon */
+            uint8_t *d = pp->buf + ((size_t)(pp->origin_y + y) * pp->stride + pp->origin_x + x) * bps;
+            for (int r = 0; r < N; ++r)
+                for (int q = 0; q < N; ++q) {
+                    if (hbd) ((uint16_t *)d)[(size_t)r * pp->stride + q] = blk[r * N + q];
+                    else d[(size_t)r * pp->stride + q] = (uint8_t)blk[r * N + q];
+                }
         }
     }
     return 0;
 }
+int port_intra_batch(const svtb200_yuv_picture *recon, const svtb200_yuv_picture *pred, const svtb200_intra_job *jobs, uint32_t n_jobs)
+{ return intra_batch_impl(recon, pred, jobs, n_jobs, 0); }
+int port_intra_batch16(const svtb200_yuv_picture *recon, const svtb200_yuv_picture *pred, const svtb200_intra_job *jobs, uint32_t n_jobs)
+{ return intra_batch_impl(recon, pred, jobs, n_jobs, 1); }
 
 /* ---- open loop ---------------------------------------------------------------------------------------------------------- */
-static void open_loop_line(const svtb200_plane *src, int W, int H, int x, int y, int N, uint8_t *line)
+static void open_loop_line(const svtb200_plane *src, int W, int H, int x, int y, int N, uint16_t *line)
 {
     const uint8_t *o = src->buf + (size_t)(src->origin_y + y) * src->stride + src->origin_x + x;
-    memset(line, 128, (size_t)4 * N + 1);
+    for (int i = 0; i < 4 * N + 1; ++i) line[i] = 128;
     if (x != 0) {
         const int cnt = y + 2 * N > H ? H - y : 2 * N;
         for (int i = 0; i < cnt; ++i) line[2 * N - 1 - i] = o[(ptrdiff_t)i * (ptrdiff_t)src->stride - 1];
@@ -173,11 +191,11 @@ static void open_loop_line(const svtb200_plane *src, int W, int H, int x, int y,
     if (x != 0 && y != 0) line[2 * N] = o[-(ptrdiff_t)src->stride - 1];
     if (y != 0) {
         const int cnt = x + 2 * N > W ? W - x : 2 * N;
-        memcpy(line + 2 * N + 1, o - src->stride, (size_t)cnt);
+        for (int i = 0; i < cnt; ++i) line[2 * N + 1 + i] = o[(ptrdiff_t)i - (ptrdiff_t)src->stride];
     }
 }
 
-static uint32_t block_sad(const svtb200_plane *src, int x, int y, int N, const uint8_t *blk)
+static uint32_t block_sad(const svtb200_plane *src, int x, int y, int N, const uint16_t *blk)
 {
     const uint8_t *o = src->buf + (size_t)(src->origin_y + y) * src->stride + src->origin_x + x;
     uint32_t s = 0;
@@ -186,10 +204,10 @@ static uint32_t block_sad(const svtb200_plane *src, int x, int y, int N, const u
     return s;
 }
 
-static uint32_t mode_sad(const svtb200_plane *src, const uint8_t *line, int x, int y, int N, int mode)
+static uint32_t mode_sad(const svtb200_plane *src, const uint16_t *line, int x, int y, int N, int mode)
 {
-    uint8_t blk[32 * 32];
-    port_intra_predict((uint32_t)mode, (uint32_t)N, 0, line, blk, (uint32_t)N);
+    uint16_t blk[32 * 32];
+    predict_block(mode, N, 0, line, 255, blk);
     return block_sad(src, x, y, N, blk);
 }
 
@@ -231,7 +249,7 @@ int port_ois_picture(const svtb200_ois_config *cfg, const svtb200_plane *src, co
     if (cap < need) return -1;
     memset(total, 0, (size_t)cols * rows * 85);
     memset(cand, 0, (size_t)cols * rows * 85 * cap * sizeof(uint32_t));
-    uint8_t line[4 * 32 + 1];
+    uint16_t line[4 * 32 + 1];
     for (int lcu = 0; lcu < cols * rows; ++lcu) {
         const int ox = (lcu % cols) * 64, oy = (lcu / cols) * 64;
         uint32_t stage1[11] = { 0 };     /* stage1SadArray and bestMode live across the CUs of an LCU (:5069,5073) */

@@ -117,24 +117,37 @@ void port_inv_transform(const int16_t *coeff, uint32_t cs, int16_t *res, uint32_
 
 static const svtb200_plane *pl(const svtb200_yuv_picture *p, int k) { return k == 0 ? &p->y : k == 1 ? &p->cb : &p->cr; }
 
-int port_tq_batch(const svtb200_yuv_picture *src, const svtb200_yuv_picture *pred, const svtb200_yuv_picture *recon,
-                  const svtb200_coeff_picture *coeff, const svtb200_tq_job *jobs, int n_jobs, uint32_t *nz_counts)
+/* hbd: 16-bit sample planes of 10-bit video -- EncodeLoop16bit / EncodeGenerateRecon16bit (Codec/EbCodingLoop.c:1240,1640): EncodeTransform with
+ * BIT_INCREMENT_10BIT (Codec/EbTransforms.c:3343; two-stage rounding in its ONLY_DC branch :3425-3447), quantiser at bitDepth 10 with
+ * qp + QP_BD_OFFSET, inverse second shift 12 - 2, reconstruction clipped to 1023 (PictureAdditionKernel16bit). */
+static int tq_batch_impl(const svtb200_yuv_picture *src, const svtb200_yuv_picture *pred, const svtb200_yuv_picture *recon,
+                         const svtb200_coeff_picture *coeff, const svtb200_tq_job *jobs, int n_jobs, uint32_t *nz_counts, int hbd)
 {
+    const int bps = hbd ? 2 : 1, bit_inc = hbd ? 2 : 0, maxv = hbd ? 1023 : 255;
+#define LD(ptr, i) (hbd ? (int)((const uint16_t *)(ptr))[i] : (int)((const uint8_t *)(ptr))[i])
     static const uint32_t QF[6] = { 26214, 23302, 20560, 18396, 16384, 14564 }, FF[6] = { 40, 45, 51, 57, 64, 72 };   /* EbTransforms.h:26-27 */
     for (int j = 0; j < n_jobs; ++j) {
         const svtb200_tq_job *t = &jobs[j];
         const svtb200_plane *sp = pl(src, t->plane), *pp = pl(pred, t->plane), *rp = pl(recon, t->plane);
         const int N = t->size;
-        const uint8_t *s = sp->buf + (size_t)(sp->origin_y + t->y) * sp->stride + sp->origin_x + t->x;
-        const uint8_t *p = pp->buf + (size_t)(pp->origin_y + t->y) * pp->stride + pp->origin_x + t->x;
-        uint8_t *r = rp->buf + (size_t)(rp->origin_y + t->y) * rp->stride + rp->origin_x + t->x;
+        const uint8_t *s = sp->buf + ((size_t)(sp->origin_y + t->y) * sp->stride + sp->origin_x + t->x) * bps;
+        const uint8_t *p = pp->buf + ((size_t)(pp->origin_y + t->y) * pp->stride + pp->origin_x + t->x) * bps;
+        uint8_t *r = rp->buf + ((size_t)(rp->origin_y + t->y) * rp->stride + rp->origin_x + t->x) * bps;
         int16_t res[32 * 32], tr[32 * 32], q[32 * 32], rc[32 * 32];
         memset(tr, 0, sizeof tr); memset(q, 0, sizeof q); memset(rc, 0, sizeof rc);
-        for (int y = 0; y < N; ++y) for (int x = 0; x < N; ++x) res[y * N + x] = (int16_t)(s[(size_t)y * sp->stride + x] - p[(size_t)y * pp->stride + x]);
-        port_estimate_transform(res, (uint32_t)N, tr, (uint32_t)N, (uint32_t)N, 0, t->dst4x4, t->shape);
+        for (int y = 0; y < N; ++y) for (int x = 0; x < N; ++x) res[y * N + x] = (int16_t)(LD(s, (size_t)y * sp->stride + x) - LD(p, (size_t)y * pp->stride + x));
+        if (hbd && t->shape == SVTB200_SHAPE_ONLY_DC) {
+            int sum = 0;
+            for (int i = 0; i < N * N; ++i) sum += res[i];
+            const int lgn = ilog2((uint32_t)N), sh1 = lgn - 1 + bit_inc, sh2 = lgn + 6;
+            const int d1 = (64 * sum + (1 << (sh1 - 1))) >> sh1;
+            tr[0] = (int16_t)((64 * d1 + (1 << (sh2 - 1))) >> sh2);
+        } else
+            port_estimate_transform(res, (uint32_t)N, tr, (uint32_t)N, (uint32_t)N, (uint32_t)bit_inc, t->dst4x4, t->shape);
         /* UnifiedQuantizeInvQuantize parameter derivation, Codec/EbTransforms.c:3047-3060 / :3094-3110 */
-        const int qpRem = t->qp % 6, qpPer = t->qp / 6;
-        const int tshift = 15 - 8 - ilog2((uint32_t)N);
+        const int qp = t->qp + (hbd ? 12 : 0);     /* QP_BD_OFFSET */
+        const int qpRem = qp % 6, qpPer = qp / 6;
+        const int tshift = 15 - (hbd ? 10 : 8) - ilog2((uint32_t)N);
         const int shiftedQBits = 14 + qpPer + tshift;
         const uint32_t qoff = (uint32_t)((t->slice_type >= 2) ? 171 : 85) << (shiftedQBits - 9);
         const int shiftedFFunc = qpPer > 8 ? (int)FF[qpRem] << (qpPer - 2) : (int)FF[qpRem] << qpPer;
@@ -180,14 +193,23 @@ int port_tq_batch(const svtb200_yuv_picture *src, const svtb200_yuv_picture *pre
             /* PfZeroOutUselessQuadrants: everything outside the active corner is zero for the inverse */
             for (int y = 0; y < N; ++y) for (int x = 0; x < N; ++x) if (y >= act || x >= act) rc[y * N + x] = 0;
             int16_t rr[32 * 32];
-            port_inv_transform(rc, (uint32_t)N, rr, (uint32_t)N, (uint32_t)N, 0, t->dst4x4);
+            port_inv_transform(rc, (uint32_t)N, rr, (uint32_t)N, (uint32_t)N, (uint32_t)bit_inc, t->dst4x4);
             for (int y = 0; y < N; ++y) for (int x = 0; x < N; ++x) {
-                const int v = p[(size_t)y * pp->stride + x] + rr[y * N + x];
-                r[(size_t)y * rp->stride + x] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+                int v = LD(p, (size_t)y * pp->stride + x) + rr[y * N + x];
+                v = v < 0 ? 0 : v > maxv ? maxv : v;
+                if (hbd) ((uint16_t *)r)[(size_t)y * rp->stride + x] = (uint16_t)v; else r[(size_t)y * rp->stride + x] = (uint8_t)v;
             }
         } else if (r != p) {
-            for (int y = 0; y < N; ++y) memcpy(r + (size_t)y * rp->stride, p + (size_t)y * pp->stride, (size_t)N);
+            for (int y = 0; y < N; ++y) memcpy(r + (size_t)y * rp->stride * bps, p + (size_t)y * pp->stride * bps, (size_t)N * bps);
         }
     }
+#undef LD
     return 0;
 }
+
+int port_tq_batch(const svtb200_yuv_picture *src, const svtb200_yuv_picture *pred, const svtb200_yuv_picture *recon,
+                  const svtb200_coeff_picture *coeff, const svtb200_tq_job *jobs, int n_jobs, uint32_t *nz_counts)
+{ return tq_batch_impl(src, pred, recon, coeff, jobs, n_jobs, nz_counts, 0); }
+int port_tq_batch16(const svtb200_yuv_picture *src, const svtb200_yuv_picture *pred, const svtb200_yuv_picture *recon,
+                    const svtb200_coeff_picture *coeff, const svtb200_tq_job *jobs, int n_jobs, uint32_t *nz_counts)
+{ return tq_batch_impl(src, pred, recon, coeff, jobs, n_jobs, nz_counts, 1); }

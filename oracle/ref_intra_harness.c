@@ -134,6 +134,67 @@ int svtref_intra_batch(const svtb200_yuv_picture *recon, const svtb200_yuv_pictu
     return 0;
 }
 
+/* 16-bit samples (10-bit video): GenerateIntraReference16bitSamplesEncodePass :1688 + EncodePassIntraPrediction16bit :4676; planes hold EB_U16 */
+int svtref_intra_batch16(const svtb200_yuv_picture *recon, const svtb200_yuv_picture *pred, const svtb200_intra_job *jobs, uint32_t n_jobs, int asm_mode)
+{
+    ASM_TYPES = asm_mode ? EbHevcGetCpuAsmType() : 0;
+    NeighborArrayUnit_t *na[4];   /* mode type, luma, cb, cr */
+    for (int k = 0; k < 4; ++k) {
+        na[k] = (NeighborArrayUnit_t *)calloc(1, sizeof(NeighborArrayUnit_t));
+        const EB_U32 w = k >= 2 ? MAX_PICTURE_WIDTH_SIZE >> 1 : MAX_PICTURE_WIDTH_SIZE, h = k >= 2 ? MAX_PICTURE_HEIGHT_SIZE >> 1 : MAX_PICTURE_HEIGHT_SIZE;
+        const EB_U32 gran = k == 0 ? PU_NEIGHBOR_ARRAY_GRANULARITY : SAMPLE_NEIGHBOR_ARRAY_GRANULARITY;
+        if (NeighborArrayUnitCtor(na[k], w, h, k == 0 ? sizeof(EB_U8) : sizeof(EB_U16), gran, gran, NEIGHBOR_ARRAY_UNIT_FULL_MASK) != EB_ErrorNone) return -1;
+    }
+    IntraReference16bitSamples_t *r = (IntraReference16bitSamples_t *)calloc(1, sizeof(*r));
+    if (IntraReference16bitSamplesCtor(r, EB_YUV420) != EB_ErrorNone) return -1;
+    EbPictureBufferDesc_t pd;
+    yuv_desc(&pd, pred);
+    pd.bitDepth = EB_16BIT;
+    const uint16_t *ry = (const uint16_t *)recon->y.buf + (size_t)recon->y.origin_y * recon->y.stride + recon->y.origin_x;
+    const uint16_t *rcb = (const uint16_t *)recon->cb.buf + (size_t)recon->cb.origin_y * recon->cb.stride + recon->cb.origin_x;
+    const uint16_t *rcr = (const uint16_t *)recon->cr.buf + (size_t)recon->cr.origin_y * recon->cr.stride + recon->cr.origin_x;
+    /* scratch copies: prediction may be in place, and each job must see the neighbours as they are before it */
+    for (uint32_t j = 0; j < n_jobs; ++j) {
+        const svtb200_intra_job *t = &jobs[j];
+        const int x = t->x, y = t->y, N = t->size;
+        NeighborArrayUnitReset(na[0]);
+        for (int i = 0; i < 2 * N; ++i) {
+            ((EB_U16 *)na[1]->topArray)[x + i] = ry[(ptrdiff_t)(y - 1) * (ptrdiff_t)recon->y.stride + x + i];
+            ((EB_U16 *)na[1]->leftArray)[y + i] = ry[(ptrdiff_t)(y + i) * (ptrdiff_t)recon->y.stride + x - 1];
+        }
+        ((EB_U16 *)na[1]->topLeftArray)[MAX_PICTURE_HEIGHT_SIZE + x - y] = ry[(ptrdiff_t)(y - 1) * (ptrdiff_t)recon->y.stride + x - 1];
+        const int xc = x >> 1, yc = y >> 1;
+        for (int i = 0; i < N; ++i) {
+            ((EB_U16 *)na[2]->topArray)[xc + i] = rcb[(ptrdiff_t)(yc - 1) * (ptrdiff_t)recon->cb.stride + xc + i];
+            ((EB_U16 *)na[2]->leftArray)[yc + i] = rcb[(ptrdiff_t)(yc + i) * (ptrdiff_t)recon->cb.stride + xc - 1];
+            ((EB_U16 *)na[3]->topArray)[xc + i] = rcr[(ptrdiff_t)(yc - 1) * (ptrdiff_t)recon->cr.stride + xc + i];
+            ((EB_U16 *)na[3]->leftArray)[yc + i] = rcr[(ptrdiff_t)(yc + i) * (ptrdiff_t)recon->cr.stride + xc - 1];
+        }
+        ((EB_U16 *)na[2]->topLeftArray)[((MAX_PICTURE_HEIGHT_SIZE - y) >> 1) + xc] = rcb[(ptrdiff_t)(yc - 1) * (ptrdiff_t)recon->cb.stride + xc - 1];
+        ((EB_U16 *)na[3]->topLeftArray)[((MAX_PICTURE_HEIGHT_SIZE - y) >> 1) + xc] = rcr[(ptrdiff_t)(yc - 1) * (ptrdiff_t)recon->cr.stride + xc - 1];
+        const int nu = 2 * N / 4;
+        for (int u = 0; u < nu; ++u) {
+            if ((t->left_avail >> u) & 1) na[0]->leftArray[(y + 2 * N - 4 - 4 * u) >> 2] = INTRA_MODE;
+            if ((t->top_avail >> u) & 1) na[0]->topArray[(x + 4 * u) >> 2] = INTRA_MODE;
+        }
+        if (t->flags & SVTB200_INTRA_TOPLEFT_AVAIL) na[0]->topLeftArray[GetNeighborArrayUnitTopLeftIndex(na[0], x, y)] = INTRA_MODE;
+        EB_U32 depth = 0;
+        while ((64u >> depth) > (EB_U32)N) ++depth;
+        GenerateIntraReference16bitSamplesEncodePass(EB_FALSE, (t->flags & SVTB200_INTRA_STRONG_SMOOTHING) ? EB_TRUE : EB_FALSE, (EB_U32)x, (EB_U32)y, (EB_U32)N, 64, depth,
+                                                na[0], na[1], na[2], na[3], r, EB_YUV420, EB_FALSE, EB_FALSE, EB_FALSE);
+        EB_U32 mask = 0;
+        if (t->luma_mode != SVTB200_INTRA_SKIP) mask |= PICTURE_BUFFER_DESC_LUMA_MASK;
+        if (t->chroma_mode != SVTB200_INTRA_SKIP) mask |= PICTURE_BUFFER_DESC_CHROMA_MASK;
+        EncodePassIntraPrediction16bit(r, (EB_U32)x + pd.originX, (EB_U32)y + pd.originY, (EB_U32)N, (EB_U32)N >> 1, &pd, EB_YUV420, EB_FALSE,
+                                  t->luma_mode == SVTB200_INTRA_SKIP ? 0 : t->luma_mode, t->chroma_mode == SVTB200_INTRA_SKIP ? EB_INTRA_CHROMA_DM : t->chroma_mode, mask);
+    }
+    if (r->dctor) r->dctor(r);
+    free(r);
+    for (int k = 0; k < 4; ++k) { if (na[k]->dctor) na[k]->dctor(na[k]); free(na[k]); }
+    return 0;
+}
+
+
 int svtref_ois_picture(const svtb200_ois_config *cfg, const svtb200_plane *src, const svtb200_me_pu_result *me_results, uint8_t *total, uint32_t *cand,
                        uint32_t cap, int asm_mode)
 {

@@ -33,7 +33,7 @@ struct DlfArgs {
 __device__ __forceinline__ int clampi(int lo, int hi, int v) { return min(max(v, lo), hi); }
 
 // s[r][k]: r = position along the edge (0..3), k = 0..7 = p3,p2,p1,p0,q0,q1,q2,q3.  Returns false when nothing changes.
-__device__ __forceinline__ bool luma_edge(int (&s)[4][8], int tc, int beta)
+__device__ __forceinline__ bool luma_edge(int (&s)[4][8], int tc, int beta, int maxv = 255)
 {
     const int dp0 = abs(s[0][1] - 2 * s[0][2] + s[0][3]), dp3 = abs(s[3][1] - 2 * s[3][2] + s[3][3]);
     const int dq0 = abs(s[0][6] - 2 * s[0][5] + s[0][4]), dq3 = abs(s[3][6] - 2 * s[3][5] + s[3][4]);
@@ -57,21 +57,21 @@ __device__ __forceinline__ bool luma_edge(int (&s)[4][8], int tc, int beta)
             int delta = ((q0 - p0) * 9 - (q1 - p1) * 3 + 8) >> 4;
             if (abs(delta) < tc * 10) {
                 delta = clampi(-tc, tc, delta);
-                s[r][4] = clampi(0, 255, q0 - delta);
-                s[r][3] = clampi(0, 255, p0 + delta);
-                if (side > dp) s[r][2] = clampi(0, 255, p1 + clampi(-tc2, tc2, (((p0 + p2 + 1) >> 1) - p1 + delta) >> 1));
-                if (side > dq) s[r][5] = clampi(0, 255, q1 + clampi(-tc2, tc2, (((q0 + q2 + 1) >> 1) - q1 - delta) >> 1));
+                s[r][4] = clampi(0, maxv, q0 - delta);
+                s[r][3] = clampi(0, maxv, p0 + delta);
+                if (side > dp) s[r][2] = clampi(0, maxv, p1 + clampi(-tc2, tc2, (((p0 + p2 + 1) >> 1) - p1 + delta) >> 1));
+                if (side > dq) s[r][5] = clampi(0, maxv, q1 + clampi(-tc2, tc2, (((q0 + q2 + 1) >> 1) - q1 - delta) >> 1));
             }
         }
     }
     return true;
 }
 
-__device__ __forceinline__ void chroma_edge(int &p1, int &p0, int &q0, int &q1, int tc)
+__device__ __forceinline__ void chroma_edge(int &p1, int &p0, int &q0, int &q1, int tc, int maxv = 255)
 {
     const int delta = clampi(-tc, tc, (((q0 - p0) << 2) + p1 - q1 + 4) >> 3);
-    p0 = clampi(0, 255, p0 + delta);
-    q0 = clampi(0, 255, q0 - delta);
+    p0 = clampi(0, maxv, p0 + delta);
+    q0 = clampi(0, maxv, q0 - delta);
 }
 
 __device__ __forceinline__ int bs_at(const DlfArgs &A, const uint8_t *arr, int x, int y)
@@ -82,7 +82,9 @@ __device__ __forceinline__ int qp_at(const DlfArgs &A, int x, int y) { return A.
 __device__ __forceinline__ int chroma_qp(int q) { return q < 0 ? q : (q > 57 ? q - 6 : c_cqp[q]); }
 
 // PASS 0: vertical edges, PASS 1: horizontal edges
-template <int PASS>
+// HBD: 16-bit sample planes (10-bit video): LCU*DLFCore16bit (Codec/EbDeblockingFilter.c:2514,3174,3922), Luma4SampleEdgeDLFCore16bit /
+// Chroma2SampleEdgeDLFCore16bit (C_DEFAULT/EbDeblockingFilter_C.c:240,524): tc and beta scaled by 4 (:1254-1255), samples clipped to 1023
+template <int PASS, bool HBD>
 __global__ void __launch_bounds__(256) dlf_pass_kernel(const __grid_constant__ DlfArgs A)
 {
     const int W = A.W, H = A.H;
@@ -97,8 +99,23 @@ __global__ void __launch_bounds__(256) dlf_pass_kernel(const __grid_constant__ D
         const int bs = bs_at(A, PASS == 0 ? A.vbs : A.hbs, x, y);
         if (!bs) return;
         const int q = (qp_at(A, x, y) + (PASS == 0 ? qp_at(A, x - 1, y) : qp_at(A, x, y - 1)) + 1) >> 1;
-        const int tc = c_tc[clampi(0, 53, q + ((bs > 1) << 1) + A.tc_off)], beta = c_beta[clampi(0, 51, q + A.beta_off)];
+        const int tc = c_tc[clampi(0, 53, q + ((bs > 1) << 1) + A.tc_off)] << (HBD ? 2 : 0), beta = c_beta[clampi(0, 51, q + A.beta_off)] << (HBD ? 2 : 0);
         int s[4][8];
+        if (HBD) {
+            uint16_t *Y = (uint16_t *)A.y;
+            const ptrdiff_t fs = PASS == 0 ? 1 : A.ys, rs = PASS == 0 ? A.ys : 1;     // across / along the edge
+            uint16_t *e = Y + (ptrdiff_t)y * A.ys + x;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s[r][k] = e[(k - 4) * fs + r * rs];
+            if (!luma_edge(s, tc, beta, 1023)) return;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int k = 1; k < 7; ++k) e[(k - 4) * fs + r * rs] = (uint16_t)s[r][k];
+            return;
+        }
         if (PASS == 0) {
             uint32_t *row = (uint32_t *)(A.y + (size_t)y * A.ys + x - 4);
             const int rs = A.ys >> 2;
@@ -137,9 +154,20 @@ __global__ void __launch_bounds__(256) dlf_pass_kernel(const __grid_constant__ D
     const int lx = 2 * cx, ly = 2 * cy;
     if (bs_at(A, PASS == 0 ? A.vbs : A.hbs, lx, ly) <= 1) return;
     const int q = (qp_at(A, lx, ly) + (PASS == 0 ? qp_at(A, lx - 2, ly) : qp_at(A, lx, ly - 2)) + 1) >> 1;
-    const int tcv[2] = {c_tc[clampi(0, 53, chroma_qp(q + A.cb_off) + 2 + A.tc_off)], c_tc[clampi(0, 53, chroma_qp(q + A.cr_off) + 2 + A.tc_off)]};
+    const int tcv[2] = {c_tc[clampi(0, 53, chroma_qp(q + A.cb_off) + 2 + A.tc_off)] << (HBD ? 2 : 0), c_tc[clampi(0, 53, chroma_qp(q + A.cr_off) + 2 + A.tc_off)] << (HBD ? 2 : 0)};
 #pragma unroll
     for (int pl = 0; pl < 2; ++pl) {
+        if (HBD) {
+            uint16_t *e = (uint16_t *)(pl == 0 ? A.cb : A.cr) + (ptrdiff_t)cy * A.cs + cx;
+            const ptrdiff_t fs = PASS == 0 ? 1 : A.cs, rs = PASS == 0 ? A.cs : 1;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                int p1 = e[-2 * fs + r * rs], p0 = e[-fs + r * rs], q0 = e[r * rs], q1 = e[fs + r * rs];
+                chroma_edge(p1, p0, q0, q1, tcv[pl], 1023);
+                e[-fs + r * rs] = (uint16_t)p0; e[r * rs] = (uint16_t)q0;
+            }
+            continue;
+        }
         uint8_t *base = (pl == 0 ? A.cb : A.cr) + (size_t)cy * A.cs + cx;
         if (PASS == 0) {
 #pragma unroll
@@ -183,13 +211,13 @@ __global__ void dlf_leaf_chroma_kernel(uint8_t *blk /* [plane][4 across][2 along
         }
 }
 
-static int dlf_launch(const DlfArgs &A, cudaStream_t st)
+static int dlf_launch(const DlfArgs &A, cudaStream_t st, bool hbd = false)
 {
     const int W = A.W, H = A.H;
     const int ncv = (W / 2 + 7) / 8 - 1, nch = (H / 2 + 7) / 8 - 1;
     const int n0 = (W / 8 - 1) * (H / 4) + ncv * (H / 4), n1 = (W / 4) * (H / 8 - 1) + (W / 4) * nch;
-    if (n0 > 0) { dlf_pass_kernel<0><<<(n0 + 255) / 256, 256, 0, st>>>(A); SVTB200_COUNT_LAUNCH(); }
-    if (n1 > 0) { dlf_pass_kernel<1><<<(n1 + 255) / 256, 256, 0, st>>>(A); SVTB200_COUNT_LAUNCH(); }
+    if (n0 > 0) { if (hbd) dlf_pass_kernel<0, true><<<(n0 + 255) / 256, 256, 0, st>>>(A); else dlf_pass_kernel<0, false><<<(n0 + 255) / 256, 256, 0, st>>>(A); SVTB200_COUNT_LAUNCH(); }
+    if (n1 > 0) { if (hbd) dlf_pass_kernel<1, true><<<(n1 + 255) / 256, 256, 0, st>>>(A); else dlf_pass_kernel<1, false><<<(n1 + 255) / 256, 256, 0, st>>>(A); SVTB200_COUNT_LAUNCH(); }
     SVTB200_CUDA_TRY(cudaGetLastError());
     return SVTB200_OK;
 }
@@ -206,12 +234,12 @@ static int dlf_check(const svtb200_yuv_picture *rec, const svtb200_dlf_params *p
 }
 
 static DlfArgs dlf_args(const svtb200_yuv_picture &rec, uint8_t *y, uint8_t *cb, uint8_t *cr, const uint8_t *vbs, const uint8_t *hbs, const uint8_t *qp,
-                        const svtb200_dlf_params &p)
+                        const svtb200_dlf_params &p, size_t bps = 1)
 {
     DlfArgs A;
-    A.y = y + (size_t)rec.y.origin_y * rec.y.stride + rec.y.origin_x;
-    A.cb = cb + (size_t)rec.cb.origin_y * rec.cb.stride + rec.cb.origin_x;
-    A.cr = cr + (size_t)rec.cr.origin_y * rec.cr.stride + rec.cr.origin_x;
+    A.y = y + ((size_t)rec.y.origin_y * rec.y.stride + rec.y.origin_x) * bps;
+    A.cb = cb + ((size_t)rec.cb.origin_y * rec.cb.stride + rec.cb.origin_x) * bps;
+    A.cr = cr + ((size_t)rec.cr.origin_y * rec.cr.stride + rec.cr.origin_x) * bps;
     A.ys = (int)rec.y.stride; A.cs = (int)rec.cb.stride;
     A.vbs = vbs; A.hbs = hbs; A.qp = qp;
     A.W = p.pic_width; A.H = p.pic_height; A.cols = (p.pic_width + 63) / 64; A.qs = p.qp_array_stride;
@@ -226,20 +254,21 @@ using namespace svtb200;
 
 extern "C" {
 
-int svtb200_dlf_picture_dev(const svtb200_yuv_picture *recon, const uint8_t *vertical_bs, const uint8_t *horizontal_bs, const uint8_t *qp_array,
-                            const svtb200_dlf_params *prm, void *cuda_stream)
+static int dlf_picture_dev_impl(const svtb200_yuv_picture *recon, const uint8_t *vertical_bs, const uint8_t *horizontal_bs, const uint8_t *qp_array,
+                                const svtb200_dlf_params *prm, void *cuda_stream, bool hbd)
 {
     int rc = dlf_check(recon, prm);
     if (rc) return rc;
     if (!vertical_bs || !horizontal_bs || !qp_array) { set_error("dlf_picture_dev: null array"); return SVTB200_ERR_BAD_ARG; }
     if (((uintptr_t)recon->y.buf & 3) || ((uintptr_t)recon->cb.buf & 1) || ((uintptr_t)recon->cr.buf & 1)) { set_error("dlf_picture_dev: planes must be 4-byte (luma) / 2-byte (chroma) aligned"); return SVTB200_ERR_BAD_ARG; }
     if ((rc = ensure_device())) return rc;
-    return dlf_launch(dlf_args(*recon, recon->y.buf, recon->cb.buf, recon->cr.buf, vertical_bs, horizontal_bs, qp_array, *prm), (cudaStream_t)cuda_stream);
+    return dlf_launch(dlf_args(*recon, recon->y.buf, recon->cb.buf, recon->cr.buf, vertical_bs, horizontal_bs, qp_array, *prm, hbd ? 2 : 1), (cudaStream_t)cuda_stream, hbd);
 }
 
-int svtb200_dlf_picture(const svtb200_yuv_picture *recon, const uint8_t *vertical_bs, const uint8_t *horizontal_bs, const uint8_t *qp_array,
-                        const svtb200_dlf_params *prm)
+static int dlf_picture_impl(const svtb200_yuv_picture *recon, const uint8_t *vertical_bs, const uint8_t *horizontal_bs, const uint8_t *qp_array,
+                            const svtb200_dlf_params *prm, bool hbd)
 {
+    const size_t bps = hbd ? 2 : 1;
     int rc = dlf_check(recon, prm);
     if (rc) return rc;
     if (!vertical_bs || !horizontal_bs || !qp_array) { set_error("dlf_picture: null array"); return SVTB200_ERR_BAD_ARG; }
@@ -250,22 +279,33 @@ int svtb200_dlf_picture(const svtb200_yuv_picture *recon, const uint8_t *vertica
     const size_t bs_bytes = n_lcu * 256, qp_bytes = (size_t)prm->qp_array_stride * ((prm->pic_height + 7) / 8);
     const svtb200_plane *pl[3] = {&recon->y, &recon->cb, &recon->cr};
     size_t need = 8192 + 2 * align_up(bs_bytes, 256) + align_up(qp_bytes, 256);
-    for (int k = 0; k < 3; ++k) need += align_up(pbytes(*pl[k]), 256);
+    for (int k = 0; k < 3; ++k) need += align_up(bps * pbytes(*pl[k]), 256);
     if ((rc = c->dev_reserve(need))) return rc;
     void *d[3], *d_v, *d_h, *d_q;
     for (int k = 0; k < 3; ++k) {
-        if ((rc = c->dev_alloc(pbytes(*pl[k]), &d[k]))) return rc;
-        SVTB200_CUDA_TRY(cudaMemcpyAsync(d[k], pl[k]->buf, pbytes(*pl[k]), cudaMemcpyHostToDevice, c->stream));
+        if ((rc = c->dev_alloc(bps * pbytes(*pl[k]), &d[k]))) return rc;
+        SVTB200_CUDA_TRY(cudaMemcpyAsync(d[k], pl[k]->buf, bps * pbytes(*pl[k]), cudaMemcpyHostToDevice, c->stream));
     }
     if ((rc = c->dev_alloc(bs_bytes, &d_v)) || (rc = c->dev_alloc(bs_bytes, &d_h)) || (rc = c->dev_alloc(qp_bytes, &d_q))) return rc;
     SVTB200_CUDA_TRY(cudaMemcpyAsync(d_v, vertical_bs, bs_bytes, cudaMemcpyHostToDevice, c->stream));
     SVTB200_CUDA_TRY(cudaMemcpyAsync(d_h, horizontal_bs, bs_bytes, cudaMemcpyHostToDevice, c->stream));
     SVTB200_CUDA_TRY(cudaMemcpyAsync(d_q, qp_array, qp_bytes, cudaMemcpyHostToDevice, c->stream));
-    if ((rc = dlf_launch(dlf_args(*recon, (uint8_t *)d[0], (uint8_t *)d[1], (uint8_t *)d[2], (const uint8_t *)d_v, (const uint8_t *)d_h, (const uint8_t *)d_q, *prm), c->stream))) return rc;
-    for (int k = 0; k < 3; ++k) SVTB200_CUDA_TRY(cudaMemcpyAsync(pl[k]->buf, d[k], pbytes(*pl[k]), cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = dlf_launch(dlf_args(*recon, (uint8_t *)d[0], (uint8_t *)d[1], (uint8_t *)d[2], (const uint8_t *)d_v, (const uint8_t *)d_h, (const uint8_t *)d_q, *prm, bps), c->stream, hbd))) return rc;
+    for (int k = 0; k < 3; ++k) SVTB200_CUDA_TRY(cudaMemcpyAsync(pl[k]->buf, d[k], bps * pbytes(*pl[k]), cudaMemcpyDeviceToHost, c->stream));
     SVTB200_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return SVTB200_OK;
 }
+
+int svtb200_dlf_picture_dev(const svtb200_yuv_picture *recon, const uint8_t *vertical_bs, const uint8_t *horizontal_bs, const uint8_t *qp_array,
+                            const svtb200_dlf_params *prm, void *cuda_stream)
+{ return dlf_picture_dev_impl(recon, vertical_bs, horizontal_bs, qp_array, prm, cuda_stream, false); }
+int svtb200_dlf_picture(const svtb200_yuv_picture *recon, const uint8_t *vertical_bs, const uint8_t *horizontal_bs, const uint8_t *qp_array, const svtb200_dlf_params *prm)
+{ return dlf_picture_impl(recon, vertical_bs, horizontal_bs, qp_array, prm, false); }
+int svtb200_dlf_picture16_dev(const svtb200_yuv_picture *recon, const uint8_t *vertical_bs, const uint8_t *horizontal_bs, const uint8_t *qp_array,
+                              const svtb200_dlf_params *prm, void *cuda_stream)
+{ return dlf_picture_dev_impl(recon, vertical_bs, horizontal_bs, qp_array, prm, cuda_stream, true); }
+int svtb200_dlf_picture16(const svtb200_yuv_picture *recon, const uint8_t *vertical_bs, const uint8_t *horizontal_bs, const uint8_t *qp_array, const svtb200_dlf_params *prm)
+{ return dlf_picture_impl(recon, vertical_bs, horizontal_bs, qp_array, prm, true); }
 
 int svtb200_Luma4SampleEdgeDLFCore(uint8_t *e, uint32_t stride, uint8_t isVerticalEdge, int32_t tc, int32_t beta)
 {

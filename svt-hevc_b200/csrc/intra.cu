@@ -19,6 +19,8 @@
 //                shared counter, build the CU's line once and run all its modes with VABSDIFF4 SADs against the staged source; the
 //                reference's candidate injection / sorting then runs on the SAD table.  Neighbours come from the source picture,
 //                so all LCUs of a picture are independent.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace svtb200 {
@@ -30,12 +32,13 @@ __constant__ int8_t c_filt_thr[4] = {35, 7, 1, 0};                              
 struct ModeSetup {
     int mode, N, lg;
     bool edge, vertical;
-    int ang, inv, dc;
+    int ang, inv, dc, maxv;
 };
 
-__device__ __forceinline__ ModeSetup mode_setup(int mode, int N, bool luma, int dc)
+__device__ __forceinline__ ModeSetup mode_setup(int mode, int N, bool luma, int dc, int maxv = 255)
 {
     ModeSetup m;
+    m.maxv = maxv;
     m.mode = mode; m.N = N; m.lg = 31 - __clz(N);
     m.edge = luma && N < 32;
     m.vertical = mode >= 18;
@@ -47,17 +50,19 @@ __device__ __forceinline__ ModeSetup mode_setup(int mode, int N, bool luma, int 
 }
 
 // sample k of the main reference: 0 = top-left, > 0 the main side, < 0 projected from the other side
-__device__ __forceinline__ int main_ref(const uint8_t *tl, bool vertical, int k, int inv)
+template <typename LT>
+__device__ __forceinline__ int main_ref(const LT *tl, bool vertical, int k, int inv)
 {
     if (k >= 0) return vertical ? tl[k] : tl[-k];
     const int j = (128 - k * inv) >> 8;
     return vertical ? tl[-j] : tl[j];
 }
 
-__device__ __forceinline__ int intra_pel(const uint8_t *line, const ModeSetup &m, int x, int y)
+template <typename LT>
+__device__ __forceinline__ int intra_pel(const LT *line, const ModeSetup &m, int x, int y)
 {
     const int N = m.N;
-    const uint8_t *tl = line + 2 * N;
+    const LT *tl = line + 2 * N;
     if (m.mode == 0)
         return ((N - 1 - x) * (int)tl[-1 - y] + (x + 1) * (int)tl[1 + N] + (N - 1 - y) * (int)tl[1 + x] + (y + 1) * (int)tl[-1 - N] + N) >> (m.lg + 1);
     if (m.mode == 1) {
@@ -68,8 +73,8 @@ __device__ __forceinline__ int intra_pel(const uint8_t *line, const ModeSetup &m
         }
         return m.dc;
     }
-    if (m.mode == 26) { const int t = tl[1 + x]; return (m.edge && x == 0) ? min(max(t + (((int)tl[-1 - y] - (int)tl[0]) >> 1), 0), 255) : t; }
-    if (m.mode == 10) { const int l = tl[-1 - y]; return (m.edge && y == 0) ? min(max(l + (((int)tl[1 + x] - (int)tl[0]) >> 1), 0), 255) : l; }
+    if (m.mode == 26) { const int t = tl[1 + x]; return (m.edge && x == 0) ? min(max(t + (((int)tl[-1 - y] - (int)tl[0]) >> 1), 0), m.maxv) : t; }
+    if (m.mode == 10) { const int l = tl[-1 - y]; return (m.edge && y == 0) ? min(max(l + (((int)tl[1 + x] - (int)tl[0]) >> 1), 0), m.maxv) : l; }
     const int along = m.vertical ? x : y, across = m.vertical ? y : x;
     const int delta = (across + 1) * m.ang, di = delta >> 5, df = delta & 31;
     const int a = main_ref(tl, m.vertical, along + di + 1, m.inv);
@@ -87,13 +92,14 @@ __device__ __forceinline__ uint32_t intra_pel4(const uint8_t *line, const ModeSe
 }
 
 // DC value of a line, computed by one full warp
-__device__ __forceinline__ int warp_dc(const uint8_t *line, int N)
+template <typename LT>
+__device__ __forceinline__ int warp_dc(const LT *line, int N)
 {
     const int lane = threadIdx.x & 31;
     uint32_t s = 0;
     for (int i = lane; i < 2 * N; i += 32) s += (i < N) ? line[2 * N + 1 + i] : line[2 * N - 1 - (i - N)];
     s = warp_sum(s);
-    return (int)(uint8_t)((s + N) >> (32 - __clz(N)));     // log2(2N) = lg + 1
+    return (int)((s + N) >> (32 - __clz(N)));     // log2(2N) = lg + 1
 }
 
 // ---- leaf -------------------------------------------------------------------------------------------------------------------
@@ -121,18 +127,20 @@ struct IntraArgs {
 
 // Reference line of one block from a reconstructed plane.  unit = samples per availability bit (4 luma, 2 chroma).
 // Scan order of the units: left column bottom-up (nu units), top-left (1), top row left to right (nu units).
-__device__ void build_line(uint8_t *line, const PlaneW &pl, int x, int y, int N, int unit, uint32_t left_avail, uint32_t top_avail, bool tl_avail)
+template <bool HBD>
+__device__ void build_line(typename std::conditional<HBD, uint16_t, uint8_t>::type *line, const PlaneW &pl, int x, int y, int N, int unit, uint32_t left_avail, uint32_t top_avail, bool tl_avail)
 {
+    using PIX = typename std::conditional<HBD, uint16_t, uint8_t>::type;
     const int nu = 2 * N / unit, lgu = unit == 4 ? 2 : 1;
     const uint64_t M = (uint64_t)(left_avail & ((1u << nu) - 1)) | ((uint64_t)(tl_avail ? 1 : 0) << nu) | ((uint64_t)(top_avail & ((1u << nu) - 1)) << (nu + 1));
-    const uint8_t *o = pl.p + (ptrdiff_t)y * pl.stride + x;
+    const PIX *o = (const PIX *)pl.p + (ptrdiff_t)y * pl.stride + x;
     for (int i = threadIdx.x; i < 4 * N + 1; i += IN_NT) {
         // this sample's unit and its position inside the unit (both in scan order)
         int u, k;
         if (i < 2 * N) { u = i >> lgu; k = i & (unit - 1); }
         else if (i == 2 * N) { u = nu; k = 0; }
         else { u = nu + 1 + ((i - 2 * N - 1) >> lgu); k = (i - 2 * N - 1) & (unit - 1); }
-        int v = 128;
+        int v = HBD ? 512 : 128;
         if (M) {
             const uint64_t below = M & ((2ull << u) - 1);
             int su, sk;                                   // source unit / sample within it
@@ -144,23 +152,31 @@ __device__ void build_line(uint8_t *line, const PlaneW &pl, int x, int y, int N,
             else off = -(ptrdiff_t)pl.stride + (su - nu - 1) * unit + sk;
             v = o[off];
         }
-        line[i] = (uint8_t)v;
+        line[i] = (PIX)v;
     }
 }
 
 // [1 2 1] smoothing, or the bilinear "strong" smoothing of 32x32 blocks (GenerateIntraReferenceSamplesEncodePass part 3)
-__device__ void filter_line(const uint8_t *in, uint8_t *out, int N, bool strong_enabled)
+template <typename LT>
+__device__ void filter_line(const LT *in, LT *out, int N, bool strong_enabled, int thr)
 {
     const int bl = in[0], tl = in[2 * N], tr = in[4 * N];
-    const bool strong = strong_enabled && N >= 32 && abs(bl + tl - 2 * (int)in[N]) < 8 && abs(tl + tr - 2 * (int)in[3 * N]) < 8;
+    const bool strong = strong_enabled && N >= 32 && abs(bl + tl - 2 * (int)in[N]) < thr && abs(tl + tr - 2 * (int)in[3 * N]) < thr;
     const int sh = 32 - __clz(N);
     for (int i = threadIdx.x; i < 4 * N + 1; i += IN_NT) {
         int v;
         if (i == 0 || i == 4 * N || (strong && i == 2 * N)) v = in[i];
         else if (strong) v = i < 2 * N ? ((2 * N - i) * bl + i * tl + N) >> sh : ((4 * N - i) * tl + (i - 2 * N) * tr + N) >> sh;
         else v = ((int)in[i - 1] + 2 * (int)in[i] + (int)in[i + 1] + 2) >> 2;
-        out[i] = (uint8_t)v;
+        out[i] = (LT)v;
     }
+}
+
+__device__ void predict_block16(const uint16_t *line, const ModeSetup &m, const PlaneW &dst, int x, int y)
+{
+    const int N = m.N;
+    uint16_t *d = (uint16_t *)dst.p + (ptrdiff_t)y * dst.stride + x;
+    for (int i = threadIdx.x; i < N * N; i += IN_NT) { const int r = i / N, c = i - r * N; d[(ptrdiff_t)r * dst.stride + c] = (uint16_t)intra_pel(line, m, c, r); }
 }
 
 __device__ void predict_block(const uint8_t *line, const ModeSetup &m, const PlaneW &dst, int x, int y)
@@ -178,37 +194,48 @@ __device__ void predict_block(const uint8_t *line, const ModeSetup &m, const Pla
     }
 }
 
+template <bool HBD>
 __global__ void __launch_bounds__(IN_NT) intra_batch_kernel(const __grid_constant__ IntraArgs A)
 {
-    __shared__ uint8_t s_line[3][4 * 32 + 4], s_filt[4 * 32 + 4];
+    using LT = typename std::conditional<HBD, uint16_t, uint8_t>::type;
+    constexpr int MAXV = HBD ? 1023 : 255, THR = HBD ? 32 : 8;      // SMOOTHING_THRESHOLD[_10BIT], Codec/EbIntraPrediction.h:119-120
+    __shared__ __align__(4) LT s_line[3][4 * 32 + 4], s_filt[4 * 32 + 4];
     __shared__ int s_dc[3];
     const svtb200_intra_job t = A.jobs[blockIdx.x];
     const bool do_luma = t.luma_mode != SVTB200_INTRA_SKIP, do_chroma = t.chroma_mode != SVTB200_INTRA_SKIP;
     const bool tl = t.flags & SVTB200_INTRA_TOPLEFT_AVAIL;
     const int N = t.size, Nc = N >> 1;
     // all neighbour reads first (the prediction may be written in place)
-    if (do_luma) build_line(s_line[0], A.recon[0], t.x, t.y, N, 4, t.left_avail, t.top_avail, tl);
+    if (do_luma) build_line<HBD>(s_line[0], A.recon[0], t.x, t.y, N, 4, t.left_avail, t.top_avail, tl);
     if (do_chroma) {
-        build_line(s_line[1], A.recon[1], t.x >> 1, t.y >> 1, Nc, 2, t.left_avail, t.top_avail, tl);
-        build_line(s_line[2], A.recon[2], t.x >> 1, t.y >> 1, Nc, 2, t.left_avail, t.top_avail, tl);
+        build_line<HBD>(s_line[1], A.recon[1], t.x >> 1, t.y >> 1, Nc, 2, t.left_avail, t.top_avail, tl);
+        build_line<HBD>(s_line[2], A.recon[2], t.x >> 1, t.y >> 1, Nc, 2, t.left_avail, t.top_avail, tl);
     }
     __syncthreads();
     const int lmode = t.luma_mode;
     int cmode = lmode;
     switch (t.chroma_mode) { case 0: cmode = 0; break; case 1: cmode = 26; break; case 2: cmode = 10; break; case 3: cmode = 1; break; default: break; }
-    const uint8_t *luma_line = s_line[0];
+    const LT *luma_line = s_line[0];
     if (do_luma) {
         const int dmin = min(abs(lmode - 10), abs(lmode - 26));
-        if (dmin > c_filt_thr[31 - __clz(N) - 2] && lmode != 1) { filter_line(s_line[0], s_filt, N, t.flags & SVTB200_INTRA_STRONG_SMOOTHING); luma_line = s_filt; }
+        if (dmin > c_filt_thr[31 - __clz(N) - 2] && lmode != 1) { filter_line<LT>(s_line[0], s_filt, N, t.flags & SVTB200_INTRA_STRONG_SMOOTHING, THR); luma_line = s_filt; }
     }
     const int w = threadIdx.x >> 5;
     if (w == 0 && do_luma && lmode == 1) { const int dc = warp_dc(s_line[0], N); if ((threadIdx.x & 31) == 0) s_dc[0] = dc; }
     if ((w == 1 || w == 2) && do_chroma && cmode == 1) { const int dc = warp_dc(s_line[w], Nc); if ((threadIdx.x & 31) == 0) s_dc[w] = dc; }
     __syncthreads();
-    if (do_luma) predict_block(luma_line, mode_setup(lmode, N, true, s_dc[0]), A.pred[0], t.x, t.y);
-    if (do_chroma) {
-        predict_block(s_line[1], mode_setup(cmode, Nc, false, s_dc[1]), A.pred[1], t.x >> 1, t.y >> 1);
-        predict_block(s_line[2], mode_setup(cmode, Nc, false, s_dc[2]), A.pred[2], t.x >> 1, t.y >> 1);
+    if (HBD) {
+        if (do_luma) predict_block16((const uint16_t *)luma_line, mode_setup(lmode, N, true, s_dc[0], MAXV), A.pred[0], t.x, t.y);
+        if (do_chroma) {
+            predict_block16((const uint16_t *)s_line[1], mode_setup(cmode, Nc, false, s_dc[1], MAXV), A.pred[1], t.x >> 1, t.y >> 1);
+            predict_block16((const uint16_t *)s_line[2], mode_setup(cmode, Nc, false, s_dc[2], MAXV), A.pred[2], t.x >> 1, t.y >> 1);
+        }
+    } else {
+        if (do_luma) predict_block((const uint8_t *)luma_line, mode_setup(lmode, N, true, s_dc[0]), A.pred[0], t.x, t.y);
+        if (do_chroma) {
+            predict_block((const uint8_t *)s_line[1], mode_setup(cmode, Nc, false, s_dc[1]), A.pred[1], t.x >> 1, t.y >> 1);
+            predict_block((const uint8_t *)s_line[2], mode_setup(cmode, Nc, false, s_dc[2]), A.pred[2], t.x >> 1, t.y >> 1);
+        }
     }
 }
 
@@ -411,7 +438,7 @@ __global__ void __launch_bounds__(OIS_NT) ois_picture_kernel(const __grid_consta
 }
 
 static size_t pbytes(const svtb200_plane &p) { return (size_t)p.stride * (p.height + 2 * p.origin_y); }
-static PlaneW plane_w(const svtb200_plane &p, uint8_t *base) { PlaneW w; w.p = base + (size_t)p.origin_y * p.stride + p.origin_x; w.stride = (int)p.stride; return w; }
+static PlaneW plane_w(const svtb200_plane &p, uint8_t *base, size_t bps = 1) { PlaneW w; w.p = base + ((size_t)p.origin_y * p.stride + p.origin_x) * bps; w.stride = (int)p.stride; return w; }
 
 static int intra_check(const svtb200_yuv_picture *recon, const svtb200_yuv_picture *pred, const svtb200_intra_job *jobs, uint32_t n, bool host_jobs)
 {
@@ -431,10 +458,10 @@ static int intra_check(const svtb200_yuv_picture *recon, const svtb200_yuv_pictu
     return SVTB200_OK;
 }
 
-static int intra_launch(const IntraArgs &A, cudaStream_t st)
+static int intra_launch(const IntraArgs &A, cudaStream_t st, bool hbd = false)
 {
     if (A.n_jobs == 0) return SVTB200_OK;
-    intra_batch_kernel<<<A.n_jobs, IN_NT, 0, st>>>(A);
+    if (hbd) intra_batch_kernel<true><<<A.n_jobs, IN_NT, 0, st>>>(A); else intra_batch_kernel<false><<<A.n_jobs, IN_NT, 0, st>>>(A);
     SVTB200_COUNT_LAUNCH();
     SVTB200_CUDA_TRY(cudaGetLastError());
     return SVTB200_OK;
@@ -495,20 +522,22 @@ int svtb200_IntraPrediction(uint32_t mode, uint32_t size, int is_chroma, const u
     return SVTB200_OK;
 }
 
-int svtb200_intra_batch_dev(const svtb200_yuv_picture *recon, const svtb200_yuv_picture *pred, const svtb200_intra_job *jobs_dev, uint32_t n_jobs, void *cuda_stream)
+static int intra_batch_dev_impl(const svtb200_yuv_picture *recon, const svtb200_yuv_picture *pred, const svtb200_intra_job *jobs_dev, uint32_t n_jobs, void *cuda_stream, bool hbd)
 {
+    const size_t bps = hbd ? 2 : 1;
     int rc = intra_check(recon, pred, jobs_dev, n_jobs, false);
     if (rc) return rc;
     if ((rc = ensure_device())) return rc;
     IntraArgs A;
     const svtb200_plane *r[3] = {&recon->y, &recon->cb, &recon->cr}, *p[3] = {&pred->y, &pred->cb, &pred->cr};
-    for (int k = 0; k < 3; ++k) { A.recon[k] = plane_w(*r[k], r[k]->buf); A.pred[k] = plane_w(*p[k], p[k]->buf); }
+    for (int k = 0; k < 3; ++k) { A.recon[k] = plane_w(*r[k], r[k]->buf, bps); A.pred[k] = plane_w(*p[k], p[k]->buf, bps); }
     A.jobs = jobs_dev; A.n_jobs = (int)n_jobs;
-    return intra_launch(A, (cudaStream_t)cuda_stream);
+    return intra_launch(A, (cudaStream_t)cuda_stream, hbd);
 }
 
-int svtb200_intra_batch(const svtb200_yuv_picture *recon, const svtb200_yuv_picture *pred, const svtb200_intra_job *jobs, uint32_t n_jobs)
+static int intra_batch_impl(const svtb200_yuv_picture *recon, const svtb200_yuv_picture *pred, const svtb200_intra_job *jobs, uint32_t n_jobs, bool hbd)
 {
+    const size_t bps = hbd ? 2 : 1;
     int rc = intra_check(recon, pred, jobs, n_jobs, true);
     if (rc) return rc;
     if (n_jobs == 0) return SVTB200_OK;
@@ -518,28 +547,37 @@ int svtb200_intra_batch(const svtb200_yuv_picture *recon, const svtb200_yuv_pict
     const svtb200_plane *r[3] = {&recon->y, &recon->cb, &recon->cr}, *p[3] = {&pred->y, &pred->cb, &pred->cr};
     const bool in_place = recon->y.buf == pred->y.buf;
     size_t need = 8192 + align_up((size_t)n_jobs * sizeof(svtb200_intra_job), 256);
-    for (int k = 0; k < 3; ++k) need += align_up(pbytes(*r[k]), 256) + (in_place ? 0 : align_up(pbytes(*p[k]), 256));
+    for (int k = 0; k < 3; ++k) need += align_up(bps * pbytes(*r[k]), 256) + (in_place ? 0 : align_up(bps * pbytes(*p[k]), 256));
     if ((rc = c->dev_reserve(need))) return rc;
     void *dr[3], *dp[3], *dj;
     for (int k = 0; k < 3; ++k) {
-        if ((rc = c->dev_alloc(pbytes(*r[k]), &dr[k]))) return rc;
-        SVTB200_CUDA_TRY(cudaMemcpyAsync(dr[k], r[k]->buf, pbytes(*r[k]), cudaMemcpyHostToDevice, c->stream));
+        if ((rc = c->dev_alloc(bps * pbytes(*r[k]), &dr[k]))) return rc;
+        SVTB200_CUDA_TRY(cudaMemcpyAsync(dr[k], r[k]->buf, bps * pbytes(*r[k]), cudaMemcpyHostToDevice, c->stream));
         dp[k] = dr[k];
         if (!in_place) {
-            if ((rc = c->dev_alloc(pbytes(*p[k]), &dp[k]))) return rc;
-            SVTB200_CUDA_TRY(cudaMemcpyAsync(dp[k], p[k]->buf, pbytes(*p[k]), cudaMemcpyHostToDevice, c->stream));
+            if ((rc = c->dev_alloc(bps * pbytes(*p[k]), &dp[k]))) return rc;
+            SVTB200_CUDA_TRY(cudaMemcpyAsync(dp[k], p[k]->buf, bps * pbytes(*p[k]), cudaMemcpyHostToDevice, c->stream));
         }
     }
     if ((rc = c->dev_alloc((size_t)n_jobs * sizeof(svtb200_intra_job), &dj))) return rc;
     SVTB200_CUDA_TRY(cudaMemcpyAsync(dj, jobs, (size_t)n_jobs * sizeof(svtb200_intra_job), cudaMemcpyHostToDevice, c->stream));
     IntraArgs A;
-    for (int k = 0; k < 3; ++k) { A.recon[k] = plane_w(*r[k], (uint8_t *)dr[k]); A.pred[k] = plane_w(*p[k], (uint8_t *)dp[k]); }
+    for (int k = 0; k < 3; ++k) { A.recon[k] = plane_w(*r[k], (uint8_t *)dr[k], bps); A.pred[k] = plane_w(*p[k], (uint8_t *)dp[k], bps); }
     A.jobs = (const svtb200_intra_job *)dj; A.n_jobs = (int)n_jobs;
-    if ((rc = intra_launch(A, c->stream))) return rc;
-    for (int k = 0; k < 3; ++k) SVTB200_CUDA_TRY(cudaMemcpyAsync(p[k]->buf, dp[k], pbytes(*p[k]), cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = intra_launch(A, c->stream, hbd))) return rc;
+    for (int k = 0; k < 3; ++k) SVTB200_CUDA_TRY(cudaMemcpyAsync(p[k]->buf, dp[k], bps * pbytes(*p[k]), cudaMemcpyDeviceToHost, c->stream));
     SVTB200_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return SVTB200_OK;
 }
+
+int svtb200_intra_batch_dev(const svtb200_yuv_picture *recon, const svtb200_yuv_picture *pred, const svtb200_intra_job *jobs_dev, uint32_t n_jobs, void *cuda_stream)
+{ return intra_batch_dev_impl(recon, pred, jobs_dev, n_jobs, cuda_stream, false); }
+int svtb200_intra_batch(const svtb200_yuv_picture *recon, const svtb200_yuv_picture *pred, const svtb200_intra_job *jobs, uint32_t n_jobs)
+{ return intra_batch_impl(recon, pred, jobs, n_jobs, false); }
+int svtb200_intra_batch16_dev(const svtb200_yuv_picture *recon, const svtb200_yuv_picture *pred, const svtb200_intra_job *jobs_dev, uint32_t n_jobs, void *cuda_stream)
+{ return intra_batch_dev_impl(recon, pred, jobs_dev, n_jobs, cuda_stream, true); }
+int svtb200_intra_batch16(const svtb200_yuv_picture *recon, const svtb200_yuv_picture *pred, const svtb200_intra_job *jobs, uint32_t n_jobs)
+{ return intra_batch_impl(recon, pred, jobs, n_jobs, true); }
 
 int svtb200_ois_picture_dev(const svtb200_ois_config *cfg, const svtb200_plane *src_luma_dev, const svtb200_me_pu_result *me_results_dev, uint8_t *total_modes_dev,
                             uint32_t *cand_dev, uint32_t cand_capacity, void *cuda_stream)

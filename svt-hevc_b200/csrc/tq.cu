@@ -202,7 +202,7 @@ __device__ __forceinline__ void rowdot_any(const int8_t *A, int lda, const int16
 
 // The whole chain for one TU held in shared memory.  s_a: residual in (pitch TP); returns nz.
 // On exit s_a holds the reconstructed residual (if nz && want_recon), s_q the quantised coefficients (act x act corner).
-__device__ uint32_t tq_chain(const int8_t *s_m, const int8_t *s_mt, int16_t *s_a, int16_t *s_b, int16_t *s_q, uint32_t *s_cnt, const svtb200_tq_job &t, bool want_recon, bool prefolded)
+__device__ uint32_t tq_chain(const int8_t *s_m, const int8_t *s_mt, int16_t *s_a, int16_t *s_b, int16_t *s_q, uint32_t *s_cnt, const svtb200_tq_job &t, bool want_recon, bool prefolded, int bit_inc)
 {
     const int N = t.size, lg = ilog2d(N);
     const bool dst = t.dst4x4 != 0;
@@ -221,14 +221,20 @@ __device__ uint32_t tq_chain(const int8_t *s_m, const int8_t *s_mt, int16_t *s_a
         const int sum = (int)*s_cnt;
         __syncthreads();
         if (threadIdx.x == 0) {
-            const int shift = (lg - 1) + (lg + 6);
-            s_a[0] = (int16_t)((64 * 64 * sum + (1 << (shift - 1))) >> shift);
+            if (bit_inc) {   // EncodeTransform ONLY_DC branch (Codec/EbTransforms.c:3425-3447): the 16-bit path rounds after each pass
+                const int sh1 = lg - 1 + bit_inc, sh2 = lg + 6;
+                const int d1 = (64 * sum + (1 << (sh1 - 1))) >> sh1;
+                s_a[0] = (int16_t)((64 * d1 + (1 << (sh2 - 1))) >> sh2);
+            } else {
+                const int shift = (lg - 1) + (lg + 6);
+                s_a[0] = (int16_t)((64 * 64 * sum + (1 << (shift - 1))) >> shift);
+            }
             *s_cnt = 0;
         }
         __syncthreads();
     } else {
         int s1, s2;
-        if (N == 32) { s1 = 6; s2 = 9; } else if (N == 16) { s1 = 4; s2 = 9; } else { s1 = lg - 1; s2 = lg + 6; }
+        if (N == 32) { s1 = 6 + bit_inc; s2 = 9; } else if (N == 16) { s1 = 4 + bit_inc; s2 = 9; } else { s1 = lg - 1 + bit_inc; s2 = lg + 6; }
         if (dst) {
             fwd_pass(s_m, s_a, s_b, N, N, act, s1, dst);     // s_b[k][r]
             __syncthreads();
@@ -246,8 +252,9 @@ __device__ uint32_t tq_chain(const int8_t *s_m, const int8_t *s_mt, int16_t *s_a
         }
     }
     // ---- quantise / dequantise (UnifiedQuantizeInvQuantize parameter derivation, Codec/EbTransforms.c:3094-3110) ----
-    const int qpRem = t.qp % 6, qpPer = t.qp / 6;
-    const int tshift = 15 - 8 - lg;
+    const int qp = t.qp + (bit_inc ? 12 : 0);      // QP_BD_OFFSET on the 10-bit path (EbCodingLoop.c:1307)
+    const int qpRem = qp % 6, qpPer = qp / 6;
+    const int tshift = 15 - (8 + bit_inc) - lg;
     const int shiftedQBits = 14 + qpPer + tshift;
     const uint32_t qoff_ip = (uint32_t)(t.slice_type >= 2 ? 171 : 85) << (shiftedQBits - 9);
     const uint32_t qoff = (!only_dc && t.dz_offset) ? (uint32_t)(t.dz_offset * (1u << shiftedQBits) / 20) : qoff_ip;
@@ -311,7 +318,7 @@ __device__ uint32_t tq_chain(const int8_t *s_m, const int8_t *s_mt, int16_t *s_a
         // pass 1: tmp(u, y) = sum_v M[v][y] * deq[v][u], written as s_a[y][u]; pass 2: res(y, x) = sum_u M[u][x] * tmp(u, y) -> s_b[y][x]
         rowdot_any<true>(s_mt, 32, s_b, 0, act, N, act, 64, 7, s_a, 1, TP);
         __syncthreads();
-        rowdot_any<true>(s_mt, 32, s_a, 0, N, N, act, 2048, 12, s_b, TP, 1);
+        rowdot_any<true>(s_mt, 32, s_a, 0, N, N, act, 2048 >> bit_inc, 12 - bit_inc, s_b, TP, 1);
         __syncthreads();
     } else if (nz && want_recon) {
         inv_pass(s_m, s_b, s_a, N, dst ? 4 : act, act, 7, dst);     // s_a[r][n], rows r >= act would be all zero
@@ -320,14 +327,33 @@ __device__ uint32_t tq_chain(const int8_t *s_m, const int8_t *s_mt, int16_t *s_a
             for (int i = threadIdx.x; i < (N - act) * N; i += TQ_NT) s_a[(act + i / N) * TP + (i % N)] = 0;
             __syncthreads();
         }
-        inv_pass(s_m, s_a, s_b, N, N, dst ? 4 : act, 12, dst);      // s_b[y][x] residual
+        inv_pass(s_m, s_a, s_b, N, N, dst ? 4 : act, 12 - bit_inc, dst);      // s_b[y][x] residual
         __syncthreads();
     }
     return nz;
 }
 
+// 4 horizontally adjacent samples at sample index i of a plane (8-bit: one 32-bit access, 16-bit: one 64-bit access)
+template <bool HBD>
+__device__ __forceinline__ void ld4(const uint8_t *base, size_t i, int (&v)[4])
+{
+    if (HBD) { const uint2 w = *(const uint2 *)(base + 2 * i); v[0] = w.x & 0xffff; v[1] = w.x >> 16; v[2] = w.y & 0xffff; v[3] = w.y >> 16; }
+    else { const uint32_t w = *(const uint32_t *)(base + i); v[0] = w & 0xff; v[1] = (w >> 8) & 0xff; v[2] = (w >> 16) & 0xff; v[3] = w >> 24; }
+}
+template <bool HBD>
+__device__ __forceinline__ void st4(uint8_t *base, size_t i, const int (&v)[4])
+{
+    if (HBD) *(uint2 *)(base + 2 * i) = make_uint2((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16));
+    else *(uint32_t *)(base + i) = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+}
+template <bool HBD>
+__device__ __forceinline__ int ld1(const uint8_t *base, size_t i) { return HBD ? (int)((const uint16_t *)base)[i] : (int)base[i]; }
+
+// HBD: 16-bit sample planes (10-bit video): EncodeLoop16bit / EncodeGenerateRecon16bit (Codec/EbCodingLoop.c:1240,1640); strides stay in samples
+template <bool HBD>
 __global__ void __launch_bounds__(TQ_NT) tq_batch_kernel(const __grid_constant__ TqArgs A)
 {
+    constexpr int BPS = HBD ? 2 : 1, BIT_INC = HBD ? 2 : 0, MAXV = HBD ? 1023 : 255;
     __shared__ __align__(16) int16_t s_a[32 * TP], s_b[32 * TP], s_q[32 * TP];
     __shared__ uint32_t s_cnt;
     __shared__ __align__(16) int8_t s_m[32 * 32], s_mt[32 * 32];
@@ -339,11 +365,12 @@ __global__ void __launch_bounds__(TQ_NT) tq_batch_kernel(const __grid_constant__
     if (threadIdx.x < 64) ((uint4 *)s_m)[threadIdx.x] = ((const uint4 *)g_dct32)[threadIdx.x];
     else ((uint4 *)s_mt)[threadIdx.x - 64] = ((const uint4 *)g_dct_t[lg - 2])[threadIdx.x - 64];
     const int ss = A.src.stride[pl], ps = A.pred.stride[pl], rs = A.recon.stride[pl], cs = A.cstride[pl];
-    const uint8_t *s = A.src.p[pl] + (size_t)(A.src.oy[pl] + t.y) * ss + A.src.ox[pl] + t.x;
-    const uint8_t *p = A.pred.p[pl] + (size_t)(A.pred.oy[pl] + t.y) * ps + A.pred.ox[pl] + t.x;
-    uint8_t *r = A.recon.p[pl] + (size_t)(A.recon.oy[pl] + t.y) * rs + A.recon.ox[pl] + t.x;
+    const uint8_t *s = A.src.p[pl] + ((size_t)(A.src.oy[pl] + t.y) * ss + A.src.ox[pl] + t.x) * BPS;
+    const uint8_t *p = A.pred.p[pl] + ((size_t)(A.pred.oy[pl] + t.y) * ps + A.pred.ox[pl] + t.x) * BPS;
+    uint8_t *r = A.recon.p[pl] + ((size_t)(A.recon.oy[pl] + t.y) * rs + A.recon.ox[pl] + t.x) * BPS;
     int16_t *co = A.coeff[pl] + (size_t)t.y * cs + t.x;
-    const bool vec_in = ((((uintptr_t)s | (uintptr_t)p) | (uintptr_t)(ss | ps)) & 3) == 0;
+    // 4 samples per access: 4 bytes (8-bit) or 8 bytes (16-bit) must be aligned
+    const bool vec_in = ((((uintptr_t)s | (uintptr_t)p) | (uintptr_t)((ss | ps) * BPS)) & (4 * BPS - 1)) == 0;
     // residual; for the 16- and 32-point DCT the first butterfly stage (x[n] +- x[N-1-n], kept in 16 bits like
     // PartialButterfly{16,32}Estimate) is applied on the way in: s_q[r][0..N/2) sums, [N/2..N) differences
     const bool prefold = vec_in && N >= 16 && !t.dst4x4 && t.shape != SVTB200_SHAPE_ONLY_DC;
@@ -351,13 +378,14 @@ __global__ void __launch_bounds__(TQ_NT) tq_batch_kernel(const __grid_constant__
         const int h = N >> 1, w8 = N >> 3, lw8 = lg - 3;
         for (int i = threadIdx.x; i < N * w8; i += TQ_NT) {
             const int y = i >> lw8, q = i & (w8 - 1), xl = 4 * q, xr = N - 4 - 4 * q;
-            const uint32_t sl = *(const uint32_t *)(s + (size_t)y * ss + xl), sr = *(const uint32_t *)(s + (size_t)y * ss + xr);
-            const uint32_t pl_ = *(const uint32_t *)(p + (size_t)y * ps + xl), pr = *(const uint32_t *)(p + (size_t)y * ps + xr);
+            int sl[4], sr[4], pl_[4], pr[4];
+            ld4<HBD>(s, (size_t)y * ss + xl, sl); ld4<HBD>(s, (size_t)y * ss + xr, sr);
+            ld4<HBD>(p, (size_t)y * ps + xl, pl_); ld4<HBD>(p, (size_t)y * ps + xr, pr);
             int a[4], b[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                a[e] = (int)((sl >> (8 * e)) & 0xff) - (int)((pl_ >> (8 * e)) & 0xff);
-                b[e] = (int)((sr >> (8 * (3 - e))) & 0xff) - (int)((pr >> (8 * (3 - e))) & 0xff);     // mirror sample N-1-(xl+e)
+                a[e] = sl[e] - pl_[e];
+                b[e] = sr[3 - e] - pr[3 - e];     // mirror sample N-1-(xl+e)
             }
             uint32_t *o = (uint32_t *)(s_q + y * TP);
             o[(xl >> 1)] = pack2(a[0] + b[0], a[1] + b[1]); o[(xl >> 1) + 1] = pack2(a[2] + b[2], a[3] + b[3]);
@@ -367,22 +395,23 @@ __global__ void __launch_bounds__(TQ_NT) tq_batch_kernel(const __grid_constant__
         const int w4 = N >> 2, lw4 = lg - 2;
         for (int i = threadIdx.x; i < N * w4; i += TQ_NT) {
             const int y = i >> lw4, x = (i & (w4 - 1)) * 4;
-            const uint32_t sw = *(const uint32_t *)(s + (size_t)y * ss + x), pw = *(const uint32_t *)(p + (size_t)y * ps + x);
+            int sw[4], pw[4];
+            ld4<HBD>(s, (size_t)y * ss + x, sw); ld4<HBD>(p, (size_t)y * ps + x, pw);
             uint32_t *o = (uint32_t *)(s_a + y * TP + x);
-            o[0] = pack2((int)(sw & 0xff) - (int)(pw & 0xff), (int)((sw >> 8) & 0xff) - (int)((pw >> 8) & 0xff));
-            o[1] = pack2((int)((sw >> 16) & 0xff) - (int)((pw >> 16) & 0xff), (int)(sw >> 24) - (int)(pw >> 24));
+            o[0] = pack2(sw[0] - pw[0], sw[1] - pw[1]);
+            o[1] = pack2(sw[2] - pw[2], sw[3] - pw[3]);
         }
     } else {
         for (int i = threadIdx.x; i < N * N; i += TQ_NT) {
             const int y = i >> lg, x = i & (N - 1);
-            s_a[y * TP + x] = (int16_t)((int)s[(size_t)y * ss + x] - (int)p[(size_t)y * ps + x]);
+            s_a[y * TP + x] = (int16_t)(ld1<HBD>(s, (size_t)y * ss + x) - ld1<HBD>(p, (size_t)y * ps + x));
         }
     }
     __syncthreads();
     const bool want_recon = !(t.flags & SVTB200_TQ_SKIP_RECON);
-    const uint32_t nz = tq_chain(s_m, s_mt, s_a, s_b, s_q, &s_cnt, t, want_recon, prefold);
+    const uint32_t nz = tq_chain(s_m, s_mt, s_a, s_b, s_q, &s_cnt, t, want_recon, prefold, BIT_INC);
     if (threadIdx.x == 0) A.nz[j] = nz;
-    const bool vec_out = vec_in && ((((uintptr_t)r | (uintptr_t)rs) & 3) == 0) && ((((uintptr_t)co | (uintptr_t)(cs * 2)) & 7) == 0);
+    const bool vec_out = vec_in && ((((uintptr_t)r | (uintptr_t)(rs * BPS)) & (4 * BPS - 1)) == 0) && ((((uintptr_t)co | (uintptr_t)(cs * 2)) & 7) == 0);
     if (vec_out) {
         const int w4 = N >> 2, lw4 = lg - 2;
         for (int i = threadIdx.x; i < N * w4; i += TQ_NT) {
@@ -390,15 +419,14 @@ __global__ void __launch_bounds__(TQ_NT) tq_batch_kernel(const __grid_constant__
             const uint32_t *q = (const uint32_t *)(s_q + y * TP + x);
             *(uint2 *)(co + (size_t)y * cs + x) = make_uint2(q[0], q[1]);
             if (want_recon && (nz || r != p)) {
-                uint32_t pw = *(const uint32_t *)(p + (size_t)y * ps + x);
+                int pw[4];
+                ld4<HBD>(p, (size_t)y * ps + x, pw);
                 if (nz) {
                     const int16_t *e = s_b + y * TP + x;
-                    uint32_t o = 0;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) o |= (uint32_t)min(max((int)((pw >> (8 * k)) & 0xff) + e[k], 0), 255) << (8 * k);
-                    pw = o;
+                    for (int k = 0; k < 4; ++k) pw[k] = min(max(pw[k] + e[k], 0), MAXV);
                 }
-                *(uint32_t *)(r + (size_t)y * rs + x) = pw;
+                st4<HBD>(r, (size_t)y * rs + x, pw);
             }
         }
     } else {
@@ -406,9 +434,9 @@ __global__ void __launch_bounds__(TQ_NT) tq_batch_kernel(const __grid_constant__
             const int y = i >> lg, x = i & (N - 1);
             co[(size_t)y * cs + x] = s_q[y * TP + x];
             if (want_recon) {
-                const int pv = p[(size_t)y * ps + x];
-                const int v = nz ? min(max(pv + s_b[y * TP + x], 0), 255) : pv;
-                if (nz || r != p) r[(size_t)y * rs + x] = (uint8_t)v;
+                const int pv = ld1<HBD>(p, (size_t)y * ps + x);
+                const int v = nz ? min(max(pv + s_b[y * TP + x], 0), MAXV) : pv;
+                if (nz || r != p) { if (HBD) ((uint16_t *)r)[(size_t)y * rs + x] = (uint16_t)v; else r[(size_t)y * rs + x] = (uint8_t)v; }
             }
         }
     }
@@ -526,8 +554,8 @@ using namespace svtb200;
 
 extern "C" {
 
-int svtb200_tq_batch_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *pred, const svtb200_yuv_picture *recon,
-                         const svtb200_coeff_picture *coeff, const svtb200_tq_job *jobs_dev, int n_jobs, uint32_t *nz_counts_dev, void *cuda_stream)
+static int tq_batch_dev_impl(const svtb200_yuv_picture *src, const svtb200_yuv_picture *pred, const svtb200_yuv_picture *recon,
+                             const svtb200_coeff_picture *coeff, const svtb200_tq_job *jobs_dev, int n_jobs, uint32_t *nz_counts_dev, void *cuda_stream, bool hbd)
 {
     if (!src || !pred || !recon || !coeff || (!jobs_dev && n_jobs) || n_jobs < 0 || !nz_counts_dev) { set_error("tq_batch_dev: bad argument"); return SVTB200_ERR_BAD_ARG; }
     int rc = ensure_device();
@@ -539,15 +567,16 @@ int svtb200_tq_batch_dev(const svtb200_yuv_picture *src, const svtb200_yuv_pictu
     A.recon = to_yuvw(*recon, recon->y.buf, recon->cb.buf, recon->cr.buf);
     for (int k = 0; k < 3; ++k) { A.coeff[k] = coeff->buf[k]; A.cstride[k] = (int)coeff->stride[k]; }
     A.jobs = jobs_dev; A.n_jobs = n_jobs; A.nz = nz_counts_dev;
-    tq_batch_kernel<<<n_jobs, TQ_NT, 0, (cudaStream_t)cuda_stream>>>(A);
+    if (hbd) tq_batch_kernel<true><<<n_jobs, TQ_NT, 0, (cudaStream_t)cuda_stream>>>(A); else tq_batch_kernel<false><<<n_jobs, TQ_NT, 0, (cudaStream_t)cuda_stream>>>(A);
     SVTB200_COUNT_LAUNCH();
     SVTB200_CUDA_TRY(cudaGetLastError());
     return SVTB200_OK;
 }
 
-int svtb200_tq_batch(const svtb200_yuv_picture *src, const svtb200_yuv_picture *pred, const svtb200_yuv_picture *recon,
-                     const svtb200_coeff_picture *coeff, const svtb200_tq_job *jobs, int n_jobs, uint32_t *nz_counts)
+static int tq_batch_impl(const svtb200_yuv_picture *src, const svtb200_yuv_picture *pred, const svtb200_yuv_picture *recon,
+                         const svtb200_coeff_picture *coeff, const svtb200_tq_job *jobs, int n_jobs, uint32_t *nz_counts, bool hbd)
 {
+    const size_t bps = hbd ? 2 : 1;
     if (!src || !pred || !recon || !coeff || (!jobs && n_jobs) || n_jobs < 0 || !nz_counts) { set_error("tq_batch: bad argument"); return SVTB200_ERR_BAD_ARG; }
     int rc = check_jobs(jobs, n_jobs, *src);
     if (rc) return rc;
@@ -560,7 +589,7 @@ int svtb200_tq_batch(const svtb200_yuv_picture *src, const svtb200_yuv_picture *
     const size_t cbytes[3] = {(size_t)coeff->stride[0] * chh * 2, (size_t)coeff->stride[1] * (chh / 2) * 2, (size_t)coeff->stride[2] * (chh / 2) * 2};
     (void)cw;
     size_t need = 8192 + (size_t)n_jobs * (sizeof(svtb200_tq_job) + 4);
-    for (int i = 0; i < 3; ++i) need += align_up(pbytes(pics[i]->y), 256) + align_up(pbytes(pics[i]->cb), 256) + align_up(pbytes(pics[i]->cr), 256);
+    for (int i = 0; i < 3; ++i) need += align_up(bps * pbytes(pics[i]->y), 256) + align_up(bps * pbytes(pics[i]->cb), 256) + align_up(bps * pbytes(pics[i]->cr), 256);
     for (int k = 0; k < 3; ++k) need += align_up(cbytes[k], 256);
     if ((rc = c->dev_reserve(need))) return rc;
     uint8_t *dp[3][3];
@@ -569,10 +598,10 @@ int svtb200_tq_batch(const svtb200_yuv_picture *src, const svtb200_yuv_picture *
         for (int k = 0; k < 3; ++k) {
             if (i == 2 && in_place) { dp[2][k] = dp[1][k]; continue; }
             void *d;
-            if ((rc = c->dev_alloc(pbytes(*pl[k]), &d))) return rc;
+            if ((rc = c->dev_alloc(bps * pbytes(*pl[k]), &d))) return rc;
             dp[i][k] = (uint8_t *)d;
             // recon (when separate) is updated only inside TU areas: bring its current content over as well
-            SVTB200_CUDA_TRY(cudaMemcpyAsync(d, pl[k]->buf, pbytes(*pl[k]), cudaMemcpyHostToDevice, c->stream));
+            SVTB200_CUDA_TRY(cudaMemcpyAsync(d, pl[k]->buf, bps * pbytes(*pl[k]), cudaMemcpyHostToDevice, c->stream));
         }
     }
     void *dc[3], *d_jobs, *d_nz;
@@ -588,16 +617,29 @@ int svtb200_tq_batch(const svtb200_yuv_picture *src, const svtb200_yuv_picture *
     drec.y.buf = dp[2][0]; drec.cb.buf = dp[2][1]; drec.cr.buf = dp[2][2];
     svtb200_coeff_picture dcoef = *coeff;
     for (int k = 0; k < 3; ++k) dcoef.buf[k] = (int16_t *)dc[k];
-    if ((rc = svtb200_tq_batch_dev(&ds, &dpred, &drec, &dcoef, (const svtb200_tq_job *)d_jobs, n_jobs, (uint32_t *)d_nz, c->stream))) return rc;
+    if ((rc = tq_batch_dev_impl(&ds, &dpred, &drec, &dcoef, (const svtb200_tq_job *)d_jobs, n_jobs, (uint32_t *)d_nz, c->stream, hbd))) return rc;
     const svtb200_plane *rpl[3] = {&recon->y, &recon->cb, &recon->cr};
     for (int k = 0; k < 3; ++k) {
-        SVTB200_CUDA_TRY(cudaMemcpyAsync(rpl[k]->buf, dp[2][k], pbytes(*rpl[k]), cudaMemcpyDeviceToHost, c->stream));
+        SVTB200_CUDA_TRY(cudaMemcpyAsync(rpl[k]->buf, dp[2][k], bps * pbytes(*rpl[k]), cudaMemcpyDeviceToHost, c->stream));
         SVTB200_CUDA_TRY(cudaMemcpyAsync(coeff->buf[k], dc[k], cbytes[k], cudaMemcpyDeviceToHost, c->stream));
     }
     if (n_jobs) SVTB200_CUDA_TRY(cudaMemcpyAsync(nz_counts, d_nz, 4 * (size_t)n_jobs, cudaMemcpyDeviceToHost, c->stream));
     SVTB200_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return SVTB200_OK;
 }
+
+int svtb200_tq_batch_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *pred, const svtb200_yuv_picture *recon, const svtb200_coeff_picture *coeff,
+                         const svtb200_tq_job *jobs_dev, int n_jobs, uint32_t *nz_counts_dev, void *cuda_stream)
+{ return tq_batch_dev_impl(src, pred, recon, coeff, jobs_dev, n_jobs, nz_counts_dev, cuda_stream, false); }
+int svtb200_tq_batch(const svtb200_yuv_picture *src, const svtb200_yuv_picture *pred, const svtb200_yuv_picture *recon, const svtb200_coeff_picture *coeff,
+                     const svtb200_tq_job *jobs, int n_jobs, uint32_t *nz_counts)
+{ return tq_batch_impl(src, pred, recon, coeff, jobs, n_jobs, nz_counts, false); }
+int svtb200_tq_batch16_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *pred, const svtb200_yuv_picture *recon, const svtb200_coeff_picture *coeff,
+                           const svtb200_tq_job *jobs_dev, int n_jobs, uint32_t *nz_counts_dev, void *cuda_stream)
+{ return tq_batch_dev_impl(src, pred, recon, coeff, jobs_dev, n_jobs, nz_counts_dev, cuda_stream, true); }
+int svtb200_tq_batch16(const svtb200_yuv_picture *src, const svtb200_yuv_picture *pred, const svtb200_yuv_picture *recon, const svtb200_coeff_picture *coeff,
+                       const svtb200_tq_job *jobs, int n_jobs, uint32_t *nz_counts)
+{ return tq_batch_impl(src, pred, recon, coeff, jobs, n_jobs, nz_counts, true); }
 
 static int tq_leaf(LeafArgs L, const int16_t *in, size_t in_elems, int16_t *out, size_t out_elems, int16_t *out2, uint32_t *nz)
 {

@@ -362,11 +362,11 @@ class HostCoeffPicture:
             self.struct.stride[i] = p.shape[1]
 
 
-def tq_batch(src, pred, recon, coeff, jobs):
-    """src/pred/recon: HostYuvPicture (recon may be pred); coeff: HostCoeffPicture; jobs: TQ_JOB_DTYPE array -> nz counts."""
+def tq_batch(src, pred, recon, coeff, jobs, hbd=False):
+    """src/pred/recon: HostYuvPicture (recon may be pred; dtype uint16 with hbd); coeff: HostCoeffPicture; jobs: TQ_JOB_DTYPE array -> nz counts."""
     jobs = np.ascontiguousarray(jobs)
     nz = np.zeros(len(jobs), np.uint32)
-    check(lib().svtb200_tq_batch(C.byref(src.struct), C.byref(pred.struct), C.byref(recon.struct), C.byref(coeff.struct), _u8p(jobs),
+    check((lib().svtb200_tq_batch16 if hbd else lib().svtb200_tq_batch)(C.byref(src.struct), C.byref(pred.struct), C.byref(recon.struct), C.byref(coeff.struct), _u8p(jobs),
                                  C.c_int(len(jobs)), _u8p(nz)))
     return nz
 
@@ -405,9 +405,9 @@ class DlfParams(C.Structure):
                 ("beta_offset", C.c_int8), ("cb_qp_offset", C.c_int8), ("cr_qp_offset", C.c_int8)]
 
 
-def dlf_picture(recon, vbs, hbs, qp_array, prm):
-    """In-place deblocking of a HostYuvPicture. vbs/hbs: uint8 [n_lcu][256]; qp_array: uint8 [H/8][qp_stride]."""
-    check(lib().svtb200_dlf_picture(C.byref(recon.struct), _u8p(vbs), _u8p(hbs), _u8p(qp_array), C.byref(prm)))
+def dlf_picture(recon, vbs, hbs, qp_array, prm, hbd=False):
+    """In-place deblocking of a HostYuvPicture (dtype uint16 with hbd). vbs/hbs: uint8 [n_lcu][256]; qp_array: uint8 [H/8][qp_stride]."""
+    check((lib().svtb200_dlf_picture16 if hbd else lib().svtb200_dlf_picture)(C.byref(recon.struct), _u8p(vbs), _u8p(hbs), _u8p(qp_array), C.byref(prm)))
 
 
 def luma_edge_dlf(buf, off, stride, vertical, tc, beta):
@@ -547,10 +547,10 @@ def intra_prediction(mode, size, is_chroma, line):
     return pred
 
 
-def intra_batch(recon, pred, jobs):
-    """recon / pred: HostYuvPicture (may be the same object); jobs: INTRA_JOB_DTYPE array"""
+def intra_batch(recon, pred, jobs, hbd=False):
+    """recon / pred: HostYuvPicture (may be the same object; dtype uint16 with hbd); jobs: INTRA_JOB_DTYPE array"""
     jobs = np.ascontiguousarray(jobs)
-    check(lib().svtb200_intra_batch(C.byref(recon.struct), C.byref(pred.struct), _u8p(jobs), C.c_uint32(len(jobs))))
+    check((lib().svtb200_intra_batch16 if hbd else lib().svtb200_intra_batch)(C.byref(recon.struct), C.byref(pred.struct), _u8p(jobs), C.c_uint32(len(jobs))))
 
 
 def intra_batch_dev(recon_struct, pred_struct, jobs_ptr, n_jobs, stream=0):

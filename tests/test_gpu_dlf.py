@@ -48,3 +48,22 @@ def test_dlf_picture_cuda_vs_oracle(case):
     # padding untouched
     fresh = S.HostYuvPicture(*(a.copy() for a in pic.interior()))
     assert np.array_equal(got.y[:80], fresh.y[:80]) and np.array_equal(got.cb[:, :40], fresh.cb[:, :40])
+
+
+@pytest.mark.parametrize("case", DLF_CASES, ids=lambda c: c[0])
+def test_dlf_picture16_cuda_vs_oracle(case):
+    """16-bit sample planes (10-bit video)"""
+    from test_oracle_dlf import run_dlf16, to16
+    name, w, h, kind, density = case
+    pic8, vbs, hbs, qp, prm = make_dlf_inputs(w, h, seed=w + h, density=density, kind=kind)
+    pic = to16(pic8, seed=w, extremes=kind == "extremes")
+    want = run_dlf16(port, "port_dlf_picture16", pic, vbs, hbs, qp, prm)
+    y, cb, cr = (a.copy() for a in pic.interior())
+    got = S.HostYuvPicture(y, cb, cr, dtype=np.uint16)
+    S.dlf_picture(got, vbs, hbs, qp, prm, hbd=True)
+    for a, b, nm in zip(got.interior(), want.interior(), "Y Cb Cr".split()):
+        assert np.array_equal(a, b), f"{name}: {nm} differs (16-bit CUDA vs port): {np.argwhere(a != b)[:5]}"
+    if ref is not None:
+        wr = run_dlf16(ref, "svtref_dlf_picture16", pic, vbs, hbs, qp, prm, asm_mode=1 if common.ref_asm_simd_ok() else 0)
+        for a, b in zip(got.interior(), wr.interior()):
+            assert np.array_equal(a, b), name

@@ -123,3 +123,25 @@ def test_ois_rejects_bad_config():
     cfg = ois_cfg(128, 64, slice_type=0)
     with pytest.raises(S.Svtb200Error):
         S.ois_picture(cfg, pl, None, 9)          # the OIS-point path reads ME distortions
+
+
+@pytest.mark.parametrize("case", INTRA_CASES, ids=lambda c: c[0])
+def test_intra_batch16_cuda_vs_oracle(case):
+    """16-bit sample planes (10-bit video)"""
+    from test_oracle_intra import make_recon16, run_intra_batch16
+    name, w, h, kind, density = case
+    recon = make_recon16(w, h, seed=w + h, kind=kind)
+    rng = np.random.default_rng(w * 3 + h)
+    jobs = disjoint_jobs(w & ~31, h & ~31, rng, density)
+    want = run_intra_batch16(port, "port_intra_batch16", recon, jobs)
+    got = S.HostYuvPicture(*[np.zeros_like(a) for a in recon.interior()], pad=80, replicate=False, dtype=np.uint16)
+    S.intra_batch(recon, got, jobs, hbd=True)
+    for a, b, pl in zip(got.interior(), want.interior(), "y cb cr".split()):
+        assert np.array_equal(a, b), (name, pl, np.argwhere(a != b)[:4])
+    if ref is not None:
+        one = jobs[:1]
+        wr = run_intra_batch16(ref, "svtref_intra_batch16", recon, one, C.c_int(1 if common.ref_asm_simd_ok() else 0))
+        g1 = S.HostYuvPicture(*[np.zeros_like(a) for a in recon.interior()], pad=80, replicate=False, dtype=np.uint16)
+        S.intra_batch(recon, g1, one, hbd=True)
+        for a, b in zip(g1.interior(), wr.interior()):
+            assert np.array_equal(a, b)

@@ -101,3 +101,26 @@ def test_tq_batch_in_place_and_4k_full_frame():
     nz = S.tq_batch(src, pred, pred, coeff, jobs)      # in place
     assert_tq_equal((pred, coeff, nz), want, "4K in-place CUDA vs oracle")
     assert nz.sum() > 0
+
+
+@pytest.mark.parametrize("case", TQ_CASES, ids=lambda c: c[0])
+def test_tq_batch16_cuda_vs_oracle(case):
+    """16-bit sample planes (10-bit video): EncodeLoop16bit / EncodeGenerateRecon16bit"""
+    from test_oracle_tq import make_src_pred16, run_tq_oracle16
+    name, w, h, kind, shapes, flags = case
+    src, pred = make_src_pred16(w, h, 31, kind)
+    jobs = make_tq_jobs(w, h, seed=8, shapes=shapes, flags=flags)
+    want = run_tq_oracle16(port, "port_tq_batch16", src, pred, jobs, w, h)
+    y, cb, cr = (a.copy() for a in pred.interior())
+    recon = S.HostYuvPicture(y, cb, cr, dtype=np.uint16)
+    coeff = S.HostCoeffPicture(w, h)
+    nz = S.tq_batch(src, pred, recon, coeff, jobs, hbd=True)
+    assert_tq_equal((recon, coeff, nz), want, name + " 16-bit CUDA vs port")
+    if ref is not None:
+        wr = run_tq_oracle16(ref, "svtref_tq_batch16", src, pred, jobs, w, h, asm_mode=1 if common.ref_asm_simd_ok() else 0)
+        assert_tq_equal((recon, coeff, nz), wr, name + " 16-bit CUDA vs reference chain")
+    # in place (recon == pred), as the encode pass runs it
+    nz2 = S.tq_batch(src, pred, pred, S.HostCoeffPicture(w, h), jobs, hbd=True)
+    assert np.array_equal(nz2, nz)
+    for a, b in zip(pred.interior(), recon.interior()):
+        assert np.array_equal(a, b)

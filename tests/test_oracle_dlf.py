@@ -114,3 +114,39 @@ def test_dlf_picture_port_vs_reference(case):
         simd = run_dlf(ref, "svtref_dlf_picture", pic, vbs, hbs, qp, prm, asm_mode=1)
         for a, b, nm in zip(simd.interior(), want.interior(), "Y Cb Cr".split()):
             assert np.array_equal(a, b), f"{name}: {nm} differs (reference SIMD vs C rows)"
+
+
+# ---- 16-bit samples (10-bit video) ---------------------------------------------------------------------------------------------
+def to16(pic, seed, extremes=False):
+    rng = np.random.default_rng(seed)
+    planes = [(a.astype(np.uint16) // 255) * 1023 if extremes else a.astype(np.uint16) * 4 + rng.integers(0, 4, a.shape, dtype=np.uint16) for a in pic.interior()]
+    return S.HostYuvPicture(*planes, dtype=np.uint16)
+
+
+def run_dlf16(lib, name, pic, vbs, hbs, qp, prm, asm_mode=None):
+    y, cb, cr = (a.copy() for a in pic.interior())
+    out = S.HostYuvPicture(y, cb, cr, dtype=np.uint16)
+    fn = getattr(lib, name); fn.restype = C.c_int
+    args = [C.byref(out.struct), vp(vbs), vp(hbs), vp(qp), C.byref(prm)]
+    if asm_mode is not None:
+        args.append(C.c_int(asm_mode))
+    assert fn(*args) == 0
+    return out
+
+
+@needs_ref
+@pytest.mark.parametrize("case", DLF_CASES, ids=lambda c: c[0])
+def test_dlf_picture16_port_vs_reference(case):
+    name, w, h, kind, density = case
+    pic8, vbs, hbs, qp, prm = make_dlf_inputs(w, h, seed=w + h, density=density, kind=kind)
+    pic = to16(pic8, seed=w, extremes=kind == "extremes")
+    want = run_dlf16(ref, "svtref_dlf_picture16", pic, vbs, hbs, qp, prm, asm_mode=0)
+    got = run_dlf16(port, "port_dlf_picture16", pic, vbs, hbs, qp, prm)
+    for a, b, nm in zip(got.interior(), want.interior(), "Y Cb Cr".split()):
+        assert np.array_equal(a, b), f"{name}: {nm} differs (16-bit port vs reference C rows): {np.argwhere(a != b)[:5]}"
+    changed = sum(int((a != b).sum()) for a, b in zip(want.interior(), pic.interior()))
+    assert changed > 0 or kind == "extremes"
+    if common.ref_asm_simd_ok():
+        simd = run_dlf16(ref, "svtref_dlf_picture16", pic, vbs, hbs, qp, prm, asm_mode=1)
+        for a, b, nm in zip(simd.interior(), want.interior(), "Y Cb Cr".split()):
+            assert np.array_equal(a, b), f"{name}: {nm} differs (16-bit reference SIMD vs C rows)"

@@ -249,3 +249,36 @@ def test_ois_port_vs_reference(variant, pic):
         gt, gc = run_ois(port, "port_ois_picture", cfg, pl, me, cap)
         assert np.array_equal(gt, wt), (vname, asm)
         assert np.array_equal(gc, wc), (vname, asm, np.argwhere(gc != wc)[:5])
+
+
+# ---- 16-bit samples (10-bit video) ---------------------------------------------------------------------------------------------
+def make_recon16(w, h, seed, kind="synth"):
+    rng = np.random.default_rng(seed + 77)
+    base = make_recon(w, h, seed, kind)
+    planes = []
+    for a in base.interior():
+        planes.append(a.astype(np.uint16) * 4 + (rng.integers(0, 4, a.shape, dtype=np.uint16) if kind != "smooth" else np.uint16(1)))
+    return S.HostYuvPicture(*planes, pad=80, replicate=False, dtype=np.uint16)
+
+
+def run_intra_batch16(lib, name, recon, jobs, *extra):
+    pred = S.HostYuvPicture(*[np.zeros_like(a) for a in recon.interior()], pad=80, replicate=False, dtype=np.uint16)
+    rc = getattr(lib, name)(C.byref(recon.struct), C.byref(pred.struct), vp(jobs), C.c_uint32(len(jobs)), *extra)
+    assert rc == 0
+    return pred
+
+
+@needs_ref
+@pytest.mark.parametrize("case", INTRA_CASES, ids=lambda c: c[0])
+def test_intra_batch16_port_vs_reference(case):
+    name, w, h, kind, density = case
+    recon = make_recon16(w, h, seed=w + h, kind=kind)
+    rng = np.random.default_rng(w * 3 + h)
+    jobs = make_intra_jobs(w & ~31, h & ~31, rng, 250, density)
+    for asm in ASM_MODES:
+        for j in range(len(jobs)):
+            one = jobs[j:j + 1]
+            want = run_intra_batch16(ref, "svtref_intra_batch16", recon, one, C.c_int(asm))
+            got = run_intra_batch16(port, "port_intra_batch16", recon, one)
+            for a, b, pl in zip(got.interior(), want.interior(), "y cb cr".split()):
+                assert np.array_equal(a, b), (name, asm, j, pl, one)

@@ -157,3 +157,38 @@ def test_tq_batch_port_vs_reference(case):
     if common.ref_asm_simd_ok():
         simd = run_tq_oracle(ref, "svtref_tq_batch", src, pred, jobs, w, h, asm_mode=1)
         assert_tq_equal(simd, want, name + " reference SIMD vs C rows")
+
+
+# ---- 16-bit samples (10-bit video): EncodeLoop16bit / EncodeGenerateRecon16bit ------------------------------------------------
+def make_src_pred16(w, h, seed, kind="synth"):
+    from test_oracle_mc import make_pictures16
+    pics = make_pictures16(w, h, seed=seed, n=2, kind=kind)
+    return pics[0], pics[1]
+
+
+def run_tq_oracle16(lib, name, src, pred, jobs, w, h, asm_mode=None):
+    y, cb, cr = (a.copy() for a in pred.interior())
+    recon = S.HostYuvPicture(y, cb, cr, dtype=np.uint16)
+    coeff = S.HostCoeffPicture(w, h)
+    nz = np.zeros(len(jobs), np.uint32)
+    fn = getattr(lib, name)
+    fn.restype = C.c_int
+    args = [C.byref(src.struct), C.byref(pred.struct), C.byref(recon.struct), C.byref(coeff.struct), vp(jobs), C.c_int(len(jobs)), vp(nz)]
+    if asm_mode is not None:
+        args += [C.c_int(asm_mode), C.c_int(0), C.c_int(len(jobs))]
+    assert fn(*args) == 0
+    return recon, coeff, nz
+
+
+@needs_ref
+@pytest.mark.parametrize("case", TQ_CASES, ids=lambda c: c[0])
+def test_tq_batch16_port_vs_reference(case):
+    name, w, h, kind, shapes, flags = case
+    src, pred = make_src_pred16(w, h, 31, kind)
+    jobs = make_tq_jobs(w, h, seed=8, shapes=shapes, flags=flags)
+    want = run_tq_oracle16(ref, "svtref_tq_batch16", src, pred, jobs, w, h, asm_mode=0)
+    got = run_tq_oracle16(port, "port_tq_batch16", src, pred, jobs, w, h)
+    assert_tq_equal(got, want, name + " 16-bit port vs reference C rows")
+    if common.ref_asm_simd_ok():
+        simd = run_tq_oracle16(ref, "svtref_tq_batch16", src, pred, jobs, w, h, asm_mode=1)
+        assert_tq_equal(simd, want, name + " 16-bit reference SIMD vs C rows")
