@@ -368,6 +368,15 @@ int svtb200_sao_apply_picture(const svtb200_yuv_picture *in, const svtb200_yuv_p
 int svtb200_sao_apply_picture_dev(const svtb200_yuv_picture *in, const svtb200_yuv_picture *out, const svtb200_sao_params *lcu_params_dev,
                                   const uint8_t sao_flag[2], void *cuda_stream);
 
+/* the same two on 16-bit sample planes (10-bit video): GatherSaoStatisticsLcu_62x62_16bit (C_DEFAULT/EbSampleAdaptiveOffset_C.c:23: differences are
+ * not clipped, band = sample >> 5), SAOApplyBO16bit / SAOApplyEO_*16bit (:431 ff, clip to 1023), ApplySaoOffsetsPicture16bit (Codec/EbEncDecProcess.c:1063) */
+int svtb200_sao_stats_picture16(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out);
+int svtb200_sao_stats_picture16_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out_dev, void *cuda_stream);
+int svtb200_sao_apply_picture16(const svtb200_yuv_picture *in, const svtb200_yuv_picture *out, const svtb200_sao_params *lcu_params,
+                                const uint8_t sao_flag[2]);
+int svtb200_sao_apply_picture16_dev(const svtb200_yuv_picture *in, const svtb200_yuv_picture *out, const svtb200_sao_params *lcu_params_dev,
+                                    const uint8_t sao_flag[2], void *cuda_stream);
+
 /* =======================================================================================
  *  D. Intra prediction
  * ===================================================================================== */

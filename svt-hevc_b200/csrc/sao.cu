@@ -174,6 +174,82 @@ __global__ void __launch_bounds__(256) sao_apply_kernel(const __grid_constant__ 
     *(uint32_t *)(A.out[c] + (size_t)y * A.ostride[c] + x0) = res;
 }
 
+
+// ---- 16-bit sample planes (10-bit video): GatherSaoStatisticsLcu_62x62_16bit (C_DEFAULT/EbSampleAdaptiveOffset_C.c:23: no diff clipping, band =
+// sample >> 5), SAOApplyBO16bit / SAOApplyEO_*16bit (:431 ff, clip to 1023), ApplySaoOffsetsPicture16bit (Codec/EbEncDecProcess.c:1063).
+// One sample per thread-iteration, neighbours straight from L1/L2; same thread-private [row][thread] histograms as the 8-bit kernel.
+__global__ void __launch_bounds__(ST_NT) sao_stats16_kernel(const __grid_constant__ StatsArgs A)
+{
+    __shared__ int s_h[ST_ROWS * ST_NT];
+    const int job = blockIdx.x, lcu = job / 3, c = job - lcu * 3, sh = c ? 1 : 0;
+    const int lx = lcu % A.cols, ly = lcu / A.cols;
+    const int ox = (lx * 64) >> sh, oy = (ly * 64) >> sh;
+    const int lw = min(64, A.W - lx * 64) >> sh, lh = min(64, A.H - ly * 64) >> sh;
+    const int rs = A.rec[c].stride, ss = A.src[c].stride;
+    const uint16_t *r = (const uint16_t *)A.rec[c].p + (size_t)oy * rs + ox, *s = (const uint16_t *)A.src[c].p + (size_t)oy * ss + ox;
+    int *my = s_h + threadIdx.x;
+#pragma unroll 4
+    for (int k = 0; k < ST_ROWS; ++k) my[k * ST_NT] = 0;
+    const int iw = lw - 2, n_items = (lh - 2) * iw;
+    for (int i = threadIdx.x; i < n_items; i += ST_NT) {
+        const int y = 1 + i / iw, x = 1 + i % iw;
+        const uint16_t *q = r + (size_t)y * rs + x;
+        const int v = q[0], d = (int)s[(size_t)y * ss + x] - v;
+        const int add = 65536 + d;       // |sum of <= 31 differences| < 2^15
+        const int e0 = sgn(v, q[-1]) + sgn(v, q[1]) + 2, e1 = sgn(v, q[-rs]) + sgn(v, q[rs]) + 2;
+        const int e2 = sgn(v, q[-rs - 1]) + sgn(v, q[rs + 1]) + 2, e3 = sgn(v, q[-rs + 1]) + sgn(v, q[rs - 1]) + 2;
+        my[(0 + e0) * ST_NT] += add; my[(5 + e1) * ST_NT] += add; my[(10 + e2) * ST_NT] += add; my[(15 + e3) * ST_NT] += add;
+        my[(20 + (v >> 5)) * ST_NT] += add;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    svtb200_sao_stats *o = A.out + job;
+    for (int row = wid; row < ST_ROWS; row += ST_NT / 32) {
+        int dsum = 0, csum = 0;
+#pragma unroll
+        for (int qd = 0; qd < ST_NT / 32; ++qd) {
+            const int w = s_h[row * ST_NT + lane + 32 * qd], dd = (int)(short)(w & 0xffff);
+            dsum += dd;
+            csum += (w - dd) >> 16;
+        }
+        dsum = __reduce_add_sync(0xffffffffu, dsum);
+        csum = __reduce_add_sync(0xffffffffu, csum);
+        if (lane == 0) {
+            if (row >= 20) { o->bo_diff[row - 20] = dsum; o->bo_count[row - 20] = (uint16_t)csum; }
+            else {
+                const int t = row / 5, k = row - t * 5;
+                if (k == 2) { o->eo_diff[t][4] = 0; o->eo_count[t][4] = 0; }
+                else { const int slot = k < 2 ? k : k - 1; o->eo_diff[t][slot] = dsum; o->eo_count[t][slot] = (uint16_t)csum; }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) sao_apply16_kernel(const __grid_constant__ ApplyArgs A)
+{
+    const int c = blockIdx.z, sh = c ? 1 : 0, pw = A.W >> sh, ph = A.H >> sh;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= pw || y >= ph) return;
+    const svtb200_sao_params p = A.prm[(size_t)((y << sh) >> 6) * A.cols + ((x << sh) >> 6)];
+    const int t = A.flag[c ? 1 : 0] ? p.type[c ? 1 : 0] : 0;
+    const int is = A.in[c].stride;
+    const uint16_t *q = (const uint16_t *)A.in[c].p + (size_t)y * is + x;
+    int v = q[0];
+    if (t == 5) {
+        const int b = (v >> 5) - p.band_position[c];
+        if (b >= 0 && b <= 3) v = min(max(v + p.offset[c][b], 0), 1023);
+    } else if (t >= 1 && t <= 4) {
+        const int dx = (t == 2) ? 0 : (t == 4 ? 1 : -1), dy = (t == 1) ? 0 : -1;
+        const bool skip = ((t != 1) && (y == 0 || y == ph - 1)) || ((t != 2) && (x == 0 || x == pw - 1));
+        if (!skip) {
+            const int idx = sgn(v, (int)q[(ptrdiff_t)dy * is + dx]) + sgn(v, (int)q[-(ptrdiff_t)dy * is - dx]) + 2;
+            const int off = idx == 0 ? p.offset[c][0] : idx == 1 ? p.offset[c][1] : idx == 3 ? p.offset[c][2] : idx == 4 ? p.offset[c][3] : 0;
+            v = min(max(v + off, 0), 1023);
+        }
+    }
+    ((uint16_t *)A.out[c])[(size_t)y * A.ostride[c] + x] = (uint16_t)v;
+}
+
 static const svtb200_plane *plane_of(const svtb200_yuv_picture *p, int k) { return k == 0 ? &p->y : k == 1 ? &p->cb : &p->cr; }
 static size_t pbytes(const svtb200_plane &p) { return (size_t)p.stride * (p.height + 2 * p.origin_y); }
 
@@ -196,29 +272,31 @@ using namespace svtb200;
 
 extern "C" {
 
-int svtb200_sao_stats_picture_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out_dev, void *cuda_stream)
+static int sao_stats_dev_impl(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out_dev, void *cuda_stream, bool hbd)
 {
+    const size_t bps = hbd ? 2 : 1;
     if (!src || !recon || !out_dev) { set_error("sao_stats_picture_dev: bad argument"); return SVTB200_ERR_BAD_ARG; }
     int rc = sao_check(src, recon, "sao_stats_picture");
     if (rc || (rc = ensure_device())) return rc;
     StatsArgs A;
     for (int k = 0; k < 3; ++k) {
         const svtb200_plane *s = plane_of(src, k), *r = plane_of(recon, k);
-        A.src[k] = {s->buf + (size_t)s->origin_y * s->stride + s->origin_x, (int)s->stride};
-        A.rec[k] = {r->buf + (size_t)r->origin_y * r->stride + r->origin_x, (int)r->stride};
+        A.src[k] = {s->buf + ((size_t)s->origin_y * s->stride + s->origin_x) * bps, (int)s->stride};
+        A.rec[k] = {r->buf + ((size_t)r->origin_y * r->stride + r->origin_x) * bps, (int)r->stride};
         if ((((uintptr_t)A.rec[k].p) & 3) || (((uintptr_t)A.src[k].p) & 3)) { set_error("sao_stats_picture: plane interiors must be 4-byte aligned"); return SVTB200_ERR_BAD_ARG; }
     }
     A.out = out_dev; A.W = recon->y.width; A.H = recon->y.height; A.cols = (A.W + 63) / 64;
     const int n = A.cols * ((A.H + 63) / 64) * 3;
-    sao_stats_kernel<<<n, ST_NT, 0, (cudaStream_t)cuda_stream>>>(A);
+    if (hbd) sao_stats16_kernel<<<n, ST_NT, 0, (cudaStream_t)cuda_stream>>>(A); else sao_stats_kernel<<<n, ST_NT, 0, (cudaStream_t)cuda_stream>>>(A);
     SVTB200_COUNT_LAUNCH();
     SVTB200_CUDA_TRY(cudaGetLastError());
     return SVTB200_OK;
 }
 
-int svtb200_sao_apply_picture_dev(const svtb200_yuv_picture *in, const svtb200_yuv_picture *out, const svtb200_sao_params *lcu_params_dev,
-                                  const uint8_t sao_flag[2], void *cuda_stream)
+static int sao_apply_dev_impl(const svtb200_yuv_picture *in, const svtb200_yuv_picture *out, const svtb200_sao_params *lcu_params_dev,
+                              const uint8_t sao_flag[2], void *cuda_stream, bool hbd)
 {
+    const size_t bps = hbd ? 2 : 1;
     if (!in || !out || !lcu_params_dev || !sao_flag) { set_error("sao_apply_picture_dev: bad argument"); return SVTB200_ERR_BAD_ARG; }
     int rc = sao_check(in, out, "sao_apply_picture");
     if (rc || (rc = ensure_device())) return rc;
@@ -226,36 +304,37 @@ int svtb200_sao_apply_picture_dev(const svtb200_yuv_picture *in, const svtb200_y
     ApplyArgs A;
     for (int k = 0; k < 3; ++k) {
         const svtb200_plane *i = plane_of(in, k), *o = plane_of(out, k);
-        A.in[k] = {i->buf + (size_t)i->origin_y * i->stride + i->origin_x, (int)i->stride};
-        A.out[k] = o->buf + (size_t)o->origin_y * o->stride + o->origin_x;
+        A.in[k] = {i->buf + ((size_t)i->origin_y * i->stride + i->origin_x) * bps, (int)i->stride};
+        A.out[k] = o->buf + ((size_t)o->origin_y * o->stride + o->origin_x) * bps;
         A.ostride[k] = (int)o->stride;
         if ((((uintptr_t)A.in[k].p) & 3) || (((uintptr_t)A.out[k]) & 3)) { set_error("sao_apply_picture: plane interiors must be 4-byte aligned"); return SVTB200_ERR_BAD_ARG; }
     }
     A.prm = lcu_params_dev; A.W = in->y.width; A.H = in->y.height; A.cols = (A.W + 63) / 64; A.flag[0] = sao_flag[0]; A.flag[1] = sao_flag[1];
-    dim3 grid((A.W / 4 + 255) / 256, A.H, 3);
-    sao_apply_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(A);
+    if (hbd) { dim3 grid((A.W + 255) / 256, A.H, 3); sao_apply16_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(A); }
+    else { dim3 grid((A.W / 4 + 255) / 256, A.H, 3); sao_apply_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(A); }
     SVTB200_COUNT_LAUNCH();
     SVTB200_CUDA_TRY(cudaGetLastError());
     return SVTB200_OK;
 }
 
-static int upload_pic(ThreadCtx *c, const svtb200_yuv_picture *h, svtb200_yuv_picture *d, bool copy)
+static int upload_pic(ThreadCtx *c, const svtb200_yuv_picture *h, svtb200_yuv_picture *d, bool copy, size_t bps = 1)
 {
     *d = *h;
     svtb200_plane *dp[3] = {&d->y, &d->cb, &d->cr};
     for (int k = 0; k < 3; ++k) {
         void *p;
-        int rc = c->dev_alloc(pbytes(*dp[k]), &p);
+        int rc = c->dev_alloc(bps * pbytes(*dp[k]), &p);
         if (rc) return rc;
-        if (copy) SVTB200_CUDA_TRY(cudaMemcpyAsync(p, plane_of(h, k)->buf, pbytes(*dp[k]), cudaMemcpyHostToDevice, c->stream));
+        if (copy) SVTB200_CUDA_TRY(cudaMemcpyAsync(p, plane_of(h, k)->buf, bps * pbytes(*dp[k]), cudaMemcpyHostToDevice, c->stream));
         dp[k]->buf = (uint8_t *)p;
     }
     return SVTB200_OK;
 }
 static size_t pic_bytes(const svtb200_yuv_picture *p) { return align_up(pbytes(p->y), 256) + align_up(pbytes(p->cb), 256) + align_up(pbytes(p->cr), 256); }
 
-int svtb200_sao_stats_picture(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out)
+static int sao_stats_impl(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out, bool hbd)
 {
+    const size_t bps = hbd ? 2 : 1;
     if (!src || !recon || !out) { set_error("sao_stats_picture: bad argument"); return SVTB200_ERR_BAD_ARG; }
     int rc = sao_check(src, recon, "sao_stats_picture");
     if (rc) return rc;
@@ -263,18 +342,19 @@ int svtb200_sao_stats_picture(const svtb200_yuv_picture *src, const svtb200_yuv_
     if ((rc = c->init())) return rc;
     c->reset();
     const size_t n = (size_t)((recon->y.width + 63) / 64) * ((recon->y.height + 63) / 64) * 3, ob = n * sizeof(svtb200_sao_stats);
-    if ((rc = c->dev_reserve(pic_bytes(src) + pic_bytes(recon) + ob + 8192))) return rc;
+    if ((rc = c->dev_reserve(bps * (pic_bytes(src) + pic_bytes(recon)) + ob + 8192))) return rc;
     svtb200_yuv_picture ds, dr;
     void *d_out;
-    if ((rc = upload_pic(c, src, &ds, true)) || (rc = upload_pic(c, recon, &dr, true)) || (rc = c->dev_alloc(ob, &d_out))) return rc;
-    if ((rc = svtb200_sao_stats_picture_dev(&ds, &dr, (svtb200_sao_stats *)d_out, c->stream))) return rc;
+    if ((rc = upload_pic(c, src, &ds, true, bps)) || (rc = upload_pic(c, recon, &dr, true, bps)) || (rc = c->dev_alloc(ob, &d_out))) return rc;
+    if ((rc = sao_stats_dev_impl(&ds, &dr, (svtb200_sao_stats *)d_out, c->stream, hbd))) return rc;
     SVTB200_CUDA_TRY(cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, c->stream));
     SVTB200_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return SVTB200_OK;
 }
 
-int svtb200_sao_apply_picture(const svtb200_yuv_picture *in, const svtb200_yuv_picture *out, const svtb200_sao_params *lcu_params, const uint8_t sao_flag[2])
+static int sao_apply_impl(const svtb200_yuv_picture *in, const svtb200_yuv_picture *out, const svtb200_sao_params *lcu_params, const uint8_t sao_flag[2], bool hbd)
 {
+    const size_t bps = hbd ? 2 : 1;
     if (!in || !out || !lcu_params || !sao_flag) { set_error("sao_apply_picture: bad argument"); return SVTB200_ERR_BAD_ARG; }
     int rc = sao_check(in, out, "sao_apply_picture");
     if (rc) return rc;
@@ -282,17 +362,32 @@ int svtb200_sao_apply_picture(const svtb200_yuv_picture *in, const svtb200_yuv_p
     if ((rc = c->init())) return rc;
     c->reset();
     const size_t n = (size_t)((in->y.width + 63) / 64) * ((in->y.height + 63) / 64), pb = n * sizeof(svtb200_sao_params);
-    if ((rc = c->dev_reserve(pic_bytes(in) + pic_bytes(out) + pb + 8192))) return rc;
+    if ((rc = c->dev_reserve(bps * (pic_bytes(in) + pic_bytes(out)) + pb + 8192))) return rc;
     svtb200_yuv_picture di, dout;
     void *d_prm;
     // the output keeps whatever the caller had in its padding: bring it over, the kernel rewrites the interior only
-    if ((rc = upload_pic(c, in, &di, true)) || (rc = upload_pic(c, out, &dout, true)) || (rc = c->dev_alloc(pb, &d_prm))) return rc;
+    if ((rc = upload_pic(c, in, &di, true, bps)) || (rc = upload_pic(c, out, &dout, true, bps)) || (rc = c->dev_alloc(pb, &d_prm))) return rc;
     SVTB200_CUDA_TRY(cudaMemcpyAsync(d_prm, lcu_params, pb, cudaMemcpyHostToDevice, c->stream));
-    if ((rc = svtb200_sao_apply_picture_dev(&di, &dout, (const svtb200_sao_params *)d_prm, sao_flag, c->stream))) return rc;
+    if ((rc = sao_apply_dev_impl(&di, &dout, (const svtb200_sao_params *)d_prm, sao_flag, c->stream, hbd))) return rc;
     const svtb200_plane *hp[3] = {&out->y, &out->cb, &out->cr}, *dp[3] = {&dout.y, &dout.cb, &dout.cr};
-    for (int k = 0; k < 3; ++k) SVTB200_CUDA_TRY(cudaMemcpyAsync(hp[k]->buf, dp[k]->buf, pbytes(*hp[k]), cudaMemcpyDeviceToHost, c->stream));
+    for (int k = 0; k < 3; ++k) SVTB200_CUDA_TRY(cudaMemcpyAsync(hp[k]->buf, dp[k]->buf, bps * pbytes(*hp[k]), cudaMemcpyDeviceToHost, c->stream));
     SVTB200_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return SVTB200_OK;
 }
+
+int svtb200_sao_stats_picture_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out_dev, void *cuda_stream)
+{ return sao_stats_dev_impl(src, recon, out_dev, cuda_stream, false); }
+int svtb200_sao_stats_picture(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out) { return sao_stats_impl(src, recon, out, false); }
+int svtb200_sao_apply_picture_dev(const svtb200_yuv_picture *in, const svtb200_yuv_picture *out, const svtb200_sao_params *lcu_params_dev, const uint8_t sao_flag[2], void *cuda_stream)
+{ return sao_apply_dev_impl(in, out, lcu_params_dev, sao_flag, cuda_stream, false); }
+int svtb200_sao_apply_picture(const svtb200_yuv_picture *in, const svtb200_yuv_picture *out, const svtb200_sao_params *lcu_params, const uint8_t sao_flag[2])
+{ return sao_apply_impl(in, out, lcu_params, sao_flag, false); }
+int svtb200_sao_stats_picture16_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out_dev, void *cuda_stream)
+{ return sao_stats_dev_impl(src, recon, out_dev, cuda_stream, true); }
+int svtb200_sao_stats_picture16(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out) { return sao_stats_impl(src, recon, out, true); }
+int svtb200_sao_apply_picture16_dev(const svtb200_yuv_picture *in, const svtb200_yuv_picture *out, const svtb200_sao_params *lcu_params_dev, const uint8_t sao_flag[2], void *cuda_stream)
+{ return sao_apply_dev_impl(in, out, lcu_params_dev, sao_flag, cuda_stream, true); }
+int svtb200_sao_apply_picture16(const svtb200_yuv_picture *in, const svtb200_yuv_picture *out, const svtb200_sao_params *lcu_params, const uint8_t sao_flag[2])
+{ return sao_apply_impl(in, out, lcu_params, sao_flag, true); }
 
 }  // extern "C"

@@ -428,17 +428,17 @@ SAO_PARAMS_DTYPE = np.dtype([("type", "u1", 2), ("band_position", "u1", 3), ("of
 assert SAO_PARAMS_DTYPE.itemsize == 20
 
 
-def sao_stats_picture(src, recon):
+def sao_stats_picture(src, recon, hbd=False):
     n_lcu = ((recon.width + 63) // 64) * ((recon.height + 63) // 64)
     out = np.zeros((n_lcu, 3), dtype=SAO_STATS_DTYPE)
-    check(lib().svtb200_sao_stats_picture(C.byref(src.struct), C.byref(recon.struct), _u8p(out)))
+    check((lib().svtb200_sao_stats_picture16 if hbd else lib().svtb200_sao_stats_picture)(C.byref(src.struct), C.byref(recon.struct), _u8p(out)))
     return out
 
 
-def sao_apply_picture(inp, out, params, sao_flag=(1, 1)):
+def sao_apply_picture(inp, out, params, sao_flag=(1, 1), hbd=False):
     params = np.ascontiguousarray(params)
     flag = (C.c_uint8 * 2)(*sao_flag)
-    check(lib().svtb200_sao_apply_picture(C.byref(inp.struct), C.byref(out.struct), _u8p(params), flag))
+    check((lib().svtb200_sao_apply_picture16 if hbd else lib().svtb200_sao_apply_picture)(C.byref(inp.struct), C.byref(out.struct), _u8p(params), flag))
 
 
 # ================================================================================================

@@ -109,3 +109,48 @@ def test_sao_apply_port_vs_reference(case, flags):
         simd = run_apply_ref(rec, prm, flags, asm_mode=1)
         for a, b, nm in zip(simd.interior(), want.interior(), "Y Cb Cr".split()):
             assert np.array_equal(a, b), f"{name}: {nm} differs (reference SIMD vs C rows)"
+
+
+# ---- 16-bit samples (10-bit video) ---------------------------------------------------------------------------------------------
+def make_sao_inputs16(w, h, seed, kind="synth"):
+    rng = np.random.default_rng(seed + 5)
+    src8, rec8, prm = make_sao_inputs(w, h, seed, kind)
+    def up(p, noise):
+        planes = [(a.astype(np.uint16) // 255) * 1023 if kind == "extremes" else np.clip(a.astype(int) * 4 + rng.integers(-noise, noise + 1, a.shape), 0, 1023).astype(np.uint16)
+                  for a in p.interior()]
+        return S.HostYuvPicture(*planes, dtype=np.uint16)
+    return up(src8, 2), up(rec8, 9), prm
+
+
+@needs_ref
+@pytest.mark.parametrize("case", SAO_CASES, ids=lambda c: c[0])
+def test_sao_stats16_port_vs_reference(case):
+    name, w, h, kind = case
+    src, rec, _ = make_sao_inputs16(w, h, seed=w * 3 + h, kind=kind)
+    want = run_stats(refsao, "svtref_sao_stats_picture16", src, rec, asm_mode=0)
+    got = run_stats(port, "port_sao_stats_picture16", src, rec)
+    assert_stats_equal(got, want, name + " 16-bit port vs reference C row")
+    if common.ref_asm_simd_ok():
+        simd = run_stats(refsao, "svtref_sao_stats_picture16", src, rec, asm_mode=1)
+        assert_stats_equal(simd, want, name + " 16-bit reference SIMD vs C row")
+
+
+@needs_ref
+@pytest.mark.parametrize("case", SAO_APPLY_CASES, ids=lambda c: c[0])
+@pytest.mark.parametrize("flags", [(1, 1), (1, 0), (0, 1)])
+def test_sao_apply16_port_vs_reference(case, flags):
+    name, w, h, kind = case
+    _, rec, prm = make_sao_inputs16(w, h, seed=w * 3 + h, kind=kind)
+    outs = []
+    for asm in ([0, 1] if common.ref_asm_simd_ok() else [0]):
+        y, cb, cr = (a.copy() for a in rec.interior())
+        o = S.HostYuvPicture(y, cb, cr, dtype=np.uint16)
+        fn = refsao.svtref_sao_apply_picture16; fn.restype = C.c_int
+        assert fn(C.byref(o.struct), vp(prm), (C.c_uint8 * 2)(*flags), C.c_int(asm)) == 0
+        outs.append(o)
+    got = S.HostYuvPicture(*(np.zeros_like(a) for a in rec.interior()), dtype=np.uint16)
+    fn = port.port_sao_apply_picture16; fn.restype = C.c_int
+    assert fn(C.byref(rec.struct), C.byref(got.struct), vp(prm), (C.c_uint8 * 2)(*flags)) == 0
+    for o in outs:
+        for a, b, nm in zip(got.interior(), o.interior(), "Y Cb Cr".split()):
+            assert np.array_equal(a, b), f"{name}: {nm} differs (16-bit port vs reference): {np.argwhere(a != b)[:5]}"
