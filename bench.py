@@ -10,9 +10,11 @@ frame's temporal layer; consecutive steps walk the 8-frame hier
                   (M10 switches sub-pel, DLF and SAO-apply off on layers 1-3: EbPictureDecisionProcess.c:353-361, EbEncDecProcess.c:2036-2054)
 Mode decision itself (host, out of scope) is replaced by a fixed stand-in: 32x32 PUs / TUs taking each PU's best ME
 candidate; SAO parameters and boundary strengths are fixed per-LCU tables.  Both arms run exactly the same jobs.
-  value : frames resident in HBM (16-frame ring > L2), device-timed with CUDA events, max over ranks
-  e2e   : the same step through the C ABI from HOST (pinned) buffers: H2D of Y/Cb/Cr, kernels, D2H of ME results,
-          quantised coefficients, nz counts and SAO statistics
+  value : frames resident in HBM (16-frame ring > L2), device-timed with CUDA events, max over ranks; consecutive (independent) frames
+          alternate between --streams compute streams, per-stage events are taken inside that timed region (`stages`), and once more
+          with a single stream (`stages_serial`: what each kernel costs alone)
+  e2e   : the same step through the C ABI from HOST (pinned) buffers: H2D of Y/Cb/Cr, kernels, D2H of ME results, OIS candidates,
+          quantised coefficients, nz counts and SAO statistics; two frames in flight (copy-in / compute / copy-out streams)
   N > 1 : independent closed GOPs / streams per GPU -- weak scaling, no data-path collective
   --impl reference : the reference's own CPU implementation of the same stages (oracle/_ref, one frame per host thread)
 """
@@ -231,6 +233,7 @@ def run_b200(args):
         """device + pinned host buffers of one frame in flight (the e2e loop keeps two in flight: copies of one overlap the kernels of the other)"""
         def __init__(self):
             self.pred_t, self.pred = dev_yuv()
+            self.sao_t, self.sao_out = dev_yuv()
             self.in_t, self.in_yuv = dev_yuv()
             self.pa = S.DevPaPicture(W, H)
             self.coeff_t = [torch.zeros((H, W), dtype=torch.int16, device=dev), torch.zeros((H // 2, W // 2), dtype=torch.int16, device=dev),
@@ -267,13 +270,14 @@ def run_b200(args):
 
     names = ["me", "ois", "mc", "tq", "dlf", "sao_stats", "sao_apply"]
 
-    def pipeline(i, src_pa, src_yuv, sl, st, ev=None):
-        """All device stages of frame i into slot sl on CUDA stream st.  ev: dict name -> list of (start, end) events."""
+    def pipeline(i, src_pa, src_yuv, sl, ts, ev=None):
+        """All device stages of frame i into slot sl on torch stream ts.  ev: dict name -> list of (start, end) events."""
+        st = ts.cuda_stream
         def timed(name, fn):
             if ev is None:
                 fn(); return
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fn(); b.record()
+            a.record(ts); fn(); b.record(ts)
             ev[name].append((a, b))
         r0, r1 = wl.refs(i)
         k = i % RING
@@ -287,10 +291,17 @@ def run_b200(args):
             timed("dlf", lambda: S.dlf_picture_dev(pred, d_vbs.data_ptr(), d_hbs.data_ptr(), d_qp.data_ptr(), wl.dlf_prm, st))
         timed("sao_stats", lambda: S.sao_stats_picture_dev(src_yuv, pred, sl.d_stats.data_ptr(), st))
         if tl0:
-            timed("sao_apply", lambda: S.sao_apply_picture_dev(pred, sao_out, d_sao_prm.data_ptr(), (1, 1), st))
+            timed("sao_apply", lambda: S.sao_apply_picture_dev(pred, sl.sao_out, d_sao_prm.data_ptr(), (1, 1), st))
+
+    # resident loop: frames are independent, so consecutive frames alternate between `--streams` compute streams (one output slot each);
+    # kernels of different frames then share the SMs, which hides launch tails and lets the latency-bound kernels overlap the issue-bound ones
+    cstreams = [tstream] + [torch.cuda.Stream(device=dev) for _ in range(args.streams - 1)]
+    while len(slots) < len(cstreams):
+        slots.append(Slot())
 
     def step_resident(i, ev=None):
-        pipeline(i, ring_pa[i % RING], ring_yuv[i % RING][1], slots[0], stream, ev)
+        k = i % len(cstreams)
+        pipeline(i, ring_pa[i % RING], ring_yuv[i % RING][1], slots[k], cstreams[k], ev)
 
     s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
 
@@ -307,7 +318,7 @@ def run_b200(args):
         tstream.wait_event(sl.ev_out)                                                      # this slot's previous results have left the device
         yint = sl.in_t[0][PAD:, PAD:]
         sl.pa.build_from_device(yint.data_ptr(), sl.in_t[0].shape[1], stream)              # pad + decimate on the device
-        pipeline(i, sl.pa, sl.in_yuv, sl, stream)
+        pipeline(i, sl.pa, sl.in_yuv, sl, tstream)
         sl.ev_cmp.record(tstream)
         with torch.cuda.stream(s_out):
             s_out.wait_event(sl.ev_cmp)
@@ -328,15 +339,25 @@ def run_b200(args):
     ev = {n: [] for n in names}
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    t0.record()
+    t0.record(tstream)
+    for cs in cstreams[1:]:
+        cs.wait_event(t0)
     for i in range(args.steps):
         step_resident(args.warmup + i, ev)
-    t1.record()
+    for cs in cstreams[1:]:
+        e = torch.cuda.Event(); e.record(cs); tstream.wait_event(e)
+    t1.record(tstream)
     barrier()
     sampler.stop_flag = True
     launches = S.lib().svtb200_launch_count() - launches0
     ms = t0.elapsed_time(t1)
     stage_ms = {n: [a.elapsed_time(b) for a, b in ev[n]] for n in names}
+    # the same stages with nothing else on the GPU (one stream): what each kernel costs alone -- reported next to the timed-region numbers
+    ev1 = {n: [] for n in names}
+    for i in range(min(args.steps, 16)):
+        pipeline(args.warmup + i, ring_pa[(args.warmup + i) % RING], ring_yuv[(args.warmup + i) % RING][1], slots[0], tstream, ev1)
+    barrier()
+    serial_ms = {n: [a.elapsed_time(b) for a, b in ev1[n]] for n in names}
 
     for i in range(args.warmup):
         step_e2e(i)
@@ -369,7 +390,7 @@ def run_b200(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "stages": STAGES,
-                       "l2": "16-frame ring of resident 4K pictures (> 400 MB of planes) > 126 MB L2", "parallelism": f"stream-per-GPU x{world}"},
+                       "l2": "16-frame ring of resident 4K pictures (> 400 MB of planes) > 126 MB L2", "parallelism": f"{args.streams} compute stream(s) per GPU, {world} GPU(s)"},
             "e2e": {"value": ctus / (e2e_ms * 1e-3), "unit": "CTU/s", "fps": ctus / (e2e_ms * 1e-3) / N_LCU,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
@@ -380,6 +401,8 @@ def run_b200(args):
                          "frac": alg[dom] / k_avg_s / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg[dom], "avg_launch_ms": k_avg_s * 1e3},
             "stages": per_stage,
+            "stages_serial": {n: {"launch_ms_avg": float(np.mean(v)) if v else None, "frac_of_hbm_peak": (alg[n] / (np.mean(v) * 1e-3) / 1e9 / peak) if v else None}
+                              for n, v in serial_ms.items()},
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_reference(frames=None)
@@ -469,6 +492,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=2, help="compute streams the resident loop spreads consecutive frames over")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
