@@ -14,7 +14,7 @@ candidate; SAO parameters and boundary strengths are fixed per-LCU tables.  Both
           alternate between --streams compute streams, per-stage events are taken inside that timed region (`stages`), and once more
           with a single stream (`stages_serial`: what each kernel costs alone)
   e2e   : the same step through the C ABI from HOST (pinned) buffers: H2D of Y/Cb/Cr, kernels, D2H of ME results, OIS candidates,
-          quantised coefficients, nz counts and SAO statistics; two frames in flight (copy-in / compute / copy-out streams)
+          quantised coefficients, nz counts and SAO statistics; three frames in flight (copy-in / compute / copy-out streams); coefficients leave as the packed stream of coded TUs
   N > 1 : independent closed GOPs / streams per GPU -- weak scaling, no data-path collective
   --impl reference : the reference's own CPU implementation of the same stages (oracle/_ref, one frame per host thread)
 """
@@ -241,16 +241,29 @@ def run_b200(args):
             self.coeff = S.CoeffPicture()
             for k in range(3):
                 self.coeff.buf[k] = self.coeff_t[k].data_ptr(); self.coeff.stride[k] = self.coeff_t[k].shape[1]
-            self.d_res = torch.zeros(N_LCU * 85 * 24, dtype=torch.uint8, device=dev)
-            self.d_nz = torch.zeros(len(wl.tq_jobs), dtype=torch.int32, device=dev)
-            self.d_stats = torch.zeros(N_LCU * 3 * 312, dtype=torch.uint8, device=dev)
-            self.d_ois_total = torch.zeros(N_LCU * 85, dtype=torch.uint8, device=dev)
-            self.d_ois_cand = torch.zeros(N_LCU * 85, dtype=torch.int32, device=dev)
-            self.dev_out = [self.d_res, *self.coeff_t, self.d_nz, self.d_stats, self.d_ois_total, self.d_ois_cand]
-            self.host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in self.dev_out]
+            # everything small the host consumes sits in ONE device buffer (one D2H): ME results, TU offsets, nz counts, SAO stats, OIS
+            sizes = [N_LCU * 85 * 24, (len(wl.tq_jobs) + 1) * 4, len(wl.tq_jobs) * 4, N_LCU * 3 * 312, N_LCU * 85, N_LCU * 85 * 4]
+            offs = np.concatenate([[0], np.cumsum([(b + 255) // 256 * 256 for b in sizes])]).astype(int)
+            self.d_small = torch.zeros(int(offs[-1]), dtype=torch.uint8, device=dev)
+            self.h_small = torch.zeros(int(offs[-1]), dtype=torch.uint8).pin_memory()
+            part = lambda k: self.d_small[offs[k]:offs[k] + sizes[k]]
+            self.d_res, self.d_nz, self.d_stats, self.d_ois_total = part(0), part(2).view(torch.int32), part(3), part(4)
+            self.d_off, self.d_ois_cand = part(1).view(torch.int32), part(5).view(torch.int32)
+            self.h_off_total = self.h_small[offs[1]:offs[1] + sizes[1]].view(torch.int32).numpy()      # [-1] = packed stream length
+            # quantised coefficients leave the device as a dense stream of the coded TUs (svtb200_tq_pack_coeffs_dev)
+            self.cap = int(sum(int(j["size"]) ** 2 for j in wl.tq_jobs))
+            self.d_stream = torch.zeros(self.cap, dtype=torch.int16, device=dev)
+            self.h_stream = torch.empty(self.cap, dtype=torch.int16).pin_memory()
+            self.small_bytes = int(sum(sizes))
+            self.pending = False
+            self.ev_small = torch.cuda.Event()
             self.ev_in, self.ev_cmp, self.ev_out = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+            # raw pointers used by the per-frame calls
+            self.p = dict(res=self.d_res.data_ptr(), nz=self.d_nz.data_ptr(), stats=self.d_stats.data_ptr(), ois_t=self.d_ois_total.data_ptr(),
+                          ois_c=self.d_ois_cand.data_ptr(), off=self.d_off.data_ptr(), stream=self.d_stream.data_ptr(), small=self.d_small.data_ptr(),
+                          h_small=self.h_small.data_ptr(), h_stream=self.h_stream.data_ptr(), yint=self.in_t[0][PAD:, PAD:].data_ptr())
 
-    slots = [Slot(), Slot()]
+    slots = [Slot(), Slot(), Slot()]      # e2e: three frames in flight (H2D / kernels / D2H of consecutive frames overlap, the host runs two frames ahead)
     d_res = slots[0].d_res
     d_tq = torch.from_numpy(wl.tq_jobs.view(np.uint8)).to(dev)
     d_vbs, d_hbs, d_qp = (torch.from_numpy(a.copy()).to(dev) for a in (wl.vbs, wl.hbs, wl.qp_array))
@@ -269,6 +282,15 @@ def run_b200(args):
     torch.cuda.synchronize()
 
     names = ["me", "ois", "mc", "tq", "dlf", "sao_stats", "sao_apply"]
+    # per-frame constants hoisted out of the loops (the loops should cost the host as little as a C caller would spend)
+    me_cfgs = {tl: S.me_config(W, H, enc_mode=10, temporal_layer=tl, num_lists=2, ref_poc=(0, 16)) for tl in set(TL_PATTERN)}
+    ref_pairs = {}
+    for i in range(RING):
+        r0, r1 = wl.refs(i)
+        ref_pairs[(r0, r1)] = S.yuv_struct_array([ring_yuv[r0][1], ring_yuv[r1][1]])
+    d_mc_ptr = [(t.data_ptr(), n) for t, n in d_mc]
+    p_tq, n_tq, p_vbs, p_hbs, p_qp, p_sao_prm = d_tq.data_ptr(), len(wl.tq_jobs), d_vbs.data_ptr(), d_hbs.data_ptr(), d_qp.data_ptr(), d_sao_prm.data_ptr()
+    hp = [(h_y[k].data_ptr(), h_cb[k].data_ptr(), h_cr[k].data_ptr()) for k in range(RING)]
 
     def pipeline(i, src_pa, src_yuv, sl, ts, ev=None):
         """All device stages of frame i into slot sl on torch stream ts.  ev: dict name -> list of (start, end) events."""
@@ -283,15 +305,16 @@ def run_b200(args):
         k = i % RING
         tl0 = wl.tl(i) == 0
         pred = sl.pred
-        timed("me", lambda: S.me_picture_dev(wl.me_cfg(i), src_pa, ring_pa[r0], ring_pa[r1], sl.d_res.data_ptr(), st))
-        timed("ois", lambda: S.ois_picture_dev(ois_cfg, src_pa.struct.full, sl.d_res.data_ptr(), sl.d_ois_total.data_ptr(), sl.d_ois_cand.data_ptr(), 1, st))
-        timed("mc", lambda: S.mc_batch_dev([ring_yuv[r0][1], ring_yuv[r1][1]], d_mc[k][0].data_ptr(), d_mc[k][1], pred, st))
-        timed("tq", lambda: S.tq_batch_dev(src_yuv, pred, pred, sl.coeff, d_tq.data_ptr(), len(wl.tq_jobs), sl.d_nz.data_ptr(), st))
+        P = sl.p
+        timed("me", lambda: S.me_picture_dev(me_cfgs[wl.tl(i)], src_pa, ring_pa[r0], ring_pa[r1], P["res"], st))
+        timed("ois", lambda: S.ois_picture_dev(ois_cfg, src_pa.struct.full, P["res"], P["ois_t"], P["ois_c"], 1, st))
+        timed("mc", lambda: S.mc_batch_dev(ref_pairs[(r0, r1)], d_mc_ptr[k][0], d_mc_ptr[k][1], pred, st))
+        timed("tq", lambda: S.tq_batch_dev(src_yuv, pred, pred, sl.coeff, p_tq, n_tq, P["nz"], st))
         if tl0:
-            timed("dlf", lambda: S.dlf_picture_dev(pred, d_vbs.data_ptr(), d_hbs.data_ptr(), d_qp.data_ptr(), wl.dlf_prm, st))
-        timed("sao_stats", lambda: S.sao_stats_picture_dev(src_yuv, pred, sl.d_stats.data_ptr(), st))
+            timed("dlf", lambda: S.dlf_picture_dev(pred, p_vbs, p_hbs, p_qp, wl.dlf_prm, st))
+        timed("sao_stats", lambda: S.sao_stats_picture_dev(src_yuv, pred, P["stats"], st))
         if tl0:
-            timed("sao_apply", lambda: S.sao_apply_picture_dev(pred, sl.sao_out, d_sao_prm.data_ptr(), (1, 1), st))
+            timed("sao_apply", lambda: S.sao_apply_picture_dev(pred, sl.sao_out, p_sao_prm, (1, 1), st))
 
     # resident loop: frames are independent, so consecutive frames alternate between `--streams` compute streams (one output slot each);
     # kernels of different frames then share the SMs, which hides launch tails and lets the latency-bound kernels overlap the issue-bound ones
@@ -303,28 +326,43 @@ def run_b200(args):
         k = i % len(cstreams)
         pipeline(i, ring_pa[i % RING], ring_yuv[i % RING][1], slots[k], cstreams[k], ev)
 
-    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    # copy-in, small-results copy-out and coefficient-stream copy-out each get a stream: a frame's stream copy is issued two frames later (its
+    # length must reach the host first) and must not queue behind the next frame's kernels
+    s_in, s_out, s_small = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    d2h_bytes = []
+
+    def finish_slot(sl):
+        """second half of a frame's D2H: the packed coefficient stream, whose length is known once the offsets have arrived"""
+        if not sl.pending:
+            return
+        sl.ev_small.synchronize()
+        total = int(sl.h_off_total[-1])
+        S.copy_async(sl.p["h_stream"], sl.p["stream"], 2 * total, True, s_out.cuda_stream)
+        sl.ev_out.record(s_out)
+        d2h_bytes.append(2 * total + sl.small_bytes)
+        sl.pending = False
 
     def step_e2e(i):
         """Frame i from pinned host buffers: H2D on the copy-in stream, kernels on the compute stream, D2H of everything the host-side
-        encoder consumes on the copy-out stream; two frames in flight, every copy inside the timed region."""
+        encoder consumes on the copy-out stream; three frames in flight, every copy inside the timed region."""
         k = i % RING
-        sl = slots[i & 1]
-        with torch.cuda.stream(s_in):
-            s_in.wait_event(sl.ev_cmp)                                                     # the kernels that read this slot's inputs are done
-            fill_yuv(sl.in_t, h_y[k], h_cb[k], h_cr[k], False)                             # H2D: Y + Cb + Cr
-            sl.ev_in.record(s_in)
+        sl = slots[i % 3]
+        finish_slot(sl)                                                                    # frame i - 3 (same slot) is completely out
+        s_in.wait_event(sl.ev_cmp)                                                         # the kernels that read this slot's inputs are done
+        S.yuv_picture_upload(sl.in_yuv, hp[k][0], W, hp[k][1], W // 2, hp[k][2], W // 2, 1, s_in.cuda_stream)    # H2D: Y + Cb + Cr
+        sl.ev_in.record(s_in)
         tstream.wait_event(sl.ev_in)
         tstream.wait_event(sl.ev_out)                                                      # this slot's previous results have left the device
-        yint = sl.in_t[0][PAD:, PAD:]
-        sl.pa.build_from_device(yint.data_ptr(), sl.in_t[0].shape[1], stream)              # pad + decimate on the device
+        sl.pa.build_from_device(sl.p["yint"], sl.in_t[0].shape[1], stream)                 # pad + decimate on the device
         pipeline(i, sl.pa, sl.in_yuv, sl, tstream)
+        S.tq_pack_coeffs_dev(sl.coeff, p_tq, sl.p["nz"], n_tq, sl.p["stream"], sl.cap, sl.p["off"], stream)
         sl.ev_cmp.record(tstream)
-        with torch.cuda.stream(s_out):
-            s_out.wait_event(sl.ev_cmp)
-            for hb, db in zip(sl.host_out, sl.dev_out):                                    # D2H: ME results, coefficients, nz, SAO stats, OIS
-                hb.copy_(db, non_blocking=True)
-            sl.ev_out.record(s_out)
+        s_small.wait_event(sl.ev_cmp)
+        S.copy_async(sl.p["h_small"], sl.p["small"], sl.d_small.numel(), True, s_small.cuda_stream)    # D2H: ME results, TU offsets, nz, SAO stats, OIS
+        sl.ev_small.record(s_small)
+        sl.pending = True
+        finish_slot(slots[(i + 1) % 3])                                                    # frame i - 2: its offsets arrived long ago, its stream goes out now
 
     def barrier():
         torch.cuda.synchronize()
@@ -361,10 +399,15 @@ def run_b200(args):
 
     for i in range(args.warmup):
         step_e2e(i)
+    for sl in slots[:3]:
+        finish_slot(sl)
     barrier()
     w0 = time.perf_counter()
+    d2h_bytes.clear()
     for i in range(args.steps):
         step_e2e(args.warmup + i)
+    for q in range(1, 4):
+        finish_slot(slots[(args.warmup + args.steps - 1 + q) % 3])
     barrier()
     e2e_s = time.perf_counter() - w0
 
@@ -384,7 +427,7 @@ def run_b200(args):
                          "frac_of_hbm_peak": (alg[n] / (np.mean(v) * 1e-3) / 1e9 / peak) if v else None} for n, v in stage_ms.items()}
         k_avg_s = float(np.mean(stage_ms[dom])) * 1e-3
         h2d = W * H * 3 // 2
-        d2h = int(sum(t.numel() * t.element_size() for t in slots[0].dev_out))
+        d2h = int(np.mean(d2h_bytes))
         out = {
             "metric": METRIC, "value": ctus / (ms * 1e-3), "unit": "CTU/s", "fps": ctus / (ms * 1e-3) / N_LCU,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -401,6 +444,8 @@ def run_b200(args):
                          "frac": alg[dom] / k_avg_s / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg[dom], "avg_launch_ms": k_avg_s * 1e3},
             "stages": per_stage,
+            "me_ms_by_temporal_layer": {str(tl): float(np.mean([t for j, t in enumerate(serial_ms["me"]) if wl.tl(args.warmup + j) == tl])) for tl in sorted(set(TL_PATTERN))
+                                        if any(wl.tl(args.warmup + j) == tl for j in range(len(serial_ms["me"])))},
             "stages_serial": {n: {"launch_ms_avg": float(np.mean(v)) if v else None, "frac_of_hbm_peak": (alg[n] / (np.mean(v) * 1e-3) / 1e9 / peak) if v else None}
                               for n, v in serial_ms.items()},
         }

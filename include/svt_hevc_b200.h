@@ -280,6 +280,15 @@ int svtb200_tq_batch16_dev(const svtb200_yuv_picture *src, const svtb200_yuv_pic
                            const svtb200_coeff_picture *coeff, const svtb200_tq_job *jobs_dev, int n_jobs, uint32_t *nz_counts_dev,
                            void *cuda_stream);
 
+/* Coefficient hand-off to the entropy coder.  EntropyCodingKernel reads coeffSamplesTB only for TUs whose cbf is set
+ * (EbCodingLoop.c:745,767-803; EbEntropyCoding.c), so the coefficient planes of svtb200_tq_batch*_dev are packed on the device into one dense
+ * stream -- TU after TU in job order, size x size int16 row-major, TUs with nz_counts == 0 skipped -- and only that stream crosses PCIe:
+ *   offsets_dev[j]       first element of job j in the stream (meaningful when nz_counts[j] != 0)
+ *   offsets_dev[n_jobs]  total elements; when it exceeds stream_capacity the stream is incomplete (TUs that did not fit are skipped)
+ * offsets_dev holds n_jobs + 1 entries. */
+int svtb200_tq_pack_coeffs_dev(const svtb200_coeff_picture *coeff_dev, const svtb200_tq_job *jobs_dev, const uint32_t *nz_counts_dev, int n_jobs,
+                               int16_t *stream_dev, uint32_t stream_capacity, uint32_t *offsets_dev, void *cuda_stream);
+
 /* Leaf entry points (reference prototypes; host pointers). */
 /* EstimateTransform, Codec/EbTransforms.c:3268 (EB_TRANSFORM_FUNC tables EbTransforms.h:339-472) */
 int svtb200_EstimateTransform(const int16_t *residualBuffer, uint32_t residualStride, int16_t *coeffBuffer, uint32_t coeffStride,
@@ -498,6 +507,12 @@ int svtb200_pa_picture_upload(const svtb200_pa_picture *dev, const uint8_t *host
 /* same, source already in device memory (unpadded, pitch dev_stride) */
 int svtb200_pa_picture_build_dev(const svtb200_pa_picture *dev, const uint8_t *dev_luma, uint32_t dev_stride, void *cuda_stream);
 int svtb200_pa_picture_download(const svtb200_pa_picture *dev, const svtb200_pa_picture *host_out);
+/* Transfers of the picture-level binding: the interiors of a device Y/Cb/Cr picture from UNPADDED host planes (strides in
+ * samples, 1 or 2 bytes per sample), and a plain asynchronous copy for job lists / results (pinned host memory on the host side). */
+int svtb200_yuv_picture_upload(const svtb200_yuv_picture *dev, const void *host_y, uint32_t host_y_stride, const void *host_cb,
+                               uint32_t host_cb_stride, const void *host_cr, uint32_t host_cr_stride, uint32_t bytes_per_sample,
+                               void *cuda_stream);
+int svtb200_copy_async(void *dst, const void *src, size_t bytes, int device_to_host, void *cuda_stream);
 void svtb200_pa_picture_destroy(svtb200_pa_picture *dev);
 
 #ifdef __cplusplus

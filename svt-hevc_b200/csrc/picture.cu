@@ -107,6 +107,34 @@ int svtb200_pa_picture_upload(const svtb200_pa_picture *dev, const uint8_t *host
     return build_planes(dev, st);
 }
 
+int svtb200_yuv_picture_upload(const svtb200_yuv_picture *dev, const void *host_y, uint32_t host_y_stride, const void *host_cb, uint32_t host_cb_stride,
+                               const void *host_cr, uint32_t host_cr_stride, uint32_t bytes_per_sample, void *cuda_stream)
+{
+    if (!dev || !host_y || !host_cb || !host_cr || (bytes_per_sample != 1 && bytes_per_sample != 2)) { set_error("yuv_picture_upload: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    int rc = ensure_device();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const svtb200_plane *pl[3] = {&dev->y, &dev->cb, &dev->cr};
+    const void *h[3] = {host_y, host_cb, host_cr};
+    const uint32_t hs[3] = {host_y_stride, host_cb_stride, host_cr_stride};
+    const size_t b = bytes_per_sample;
+    for (int k = 0; k < 3; ++k) {
+        if (!pl[k]->buf) { set_error("yuv_picture_upload: null device plane"); return SVTB200_ERR_BAD_ARG; }
+        SVTB200_CUDA_TRY(cudaMemcpy2DAsync(pl[k]->buf + ((size_t)pl[k]->origin_y * pl[k]->stride + pl[k]->origin_x) * b, pl[k]->stride * b, h[k], hs[k] * b,
+                                           pl[k]->width * b, pl[k]->height, cudaMemcpyHostToDevice, st));
+    }
+    return SVTB200_OK;
+}
+
+int svtb200_copy_async(void *dst, const void *src, size_t bytes, int device_to_host, void *cuda_stream)
+{
+    if ((!dst || !src) && bytes) { set_error("copy_async: null pointer"); return SVTB200_ERR_BAD_ARG; }
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (bytes) SVTB200_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, device_to_host ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice, (cudaStream_t)cuda_stream));
+    return SVTB200_OK;
+}
+
 int svtb200_pa_picture_download(const svtb200_pa_picture *dev, const svtb200_pa_picture *host)
 {
     if (!dev || !host) { set_error("pa_picture_download: bad argument"); return SVTB200_ERR_BAD_ARG; }

@@ -442,6 +442,55 @@ __global__ void __launch_bounds__(TQ_NT) tq_batch_kernel(const __grid_constant__
     }
 }
 
+
+// ---- coefficient hand-off: only coded TUs cross PCIe -------------------------------------------------------------------
+// The entropy coder reads coeffSamplesTB of TUs whose cbf is set (EbCodingLoop.c:745, EbEntropyCoding.c) and nothing else, so the coefficient
+// planes are packed on the device into one dense stream: TU after TU in job order, size x size int16 row-major, TUs with nz == 0 skipped.
+// offsets[j] = first element of job j in the stream, offsets[n_jobs] = total elements.
+constexpr int PK_SCAN_NT = 1024;
+__global__ void __launch_bounds__(PK_SCAN_NT) tq_pack_scan_kernel(const svtb200_tq_job *jobs, const uint32_t *nz, int n_jobs, uint32_t *offsets)
+{
+    __shared__ uint32_t s_part[PK_SCAN_NT / 32];
+    const int per = (n_jobs + PK_SCAN_NT - 1) / PK_SCAN_NT, j0 = threadIdx.x * per, j1 = min(n_jobs, j0 + per);
+    uint32_t local = 0;
+    for (int j = j0; j < j1; ++j) local += nz[j] ? (uint32_t)jobs[j].size * jobs[j].size : 0u;
+    // exclusive scan of the per-thread sums: warp scan, then scan of the 32 warp totals
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_part[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t v = s_part[lane], w = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+        s_part[lane] = w - v;      // exclusive
+        if (lane == 31) offsets[n_jobs] = w;
+    }
+    __syncthreads();
+    uint32_t run = s_part[wid] + incl - local;
+    for (int j = j0; j < j1; ++j) { offsets[j] = run; run += nz[j] ? (uint32_t)jobs[j].size * jobs[j].size : 0u; }
+}
+
+__global__ void __launch_bounds__(128) tq_pack_copy_kernel(const __grid_constant__ TqArgs A, const uint32_t *offsets, int16_t *stream, uint32_t capacity)
+{
+    const int j = blockIdx.x;
+    if (j >= A.n_jobs || A.nz[j] == 0) return;
+    const svtb200_tq_job t = A.jobs[j];
+    const int N = t.size, cs = A.cstride[t.plane];
+    const uint32_t off = offsets[j];
+    if (off + (uint32_t)(N * N) > capacity) return;      // the caller sees offsets[n_jobs] > capacity
+    const int16_t *co = A.coeff[t.plane] + (size_t)t.y * cs + t.x;
+    int16_t *o = stream + off;
+    if (((((uintptr_t)co | (uintptr_t)(cs * 2)) & 7) == 0) && (((uintptr_t)o & 7) == 0)) {      // 4 coefficients per access
+        const int w4 = N >> 2;
+        for (int i = threadIdx.x; i < N * w4; i += 128) { const int y = i / w4, x = (i - y * w4) * 4; *(uint2 *)(o + y * N + x) = *(const uint2 *)(co + (size_t)y * cs + x); }
+    } else {
+        for (int i = threadIdx.x; i < N * N; i += 128) { const int y = i / N, x = i - y * N; o[i] = co[(size_t)y * cs + x]; }
+    }
+}
+
 // leaf kernels: mode 0 forward (EstimateTransform), 1 QiQ with explicit parameters, 2 inverse
 struct LeafArgs {
     const int16_t *in; int16_t *out, *out2; uint32_t *nz;
@@ -702,6 +751,28 @@ int svtb200_EncodeInvTransform(const int16_t *coeffBuffer, uint32_t coeffStride,
     LeafArgs L{};
     L.istride = (int)coeffStride; L.ostride = (int)reconStride; L.N = (int)N; L.bit_inc = (int)bitIncrement; L.dst = dstTransformFlag; L.mode = 2;
     return tq_leaf(L, coeffBuffer, (size_t)(N - 1) * coeffStride + N, reconBuffer, (size_t)(N - 1) * reconStride + N, nullptr, nullptr);
+}
+
+
+int svtb200_tq_pack_coeffs_dev(const svtb200_coeff_picture *coeff_dev, const svtb200_tq_job *jobs_dev, const uint32_t *nz_counts_dev, int n_jobs,
+                               int16_t *stream_dev, uint32_t stream_capacity, uint32_t *offsets_dev, void *cuda_stream)
+{
+    if (!coeff_dev || (!jobs_dev && n_jobs) || !nz_counts_dev || n_jobs < 0 || !stream_dev || !offsets_dev) { set_error("tq_pack_coeffs_dev: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    int rc = ensure_device();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    tq_pack_scan_kernel<<<1, PK_SCAN_NT, 0, st>>>(jobs_dev, nz_counts_dev, n_jobs, offsets_dev);
+    SVTB200_COUNT_LAUNCH();
+    if (n_jobs) {
+        TqArgs A;
+        memset(&A, 0, sizeof A);
+        for (int k = 0; k < 3; ++k) { A.coeff[k] = coeff_dev->buf[k]; A.cstride[k] = (int)coeff_dev->stride[k]; }
+        A.jobs = jobs_dev; A.n_jobs = n_jobs; A.nz = (uint32_t *)nz_counts_dev;
+        tq_pack_copy_kernel<<<n_jobs, 128, 0, st>>>(A, offsets_dev, stream_dev, stream_capacity);
+        SVTB200_COUNT_LAUNCH();
+    }
+    SVTB200_CUDA_TRY(cudaGetLastError());
+    return SVTB200_OK;
 }
 
 }  // extern "C"

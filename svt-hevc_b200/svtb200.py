@@ -454,8 +454,13 @@ def make_yuv_struct(ptrs, strides, pad, width, height):
     return s
 
 
+def yuv_struct_array(ref_structs):
+    """a C array of svtb200_yuv_picture descriptors (build once, reuse per call)"""
+    return (YuvPicture * len(ref_structs))(*ref_structs)
+
+
 def mc_batch_dev(ref_structs, jobs_ptr, n_jobs, dst_struct, stream=0):
-    arr = (YuvPicture * len(ref_structs))(*ref_structs)
+    arr = ref_structs if isinstance(ref_structs, C.Array) else yuv_struct_array(ref_structs)
     check(lib().svtb200_mc_batch_dev(arr, C.c_int(len(ref_structs)), C.c_void_p(jobs_ptr), C.c_int(n_jobs), C.byref(dst_struct), C.c_void_p(stream)))
 
 
@@ -569,3 +574,18 @@ def ois_picture(cfg, src_plane, me_results, cap):
 def ois_picture_dev(cfg, src_plane_dev, me_ptr, total_ptr, cand_ptr, cap, stream=0):
     check(lib().svtb200_ois_picture_dev(C.byref(cfg), C.byref(src_plane_dev), C.c_void_p(me_ptr), C.c_void_p(total_ptr), C.c_void_p(cand_ptr), C.c_uint32(cap),
                                         C.c_void_p(stream)))
+
+
+def tq_pack_coeffs_dev(coeff, jobs_ptr, nz_ptr, n_jobs, stream_ptr, capacity, offsets_ptr, stream=0):
+    """coeff: CoeffPicture with device pointers; packs the coefficients of the TUs with nz != 0 into one dense int16 stream"""
+    check(lib().svtb200_tq_pack_coeffs_dev(C.byref(coeff), C.c_void_p(jobs_ptr), C.c_void_p(nz_ptr), C.c_int(n_jobs), C.c_void_p(stream_ptr), C.c_uint32(capacity),
+                                           C.c_void_p(offsets_ptr), C.c_void_p(stream)))
+
+
+def yuv_picture_upload(dev_struct, y_ptr, y_stride, cb_ptr, cb_stride, cr_ptr, cr_stride, bps=1, stream=0):
+    check(lib().svtb200_yuv_picture_upload(C.byref(dev_struct), C.c_void_p(y_ptr), C.c_uint32(y_stride), C.c_void_p(cb_ptr), C.c_uint32(cb_stride),
+                                           C.c_void_p(cr_ptr), C.c_uint32(cr_stride), C.c_uint32(bps), C.c_void_p(stream)))
+
+
+def copy_async(dst_ptr, src_ptr, nbytes, device_to_host, stream=0):
+    check(lib().svtb200_copy_async(C.c_void_p(dst_ptr), C.c_void_p(src_ptr), C.c_size_t(nbytes), C.c_int(1 if device_to_host else 0), C.c_void_p(stream)))

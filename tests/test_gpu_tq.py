@@ -124,3 +124,43 @@ def test_tq_batch16_cuda_vs_oracle(case):
     assert np.array_equal(nz2, nz)
     for a, b in zip(pred.interior(), recon.interior()):
         assert np.array_equal(a, b)
+
+
+def test_pack_coeffs_stream_matches_planes():
+    """the dense coefficient stream holds exactly the TUs with nz != 0, in job order; offsets are an exclusive scan"""
+    import torch
+    w, h = 256, 192
+    jobs = make_tq_jobs(w, h, seed=3, shapes=(0,), flags=(0,))
+    rng = np.random.default_rng(4)
+    planes = [rng.integers(-300, 300, (h, w)).astype(np.int16), rng.integers(-300, 300, (h // 2, w // 2)).astype(np.int16),
+              rng.integers(-300, 300, (h // 2, w // 2)).astype(np.int16)]
+    nz = (rng.random(len(jobs)) < 0.35).astype(np.uint32) * rng.integers(1, 50, len(jobs)).astype(np.uint32)
+    dev = torch.device("cuda", 0)
+    d_planes = [torch.from_numpy(p).to(dev) for p in planes]
+    coeff = S.CoeffPicture()
+    for k in range(3):
+        coeff.buf[k] = d_planes[k].data_ptr(); coeff.stride[k] = planes[k].shape[1]
+    d_jobs = torch.from_numpy(jobs.view(np.uint8)).to(dev)
+    d_nz = torch.from_numpy(nz.view(np.int32)).to(dev)
+    cap = int(sum(int(j["size"]) ** 2 for j in jobs))
+    d_stream = torch.full((cap,), -1, dtype=torch.int16, device=dev)
+    d_off = torch.zeros(len(jobs) + 1, dtype=torch.int32, device=dev)
+    S.tq_pack_coeffs_dev(coeff, d_jobs.data_ptr(), d_nz.data_ptr(), len(jobs), d_stream.data_ptr(), cap, d_off.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    off = d_off.cpu().numpy().view(np.uint32)
+    stream = d_stream.cpu().numpy()
+    sizes = np.array([int(j["size"]) ** 2 if n else 0 for j, n in zip(jobs, nz)], np.uint32)
+    assert np.array_equal(off[:-1], np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint32)) and off[-1] == sizes.sum()
+    for j, n in zip(range(len(jobs)), nz):
+        if not n:
+            continue
+        t = jobs[j]
+        N = int(t["size"])
+        tu = planes[int(t["plane"])][int(t["y"]):int(t["y"]) + N, int(t["x"]):int(t["x"]) + N]
+        assert np.array_equal(stream[off[j]:off[j] + N * N].reshape(N, N), tu), j
+    assert np.all(stream[off[-1]:] == -1)
+    # a stream that is too small: the total still tells the caller, nothing is written past the capacity
+    d_small = torch.full((1000,), -1, dtype=torch.int16, device=dev)
+    S.tq_pack_coeffs_dev(coeff, d_jobs.data_ptr(), d_nz.data_ptr(), len(jobs), d_small.data_ptr(), 1000, d_off.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert int(d_off.cpu().numpy().view(np.uint32)[-1]) == int(sizes.sum())
