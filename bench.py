@@ -352,12 +352,13 @@ def run_b200(args):
         s_in.wait_event(sl.ev_cmp)                                                         # the kernels that read this slot's inputs are done
         S.yuv_picture_upload(sl.in_yuv, hp[k][0], W, hp[k][1], W // 2, hp[k][2], W // 2, 1, s_in.cuda_stream)    # H2D: Y + Cb + Cr
         sl.ev_in.record(s_in)
-        tstream.wait_event(sl.ev_in)
-        tstream.wait_event(sl.ev_out)                                                      # this slot's previous results have left the device
-        sl.pa.build_from_device(sl.p["yint"], sl.in_t[0].shape[1], stream)                 # pad + decimate on the device
-        pipeline(i, sl.pa, sl.in_yuv, sl, tstream)
-        S.tq_pack_coeffs_dev(sl.coeff, p_tq, sl.p["nz"], n_tq, sl.p["stream"], sl.cap, sl.p["off"], stream)
-        sl.ev_cmp.record(tstream)
+        cs = cstreams[i % len(cstreams)]                                                   # consecutive frames alternate compute streams, as in the resident loop
+        cs.wait_event(sl.ev_in)
+        cs.wait_event(sl.ev_out)                                                           # this slot's previous results have left the device
+        sl.pa.build_from_device(sl.p["yint"], sl.in_t[0].shape[1], cs.cuda_stream)         # pad + decimate on the device
+        pipeline(i, sl.pa, sl.in_yuv, sl, cs)
+        S.tq_pack_coeffs_dev(sl.coeff, p_tq, sl.p["nz"], n_tq, sl.p["stream"], sl.cap, sl.p["off"], cs.cuda_stream)
+        sl.ev_cmp.record(cs)
         s_small.wait_event(sl.ev_cmp)
         S.copy_async(sl.p["h_small"], sl.p["small"], sl.d_small.numel(), True, s_small.cuda_stream)    # D2H: ME results, TU offsets, nz, SAO stats, OIS
         sl.ev_small.record(s_small)
