@@ -398,6 +398,30 @@ def run_b200(args):
     barrier()
     serial_ms = {n: [a.elapsed_time(b) for a, b in ev1[n]] for n in names}
 
+    # what the host link gives this process (pinned buffers, one direction at a time and both at once): the e2e figure is read against it
+    def pcie_probe(nbytes=64 << 20, reps=4):
+        hb, hb2 = torch.empty(nbytes, dtype=torch.uint8).pin_memory(), torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        db, db2 = torch.empty(nbytes, dtype=torch.uint8, device=dev), torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        res = {}
+        for name, fn in (("h2d_gbs", lambda: db.copy_(hb, non_blocking=True)), ("d2h_gbs", lambda: hb2.copy_(db2, non_blocking=True))):
+            fn(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record(); torch.cuda.synchronize()
+            res[name] = nbytes * reps / (a.elapsed_time(b) * 1e-3) / 1e9
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            with torch.cuda.stream(s_in):
+                db.copy_(hb, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                hb2.copy_(db2, non_blocking=True)
+        torch.cuda.synchronize()
+        res["duplex_each_gbs"] = nbytes * reps / (time.perf_counter() - t0) / 1e9
+        return res
+    pcie = pcie_probe()
+
     for i in range(args.warmup):
         step_e2e(i)
     for sl in slots[:3]:
@@ -436,7 +460,7 @@ def run_b200(args):
             "config": {"workload": WORKLOAD, "stages": STAGES,
                        "l2": "16-frame ring of resident 4K pictures (> 400 MB of planes) > 126 MB L2", "parallelism": f"{args.streams} compute stream(s) per GPU, {world} GPU(s)"},
             "e2e": {"value": ctus / (e2e_ms * 1e-3), "unit": "CTU/s", "fps": ctus / (e2e_ms * 1e-3) / N_LCU,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_link": pcie},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"kernel": {"me": "me_picture_kernel", "ois": "ois_picture_kernel", "mc": "mc_batch_kernel", "tq": "tq_batch_kernel", "dlf": "dlf_pass_kernel",

@@ -81,6 +81,18 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
     }
     return v;
 }
+// division of small non-negative n by a loop-invariant d: a shift when d is a power of two (every size the batch kernel sees), else a
+// multiply-high with ceil(2^32 / d) (exact for n * d < 2^32 / d; the leaf entry points accept any multiple of 4)
+struct SmallDiv { uint32_t m; int sh; };
+__device__ __forceinline__ SmallDiv mk_div(int d)
+{
+    SmallDiv q;
+    q.sh = 31 - __clz(d);
+    q.m = (d & (d - 1)) ? 0xFFFFFFFFu / (uint32_t)d + 1u : 0u;
+    return q;
+}
+__device__ __forceinline__ int udiv(int n, const SmallDiv &q) { return q.m ? (int)__umulhi((uint32_t)n, q.m) : n >> q.sh; }
+
 // ---- window staging ------------------------------------------------------------------------
 // Copies `rows` rows of `wbytes` bytes starting at global address g (row pitch gstride) into shared memory with row pitch
 // wp = win_pitch(wbytes) (s_win 16-byte aligned).  The global byte misalignment `a` is preserved: window byte x lives at

@@ -7,13 +7,15 @@
 //   EncodeUniPredInterpolation / EncodeBiPredInterpolation (Codec/EbMcp.c:175,562), EncodePassInterPrediction
 //   position clamp (Codec/EbInterPrediction.c:794-808)
 //
-// Design: one CTA (128 threads) per <= 32x32 luma tile of a PU (+ its two 16x16 chroma tiles).  For each plane and
-// list the (tile + taps - 1)^2 reference window is staged once in shared memory with coalesced word loads, then
-//   H pass : 4 outputs per thread from funnel-shifted words with DP4A (u8 x s8), s16 rows in shared memory,
-//   V pass : a 2x2 output quad per thread with DP2A on PRMT-built vertical s16 pairs.
-// Both passes ALWAYS run; integer phases use the identity taps {..,64,..}.  That is bit-exact with the reference's
+// Design: one CTA (128 threads) per PU, walked in <= 32x32 luma tiles (+ the two 16x16 chroma tiles).  Per tile ALL reference windows
+// (luma / Cb / Cr x list 0 / list 1, (tile + taps - 1)^2 each) are staged in shared memory back to back with coalesced 128-bit loads, then
+//   H pass : every window, flattened over the CTA; 4 outputs per thread from funnel-shifted words with DP4A (u8 x s8), s16 rows in smem,
+//   V pass : a 2x2 output quad per thread with DP2A on PRMT-built vertical s16 pairs, both lists in registers, final rounding /
+//            BiPredClipping fused (three barriers per tile in total).
+// Interpolated planes ALWAYS run both passes; integer phases use the identity taps {..,64,..}.  That is bit-exact with the reference's
 // 16 (64) specialised functions because their 14-bit intermediates differ from the two-pass value only by an exact
-// factor of 64 that the final shift removes (see oracle/port/mc_port.c and tests/test_gpu_mc.py, every phase pair).
+// factor of 64 that the final shift removes (see oracle/port/mc_port.c and tests/test_gpu_mc.py, every phase pair).  Planes whose used
+// lists are all at integer positions are copied / averaged straight from global memory.
 // HBM traffic per CTU is the algorithmic minimum + the 7-sample halo (served by L2 between neighbouring CTAs).
 #include "common.cuh"
 
@@ -60,35 +62,70 @@ __device__ __forceinline__ int dp2a_hi_ss(uint32_t a_s16x2, uint32_t b_s8x4, int
 }
 __device__ __forceinline__ uint32_t pack4(const int8_t *t) { return (uint8_t)t[0] | ((uint32_t)(uint8_t)t[1] << 8) | ((uint32_t)(uint8_t)t[2] << 16) | ((uint32_t)(uint8_t)t[3] << 24); }
 
-// One plane, one list: window -> H pass -> V pass.  TAPS = 8 (luma) or 4 (chroma).
-//   ref   : integer sample of the tile's top-left in the reference plane
-//   out8  : != nullptr -> uni-pred, final samples written to global memory (pitch ostride)
-//   raw   : != nullptr -> bi-pred, 14-bit intermediates written to shared memory (pitch tw)
-// HBD: 16-bit samples (10-bit video).  ref / out8 are byte pointers, rstride / ostride are in SAMPLES.  The same two-pass
-// form is exact there as well: first pass (S - 32768) >> 2 kept in 16 bits like LumaInterpolationFilterPos*OutRaw16bit, second pass
-// (S2 + 524800) >> 10 (uni) or S2 >> 6 (bi); with identity taps these reduce to the reference's 1-D (S + 32) >> 6, (S - 32768) >> 2 and copy
-// forms (Codec/EbDefinitions.h:1041-1059).
+// ---- staged three-phase tile predictor -------------------------------------------------------------------------------------
+// A tile has up to six reference windows ("units"): luma L0/L1 (8 taps) and Cb/Cr x L0/L1 (4 taps).  All windows of a tile are
+// fetched back to back (one exposed HBM/L2 latency), then ONE barrier, the H passes of every unit flattened over the CTA, ONE
+// barrier, and the V passes: a thread produces the same 2x2 output quad of both lists and finishes uni-pred rounding or
+// BiPredClipping in registers (no raw 14-bit buffers, no third pass).  Planes whose used lists all have integer phases skip the
+// staging altogether (copy / rounded average straight from global memory).
+// HBD: 16-bit samples (10-bit video).  Pointers are byte pointers, strides are in SAMPLES.  The two-pass form is exact there as
+// well: first pass (S - 32768) >> 2 kept in 16 bits like LumaInterpolationFilterPos*OutRaw16bit, second pass (S2 + 524800) >> 10 (uni) or
+// S2 >> 6 (bi); with identity taps these reduce to the reference's 1-D (S + 32) >> 6, (S - 32768) >> 2 and copy forms (Codec/EbDefinitions.h:1041-1059).
+struct McUnit {
+    const uint8_t *ref;   // integer sample of the tile's top-left in the reference plane (byte pointer)
+    int rstride;          // samples
+};
+struct McClass {          // the units of one plane class (luma: np = 1; chroma: np = 2, same geometry and phases)
+    McUnit u[2][2];       // [plane][list slot]; slot 0 = the only list of a uni-pred PU
+    uint8_t *out[2];
+    int ostride[2];
+    int fx[2], fy[2];     // phases per list slot
+    int np, tw, th;
+    bool interp;
+};
+
 template <int TAPS, bool HBD>
-__device__ void interp_tile(const uint8_t *ref, int rstride, int fx, int fy, int tw, int th, uint8_t *s_win, int16_t *s_tmp,
-                            uint8_t *out8, int ostride, int16_t *raw)
+__device__ __forceinline__ void mc_stage_load(const McClass &c, int nl, uint8_t *s_win, int win_unit, int *s_a)
 {
     constexpr int HALF = TAPS / 2 - 1, BPS = HBD ? 2 : 1;
-    const int wbytes = (tw + TAPS - 1) * BPS, wrows = th + TAPS - 1, wp = win_pitch(wbytes);
-    __syncthreads();   // previous users of s_win / s_tmp are done
-    const int a = load_window_t<MC_NT>(s_win, wp, ref - (HALF * rstride + HALF) * BPS, rstride * BPS, wbytes, wrows);
-    __syncthreads();
-    const int8_t *tx = TAPS == 8 ? c_luma_taps[fx] : c_chroma_taps[fx];
-    const int8_t *ty = TAPS == 8 ? c_luma_taps[fy] : c_chroma_taps[fy];
-    const uint32_t cx0 = pack4(tx), cx1 = TAPS == 8 ? pack4(tx + 4) : 0u;
-    const uint32_t cy0 = pack4(ty), cy1 = TAPS == 8 ? pack4(ty + 4) : 0u;
-    // ---- H pass: s_tmp[r][x], r in [0, wrows), pitch tw (s16) ----
-    if (HBD) {
-        // two adjacent outputs per thread from TAPS/2 + 1 words of s16 pairs; DP2A on (sample, sample) x (tap, tap)
-        const int ppr = tw >> 1;
-        for (int i = threadIdx.x; i < wrows * ppr; i += MC_NT) {
-            const int r = i / ppr, x0 = (i - r * ppr) * 2;
-            const int c0 = (a >> 1) + x0, par = c0 & 1;
-            const uint32_t *row = (const uint32_t *)(s_win + r * wp) + (c0 >> 1);
+    const int wbytes = (c.tw + TAPS - 1) * BPS, wrows = c.th + TAPS - 1, wp = win_pitch(wbytes);
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int l = 0; l < 2; ++l) {
+            if (p >= c.np || l >= nl) continue;
+            const int a = load_window_t<MC_NT>(s_win + (p * 2 + l) * win_unit, wp, c.u[p][l].ref - (HALF * c.u[p][l].rstride + HALF) * BPS,
+                                               c.u[p][l].rstride * BPS, wbytes, wrows);
+            if (threadIdx.x == 0) s_a[p * 2 + l] = a;
+        }
+}
+
+// H pass of every unit of the class: s_tmp[unit][r][x], r in [0, wrows), pitch tw (s16)
+template <int TAPS, bool HBD>
+__device__ __forceinline__ void mc_stage_h(const McClass &c, int nl, const uint8_t *s_win, int win_unit, const int *s_a, int16_t *s_tmp, int tmp_unit)
+{
+    constexpr int BPS = HBD ? 2 : 1;
+    const int wbytes = (c.tw + TAPS - 1) * BPS, wrows = c.th + TAPS - 1, wp = win_pitch(wbytes), tw = c.tw;
+    const int ipr = HBD ? tw >> 1 : tw >> 2, per_unit = wrows * ipr, total = c.np * nl * per_unit;
+    const SmallDiv d_ipr = mk_div(ipr);
+    uint32_t kx0[2], kx1[2];
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+        const int8_t *tx = TAPS == 8 ? c_luma_taps[c.fx[l] & 3] : c_chroma_taps[c.fx[l] & 7];
+        kx0[l] = pack4(tx); kx1[l] = TAPS == 8 ? pack4(tx + 4) : 0u;
+    }
+    for (int i = threadIdx.x; i < total; i += MC_NT) {
+        const int rr = udiv(i, d_ipr), g = i - rr * ipr;                                                  // row over all units, item in the row
+        const int uu = (rr >= wrows) + (rr >= 2 * wrows) + (rr >= 3 * wrows), r = rr - uu * wrows;     // <= 4 units per class
+        const int l = nl == 2 ? (uu & 1) : 0, slot = (nl == 2 ? (uu >> 1) : uu) * 2 + l;
+        const int a = s_a[slot];
+        const uint8_t *rowb = s_win + slot * win_unit + r * wp;
+        int16_t *trow = s_tmp + slot * tmp_unit + r * tw;
+        const uint32_t cx0 = l ? kx0[1] : kx0[0], cx1 = l ? kx1[1] : kx1[0];
+        if (HBD) {
+            // two adjacent outputs per thread from TAPS/2 + 1 words of s16 pairs; DP2A on (sample, sample) x (tap, tap)
+            const int x0 = g * 2, c0 = (a >> 1) + x0, par = c0 & 1;
+            const uint32_t *row = (const uint32_t *)rowb + (c0 >> 1);
             uint32_t w[TAPS / 2 + 1];
 #pragma unroll
             for (int k = 0; k < TAPS / 2 + 1; ++k) w[k] = row[k];
@@ -101,206 +138,306 @@ __device__ void interp_tile(const uint8_t *ref, int rstride, int fx, int fy, int
                 if ((k & 1) == 0) { o0 = dp2a_lo_ss(p0, cc, o0); o1 = dp2a_lo_ss(p1, cc, o1); }
                 else { o0 = dp2a_hi_ss(p0, cc, o0); o1 = dp2a_hi_ss(p1, cc, o1); }
             }
-            *(uint32_t *)(s_tmp + r * tw + x0) = (uint32_t)(uint16_t)((o0 - 32768) >> 2) | ((uint32_t)(uint16_t)((o1 - 32768) >> 2) << 16);
-        }
-    }
-    const int gpr = HBD ? 0 : tw >> 2;
-    for (int i = threadIdx.x; i < wrows * gpr; i += MC_NT) {
-        const int r = i / gpr, x0 = (i - r * gpr) * 4;
-        const uint32_t *row = (const uint32_t *)(s_win + r * wp);
-        const int c0 = a + x0, wi = c0 >> 2, sh = (c0 & 3) * 8;
-        uint32_t w[TAPS == 8 ? 4 : 3];
-#pragma unroll
-        for (int k = 0; k < (TAPS == 8 ? 4 : 3); ++k) w[k] = row[wi + k];
-        int o[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            // bytes c0+k .. c0+k+TAPS-1
-            const int s0 = sh + 8 * k;                       // bit offset of byte k inside (w[0],w[1])
-            const uint32_t lo = s0 < 32 ? __funnelshift_r(w[0], w[1], s0) : __funnelshift_r(w[1], w[2], s0 - 32);
-            int acc = dp4a_us(lo, cx0, 0);
-            if (TAPS == 8) {
-                const int s1 = s0 + 32;
-                const uint32_t hi = s1 < 64 ? __funnelshift_r(w[1], w[2], s1 - 32) : __funnelshift_r(w[2], w[3], s1 - 64);
-                acc = dp4a_us(hi, cx1, acc);
-            }
-            o[k] = acc;
-        }
-        uint32_t *t = (uint32_t *)(s_tmp + r * tw + x0);
-        t[0] = (uint32_t)(uint16_t)o[0] | ((uint32_t)(uint16_t)o[1] << 16);
-        t[1] = (uint32_t)(uint16_t)o[2] | ((uint32_t)(uint16_t)o[3] << 16);
-    }
-    __syncthreads();
-    // ---- V pass: 2x2 output quads ----
-    const int qpr = tw >> 1;
-    for (int i = threadIdx.x; i < (th >> 1) * qpr; i += MC_NT) {
-        const int qy = i / qpr, x = (i - qy * qpr) * 2, y = qy * 2;
-        const uint32_t *col = (const uint32_t *)(s_tmp + y * tw + x);
-        const int p4 = tw >> 1;   // words per row
-        uint32_t w[TAPS + 1];
-#pragma unroll
-        for (int k = 0; k < TAPS + 1; ++k) w[k] = col[k * p4];
-        int acc[2][2];   // [row][col]
-#pragma unroll
-        for (int ry = 0; ry < 2; ++ry) {
-            int a0 = 0, a1 = 0;
-#pragma unroll
-            for (int k = 0; k < TAPS; k += 2) {
-                const uint32_t lo = __byte_perm(w[ry + k], w[ry + k + 1], 0x5410);   // (x, row k), (x, row k+1)
-                const uint32_t hi = __byte_perm(w[ry + k], w[ry + k + 1], 0x7632);   // (x+1, ..)
-                const uint32_t cc = k < 4 ? cy0 : cy1;
-                if ((k & 2) == 0) { a0 = dp2a_lo_ss(lo, cc, a0); a1 = dp2a_lo_ss(hi, cc, a1); }
-                else { a0 = dp2a_hi_ss(lo, cc, a0); a1 = dp2a_hi_ss(hi, cc, a1); }
-            }
-            acc[ry][0] = a0; acc[ry][1] = a1;
-        }
-        if (out8 && HBD) {
-#pragma unroll
-            for (int ry = 0; ry < 2; ++ry) {
-                const int v0 = min(max((acc[ry][0] + 524800) >> 10, 0), 1023), v1 = min(max((acc[ry][1] + 524800) >> 10, 0), 1023);
-                uint16_t *o = (uint16_t *)out8 + (size_t)(y + ry) * ostride + x;
-                if (((uintptr_t)o & 3) == 0) *(uint32_t *)o = (uint32_t)v0 | ((uint32_t)v1 << 16);
-                else { o[0] = (uint16_t)v0; o[1] = (uint16_t)v1; }
-            }
-        } else if (out8) {
-#pragma unroll
-            for (int ry = 0; ry < 2; ++ry) {
-                const int v0 = min(max((acc[ry][0] + 2048) >> 12, 0), 255), v1 = min(max((acc[ry][1] + 2048) >> 12, 0), 255);
-                uint8_t *o = out8 + (size_t)(y + ry) * ostride + x;
-                if (((uintptr_t)o & 1) == 0) *(uint16_t *)o = (uint16_t)(v0 | (v1 << 8));
-                else { o[0] = (uint8_t)v0; o[1] = (uint8_t)v1; }
-            }
+            *(uint32_t *)(trow + x0) = (uint32_t)(uint16_t)((o0 - 32768) >> 2) | ((uint32_t)(uint16_t)((o1 - 32768) >> 2) << 16);
         } else {
+            // four outputs per thread from funnel-shifted words with DP4A (u8 x s8)
+            const int x0 = g * 4, c0 = a + x0, wi = c0 >> 2, sh = (c0 & 3) * 8;
+            const uint32_t *row = (const uint32_t *)rowb;
+            uint32_t w[TAPS == 8 ? 4 : 3];
 #pragma unroll
-            for (int ry = 0; ry < 2; ++ry)
-                *(uint32_t *)(raw + (y + ry) * tw + x) = (uint32_t)(uint16_t)(acc[ry][0] >> 6) | ((uint32_t)(uint16_t)(acc[ry][1] >> 6) << 16);
+            for (int k = 0; k < (TAPS == 8 ? 4 : 3); ++k) w[k] = row[wi + k];
+            int o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int s0 = sh + 8 * k;                       // bit offset of byte c0 + k inside (w[0], w[1])
+                const uint32_t lo = s0 < 32 ? __funnelshift_r(w[0], w[1], s0) : __funnelshift_r(w[1], w[2], s0 - 32);
+                int acc = dp4a_us(lo, cx0, 0);
+                if (TAPS == 8) {
+                    const int s1 = s0 + 32;
+                    const uint32_t hi = s1 < 64 ? __funnelshift_r(w[1], w[2], s1 - 32) : __funnelshift_r(w[2], w[3], s1 - 64);
+                    acc = dp4a_us(hi, cx1, acc);
+                }
+                o[k] = acc;
+            }
+            uint32_t *t = (uint32_t *)(trow + x0);
+            t[0] = (uint32_t)(uint16_t)o[0] | ((uint32_t)(uint16_t)o[1] << 16);
+            t[1] = (uint32_t)(uint16_t)o[2] | ((uint32_t)(uint16_t)o[3] << 16);
         }
     }
 }
 
-__device__ __forceinline__ int clampi(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
-
-// uni (rp1 == nullptr) or bi prediction of one tile of one plane
+// V pass: a 2x2 output quad per thread with DP2A on PRMT-built vertical s16 pairs, both lists, then the final rounding:
+//   uni 8-bit (S2 + 2048) >> 12, bi 8-bit BiPredClipping (C_DEFAULT/EbMcp_C.c:21; the -8192 biases of the reference's raw buffers cancel
+//   against Offset5): ((S2_0 >> 6) + (S2_1 >> 6) + 64) >> 7;  16-bit: (S2 + 524800) >> 10 / BiPredClipping16bit :3265 (l0 + l1 + 16400) >> 5
 template <int TAPS, bool HBD>
-__device__ void predict_tile(const uint8_t *rp0, int s0, int f0x, int f0y, const uint8_t *rp1, int s1, int f1x, int f1y, int tw, int th,
-                             uint8_t *out, int ostride, uint8_t *s_win, int16_t *s_tmp, int16_t *s_raw0, int16_t *s_raw1)
+__device__ __forceinline__ void mc_stage_v(const McClass &c, int nl, const int16_t *s_tmp, int tmp_unit)
 {
-    if (HBD && (f0x | f0y) == 0 && (!rp1 || (f1x | f1y) == 0)) {
-        // uniPredCopy16bit (C_DEFAULT/EbMcp_C.c:3827) / BiPredClippingOnTheFly16bit (Codec/EbMcp.c:847): (p0 + p1 + 1) >> 1
-        for (int i = threadIdx.x; i < th * (tw >> 1); i += MC_NT) {
-            const int y = i / (tw >> 1), x = (i - y * (tw >> 1)) * 2;
-            const uint16_t *a = (const uint16_t *)rp0 + (size_t)y * s0 + x;
-            uint32_t v = (uint32_t)a[0] | ((uint32_t)a[1] << 16);
-            if (rp1) { const uint16_t *b = (const uint16_t *)rp1 + (size_t)y * s1 + x; v = __vavgu2(v, (uint32_t)b[0] | ((uint32_t)b[1] << 16)); }
-            uint16_t *o = (uint16_t *)out + (size_t)y * ostride + x;
-            o[0] = (uint16_t)v; o[1] = (uint16_t)(v >> 16);
-        }
-        return;
+    const int tw = c.tw, qpr = tw >> 1, per_plane = (c.th >> 1) * qpr, total = c.np * per_plane, p4 = tw >> 1;
+    const SmallDiv d_qpr = mk_div(qpr);
+    uint32_t ky0[2], ky1[2];
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+        const int8_t *ty = TAPS == 8 ? c_luma_taps[c.fy[l] & 3] : c_chroma_taps[c.fy[l] & 7];
+        ky0[l] = pack4(ty); ky1[l] = TAPS == 8 ? pack4(ty + 4) : 0u;
     }
-    if (!HBD && (f0x | f0y) == 0 && (!rp1 || (f1x | f1y) == 0)) {
-        // integer motion vectors (every layer-1..3 picture of M10 runs integer-pel ME): LumaInterpolationCopy (C_DEFAULT/EbMcp_C.c:221) /
-        // BiPredClippingOnTheFly (Codec/EbMcp.c:603): ((p0 << 6) + (p1 << 6) + 64) >> 7 == (p0 + p1 + 1) >> 1
-        for (int i = threadIdx.x; i < th * (tw >> 2); i += MC_NT) {
-            const int y = i / (tw >> 2), x = (i - y * (tw >> 2)) * 4;
-            uint32_t v = ld_u32_unaligned(rp0 + (size_t)y * s0 + x);
-            if (rp1) v = __vavgu4(v, ld_u32_unaligned(rp1 + (size_t)y * s1 + x));
-            uint8_t *o = out + (size_t)y * ostride + x;
+    for (int i = threadIdx.x; i < total; i += MC_NT) {
+        const int p = i >= per_plane ? 1 : 0, j = i - p * per_plane;
+        const int qy = udiv(j, d_qpr), x = (j - qy * qpr) * 2, y = qy * 2;
+        int acc[2][2][2];   // [list][row][col]
+#pragma unroll
+        for (int l = 0; l < 2; ++l) {
+            if (l >= nl) { acc[l][0][0] = acc[l][0][1] = acc[l][1][0] = acc[l][1][1] = 0; continue; }
+            const uint32_t *col = (const uint32_t *)(s_tmp + (p * 2 + l) * tmp_unit + y * tw + x);
+            uint32_t w[TAPS + 1];
+#pragma unroll
+            for (int k = 0; k < TAPS + 1; ++k) w[k] = col[k * p4];
+#pragma unroll
+            for (int ry = 0; ry < 2; ++ry) {
+                int a0 = 0, a1 = 0;
+#pragma unroll
+                for (int k = 0; k < TAPS; k += 2) {
+                    const uint32_t lo = __byte_perm(w[ry + k], w[ry + k + 1], 0x5410);   // (x, row k), (x, row k+1)
+                    const uint32_t hi = __byte_perm(w[ry + k], w[ry + k + 1], 0x7632);   // (x+1, ..)
+                    const uint32_t cc = k < 4 ? ky0[l] : ky1[l];
+                    if ((k & 2) == 0) { a0 = dp2a_lo_ss(lo, cc, a0); a1 = dp2a_lo_ss(hi, cc, a1); }
+                    else { a0 = dp2a_hi_ss(lo, cc, a0); a1 = dp2a_hi_ss(hi, cc, a1); }
+                }
+                acc[l][ry][0] = a0; acc[l][ry][1] = a1;
+            }
+        }
+        uint8_t *outp = p ? c.out[1] : c.out[0];
+        const int ostride = p ? c.ostride[1] : c.ostride[0];
+#pragma unroll
+        for (int ry = 0; ry < 2; ++ry) {
+            int v0, v1;
+            if (nl == 2) {
+                const int s0 = (int)(short)(acc[0][ry][0] >> 6) + (int)(short)(acc[1][ry][0] >> 6), s1 = (int)(short)(acc[0][ry][1] >> 6) + (int)(short)(acc[1][ry][1] >> 6);
+                if (HBD) { v0 = min(max((s0 + 16400) >> 5, 0), 1023); v1 = min(max((s1 + 16400) >> 5, 0), 1023); }
+                else { v0 = min(max((s0 + 64) >> 7, 0), 255); v1 = min(max((s1 + 64) >> 7, 0), 255); }
+            } else if (HBD) {
+                v0 = min(max((acc[0][ry][0] + 524800) >> 10, 0), 1023); v1 = min(max((acc[0][ry][1] + 524800) >> 10, 0), 1023);
+            } else {
+                v0 = min(max((acc[0][ry][0] + 2048) >> 12, 0), 255); v1 = min(max((acc[0][ry][1] + 2048) >> 12, 0), 255);
+            }
+            if (HBD) {
+                uint16_t *o = (uint16_t *)outp + (size_t)(y + ry) * ostride + x;
+                if (((uintptr_t)o & 3) == 0) *(uint32_t *)o = (uint32_t)v0 | ((uint32_t)v1 << 16);
+                else { o[0] = (uint16_t)v0; o[1] = (uint16_t)v1; }
+            } else {
+                uint8_t *o = outp + (size_t)(y + ry) * ostride + x;
+                if (((uintptr_t)o & 1) == 0) *(uint16_t *)o = (uint16_t)(v0 | (v1 << 8));
+                else { o[0] = (uint8_t)v0; o[1] = (uint8_t)v1; }
+            }
+        }
+    }
+}
+
+// Integer motion vectors on every used list of the class (every layer-1..3 picture of M10 runs integer-pel ME): LumaInterpolationCopy
+// (C_DEFAULT/EbMcp_C.c:221) / BiPredClippingOnTheFly (Codec/EbMcp.c:603): ((p0 << 6) + (p1 << 6) + 64) >> 7 == (p0 + p1 + 1) >> 1;
+// 16-bit: uniPredCopy16bit (C_DEFAULT/EbMcp_C.c:3827) / BiPredClippingOnTheFly16bit (Codec/EbMcp.c:847).  No shared memory, no barrier.
+template <bool HBD>
+__device__ __forceinline__ void mc_copy_scalar(const McClass &c, int nl)
+{
+    const int tw = c.tw, ipr = HBD ? tw >> 1 : tw >> 2, per_plane = c.th * ipr, total = c.np * per_plane;
+    const SmallDiv d_ipr = mk_div(ipr);
+    for (int i = threadIdx.x; i < total; i += MC_NT) {
+        const int p = i >= per_plane ? 1 : 0, j = i - p * per_plane;
+        const int y = udiv(j, d_ipr), g = j - y * ipr;
+        const uint8_t *r0 = p ? c.u[1][0].ref : c.u[0][0].ref, *r1 = p ? c.u[1][1].ref : c.u[0][1].ref;
+        const int s0 = p ? c.u[1][0].rstride : c.u[0][0].rstride, s1 = p ? c.u[1][1].rstride : c.u[0][1].rstride;
+        uint8_t *outp = p ? c.out[1] : c.out[0];
+        const int ostride = p ? c.ostride[1] : c.ostride[0];
+        if (HBD) {
+            const int x = g * 2;
+            const uint16_t *a = (const uint16_t *)r0 + (size_t)y * s0 + x;
+            uint32_t v = (uint32_t)a[0] | ((uint32_t)a[1] << 16);
+            if (nl == 2) { const uint16_t *b = (const uint16_t *)r1 + (size_t)y * s1 + x; v = __vavgu2(v, (uint32_t)b[0] | ((uint32_t)b[1] << 16)); }
+            uint16_t *o = (uint16_t *)outp + (size_t)y * ostride + x;
+            o[0] = (uint16_t)v; o[1] = (uint16_t)(v >> 16);
+        } else {
+            const int x = g * 4;
+            uint32_t v = ld_u32_unaligned(r0 + (size_t)y * s0 + x);
+            if (nl == 2) v = __vavgu4(v, ld_u32_unaligned(r1 + (size_t)y * s1 + x));
+            uint8_t *o = outp + (size_t)y * ostride + x;
             if (((uintptr_t)o & 3) == 0) *(uint32_t *)o = v;
             else { o[0] = (uint8_t)v; o[1] = (uint8_t)(v >> 8); o[2] = (uint8_t)(v >> 16); o[3] = (uint8_t)(v >> 24); }
         }
-        return;
     }
-    if (!rp1) {
-        interp_tile<TAPS, HBD>(rp0, s0, f0x, f0y, tw, th, s_win, s_tmp, out, ostride, nullptr);
-        return;
+}
+
+// VW consecutive 32-bit words starting at an arbitrary byte address: two aligned 8 / 16-byte loads, a word-granular select chain and VW funnel shifts
+template <int VW>
+__device__ __forceinline__ void ld_bytes_vec(const uint8_t *p, uint32_t (&o)[VW])
+{
+    const uintptr_t a = (uintptr_t)p;
+    const int off = (int)(a & (4 * VW - 1));
+    uint32_t w[2 * VW];
+    if (VW == 4) {
+        const uint4 *b = (const uint4 *)(a - off);
+        const uint4 A = __ldg(b), B = __ldg(b + 1);
+        w[0] = A.x; w[1] = A.y; w[2] = A.z; w[3] = A.w; w[4] = B.x; w[5] = B.y; w[6] = B.z; w[7] = B.w;
+    } else {
+        const uint2 *b = (const uint2 *)(a - off);
+        const uint2 A = __ldg(b), B = __ldg(b + 1);
+        w[0] = A.x; w[1] = A.y; w[2] = B.x; w[3] = B.y;
     }
-    interp_tile<TAPS, HBD>(rp0, s0, f0x, f0y, tw, th, s_win, s_tmp, nullptr, 0, s_raw0);
-    interp_tile<TAPS, HBD>(rp1, s1, f1x, f1y, tw, th, s_win, s_tmp, nullptr, 0, s_raw1);
-    __syncthreads();
-    if (HBD) {   // BiPredClipping16bit, C_DEFAULT/EbMcp_C.c:3265: (l0 + l1 + 16400) >> 5 (16400 = 2 * 8192 bias + rounding)
-        for (int i = threadIdx.x; i < th * (tw >> 1); i += MC_NT) {
-            const int y = i / (tw >> 1), x = (i - y * (tw >> 1)) * 2;
-            const uint32_t a = *(const uint32_t *)(s_raw0 + y * tw + x), b = *(const uint32_t *)(s_raw1 + y * tw + x);
-            uint16_t *o = (uint16_t *)out + (size_t)y * ostride + x;
-            o[0] = (uint16_t)min(max(((int)(short)(a & 0xffff) + (int)(short)(b & 0xffff) + 16400) >> 5, 0), 1023);
-            o[1] = (uint16_t)min(max((((int)a >> 16) + ((int)b >> 16) + 16400) >> 5, 0), 1023);
+    const int q = off >> 2;
+    const uint32_t sh = (uint32_t)(off & 3) * 8;
+    if (VW == 4 && (q & 2)) {
+#pragma unroll
+        for (int k = 0; k < 2 * VW - 2; ++k) w[k] = w[k + 2];
+    }
+    if (q & 1) {
+#pragma unroll
+        for (int k = 0; k < 2 * VW - 1; ++k) w[k] = w[k + 1];
+    }
+#pragma unroll
+    for (int k = 0; k < VW; ++k) o[k] = __funnelshift_r(w[k], w[k + 1], sh);
+}
+
+// the same copy / rounded average with 8- or 16-byte items (row bytes, destination pointers and pitches multiples of 4 * VW)
+template <bool HBD, int VW>
+__device__ __forceinline__ void mc_copy_vec(const McClass &c, int nl)
+{
+    constexpr int BPS = HBD ? 2 : 1, VB = 4 * VW;
+    const int ipr = (c.tw * BPS) / VB, lg = 31 - __clz(ipr), per_plane = c.th * ipr, total = c.np * per_plane;   // ipr is a power of two here
+    for (int i = threadIdx.x; i < total; i += MC_NT) {
+        const int p = i >= per_plane ? 1 : 0, j = i - p * per_plane;
+        const int y = j >> lg, g = j & (ipr - 1);
+        const uint8_t *r0 = p ? c.u[1][0].ref : c.u[0][0].ref, *r1 = p ? c.u[1][1].ref : c.u[0][1].ref;
+        const int s0 = p ? c.u[1][0].rstride : c.u[0][0].rstride, s1 = p ? c.u[1][1].rstride : c.u[0][1].rstride;
+        uint8_t *outp = p ? c.out[1] : c.out[0];
+        const int ostride = p ? c.ostride[1] : c.ostride[0];
+        uint32_t v[VW];
+        ld_bytes_vec<VW>(r0 + (size_t)y * s0 * BPS + g * VB, v);
+        if (nl == 2) {
+            uint32_t u[VW];
+            ld_bytes_vec<VW>(r1 + (size_t)y * s1 * BPS + g * VB, u);
+#pragma unroll
+            for (int k = 0; k < VW; ++k) v[k] = HBD ? __vavgu2(v[k], u[k]) : __vavgu4(v[k], u[k]);
         }
-        return;
-    }
-    // BiPredClipping, C_DEFAULT/EbMcp_C.c:21 (the -8192 biases of the reference's raw buffers cancel against Offset5)
-    for (int i = threadIdx.x; i < th * (tw >> 1); i += MC_NT) {
-        const int y = i / (tw >> 1), x = (i - y * (tw >> 1)) * 2;
-        const uint32_t a = *(const uint32_t *)(s_raw0 + y * tw + x), b = *(const uint32_t *)(s_raw1 + y * tw + x);
-        const int v0 = min(max(((int)(short)(a & 0xffff) + (int)(short)(b & 0xffff) + 64) >> 7, 0), 255);
-        const int v1 = min(max((((int)a >> 16) + ((int)b >> 16) + 64) >> 7, 0), 255);
-        uint8_t *o = out + (size_t)y * ostride + x;
-        o[0] = (uint8_t)v0;
-        o[1] = (uint8_t)v1;
+        uint8_t *o = outp + (size_t)y * ostride * BPS + g * VB;
+        if (VW == 4) *(uint4 *)o = make_uint4(v[0], v[1], v[2], v[3]);
+        else *(uint2 *)o = make_uint2(v[0], v[1]);
     }
 }
 
 template <bool HBD>
-__global__ void __launch_bounds__(MC_NT) mc_batch_kernel(const __grid_constant__ McArgs A)
+__device__ __forceinline__ void mc_copy(const McClass &c, int nl)
 {
     constexpr int BPS = HBD ? 2 : 1;
-    __shared__ __align__(16) uint8_t s_win[(TILE + 7) * (HBD ? 128 : 96)];   // win_pitch(39) = 80, win_pitch(78) = 112
-    __shared__ __align__(16) int16_t s_tmp[(TILE + 7) * TILE];
-    __shared__ __align__(16) int16_t s_raw[2][TILE * TILE];
+    const int rb = c.tw * BPS;
+    uintptr_t al = (uintptr_t)c.out[0] | (uintptr_t)(c.ostride[0] * BPS) | (uintptr_t)rb;
+    if (c.np == 2) al |= (uintptr_t)c.out[1] | (uintptr_t)(c.ostride[1] * BPS);
+    const bool pow2 = (rb & (rb - 1)) == 0;
+    if (pow2 && (al & 15) == 0) mc_copy_vec<HBD, 4>(c, nl);
+    else if (pow2 && (al & 7) == 0) mc_copy_vec<HBD, 2>(c, nl);
+    else mc_copy_scalar<HBD>(c, nl);
+}
+
+__device__ __forceinline__ int clampi(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// shared-memory geometry of the staged path: window pitches win_pitch(39) = 80, win_pitch(19) = 64, 16-bit win_pitch(78) = 112, win_pitch(38) = 80
+template <bool HBD> struct McSmem {
+    static constexpr int WIN_L = (TILE + 7) * (HBD ? 112 : 80), WIN_C = (TILE / 2 + 3) * (HBD ? 80 : 64);
+    static constexpr int TMP_L = (TILE + 7) * TILE, TMP_C = (TILE / 2 + 3) * (TILE / 2);   // s16 elements
+};
+
+template <bool HBD>
+__global__ void __launch_bounds__(MC_NT, 8) mc_batch_kernel(const __grid_constant__ McArgs A)
+{
+    constexpr int BPS = HBD ? 2 : 1;
+    using G = McSmem<HBD>;
+    __shared__ __align__(16) uint8_t s_win[2 * G::WIN_L + 4 * G::WIN_C];
+    __shared__ __align__(16) int16_t s_tmp[2 * G::TMP_L + 4 * G::TMP_C];
+    __shared__ int s_a[8];
     const int job = blockIdx.x;
     if (job >= A.n_jobs) return;
     const svtb200_mc_job q = A.jobs[job];
-    int px[2] = {0, 0}, py[2] = {0, 0};
-    const YuvD *r[2] = {nullptr, nullptr};
-#pragma unroll
-    for (int l = 0; l < 2; ++l) {
-        if (!(q.dir == l || q.dir == 2)) continue;
-        r[l] = &A.refs[min((int)q.ref_idx[l], A.n_refs - 1)];   // param space
-        // absolute quarter-pel position in the padded reference (EB_U16 like the reference); a clamped position has no fraction
-        px[l] = (uint16_t)clampi((r[l]->ox - 71) << 2, (r[l]->w + r[l]->ox + 7) << 2, ((q.x + r[l]->ox) << 2) + q.mv[l][0]);
-        py[l] = (uint16_t)clampi((r[l]->oy - 71) << 2, (r[l]->h + r[l]->oy + 7) << 2, ((q.y + r[l]->oy) << 2) + q.mv[l][1]);
-    }
-  // one CTA per PU; PUs larger than 32x32 are walked tile by tile (an early-exit CTA per absent tile cost more than the copy itself)
-  for (int ty0 = 0; ty0 < q.h; ty0 += TILE)
-   for (int tx0 = 0; tx0 < q.w; tx0 += TILE) {
-    const int tw = min(TILE, q.w - tx0), th = min(TILE, q.h - ty0);
     const bool bi = q.dir == 2;
-    const int l0 = bi ? 0 : q.dir, l1 = 1;
-    // luma
-    {
-        uint8_t *dy = A.dst[0] + ((size_t)(A.doy + q.y + ty0) * A.dstride[0] + A.dox + q.x + tx0) * BPS;
-        const uint8_t *rp0 = r[l0]->p[0] + ((size_t)((py[l0] >> 2) + ty0) * r[l0]->stride[0] + (px[l0] >> 2) + tx0) * BPS;
-        const uint8_t *rp1 = bi ? r[l1]->p[0] + ((size_t)((py[l1] >> 2) + ty0) * r[l1]->stride[0] + (px[l1] >> 2) + tx0) * BPS : nullptr;
-        predict_tile<8, HBD>(rp0, r[l0]->stride[0], px[l0] & 3, py[l0] & 3, rp1, bi ? r[l1]->stride[0] : 0, px[l1] & 3, py[l1] & 3, tw, th, dy, A.dstride[0],
-                        s_win, s_tmp, s_raw[0], s_raw[1]);
+    const int nl = bi ? 2 : 1;
+    // list slot s -> list: uni-pred PUs use slot 0 for their only list
+    int px[2], py[2];
+    const YuvD *r[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int l = bi ? s : (q.dir == 1 ? 1 : 0);
+        const int ri = l ? q.ref_idx[1] : q.ref_idx[0], mvx = l ? q.mv[1][0] : q.mv[0][0], mvy = l ? q.mv[1][1] : q.mv[0][1];
+        r[s] = &A.refs[min(ri, A.n_refs - 1)];   // param space
+        // absolute quarter-pel position in the padded reference (EB_U16 like the reference); a clamped position has no fraction
+        px[s] = (uint16_t)clampi((r[s]->ox - 71) << 2, (r[s]->w + r[s]->ox + 7) << 2, ((q.x + r[s]->ox) << 2) + mvx);
+        py[s] = (uint16_t)clampi((r[s]->oy - 71) << 2, (r[s]->h + r[s]->oy + 7) << 2, ((q.y + r[s]->oy) << 2) + mvy);
     }
-    // chroma (Cb then Cr): half-size tile, eighth-pel phases
-    const int cw = tw >> 1, ch = th >> 1;
-    // chroma destination index exactly as the reference forms it (EbInterPrediction.c:783)
-    const size_t cidx = (((size_t)(A.doy + q.y) * A.dstride[1]) >> 1) + ((A.dox + q.x) >> 1) + (size_t)(ty0 >> 1) * A.dstride[1] + (tx0 >> 1);
-#pragma unroll 1
-    for (int pl = 1; pl < 3; ++pl) {
-        const uint8_t *rp0 = r[l0]->p[pl] + ((size_t)((py[l0] >> 3) + (ty0 >> 1)) * r[l0]->stride[pl] + (px[l0] >> 3) + (tx0 >> 1)) * BPS;
-        const uint8_t *rp1 = bi ? r[l1]->p[pl] + ((size_t)((py[l1] >> 3) + (ty0 >> 1)) * r[l1]->stride[pl] + (px[l1] >> 3) + (tx0 >> 1)) * BPS : nullptr;
-        predict_tile<4, HBD>(rp0, r[l0]->stride[pl], px[l0] & 7, py[l0] & 7, rp1, bi ? r[l1]->stride[pl] : 0, px[l1] & 7, py[l1] & 7, cw, ch, A.dst[pl] + cidx * BPS,
-                        A.dstride[pl], s_win, s_tmp, s_raw[0], s_raw[1]);
-    }
-    __syncthreads();
-   }
+    // one CTA per PU; PUs larger than 32x32 are walked tile by tile (an early-exit CTA per absent tile cost more than the copy itself)
+    for (int ty0 = 0; ty0 < q.h; ty0 += TILE)
+        for (int tx0 = 0; tx0 < q.w; tx0 += TILE) {
+            McClass L, K;   // luma, chroma
+            L.np = 1; L.tw = min(TILE, q.w - tx0); L.th = min(TILE, q.h - ty0);
+            K.np = 2; K.tw = L.tw >> 1; K.th = L.th >> 1;
+            L.out[0] = L.out[1] = A.dst[0] + ((size_t)(A.doy + q.y + ty0) * A.dstride[0] + A.dox + q.x + tx0) * BPS;
+            L.ostride[0] = L.ostride[1] = A.dstride[0];
+            // chroma destination index exactly as the reference forms it (EbInterPrediction.c:783)
+            const size_t cidx = (((size_t)(A.doy + q.y) * A.dstride[1]) >> 1) + ((A.dox + q.x) >> 1) + (size_t)(ty0 >> 1) * A.dstride[1] + (tx0 >> 1);
+            K.out[0] = A.dst[1] + cidx * BPS; K.out[1] = A.dst[2] + cidx * BPS;
+            K.ostride[0] = A.dstride[1]; K.ostride[1] = A.dstride[2];
+            int lf = 0, kf = 0;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                L.fx[s] = px[s] & 3; L.fy[s] = py[s] & 3; K.fx[s] = px[s] & 7; K.fy[s] = py[s] & 7;
+                if (s < nl) { lf |= L.fx[s] | L.fy[s]; kf |= K.fx[s] | K.fy[s]; }
+                L.u[0][s].ref = r[s]->p[0] + ((size_t)((py[s] >> 2) + ty0) * r[s]->stride[0] + (px[s] >> 2) + tx0) * BPS;
+                L.u[0][s].rstride = r[s]->stride[0];
+                L.u[1][s] = L.u[0][s];
+#pragma unroll
+                for (int pl = 1; pl < 3; ++pl) {
+                    K.u[pl - 1][s].ref = r[s]->p[pl] + ((size_t)((py[s] >> 3) + (ty0 >> 1)) * r[s]->stride[pl] + (px[s] >> 3) + (tx0 >> 1)) * BPS;
+                    K.u[pl - 1][s].rstride = r[s]->stride[pl];
+                }
+            }
+            L.interp = lf != 0; K.interp = kf != 0;
+            if (L.interp) mc_stage_load<8, HBD>(L, nl, s_win, G::WIN_L, s_a);
+            if (K.interp) mc_stage_load<4, HBD>(K, nl, s_win + 2 * G::WIN_L, G::WIN_C, s_a + 2);
+            if (!L.interp) mc_copy<HBD>(L, nl);
+            if (!K.interp) mc_copy<HBD>(K, nl);
+            if (L.interp || K.interp) {
+                __syncthreads();
+                if (L.interp) mc_stage_h<8, HBD>(L, nl, s_win, G::WIN_L, s_a, s_tmp, G::TMP_L);
+                if (K.interp) mc_stage_h<4, HBD>(K, nl, s_win + 2 * G::WIN_L, G::WIN_C, s_a + 2, s_tmp + 2 * G::TMP_L, G::TMP_C);
+                __syncthreads();
+                if (L.interp) mc_stage_v<8, HBD>(L, nl, s_tmp, G::TMP_L);
+                if (K.interp) mc_stage_v<4, HBD>(K, nl, s_tmp + 2 * G::TMP_L, G::TMP_C);
+                __syncthreads();   // the next tile's loads reuse the windows
+            }
+        }
 }
 
-// leaf: one block (w x h, multiples of 4 x 2) through the same tile routine
+// leaf: one block (w x h, multiples of 4 x 2) through the same three stages, one plane, one or two lists
 template <int TAPS>
 __global__ void __launch_bounds__(MC_NT) mc_leaf_kernel(const uint8_t *r0, int s0, int f0x, int f0y, const uint8_t *r1, int s1, int f1x, int f1y,
                                                         uint8_t *dst, int ds, int w, int h)
 {
-    __shared__ __align__(16) uint8_t s_win[(TILE + 7) * 96];   // win_pitch(39) = 80
-    __shared__ __align__(16) int16_t s_tmp[(TILE + 7) * TILE];
-    __shared__ __align__(16) int16_t s_raw[2][TILE * TILE];
+    using G = McSmem<false>;
+    __shared__ __align__(16) uint8_t s_win[2 * G::WIN_L];
+    __shared__ __align__(16) int16_t s_tmp[2 * G::TMP_L];
+    __shared__ int s_a[4];
+    const int nl = r1 ? 2 : 1;
     for (int ty0 = 0; ty0 < h; ty0 += TILE)
         for (int tx0 = 0; tx0 < w; tx0 += TILE) {
-            const int tw = min(TILE, w - tx0), th = min(TILE, h - ty0);
-            predict_tile<TAPS, false>(r0 + (size_t)ty0 * s0 + tx0, s0, f0x, f0y, r1 ? r1 + (size_t)ty0 * s1 + tx0 : nullptr, s1, f1x, f1y, tw, th,
-                               dst + (size_t)ty0 * ds + tx0, ds, s_win, s_tmp, s_raw[0], s_raw[1]);
+            McClass c;
+            c.np = 1; c.tw = min(TILE, w - tx0); c.th = min(TILE, h - ty0);
+            c.out[0] = c.out[1] = dst + (size_t)ty0 * ds + tx0; c.ostride[0] = c.ostride[1] = ds;
+            c.fx[0] = f0x; c.fy[0] = f0y; c.fx[1] = f1x; c.fy[1] = f1y;
+            c.u[0][0].ref = r0 + (size_t)ty0 * s0 + tx0; c.u[0][0].rstride = s0;
+            c.u[0][1].ref = r1 ? r1 + (size_t)ty0 * s1 + tx0 : c.u[0][0].ref; c.u[0][1].rstride = r1 ? s1 : s0;
+            c.u[1][0] = c.u[0][0]; c.u[1][1] = c.u[0][1];
+            c.interp = (f0x | f0y | (r1 ? (f1x | f1y) : 0)) != 0;
+            if (!c.interp) { mc_copy<false>(c, nl); continue; }
+            mc_stage_load<TAPS, false>(c, nl, s_win, G::WIN_L, s_a);
+            __syncthreads();
+            mc_stage_h<TAPS, false>(c, nl, s_win, G::WIN_L, s_a, s_tmp, G::TMP_L);
+            __syncthreads();
+            mc_stage_v<TAPS, false>(c, nl, s_tmp, G::TMP_L);
+            __syncthreads();
         }
 }
 
@@ -428,7 +565,7 @@ static int mc_leaf(int taps, uint32_t f0x, uint32_t f0y, const uint8_t *ref0, ui
     const int half = taps / 2 - 1, ext = taps - 1;
     const size_t b0 = (size_t)(h + ext - 1) * r0s + w + ext, b1 = bi ? (size_t)(h + ext - 1) * r1s + w + ext : 0, bd = (size_t)(h - 1) * ds + w;
     void *d0, *d1 = nullptr, *dd, *hd;
-    if ((rc = c->dev_reserve(b0 + b1 + bd + 4096)) || (rc = c->dev_alloc(b0 + 8, &d0)) || (rc = c->dev_alloc(b1 + 8, &d1)) || (rc = c->dev_alloc(bd, &dd)) || (rc = c->pin_alloc(bd, &hd))) return rc;
+    if ((rc = c->dev_reserve(b0 + b1 + bd + 4096)) || (rc = c->dev_alloc(b0 + 48, &d0)) || (rc = c->dev_alloc(b1 + 48, &d1)) || (rc = c->dev_alloc(bd, &dd)) || (rc = c->pin_alloc(bd, &hd))) return rc;
     const uint8_t *h0 = ref0 - (size_t)half * r0s - half, *h1 = bi ? ref1 - (size_t)half * r1s - half : nullptr;
     const size_t m0 = (uintptr_t)h0 & 3, m1 = bi ? ((uintptr_t)h1 & 3) : 0;   // keep the host misalignment: exercises every window phase
     SVTB200_CUDA_TRY(cudaMemcpyAsync((uint8_t *)d0 + m0, h0, b0, cudaMemcpyHostToDevice, c->stream));

@@ -20,7 +20,6 @@
 
 namespace svtb200 {
 
-constexpr int NT = 256;                 // threads per CTA
 constexpr int CHUNK = 64;               // full-pel search positions evaluated per pass
 constexpr uint32_t MAX_SAD_INIT = 64 * 64 * 255;   // MAX_SAD_VALUE, EbMotionEstimation.c:99
 
@@ -39,920 +38,29 @@ struct MeArgs {
     int win_bytes;        // bytes reserved for the window region of dynamic shared memory
 };
 
-__device__ __forceinline__ const uint8_t *pat(const PlaneD &p, int x, int y)
-{
-    return p.buf + (ptrdiff_t)(p.oy + y) * p.stride + (p.ox + x);
-}
+}  // namespace svtb200
 
-// ---- block-wide reductions ---------------------------------------------------------------
-template <int N>
-__device__ __forceinline__ void block_sum(uint32_t (&v)[N], uint32_t *s_red /* [8*N] */)
-{
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
-    __syncthreads();
-    if (lane == 0)
-#pragma unroll
-        for (int i = 0; i < N; ++i) s_red[wid * N + i] = v[i];
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        uint32_t t = 0;
-#pragma unroll
-        for (int w = 0; w < NT / 32; ++w) t += s_red[w * N + i];
-        v[i] = t;
-    }
-}
-__device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v, unsigned long long *s_red /* [8] */)
-{
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    v = warp_min_u64(v);
-    __syncthreads();
-    if (lane == 0) s_red[wid] = v;
-    __syncthreads();
-    unsigned long long t = s_red[0];
-#pragma unroll
-    for (int w = 1; w < NT / 32; ++w) t = s_red[w] < t ? s_red[w] : t;
-    return t;
-}
-
-// Fast path of sad_search for full-width HME level-0 blocks (16 x bh, pitch 16): each thread evaluates FOUR consecutive x
-// positions from one set of window words.  The window's byte misalignment is the same for every group (x0 is a multiple of
-// 4), so it is a template parameter and every funnel shift has a compile-time amount: per block row 6 window words + 4
-// source words feed 16 VABSDIFF4.
-template <int SH>
-__device__ __forceinline__ unsigned long long sad_search4_body(const uint32_t *blk32, int bh, const uint8_t *s_win, int wp, int a, int row_step,
-                                                               int saw, int sah)
-{
-    const int gpr = (saw + 3) >> 2, G = gpr * sah, wp4 = wp >> 2;
-    unsigned long long best = ~0ull;
-    for (int g = threadIdx.x; g < G; g += NT) {
-        const int y = g / gpr, x0 = (g - y * gpr) * 4;
-        const uint32_t *row = (const uint32_t *)(s_win + y * wp) + ((a + x0) >> 2);
-        uint32_t acc[4] = {0, 0, 0, 0};
-        for (int r = 0; r < bh; ++r, row += row_step * wp4) {
-            uint32_t w[6];
-#pragma unroll
-            for (int j = 0; j < 6; ++j) w[j] = row[j];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t s = blk32[r * 4 + j];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int t = SH * 8 + 8 * k, idx = t >> 5, sft = t & 31;
-                    const uint32_t v = sft ? __funnelshift_r(w[j + idx], w[j + idx + 1], sft) : w[j + idx];
-                    acc[k] += __vsadu4(v, s);
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (x0 + k < saw && acc[k] < 0xffffffu) {
-                const unsigned long long key = ((unsigned long long)acc[k] << 32) | (uint32_t)(y * saw + x0 + k);
-                best = key < best ? key : best;
-            }
-    }
-    return best;
-}
-
-// ---- exhaustive block search (semantics of SadLoopKernel, C_DEFAULT/EbComputeSAD_C.c:165) -----------------
-// s_blk: bw x bh source block in shared memory (pitch bp, multiple of 4); window staged by load_window_t<NT>().
-// Block row r is compared with window row y + r*row_step.  Returns min SAD (start value 0xffffff) and the
-// FIRST raster position attaining it; x/y are left untouched when no position qualifies.
-__device__ void sad_search(const uint8_t *s_blk, int bp, int bw, int bh, const uint8_t *s_win, int wp, int a,
-                           int row_step, int saw, int sah, unsigned long long *s_red64,
-                           uint32_t &best_sad, int &best_x, int &best_y)
-{
-    const int P = saw * sah;
-    if (bw == 16 && bp == 16 && P >= NT) {
-        unsigned long long b;
-        switch (a & 3) {
-        case 0: b = sad_search4_body<0>((const uint32_t *)s_blk, bh, s_win, wp, a, row_step, saw, sah); break;
-        case 1: b = sad_search4_body<1>((const uint32_t *)s_blk, bh, s_win, wp, a, row_step, saw, sah); break;
-        case 2: b = sad_search4_body<2>((const uint32_t *)s_blk, bh, s_win, wp, a, row_step, saw, sah); break;
-        default: b = sad_search4_body<3>((const uint32_t *)s_blk, bh, s_win, wp, a, row_step, saw, sah); break;
-        }
-        b = block_min_u64(b, s_red64);
-        if (b != ~0ull) { const int p = (int)(uint32_t)b; best_sad = (uint32_t)(b >> 32); best_y = p / saw; best_x = p - best_y * saw; }
-        else best_sad = 0xffffffu;
-        return;
-    }
-    // split block rows over RS lanes when there are few positions (HME level 1/2 windows)
-    int rs_log = 0;
-    while ((P << rs_log) < NT && (1 << (rs_log + 1)) <= bh && rs_log < 5) ++rs_log;
-    const int RS = 1 << rs_log;
-    const int rows_per = (bh + RS - 1) >> rs_log;
-    const int nw = (bw + 3) >> 2;
-    const uint32_t tail_mask = (bw & 3) ? ((1u << ((bw & 3) * 8)) - 1u) : 0xffffffffu;
-    const uint32_t *blk32 = (const uint32_t *)s_blk;
-    const int bp4 = bp >> 2;
-    unsigned long long best = ~0ull;
-    const int total = P << rs_log;
-    for (int base = 0; base < total; base += NT) {
-        const int i = base + threadIdx.x;
-        const bool active = i < total;
-        const int p = active ? (i >> rs_log) : 0, rsub = i & (RS - 1);
-        const int y = p / saw, x = p - y * saw;
-        uint32_t sad = 0;
-        if (active) {
-            const int r0 = rsub * rows_per, r1 = min(bh, r0 + rows_per);
-            const int col = a + x, wi = col >> 2, sh = (col & 3) * 8;
-            for (int r = r0; r < r1; ++r) {
-                const uint32_t *row = (const uint32_t *)(s_win + (y + r * row_step) * wp) + wi;
-                uint32_t lo = row[0];
-                for (int j = 0; j < nw; ++j) {
-                    const uint32_t hi = row[j + 1];
-                    uint32_t v = __funnelshift_r(lo, hi, sh);
-                    uint32_t s = blk32[r * bp4 + j];
-                    if (j == nw - 1) { v &= tail_mask; s &= tail_mask; }
-                    sad += __vsadu4(v, s);
-                    lo = hi;
-                }
-            }
-        }
-        for (int o = 1; o < RS; o <<= 1) sad += __shfl_xor_sync(0xffffffffu, sad, o);
-        if (active && rsub == 0 && sad < 0xffffffu) {
-            const unsigned long long key = ((unsigned long long)sad << 32) | (uint32_t)p;
-            best = key < best ? key : best;
-        }
-    }
-    best = block_min_u64(best, s_red64);
-    if (best != ~0ull) {
-        const int p = (int)(uint32_t)best;
-        best_sad = (uint32_t)(best >> 32);
-        best_y = p / saw;
-        best_x = p - best_y * saw;
-    } else {
-        best_sad = 0xffffffu;
-    }
-}
-
-// ---- LCU-sized row-subsampled SADs straight from global memory (centre tests) ----------------------------
-// N candidate displacements; SAD over lw x (lh/2) on every other row, doubled (subsampleSad = 1 calls in
-// TestSearchAreaBounds :3397 and EbHevcCheckZeroZeroCenter :2964).
-template <int N>
-__device__ void lcu_sads(const uint8_t *s_src, const PlaneD &rF, int ox, int oy, int lw, int lh,
-                         const int (&dx)[N], const int (&dy)[N], int ncand, uint32_t *s_red32, uint32_t (&out)[N])
-{
-    uint32_t acc[N];
-#pragma unroll
-    for (int k = 0; k < N; ++k) acc[k] = 0;
-    const int rows = lh >> 1, nw = lw >> 2;   // lw is a multiple of 8 (minimum CU size)
-    const uint8_t *base[N];
-#pragma unroll
-    for (int k = 0; k < N; ++k) base[k] = pat(rF, ox + dx[k < ncand ? k : 0], oy + dy[k < ncand ? k : 0]);
-    const ptrdiff_t rs2 = 2 * (ptrdiff_t)rF.stride;
-#pragma unroll 2
-    for (int i = threadIdx.x; i < rows * nw; i += NT) {
-        const int r = i / nw, j = i - r * nw;
-        const uint32_t s = ((const uint32_t *)s_src)[(2 * r) * 16 + j];
-        const ptrdiff_t off = r * rs2 + 4 * j;
-#pragma unroll
-        for (int k = 0; k < N; ++k)
-            if (k < ncand) acc[k] += __vsadu4(s, ld_u32_unaligned(base[k] + off));
-    }
-    block_sum<N>(acc, s_red32);
-#pragma unroll
-    for (int k = 0; k < N; ++k) out[k] = acc[k] << 1;
-}
-
-// the four-sided window clamp repeated through EbMotionEstimation.c (e.g. :1892-1930)
-__device__ __forceinline__ void clamp_window(int org, int pad, int limit, int &o, int &len)
-{
-    // left/top: the reference moves the origin first and then re-tests the SAME condition with the moved origin
-    // (e.g. :1892-1900), so the window is shifted but never shortened on this side
-    if (org + o < -pad) o = -pad - org;
-    if (org + o > limit - 1) o -= (org + o) - (limit - 1);
-    if (org + o + len > limit) { const int l = len - ((org + o + len) - limit); len = l < 1 ? 1 : l; }
-}
-__device__ __forceinline__ int clamp_center(int org, int c, int pad, int limit)
-{
-    if (org + c < -pad) c = -pad - org;
-    if (org + c > limit - 1) c -= (org + c) - (limit - 1);
-    return c;
-}
-__device__ __forceinline__ int s16(int v) { return (int)(short)v; }
-
-// MeEbHevcGetMvdFractionBits, Codec/EbMdRateEstimation.c:172
-__device__ uint32_t egk1_bits(int sym)
-{
-    uint32_t k = 1, n = 0;
-    while (sym >= (int)(1u << k)) { sym -= (1 << k); ++k; ++n; }
-    return n + 1 + k;
-}
-__device__ uint32_t mvd_bits(int mx, int my, const uint32_t *t)
-{
-    const uint32_t ax = (uint32_t)abs(mx), ay = (uint32_t)abs(my);
-    const uint32_t xn = ax != 0, yn = ay != 0, xg = ax > 1, yg = ay > 1;
-    uint32_t b = t[xn] + t[yn + (2u << xn)];
-    if (xn) b += t[xg + 6];
-    if (yn) b += t[yg + 6 + (2u << xg)];
-    if (xn) b += (xg ? egk1_bits((int)ax - 2) * 32768u : 0u) + 32768u;
-    if (yn) b += (yg ? egk1_bits((int)ay - 2) * 32768u : 0u) + 32768u;
-    return b;
-}
-
-__constant__ int c_hme_mult[6][6] = {   // HME_LEVEL_0_SEARCH_AREA_MULTIPLIER_X/_Y, EbDefinitions.h:1322-1340
-    {100, 0, 0, 0, 0, 0}, {100, 100, 0, 0, 0, 0}, {100, 100, 100, 0, 0, 0},
-    {200, 140, 100, 70, 0, 0}, {350, 200, 100, 100, 100, 0}, {525, 350, 200, 100, 100, 100}};
-__constant__ uint8_t c_tab32[16] = {0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 11, 14, 15};   // tab32x32, EbMotionEstimation.c:101
-__constant__ uint8_t c_tab8[64] = {0, 1, 4, 5, 16, 17, 20, 21, 2, 3, 6, 7, 18, 19, 22, 23, 8, 9, 12, 13, 24, 25, 28, 29,
-                                   10, 11, 14, 15, 26, 27, 30, 31, 32, 33, 36, 37, 48, 49, 52, 53, 34, 35, 38, 39, 50, 51, 54, 55,
-                                   40, 41, 44, 45, 56, 57, 60, 61, 42, 43, 46, 47, 58, 59, 62, 63};    // tab8x8, :102
-
-// geometry of PU n (n-order of pLcuBestSad: 64x64, 32x32 raster, 16x16 z-order, 8x8 four per 16x16)
-__device__ __forceinline__ void pu_geom(int n, int &px, int &py, int &sz)
-{
-    if (n == 0) { px = 0; py = 0; sz = 64; return; }
-    if (n < 5) { px = ((n - 1) & 1) * 32; py = ((n - 1) >> 1) * 32; sz = 32; return; }
-    int z, q = 0;
-    if (n < 21) { z = n - 5; sz = 16; } else { z = (n - 21) >> 2; q = (n - 21) & 3; sz = 8; }
-    const int Q = z >> 2, s = z & 3;
-    const int X = (Q & 1) * 2 + (s & 1), Y = (Q >> 1) * 2 + (s >> 1);
-    px = X * 16 + (q & 1) * 8;
-    py = Y * 16 + (q >> 1) * 8;
-}
-
-// ---- 85-PU full-pel search (FullPelSearch_LCU, EbMotionEstimation.c:586) ---------------------------------
-// s_src: 64x64 source (pitch 64).  Window (saw+63) x (sah+63) staged in s_win (pitch wp, misalignment a).
-// s_bsad/s_bmv: running best (n-order), updated with the reference's scan-order semantics:
-//   positions with x < (saw & ~7) follow the 8-position path (u16 16x16 partials, 64x64 uses '<='),
-//   the remainder follows the single-position path (strict '<' everywhere).
-// (1) of fullpel_search: 8x8 SADs (rows 0,2,4,6; Subsad8x8, C_DEFAULT/EbComputeSAD_C.c:214) of one chunk of search positions.
-// A work item = (8x8 block b, search row, group of 8 consecutive x positions): five window words per block row serve all 8
-// positions (the same sharing GetEightHorizontalSearchPointResults_8x8_16x16_PU gets from mpsadbw).  The byte misalignment
-// of the staged window is uniform, hence a template parameter.
-template <int SH>
-__device__ __forceinline__ void fullpel_sad8_chunk(const uint32_t *src32, const uint8_t *s_win, int wp, int a, int y0, int nrows, int xg0, int ngr,
-                                                   int gw, uint16_t *s_sad8)
-{
-    const int n_items = nrows * ngr * 64;
-    for (int i = threadIdx.x; i < n_items; i += NT) {
-        const int b = i & 63, t = i >> 6, yy = t / ngr, xgi = t - yy * ngr;
-        const int bx = b & 7, by = b >> 3;
-        const int x0 = (xg0 + xgi) * 8, y = y0 + yy;
-        uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const uint32_t *row = (const uint32_t *)(s_win + (y + by * 8 + 2 * r) * wp) + ((a + x0 + bx * 8) >> 2);
-            uint32_t w[5];
-#pragma unroll
-            for (int j = 0; j < 5; ++j) w[j] = row[j];
-            const uint32_t s0 = src32[(by * 8 + 2 * r) * 16 + bx * 2], s1 = src32[(by * 8 + 2 * r) * 16 + bx * 2 + 1];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int tt = SH * 8 + 8 * k, idx = tt >> 5, sft = tt & 31;
-                const uint32_t v0 = sft ? __funnelshift_r(w[idx], w[idx + 1], sft) : w[idx];
-                const uint32_t v1 = sft ? __funnelshift_r(w[idx + 1], w[idx + 2], sft) : w[idx + 1];
-                acc[k] += __vsadu4(v0, s0) + __vsadu4(v1, s1);
-            }
-        }
-        uint16_t *o = s_sad8 + (yy * gw + xgi * 8) * 64 + b;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o[k * 64] = (uint16_t)acc[k];
-    }
-}
-
-__device__ void fullpel_search(const uint8_t *s_src, const uint8_t *s_win, int wp, int a, int sox, int soy,
-                               int saw, int sah, uint16_t *s_sad8 /*[CHUNK][64]*/, uint32_t *s_sum /*[CHUNK][21]*/,
-                               uint32_t *s_bsad, uint32_t *s_bmv)
-{
-    const int w8 = saw & ~7;
-    const uint32_t *src32 = (const uint32_t *)s_src;
-    // chunks of <= CHUNK positions in scan order: whole search rows when a row has <= 8 groups of 8, else 8 groups of one row
-    const int ng_total = (saw + 7) >> 3;
-    const int ngr_chunk = ng_total < 8 ? ng_total : 8, rows_chunk = ng_total <= 8 ? max(1, 8 / ng_total) : 1;
-    for (int y0 = 0; y0 < sah; y0 += rows_chunk)
-      for (int xg0 = 0; xg0 < ng_total; xg0 += ngr_chunk) {
-        const int nrows = min(rows_chunk, sah - y0), ngr = min(ngr_chunk, ng_total - xg0), gw = ngr * 8, cn = nrows * gw;
-        switch (a & 3) {
-        case 0: fullpel_sad8_chunk<0>(src32, s_win, wp, a, y0, nrows, xg0, ngr, gw, s_sad8); break;
-        case 1: fullpel_sad8_chunk<1>(src32, s_win, wp, a, y0, nrows, xg0, ngr, gw, s_sad8); break;
-        case 2: fullpel_sad8_chunk<2>(src32, s_win, wp, a, y0, nrows, xg0, ngr, gw, s_sad8); break;
-        default: fullpel_sad8_chunk<3>(src32, s_win, wp, a, y0, nrows, xg0, ngr, gw, s_sad8); break;
-        }
-        __syncthreads();
-        // (2) 16x16 partial sums in n-order
-        for (int i = threadIdx.x; i < cn * 16; i += NT) {
-            const int pc = i >> 4, z = i & 15, Q = z >> 2, s = z & 3;
-            const int X = (Q & 1) * 2 + (s & 1), Y = (Q >> 1) * 2 + (s >> 1);
-            const uint16_t *q = s_sad8 + pc * 64 + (Y * 2) * 8 + X * 2;
-            uint32_t t = (uint32_t)q[0] + q[1] + q[8] + q[9];
-            const int x = xg0 * 8 + pc % gw;
-            if (x < w8) t = (uint16_t)t;     // EB_U16 sad16x16, C_DEFAULT/EbComputeSAD_C.c:259,337
-            s_sum[pc * 21 + 5 + z] = t;
-        }
-        __syncthreads();
-        // (3) 32x32 and 64x64
-        for (int i = threadIdx.x; i < cn * 4; i += NT) {
-            const int pc = i >> 2, k = i & 3;
-            const uint32_t *q = s_sum + pc * 21 + 5 + 4 * k;
-            s_sum[pc * 21 + 1 + k] = q[0] + q[1] + q[2] + q[3];
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < cn; i += NT) {
-            const uint32_t *q = s_sum + i * 21 + 1;
-            s_sum[i * 21] = q[0] + q[1] + q[2] + q[3];
-        }
-        __syncthreads();
-        // (4) best-update with the reference's scan-order semantics, one WARP per PU (lanes = the <= 64 positions of the chunk):
-        //     strict '<' PUs keep the FIRST minimum; the 64x64 PU uses '<=' on 8-position-path positions (x < w8), so among
-        //     positions tied at the minimum the LAST such position wins if it comes after the first tied one -- and it also
-        //     replaces an equal best carried in from earlier chunks (C_DEFAULT/EbComputeSAD_C.c:439 vs EbMeSadCalculation_C.c:109).
-        {
-            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-            // PUs 1..84 (strict '<'): 8 lanes per PU, lane l scans positions l, l + 8, ... keeping (sad, position) as one 64-bit key, so the
-            // minimum key is the FIRST minimum in scan order; three shuffles merge the 8 lanes.  gw is a multiple of 8, so x advances by 8.
-            for (int g = (int)(threadIdx.x >> 3); g < 84; g += NT / 8) {
-                const int n = 1 + g, l = lane & 7;
-                int b8 = 0;
-                if (n >= 21) {
-                    int px, py, sz;
-                    pu_geom(n, px, py, sz);
-                    b8 = (py >> 3) * 8 + (px >> 3);
-                }
-                unsigned long long key = ~0ull;
-                int xx = l;                                  // position pc = l + 8k; xx = pc mod gw (l < 8 <= gw)
-                for (int pc = l; pc < cn; pc += 8) {
-                    if (xg0 * 8 + xx < saw) {
-                        const uint32_t v = 2u * (n >= 21 ? (uint32_t)s_sad8[pc * 64 + b8] : s_sum[pc * 21 + n]);
-                        const unsigned long long k = ((unsigned long long)v << 32) | (uint32_t)pc;
-                        key = k < key ? k : key;
-                    }
-                    xx += 8;
-                    if (xx >= gw) xx -= gw;
-                }
-#pragma unroll
-                for (int o = 4; o > 0; o >>= 1) {
-                    const unsigned long long t = __shfl_xor_sync(0xffffffffu, key, o);
-                    key = t < key ? t : key;
-                }
-                if (l == 0 && key != ~0ull) {
-                    const uint32_t m = (uint32_t)(key >> 32);
-                    if (m < s_bsad[n]) {
-                        const int win = (int)(uint32_t)key, yy = win / gw, x = xg0 * 8 + (win - yy * gw), y = y0 + yy;
-                        s_bsad[n] = m;
-                        s_bmv[n] = ((uint32_t)(uint16_t)((y + soy) * 4) << 16) | (uint16_t)((x + sox) * 4);
-                    }
-                }
-            }
-            // PU 0 (64x64): '<=' on 8-position-path positions -- one warp, lanes = the <= 64 positions of the chunk
-            if (wid == NT / 32 - 1) {
-                const int n = 0;
-                uint32_t v[2];
-                bool valid[2], le[2];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int pc = lane + 32 * h, yy = pc / gw, xx = pc - yy * gw, x = xg0 * 8 + xx;
-                    valid[h] = pc < cn && x < saw;
-                    le[h] = valid[h] && x < w8;
-                    v[h] = valid[h] ? 2u * s_sum[pc * 21 + n] : 0xffffffffu;
-                }
-                const uint32_t m = __reduce_min_sync(0xffffffffu, min(v[0], v[1]));
-                const uint32_t bs = s_bsad[n];
-                const unsigned long long tied = (unsigned long long)__ballot_sync(0xffffffffu, valid[0] && v[0] == m) |
-                                                ((unsigned long long)__ballot_sync(0xffffffffu, valid[1] && v[1] == m) << 32);
-                const unsigned long long tied_le = (unsigned long long)__ballot_sync(0xffffffffu, le[0] && v[0] == m) |
-                                                   ((unsigned long long)__ballot_sync(0xffffffffu, le[1] && v[1] == m) << 32);
-                int win = -1;
-                if (tied) {
-                    const int t1 = __ffsll((long long)tied) - 1, L = tied_le ? 63 - __clzll((long long)tied_le) : -1;
-                    if (m < bs) win = L > t1 ? L : t1;
-                    else if (m == bs && L >= 0) win = L;
-                }
-                if (lane == 0 && win >= 0) {
-                    const int yy = win / gw, x = xg0 * 8 + (win - yy * gw), y = y0 + yy;
-                    s_bsad[n] = m;
-                    s_bmv[n] = ((uint32_t)(uint16_t)((y + soy) * 4) << 16) | (uint16_t)((x + sox) * 4);
-                }
-            }
-        }
-        __syncthreads();
-      }
-}
-
-
-// ---- sub-pel refinement --------------------------------------------------------------------------
-// EbHevcInterpolateSearchRegionAVC :645 (AvcStyleLumaInterpolationFilterHorizontal / Vertical, C_DEFAULT/EbAvcStyleMcp_C.c:34,62, half-sample
-// taps {-2, 18, 18, -2}, (+16) >> 5), PU_HalfPelRefinement :733 / EbHevcHalfPelSearch_LCU :1036, SetQuarterPelRefinementInputsOnTheFly :1540,
-// PU_QuarterPelRefinementOnTheFly :1226 / QuarterPelSearch_LCU :1623, SuPelEnable :3035.
-// The reference interpolates three half-sample planes over the whole search region of the LCU and indexes them per PU; here the same
-// planes live in shared memory (per list, kept until bi-prediction).  Plane coordinates relative to the search-area origin O:
-//   F(x, y) integer sample O + (x, y);  B(c, y) = (c - 1/2, y);  H(x, r) = (x, r - 1/2);  J(c, r) = (c - 1/2, r - 1/2) filtered from the ROUNDED B.
-// F is staged by load_window_t (pitch fp, misalignment a); B / H / J share the pitch sp.  All carry a 2-sample apron.
-struct SpList {
-    uint8_t *F, *B, *H, *J;
-    int fp, sp, a;
-    int sox, soy, saw, sah;
-};
-__device__ __forceinline__ const uint8_t *spF(const SpList &L, int x, int y) { return L.F + (y + 2) * L.fp + (x + 2) + L.a; }
-__device__ __forceinline__ const uint8_t *spP(const uint8_t *pl, const SpList &L, int x, int y) { return pl + (y + 2) * L.sp + (x + 2); }
-__device__ __forceinline__ const uint8_t *sp_plane(const SpList &L, int which, int x, int y)
-{
-    return which == 0 ? spF(L, x, y) : spP(which == 1 ? L.B : which == 2 ? L.H : L.J, L, x, y);
-}
-__device__ __forceinline__ int sp_pitch(const SpList &L, int which) { return which == 0 ? L.fp : L.sp; }
-__device__ __forceinline__ uint32_t lds_u32u(const uint8_t *p)
-{
-    const uint32_t *w = (const uint32_t *)((uintptr_t)p & ~(uintptr_t)3);
-    return __funnelshift_r(w[0], w[1], (uint32_t)((uintptr_t)p & 3) * 8);
-}
-__device__ __forceinline__ int half4(int a, int b, int c, int d) { return min(max((-2 * a + 18 * b + 18 * c - 2 * d + 16) >> 5, 0), 255); }
-
-__device__ void sp_build(SpList &L, const PlaneD &rF, int ox, int oy)
-{
-    __syncthreads();
-    const int a = load_window_t<NT>(L.F, L.fp, pat(rF, ox + L.sox - 2, oy + L.soy - 2), rF.stride, L.saw + 68, L.sah + 68);
-    if (threadIdx.x == 0) L.a = a;
-    __syncthreads();
-    const int bw = L.saw + 65, hw = L.saw + 66;
-    for (int i = threadIdx.x; i < (L.sah + 67) * bw; i += NT) {
-        const int r = i / bw, c = i - r * bw, y = r - 2;
-        const uint8_t *f = spF(L, c, y);
-        ((uint8_t *)spP(L.B, L, c, y))[0] = (uint8_t)half4(f[-2], f[-1], f[0], f[1]);
-    }
-    for (int i = threadIdx.x; i < (L.sah + 64) * hw; i += NT) {
-        const int r = i / hw, x = i - r * hw - 1;
-        const uint8_t *f = spF(L, x, r);
-        ((uint8_t *)spP(L.H, L, x, r))[0] = (uint8_t)half4(f[-2 * L.fp], f[-L.fp], f[0], f[L.fp]);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < (L.sah + 64) * bw; i += NT) {
-        const int r = i / bw, c = i - r * bw;
-        const uint8_t *b = spP(L.B, L, c, r);
-        ((uint8_t *)spP(L.J, L, c, r))[0] = (uint8_t)half4(b[-2 * L.sp], b[-L.sp], b[0], b[L.sp]);
-    }
-    __syncthreads();
-}
-
-// SAD of one PU against a plane position (p2 == nullptr) or the rounded average of two; sub: even rows only, doubled (SUB_SAD_SEARCH)
-__device__ __forceinline__ uint32_t sp_pu_sad(const uint8_t *s_src, int px, int py, int sz, const uint8_t *p1, int pitch1, const uint8_t *p2, int pitch2, bool sub)
-{
-    const int step = sub ? 2 : 1, nw = sz >> 2;
-    uint32_t acc = 0;
-    for (int r = 0; r < sz; r += step)
-        for (int j = 0; j < nw; ++j) {
-            const uint32_t sw = ((const uint32_t *)s_src)[(py + r) * 16 + (px >> 2) + j];
-            uint32_t pw = lds_u32u(p1 + r * pitch1 + 4 * j);
-            if (p2) pw = __vavgu4(pw, lds_u32u(p2 + r * pitch2 + 4 * j));
-            acc = __vsadu4(sw, pw) + acc;
-        }
-    return sub ? acc << 1 : acc;
-}
-
-// the two planes averaged at each of the 8 quarter positions (order L R T B TL TR BR BL) by the kind of the current best MV (0 integer, 1 horizontal
-// half, 2 vertical half, 3 diagonal half): {plane, dx, dy} x 2, planes 0 F, 1 B, 2 H, 3 J  (SetQuarterPelRefinementInputsOnTheFly :1540)
-__constant__ int8_t c_qpel[4][8][6] = {
-    {{1, 0, 0, 0, 0, 0}, {0, 0, 0, 1, 1, 0}, {2, 0, 0, 0, 0, 0}, {0, 0, 0, 2, 0, 1}, {1, 0, 0, 2, 0, 0}, {2, 0, 0, 1, 1, 0}, {2, 0, 1, 1, 1, 0}, {1, 0, 0, 2, 0, 1}},
-    {{0, -1, 0, 1, 0, 0}, {1, 0, 0, 0, 0, 0}, {3, 0, 0, 1, 0, 0}, {1, 0, 0, 3, 0, 1}, {2, -1, 0, 1, 0, 0}, {1, 0, 0, 2, 0, 0}, {1, 0, 0, 2, 0, 1}, {2, -1, 1, 1, 0, 0}},
-    {{3, 0, 0, 2, 0, 0}, {2, 0, 0, 3, 1, 0}, {0, 0, -1, 2, 0, 0}, {2, 0, 0, 0, 0, 0}, {1, 0, -1, 2, 0, 0}, {2, 0, 0, 1, 1, -1}, {2, 0, 0, 1, 1, 0}, {1, 0, 0, 2, 0, 0}},
-    {{2, -1, 0, 3, 0, 0}, {3, 0, 0, 2, 0, 0}, {1, 0, -1, 3, 0, 0}, {3, 0, 0, 1, 0, 0}, {2, -1, 0, 1, 0, -1}, {1, 0, -1, 2, 0, 0}, {1, 0, 0, 2, 0, 0}, {2, -1, 0, 1, 0, 0}}};
-__constant__ int8_t c_sp_dx[8] = {-1, 1, 0, 0, -1, 1, 1, -1}, c_sp_dy[8] = {0, 0, -1, 1, -1, -1, 1, 1};   // L R T B TL TR BR BL
-__constant__ uint8_t c_sp_dir[8] = {7, 3, 1, 5, 0, 2, 4, 6};    // *_POSITION codes of those positions (TL 0, T 1, TR 2, R 3, BR 4, B 5, BL 6, L 7)
-
-// bi-prediction: per fractional position (x & 3) + ((y & 3) << 2) the plane, or the two planes whose rounded average is the list's prediction
-// (SelectBuffer :2440, QuarterPelCompensation :2490); {plane, dx, dy, plane2 or -1, dx2, dy2} relative to the integer part of the MV
-__constant__ int8_t c_bip[16][6] = {{0, 0, 0, -1, 0, 0}, {0, 0, 0, 1, 1, 0}, {1, 1, 0, -1, 0, 0}, {1, 1, 0, 0, 1, 0}, {0, 0, 0, 2, 0, 1}, {1, 1, 0, 2, 0, 1}, {1, 1, 0, 3, 1, 1}, {1, 1, 0, 2, 1, 1},
-                                    {2, 0, 1, -1, 0, 0}, {2, 0, 1, 3, 1, 1}, {3, 1, 1, -1, 0, 0}, {3, 1, 1, 2, 1, 1}, {2, 0, 1, 0, 0, 1}, {2, 0, 1, 1, 1, 1}, {3, 1, 1, 1, 1, 1}, {2, 1, 1, 1, 1, 1}};
-
-// Half- and quarter-pel refinement of the PUs of one list.  s_d: [84][8] scratch, s_dir: psubPelDirection per n-slot, s_en: [3] size enables.
-__device__ void sp_refine(const SpList &L, const uint8_t *s_src, uint32_t *s_bsad, uint32_t *s_bmv, uint32_t *s_d, uint8_t *s_dir, const int *s_en, bool no8, bool sub)
-{
-    for (int pass = 0; pass < 2; ++pass) {
-        // (A) one thread per (PU, position): the distortion
-        for (int t = threadIdx.x; t < 84 * 8; t += NT) {
-            const int n = 1 + (t >> 3), pos = t & 7;
-            int px, py, sz;
-            pu_geom(n, px, py, sz);
-            const bool on = sz == 32 ? s_en[0] : sz == 16 ? s_en[1] : (s_en[2] && !no8);
-            uint32_t d = 0xffffffffu;
-            if (on) {
-                const uint32_t mv = s_bmv[n];
-                const int xmv = s16(mv & 0xffff), ymv = s16(mv >> 16);
-                if (pass == 0) {
-                    const int xs = (xmv >> 2) - L.sox + px, ys = (ymv >> 2) - L.soy + py;
-                    // L R: B(xs), B(xs + 1);  T B: H(ys), H(ys + 1);  TL TR BR BL: J
-                    const uint8_t *p = pos < 2 ? spP(L.B, L, xs + pos, ys) : pos < 4 ? spP(L.H, L, xs, ys + pos - 2)
-                                                : spP(L.J, L, xs + (pos == 5 || pos == 6), ys + (pos >= 6));
-                    d = sp_pu_sad(s_src, px, py, sz, p, L.sp, nullptr, 0, sub);
-                } else {
-                    const int kind = (ymv & 2) + ((xmv & 2) >> 1);
-                    // valid when the half-pel direction is this position or one of its two ring neighbours (integer best), or the opposite three (half best)
-                    const int want = (c_sp_dir[pos] + (kind ? 4 : 0)) & 7, diff = (s_dir[n] - want) & 7;
-                    if (diff == 0 || diff == 1 || diff == 7) {
-                        const int xs = ((xmv + 2) >> 2) - L.sox + px, ys = ((ymv + 2) >> 2) - L.soy + py;
-                        const int8_t *q = c_qpel[kind][pos];
-                        d = sp_pu_sad(s_src, px, py, sz, sp_plane(L, q[0], xs + q[1], ys + q[2]), sp_pitch(L, q[0]), sp_plane(L, q[3], xs + q[4], ys + q[5]), sp_pitch(L, q[3]), sub);
-                    }
-                }
-            }
-            s_d[t] = d;
-        }
-        __syncthreads();
-        // (B) one thread per PU: the reference's sequential update (strict '<', order L R T B TL TR BR BL)
-        for (int n = 1 + threadIdx.x; n < 85; n += NT) {
-            const uint32_t *d = s_d + (n - 1) * 8;
-            if (d[0] == 0xffffffffu && pass == 0) continue;      // size not refined on this LCU
-            uint32_t bs = s_bsad[n], mv = s_bmv[n];
-            const int xmv = s16(mv & 0xffff), ymv = s16(mv >> 16), stepmv = pass == 0 ? 2 : 1;
-            uint32_t best = 0xffffffffu;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if (d[k] < bs) { bs = d[k]; mv = ((uint32_t)(uint16_t)(ymv + c_sp_dy[k] * stepmv) << 16) | (uint16_t)(xmv + c_sp_dx[k] * stepmv); }
-                best = min(best, d[k]);
-            }
-            s_bsad[n] = bs; s_bmv[n] = mv;
-            if (pass == 0) {   // first match in the order L R T B TL TR BL BR (:1000-1023)
-                const int order[8] = {0, 1, 2, 3, 4, 5, 7, 6};
-                int dir = 0;
-#pragma unroll
-                for (int k = 7; k >= 0; --k) if (d[order[k]] == best) dir = c_sp_dir[order[k]];
-                s_dir[n] = (uint8_t)dir;
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// SuPelEnable :3035 (fractionalSearchModel 1): per-size gates from the LCU means of the full-pel MVs and SADs; warp 0
-__device__ void sp_enables(const uint32_t *s_bsad, const uint32_t *s_bmv, int model, int tl, bool cu16_on, int *s_en)
-{
-    if (threadIdx.x >= 32) return;
-    const int lane = threadIdx.x;
-    int e[3] = {1, 1, 1};
-    if (model == 1) {
-        uint32_t mag[3], avg[3];
-#pragma unroll
-        for (int l = 0; l < 3; ++l) {
-            const int first = l == 0 ? 1 : l == 1 ? 5 : 21, cnt = l == 0 ? 4 : l == 1 ? 16 : 64, sh = 2 + 2 * l;
-            int sx = 0, sy = 0; uint32_t sd = 0;
-            for (int k = lane; k < cnt; k += 32) { const uint32_t mv = s_bmv[first + k]; sx += s16(mv & 0xffff); sy += s16(mv >> 16); sd += s_bsad[first + k]; }
-            sx = (int)warp_sum((uint32_t)sx); sy = (int)warp_sum((uint32_t)sy); sd = warp_sum(sd);
-            const uint32_t ax = (uint32_t)(sx >> sh), ay = (uint32_t)(sy >> sh);
-            mag[l] = ax * ax + ay * ay;
-            avg[l] = sd >> sh;
-        }
-        const uint32_t thr = tl == 1 ? 32 * 32 : tl == 2 ? 80 * 80 : 48 * 48;
-        const int c32 = (mag[0] < thr ? 0 : 2) + (avg[0] < 32 * 32 * 6 ? 0 : 1), c16 = (mag[1] < thr ? 0 : 2) + (avg[1] < 16 * 16 * 2 ? 0 : 1), c8 = (mag[2] < thr ? 0 : 2) + (avg[2] < 8 * 8 * 2 ? 0 : 1);
-        const int row = tl > 2 ? 3 : tl;
-        // 32x32 gate per temporal layer row {0, 1, 2, other} and class: {1,0,1,0} {1,0,1,1} {1,0,1,0} {1,1,1,0}, bit (row * 4 + class)
-        e[0] = (int)((((0x5u) | (0xDu << 4) | (0x5u << 8) | (0x7u << 12)) >> (row * 4 + c32)) & 1u);
-        e[1] = c16 & 1;
-        e[2] = (row == 3 && c8 == 3) ? 0 : (c8 & 1);
-    }
-    if (lane == 0) { s_en[0] = e[0]; s_en[1] = e[1] && cu16_on; s_en[2] = e[2]; }
-}
-
-#ifndef ME_MIN_CTAS
+#define ME_NS k256
+#define ME_NT 256
 #define ME_MIN_CTAS 4
-#endif
-struct HmeRes { uint32_t sad; int x, y; };   // sad already doubled may exceed 24 bits -> keep 32
-
-// ============================================================================================
-// Picture kernel: one CTA per LCU
-// ============================================================================================
-template <bool SUBPEL>
-__global__ void __launch_bounds__(NT, SUBPEL ? 2 : ME_MIN_CTAS) me_picture_kernel(const __grid_constant__ MeArgs A)
-{
-    extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t *s_src = smem;                                   // 64*64
-    uint8_t *s_q = s_src + 4096;                             // quarter-res block 32x32 (pitch 64 like the reference's stride*2 view)
-    uint8_t *s_s16 = s_q + 2048;                             // sixteenth-res block, every other row, pitch 16
-    uint16_t *s_sad8 = (uint16_t *)(s_s16 + 128);            // [CHUNK][64]
-    uint32_t *s_sum = (uint32_t *)(s_sad8 + CHUNK * 64);     // [CHUNK][21]
-    uint32_t *s_bsad = s_sum + CHUNK * 21;                   // [2][85]
-    uint32_t *s_bmv = s_bsad + 170;                          // [2][85]
-    uint32_t *s_bi = s_bmv + 170;                            // [85]
-    uint32_t *s_red32 = s_bi + 85 + 1;                       // [8*6]
-    unsigned long long *s_red64 = (unsigned long long *)(s_red32 + 48);   // [8]
-    uint8_t *s_win = (uint8_t *)(((uintptr_t)(s_red64 + 8) + 15) & ~(uintptr_t)15);
-    __shared__ SpList s_spl[2];
-    __shared__ int s_en[4];
-    __shared__ uint8_t s_dir[88];
-    uint32_t *s_d = (uint32_t *)(s_win + A.win_bytes);      // [84][8], then the planes of both lists (SUBPEL only)
-
-    const svtb200_me_config &cfg = A.cfg;
-    const int lcu = blockIdx.x, lx = lcu % A.cols, ly = lcu / A.cols;
-    const int ox = lx * 64, oy = ly * 64;
-    const int W = cfg.pic_width, H = cfg.pic_height;
-    const int lw = min(64, W - ox), lh = min(64, H - oy);
-    const int nl = cfg.num_lists;
-    const int mult = c_hme_mult[cfg.hierarchical_levels][cfg.temporal_layer];
-    const PlaneD &sF = A.src[0];
-
-    // stage the source blocks (full 64x64 always: the 85-PU search reads the padded picture beyond lw/lh)
-    for (int i = threadIdx.x; i < 64 * 16; i += NT) {
-        const int r = i >> 4, j = i & 15;
-        ((uint32_t *)s_src)[i] = ld_u32_unaligned(pat(sF, ox + 4 * j, oy + r));
-    }
-    for (int i = threadIdx.x; i < 170; i += NT) { s_bsad[i] = 0; s_bmv[i] = 0; }
-    if (threadIdx.x < 86) s_bi[threadIdx.x] = 0;
-    if (cfg.enable_hme_l1) {
-        for (int i = threadIdx.x; i < 32 * 32; i += NT) {
-            const int r = i >> 5, c = i & 31;
-            s_q[r * 32 + c] = (r < (lh >> 1) && c < (lw >> 1)) ? *pat(A.src[1], (ox >> 1) + c, (oy >> 1) + r) : 0;
-        }
-    }
-    if (cfg.enable_hme_l0 && threadIdx.x < 128) {
-        const int r = threadIdx.x >> 4, c = threadIdx.x & 15;
-        s_s16[threadIdx.x] = (2 * r < (lh >> 2) && c < (lw >> 2)) ? *pat(A.src[2], (ox >> 2) + c, (oy >> 2) + 2 * r) : 0;
-    }
-    __syncthreads();
-
-    int sa_w[2] = {0, 0};
-    for (int li = 0; li < nl; ++li) {
-        const PlaneD &rF = A.ref[li][0], &rQ = A.ref[li][1], &rS = A.ref[li][2];
-        int cx = 0, cy = 0;
-        if (cfg.temporal_layer > 0 || li == 0) {
-            if (cfg.update_hme_search_center) {
-                // TestSearchAreaBounds, EbMotionEstimation.c:3363-3665: zero, A, B, C, [direct], D; SAD at the clamped
-                // vector, unclamped vector returned; ties resolve zero,A,B,C,direct,D.
-                const int tw = cfg.hme_l0_total_w, th = cfg.hme_l0_total_h;
-                int cxv[6] = {0, -tw, tw, 0, 0, 0}, cyv[6] = {0, 0, 0, -th, 0, th};
-                if (li == 1) {
-                    cxv[4] = 0 - (s16(s_bmv[0] & 0xffff) >> 2);
-                    cyv[4] = 0 - (s16(s_bmv[0] >> 16) >> 2);
-                }
-                int dx[6], dy[6];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    dx[k] = k ? clamp_center(ox, cxv[k], 63, rF.w) : 0;
-                    dy[k] = k ? clamp_center(oy, cyv[k], 63, rF.h) : 0;
-                }
-                uint32_t sad[6];
-                lcu_sads<6>(s_src, rF, ox, oy, lw, lh, dx, dy, 6, s_red32, sad);
-                int best = 0;
-#pragma unroll
-                for (int k = 1; k < 6; ++k) {
-                    if (k == 4 && li == 0) continue;
-                    if (sad[k] < sad[best]) best = k;
-                }
-                cx = cxv[best];
-                cy = cyv[best];
-            }
-            if (cfg.enable_hme && lh == 64) {
-                HmeRes l0[2][2], l1[2][2], l2[2][2];
-                const int nw = min((int)cfg.n_hme_regions_w, 2), nh = min((int)cfg.n_hme_regions_h, 2);
-                const int sh0 = cfg.update_hme_search_center ? 2 : 0, sh1 = cfg.update_hme_search_center ? 1 : 0;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    HmeRes &a0 = l0[q & 1][q >> 1], &a1 = l1[q & 1][q >> 1], &a2 = l2[q & 1][q >> 1];
-                    a0.sad = a1.sad = a2.sad = 0;
-                    a0.x = s16(cx >> sh0); a0.y = s16(cy >> sh0);
-                    a1.x = s16(cx >> sh1); a1.y = s16(cy >> sh1);
-                    a2.x = s16(cx); a2.y = s16(cy);
-                }
-                if (cfg.enable_hme_l0) {
-                    const bool one = cfg.one_quadrant_hme && !cfg.enable_hme_l1 && !cfg.enable_hme_l2;
-                    const int o4x = ox >> 2, o4y = oy >> 2;
-                    for (int qy = 0; qy < (one ? 1 : nh); ++qy)
-                        for (int qx = 0; qx < (one ? 1 : nw); ++qx) {
-                            int saw, sah, sox, soy;
-                            if (one) {   // EbHevcHmeOneQuadrantLevel0 :1847
-                                saw = (cfg.hme_l0_total_w * mult) / 100;
-                                sah = (cfg.hme_l0_total_h * mult) / 100;
-                                sox = -(saw >> 1) + (cx >> 2);
-                                soy = -(sah >> 1) + (cy >> 2);
-                            } else {     // EbHevcHmeLevel0 :2012
-                                saw = (cfg.hme_l0_w[qx] * mult) / 100;
-                                sah = (cfg.hme_l0_h[qy] * mult) / 100;
-                                int ddx = cx >> 2, ddy = cy >> 2;
-                                for (int k = 0; k < qx; ++k) ddx += (cfg.hme_l0_w[k] * mult) / 100;
-                                for (int k = 0; k < qy; ++k) ddy += (cfg.hme_l0_h[k] * mult) / 100;
-                                sox = -(((cfg.hme_l0_total_w * mult) / 100) >> 1) + ddx;
-                                soy = -(((cfg.hme_l0_total_h * mult) / 100) >> 1) + ddy;
-                            }
-                            sox = s16(sox); soy = s16(soy);
-                            clamp_window(o4x, rS.ox - 1, rS.w, sox, saw);
-                            clamp_window(o4y, rS.oy - 1, rS.h, soy, sah);
-                            if (one && (saw & 15)) saw = (saw >> 4) << 4;   // :1933-1936
-                            const int bw = lw >> 2, bh = (lh >> 2) >> 1;
-                            HmeRes &o = l0[qx][qy];
-                            uint32_t bs = 0xffffffu;
-                            int bx = o.x, by = o.y;
-                            if (saw > 0 && sah > 0) {
-                                const int wbytes = saw + bw - 1, wrows = sah + (bh - 1) * 2, wp = win_pitch(wbytes);
-                                __syncthreads();
-                                const int a = load_window_t<NT>(s_win, wp, pat(rS, o4x + sox, o4y + soy), rS.stride, wbytes, wrows);
-                                __syncthreads();
-                                sad_search(s_s16, 16, bw, bh, s_win, wp, a, 2, saw, sah, s_red64, bs, bx, by);
-                            }
-                            o.sad = bs * 2;
-                            o.x = s16(s16(bx + sox) * 4);
-                            o.y = s16(s16(by + soy) * 4);
-                        }
-                }
-                if (cfg.enable_hme_l1) {
-                    const int o2x = ox >> 1, o2y = oy >> 1;
-                    for (int qy = 0; qy < nh; ++qy)
-                        for (int qx = 0; qx < nw; ++qx) {   // EbHevcHmeLevel1 :2194
-                            const int w1 = cfg.hme_l1_w[qx];
-                            int saw = w1 < 8 ? 8 : (w1 & 7) ? w1 + (w1 - ((w1 >> 3) << 3)) : w1, sah = cfg.hme_l1_h[qy];
-                            int sox = s16(-(saw >> 1) + (l0[qx][qy].x >> 1)), soy = s16(-(sah >> 1) + (l0[qx][qy].y >> 1));
-                            clamp_window(o2x, rQ.ox - 1, rQ.w, sox, saw);
-                            clamp_window(o2y, rQ.oy - 1, rQ.h, soy, sah);
-                            const int bw = lw >> 1, bh = (lh >> 1) >> 1;
-                            HmeRes &o = l1[qx][qy];
-                            uint32_t bs = 0xffffffu;
-                            int bx = o.x, by = o.y;
-                            if (saw > 0 && sah > 0) {
-                                const int wbytes = saw + bw - 1, wrows = sah + (bh - 1) * 2, wp = win_pitch(wbytes);
-                                __syncthreads();
-                                const int a = load_window_t<NT>(s_win, wp, pat(rQ, o2x + sox, o2y + soy), rQ.stride, wbytes, wrows);
-                                __syncthreads();
-                                // the reference passes quarterLcuBufferStride*2 = 64 as block pitch: rows 0,2,4,.. of the 32-pitch block
-                                sad_search(s_q, 64, bw, bh, s_win, wp, a, 2, saw, sah, s_red64, bs, bx, by);
-                            }
-                            o.sad = bs * 2;
-                            o.x = s16(s16(bx + sox) * 2);
-                            o.y = s16(s16(by + soy) * 2);
-                        }
-                }
-                if (cfg.enable_hme_l2) {
-                    for (int qy = 0; qy < nh; ++qy)
-                        for (int qx = 0; qx < nw; ++qx) {   // EbHevcHmeLevel2 :2315
-                            const int w2 = cfg.hme_l2_w[qx];
-                            int saw = w2 < 8 ? 8 : (w2 & 7) ? w2 + (w2 - ((w2 >> 3) << 3)) : w2, sah = cfg.hme_l2_h[qy];
-                            int sox = s16(-(saw >> 1) + l1[qx][qy].x), soy = s16(-(sah >> 1) + l1[qx][qy].y);
-                            clamp_window(ox, 63, rF.w, sox, saw);
-                            clamp_window(oy, 63, rF.h, soy, sah);
-                            const int bw = lw, bh = lh >> 1;
-                            HmeRes &o = l2[qx][qy];
-                            uint32_t bs = 0xffffffu;
-                            int bx = o.x, by = o.y;
-                            if (saw > 0 && sah > 0) {
-                                const int wbytes = saw + bw - 1, wrows = sah + (bh - 1) * 2, wp = win_pitch(wbytes);
-                                __syncthreads();
-                                const int a = load_window_t<NT>(s_win, wp, pat(rF, ox + sox, oy + soy), rF.stride, wbytes, wrows);
-                                __syncthreads();
-                                sad_search(s_src, 128, bw, bh, s_win, wp, a, 2, saw, sah, s_red64, bs, bx, by);
-                            }
-                            o.sad = bs * 2;
-                            o.x = s16(bx + sox);
-                            o.y = s16(by + soy);
-                        }
-                }
-                // best region of the last enabled level; first minimum in width-fastest order (:3959-4030)
-                HmeRes(*lvl)[2] = cfg.enable_hme_l2 ? l2 : cfg.enable_hme_l1 ? l1 : l0;
-                if (cfg.enable_hme_l0 || cfg.enable_hme_l1 || cfg.enable_hme_l2) {
-                    uint32_t bsd = lvl[0][0].sad;
-                    int hx = lvl[0][0].x, hy = lvl[0][0].y;
-                    const bool onlyone = (!cfg.enable_hme_l1 && !cfg.enable_hme_l2) && cfg.one_quadrant_hme;
-                    if (!onlyone)
-                        for (int qy = 0; qy < nh; ++qy)
-                            for (int qx = (qy == 0 ? 1 : 0); qx < nw; ++qx)
-                                if (lvl[qx][qy].sad < bsd) { bsd = lvl[qx][qy].sad; hx = lvl[qx][qy].x; hy = lvl[qx][qy].y; }
-                    if (cfg.enable_hme_l2 && cfg.ref_poc[0] == cfg.ref_poc[1] && li == 1 && nw * nh > 1) {
-                        // same-POC second list: second-best region after the reference's selection sort, whose
-                        // [q / nw][q % nw] indexing is kept as is (:4032-4060)
-                        const int nq = nw * nh;
-                        for (int p = 0; p < nq - 1; ++p)
-                            for (int q = p + 1; q < nq; ++q)
-                                if (l2[p / nw][p % nw].sad > l2[q / nw][q % nw].sad) {
-                                    HmeRes t = l2[p / nw][p % nw]; l2[p / nw][p % nw] = l2[q / nw][q % nw]; l2[q / nw][q % nw] = t;
-                                }
-                        hx = l2[0][1].x; hy = l2[0][1].y;
-                    }
-                    cx = hx; cy = hy;
-                } else { cx = 0; cy = 0; }
-            }
-        }
-        int saw = min((int)cfg.search_area_w, 127), sah = min((int)cfg.search_area_h, 127);
-        if (cx != 0 || cy != 0) {   // EbHevcCheckZeroZeroCenter :2946
-            if (cfg.update_hme_search_center) { cx = clamp_center(ox, cx, 63, rF.w); cy = clamp_center(oy, cy, 63, rF.h); }
-            const int dx[2] = {0, cx}, dy[2] = {0, cy};
-            uint32_t sad[2];
-            lcu_sads<2>(s_src, rF, ox, oy, lw, lh, dx, dy, 2, s_red32, sad);
-            const uint32_t rate = mvd_bits(s16(cx) << 2, s16(cy) << 2, cfg.mvd_bits);
-            const unsigned long long zc = (unsigned long long)sad[0] << 8;
-            const unsigned long long hc = ((unsigned long long)sad[1] << 8) + (((unsigned long long)cfg.lambda * rate + (1u << 22)) >> 23);
-            if (zc <= hc) { cx = 0; cy = 0; }
-        }
-        int sox = s16(cx - (saw >> 1)), soy = s16(cy - (sah >> 1));
-        clamp_window(ox, 63, W, sox, saw);
-        clamp_window(oy, 63, H, soy, sah);
-        sa_w[li] = saw;
-        // full-pel 85-PU search
-        {
-            const int wbytes = saw + 63, wrows = sah + 63, wp = win_pitch(wbytes);
-            __syncthreads();
-            for (int i = threadIdx.x; i < 85; i += NT) s_bsad[li * 85 + i] = MAX_SAD_INIT;
-            const int a = load_window_t<NT>(s_win, wp, pat(rF, ox + sox, oy + soy), rF.stride, wbytes, wrows);
-            __syncthreads();
-            fullpel_search(s_src, s_win, wp, a, sox, soy, saw, sah, s_sad8, s_sum, s_bsad + li * 85, s_bmv + li * 85);
-        }
-        if (SUBPEL) {   // MotionEstimateLcu :4242-4316
-            __syncthreads();
-            SpList &L = s_spl[li];
-            if (threadIdx.x == 0) {
-                uint8_t *base = (uint8_t *)(s_d + 84 * 8) + (size_t)li * (A.sp_f_bytes + 3 * A.sp_p_bytes);
-                L.F = base; L.B = base + A.sp_f_bytes; L.H = L.B + A.sp_p_bytes; L.J = L.H + A.sp_p_bytes;
-                L.fp = A.sp_fp; L.sp = A.sp_sp; L.a = 0;
-                L.sox = sox; L.soy = soy; L.saw = saw; L.sah = sah;
-            }
-            sp_enables(s_bsad + li * 85, s_bmv + li * 85, cfg.fractional_search_model, cfg.temporal_layer, cfg.cu16x16_mode == 0, s_en);
-            sp_build(L, rF, ox, oy);
-            sp_refine(L, s_src, s_bsad + li * 85, s_bmv + li * 85, s_d, s_dir, s_en, cfg.cu8x8_mode == 1, cfg.fractional_search_method == 0);
-        }
-    }
-    (void)sa_w;
-    __syncthreads();
-
-    // integer-pel bi-prediction SAD (EbHevcBiPredictionCompensation :2742 -> EbHevcBiPredAverging :2600, SUB_SAD_SEARCH):
-    // SAD(src, avg(ref0 @mv0, ref1 @mv1)) on every other row, doubled.  One warp per PU.
-    if (nl == 2) {
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        const int npu = cfg.cu16x16_mode ? 5 : (cfg.cu8x8_mode ? 21 : 85);
-        const bool sub = cfg.fractional_search_method == 0;
-        for (int n = wid; n < npu; n += NT / 32) {
-            int px, py, sz;
-            pu_geom(n, px, py, sz);
-            const int nw = sz >> 2, step = sub ? 2 : 1, items = (sz / step) * nw;
-            uint32_t acc = 0;
-            if (SUBPEL) {
-                // every list's prediction is one of its planes, or the rounded average of two, chosen by the fractional position
-                const uint8_t *pa[2], *pb[2];
-                int sa[2], sb[2];
-#pragma unroll
-                for (int l = 0; l < 2; ++l) {
-                    const SpList &L = s_spl[l];
-                    const uint32_t mv = s_bmv[l * 85 + n];
-                    const int mx = s16(mv & 0xffff), my = s16(mv >> 16);
-                    const int ix = (mx >> 2) - L.sox + px, iy = (my >> 2) - L.soy + py;
-                    const int8_t *q = c_bip[(mx & 3) + ((my & 3) << 2)];
-                    pa[l] = sp_plane(L, q[0], ix + q[1], iy + q[2]); sa[l] = sp_pitch(L, q[0]);
-                    pb[l] = q[3] < 0 ? nullptr : sp_plane(L, q[3], ix + q[4], iy + q[5]); sb[l] = q[3] < 0 ? 0 : sp_pitch(L, q[3]);
-                }
-                for (int i = lane; i < items; i += 32) {
-                    const int r = (i / nw) * step, j = i - (i / nw) * nw;
-                    const uint32_t sw = ((const uint32_t *)s_src)[(py + r) * 16 + (px >> 2) + j];
-                    uint32_t p0 = lds_u32u(pa[0] + r * sa[0] + 4 * j), p1 = lds_u32u(pa[1] + r * sa[1] + 4 * j);
-                    if (pb[0]) p0 = __vavgu4(p0, lds_u32u(pb[0] + r * sb[0] + 4 * j));
-                    if (pb[1]) p1 = __vavgu4(p1, lds_u32u(pb[1] + r * sb[1] + 4 * j));
-                    acc += __vsadu4(sw, __vavgu4(p0, p1));
-                }
-            } else {
-                const int x0 = s16(s_bmv[n] & 0xffff) >> 2, y0 = s16(s_bmv[n] >> 16) >> 2;
-                const int x1 = s16(s_bmv[85 + n] & 0xffff) >> 2, y1 = s16(s_bmv[85 + n] >> 16) >> 2;
-                const uint8_t *b0 = pat(A.ref[0][0], ox + px + x0, oy + py + y0), *b1 = pat(A.ref[1][0], ox + px + x1, oy + py + y1);
-                const ptrdiff_t st0 = A.ref[0][0].stride, st1 = A.ref[1][0].stride;
-                const int lgnw = 31 - __clz(nw);
-#pragma unroll 4
-                for (int i = lane; i < items; i += 32) {
-                    const int r = (i >> lgnw) * step, j = i & (nw - 1);
-                    const uint32_t sw = ((const uint32_t *)s_src)[(py + r) * 16 + (px >> 2) + j];
-                    const uint32_t p0 = ld_u32_unaligned(b0 + r * st0 + 4 * j);
-                    const uint32_t p1 = ld_u32_unaligned(b1 + r * st1 + 4 * j);
-                    acc += __vsadu4(sw, __vavgu4(p0, p1));
-                }
-            }
-            acc = warp_sum(acc);
-            if (lane == 0) s_bi[n] = sub ? acc << 1 : acc;
-        }
-    }
-    __syncthreads();
-
-    // MeCuResults assembly, EbMotionEstimation.c:4321-4438
-    if (threadIdx.x < 85) {
-        const int pu = threadIdx.x;
-        const int n = pu > 20 ? c_tab8[pu - 21] + 21 : pu > 4 ? c_tab32[pu - 5] + 5 : pu;
-        int total = nl;
-        if (nl == 2 && (cfg.cu8x8_mode == 0 || pu < 21) && (cfg.cu16x16_mode == 0 || pu < 5)) total = 3;
-        const uint32_t a = s_bsad[n], b = s_bsad[85 + n], c = s_bi[n];
-        uint32_t d[3] = {0, 0, 0};
-        uint8_t dir[3] = {0, 0, 0};
-        if (total == 3) {   // Sort3Elements :2919
-            if (a <= b && a <= c) { d[0] = a; dir[0] = 0; if (b <= c) { d[1] = b; dir[1] = 1; d[2] = c; dir[2] = 2; } else { d[1] = c; dir[1] = 2; d[2] = b; dir[2] = 1; } }
-            else if (b <= a && b <= c) { d[0] = b; dir[0] = 1; if (a <= c) { d[1] = a; dir[1] = 0; d[2] = c; dir[2] = 2; } else { d[1] = c; dir[1] = 2; d[2] = a; dir[2] = 0; } }
-            else if (a <= b) { d[0] = c; dir[0] = 2; d[1] = a; dir[1] = 0; d[2] = b; dir[2] = 1; }
-            else { d[0] = c; dir[0] = 2; d[1] = b; dir[1] = 1; d[2] = a; dir[2] = 0; }
-        } else if (total == 2) {
-            if (a <= b) { d[0] = a; dir[0] = 0; d[1] = b; dir[1] = 1; } else { d[0] = b; dir[0] = 1; d[1] = a; dir[1] = 0; }
-        } else { d[0] = a; dir[0] = 0; }
-        svtb200_me_pu_result r;
-        r.x_mv_l0 = (int16_t)(s_bmv[n] & 0xffff); r.y_mv_l0 = (int16_t)(s_bmv[n] >> 16);
-        r.x_mv_l1 = (int16_t)(s_bmv[85 + n] & 0xffff); r.y_mv_l1 = (int16_t)(s_bmv[85 + n] >> 16);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { r.distortion[k] = d[k]; r.direction[k] = dir[k]; }
-        r.total_me_candidates = (uint8_t)total;
-        A.results[(size_t)lcu * 85 + pu] = r;
-        s_sum[pu] = d[0];
-    }
-    if (A.best_sad || A.best_mv)
-        for (int i = threadIdx.x; i < 170; i += NT) {
-            if (A.best_sad) A.best_sad[(size_t)lcu * 170 + i] = s_bsad[i];
-            if (A.best_mv) A.best_mv[(size_t)lcu * 170 + i] = s_bmv[i];
-        }
-    if (A.rc) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t t = 0;
-            if (cfg.rate_control_mode) for (int i = 0; i < 16; ++i) t += s_sum[5 + i];
-            A.rc[lcu] = t;
-        }
-    }
+namespace svtb200 {
+#include "me_kernels.inc"
 }
+#undef ME_NS
+#undef ME_NT
+#undef ME_MIN_CTAS
+#define ME_NS k128
+#define ME_NT 128
+#define ME_MIN_CTAS 7
+namespace svtb200 {
+#include "me_kernels.inc"
+}
+#undef ME_NS
+#undef ME_NT
+#undef ME_MIN_CTAS
+
+namespace svtb200 {
+using namespace k256;      // leaf kernels and the sub-pel picture kernel
 
 static size_t me_fixed_smem()
 {
@@ -1020,12 +128,12 @@ static int launch_me(const svtb200_me_config *cfg, const PlaneD src[3], const Pl
     if (smem > 227 * 1024) { set_error("me: this search configuration needs %zu B of shared memory (> 227 KB)", smem); return SVTB200_ERR_UNSUPPORTED; }
     static thread_local size_t smem_set[2] = {0, 0};
     if (smem > smem_set[subpel]) {
-        if (subpel) SVTB200_CUDA_TRY(cudaFuncSetAttribute(me_picture_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
-        else SVTB200_CUDA_TRY(cudaFuncSetAttribute(me_picture_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+        if (subpel) SVTB200_CUDA_TRY(cudaFuncSetAttribute(k256::me_picture_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+        else SVTB200_CUDA_TRY(cudaFuncSetAttribute(k128::me_picture_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
         smem_set[subpel] = smem;
     }
-    if (subpel) me_picture_kernel<true><<<A.cols * A.rows, NT, smem, st>>>(A);
-    else me_picture_kernel<false><<<A.cols * A.rows, NT, smem, st>>>(A);
+    if (subpel) k256::me_picture_kernel<true><<<A.cols * A.rows, k256::NT, smem, st>>>(A);
+    else k128::me_picture_kernel<false><<<A.cols * A.rows, k128::NT, smem, st>>>(A);
     SVTB200_COUNT_LAUNCH();
     SVTB200_CUDA_TRY(cudaGetLastError());
     return SVTB200_OK;

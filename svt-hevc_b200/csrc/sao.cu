@@ -56,8 +56,9 @@ __global__ void __launch_bounds__(ST_NT) sao_stats_kernel(const __grid_constant_
     const int lw = min(64, A.W - lx * 64) >> sh, lh = min(64, A.H - ly * 64) >> sh;
     const uint8_t *r = A.rec[c].p + (size_t)oy * A.rec[c].stride + ox, *s = A.src[c].p + (size_t)oy * A.src[c].stride + ox;
     const int wpr = lw >> 2;
+    const SmallDiv d_wpr = mk_div(wpr);
     for (int i = threadIdx.x; i < lh * wpr; i += ST_NT) {
-        const int y = i / wpr, x4 = i - y * wpr;
+        const int y = udiv(i, d_wpr), x4 = i - y * wpr;
         ((uint32_t *)(s_rec + y * 72))[1 + x4] = *(const uint32_t *)(r + (size_t)y * A.rec[c].stride + 4 * x4);   // block origins are 4-aligned
     }
     int *my = s_h + threadIdx.x;
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(ST_NT) sao_stats_kernel(const __grid_constant_
     __syncthreads();
     const int n_items = (lh - 2) * wpr;
     for (int i = threadIdx.x; i < n_items; i += ST_NT) {
-        const int y = 1 + i / wpr, xw = i % wpr;
+        const int y0 = udiv(i, d_wpr), y = 1 + y0, xw = i - y0 * wpr;
         const uint32_t *row = (const uint32_t *)(s_rec + y * 72) + 1 + xw;
         const uint32_t up0 = row[-19], up1 = row[-18], up2 = row[-17], c0 = row[-1], v = row[0], c2 = row[1], dn0 = row[17], dn1 = row[18], dn2 = row[19];
         const uint32_t sv = *(const uint32_t *)(s + (size_t)y * A.src[c].stride + 4 * xw);
@@ -94,13 +95,11 @@ __global__ void __launch_bounds__(ST_NT) sao_stats_kernel(const __grid_constant_
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     svtb200_sao_stats *o = A.out + job;
     for (int row = wid; row < ST_ROWS; row += ST_NT / 32) {
-        int dsum = 0, csum = 0;
+        // the packed words add as integers: (sum of counts << 16) + sum of diffs, the latter within s16 for four threads (4 * 32 samples * 127)
+        int w = 0;
 #pragma unroll
-        for (int q = 0; q < ST_NT / 32; ++q) {
-            const int w = s_h[row * ST_NT + lane + 32 * q], dd = (int)(short)(w & 0xffff);
-            dsum += dd;
-            csum += (w - dd) >> 16;
-        }
+        for (int q = 0; q < ST_NT / 32; ++q) w += s_h[row * ST_NT + lane + 32 * q];
+        int dsum = (int)(short)(w & 0xffff), csum = (w - dsum) >> 16;
         dsum = __reduce_add_sync(0xffffffffu, dsum);
         csum = __reduce_add_sync(0xffffffffu, csum);
         if (lane == 0) {
