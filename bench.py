@@ -47,6 +47,12 @@ STAGES = ["me_picture (+ sub-pel on layer 0)", "ois_picture", "mc_batch", "tq_ba
 ALG = {"me": 9384 * 2, "ois": 4096 + 21 * 5, "mc_uni": 12288, "mc_bi": 18432, "tq": 30720, "dlf": 12864, "sao_stats": 12288 + 3 * 312, "sao_apply": 12288}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this command (profiles/r01_s3_summary.txt;
+# ME = 7/8 integer-pel launches + 1/8 sub-pel launches of the mini-GOP).  Writes mostly stay in the 126 MB L2 during a capture, so the figure is read-dominated.
+NCU_TRAFFIC = {"me": (7 * (27.690752 + 3.109120) + (18.473472 + 0.128512)) / 8 * 1e6, "ois": 8.635648e6, "mc": 13.198592e6, "tq": 27.984128e6, "sao_stats": 25.262080e6}
+NCU_TRAFFIC_SOURCE = "profiles/r01_s3_summary.txt"
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -466,7 +472,8 @@ def run_b200(args):
             "roofline": {"kernel": {"me": "me_picture_kernel", "ois": "ois_picture_kernel", "mc": "mc_batch_kernel", "tq": "tq_batch_kernel", "dlf": "dlf_pass_kernel",
                                     "sao_stats": "sao_stats_kernel", "sao_apply": "sao_apply_kernel"}[dom],
                          "bound": "hbm", "achieved": alg[dom] / k_avg_s / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg[dom] / k_avg_s / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": alg[dom] / k_avg_s / 1e9 / peak, "traffic": NCU_TRAFFIC.get(dom), "traffic_source": NCU_TRAFFIC_SOURCE if dom in NCU_TRAFFIC else None,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg[dom], "avg_launch_ms": k_avg_s * 1e3},
             "stages": per_stage,
             "me_ms_by_temporal_layer": {str(tl): float(np.mean([t for j, t in enumerate(serial_ms["me"]) if wl.tl(args.warmup + j) == tl])) for tl in sorted(set(TL_PATTERN))
