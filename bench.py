@@ -14,7 +14,7 @@ candidate; SAO parameters and boundary strengths are fixed per-LCU tables.  Both
           alternate between --streams compute streams, per-stage events are taken inside that timed region (`stages`), and once more
           with a single stream (`stages_serial`: what each kernel costs alone)
   e2e   : the same step through the C ABI from HOST (pinned) buffers: H2D of Y/Cb/Cr, kernels, D2H of ME results, OIS candidates,
-          quantised coefficients, nz counts and SAO statistics; three frames in flight (copy-in / compute / copy-out streams); coefficients leave as the packed stream of coded TUs
+          quantised coefficients, nz counts and SAO statistics; --inflight frames in flight (copy-in / compute / copy-out streams); coefficients leave as the packed stream of coded TUs
   N > 1 : independent closed GOPs / streams per GPU -- weak scaling, no data-path collective
   --impl reference : the reference's own CPU implementation of the same stages (oracle/_ref, one frame per host thread)
 """
@@ -269,7 +269,8 @@ def run_b200(args):
                           ois_c=self.d_ois_cand.data_ptr(), off=self.d_off.data_ptr(), stream=self.d_stream.data_ptr(), small=self.d_small.data_ptr(),
                           h_small=self.h_small.data_ptr(), h_stream=self.h_stream.data_ptr(), yint=self.in_t[0][PAD:, PAD:].data_ptr())
 
-    slots = [Slot(), Slot(), Slot()]      # e2e: three frames in flight (H2D / kernels / D2H of consecutive frames overlap, the host runs two frames ahead)
+    NS = max(3, args.inflight)            # e2e: NS frames in flight (H2D / kernels / D2H of consecutive frames overlap, the host runs NS - 1 frames ahead)
+    slots = [Slot() for _ in range(NS)]
     d_res = slots[0].d_res
     d_tq = torch.from_numpy(wl.tq_jobs.view(np.uint8)).to(dev)
     d_vbs, d_hbs, d_qp = (torch.from_numpy(a.copy()).to(dev) for a in (wl.vbs, wl.hbs, wl.qp_array))
@@ -337,6 +338,7 @@ def run_b200(args):
     s_in, s_out, s_small = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
 
     d2h_bytes = []
+    skip = set(x for x in args.e2e_skip.split(",") if x)
 
     def finish_slot(sl):
         """second half of a frame's D2H: the packed coefficient stream, whose length is known once the offsets have arrived"""
@@ -344,32 +346,37 @@ def run_b200(args):
             return
         sl.ev_small.synchronize()
         total = int(sl.h_off_total[-1])
-        S.copy_async(sl.p["h_stream"], sl.p["stream"], 2 * total, True, s_out.cuda_stream)
+        if "d2h" not in skip:
+            S.copy_async(sl.p["h_stream"], sl.p["stream"], 2 * total, True, s_out.cuda_stream)
         sl.ev_out.record(s_out)
         d2h_bytes.append(2 * total + sl.small_bytes)
         sl.pending = False
 
     def step_e2e(i):
         """Frame i from pinned host buffers: H2D on the copy-in stream, kernels on the compute stream, D2H of everything the host-side
-        encoder consumes on the copy-out stream; three frames in flight, every copy inside the timed region."""
+        encoder consumes on the copy-out stream; NS frames in flight, every copy inside the timed region."""
         k = i % RING
-        sl = slots[i % 3]
-        finish_slot(sl)                                                                    # frame i - 3 (same slot) is completely out
+        sl = slots[i % NS]
+        finish_slot(sl)                                                                    # frame i - NS (same slot) is completely out
         s_in.wait_event(sl.ev_cmp)                                                         # the kernels that read this slot's inputs are done
-        S.yuv_picture_upload(sl.in_yuv, hp[k][0], W, hp[k][1], W // 2, hp[k][2], W // 2, 1, s_in.cuda_stream)    # H2D: Y + Cb + Cr
+        if "h2d" not in skip:
+            S.yuv_picture_upload(sl.in_yuv, hp[k][0], W, hp[k][1], W // 2, hp[k][2], W // 2, 1, s_in.cuda_stream)    # H2D: Y + Cb + Cr
         sl.ev_in.record(s_in)
         cs = cstreams[i % len(cstreams)]                                                   # consecutive frames alternate compute streams, as in the resident loop
         cs.wait_event(sl.ev_in)
         cs.wait_event(sl.ev_out)                                                           # this slot's previous results have left the device
-        sl.pa.build_from_device(sl.p["yint"], sl.in_t[0].shape[1], cs.cuda_stream)         # pad + decimate on the device
+        if "pa" not in skip:
+            sl.pa.build_from_device(sl.p["yint"], sl.in_t[0].shape[1], cs.cuda_stream)     # pad + decimate on the device
         pipeline(i, sl.pa, sl.in_yuv, sl, cs)
-        S.tq_pack_coeffs_dev(sl.coeff, p_tq, sl.p["nz"], n_tq, sl.p["stream"], sl.cap, sl.p["off"], cs.cuda_stream)
+        if "pack" not in skip:
+            S.tq_pack_coeffs_dev(sl.coeff, p_tq, sl.p["nz"], n_tq, sl.p["stream"], sl.cap, sl.p["off"], cs.cuda_stream)
         sl.ev_cmp.record(cs)
         s_small.wait_event(sl.ev_cmp)
-        S.copy_async(sl.p["h_small"], sl.p["small"], sl.d_small.numel(), True, s_small.cuda_stream)    # D2H: ME results, TU offsets, nz, SAO stats, OIS
+        if "d2h" not in skip:
+            S.copy_async(sl.p["h_small"], sl.p["small"], sl.d_small.numel(), True, s_small.cuda_stream)    # D2H: ME results, TU offsets, nz, SAO stats, OIS
         sl.ev_small.record(s_small)
         sl.pending = True
-        finish_slot(slots[(i + 1) % 3])                                                    # frame i - 2: its offsets arrived long ago, its stream goes out now
+        finish_slot(slots[(i + 1) % NS])                                                   # frame i - NS + 1: its offsets arrived long ago, its stream goes out now
 
     def barrier():
         torch.cuda.synchronize()
@@ -430,15 +437,15 @@ def run_b200(args):
 
     for i in range(args.warmup):
         step_e2e(i)
-    for sl in slots[:3]:
+    for sl in slots[:NS]:
         finish_slot(sl)
     barrier()
     w0 = time.perf_counter()
     d2h_bytes.clear()
     for i in range(args.steps):
         step_e2e(args.warmup + i)
-    for q in range(1, 4):
-        finish_slot(slots[(args.warmup + args.steps - 1 + q) % 3])
+    for q in range(1, NS + 1):
+        finish_slot(slots[(args.warmup + args.steps - 1 + q) % NS])
     barrier()
     e2e_s = time.perf_counter() - w0
 
@@ -468,6 +475,7 @@ def run_b200(args):
             "e2e": {"value": ctus / (e2e_ms * 1e-3), "unit": "CTU/s", "fps": ctus / (e2e_ms * 1e-3) / N_LCU,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_link": pcie},
             "gpu_launches": int(launches),
+            **({"diagnosis_only_e2e_skip": sorted(skip)} if skip else {}),
             "clocks": sampler.summary(),
             "roofline": {"kernel": {"me": "me_picture_kernel", "ois": "ois_picture_kernel", "mc": "mc_batch_kernel", "tq": "tq_batch_kernel", "dlf": "dlf_pass_kernel",
                                     "sao_stats": "sao_stats_kernel", "sao_apply": "sao_apply_kernel"}[dom],
@@ -569,6 +577,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-skip", default="", help="diagnosis only: comma list of e2e parts to leave out (h2d, d2h, pack, pa); a run with this set is not a bench value")
+    ap.add_argument("--inflight", type=int, default=5, help="frames in flight in the end-to-end loop (device + pinned host buffers per frame)")
     ap.add_argument("--streams", type=int, default=2, help="compute streams the resident loop spreads consecutive frames over")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

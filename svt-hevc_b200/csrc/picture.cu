@@ -16,6 +16,12 @@ __global__ void __launch_bounds__(256) decim_pad_kernel(const uint8_t *full, int
     const int sy = min(max(y - opad, 0), h - 1) * step;
     const uint8_t *srow = full + (size_t)(fpad + sy) * fstride + fpad;
     const bool row_in = (y >= opad && y < opad + h);
+    uint8_t *o = out + (size_t)y * ostride + x4;
+    if (skip_interior && row_in && x4 >= opad && x4 + 3 < opad + w) return;   // in-place full plane: interior untouched
+    if (step == 1 && x4 >= opad && x4 + 3 < opad + w && ((((uintptr_t)(srow + x4 - opad)) | (uintptr_t)o) & 3) == 0) {
+        *(uint32_t *)o = *(const uint32_t *)(srow + x4 - opad);              // four interior samples of a full-resolution plane: one word
+        return;
+    }
     uint8_t v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -23,8 +29,6 @@ __global__ void __launch_bounds__(256) decim_pad_kernel(const uint8_t *full, int
         const int sx = min(max(x - opad, 0), w - 1) * step;
         v[k] = srow[sx];
     }
-    uint8_t *o = out + (size_t)y * ostride + x4;
-    if (skip_interior && row_in && x4 >= opad && x4 + 3 < opad + w) return;   // in-place full plane: interior untouched
     if (x4 + 3 < tw && (((uintptr_t)o) & 3) == 0 && !(skip_interior && row_in)) {
         *(uint32_t *)o = v[0] | (v[1] << 8) | (v[2] << 16) | ((uint32_t)v[3] << 24);
     } else {
@@ -38,7 +42,9 @@ __global__ void __launch_bounds__(256) decim_pad_kernel(const uint8_t *full, int
     }
 }
 
-static int build_planes(const svtb200_pa_picture *d, cudaStream_t st)
+// src: full-resolution luma the planes are derived from (interior origin at src + spad * (sstride + 1)).  in_place: src is d->full itself,
+// whose interior is already there (only its border is written).
+static int build_planes(const svtb200_pa_picture *d, cudaStream_t st, const uint8_t *src, int sstride, int spad, bool in_place)
 {
     const svtb200_plane *pl[3] = {&d->full, &d->quarter, &d->sixteenth};
     const int steps[3] = {1, 2, 4};
@@ -49,8 +55,7 @@ static int build_planes(const svtb200_pa_picture *d, cudaStream_t st)
         const int tw = p.width + 2 * p.origin_x, th = p.height + 2 * p.origin_y;
         dim3 grid((tw / 4 + 255) / 256 + ((tw / 4) % 256 ? 0 : 0) + 1, th);
         grid.x = ((tw + 3) / 4 + 255) / 256;
-        decim_pad_kernel<<<grid, 256, 0, st>>>(d->full.buf, (int)d->full.stride, d->full.origin_x, p.buf, (int)p.stride, p.origin_x, p.width,
-                                               p.height, steps[k], k == 0);
+        decim_pad_kernel<<<grid, 256, 0, st>>>(src, sstride, spad, p.buf, (int)p.stride, p.origin_x, p.width, p.height, steps[k], k == 0 && in_place);
         SVTB200_COUNT_LAUNCH();
     }
     SVTB200_CUDA_TRY(cudaGetLastError());
@@ -90,9 +95,8 @@ int svtb200_pa_picture_build_dev(const svtb200_pa_picture *dev, const uint8_t *d
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const svtb200_plane &f = dev->full;
-    SVTB200_CUDA_TRY(cudaMemcpy2DAsync(f.buf + (size_t)f.origin_y * f.stride + f.origin_x, f.stride, dev_luma, dev_stride, f.width, f.height,
-                                       cudaMemcpyDeviceToDevice, st));
-    return build_planes(dev, st);
+    (void)f;
+    return build_planes(dev, st, dev_luma, (int)dev_stride, 0, false);      // all three planes straight from the caller's luma: no intermediate copy
 }
 
 int svtb200_pa_picture_upload(const svtb200_pa_picture *dev, const uint8_t *host_luma, uint32_t host_stride, void *cuda_stream)
@@ -104,7 +108,7 @@ int svtb200_pa_picture_upload(const svtb200_pa_picture *dev, const uint8_t *host
     const svtb200_plane &f = dev->full;
     SVTB200_CUDA_TRY(cudaMemcpy2DAsync(f.buf + (size_t)f.origin_y * f.stride + f.origin_x, f.stride, host_luma, host_stride, f.width, f.height,
                                        cudaMemcpyHostToDevice, st));
-    return build_planes(dev, st);
+    return build_planes(dev, st, f.buf, (int)f.stride, f.origin_x, true);
 }
 
 int svtb200_yuv_picture_upload(const svtb200_yuv_picture *dev, const void *host_y, uint32_t host_y_stride, const void *host_cb, uint32_t host_cb_stride,

@@ -448,29 +448,45 @@ __global__ void __launch_bounds__(TQ_NT) tq_batch_kernel(const __grid_constant__
 // planes are packed on the device into one dense stream: TU after TU in job order, size x size int16 row-major, TUs with nz == 0 skipped.
 // offsets[j] = first element of job j in the stream, offsets[n_jobs] = total elements.
 constexpr int PK_SCAN_NT = 1024;
+constexpr int PK_TILE = 32 * 1024;      // jobs per pass of the scan kernel (one size code byte each in shared memory)
+// One CTA: per pass the size codes of PK_TILE jobs are fetched with coalesced loads (jobs of TUs without coefficients count 0) and kept as
+// bytes in shared memory; every thread then owns a run of consecutive jobs, the run totals are scanned across the CTA with shuffles, and the
+// offsets of the run are written.  (The earlier version walked the job array with a per-thread stride: ~50 us of dependent, uncoalesced loads.)
 __global__ void __launch_bounds__(PK_SCAN_NT) tq_pack_scan_kernel(const svtb200_tq_job *jobs, const uint32_t *nz, int n_jobs, uint32_t *offsets)
 {
+    __shared__ uint8_t s_code[PK_TILE];          // 0: not coded, else log2(size) (size * size = 1 << 2 * code)
     __shared__ uint32_t s_part[PK_SCAN_NT / 32];
-    const int per = (n_jobs + PK_SCAN_NT - 1) / PK_SCAN_NT, j0 = threadIdx.x * per, j1 = min(n_jobs, j0 + per);
-    uint32_t local = 0;
-    for (int j = j0; j < j1; ++j) local += nz[j] ? (uint32_t)jobs[j].size * jobs[j].size : 0u;
-    // exclusive scan of the per-thread sums: warp scan, then scan of the 32 warp totals
+    __shared__ uint32_t s_base;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t incl = local;
+    if (threadIdx.x == 0) s_base = 0;
+    for (int t0 = 0; t0 < n_jobs; t0 += PK_TILE) {
+        const int nt = min(PK_TILE, n_jobs - t0);
+        __syncthreads();
+        const uint32_t base = s_base;          // stable here: its last update is followed by a barrier
+        for (int i = threadIdx.x; i < nt; i += PK_SCAN_NT) s_code[i] = nz[t0 + i] ? (uint8_t)(31 - __clz((int)jobs[t0 + i].size)) : (uint8_t)0;
+        __syncthreads();
+        const int per = (nt + PK_SCAN_NT - 1) / PK_SCAN_NT, j0 = min(nt, (int)threadIdx.x * per), j1 = min(nt, j0 + per);
+        uint32_t local = 0;
+        for (int j = j0; j < j1; ++j) { const uint32_t c = s_code[j]; local += c ? 1u << (2 * c) : 0u; }
+        // exclusive scan of the per-thread sums: warp scan, then scan of the 32 warp totals
+        uint32_t incl = local;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    if (lane == 31) s_part[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-        uint32_t v = s_part[lane], w = v;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) s_part[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t v = s_part[lane], w = v;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
-        s_part[lane] = w - v;      // exclusive
-        if (lane == 31) offsets[n_jobs] = w;
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+            s_part[lane] = w - v;      // exclusive
+            if (lane == 31) s_base = base + w;
+        }
+        __syncthreads();
+        uint32_t run = base + s_part[wid] + incl - local;
+        for (int j = j0; j < j1; ++j) { offsets[t0 + j] = run; const uint32_t c = s_code[j]; run += c ? 1u << (2 * c) : 0u; }
     }
     __syncthreads();
-    uint32_t run = s_part[wid] + incl - local;
-    for (int j = j0; j < j1; ++j) { offsets[j] = run; run += nz[j] ? (uint32_t)jobs[j].size * jobs[j].size : 0u; }
+    if (threadIdx.x == 0) offsets[n_jobs] = s_base;
 }
 
 __global__ void __launch_bounds__(128) tq_pack_copy_kernel(const __grid_constant__ TqArgs A, const uint32_t *offsets, int16_t *stream, uint32_t capacity)

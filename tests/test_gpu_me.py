@@ -123,6 +123,24 @@ def test_device_picture_build_matches_host_pad_and_decimation(wh):
     dev.destroy()
 
 
+@pytest.mark.parametrize("wh,pad", [((448, 256), 80), ((328, 200), 16), ((72, 40), 0), ((3840, 2160), 80)])
+def test_device_picture_build_from_device_luma(wh, pad):
+    """svtb200_pa_picture_build_dev: all three planes straight from a (padded) luma plane already on the device"""
+    import torch
+    w, h = wh
+    luma = common.SynthVideo(w, h, seed=5).luma(1)
+    host = S.HostPaPicture(luma)
+    t = torch.zeros((h + 2 * pad, w + 2 * pad + (-(w + 2 * pad)) % 4), dtype=torch.uint8, device="cuda")
+    t[pad:pad + h, pad:pad + w] = torch.from_numpy(luma).cuda()
+    dev = S.DevPaPicture(w, h)
+    dev.build_from_device(t[pad:, pad:].data_ptr(), t.shape[1], torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = dev.download()
+    for (a, _, _, _), (b, _, _, _) in zip(host.planes, got.planes):
+        assert np.array_equal(a, b[:, :a.shape[1]])
+    dev.destroy()
+
+
 def test_me_picture_dev_resident_matches_host_api():
     import torch
     w, h = 448, 256

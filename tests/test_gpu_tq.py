@@ -164,3 +164,42 @@ def test_pack_coeffs_stream_matches_planes():
     S.tq_pack_coeffs_dev(coeff, d_jobs.data_ptr(), d_nz.data_ptr(), len(jobs), d_small.data_ptr(), 1000, d_off.data_ptr(), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert int(d_off.cpu().numpy().view(np.uint32)[-1]) == int(sizes.sum())
+
+
+@pytest.mark.gpu
+def test_tq_pack_coeffs_many_jobs():
+    """more jobs than one pass of the scan kernel holds (PK_TILE = 32768), several jobs per scan thread, mixed sizes"""
+    import torch
+    w, h = 2560, 1536
+    rng = np.random.default_rng(11)
+    tiles = []
+    for ty in range(0, h, 32):
+        for tx in range(0, w, 32):
+            n = int(rng.choice([8, 8, 8, 8, 16, 32]))
+            tiles += [(tx + x, ty + y, n) for y in range(0, 32, n) for x in range(0, 32, n)]
+    jobs = np.zeros(len(tiles), dtype=S.TQ_JOB_DTYPE)
+    arr = np.array(tiles)
+    jobs["x"], jobs["y"], jobs["size"], jobs["plane"] = arr[:, 0], arr[:, 1], arr[:, 2], 0
+    assert len(jobs) > 32768
+    plane = rng.integers(-300, 300, (h, w)).astype(np.int16)
+    nz = (rng.random(len(jobs)) < 0.4).astype(np.uint32)
+    dev = torch.device("cuda", 0)
+    d_plane = torch.from_numpy(plane).to(dev)
+    coeff = S.CoeffPicture()
+    for k in range(3):
+        coeff.buf[k] = d_plane.data_ptr(); coeff.stride[k] = w
+    d_jobs = torch.from_numpy(jobs.view(np.uint8)).to(dev)
+    d_nz = torch.from_numpy(nz.view(np.int32)).to(dev)
+    sizes = np.where(nz != 0, jobs["size"].astype(np.uint32) ** 2, 0).astype(np.uint32)
+    cap = int(sizes.sum()) + 64
+    d_stream = torch.full((cap,), -1, dtype=torch.int16, device=dev)
+    d_off = torch.zeros(len(jobs) + 1, dtype=torch.int32, device=dev)
+    S.tq_pack_coeffs_dev(coeff, d_jobs.data_ptr(), d_nz.data_ptr(), len(jobs), d_stream.data_ptr(), cap, d_off.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    off = d_off.cpu().numpy().view(np.uint32)
+    stream = d_stream.cpu().numpy()
+    assert np.array_equal(off, np.concatenate([[0], np.cumsum(sizes, dtype=np.uint64)]).astype(np.uint32))
+    for j in rng.choice(np.nonzero(nz)[0], 400, replace=False):
+        N, x, y = int(jobs["size"][j]), int(jobs["x"][j]), int(jobs["y"][j])
+        assert np.array_equal(stream[off[j]:off[j] + N * N].reshape(N, N), plane[y:y + N, x:x + N]), j
+    assert np.all(stream[off[-1]:] == -1)
