@@ -240,7 +240,10 @@ __global__ void __launch_bounds__(IN_NT) intra_batch_kernel(const __grid_constan
 }
 
 // ---- open-loop intra search -------------------------------------------------------------------------------------------------
-constexpr int OIS_NT = 256, OIS_NW = OIS_NT / 32;
+#ifndef OIS_NT_V
+#define OIS_NT_V 256
+#endif
+constexpr int OIS_NT = OIS_NT_V, OIS_NW = OIS_NT / 32;
 constexpr int SRC_P = 128, SRC_R = 97;      // staged source: rows / cols -1 .. 95 relative to the LCU origin; pitch = win_pitch(97)
 constexpr int SAD_SLOTS = 36;
 

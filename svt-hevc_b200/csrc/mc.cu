@@ -7,7 +7,7 @@
 //   EncodeUniPredInterpolation / EncodeBiPredInterpolation (Codec/EbMcp.c:175,562), EncodePassInterPrediction
 //   position clamp (Codec/EbInterPrediction.c:794-808)
 //
-// Design: one CTA (128 threads) per PU, walked in <= 32x32 luma tiles (+ the two 16x16 chroma tiles).  Per tile ALL reference windows
+// Design: one CTA (64 threads; most PUs of M10 are integer-vector copies, where the per-PU address derivation every warp repeats dominates) per PU, walked in <= 32x32 luma tiles (+ the two 16x16 chroma tiles).  Per tile ALL reference windows
 // (luma / Cb / Cr x list 0 / list 1, (tile + taps - 1)^2 each) are staged in shared memory back to back with coalesced 128-bit loads, then
 //   H pass : every window, flattened over the CTA; 4 outputs per thread from funnel-shifted words with DP4A (u8 x s8), s16 rows in smem,
 //   V pass : a 2x2 output quad per thread with DP2A on PRMT-built vertical s16 pairs, both lists in registers, final rounding /
@@ -21,7 +21,10 @@
 
 namespace svtb200 {
 
-constexpr int MC_NT = 128;
+#ifndef MC_NT_V
+#define MC_NT_V 64
+#endif
+constexpr int MC_NT = MC_NT_V;
 constexpr int TILE = 32;
 
 struct YuvD {
@@ -344,7 +347,7 @@ template <bool HBD> struct McSmem {
 };
 
 template <bool HBD>
-__global__ void __launch_bounds__(MC_NT, 8) mc_batch_kernel(const __grid_constant__ McArgs A)
+__global__ void __launch_bounds__(MC_NT, 1024 / MC_NT) mc_batch_kernel(const __grid_constant__ McArgs A)
 {
     constexpr int BPS = HBD ? 2 : 1;
     using G = McSmem<HBD>;

@@ -41,7 +41,10 @@ __device__ __forceinline__ int dp4a_ss(uint32_t a_s8x4, uint32_t b_s8x4, int c)
     return d;
 }
 
-constexpr int ST_NT = 128;
+#ifndef ST_NT_V
+#define ST_NT_V 128
+#endif
+constexpr int ST_NT = ST_NT_V;
 constexpr int ST_ROWS = 20 + 32;      // histogram rows: EO type * 5 + edge index (0..4), then the 32 bands
 __global__ void __launch_bounds__(ST_NT) sao_stats_kernel(const __grid_constant__ StatsArgs A)
 {

@@ -43,11 +43,23 @@ def main():
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", f"regex:{kernel}"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    hi = [i for i, r in enumerate(rows) if "Instructions Executed" in r][0]
-    hdr = rows[hi]
-    ie, st = hdr.index("Instructions Executed"), hdr.index("# Samples")
-    data = [(int(r[ie] or 0), int(r[st] or 0)) for r in rows[hi + 1:] if len(r) > ie and r[0].startswith("0x")]
+    # one section per captured launch (and per view): "Kernel Name" row, header row, SASS rows
+    secs, cur = [], None
+    for r in rows:
+        if r and r[0] == "Kernel Name":
+            cur = {"name": r[1], "rows": []}
+            secs.append(cur)
+        elif cur is not None:
+            cur["rows"].append(r)
     lines = sass_lines(mangled, cu)
+    def parse(sec):
+        hdr = sec["rows"][0]
+        ie, st = hdr.index("Instructions Executed"), hdr.index("# Samples")
+        return [(int(r[ie] or 0), int(r[st] or 0)) for r in sec["rows"][1:] if len(r) > ie and r[0].startswith("0x")]
+    parsed = [(sec["name"], parse(sec)) for sec in secs if sec["rows"] and "Instructions Executed" in sec["rows"][0]]
+    # the launch whose SASS length matches the cubin's function (template instantiations share the base name)
+    name, data = next(((n, d) for n, d in parsed if len(d) == len(lines)), parsed[0])
+    print(f"# launch: {name}")
     if len(lines) != len(data):
         print(f"# warning: {len(data)} SASS rows in the report vs {len(lines)} in the cubin (binary changed since the capture?)")
     n = min(len(lines), len(data))
