@@ -30,6 +30,7 @@ struct PlaneD {
 struct MeArgs {
     svtb200_me_config cfg;
     int sp_fp, sp_sp, sp_f_bytes, sp_p_bytes;   // sub-pel planes: pitches and bytes of the F plane / of each of B, H, J
+    int sp_alias;         // the second list's planes overlay the search scratch (8x8 SADs, sums, window)
     PlaneD src[3];        // full, quarter, sixteenth
     PlaneD ref[2][3];
     svtb200_me_pu_result *results;
@@ -123,7 +124,9 @@ static int launch_me(const svtb200_me_config *cfg, const PlaneD src[3], const Pl
         A.sp_sp = (saw + 68 + 4 + 3) & ~3;
         A.sp_f_bytes = (A.sp_fp * (sah + 68) + 15) & ~15;
         A.sp_p_bytes = (A.sp_sp * (sah + 68) + 15) & ~15;
-        smem += 84 * 8 * 4 + 2 * ((size_t)A.sp_f_bytes + 3 * (size_t)A.sp_p_bytes);
+        const size_t per_list = (size_t)A.sp_f_bytes + 3 * (size_t)A.sp_p_bytes;
+        A.sp_alias = cfg->num_lists == 2 && per_list <= (size_t)CHUNK * 64 * 2 + (size_t)CHUNK * 21 * 4 + (size_t)A.win_bytes;
+        smem += 84 * 8 * 4 + (A.sp_alias || cfg->num_lists < 2 ? 1 : 2) * per_list;
     }
     if (smem > 227 * 1024) { set_error("me: this search configuration needs %zu B of shared memory (> 227 KB)", smem); return SVTB200_ERR_UNSUPPORTED; }
     static thread_local size_t smem_set[2] = {0, 0};
