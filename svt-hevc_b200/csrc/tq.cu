@@ -468,7 +468,14 @@ __global__ void __launch_bounds__(PK_SCAN_NT) tq_pack_scan_kernel(const svtb200_
         const int nt = min(PK_TILE, n_jobs - t0);
         __syncthreads();
         const uint32_t base = s_base;          // stable here: its last update is followed by a barrier
-        for (int i = threadIdx.x; i < nt; i += PK_SCAN_NT) s_code[i] = nz[t0 + i] ? (uint8_t)(31 - __clz((int)jobs[t0 + i].size)) : (uint8_t)0;
+        // both loads unconditional and unrolled: the batch of independent requests is in flight together (a conditional second load serialised
+        // ~50 dependent DRAM round trips)
+#pragma unroll 8
+        for (int i = threadIdx.x; i < nt; i += PK_SCAN_NT) {
+            const uint32_t z = __ldg(nz + t0 + i);
+            const int sz = __ldg(&jobs[t0 + i].size);
+            s_code[i] = z ? (uint8_t)(31 - __clz(sz)) : (uint8_t)0;
+        }
         __syncthreads();
         const int per = (nt + PK_SCAN_NT - 1) / PK_SCAN_NT, j0 = min(nt, (int)threadIdx.x * per), j1 = min(nt, j0 + per);
         uint32_t local = 0;
