@@ -47,10 +47,10 @@ STAGES = ["me_picture (+ sub-pel on layer 0)", "ois_picture", "mc_batch", "tq_ba
 ALG = {"me": 9384 * 2, "ois": 4096 + 21 * 5, "mc_uni": 12288, "mc_bi": 18432, "tq": 30720, "dlf": 12864, "sao_stats": 12288 + 3 * 312, "sao_apply": 12288}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this command (profiles/r01_s3_summary.txt;
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this command (profiles/r01_s4_summary.txt;
 # ME = 7/8 integer-pel launches + 1/8 sub-pel launches of the mini-GOP).  Writes mostly stay in the 126 MB L2 during a capture, so the figure is read-dominated.
-NCU_TRAFFIC = {"me": (7 * (27.690752 + 3.109120) + (18.473472 + 0.128512)) / 8 * 1e6, "ois": 8.635648e6, "mc": 13.198592e6, "tq": 27.984128e6, "sao_stats": 25.262080e6}
-NCU_TRAFFIC_SOURCE = "profiles/r01_s3_summary.txt"
+NCU_TRAFFIC = {"me": (7 * (27.699200 + 4.423424) + (18.488576 + 1.536256)) / 8 * 1e6, "ois": 8.636416e6, "mc": 13.201408e6, "tq": 27.947776e6, "sao_stats": 25.263616e6}
+NCU_TRAFFIC_SOURCE = "profiles/r01_s4_summary.txt"
 
 
 def peaks():
