@@ -1,0 +1,169 @@
+"""Golden fixtures of the hot path (the reference stores no vectors for this path, so they are generated HERE from the compiled,
+unmodified reference -- oracle/_ref -- by tests/golden/make_golden.py and committed as SHA-256 digests of canonical output bytes).
+
+One case = (stage, name, build() -> inputs, digest(outputs)).  `run_case(case, backend)` produces the digest with
+  backend "reference": the reference's own functions (oracle/_ref harness entry points, C rows),
+  backend "port"     : oracle/port (the plain-C restatement),
+  backend "cuda"     : libsvthevc_b200.so through its C ABI.
+All three must hash to the committed value; the inputs are seeded and built by the same helpers the parity tests use."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+
+import common
+import svtb200 as S
+
+
+def _h(*arrays):
+    m = hashlib.sha256()
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        m.update(str(a.dtype).encode()); m.update(str(a.shape).encode()); m.update(a.tobytes())
+    return m.hexdigest()
+
+
+def _planes(pic):
+    return [np.ascontiguousarray(p) for p in pic.interior()]
+
+
+# ---- motion estimation ------------------------------------------------------------------------------------------------------
+def _me_digest(out, nl):
+    res, bs, bm, rc = out
+    fields = [res[f] for f in res.dtype.names if not (nl == 1 and f in ("x_mv_l1", "y_mv_l1"))]
+    return _h(*fields, bs[:, :nl], bm[:, :nl], rc)
+
+
+def _me(case, backend):
+    from test_oracle_me import build_me_case
+    name, w, h, kw, content = case
+    cfg, (src, r0, r1) = build_me_case(w, h, kw, content)
+    r1 = r1 if cfg.num_lists == 2 else None
+    if backend == "reference":
+        out = common.oracle_me_picture(common.load_ref(), "svtref_me_picture", cfg, src, r0, r1, asm_mode=0)
+    elif backend == "port":
+        out = common.oracle_me_picture(common.load_port(), "port_me_picture", cfg, src, r0, r1)
+    else:
+        out = S.me_picture(cfg, src, r0, r1, want_raw=True, want_rc=True)
+    return _me_digest(out, cfg.num_lists)
+
+
+# ---- motion compensation ------------------------------------------------------------------------------------------------------
+def _mc(case, backend):
+    from test_oracle_mc import make_jobs, make_pictures, run_oracle
+    name, w, h, kind, all_fracs, big = case
+    refs = make_pictures(w, h, seed=11, kind=kind)
+    jobs = make_jobs(w, h, len(refs), seed=5, all_fracs=all_fracs, big_mv=big)
+    if backend == "reference":
+        out = run_oracle(common.load_ref(), "svtref_mc_batch", refs, jobs, w, h, asm_mode=0)
+    elif backend == "port":
+        out = run_oracle(common.load_port(), "port_mc_batch", refs, jobs, w, h)
+    else:
+        out = S.HostYuvPicture(np.zeros((h, w), np.uint8), np.zeros((h // 2, w // 2), np.uint8), np.zeros((h // 2, w // 2), np.uint8))
+        S.mc_batch(refs, jobs, out)
+    return _h(*_planes(out))
+
+
+# ---- transform / quantisation chain ---------------------------------------------------------------------------------------------
+def _tq(case, backend):
+    from test_oracle_tq import make_src_pred, make_tq_jobs, run_tq_oracle
+    name, w, h, kind, shapes, flags = case
+    src, pred = make_src_pred(w, h, 31, kind)
+    jobs = make_tq_jobs(w, h, seed=8, shapes=shapes, flags=flags)
+    if backend == "reference":
+        recon, coeff, nz = run_tq_oracle(common.load_ref(), "svtref_tq_batch", src, pred, jobs, w, h, asm_mode=0)
+    elif backend == "port":
+        recon, coeff, nz = run_tq_oracle(common.load_port(), "port_tq_batch", src, pred, jobs, w, h)
+    else:
+        y, cb, cr = (a.copy() for a in pred.interior())
+        recon = S.HostYuvPicture(y, cb, cr)
+        coeff = S.HostCoeffPicture(w, h)
+        nz = S.tq_batch(src, pred, recon, coeff, jobs)
+    return _h(*_planes(recon), *[np.ascontiguousarray(p) for p in coeff.planes], np.asarray(nz, np.uint32))
+
+
+# ---- deblocking ---------------------------------------------------------------------------------------------------------------
+def _dlf(case, backend):
+    from test_oracle_dlf import make_dlf_inputs, run_dlf
+    name, w, h, kind, density = case
+    pic, vbs, hbs, qp, prm = make_dlf_inputs(w, h, seed=w + h, density=density, kind=kind)
+    if backend == "reference":
+        out = run_dlf(common.load_ref(), "svtref_dlf_picture", pic, vbs, hbs, qp, prm, asm_mode=0)
+    elif backend == "port":
+        out = run_dlf(common.load_port(), "port_dlf_picture", pic, vbs, hbs, qp, prm)
+    else:
+        out = S.HostYuvPicture(*(a.copy() for a in pic.interior()))
+        S.dlf_picture(out, vbs, hbs, qp, prm)
+    return _h(*_planes(out))
+
+
+# ---- SAO ------------------------------------------------------------------------------------------------------------------------
+def _sao_stats(case, backend):
+    from test_oracle_sao import load_ref_sao, make_sao_inputs, run_stats
+    name, w, h, kind = case
+    src, rec, _ = make_sao_inputs(w, h, seed=w * 3 + h, kind=kind)
+    if backend == "reference":
+        st = run_stats(load_ref_sao(), "svtref_sao_stats_picture", src, rec, asm_mode=0)
+    elif backend == "port":
+        st = run_stats(common.load_port(), "port_sao_stats_picture", src, rec)
+    else:
+        st = S.sao_stats_picture(src, rec)
+    # slot [4] of the EO arrays is scratch in the reference (tests/test_oracle_sao.py)
+    return _h(st["bo_diff"], st["bo_count"], st["eo_diff"][..., :4], st["eo_count"][..., :4])
+
+
+def _sao_apply(case, backend):
+    from test_oracle_sao import make_sao_inputs, run_apply_port, run_apply_ref
+    name, w, h, kind = case
+    _, rec, prm = make_sao_inputs(w, h, seed=w * 3 + h, kind=kind)
+    if backend == "reference":
+        out = run_apply_ref(rec, prm, (1, 1), asm_mode=0)
+    elif backend == "port":
+        out = run_apply_port(rec, prm, (1, 1))
+    else:
+        out = S.HostYuvPicture(*(np.zeros_like(a) for a in rec.interior()))
+        S.sao_apply_picture(rec, out, prm, (1, 1))
+    return _h(*_planes(out))
+
+
+# ---- open-loop intra search -----------------------------------------------------------------------------------------------------
+def _ois(case, backend):
+    from test_oracle_intra import fake_me, luma_plane, ois_cfg, run_ois
+    name, w, h, kw, cap = case
+    cfg = ois_cfg(w, h, **kw)
+    pl, _keep = luma_plane(w, h, seed=w + h, kind="synth")
+    n_lcu = ((w + 63) // 64) * ((h + 63) // 64)
+    me = fake_me(n_lcu, seed=5, scale=3)
+    if backend == "reference":
+        t, c = run_ois(common.load_ref(), "svtref_ois_picture", cfg, pl, me, cap, C.c_int(0))
+    elif backend == "port":
+        t, c = run_ois(common.load_port(), "port_ois_picture", cfg, pl, me, cap)
+    else:
+        t, c = S.ois_picture(cfg, pl, me, cap)
+    return _h(t, c)
+
+
+def cases():
+    """[(key, runner, case)] -- small, seeded, a few seconds for all of them on any backend"""
+    from test_oracle_dlf import DLF_CASES
+    from test_oracle_mc import MC_CASES
+    from test_oracle_me import _me_cases
+    from test_oracle_sao import SAO_APPLY_CASES, SAO_CASES
+    from test_oracle_tq import TQ_CASES
+    out = []
+    me = _me_cases()
+    for c in me[:: max(1, len(me) // 6)][:6]:
+        out.append((f"me/{c[0]}", _me, c))
+    for c in MC_CASES:
+        out.append((f"mc/{c[0]}", _mc, c))
+    for c in TQ_CASES:
+        out.append((f"tq/{c[0]}", _tq, c))
+    for c in DLF_CASES[:4]:
+        out.append((f"dlf/{c[0]}", _dlf, c))
+    for c in SAO_CASES[:3]:
+        out.append((f"sao_stats/{c[0]}", _sao_stats, c))
+    for c in SAO_APPLY_CASES[:2]:
+        out.append((f"sao_apply/{c[0]}", _sao_apply, c))
+    out.append(("ois/islice_256x192", _ois, ("islice", 256, 192, dict(slice_type=2), 9)))
+    out.append(("ois/dc_only_448x256", _ois, ("dc_only", 448, 256, dict(slice_type=0, limit_ois_to_dc_mode=1, skip_ois_8x8=1), 1)))
+    return out
