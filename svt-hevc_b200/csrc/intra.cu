@@ -274,20 +274,21 @@ __device__ __forceinline__ uint32_t ois_pack(uint32_t dist, bool valid, uint32_t
 
 __device__ __forceinline__ void cu_geometry(int cu, int &N, int &cx, int &cy)
 {
-    int k, per;
-    if (cu < 5) { N = 32; k = cu - 1; per = 2; } else if (cu < 21) { N = 16; k = cu - 5; per = 4; } else { N = 8; k = cu - 21; per = 8; }
-    cx = (k % per) * N; cy = (k / per) * N;
+    int k, lp;      // lp = log2(CUs per LCU row)
+    if (cu < 5) { N = 32; k = cu - 1; lp = 1; } else if (cu < 21) { N = 16; k = cu - 5; lp = 2; } else { N = 8; k = cu - 21; lp = 3; }
+    cx = (k & ((1 << lp) - 1)) * N; cy = (k >> lp) * N;
 }
 
 // SAD of one predicted mode against the staged source, one warp; lanes take 4 horizontally adjacent samples each
 __device__ __forceinline__ uint32_t warp_mode_sad(const uint8_t *line, const ModeSetup &m, const uint8_t *s_src, int cx, int cy)   // s_src: sample (-1, -1) of the LCU
 {
-    const int N = m.N, q = N >> 2, lane = threadIdx.x & 31;
+    const int N = m.N, q = N >> 2, lq = 31 - __clz(q), lane = threadIdx.x & 31;      // N is 8, 16 or 32
     uint32_t acc = 0;
     for (int i = lane; i < N * q; i += 32) {
-        const int r = i / q, c = (i - r * q) * 4;
-        const uint8_t *sp = s_src + (cy + r + 1) * SRC_P + cx + c + 1;      // not 4-byte aligned (the apron column): assemble from bytes
-        const uint32_t sw = (uint32_t)sp[0] | ((uint32_t)sp[1] << 8) | ((uint32_t)sp[2] << 16) | ((uint32_t)sp[3] << 24);
+        const int r = i >> lq, c = (i & (q - 1)) * 4;
+        const uintptr_t sp = (uintptr_t)(s_src + (cy + r + 1) * SRC_P + cx + c + 1);   // not 4-byte aligned (the apron column): two words + funnel shift
+        const uint32_t *sw2 = (const uint32_t *)(sp & ~(uintptr_t)3);
+        const uint32_t sw = __funnelshift_r(sw2[0], sw2[1], (uint32_t)(sp & 3) * 8);
         acc = __vsadu4(intra_pel4(line, m, c, r), sw) + acc;
     }
     return warp_sum(acc);
