@@ -500,6 +500,10 @@ def run_b200(args):
 # reference arm / cpu baseline: the reference's own functions (oracle/_ref), one frame per host thread
 # ------------------------------------------------------------------------------------------------
 def cpu_reference(frames):
+    """The reference's own functions on every host thread.  Like the B200 arm, the timed region holds nothing but the stage calls: the
+    mode-decision stand-in (MC job lists from one ME pass per ring frame) is computed beforehand, every worker thread owns its output buffers for
+    the whole run (no per-frame allocation), and the workers start together behind a barrier.  ctypes releases the GIL inside the calls."""
+    import threading
     import common
     import svtb200 as S
     from concurrent.futures import ThreadPoolExecutor
@@ -509,7 +513,9 @@ def cpu_reference(frames):
         raise RuntimeError("oracle/_ref missing: build it with oracle/build_ref.sh where /root/reference exists")
     refsao = C.CDLL(os.path.join(ROOT, "oracle", "_ref", f"libsvtref_sao_{variant}.so"))
     nthreads = os.cpu_count() or 1
-    frames = frames or max(8, min(nthreads, 128) // 8 * 8)
+    per_thread = 4
+    frames = frames or nthreads * per_thread
+    nworkers = min(nthreads, frames)
     wl = Workload(RING, seed=0x5F7C0001)
     pa = [S.HostPaPicture(l) for l in wl.luma]
     yuv = [S.HostYuvPicture(wl.luma[i], wl.chroma[i][0], wl.chroma[i][1]) for i in range(RING)]
@@ -519,41 +525,121 @@ def cpu_reference(frames):
               refsao.svtref_sao_apply_picture):
         f.restype = C.c_int
     flags = (C.c_uint8 * 2)(1, 1)
+    me_cfgs = {tl: S.me_config(W, H, enc_mode=10, temporal_layer=tl, num_lists=2, ref_poc=(0, 16)) for tl in set(TL_PATTERN)}
+    ref_pairs = {}
+    for i in range(RING):
+        ref_pairs[wl.refs(i)] = S.yuv_array([yuv[wl.refs(i)[0]], yuv[wl.refs(i)[1]]])
+    n_tq = len(wl.tq_jobs)
 
-    def frame(i):
+    def me(i, res):
         k = i % RING
         r0, r1 = wl.refs(i)
-        cfg = wl.me_cfg(i)
-        res = np.zeros((N_LCU, 85), dtype=S.ME_PU_RESULT_DTYPE)
-        assert ref.svtref_me_picture_rows(C.byref(cfg), C.byref(pa[k].struct), C.byref(pa[r0].struct), C.byref(pa[r1].struct), vp(res), None, None, None,
+        assert ref.svtref_me_picture_rows(C.byref(me_cfgs[wl.tl(i)]), C.byref(pa[k].struct), C.byref(pa[r0].struct), C.byref(pa[r1].struct), vp(res), None, None, None,
                                           C.c_int(1), C.c_int(0), C.c_int(ROWS)) == 0
-        ois_total, ois_cand = np.zeros((N_LCU, 85), np.uint8), np.zeros((N_LCU, 85, 1), np.uint32)
-        assert ref.svtref_ois_picture(C.byref(ois_cfg), C.byref(pa[k].struct.full), vp(res), vp(ois_total), vp(ois_cand), C.c_uint32(1), C.c_int(1)) == 0
-        jobs = wl.mc_jobs(res)
-        pred = S.HostYuvPicture(np.zeros((H, W), np.uint8), np.zeros((H // 2, W // 2), np.uint8), np.zeros((H // 2, W // 2), np.uint8), replicate=False)
-        assert ref.svtref_mc_batch(S.yuv_array([yuv[r0], yuv[r1]]), C.c_int(2), vp(jobs), C.c_int(len(jobs)), C.byref(pred.struct), C.c_int(1)) == 0
-        coeff = S.HostCoeffPicture(W, H)
-        nz = np.zeros(len(wl.tq_jobs), np.uint32)
-        assert ref.svtref_tq_batch(C.byref(yuv[k].struct), C.byref(pred.struct), C.byref(pred.struct), C.byref(coeff.struct), vp(wl.tq_jobs),
-                                   C.c_int(len(wl.tq_jobs)), vp(nz), C.c_int(1), C.c_int(0), C.c_int(len(wl.tq_jobs))) == 0
-        if wl.tl(i) == 0:
-            assert ref.svtref_dlf_picture(C.byref(pred.struct), vp(wl.vbs), vp(wl.hbs), vp(wl.qp_array), C.byref(wl.dlf_prm), C.c_int(1)) == 0
-        stats = np.zeros((N_LCU, 3), dtype=S.SAO_STATS_DTYPE)
-        assert refsao.svtref_sao_stats_picture(C.byref(yuv[k].struct), C.byref(pred.struct), vp(stats), C.c_int(1)) == 0
-        if wl.tl(i) == 0:
-            assert refsao.svtref_sao_apply_picture(C.byref(pred.struct), vp(wl.sao_prm), flags, C.c_int(1)) == 0
-        return int(nz.sum())
 
-    with ThreadPoolExecutor(nthreads) as ex:
-        list(ex.map(frame, range(min(nthreads, 8))))                      # warm-up (page in libraries, touch buffers)
-        t0 = time.perf_counter()
-        list(ex.map(frame, range(frames)))
-        dt = time.perf_counter() - t0
+    # mode-decision stand-in, outside the timed region (the B200 arm does the same with its own ME): the job list of ring frame k
+    def jobs_of(k):
+        res = np.zeros((N_LCU, 85), dtype=S.ME_PU_RESULT_DTYPE)
+        me(k, res)
+        return wl.mc_jobs(res)
+    with ThreadPoolExecutor(min(nthreads, RING)) as ex:
+        mc_jobs = list(ex.map(jobs_of, range(RING)))
+
+    class Worker:
+        def __init__(self):
+            self.res = np.zeros((N_LCU, 85), dtype=S.ME_PU_RESULT_DTYPE)
+            self.ois_total, self.ois_cand = np.zeros((N_LCU, 85), np.uint8), np.zeros((N_LCU, 85, 1), np.uint32)
+            self.pred = S.HostYuvPicture(np.zeros((H, W), np.uint8), np.zeros((H // 2, W // 2), np.uint8), np.zeros((H // 2, W // 2), np.uint8), replicate=False)
+            self.coeff = S.HostCoeffPicture(W, H)
+            self.nz = np.zeros(n_tq, np.uint32)
+            self.stats = np.zeros((N_LCU, 3), dtype=S.SAO_STATS_DTYPE)
+
+        def frame(self, i):
+            k = i % RING
+            me(i, self.res)
+            assert ref.svtref_ois_picture(C.byref(ois_cfg), C.byref(pa[k].struct.full), vp(self.res), vp(self.ois_total), vp(self.ois_cand), C.c_uint32(1), C.c_int(1)) == 0
+            jobs = mc_jobs[k]
+            assert ref.svtref_mc_batch(ref_pairs[wl.refs(i)], C.c_int(2), vp(jobs), C.c_int(len(jobs)), C.byref(self.pred.struct), C.c_int(1)) == 0
+            assert ref.svtref_tq_batch(C.byref(yuv[k].struct), C.byref(self.pred.struct), C.byref(self.pred.struct), C.byref(self.coeff.struct), vp(wl.tq_jobs),
+                                       C.c_int(n_tq), vp(self.nz), C.c_int(1), C.c_int(0), C.c_int(n_tq)) == 0
+            if wl.tl(i) == 0:
+                assert ref.svtref_dlf_picture(C.byref(self.pred.struct), vp(wl.vbs), vp(wl.hbs), vp(wl.qp_array), C.byref(wl.dlf_prm), C.c_int(1)) == 0
+            assert refsao.svtref_sao_stats_picture(C.byref(yuv[k].struct), C.byref(self.pred.struct), vp(self.stats), C.c_int(1)) == 0
+            if wl.tl(i) == 0:
+                assert refsao.svtref_sao_apply_picture(C.byref(self.pred.struct), vp(wl.sao_prm), flags, C.c_int(1)) == 0
+
+    gate = threading.Barrier(nworkers + 1)
+    errors = []
+
+    def run(t):
+        try:
+            w = Worker()
+            w.frame(t)                                  # warm-up: page in the libraries, touch this worker's buffers
+            gate.wait()                                 # everybody is ready
+            gate.wait()                                 # timed region starts
+            for i in range(t, frames, nworkers):
+                w.frame(i)
+        except Exception as e:      # noqa: BLE001
+            errors.append(e)
+            gate.abort()
+        finally:
+            try:
+                gate.wait()                             # timed region ends when the last worker is through
+            except threading.BrokenBarrierError:
+                pass
+
+    threads = [threading.Thread(target=run, args=(t,)) for t in range(nworkers)]
+    for th in threads:
+        th.start()
+    gate.wait()
+    t0 = time.perf_counter()
+    gate.wait()
+    gate.wait()
+    dt = time.perf_counter() - t0
+    for th in threads:
+        th.join()
+    if errors:
+        raise errors[0]
     v = N_LCU * frames / dt
-    return {"value": v, "unit": "CTU/s", "fps": v / N_LCU, "cores": min(nthreads, frames), "kind": "reference",
+    return {"value": v, "unit": "CTU/s", "fps": v / N_LCU, "cores": nworkers, "kind": "reference",
             "sample": f"{frames} full 4K frames of the same stages and jobs through the reference's own functions (MotionEstimateLcu, OpenLoopIntraSearchLcu, "
                       f"EncodePassInterPrediction, EstimateTransform/UnifiedQuantizeInvQuantize/EncodeInvTransform, LCU DLF drivers, SAO gather/apply; "
-                      f"{variant} rows), one frame per host thread, {nthreads} threads"}
+                      f"{variant} rows), {nworkers} worker threads with their own buffers, {frames // nworkers} frame(s) each behind a barrier; job lists "
+                      f"prepared beforehand as on the B200 arm"}
+
+
+def reference_encoder_app(n_frames=32, timeout_s=180):
+    """The reference's WHOLE encoder (its own CLI, AVX-512 build from oracle/build_ref.sh) on the same synthetic 4K video at preset M10, CQP:
+    ME + mode decision + EncDec + entropy coding on all host threads.  Informational: the stages this repo replaces are timed by cpu_reference();
+    this is what the unmodified encoder delivers end to end on the box.  Never raises (the line it decorates must not fail because of it)."""
+    import re
+    import subprocess
+    import tempfile
+    app = os.path.join(ROOT, "oracle", "_ref", "SvtHevcEncApp_avx512")
+    try:
+        import common
+        if not os.path.exists(app) or not common.cpu_has("avx512bw"):
+            return {"unavailable": "oracle/_ref/SvtHevcEncApp_avx512 missing or no AVX-512 on this host"}
+        wl = Workload(RING, seed=0x5F7C0001)
+        with tempfile.TemporaryDirectory() as d:      # -nb preloads the frames into RAM, so the file system does not matter
+            yuv = os.path.join(d, "in.yuv")
+            with open(yuv, "wb") as f:
+                for i in range(n_frames):
+                    k = i % RING
+                    f.write(wl.luma[k].tobytes()); f.write(wl.chroma[k][0].tobytes()); f.write(wl.chroma[k][1].tobytes())
+            cmd = [app, "-i", yuv, "-w", str(W), "-h", str(H), "-n", str(n_frames), "-nb", str(n_frames), "-encMode", "10", "-q", "32", "-fps", "60",
+                   "-intra-period", "55", "-irefresh-type", "1", "-b", os.path.join(d, "out.265")]
+            t0 = time.perf_counter()
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s).stdout
+            wall = time.perf_counter() - t0
+        m = re.search(r"Average Speed:\s*([0-9.]+)\s*fps", out)
+        if not m:
+            return {"unavailable": "no 'Average Speed' line in the encoder's output", "tail": out[-300:]}
+        fps = float(m.group(1))
+        return {"fps": fps, "ctu_per_s": fps * N_LCU, "frames": n_frames, "threads": os.cpu_count(), "wall_s": wall,
+                "what": "SvtHevcEncApp (reference, AVX-512 build) 3840x2160 8-bit, -encMode 10 -q 32 -intra-period 55, frames preloaded (-nb): whole encoder"}
+    except Exception as e:      # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"}
 
 
 def run_reference(args):
@@ -567,6 +653,8 @@ def run_reference(args):
            "dtype": "u8", "data": "synthetic", "config": {"workload": WORKLOAD, "stages": STAGES},
            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "CTU/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "wall_s": time.perf_counter() - t0}
+    if not args.no_encoder_app:
+        out["reference_encoder_app"] = reference_encoder_app()
     print(json.dumps(out))
 
 
@@ -577,6 +665,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-encoder-app", action="store_true", help="reference arm: skip the whole-encoder run of the reference's own CLI")
     ap.add_argument("--e2e-skip", default="", help="diagnosis only: comma list of e2e parts to leave out (h2d, d2h, pack, pa); a run with this set is not a bench value")
     ap.add_argument("--inflight", type=int, default=5, help="frames in flight in the end-to-end loop (device + pinned host buffers per frame)")
     ap.add_argument("--streams", type=int, default=2, help="compute streams the resident loop spreads consecutive frames over")
