@@ -143,6 +143,60 @@ def _ois(case, backend):
     return _h(t, c)
 
 
+# ---- 16-bit samples (10-bit video): MC and the T/Q chain ---------------------------------------------------------------------------
+def _mc16(case, backend):
+    from test_oracle_mc import make_jobs, make_pictures16, run_oracle16
+    name, w, h, kind, all_fracs, big = case
+    refs = make_pictures16(w, h, seed=w + h, kind=kind)
+    jobs = make_jobs(w, h, len(refs), seed=w, all_fracs=all_fracs, big_mv=big)
+    if backend == "reference":
+        out = run_oracle16(common.load_ref(), "svtref_mc_batch16", refs, jobs, w, h, asm_mode=0)
+    elif backend == "port":
+        out = run_oracle16(common.load_port(), "port_mc_batch16", refs, jobs, w, h)
+    else:
+        out = S.HostYuvPicture(np.zeros((h, w), np.uint16), np.zeros((h // 2, w // 2), np.uint16), np.zeros((h // 2, w // 2), np.uint16), dtype=np.uint16)
+        S.mc_batch16(refs, jobs, out)
+    return _h(*_planes(out))
+
+
+def _tq16(case, backend):
+    from test_oracle_tq import make_src_pred16, make_tq_jobs, run_tq_oracle16
+    name, w, h, kind, shapes, flags = case
+    src, pred = make_src_pred16(w, h, 31, kind)
+    jobs = make_tq_jobs(w, h, seed=8, shapes=shapes, flags=flags)
+    if backend == "reference":
+        recon, coeff, nz = run_tq_oracle16(common.load_ref(), "svtref_tq_batch16", src, pred, jobs, w, h, asm_mode=0)
+    elif backend == "port":
+        recon, coeff, nz = run_tq_oracle16(common.load_port(), "port_tq_batch16", src, pred, jobs, w, h)
+    else:
+        y, cb, cr = (a.copy() for a in pred.interior())
+        recon = S.HostYuvPicture(y, cb, cr, dtype=np.uint16)
+        coeff = S.HostCoeffPicture(w, h)
+        nz = S.tq_batch(src, pred, recon, coeff, jobs, hbd=True)
+    return _h(*_planes(recon), *[np.ascontiguousarray(p) for p in coeff.planes], np.asarray(nz, np.uint32))
+
+
+# ---- encode-pass intra prediction ---------------------------------------------------------------------------------------------------
+def _intra(case, backend):
+    from test_oracle_intra import make_intra_jobs, make_recon, run_intra_batch
+    name, w, h, seed, n_jobs = case
+    jobs = make_intra_jobs(w, h, np.random.default_rng(seed), n_jobs, 0.8)
+    digests = []
+    # a sample of the jobs, one at a time, each predicted from the same reconstructed picture into an empty prediction picture
+    for j in range(0, len(jobs), max(1, len(jobs) // 24)):
+        recon = make_recon(w, h, seed=3)
+        one = jobs[j:j + 1]
+        if backend == "reference":
+            pred = run_intra_batch(common.load_ref(), "svtref_intra_batch", recon, one, C.c_int(0))
+        elif backend == "port":
+            pred = run_intra_batch(common.load_port(), "port_intra_batch", recon, one)
+        else:
+            pred = S.HostYuvPicture(*[np.zeros_like(a) for a in recon.interior()], pad=80, replicate=False)
+            S.intra_batch(recon, pred, one)
+        digests.append(_h(*_planes(pred)))
+    return _h(np.frombuffer("".join(digests).encode(), np.uint8))
+
+
 def cases():
     """[(key, runner, case)] -- small, seeded, a few seconds for all of them on any backend"""
     from test_oracle_dlf import DLF_CASES
@@ -164,6 +218,11 @@ def cases():
         out.append((f"sao_stats/{c[0]}", _sao_stats, c))
     for c in SAO_APPLY_CASES[:2]:
         out.append((f"sao_apply/{c[0]}", _sao_apply, c))
+    for c in MC_CASES[:2]:
+        out.append((f"mc16/{c[0]}", _mc16, c))
+    for c in TQ_CASES[:2] + TQ_CASES[3:4]:
+        out.append((f"tq16/{c[0]}", _tq16, c))
+    out.append(("intra/single_jobs_256x192", _intra, ("single_jobs", 256, 192, 9, 300)))
     out.append(("ois/islice_256x192", _ois, ("islice", 256, 192, dict(slice_type=2), 9)))
     out.append(("ois/dc_only_448x256", _ois, ("dc_only", 448, 256, dict(slice_type=0, limit_ois_to_dc_mode=1, skip_ois_8x8=1), 1)))
     return out
