@@ -66,6 +66,15 @@ __device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t *p)
     return __funnelshift_r(lo, w[1], sh);
 }
 
+// c + the four byte-wise absolute differences of a and b in ONE instruction (VABSDIFF4 with its accumulate operand).  __vsadu4() passes 0 there and
+// leaves the addition to a separate IADD3 that ptxas only sometimes folds back (static count in the ME search bodies: 540 IADD3 next to 1152 VABSDIFF4).
+__device__ __forceinline__ uint32_t vsad4_acc(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v)
 {
 #pragma unroll
