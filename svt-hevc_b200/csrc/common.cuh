@@ -54,16 +54,17 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 // device helpers
 // ------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
-// 4 consecutive bytes starting at an arbitrary byte address (global or shared): two aligned
+// 4 consecutive bytes starting at an arbitrary byte address of a read-only GLOBAL buffer: two aligned
 // 32-bit loads + one funnel shift (SASS: SHF.R.W).
 __device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t *p)
 {
     const uintptr_t a = (uintptr_t)p;
     const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
     const uint32_t sh = (uint32_t)(a & 3) * 8;
-    const uint32_t lo = w[0];
+    // every caller reads a picture plane in global memory that the kernel never writes: LDG (read-only path) instead of a generic LD
+    const uint32_t lo = __ldg(w);
     if (sh == 0) return lo;
-    return __funnelshift_r(lo, w[1], sh);
+    return __funnelshift_r(lo, __ldg(w + 1), sh);
 }
 
 // c + the four byte-wise absolute differences of a and b in ONE instruction (VABSDIFF4 with its accumulate operand).  __vsadu4() passes 0 there and
