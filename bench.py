@@ -591,15 +591,19 @@ def cpu_reference(frames):
     threads = [threading.Thread(target=run, args=(t,)) for t in range(nworkers)]
     for th in threads:
         th.start()
-    gate.wait()
-    t0 = time.perf_counter()
-    gate.wait()
-    gate.wait()
-    dt = time.perf_counter() - t0
+    t0 = dt = None
+    try:
+        gate.wait()
+        t0 = time.perf_counter()
+        gate.wait()
+        gate.wait()
+        dt = time.perf_counter() - t0
+    except threading.BrokenBarrierError:
+        pass                                            # a worker failed and aborted the barrier: its exception is re-raised below
     for th in threads:
         th.join()
-    if errors:
-        raise errors[0]
+    if errors or dt is None:
+        raise errors[0] if errors else RuntimeError("cpu_reference: the worker barrier broke")
     v = N_LCU * frames / dt
     return {"value": v, "unit": "CTU/s", "fps": v / N_LCU, "cores": nworkers, "kind": "reference",
             "sample": f"{frames} full 4K frames of the same stages and jobs through the reference's own functions (MotionEstimateLcu, OpenLoopIntraSearchLcu, "

@@ -10,7 +10,7 @@
 //   MotionEstimateLcu + helpers (driver logic)                         Codec/EbMotionEstimation.c:3671 (and :586,
 //                                        :1847,:2012,:2194,:2315,:2946,:3363,:2742,:2870,:4321-4438)
 //
-// Design: ONE CTA PER LCU for the whole picture (grid = #LCUs, 256 threads).  The CTA stages the 64x64 source
+// Design: ONE CTA PER LCU for the whole picture (grid = #LCUs; 128 threads on integer-pel pictures, 256 with sub-pel refinement: me_kernels.inc).  The CTA stages the 64x64 source
 // block and each reference search window in shared memory exactly once (every reference byte is read from
 // HBM/L2 once per LCU), evaluates search positions with VABSDIFF4 (__vsadu4: 4 byte-SADs per lane-op) on
 // funnel-shifted words, and reduces candidates with warp shuffles.  The reference's sequential tie-break rules

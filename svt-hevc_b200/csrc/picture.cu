@@ -53,8 +53,7 @@ static int build_planes(const svtb200_pa_picture *d, cudaStream_t st, const uint
         const svtb200_plane &p = *pl[k];
         if (!p.buf) continue;
         const int tw = p.width + 2 * p.origin_x, th = p.height + 2 * p.origin_y;
-        dim3 grid((tw / 4 + 255) / 256 + ((tw / 4) % 256 ? 0 : 0) + 1, th);
-        grid.x = ((tw + 3) / 4 + 255) / 256;
+        const dim3 grid(((tw + 3) / 4 + 255) / 256, th);      // one thread per 4 output bytes of a padded row
         decim_pad_kernel<<<grid, 256, 0, st>>>(src, sstride, spad, p.buf, (int)p.stride, p.origin_x, p.width, p.height, steps[k], k == 0 && in_place);
         SVTB200_COUNT_LAUNCH();
     }
