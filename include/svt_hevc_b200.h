@@ -367,6 +367,31 @@ typedef struct svtb200_sao_params {
     uint8_t reserved[3];
 } svtb200_sao_params;
 
+/* f2 / N3: the per-LCU rate-distortion decision between the statistics and the application (saoMode = 1, presets <= M10):
+ * DetermineSaoLumaModeOffsets / DetermineSaoChromaModeOffsets / TestSaoCopyModes in the order SaoGenerationDecision calls them
+ * (Codec/EbSampleAdaptiveOffsetGenerationDecision.c:44,182,437,647-767).  rates = saoMergeFlagBits / saoTypeIndexBits / saoOffsetTrunUnaryBits of
+ * the picture's MdRateEstimationContext_t (Codec/EbMdRateEstimation.h:148-150); lambdas = contextPtr->fullLambda / fullChromaLambdaSao
+ * (Codec/EbCodingLoop.c:4732-4748).  LCUs in raster order, one tile: left / top neighbour = the previous decisions.  The shutSaoCondition* and
+ * noise-class overrides around the call (EbCodingLoop.c:4671-4760) stay with the caller. */
+typedef struct svtb200_sao_rate_tables {
+    uint32_t merge_flag_bits[2];
+    uint32_t type_index_bits[6];
+    uint32_t offset_trun_unary_bits[8];
+} svtb200_sao_rate_tables;
+typedef struct svtb200_sao_decision {
+    uint8_t  merge_left, merge_up;   /* saoMergeLeftFlag / saoMergeUpFlag */
+    uint8_t  type[2];                /* saoTypeIndex[luma, chroma]        */
+    uint8_t  band_position[3];
+    uint8_t  reserved;
+    int32_t  offset[3][4];
+    int64_t  luma_cost, chroma_cost; /* saoLumaBestCost / saoChromaBestCost */
+} svtb200_sao_decision;
+int svtb200_sao_decision_picture(const svtb200_sao_stats *stats, int lcu_cols, int lcu_rows, const svtb200_sao_rate_tables *rates, uint64_t full_lambda,
+                                 uint64_t full_chroma_lambda_sao, int is10bit, svtb200_sao_decision *out);
+/* params_out_dev (optional): the same decisions in the form svtb200_sao_apply_picture_dev consumes */
+int svtb200_sao_decision_picture_dev(const svtb200_sao_stats *stats_dev, int lcu_cols, int lcu_rows, const svtb200_sao_rate_tables *rates, uint64_t full_lambda,
+                                     uint64_t full_chroma_lambda_sao, int is10bit, svtb200_sao_decision *out_dev, svtb200_sao_params *params_out_dev, void *cuda_stream);
+
 /* Applies SAO to a whole picture: out = SAO(in), every sample classified on the UNMODIFIED input (what the reference
  * achieves in place with its saoUpBuffer / saoLeftBuffer line buffers, ApplySaoOffsetsPicture Codec/EbEncDecProcess.c:522,
  * ApplySaoOffsetsLcu :215, kernels SAOApplyBO / SAOApplyEO_{0,90,135,45} C_DEFAULT/EbSampleAdaptiveOffset_C.c:394-861).
