@@ -58,6 +58,37 @@ static int sao_stats_impl(const svtb200_yuv_picture *src, const svtb200_yuv_pict
 int port_sao_stats_picture(const svtb200_yuv_picture *src, const svtb200_yuv_picture *rec, svtb200_sao_stats *out) { return sao_stats_impl(src, rec, out, 0); }
 int port_sao_stats_picture16(const svtb200_yuv_picture *src, const svtb200_yuv_picture *rec, svtb200_sao_stats *out) { return sao_stats_impl(src, rec, out, 1); }
 
+/* SURVEY §7 H3 -- the deblocking state the encoder's SAO gather sees.  EncodePass deblocks LCU n and gathers its statistics before any later LCU is
+ * even reconstructed (Codec/EbCodingLoop.c:4600-4760), and the per-LCU DLF drivers postpone everything that needs the right / bottom neighbour
+ * (LCUInternalAreaDLFCore leaves the last 4 columns / rows alone, LCUBoundaryDLFCore of the NEXT LCUs finishes them, Codec/EbDeblockingFilter.c:2222,
+ * 2828).  Checked sample by sample against the reference's own interleaving (oracle/ref_dlf_harness.c: svtref_dlf_sao_stats_picture) on every DLF test
+ * picture: at gather time an LCU holds the FINAL deblocked samples everywhere except its last 4 columns (when a right neighbour exists) and its last
+ * 4 rows (when a bottom neighbour exists) -- 4 samples in each plane's own units, luma and chroma alike -- which still hold the UNFILTERED
+ * reconstruction.  The strips of different LCUs never overlap, so one composite picture serves every LCU: */
+int port_sao_h3_compose(const svtb200_yuv_picture *deblocked, const svtb200_yuv_picture *unfiltered, const svtb200_yuv_picture *out)
+{
+    const int W = deblocked->y.width, H = deblocked->y.height;
+    for (int c = 0; c < 3; ++c) {
+        const int sh = c ? 1 : 0, pw = W >> sh, ph = H >> sh, L = 64 >> sh;
+        const svtb200_plane *d = pl(deblocked, c), *u = pl(unfiltered, c), *o = pl(out, c);
+        for (int y = 0; y < ph; ++y)
+            for (int x = 0; x < pw; ++x) {
+                const int x1 = ((x / L) + 1) * L < pw ? ((x / L) + 1) * L : pw, y1 = ((y / L) + 1) * L < ph ? ((y / L) + 1) * L : ph;   /* end of this LCU */
+                const int strip = (x1 < pw && x >= x1 - 4) || (y1 < ph && y >= y1 - 4);
+                const svtb200_plane *s = strip ? u : d;
+                o->buf[(size_t)(o->origin_y + y) * o->stride + o->origin_x + x] = s->buf[(size_t)(s->origin_y + y) * s->stride + s->origin_x + x];
+            }
+    }
+    return 0;
+}
+/* statistics of every LCU in the state the encoder gathers them on a picture with deblocking: `scratch` (same geometry) receives the composite */
+int port_sao_stats_picture_h3(const svtb200_yuv_picture *src, const svtb200_yuv_picture *deblocked, const svtb200_yuv_picture *unfiltered,
+                              const svtb200_yuv_picture *scratch, svtb200_sao_stats *out)
+{
+    port_sao_h3_compose(deblocked, unfiltered, scratch);
+    return sao_stats_impl(src, scratch, out, 0);
+}
+
 /* hbd: SAOApplyBO16bit / SAOApplyEO_*16bit (:431 ff): band = sample >> 5, results clipped to 1023 */
 static int sao_apply_impl(const svtb200_yuv_picture *in, const svtb200_yuv_picture *outp, const svtb200_sao_params *prm, const uint8_t sao_flag[2], int hbd)
 {
