@@ -358,6 +358,11 @@ typedef struct svtb200_sao_stats {
  * SURVEY §7 H3 / Codec/EbCodingLoop.c:4692-4748; on pictures whose DLF is off that state is simply the un-deblocked recon). */
 int svtb200_sao_stats_picture(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out);
 int svtb200_sao_stats_picture_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out_dev, void *cuda_stream);
+/* H3: the statistics the encoder gathers on a picture WITH deblocking -- LCU n is gathered right after its own deblocking step
+ * (Codec/EbCodingLoop.c:4600-4760), when its last 4 columns / rows still wait for the right / bottom neighbour: `deblocked` everywhere except those
+ * strips, which are read from `unfiltered` (same geometry; the reconstruction before svtb200_dlf_picture).  Device pictures. */
+int svtb200_sao_stats_picture_h3_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *deblocked, const svtb200_yuv_picture *unfiltered,
+                                     svtb200_sao_stats *out_dev, void *cuda_stream);
 
 /* Per-LCU SAO parameters: mirror of SaoParameters_t (Codec/EbCodingUnit.h:137-146). */
 typedef struct svtb200_sao_params {

@@ -610,3 +610,8 @@ def sao_decision_picture(stats, lcu_cols, lcu_rows, rates, full_lambda, full_chr
     check(lib().svtb200_sao_decision_picture(_u8p(stats), C.c_int(lcu_cols), C.c_int(lcu_rows), C.byref(r), C.c_uint64(full_lambda),
                                              C.c_uint64(full_chroma_lambda_sao), C.c_int(is10bit), _u8p(out)))
     return out
+
+
+def sao_stats_picture_h3_dev(src_struct, deblocked_struct, unfiltered_struct, out_ptr, stream=0):
+    """H3 statistics (device pictures): `deblocked` except the right / bottom 4-sample strips of every LCU, which come from `unfiltered`."""
+    check(lib().svtb200_sao_stats_picture_h3_dev(C.byref(src_struct), C.byref(deblocked_struct), C.byref(unfiltered_struct), C.c_void_p(out_ptr), C.c_void_p(stream)))
