@@ -65,7 +65,7 @@ int port_sao_stats_picture16(const svtb200_yuv_picture *src, const svtb200_yuv_p
  * picture: at gather time an LCU holds the FINAL deblocked samples everywhere except its last 4 columns (when a right neighbour exists) and its last
  * 4 rows (when a bottom neighbour exists) -- 4 samples in each plane's own units, luma and chroma alike -- which still hold the UNFILTERED
  * reconstruction.  The strips of different LCUs never overlap, so one composite picture serves every LCU: */
-int port_sao_h3_compose(const svtb200_yuv_picture *deblocked, const svtb200_yuv_picture *unfiltered, const svtb200_yuv_picture *out)
+static int h3_compose_impl(const svtb200_yuv_picture *deblocked, const svtb200_yuv_picture *unfiltered, const svtb200_yuv_picture *out, int bps)
 {
     const int W = deblocked->y.width, H = deblocked->y.height;
     for (int c = 0; c < 3; ++c) {
@@ -76,17 +76,25 @@ int port_sao_h3_compose(const svtb200_yuv_picture *deblocked, const svtb200_yuv_
                 const int x1 = ((x / L) + 1) * L < pw ? ((x / L) + 1) * L : pw, y1 = ((y / L) + 1) * L < ph ? ((y / L) + 1) * L : ph;   /* end of this LCU */
                 const int strip = (x1 < pw && x >= x1 - 4) || (y1 < ph && y >= y1 - 4);
                 const svtb200_plane *s = strip ? u : d;
-                o->buf[(size_t)(o->origin_y + y) * o->stride + o->origin_x + x] = s->buf[(size_t)(s->origin_y + y) * s->stride + s->origin_x + x];
+                memcpy(o->buf + ((size_t)(o->origin_y + y) * o->stride + o->origin_x + x) * bps, s->buf + ((size_t)(s->origin_y + y) * s->stride + s->origin_x + x) * bps, (size_t)bps);
             }
     }
     return 0;
 }
+int port_sao_h3_compose(const svtb200_yuv_picture *deblocked, const svtb200_yuv_picture *unfiltered, const svtb200_yuv_picture *out) { return h3_compose_impl(deblocked, unfiltered, out, 1); }
+int port_sao_h3_compose16(const svtb200_yuv_picture *deblocked, const svtb200_yuv_picture *unfiltered, const svtb200_yuv_picture *out) { return h3_compose_impl(deblocked, unfiltered, out, 2); }
 /* statistics of every LCU in the state the encoder gathers them on a picture with deblocking: `scratch` (same geometry) receives the composite */
 int port_sao_stats_picture_h3(const svtb200_yuv_picture *src, const svtb200_yuv_picture *deblocked, const svtb200_yuv_picture *unfiltered,
                               const svtb200_yuv_picture *scratch, svtb200_sao_stats *out)
 {
     port_sao_h3_compose(deblocked, unfiltered, scratch);
     return sao_stats_impl(src, scratch, out, 0);
+}
+int port_sao_stats_picture16_h3(const svtb200_yuv_picture *src, const svtb200_yuv_picture *deblocked, const svtb200_yuv_picture *unfiltered,
+                                const svtb200_yuv_picture *scratch, svtb200_sao_stats *out)
+{
+    port_sao_h3_compose16(deblocked, unfiltered, scratch);
+    return sao_stats_impl(src, scratch, out, 1);
 }
 
 /* hbd: SAOApplyBO16bit / SAOApplyEO_*16bit (:431 ff): band = sample >> 5, results clipped to 1023 */

@@ -92,3 +92,35 @@ def test_composite_touches_only_the_strips():
                 if y1 < ph:
                     m[y1 - 4:y1, x0:x1] = True
         assert np.array_equal(o, np.where(m, u, f))
+
+
+# ---- 16-bit sample planes (10-bit video): LCU*DLFCore16bit + GatherSaoStatisticsLcu_62x62_16bit ----------------------------------------------
+@needs_ref
+@pytest.mark.parametrize("case", CASES[:5] + CASES[-1:], ids=lambda c: c[0])
+def test_gather_time_state_and_statistics16_port_vs_reference(case):
+    from test_oracle_dlf import run_dlf16, to16
+    name, w, h, kind, density = case
+    pic8, vbs, hbs, qp, prm = make_dlf_inputs(w, h, seed=w + h, density=density, kind=kind)
+    pic = to16(pic8, seed=w, extremes=(kind == "extremes"))
+    rng = np.random.default_rng(w * 7 + h)
+    src = S.HostYuvPicture(*[np.clip(a.astype(np.int32) + rng.integers(-30, 31, a.shape), 0, 1023).astype(np.uint16) for a in pic.interior()], dtype=np.uint16)
+    n = ((w + 63) // 64) * ((h + 63) // 64)
+    # the reference's interleaved run
+    work = S.HostYuvPicture(*(a.copy() for a in pic.interior()), dtype=np.uint16)
+    snap = S.HostYuvPicture(*(np.zeros_like(a) for a in pic.interior()), dtype=np.uint16)
+    want = np.zeros((n, 3), dtype=S.SAO_STATS_DTYPE)
+    fn = ref.svtref_dlf_sao_stats_picture16
+    fn.restype = C.c_int
+    assert fn(C.byref(work.struct), C.byref(src.struct), vp(vbs), vp(hbs), vp(qp), C.byref(prm), vp(want), C.byref(snap.struct), C.c_int(0)) == 0
+    # the oracle: picture-order deblocking, composite, statistics
+    final = run_dlf16(port, "port_dlf_picture16", pic, vbs, hbs, qp, prm)
+    scratch = S.HostYuvPicture(*(np.zeros_like(a) for a in pic.interior()), dtype=np.uint16)
+    got = np.zeros((n, 3), dtype=S.SAO_STATS_DTYPE)
+    pf = port.port_sao_stats_picture16_h3
+    pf.restype = C.c_int
+    assert pf(C.byref(src.struct), C.byref(final.struct), C.byref(pic.struct), C.byref(scratch.struct), vp(got)) == 0
+    for a, b, nm in zip(work.interior(), final.interior(), "Y Cb Cr".split()):
+        assert np.array_equal(a, b), f"{name}: final {nm} (16-bit) differs"
+    for a, b, nm in zip(snap.interior(), scratch.interior(), "Y Cb Cr".split()):
+        assert np.array_equal(a, b), f"{name}: 16-bit gather-time state of {nm} differs from the rule at {np.argwhere(a != b)[:4]}"
+    assert_stats_equal(got, want, name + " 16-bit H3 statistics port vs reference")
