@@ -542,6 +542,9 @@ int svtb200_pa_picture_download(const svtb200_pa_picture *dev, const svtb200_pa_
 int svtb200_yuv_picture_upload(const svtb200_yuv_picture *dev, const void *host_y, uint32_t host_y_stride, const void *host_cb,
                                uint32_t host_cb_stride, const void *host_cr, uint32_t host_cr_stride, uint32_t bytes_per_sample,
                                void *cuda_stream);
+/* b6: GeneratePadding (Codec/EbMcp.c:1017) on a device-resident reconstructed picture, in place, before it serves as a reference
+ * (PadRefAndSetFlags, Codec/EbEncDecProcess.c): every padding sample takes the nearest interior sample.  8-bit planes. */
+int svtb200_yuv_picture_pad_dev(const svtb200_yuv_picture *dev, void *cuda_stream);
 int svtb200_copy_async(void *dst, const void *src, size_t bytes, int device_to_host, void *cuda_stream);
 void svtb200_pa_picture_destroy(svtb200_pa_picture *dev);
 
