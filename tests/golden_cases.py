@@ -197,6 +197,31 @@ def _intra(case, backend):
     return _h(np.frombuffer("".join(digests).encode(), np.uint8))
 
 
+# ---- oracles whose device version is not on main yet (reference and port only) -------------------------------------------------------------
+NO_CUDA_YET = ("saodec/", "sao_h3/")
+
+
+def _saodec(case, backend):
+    import test_oracle_saodec as T
+    name, sao_case, rates, lam, lam_c = case
+    stats, cols, rows = T.picture_stats(sao_case)
+    lib, fn = (T.refdec, "svtref_sao_decision_picture") if backend == "reference" else (T.port, "port_sao_decision_picture")
+    assert backend != "cuda" and lib is not None
+    d = T.run_decision(lib, fn, stats, cols, rows, T.rate_tables(rates), lam, lam_c)
+    return _h(*[d[f] for f in ("merge_left", "merge_up", "type", "band_position", "offset", "luma_cost", "chroma_cost")])
+
+
+def _sao_h3(case, backend):
+    import test_oracle_sao_h3 as T
+    from test_oracle_dlf import make_dlf_inputs
+    name, w, h, kind, density = case
+    pic, vbs, hbs, qp, prm = make_dlf_inputs(w, h, seed=w + h, density=density, kind=kind)
+    src = T.noisy_source(pic, w * 7 + h)
+    assert backend != "cuda"
+    st = T.reference_interleaved(pic, src, vbs, hbs, qp, prm, asm_mode=0)[2] if backend == "reference" else T.port_h3(pic, src, vbs, hbs, qp, prm)[2]
+    return _h(st["bo_diff"], st["bo_count"], st["eo_diff"][..., :4], st["eo_count"][..., :4])
+
+
 def cases():
     """[(key, runner, case)] -- small, seeded, a few seconds for all of them on any backend"""
     from test_oracle_dlf import DLF_CASES
@@ -223,6 +248,10 @@ def cases():
     for c in TQ_CASES[:2] + TQ_CASES[3:4]:
         out.append((f"tq16/{c[0]}", _tq16, c))
     out.append(("intra/single_jobs_256x192", _intra, ("single_jobs", 256, 192, 9, 300)))
+    out.append(("saodec/synth_typical", _saodec, ("synth_typical", SAO_CASES[0], "typical", 439162, 350000)))
+    out.append(("saodec/partial_expensive", _saodec, ("partial_expensive", SAO_CASES[1], "expensive", 9000000, 7000000)))
+    out.append(("sao_h3/synth_dense_320x256", _sao_h3, DLF_CASES[4]))
+    out.append(("sao_h3/synth_partial_lcu_200x136", _sao_h3, DLF_CASES[1]))
     out.append(("ois/islice_256x192", _ois, ("islice", 256, 192, dict(slice_type=2), 9)))
     out.append(("ois/dc_only_448x256", _ois, ("dc_only", 448, 256, dict(slice_type=0, limit_ois_to_dc_mode=1, skip_ois_8x8=1), 1)))
     return out
