@@ -358,6 +358,11 @@ typedef struct svtb200_sao_stats {
  * SURVEY §7 H3 / Codec/EbCodingLoop.c:4692-4748; on pictures whose DLF is off that state is simply the un-deblocked recon). */
 int svtb200_sao_stats_picture(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out);
 int svtb200_sao_stats_picture_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out_dev, void *cuda_stream);
+/* H3: the statistics the encoder gathers on a picture WITH deblocking -- LCU n is gathered right after its own deblocking step
+ * (Codec/EbCodingLoop.c:4600-4760), when its last 4 columns / rows still wait for the right / bottom neighbour: `deblocked` everywhere except those
+ * strips, which are read from `unfiltered` (same geometry; the reconstruction before svtb200_dlf_picture).  Device pictures. */
+int svtb200_sao_stats_picture_h3_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *deblocked, const svtb200_yuv_picture *unfiltered,
+                                     svtb200_sao_stats *out_dev, void *cuda_stream);
 
 /* Per-LCU SAO parameters: mirror of SaoParameters_t (Codec/EbCodingUnit.h:137-146). */
 typedef struct svtb200_sao_params {
@@ -366,6 +371,31 @@ typedef struct svtb200_sao_params {
     int8_t  offset[3][4];       /* saoOffset[Y, Cb, Cr][4]                                                      */
     uint8_t reserved[3];
 } svtb200_sao_params;
+
+/* f2 / N3: the per-LCU rate-distortion decision between the statistics and the application (saoMode = 1, presets <= M10):
+ * DetermineSaoLumaModeOffsets / DetermineSaoChromaModeOffsets / TestSaoCopyModes in the order SaoGenerationDecision calls them
+ * (Codec/EbSampleAdaptiveOffsetGenerationDecision.c:44,182,437,647-767).  rates = saoMergeFlagBits / saoTypeIndexBits / saoOffsetTrunUnaryBits of
+ * the picture's MdRateEstimationContext_t (Codec/EbMdRateEstimation.h:148-150); lambdas = contextPtr->fullLambda / fullChromaLambdaSao
+ * (Codec/EbCodingLoop.c:4732-4748).  LCUs in raster order, one tile: left / top neighbour = the previous decisions.  The shutSaoCondition* and
+ * noise-class overrides around the call (EbCodingLoop.c:4671-4760) stay with the caller. */
+typedef struct svtb200_sao_rate_tables {
+    uint32_t merge_flag_bits[2];
+    uint32_t type_index_bits[6];
+    uint32_t offset_trun_unary_bits[8];
+} svtb200_sao_rate_tables;
+typedef struct svtb200_sao_decision {
+    uint8_t  merge_left, merge_up;   /* saoMergeLeftFlag / saoMergeUpFlag */
+    uint8_t  type[2];                /* saoTypeIndex[luma, chroma]        */
+    uint8_t  band_position[3];
+    uint8_t  reserved;
+    int32_t  offset[3][4];
+    int64_t  luma_cost, chroma_cost; /* saoLumaBestCost / saoChromaBestCost */
+} svtb200_sao_decision;
+int svtb200_sao_decision_picture(const svtb200_sao_stats *stats, int lcu_cols, int lcu_rows, const svtb200_sao_rate_tables *rates, uint64_t full_lambda,
+                                 uint64_t full_chroma_lambda_sao, int is10bit, svtb200_sao_decision *out);
+/* params_out_dev (optional): the same decisions in the form svtb200_sao_apply_picture_dev consumes */
+int svtb200_sao_decision_picture_dev(const svtb200_sao_stats *stats_dev, int lcu_cols, int lcu_rows, const svtb200_sao_rate_tables *rates, uint64_t full_lambda,
+                                     uint64_t full_chroma_lambda_sao, int is10bit, svtb200_sao_decision *out_dev, svtb200_sao_params *params_out_dev, void *cuda_stream);
 
 /* Applies SAO to a whole picture: out = SAO(in), every sample classified on the UNMODIFIED input (what the reference
  * achieves in place with its saoUpBuffer / saoLeftBuffer line buffers, ApplySaoOffsetsPicture Codec/EbEncDecProcess.c:522,
@@ -512,6 +542,9 @@ int svtb200_pa_picture_download(const svtb200_pa_picture *dev, const svtb200_pa_
 int svtb200_yuv_picture_upload(const svtb200_yuv_picture *dev, const void *host_y, uint32_t host_y_stride, const void *host_cb,
                                uint32_t host_cb_stride, const void *host_cr, uint32_t host_cr_stride, uint32_t bytes_per_sample,
                                void *cuda_stream);
+/* b6: GeneratePadding (Codec/EbMcp.c:1017) on a device-resident reconstructed picture, in place, before it serves as a reference
+ * (PadRefAndSetFlags, Codec/EbEncDecProcess.c): every padding sample takes the nearest interior sample.  8-bit planes. */
+int svtb200_yuv_picture_pad_dev(const svtb200_yuv_picture *dev, void *cuda_stream);
 int svtb200_copy_async(void *dst, const void *src, size_t bytes, int device_to_host, void *cuda_stream);
 void svtb200_pa_picture_destroy(svtb200_pa_picture *dev);
 

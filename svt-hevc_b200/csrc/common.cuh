@@ -54,16 +54,26 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 // device helpers
 // ------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
-// 4 consecutive bytes starting at an arbitrary byte address (global or shared): two aligned
+// 4 consecutive bytes starting at an arbitrary byte address of a read-only GLOBAL buffer: two aligned
 // 32-bit loads + one funnel shift (SASS: SHF.R.W).
 __device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t *p)
 {
     const uintptr_t a = (uintptr_t)p;
     const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
     const uint32_t sh = (uint32_t)(a & 3) * 8;
-    const uint32_t lo = w[0];
+    // every caller reads a picture plane in global memory that the kernel never writes: LDG (read-only path) instead of a generic LD
+    const uint32_t lo = __ldg(w);
     if (sh == 0) return lo;
-    return __funnelshift_r(lo, w[1], sh);
+    return __funnelshift_r(lo, __ldg(w + 1), sh);
+}
+
+// c + the four byte-wise absolute differences of a and b in ONE instruction (VABSDIFF4 with its accumulate operand).  __vsadu4() passes 0 there and
+// leaves the addition to a separate IADD3 that ptxas only sometimes folds back (static count in the ME search bodies: 540 IADD3 next to 1152 VABSDIFF4).
+__device__ __forceinline__ uint32_t vsad4_acc(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v)

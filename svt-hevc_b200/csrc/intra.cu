@@ -289,7 +289,7 @@ __device__ __forceinline__ uint32_t warp_mode_sad(const uint8_t *line, const Mod
         const uintptr_t sp = (uintptr_t)(s_src + (cy + r + 1) * SRC_P + cx + c + 1);   // not 4-byte aligned (the apron column): two words + funnel shift
         const uint32_t *sw2 = (const uint32_t *)(sp & ~(uintptr_t)3);
         const uint32_t sw = __funnelshift_r(sw2[0], sw2[1], (uint32_t)(sp & 3) * 8);
-        acc = __vsadu4(intra_pel4(line, m, c, r), sw) + acc;
+        acc = vsad4_acc(intra_pel4(line, m, c, r), sw, acc);
     }
     return warp_sum(acc);
 }

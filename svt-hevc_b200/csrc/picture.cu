@@ -129,6 +129,29 @@ int svtb200_yuv_picture_upload(const svtb200_yuv_picture *dev, const void *host_
     return SVTB200_OK;
 }
 
+// Edge replication of a device-resident Y/Cb/Cr picture in place (GeneratePadding, Codec/EbMcp.c:1017, as the reference runs it on a reconstructed
+// picture before it serves as a reference: PadRefAndSetFlags, Codec/EbEncDecProcess.c): the interior stays, every padding sample takes the nearest
+// interior sample.  8-bit planes.
+int svtb200_yuv_picture_pad_dev(const svtb200_yuv_picture *dev, void *cuda_stream)
+{
+    if (!dev) { set_error("yuv_picture_pad_dev: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    int rc = ensure_device();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const svtb200_plane *pl[3] = {&dev->y, &dev->cb, &dev->cr};
+    for (int k = 0; k < 3; ++k) {
+        const svtb200_plane &p = *pl[k];
+        if (!p.buf || p.origin_x != p.origin_y) { set_error("yuv_picture_pad_dev: null plane or unequal horizontal / vertical padding"); return SVTB200_ERR_BAD_ARG; }
+        const int tw = p.width + 2 * p.origin_x, th = p.height + 2 * p.origin_y;
+        if ((uint32_t)tw > p.stride) { set_error("yuv_picture_pad_dev: pitch smaller than the padded width"); return SVTB200_ERR_BAD_ARG; }
+        const dim3 grid(((tw + 3) / 4 + 255) / 256, th);
+        decim_pad_kernel<<<grid, 256, 0, st>>>(p.buf, (int)p.stride, p.origin_x, p.buf, (int)p.stride, p.origin_x, p.width, p.height, 1, 1);
+        SVTB200_COUNT_LAUNCH();
+    }
+    SVTB200_CUDA_TRY(cudaGetLastError());
+    return SVTB200_OK;
+}
+
 int svtb200_copy_async(void *dst, const void *src, size_t bytes, int device_to_host, void *cuda_stream)
 {
     if ((!dst || !src) && bytes) { set_error("copy_async: null pointer"); return SVTB200_ERR_BAD_ARG; }

@@ -20,6 +20,7 @@ namespace svtb200 {
 struct PlaneRO { const uint8_t *p; int stride; };
 struct StatsArgs {
     PlaneRO src[3], rec[3];      // pointers at the interior origin of each plane
+    PlaneRO pre[3];              // H3: the unfiltered reconstruction (p == nullptr: statistics of `rec` as it is)
     svtb200_sao_stats *out;
     int W, H, cols;
 };
@@ -60,9 +61,15 @@ __global__ void __launch_bounds__(ST_NT) sao_stats_kernel(const __grid_constant_
     const uint8_t *r = A.rec[c].p + (size_t)oy * A.rec[c].stride + ox, *s = A.src[c].p + (size_t)oy * A.src[c].stride + ox;
     const int wpr = lw >> 2;
     const SmallDiv d_wpr = mk_div(wpr);
+    // H3 (rule pinned by tests/test_oracle_sao_h3.py): when the encoder gathers LCU n's statistics its last 4 columns / rows still hold the
+    // UNFILTERED reconstruction if a right / bottom neighbour exists (their deblocking waits for that neighbour); everything else is final.
+    const uint8_t *u = A.pre[c].p ? A.pre[c].p + (size_t)oy * A.pre[c].stride + ox : nullptr;
+    const bool has_right = (lx + 1) * 64 < A.W, has_bottom = (ly + 1) * 64 < A.H;
     for (int i = threadIdx.x; i < lh * wpr; i += ST_NT) {
         const int y = udiv(i, d_wpr), x4 = i - y * wpr;
-        ((uint32_t *)(s_rec + y * 72))[1 + x4] = *(const uint32_t *)(r + (size_t)y * A.rec[c].stride + 4 * x4);   // block origins are 4-aligned
+        const bool strip = u && ((has_right && 4 * x4 >= lw - 4) || (has_bottom && y >= lh - 4));
+        ((uint32_t *)(s_rec + y * 72))[1 + x4] = strip ? *(const uint32_t *)(u + (size_t)y * A.pre[c].stride + 4 * x4)
+                                                        : *(const uint32_t *)(r + (size_t)y * A.rec[c].stride + 4 * x4);   // block origins are 4-aligned
     }
     int *my = s_h + threadIdx.x;
 #pragma unroll 4
@@ -274,14 +281,23 @@ using namespace svtb200;
 
 extern "C" {
 
-static int sao_stats_dev_impl(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out_dev, void *cuda_stream, bool hbd)
+static int sao_stats_dev_impl(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out_dev, void *cuda_stream, bool hbd,
+                              const svtb200_yuv_picture *unfiltered = nullptr)
 {
     const size_t bps = hbd ? 2 : 1;
     if (!src || !recon || !out_dev) { set_error("sao_stats_picture_dev: bad argument"); return SVTB200_ERR_BAD_ARG; }
     int rc = sao_check(src, recon, "sao_stats_picture");
+    if (!rc && unfiltered) rc = sao_check(unfiltered, recon, "sao_stats_picture_h3");
     if (rc || (rc = ensure_device())) return rc;
+    if (unfiltered && hbd) { set_error("sao_stats_picture_h3: 16-bit planes not supported yet"); return SVTB200_ERR_UNSUPPORTED; }
     StatsArgs A;
     for (int k = 0; k < 3; ++k) {
+        A.pre[k] = {nullptr, 0};
+        if (unfiltered) {
+            const svtb200_plane *q = plane_of(unfiltered, k);
+            A.pre[k] = {q->buf + ((size_t)q->origin_y * q->stride + q->origin_x) * bps, (int)q->stride};
+            if (((uintptr_t)A.pre[k].p) & 3) { set_error("sao_stats_picture_h3: plane interiors must be 4-byte aligned"); return SVTB200_ERR_BAD_ARG; }
+        }
         const svtb200_plane *s = plane_of(src, k), *r = plane_of(recon, k);
         A.src[k] = {s->buf + ((size_t)s->origin_y * s->stride + s->origin_x) * bps, (int)s->stride};
         A.rec[k] = {r->buf + ((size_t)r->origin_y * r->stride + r->origin_x) * bps, (int)r->stride};
@@ -380,6 +396,12 @@ static int sao_apply_impl(const svtb200_yuv_picture *in, const svtb200_yuv_pictu
 int svtb200_sao_stats_picture_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out_dev, void *cuda_stream)
 { return sao_stats_dev_impl(src, recon, out_dev, cuda_stream, false); }
 int svtb200_sao_stats_picture(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out) { return sao_stats_impl(src, recon, out, false); }
+int svtb200_sao_stats_picture_h3_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *deblocked, const svtb200_yuv_picture *unfiltered, svtb200_sao_stats *out_dev,
+                                     void *cuda_stream)
+{
+    if (!unfiltered) { set_error("sao_stats_picture_h3_dev: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    return sao_stats_dev_impl(src, deblocked, out_dev, cuda_stream, false, unfiltered);
+}
 int svtb200_sao_apply_picture_dev(const svtb200_yuv_picture *in, const svtb200_yuv_picture *out, const svtb200_sao_params *lcu_params_dev, const uint8_t sao_flag[2], void *cuda_stream)
 { return sao_apply_dev_impl(in, out, lcu_params_dev, sao_flag, cuda_stream, false); }
 int svtb200_sao_apply_picture(const svtb200_yuv_picture *in, const svtb200_yuv_picture *out, const svtb200_sao_params *lcu_params, const uint8_t sao_flag[2])

@@ -589,3 +589,29 @@ def yuv_picture_upload(dev_struct, y_ptr, y_stride, cb_ptr, cb_stride, cr_ptr, c
 
 def copy_async(dst_ptr, src_ptr, nbytes, device_to_host, stream=0):
     check(lib().svtb200_copy_async(C.c_void_p(dst_ptr), C.c_void_p(src_ptr), C.c_size_t(nbytes), C.c_int(1 if device_to_host else 0), C.c_void_p(stream)))
+
+
+# ------------------------------------------------------------------------------------------------
+# SAO rate-distortion decision (row f2 / next-row N3)
+# ------------------------------------------------------------------------------------------------
+class SaoRateTables(C.Structure):
+    _fields_ = [("merge_flag_bits", C.c_uint32 * 2), ("type_index_bits", C.c_uint32 * 6), ("offset_trun_unary_bits", C.c_uint32 * 8)]
+
+
+SAO_DECISION_DTYPE = np.dtype([("merge_left", np.uint8), ("merge_up", np.uint8), ("type", np.uint8, 2), ("band_position", np.uint8, 3), ("reserved", np.uint8),
+                               ("offset", np.int32, (3, 4)), ("luma_cost", np.int64), ("chroma_cost", np.int64)], align=True)
+
+
+def sao_decision_picture(stats, lcu_cols, lcu_rows, rates, full_lambda, full_chroma_lambda_sao, is10bit=0):
+    """Host-buffer SAO decision of a picture: stats[(lcu, component)] -> one SAO_DECISION_DTYPE record per LCU."""
+    out = np.zeros(lcu_cols * lcu_rows, dtype=SAO_DECISION_DTYPE)
+    r = SaoRateTables()
+    C.memmove(C.byref(r), C.byref(rates), C.sizeof(r))
+    check(lib().svtb200_sao_decision_picture(_u8p(stats), C.c_int(lcu_cols), C.c_int(lcu_rows), C.byref(r), C.c_uint64(full_lambda),
+                                             C.c_uint64(full_chroma_lambda_sao), C.c_int(is10bit), _u8p(out)))
+    return out
+
+
+def sao_stats_picture_h3_dev(src_struct, deblocked_struct, unfiltered_struct, out_ptr, stream=0):
+    """H3 statistics (device pictures): `deblocked` except the right / bottom 4-sample strips of every LCU, which come from `unfiltered`."""
+    check(lib().svtb200_sao_stats_picture_h3_dev(C.byref(src_struct), C.byref(deblocked_struct), C.byref(unfiltered_struct), C.c_void_p(out_ptr), C.c_void_p(stream)))

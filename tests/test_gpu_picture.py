@@ -44,3 +44,22 @@ def test_yuv_picture_upload_8bit(w, h, contiguous):
 @pytest.mark.parametrize("contiguous", [True, False])
 def test_yuv_picture_upload_16bit(contiguous):
     _upload(448, 256, 80, 2, contiguous)
+
+
+@pytest.mark.parametrize("w,h,pad", [(3840, 2160, 80), (448, 256, 80), (200, 72, 16), (136, 40, 8)])
+def test_yuv_picture_pad_dev_replicates_edges(w, h, pad):
+    """GeneratePadding on a device picture == numpy edge padding of the interior"""
+    import ctypes as C
+    import torch
+    rng = np.random.default_rng(w + h)
+    planes, want = [], []
+    for (pw, ph, pp) in ((w, h, pad), (w // 2, h // 2, pad // 2), (w // 2, h // 2, pad // 2)):
+        a = rng.integers(0, 256, (ph, pw), dtype=np.uint8)
+        t = torch.full((ph + 2 * pp, pw + 2 * pp + (-(pw + 2 * pp)) % 4), 7, dtype=torch.uint8, device="cuda")
+        t[pp:pp + ph, pp:pp + pw] = torch.from_numpy(a).cuda()
+        planes.append(t); want.append(np.pad(a, pp, mode="edge"))
+    st = S.make_yuv_struct(tuple(t.data_ptr() for t in planes), tuple(t.shape[1] for t in planes), pad, w, h)
+    S.check(S.lib().svtb200_yuv_picture_pad_dev(C.byref(st), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    for t, wnt in zip(planes, want):
+        assert np.array_equal(t.cpu().numpy()[:, :wnt.shape[1]], wnt)
