@@ -5,6 +5,7 @@
 // CUDA stream and its own grow-only device scratch arena + pinned staging block (thread_local),
 // so no entry point takes a lock after first use.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -36,6 +37,8 @@ struct ThreadCtx {
     uint8_t *dev = nullptr;   size_t dev_cap = 0,  dev_used = 0;
     uint8_t *pin = nullptr;   size_t pin_cap = 0,  pin_used = 0;
     int init();
+    void release();
+    ~ThreadCtx();
     void reset() { dev_used = 0; pin_used = 0; }
     // bump allocators; pointers stay valid until the next reset(); grow = sync + realloc
     int dev_alloc(size_t bytes, void **out);
@@ -47,6 +50,9 @@ struct ThreadCtx {
 ThreadCtx *tls_ctx();
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// 2-D uint8 tensor map over a padded plane buffer (pitch % 16 == 0, base % 16 == 0) with a box of box_w x box_h bytes (box_w % 16 == 0, both <= 256)
+int make_plane_tensor_map(CUtensorMap *out, const void *buf, uint32_t pitch, uint32_t rows, uint32_t box_w, uint32_t box_h);
 
 #define SVTB200_COUNT_LAUNCH() (::svtb200::g_launches.fetch_add(1, std::memory_order_relaxed))
 
@@ -102,6 +108,39 @@ __device__ __forceinline__ SmallDiv mk_div(int d)
     return q;
 }
 __device__ __forceinline__ int udiv(int n, const SmallDiv &q) { return q.m ? (int)__umulhi((uint32_t)n, q.m) : n >> q.sh; }
+
+// ---- TMA (cp.async.bulk.tensor) + mbarrier primitives --------------------------------------------------
+// Picture planes are described by 2-D uint8 tensor maps over the PADDED buffer (row pitch a multiple of 16 bytes); a box is fetched
+// at an ARBITRARY byte coordinate and lands densely packed at a 128-byte-aligned shared-memory address, i.e. the copy engine does the
+// byte realignment that the register path (load_window_t) leaves to funnel shifts.  Out-of-buffer parts of a box are zero-filled and
+// still counted in the transaction bytes.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// every thread of the CTA polls the phase bit; a transfer that never completes traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t a = smem_u32(bar);
+    uint32_t done = 0;
+    for (int spin = 0; !done; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (spin > (1 << 22)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int x, int y, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(smem_dst)),
+                 "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 // ---- window staging ------------------------------------------------------------------------
 // Copies `rows` rows of `wbytes` bytes starting at global address g (row pitch gstride) into shared memory with row pitch

@@ -30,14 +30,21 @@ struct PlaneD {
 struct MeArgs {
     svtb200_me_config cfg;
     int sp_fp, sp_sp, sp_f_bytes, sp_p_bytes;   // sub-pel planes: pitches and bytes of the F plane / of each of B, H, J
-    int sp_alias;         // the second list's planes overlay the search scratch (8x8 SADs, sums, window)
+    int sp_alias;         // the second list's planes overlay the search scratch
     PlaneD src[3];        // full, quarter, sixteenth
     PlaneD ref[2][3];
     svtb200_me_pu_result *results;
     uint32_t *best_sad, *best_mv, *rc;
     int cols, rows;
-    int win_bytes;        // bytes reserved for the window region of dynamic shared memory
+    int scratch_bytes;    // bytes of the search-scratch union in dynamic shared memory
+    // fast paths (me_kernels.inc): HME level 0 on byte-phase copies, 85-PU full-pel search of 8 x 7 / 16 x 9 areas
+    int hme_fast, hme_p, hme_band, hme_cs;      // window pitch (= TMA box width), search rows per band, bytes between phase copies
+    int fp_yt, fp_nxh, fp_cs;                   // full-pel: search rows (7 / 9, 0 = generic path only), search width / 8, bytes between phase copies
+    CUtensorMap map_hme[2];                     // per list: (hme_p + 16) x (hme_band + 14) box of the sixteenth-resolution reference plane
+    CUtensorMap map_fp[2];                      // per list: 96 x (fp_yt + 63) box of the full-resolution reference plane
 };
+
+constexpr int ME_SCRATCH_OFF = 8320;            // fixed part (8232) + mbarrier, rounded up to the 128-byte TMA destination alignment
 
 }  // namespace svtb200
 
@@ -52,7 +59,7 @@ namespace svtb200 {
 #undef ME_MIN_CTAS
 #define ME_NS k128
 #define ME_NT 128
-#define ME_MIN_CTAS 7
+#define ME_MIN_CTAS 6
 namespace svtb200 {
 #include "me_kernels.inc"
 }
@@ -63,12 +70,7 @@ namespace svtb200 {
 namespace svtb200 {
 using namespace k256;      // leaf kernels and the sub-pel picture kernel
 
-static size_t me_fixed_smem()
-{
-    return 4096 + 2048 + 128 + CHUNK * 64 * 2 + CHUNK * 21 * 4 + 170 * 4 * 2 + 86 * 4 + 48 * 4 + 8 * 8;
-}
-
-// worst-case window bytes over every search this configuration can issue
+// worst-case window bytes over every search the GENERIC path of this configuration can issue
 static int me_window_bytes(const svtb200_me_config &c)
 {
     static const int mult_tab[6][6] = {{100}, {100, 100}, {100, 100, 100}, {200, 140, 100, 70}, {350, 200, 100, 100, 100}, {525, 350, 200, 100, 100, 100}};
@@ -89,6 +91,43 @@ static int me_window_bytes(const svtb200_me_config &c)
     if (c.enable_hme && c.enable_hme_l2) upd(rnd8(std::max(c.hme_l2_w[0], c.hme_l2_w[1])), std::max(c.hme_l2_h[0], c.hme_l2_h[1]), 64, 62);
     upd(std::min<int>(c.search_area_w, 127), std::min<int>(c.search_area_h, 127), 64, 63);
     return (best + 15) & ~15;
+}
+
+// geometry of the fast paths for this configuration (MeArgs::hme_* / fp_*) and the scratch union they share with the generic path
+static void me_plan(const svtb200_me_config &c, MeArgs &A)
+{
+    static const int mult_tab[6][6] = {{100}, {100, 100}, {100, 100, 100}, {200, 140, 100, 70}, {350, 200, 100, 100, 100}, {525, 350, 200, 100, 100, 100}};
+    const int mult = mult_tab[c.hierarchical_levels][c.temporal_layer];
+    size_t need = (size_t)CHUNK * 64 * 2 + (size_t)CHUNK * 21 * 4 + (size_t)me_window_bytes(c);
+    A.hme_fast = 0;
+    if (c.enable_hme && c.enable_hme_l0) {
+        const bool one = c.one_quadrant_hme && !c.enable_hme_l1 && !c.enable_hme_l2;
+        int w = 0, h = 0;
+        if (one) { w = (c.hme_l0_total_w * mult) / 100; h = (c.hme_l0_total_h * mult) / 100; }
+        else for (int q = 0; q < 2; ++q) { w = std::max(w, (c.hme_l0_w[q] * mult) / 100); h = std::max(h, (c.hme_l0_h[q] * mult) / 100); }
+        // a row of 8-position items reads 32 (G - 1) + 48 bytes of each phase copy; copies 1..3 are shifted from copy 0, which costs its last word:
+        // pitch >= that + 4, a multiple of 16 with an ODD number of 16-byte chunks (8 consecutive rows -> 8 different bank groups)
+        const int G = (std::max(w, 1) + 31) / 32;
+        int P = (32 * (G - 1) + 52 + 15) & ~15;
+        if (((P >> 4) & 1) == 0) P += 16;
+        const int nbands = (std::max(h, 1) + 23) / 24, band = (std::max(h, 1) + nbands - 1) / nbands;
+        if (w > 0 && h > 0 && P + 16 <= 256 && band + 14 <= 256 && (size_t)w * h <= 65536) {
+            A.hme_fast = 1; A.hme_p = P; A.hme_band = band;
+            A.hme_cs = (P * (band + 14) + 127) & ~127;
+            need = std::max(need, (size_t)(((P + 16) * (band + 14) + 127) & ~127) + (size_t)4 * A.hme_cs + 64);      // raw TMA box + four phase copies
+        }
+    }
+    A.fp_yt = 0;
+    const int saw = std::min<int>(c.search_area_w, 127), sah = std::min<int>(c.search_area_h, 127);
+    if ((saw == 8 && sah == 7) || (saw == 16 && sah == 9)) {
+        A.fp_yt = sah; A.fp_nxh = saw / 8;
+        int cs = (saw == 8 ? 72 : 80) * (sah + 63);
+        cs = (cs + 15) & ~15;
+        while ((cs & 127) != 64) cs += 16;       // phases 0 / 1 (and 2 / 3) of a half warp land in different halves of the 32 banks
+        A.fp_cs = cs;
+        need = std::max(need, (size_t)((96 * (sah + 63) + 127) & ~127) + (size_t)4 * cs + (size_t)(88 + 12 * saw * sah) * 4);
+    }
+    A.scratch_bytes = (int)((need + 127) & ~(size_t)127);
 }
 
 static int validate_cfg(const svtb200_me_config *c)
@@ -115,9 +154,18 @@ static int launch_me(const svtb200_me_config *cfg, const PlaneD src[3], const Pl
     for (int i = 0; i < 3; ++i) { A.src[i] = src[i]; A.ref[0][i] = ref[0][i]; A.ref[1][i] = ref[1][i]; }
     A.results = results; A.best_sad = bs; A.best_mv = bm; A.rc = rc;
     A.cols = (cfg->pic_width + 63) / 64; A.rows = (cfg->pic_height + 63) / 64;
-    A.win_bytes = me_window_bytes(*cfg);
+    me_plan(*cfg, A);
+    // tensor maps over the padded plane buffers (pitch and base multiples of 16: svtb200_pa_picture_create / the host entry point's re-pitched copies)
+    auto rows_of = [](const PlaneD &p) { return (uint32_t)(p.h + 2 * p.oy); };
+    int rc2 = 0;
+    for (int li = 0; li < 2; ++li) {
+        const PlaneD &rF = ref[li][0], &rS = ref[li][2];
+        if (A.hme_fast && rS.buf) { if ((rc2 = make_plane_tensor_map(&A.map_hme[li], rS.buf, (uint32_t)rS.stride, rows_of(rS), (uint32_t)A.hme_p + 16, (uint32_t)A.hme_band + 14))) return rc2; }
+        else if (li == 0) A.hme_fast = 0;
+        if (A.fp_yt) { if ((rc2 = make_plane_tensor_map(&A.map_fp[li], rF.buf, (uint32_t)rF.stride, rows_of(rF), 96, (uint32_t)A.fp_yt + 63))) return rc2; }
+    }
     const bool subpel = cfg->fractional_search_model != 2;
-    size_t smem = me_fixed_smem() + (size_t)A.win_bytes + 96;
+    size_t smem = (size_t)ME_SCRATCH_OFF + (size_t)A.scratch_bytes + 128;
     if (subpel) {   // [84][8] distortions + per list the integer plane with apron and the three half-sample planes
         const int saw = std::min<int>(cfg->search_area_w, 127), sah = std::min<int>(cfg->search_area_h, 127);
         A.sp_fp = win_pitch(saw + 68);
@@ -125,7 +173,7 @@ static int launch_me(const svtb200_me_config *cfg, const PlaneD src[3], const Pl
         A.sp_f_bytes = (A.sp_fp * (sah + 68) + 15) & ~15;
         A.sp_p_bytes = (A.sp_sp * (sah + 68) + 15) & ~15;
         const size_t per_list = (size_t)A.sp_f_bytes + 3 * (size_t)A.sp_p_bytes;
-        A.sp_alias = cfg->num_lists == 2 && per_list <= (size_t)CHUNK * 64 * 2 + (size_t)CHUNK * 21 * 4 + (size_t)A.win_bytes;
+        A.sp_alias = cfg->num_lists == 2 && per_list <= (size_t)A.scratch_bytes;
         smem += 84 * 8 * 4 + (A.sp_alias || cfg->num_lists < 2 ? 1 : 2) * per_list;
     }
     if (smem > 227 * 1024) { set_error("me: this search configuration needs %zu B of shared memory (> 227 KB)", smem); return SVTB200_ERR_UNSUPPORTED; }
@@ -142,7 +190,24 @@ static int launch_me(const svtb200_me_config *cfg, const PlaneD src[3], const Pl
     return SVTB200_OK;
 }
 
+// tensor maps need 16-byte pitches and bases; the picture kernel has no other loader for the source block
+static int check_dev_planes(const svtb200_me_config *cfg, const svtb200_pa_picture *p, const char *what)
+{
+    const svtb200_plane *pl[3] = {&p->full, &p->quarter, &p->sixteenth};
+    for (int k = 0; k < 3; ++k) {
+        const bool used = k == 0 || (k == 1 && cfg->enable_hme && cfg->enable_hme_l1) || (k == 2 && cfg->enable_hme && cfg->enable_hme_l0);
+        if (!used) continue;
+        if (!pl[k]->buf) { set_error("me: plane %d of the %s picture is null", k, what); return SVTB200_ERR_BAD_ARG; }
+        if (((uintptr_t)pl[k]->buf & 15) || (pl[k]->stride & 15)) {
+            set_error("me: plane %d of the %s picture: device planes need a 16-byte-aligned base and pitch (svtb200_pa_picture_create provides both)", k, what);
+            return SVTB200_ERR_UNSUPPORTED;
+        }
+    }
+    return SVTB200_OK;
+}
+
 static size_t plane_bytes(const svtb200_plane &p) { return (size_t)p.stride * (p.height + 2 * p.origin_y); }
+static size_t plane_bytes16(const svtb200_plane &p) { return align_up(p.stride, 16) * (size_t)(p.height + 2 * p.origin_y) + 64; }
 
 // ---- leaf kernels --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT) sad_loop_leaf_kernel(const uint8_t *src, int sstride, const uint8_t *ref, int rstride,
@@ -212,6 +277,7 @@ int svtb200_me_picture_dev(const svtb200_me_config *cfg, const svtb200_pa_pictur
     if (!src || !ref_l0 || !results || (cfg->num_lists == 2 && !ref_l1)) { set_error("me: null picture/result pointer"); return SVTB200_ERR_BAD_ARG; }
     if ((rc = ensure_device())) return rc;
     const svtb200_pa_picture *r1 = ref_l1 ? ref_l1 : ref_l0;
+    if ((rc = check_dev_planes(cfg, src, "source")) || (rc = check_dev_planes(cfg, ref_l0, "list-0 reference")) || (rc = check_dev_planes(cfg, r1, "list-1 reference"))) return rc;
     PlaneD s[3] = {to_dev_plane(src->full, src->full.buf), to_dev_plane(src->quarter, src->quarter.buf), to_dev_plane(src->sixteenth, src->sixteenth.buf)};
     PlaneD r[2][3] = {{to_dev_plane(ref_l0->full, ref_l0->full.buf), to_dev_plane(ref_l0->quarter, ref_l0->quarter.buf), to_dev_plane(ref_l0->sixteenth, ref_l0->sixteenth.buf)},
                       {to_dev_plane(r1->full, r1->full.buf), to_dev_plane(r1->quarter, r1->quarter.buf), to_dev_plane(r1->sixteenth, r1->sixteenth.buf)}};
@@ -235,7 +301,7 @@ int svtb200_me_picture(const svtb200_me_config *cfg, const svtb200_pa_picture *s
     size_t need = 0;
     for (int p = 0; p < 3; ++p) {
         if (!pics[p] || (p == 2 && same_ref)) continue;
-        need += align_up(plane_bytes(pics[p]->full), 256) + align_up(plane_bytes(pics[p]->quarter), 256) + align_up(plane_bytes(pics[p]->sixteenth), 256);
+        need += align_up(plane_bytes16(pics[p]->full), 256) + align_up(plane_bytes16(pics[p]->quarter), 256) + align_up(plane_bytes16(pics[p]->sixteenth), 256);
     }
     const size_t res_bytes = n_lcu * 85 * sizeof(svtb200_me_pu_result), arr_bytes = n_lcu * 170 * 4, rc_bytes = n_lcu * 4;
     need += align_up(res_bytes, 256) + 2 * align_up(arr_bytes, 256) + align_up(rc_bytes, 256) + 1024;
@@ -250,10 +316,13 @@ int svtb200_me_picture(const svtb200_me_config *cfg, const svtb200_pa_picture *s
             void *d = nullptr;
             if (used) {
                 if (!pl[k]->buf) { set_error("me: plane %d of picture %d is null", k, p); return SVTB200_ERR_BAD_ARG; }
-                if ((rc = c->dev_alloc(plane_bytes(*pl[k]), &d))) return rc;
-                SVTB200_CUDA_TRY(cudaMemcpyAsync(d, pl[k]->buf, plane_bytes(*pl[k]), cudaMemcpyHostToDevice, c->stream));
+                // the device copy gets a 16-byte pitch (TMA tensor maps); the geometry (origin, size) stays the caller's
+                const size_t rows = (size_t)pl[k]->height + 2 * pl[k]->origin_y, p16 = align_up(pl[k]->stride, 16);
+                if ((rc = c->dev_alloc(plane_bytes16(*pl[k]), &d))) return rc;
+                SVTB200_CUDA_TRY(cudaMemcpy2DAsync(d, p16, pl[k]->buf, pl[k]->stride, pl[k]->stride, rows, cudaMemcpyHostToDevice, c->stream));
             }
             dp[p][k] = to_dev_plane(*pl[k], (const uint8_t *)d);
+            dp[p][k].stride = (int)align_up(pl[k]->stride, 16);
         }
     }
     if (nl == 1) for (int k = 0; k < 3; ++k) dp[2][k] = dp[1][k];

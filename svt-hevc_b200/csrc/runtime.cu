@@ -11,8 +11,9 @@ namespace svtb200 {
 std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_device{-1};          // -1: not initialised, -2: no device
 static std::mutex g_init_mu;
+// the last error is per calling thread (the boundary promises lock-free concurrent callers: 8*u ME threads + EncDec threads);
+// svtb200_last_error() returns the calling thread's own message
 static thread_local char t_err[512] = "";
-static char g_err[512] = "";
 
 void set_error(const char *fmt, ...)
 {
@@ -20,7 +21,36 @@ void set_error(const char *fmt, ...)
     va_start(ap, fmt);
     vsnprintf(t_err, sizeof t_err, fmt, ap);
     va_end(ap);
-    strncpy(g_err, t_err, sizeof g_err - 1);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_plane_tensor_map(CUtensorMap *out, const void *buf, uint32_t pitch, uint32_t rows, uint32_t box_w, uint32_t box_h)
+{
+    static std::atomic<EncodeTiledFn> g_fn{nullptr};
+    EncodeTiledFn fn = g_fn.load(std::memory_order_acquire);
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return SVTB200_ERR_CUDA;
+        }
+        fn = (EncodeTiledFn)p;
+        g_fn.store(fn, std::memory_order_release);
+    }
+    if (((uintptr_t)buf & 15) || (pitch & 15) || (box_w & 15) || box_w == 0 || box_w > 256 || box_h == 0 || box_h > 256) {
+        set_error("tensor map: buffer %p pitch %u box %ux%u violates the 16-byte / 256-element rules", buf, pitch, box_w, box_h);
+        return SVTB200_ERR_UNSUPPORTED;
+    }
+    const cuuint64_t dims[2] = {pitch, rows}, strides[1] = {pitch};
+    const cuuint32_t box[2] = {box_w, box_h}, es[2] = {1, 1};
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(buf), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for pitch %u rows %u box %ux%u", (int)r, pitch, rows, box_w, box_h); return SVTB200_ERR_CUDA; }
+    return SVTB200_OK;
 }
 
 int ensure_device()
@@ -45,8 +75,8 @@ int ensure_device()
         }
     }
     if (d < 0) { set_error("no CUDA device visible: libsvthevc_b200 has no CPU fallback"); return SVTB200_ERR_NO_DEVICE; }
-    static thread_local bool t_set = false;
-    if (!t_set) { if (cudaSetDevice(d) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", d); return SVTB200_ERR_CUDA; } t_set = true; }
+    static thread_local int t_dev = -1;          // the device this thread last selected (svtb200_init may change the ordinal)
+    if (t_dev != d) { if (cudaSetDevice(d) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", d); return SVTB200_ERR_CUDA; } t_dev = d; }
     return SVTB200_OK;
 }
 
@@ -101,9 +131,19 @@ int ThreadCtx::pin_alloc(size_t bytes, void **out)
     return SVTB200_OK;
 }
 
+void ThreadCtx::release()
+{
+    if (stream) cudaStreamSynchronize(stream);
+    if (dev) { cudaFree(dev); dev = nullptr; dev_cap = 0; }
+    if (pin) { cudaFreeHost(pin); pin = nullptr; pin_cap = 0; }
+    if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+    cudaGetLastError();      // a worker thread may exit after the primary context is gone: nothing to report
+}
+ThreadCtx::~ThreadCtx() { release(); }
+
 ThreadCtx *tls_ctx()
 {
-    static thread_local ThreadCtx ctx;
+    static thread_local ThreadCtx ctx;      // destroyed (stream, arenas released) when the calling thread exits
     return &ctx;
 }
 
@@ -133,15 +173,11 @@ int svtb200_init(int device_ordinal)
 
 void svtb200_shutdown(void)
 {
-    ThreadCtx *c = tls_ctx();
-    if (c->stream) { cudaStreamSynchronize(c->stream); }
-    if (c->dev) { cudaFree(c->dev); c->dev = nullptr; c->dev_cap = 0; }
-    if (c->pin) { cudaFreeHost(c->pin); c->pin = nullptr; c->pin_cap = 0; }
-    if (c->stream) { cudaStreamDestroy(c->stream); c->stream = nullptr; }
+    tls_ctx()->release();      // the calling thread's context; every other thread's is released when that thread exits
 }
 
 const char *svtb200_version(void) { return "svt-hevc_b200 0.1 (sm_100a)"; }
-const char *svtb200_last_error(void) { return g_err; }
+const char *svtb200_last_error(void) { return t_err; }
 uint64_t svtb200_launch_count(void) { return g_launches.load(); }
 
 }  // extern "C"
