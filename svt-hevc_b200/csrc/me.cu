@@ -114,18 +114,18 @@ static void me_plan(const svtb200_me_config &c, MeArgs &A)
         if (w > 0 && h > 0 && P + 16 <= 256 && band + 14 <= 256 && (size_t)w * h <= 65536) {
             A.hme_fast = 1; A.hme_p = P; A.hme_band = band;
             A.hme_cs = (P * (band + 14) + 127) & ~127;
-            need = std::max(need, (size_t)(((P + 16) * (band + 14) + 127) & ~127) + (size_t)4 * A.hme_cs + 64);      // raw TMA box + four phase copies
+            need = std::max(need, (size_t)4 * A.hme_cs + 64);      // four phase copies (the raw TMA box is parked on copies 2 / 3)
         }
     }
     A.fp_yt = 0;
     const int saw = std::min<int>(c.search_area_w, 127), sah = std::min<int>(c.search_area_h, 127);
     if ((saw == 8 && sah == 7) || (saw == 16 && sah == 9)) {
         A.fp_yt = sah; A.fp_nxh = saw / 8;
-        int cs = (saw == 8 ? 72 : 80) * (sah + 63);
+        int cs = 80 * (sah + 63);
         cs = (cs + 15) & ~15;
         while ((cs & 127) != 64) cs += 16;       // phases 0 / 1 (and 2 / 3) of a half warp land in different halves of the 32 banks
         A.fp_cs = cs;
-        need = std::max(need, (size_t)((96 * (sah + 63) + 127) & ~127) + (size_t)4 * cs + (size_t)(88 + 12 * saw * sah) * 4);
+        need = std::max(need, (size_t)4 * cs + (size_t)(88 + 12 * saw * sah) * 4);
     }
     A.scratch_bytes = (int)((need + 127) & ~(size_t)127);
 }

@@ -1,10 +1,10 @@
 #!/bin/bash
 # Runs ON the GPU box (via gpurun): one ncu --set full pass over the first frames of bench.py, condensed to text there
 # (the .ncu-rep of several kernels exceeds what gpurun copies back).  usage: tools/prof_box.sh <tag> [launch-count]
-tag=${1:-prof}; cnt=${2:-6}
+tag=${1:-prof}; cnt=${2:-6}; kreg=${KREG:-"me_picture|tq_batch|mc_batch|sao_stats|ois_picture"}; skip=${SKIP:-16}
 mkdir -p gpurun_out
 timeout 500 ncu --set full --clock-control none --import-source on \
-  --kernel-name regex:"me_picture|tq_batch|mc_batch|sao_stats|ois_picture" --launch-skip 16 --launch-count $cnt \
+  --kernel-name regex:"$kreg" --launch-skip $skip --launch-count $cnt \
   -o /tmp/$tag -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench.log 2>&1
 python tools/ncu_summary.py /tmp/$tag.ncu-rep > gpurun_out/${tag}_summary.txt 2>&1
 python tools/ncu_lines.py /tmp/$tag.ncu-rep "me_picture:k12817me_picture_kernelILb0" me.cu 70 > gpurun_out/${tag}_lines_me0.txt 2>&1
