@@ -37,6 +37,7 @@ struct MeArgs {
     uint32_t *best_sad, *best_mv, *rc;
     int cols, rows;
     int scratch_bytes;    // bytes of the search-scratch union in dynamic shared memory
+    int sq_bytes;         // bytes of the quarter-resolution source block behind it (HME level 1 only)
     // fast paths (me_kernels.inc): HME level 0 on byte-phase copies, 85-PU full-pel search of 8 x 7 / 16 x 9 areas
     int hme_fast, hme_p, hme_band, hme_cs;      // window pitch (= TMA box width), search rows per band, bytes between phase copies
     int fp_yt, fp_nxh, fp_cs;                   // full-pel: search rows (7 / 9, 0 = generic path only), search width / 8, bytes between phase copies
@@ -44,7 +45,7 @@ struct MeArgs {
     CUtensorMap map_fp[2];                      // per list: 96 x (fp_yt + 63) box of the full-resolution reference plane
 };
 
-constexpr int ME_SCRATCH_OFF = 8320;            // fixed part (8232) + mbarrier, rounded up to the 128-byte TMA destination alignment
+constexpr int ME_SCRATCH_OFF = 6272;            // fixed part (6184) + mbarrier, rounded up to the 128-byte TMA destination alignment
 
 }  // namespace svtb200
 
@@ -59,7 +60,7 @@ namespace svtb200 {
 #undef ME_MIN_CTAS
 #define ME_NS k128
 #define ME_NT 128
-#define ME_MIN_CTAS 6
+#define ME_MIN_CTAS 7
 namespace svtb200 {
 #include "me_kernels.inc"
 }
@@ -121,7 +122,7 @@ static void me_plan(const svtb200_me_config &c, MeArgs &A)
     const int saw = std::min<int>(c.search_area_w, 127), sah = std::min<int>(c.search_area_h, 127);
     if ((saw == 8 && sah == 7) || (saw == 16 && sah == 9)) {
         A.fp_yt = sah; A.fp_nxh = saw / 8;
-        int cs = 80 * (sah + 63);
+        int cs = (saw == 8 ? 72 : 80) * (sah + 63);
         cs = (cs + 15) & ~15;
         while ((cs & 127) != 64) cs += 16;       // phases 0 / 1 (and 2 / 3) of a half warp land in different halves of the 32 banks
         A.fp_cs = cs;
@@ -165,7 +166,8 @@ static int launch_me(const svtb200_me_config *cfg, const PlaneD src[3], const Pl
         if (A.fp_yt) { if ((rc2 = make_plane_tensor_map(&A.map_fp[li], rF.buf, (uint32_t)rF.stride, rows_of(rF), 96, (uint32_t)A.fp_yt + 63))) return rc2; }
     }
     const bool subpel = cfg->fractional_search_model != 2;
-    size_t smem = (size_t)ME_SCRATCH_OFF + (size_t)A.scratch_bytes + 128;
+    A.sq_bytes = (cfg->enable_hme && cfg->enable_hme_l1) ? 2048 : 0;
+    size_t smem = (size_t)ME_SCRATCH_OFF + (size_t)A.scratch_bytes + (size_t)A.sq_bytes + 128;
     if (subpel) {   // [84][8] distortions + per list the integer plane with apron and the three half-sample planes
         const int saw = std::min<int>(cfg->search_area_w, 127), sah = std::min<int>(cfg->search_area_h, 127);
         A.sp_fp = win_pitch(saw + 68);
