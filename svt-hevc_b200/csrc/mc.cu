@@ -40,6 +40,10 @@ struct McArgs {
     uint8_t *dst[3];
     int dstride[3];
     int dox, doy;
+    // TMA path of the 8-bit batch kernel (n_refs <= 4, every plane 16-byte aligned with a 16-byte pitch): per reference a 48 x 32 box of the luma
+    // plane and 48 x 19 boxes of Cb / Cr
+    int tma;
+    CUtensorMap maps[4][3];
 };
 
 __constant__ int8_t c_luma_taps[4][8] = {{0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1}};
@@ -87,7 +91,7 @@ struct McClass {          // the units of one plane class (luma: np = 1; chroma:
     bool interp;
 };
 
-template <int TAPS, bool HBD>
+template <int TAPS, bool HBD, int NTH = MC_NT>
 __device__ __forceinline__ void mc_stage_load(const McClass &c, int nl, uint8_t *s_win, int win_unit, int *s_a)
 {
     constexpr int HALF = TAPS / 2 - 1, BPS = HBD ? 2 : 1;
@@ -97,16 +101,17 @@ __device__ __forceinline__ void mc_stage_load(const McClass &c, int nl, uint8_t 
 #pragma unroll
         for (int l = 0; l < 2; ++l) {
             if (p >= c.np || l >= nl) continue;
-            const int a = load_window_t<MC_NT>(s_win + (p * 2 + l) * win_unit, wp, c.u[p][l].ref - (HALF * c.u[p][l].rstride + HALF) * BPS,
+            const int a = load_window_t<NTH>(s_win + (p * 2 + l) * win_unit, wp, c.u[p][l].ref - (HALF * c.u[p][l].rstride + HALF) * BPS,
                                                c.u[p][l].rstride * BPS, wbytes, wrows);
             if (threadIdx.x == 0) s_a[p * 2 + l] = a;
         }
 }
 
 // H pass of every unit of the class: s_tmp[unit][r][x], r in [0, wrows), pitch tw (s16)
-template <int TAPS, bool HBD>
+template <int TAPS, bool HBD, int NTH = MC_NT>
 __device__ __forceinline__ void mc_stage_h(const McClass &c, int nl, const uint8_t *s_win, int win_unit, const int *s_a, int16_t *s_tmp, int tmp_unit)
 {
+    const int tid = NTH == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x;      // NTH == 32: the warp works alone
     constexpr int BPS = HBD ? 2 : 1;
     const int wbytes = (c.tw + TAPS - 1) * BPS, wrows = c.th + TAPS - 1, wp = win_pitch(wbytes), tw = c.tw;
     const int ipr = HBD ? tw >> 1 : tw >> 2, per_unit = wrows * ipr, total = c.np * nl * per_unit;
@@ -117,7 +122,7 @@ __device__ __forceinline__ void mc_stage_h(const McClass &c, int nl, const uint8
         const int8_t *tx = TAPS == 8 ? c_luma_taps[c.fx[l] & 3] : c_chroma_taps[c.fx[l] & 7];
         kx0[l] = pack4(tx); kx1[l] = TAPS == 8 ? pack4(tx + 4) : 0u;
     }
-    for (int i = threadIdx.x; i < total; i += MC_NT) {
+    for (int i = tid; i < total; i += NTH) {
         const int rr = udiv(i, d_ipr), g = i - rr * ipr;                                                  // row over all units, item in the row
         const int uu = (rr >= wrows) + (rr >= 2 * wrows) + (rr >= 3 * wrows), r = rr - uu * wrows;     // <= 4 units per class
         const int l = nl == 2 ? (uu & 1) : 0, slot = (nl == 2 ? (uu >> 1) : uu) * 2 + l;
@@ -172,9 +177,10 @@ __device__ __forceinline__ void mc_stage_h(const McClass &c, int nl, const uint8
 // V pass: a 2x2 output quad per thread with DP2A on PRMT-built vertical s16 pairs, both lists, then the final rounding:
 //   uni 8-bit (S2 + 2048) >> 12, bi 8-bit BiPredClipping (C_DEFAULT/EbMcp_C.c:21; the -8192 biases of the reference's raw buffers cancel
 //   against Offset5): ((S2_0 >> 6) + (S2_1 >> 6) + 64) >> 7;  16-bit: (S2 + 524800) >> 10 / BiPredClipping16bit :3265 (l0 + l1 + 16400) >> 5
-template <int TAPS, bool HBD>
+template <int TAPS, bool HBD, int NTH = MC_NT>
 __device__ __forceinline__ void mc_stage_v(const McClass &c, int nl, const int16_t *s_tmp, int tmp_unit)
 {
+    const int tid = NTH == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
     const int tw = c.tw, qpr = tw >> 1, per_plane = (c.th >> 1) * qpr, total = c.np * per_plane, p4 = tw >> 1;
     const SmallDiv d_qpr = mk_div(qpr);
     uint32_t ky0[2], ky1[2];
@@ -183,7 +189,7 @@ __device__ __forceinline__ void mc_stage_v(const McClass &c, int nl, const int16
         const int8_t *ty = TAPS == 8 ? c_luma_taps[c.fy[l] & 3] : c_chroma_taps[c.fy[l] & 7];
         ky0[l] = pack4(ty); ky1[l] = TAPS == 8 ? pack4(ty + 4) : 0u;
     }
-    for (int i = threadIdx.x; i < total; i += MC_NT) {
+    for (int i = tid; i < total; i += NTH) {
         const int p = i >= per_plane ? 1 : 0, j = i - p * per_plane;
         const int qy = udiv(j, d_qpr), x = (j - qy * qpr) * 2, y = qy * 2;
         int acc[2][2][2];   // [list][row][col]
@@ -238,12 +244,13 @@ __device__ __forceinline__ void mc_stage_v(const McClass &c, int nl, const int16
 // Integer motion vectors on every used list of the class (every layer-1..3 picture of M10 runs integer-pel ME): LumaInterpolationCopy
 // (C_DEFAULT/EbMcp_C.c:221) / BiPredClippingOnTheFly (Codec/EbMcp.c:603): ((p0 << 6) + (p1 << 6) + 64) >> 7 == (p0 + p1 + 1) >> 1;
 // 16-bit: uniPredCopy16bit (C_DEFAULT/EbMcp_C.c:3827) / BiPredClippingOnTheFly16bit (Codec/EbMcp.c:847).  No shared memory, no barrier.
-template <bool HBD>
+template <bool HBD, int NTH = MC_NT>
 __device__ __forceinline__ void mc_copy_scalar(const McClass &c, int nl)
 {
+    const int tid = NTH == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
     const int tw = c.tw, ipr = HBD ? tw >> 1 : tw >> 2, per_plane = c.th * ipr, total = c.np * per_plane;
     const SmallDiv d_ipr = mk_div(ipr);
-    for (int i = threadIdx.x; i < total; i += MC_NT) {
+    for (int i = tid; i < total; i += NTH) {
         const int p = i >= per_plane ? 1 : 0, j = i - p * per_plane;
         const int y = udiv(j, d_ipr), g = j - y * ipr;
         const uint8_t *r0 = p ? c.u[1][0].ref : c.u[0][0].ref, *r1 = p ? c.u[1][1].ref : c.u[0][1].ref;
@@ -299,12 +306,14 @@ __device__ __forceinline__ void ld_bytes_vec(const uint8_t *p, uint32_t (&o)[VW]
 }
 
 // the same copy / rounded average with 8- or 16-byte items (row bytes, destination pointers and pitches multiples of 4 * VW)
-template <bool HBD, int VW>
+template <bool HBD, int VW, int NTH = MC_NT>
 __device__ __forceinline__ void mc_copy_vec(const McClass &c, int nl)
 {
+    const int tid = NTH == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
     constexpr int BPS = HBD ? 2 : 1, VB = 4 * VW;
     const int ipr = (c.tw * BPS) / VB, lg = 31 - __clz(ipr), per_plane = c.th * ipr, total = c.np * per_plane;   // ipr is a power of two here
-    for (int i = threadIdx.x; i < total; i += MC_NT) {
+#pragma unroll 2
+    for (int i = tid; i < total; i += NTH) {
         const int p = i >= per_plane ? 1 : 0, j = i - p * per_plane;
         const int y = j >> lg, g = j & (ipr - 1);
         const uint8_t *r0 = p ? c.u[1][0].ref : c.u[0][0].ref, *r1 = p ? c.u[1][1].ref : c.u[0][1].ref;
@@ -325,7 +334,7 @@ __device__ __forceinline__ void mc_copy_vec(const McClass &c, int nl)
     }
 }
 
-template <bool HBD>
+template <bool HBD, int NTH = MC_NT>
 __device__ __forceinline__ void mc_copy(const McClass &c, int nl)
 {
     constexpr int BPS = HBD ? 2 : 1;
@@ -333,9 +342,9 @@ __device__ __forceinline__ void mc_copy(const McClass &c, int nl)
     uintptr_t al = (uintptr_t)c.out[0] | (uintptr_t)(c.ostride[0] * BPS) | (uintptr_t)rb;
     if (c.np == 2) al |= (uintptr_t)c.out[1] | (uintptr_t)(c.ostride[1] * BPS);
     const bool pow2 = (rb & (rb - 1)) == 0;
-    if (pow2 && (al & 15) == 0) mc_copy_vec<HBD, 4>(c, nl);
-    else if (pow2 && (al & 7) == 0) mc_copy_vec<HBD, 2>(c, nl);
-    else mc_copy_scalar<HBD>(c, nl);
+    if (pow2 && (al & 15) == 0) mc_copy_vec<HBD, 4, NTH>(c, nl);
+    else if (pow2 && (al & 7) == 0) mc_copy_vec<HBD, 2, NTH>(c, nl);
+    else mc_copy_scalar<HBD, NTH>(c, nl);
 }
 
 __device__ __forceinline__ int clampi(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -422,6 +431,225 @@ __global__ void __launch_bounds__(MC_NT, 1024 / MC_NT) mc_batch_kernel(const __g
         }
 }
 
+// ---- round-2 batch kernel (8-bit): ONE WARP PER PU, eight PUs per CTA -------------------------------------------------------------------------------
+// At M10 every layer-1..3 picture has integer-sample luma vectors, so a PU is a luma copy (or average) plus chroma that is half-sample on the PUs whose
+// vector is odd.  That work has no block-wide step: a warp decodes its own job, issues the luma copy loads (16-byte items, no shared memory), filters its
+// chroma rows straight from global memory into a per-warp s16 tile (H pass) and finishes them with the V pass of the staged path -- no block barrier, the
+// whole picture in flight in about two waves of 256-thread CTAs.  PUs with fractional LUMA vectors (base-layer pictures) are left to phase 2, where the
+// whole CTA runs the staged 8-tap path on them one after the other.
+constexpr int MC8_NT = 256, MC8_JOBS = MC8_NT / 32;
+
+// H pass of the chroma class without a staging step: work item = one row of one unit (plane x list): tw + 3 bytes -> tw s16 outputs (tw in {4, 8, 16}).
+// SMEM = false: rows straight from global memory;  SMEM = true: rows of the TMA-fetched 48-byte-pitch tiles (tile[slot], byte misalignment am[l]).
+template <bool SMEM>
+__device__ __forceinline__ void mc_chroma_h_rows(const McClass &c, int nl, int16_t *s_tmp, int tmp_unit, const uint8_t *tiles, int tile_bytes, const int (&am)[2])
+{
+    const int lane = threadIdx.x & 31;
+    const int tw = c.tw, wrows = c.th + 3, units = c.np * nl, total = units * wrows;
+    const SmallDiv d_rows = mk_div(wrows);
+    for (int i = lane; i < total; i += 32) {
+        const int uu = udiv(i, d_rows), r = i - uu * wrows;
+        const int l = nl == 2 ? (uu & 1) : 0, p = nl == 2 ? (uu >> 1) : uu, slot = p * 2 + l;
+        const uint32_t k0 = pack4(c_chroma_taps[(l ? c.fx[1] : c.fx[0]) & 7]);
+        uint32_t raw[6], sh;
+        if (SMEM) {
+            const int a = l ? am[1] : am[0];
+            const uint32_t *w = (const uint32_t *)(tiles + slot * tile_bytes + r * 48) + (a >> 2);
+            sh = (uint32_t)(a & 3) * 8;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) raw[k] = (4 * k < tw + 3 + 3) ? w[k] : 0u;
+        } else {
+            const uint8_t *uref = p ? (l ? c.u[1][1].ref : c.u[1][0].ref) : (l ? c.u[0][1].ref : c.u[0][0].ref);
+            const int ustride = p ? (l ? c.u[1][1].rstride : c.u[1][0].rstride) : (l ? c.u[0][1].rstride : c.u[0][0].rstride);
+            const uintptr_t ga = (uintptr_t)(uref + (ptrdiff_t)(r - 1) * ustride - 1);
+            const uint32_t *w = (const uint32_t *)(ga & ~(uintptr_t)3);
+            sh = (uint32_t)(ga & 3) * 8;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) raw[k] = (4 * k < tw + 3 + 3) ? __ldg(w + k) : 0u;          // tw + 3 bytes from byte offset <= 3
+        }
+        uint32_t v[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) v[k] = __funnelshift_r(raw[k], raw[k + 1], sh);                  // bytes 4k .. 4k + 3 of the row
+        uint32_t *t = (uint32_t *)(s_tmp + slot * tmp_unit + r * tw);
+#pragma unroll
+        for (int x = 0; x < 16; x += 2) {
+            if (x >= tw) break;
+            const uint32_t b0 = (x & 3) ? __funnelshift_r(v[x >> 2], v[(x >> 2) + 1], 8 * (x & 3)) : v[x >> 2];
+            const uint32_t b1 = __funnelshift_r(v[(x + 1) >> 2], v[((x + 1) >> 2) + 1], 8 * ((x + 1) & 3));
+            t[x >> 1] = (uint32_t)(uint16_t)dp4a_us(b0, k0, 0) | ((uint32_t)(uint16_t)dp4a_us(b1, k0, 0) << 16);
+        }
+    }
+}
+
+// copy / rounded average of np planes out of TMA-fetched tiles (pitch 48): plane p, list l at tiles + (p * 2 + l) * tile_bytes, sample (x, y) of the block at
+// tile row y + row0, byte am[l] + col0 + x.  8-byte items (block widths are multiples of 8 for luma; chroma widths 4 take the 4-byte form).
+__device__ __forceinline__ void mc_copy_tiles(const McClass &c, int nl, const uint8_t *tiles, int tile_bytes, const int (&am)[2], int row0, int col0)
+{
+    const int lane = threadIdx.x & 31;
+    const int tw = c.tw, th = c.th;
+    const bool wide = (tw & 7) == 0 && ((((uintptr_t)c.out[0] | (uintptr_t)c.ostride[0]) | (c.np == 2 ? ((uintptr_t)c.out[1] | (uintptr_t)c.ostride[1]) : 0)) & 7) == 0;
+    const int ib = wide ? 8 : 4, ipr = tw / ib, lg = 31 - __clz(ipr), per_plane = th * ipr, total = c.np * per_plane;
+#pragma unroll 2
+    for (int i = lane; i < total; i += 32) {
+        const int p = i >= per_plane ? 1 : 0, j = i - p * per_plane;
+        const int y = j >> lg, g = j & (ipr - 1);
+        uint32_t v[2][2];
+#pragma unroll
+        for (int l = 0; l < 2; ++l) {
+            if (l >= nl) { v[l][0] = v[l][1] = 0; continue; }
+            const int o = (l ? am[1] : am[0]) + col0 + g * ib;
+            const uint32_t *w = (const uint32_t *)(tiles + (p * 2 + l) * tile_bytes + (y + row0) * 48) + (o >> 2);
+            const uint32_t sh = (uint32_t)(o & 3) * 8;
+            const uint32_t w0 = w[0], w1 = w[1], w2 = wide ? w[2] : 0u;
+            v[l][0] = __funnelshift_r(w0, w1, sh);
+            v[l][1] = __funnelshift_r(w1, w2, sh);
+        }
+        if (nl == 2) { v[0][0] = __vavgu4(v[0][0], v[1][0]); v[0][1] = __vavgu4(v[0][1], v[1][1]); }
+        uint8_t *o = (p ? c.out[1] : c.out[0]) + (size_t)y * (p ? c.ostride[1] : c.ostride[0]) + g * ib;
+        if (wide) *(uint2 *)o = make_uint2(v[0][0], v[0][1]);
+        else if (((uintptr_t)o & 3) == 0) *(uint32_t *)o = v[0][0];
+        else { o[0] = (uint8_t)v[0][0]; o[1] = (uint8_t)(v[0][0] >> 8); o[2] = (uint8_t)(v[0][0] >> 16); o[3] = (uint8_t)(v[0][0] >> 24); }
+    }
+}
+
+// TMA = true: the windows of a PU arrive by cp.async.bulk.tensor (lane 0 issues up to six boxes on the warp's mbarrier, nothing else of the PU touches
+// global memory for reading): one round trip per PU, the address generation is the copy engine's.  Per warp: two 48 x 32 luma tiles (reused by the
+// chroma H-pass output) and four 48 x 19 chroma tiles.
+constexpr int MC8_LT = 48 * 32, MC8_CT = 1024;        // tile bytes: luma 1536, chroma 48 * 19 = 912 -> 1024 (TMA destinations are 128-byte aligned)
+template <bool TMA>
+__global__ void __launch_bounds__(MC8_NT, TMA ? 3 : 4) mc_batch8_kernel(const __grid_constant__ McArgs A)
+{
+    using G = McSmem<false>;
+    extern __shared__ __align__(128) uint8_t mc_dyn[];
+    // layout: [TMA: per warp 2 luma + 4 chroma tiles | else per warp 4 chroma s16 tiles] [staged path: windows, s16 rows]
+    constexpr int PER_WARP = TMA ? 2 * MC8_LT + 4 * MC8_CT : 4 * G::TMP_C * 2;
+    uint8_t *s_warp = mc_dyn + (threadIdx.x >> 5) * PER_WARP;
+    uint8_t *s_win = mc_dyn + MC8_JOBS * PER_WARP;
+    int16_t *s_tmp = (int16_t *)(s_win + 2 * G::WIN_L);
+    __shared__ int s_a[4];
+    __shared__ int s_luma_frac[MC8_JOBS];
+    __shared__ __align__(8) uint64_t s_bar[MC8_JOBS];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t parity = 0;
+    if (TMA) {
+        if (lane == 0) mbar_init(&s_bar[wid], 1);
+        __syncwarp();
+    }
+    for (int phase = 0; phase < 2; ++phase) {
+        // phase 0: every warp its own job (luma copy, chroma);  phase 1: the CTA walks the jobs whose luma needs the staged 8-tap path
+        int any = 0;
+        if (phase == 1) {
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < MC8_JOBS; ++k) any |= s_luma_frac[k];
+            if (!any) return;
+        }
+        for (int jj = 0; jj < (phase ? MC8_JOBS : 1); ++jj) {
+            const int slot_j = phase ? jj : wid, job = blockIdx.x * MC8_JOBS + slot_j;
+            if (phase == 1 && !s_luma_frac[jj]) continue;
+            if (job >= A.n_jobs) { if (phase == 0 && lane == 0) s_luma_frac[wid] = 0; continue; }
+            const svtb200_mc_job q = A.jobs[job];
+            const bool bi = q.dir == 2;
+            const int nl = bi ? 2 : 1;
+            int px[2], py[2], rix[2];
+            const YuvD *r[2];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int l = bi ? s : (q.dir == 1 ? 1 : 0);
+                const int ri = l ? q.ref_idx[1] : q.ref_idx[0], mvx = l ? q.mv[1][0] : q.mv[0][0], mvy = l ? q.mv[1][1] : q.mv[0][1];
+                rix[s] = min(ri, A.n_refs - 1);
+                r[s] = &A.refs[rix[s]];   // param space
+                px[s] = (uint16_t)clampi((r[s]->ox - 71) << 2, (r[s]->w + r[s]->ox + 7) << 2, ((q.x + r[s]->ox) << 2) + mvx);
+                py[s] = (uint16_t)clampi((r[s]->oy - 71) << 2, (r[s]->h + r[s]->oy + 7) << 2, ((q.y + r[s]->oy) << 2) + mvy);
+            }
+            int lfrac = 0;
+            for (int ty0 = 0; ty0 < q.h; ty0 += TILE)
+                for (int tx0 = 0; tx0 < q.w; tx0 += TILE) {
+                    McClass L, K;   // luma, chroma
+                    L.np = 1; L.tw = min(TILE, q.w - tx0); L.th = min(TILE, q.h - ty0);
+                    K.np = 2; K.tw = L.tw >> 1; K.th = L.th >> 1;
+                    L.out[0] = L.out[1] = A.dst[0] + ((size_t)(A.doy + q.y + ty0) * A.dstride[0] + A.dox + q.x + tx0);
+                    L.ostride[0] = L.ostride[1] = A.dstride[0];
+                    const size_t cidx = (((size_t)(A.doy + q.y) * A.dstride[1]) >> 1) + ((A.dox + q.x) >> 1) + (size_t)(ty0 >> 1) * A.dstride[1] + (tx0 >> 1);
+                    K.out[0] = A.dst[1] + cidx; K.out[1] = A.dst[2] + cidx;
+                    K.ostride[0] = A.dstride[1]; K.ostride[1] = A.dstride[2];
+                    int lf = 0, kf = 0;
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+                        L.fx[s] = px[s] & 3; L.fy[s] = py[s] & 3; K.fx[s] = px[s] & 7; K.fy[s] = py[s] & 7;
+                        if (s < nl) { lf |= L.fx[s] | L.fy[s]; kf |= K.fx[s] | K.fy[s]; }
+                        L.u[0][s].ref = r[s]->p[0] + ((size_t)((py[s] >> 2) + ty0) * r[s]->stride[0] + (px[s] >> 2) + tx0);
+                        L.u[0][s].rstride = r[s]->stride[0];
+                        L.u[1][s] = L.u[0][s];
+#pragma unroll
+                        for (int pl = 1; pl < 3; ++pl) {
+                            K.u[pl - 1][s].ref = r[s]->p[pl] + ((size_t)((py[s] >> 3) + (ty0 >> 1)) * r[s]->stride[pl] + (px[s] >> 3) + (tx0 >> 1));
+                            K.u[pl - 1][s].rstride = r[s]->stride[pl];
+                        }
+                    }
+                    L.interp = lf != 0; K.interp = kf != 0;
+                    lfrac |= lf;
+                    if (phase == 0) {
+                        if (TMA) {
+                            uint8_t *s_lt = s_warp, *s_ct = s_warp + 2 * MC8_LT;
+                            int16_t *s_ctmp = (int16_t *)s_warp;                  // the chroma H-pass rows overlay the luma tiles once the luma copy is done
+                            int al[2], ac[2];
+#pragma unroll
+                            for (int s = 0; s < 2; ++s) { al[s] = ((px[s] >> 2) + tx0) & 15; ac[s] = ((px[s] >> 3) + (tx0 >> 1) - 1) & 15; }
+                            __syncwarp();                                      // every lane is done with the previous tile's shared memory
+                            if (lane == 0) {
+                                fence_proxy_async();
+                                mbar_expect_tx(&s_bar[wid], (uint32_t)(nl * ((L.interp ? 0 : 48 * 32) + 2 * 48 * 19)));
+#pragma unroll
+                                for (int s = 0; s < 2; ++s) {
+                                    if (s >= nl) continue;
+                                    const int lx = (px[s] >> 2) + tx0, ly = (py[s] >> 2) + ty0, cx = (px[s] >> 3) + (tx0 >> 1) - 1, cy = (py[s] >> 3) + (ty0 >> 1) - 1;
+                                    if (!L.interp) tma_load_2d(s_lt + s * MC8_LT, &A.maps[rix[s]][0], lx & ~15, ly, &s_bar[wid]);
+                                    tma_load_2d(s_ct + (0 * 2 + s) * MC8_CT, &A.maps[rix[s]][1], cx & ~15, cy, &s_bar[wid]);
+                                    tma_load_2d(s_ct + (1 * 2 + s) * MC8_CT, &A.maps[rix[s]][2], cx & ~15, cy, &s_bar[wid]);
+                                }
+                            }
+                            mbar_wait(&s_bar[wid], parity);
+                            parity ^= 1u;
+                            if (!L.interp) mc_copy_tiles(L, nl, s_lt, MC8_LT, al, 0, 0);
+                            if (!K.interp) mc_copy_tiles(K, nl, s_ct, MC8_CT, ac, 1, 1);
+                            else {
+                                __syncwarp();                                  // the luma copy has read its tiles
+                                mc_chroma_h_rows<true>(K, nl, s_ctmp, G::TMP_C, s_ct, MC8_CT, ac);
+                                __syncwarp();
+                                mc_stage_v<4, false, 32>(K, nl, s_ctmp, G::TMP_C);
+                            }
+                        } else {
+                            int16_t *s_ctmp = (int16_t *)s_warp;
+                            const int dummy[2] = {0, 0};
+                            if (!L.interp) mc_copy<false, 32>(L, nl);
+                            if (!K.interp) mc_copy<false, 32>(K, nl);
+                            else {
+                                mc_chroma_h_rows<false>(K, nl, s_ctmp, G::TMP_C, nullptr, 0, dummy);
+                                __syncwarp();
+                                mc_stage_v<4, false, 32>(K, nl, s_ctmp, G::TMP_C);
+                                __syncwarp();      // the next tile reuses the per-warp tile
+                            }
+                        }
+                    } else if (L.interp) {
+                        mc_stage_load<8, false, MC8_NT>(L, nl, s_win, G::WIN_L, s_a);
+                        __syncthreads();
+                        mc_stage_h<8, false, MC8_NT>(L, nl, s_win, G::WIN_L, s_a, s_tmp, G::TMP_L);
+                        __syncthreads();
+                        mc_stage_v<8, false, MC8_NT>(L, nl, s_tmp, G::TMP_L);
+                        __syncthreads();
+                    }
+                }
+            if (phase == 0 && lane == 0) s_luma_frac[wid] = lfrac != 0;
+        }
+    }
+}
+static size_t mc8_smem(bool tma)
+{
+    using G = McSmem<false>;
+    return (size_t)MC8_JOBS * (tma ? 2 * MC8_LT + 4 * MC8_CT : 4 * G::TMP_C * 2) + 2 * G::WIN_L + 2 * G::TMP_L * 2 + 128;
+}
+
 // leaf: one block (w x h, multiples of 4 x 2) through the same three stages, one plane, one or two lists
 template <int TAPS>
 __global__ void __launch_bounds__(MC_NT) mc_leaf_kernel(const uint8_t *r0, int s0, int f0x, int f0y, const uint8_t *r1, int s1, int f1x, int f1y,
@@ -481,7 +709,29 @@ static int launch_mc(const YuvD *h_refs, int n_refs, const svtb200_mc_job *d_job
     A.dstride[0] = (int)dst.y.stride; A.dstride[1] = (int)dst.cb.stride; A.dstride[2] = (int)dst.cr.stride;
     A.dox = dst.y.origin_x; A.doy = dst.y.origin_y;
     if (n_jobs == 0) return SVTB200_OK;
-    if (hbd) mc_batch_kernel<true><<<n_jobs, MC_NT, 0, st>>>(A); else mc_batch_kernel<false><<<n_jobs, MC_NT, 0, st>>>(A);
+    if (hbd) mc_batch_kernel<true><<<n_jobs, MC_NT, 0, st>>>(A);
+    else {
+        // TMA path: at most four references, every plane 16-byte aligned with a 16-byte pitch (device pictures of svtb200_yuv_picture_create)
+        A.tma = n_refs <= 4;
+        for (int i = 0; i < n_refs && A.tma; ++i)
+            for (int k = 0; k < 3; ++k) if (((uintptr_t)h_refs[i].p[k] & 15) || (h_refs[i].stride[k] & 15)) A.tma = 0;
+        for (int i = 0; i < n_refs && A.tma; ++i) {
+            const uint32_t rows_y = (uint32_t)(h_refs[i].h + 2 * h_refs[i].oy), rows_c = (uint32_t)(h_refs[i].h / 2 + h_refs[i].oy);
+            int rc = make_plane_tensor_map(&A.maps[i][0], h_refs[i].p[0], (uint32_t)h_refs[i].stride[0], rows_y, 48, 32);
+            if (!rc) rc = make_plane_tensor_map(&A.maps[i][1], h_refs[i].p[1], (uint32_t)h_refs[i].stride[1], rows_c, 48, 19);
+            if (!rc) rc = make_plane_tensor_map(&A.maps[i][2], h_refs[i].p[2], (uint32_t)h_refs[i].stride[2], rows_c, 48, 19);
+            if (rc) return rc;
+        }
+        const size_t smem = mc8_smem(A.tma != 0);
+        static thread_local bool attr_set[2] = {false, false};
+        if (!attr_set[A.tma != 0]) {
+            if (A.tma) SVTB200_CUDA_TRY(cudaFuncSetAttribute(mc_batch8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else SVTB200_CUDA_TRY(cudaFuncSetAttribute(mc_batch8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set[A.tma != 0] = true;
+        }
+        const int grid = (n_jobs + MC8_JOBS - 1) / MC8_JOBS;
+        if (A.tma) mc_batch8_kernel<true><<<grid, MC8_NT, smem, st>>>(A); else mc_batch8_kernel<false><<<grid, MC8_NT, smem, st>>>(A);
+    }
     SVTB200_COUNT_LAUNCH();
     SVTB200_CUDA_TRY(cudaGetLastError());
     return SVTB200_OK;
