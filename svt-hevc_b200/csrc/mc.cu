@@ -481,13 +481,97 @@ __device__ __forceinline__ void mc_chroma_h_rows(const McClass &c, int nl, int16
     }
 }
 
+__device__ __forceinline__ uint32_t pack_sat_u8x4(int o0, int o1, int o2, int o3)
+{
+    uint32_t t, d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(o3), "r"(o2), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(o1), "r"(o0), "r"(t));
+    return d;
+}
+// V pass of the chroma class for the warp path: a 4-column x 4-row output block per lane and plane (the 2 x 16 x 16 samples of a 32x32 PU = one block
+// per lane): seven s16 rows of four columns, six vertical pairs per column by PRMT, two DP2A per output, (S2 + 2048) >> 12 or BiPredClipping, then
+// cvt.pack.sat to four bytes and ONE 32-bit store per row.  Same arithmetic as mc_stage_v<4, false>.
+__device__ __forceinline__ void mc_chroma_v_warp(const McClass &c, int nl, const int16_t *s_tmp, int tmp_unit)
+{
+    const int lane = threadIdx.x & 31;
+    const int tw = c.tw, gpr = tw >> 2, per_plane = gpr * (c.th >> 2), total = 2 * per_plane;
+    const int lgg = 31 - __clz(gpr);
+    const uint32_t ky[2] = {pack4(c_chroma_taps[c.fy[0] & 7]), pack4(c_chroma_taps[c.fy[1] & 7])};
+    const bool al4 = ((((uintptr_t)c.out[0] | (uintptr_t)c.out[1]) | (uintptr_t)(c.ostride[0] | c.ostride[1])) & 3) == 0;
+    for (int i = lane; i < total; i += 32) {
+        const int p = i >= per_plane ? 1 : 0, j = i - p * per_plane;
+        const int rq = j >> lgg, cg = j & (gpr - 1);
+        int sum[4][4];      // [row][col]: uni S2 + 2048; bi (S2_0 >> 6) + (S2_1 >> 6)
+#pragma unroll
+        for (int l = 0; l < 2; ++l) {
+            if (l >= nl) continue;
+            const uint8_t *base = (const uint8_t *)(s_tmp + (p * 2 + l) * tmp_unit + (rq * 4) * tw + cg * 4);
+            uint2 w[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) w[k] = *(const uint2 *)(base + k * tw * 2);
+            uint32_t pr[6][4];      // vertical pairs (row k, row k + 1) per column
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                pr[k][0] = __byte_perm(w[k].x, w[k + 1].x, 0x5410); pr[k][1] = __byte_perm(w[k].x, w[k + 1].x, 0x7632);
+                pr[k][2] = __byte_perm(w[k].y, w[k + 1].y, 0x5410); pr[k][3] = __byte_perm(w[k].y, w[k + 1].y, 0x7632);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const int v = dp2a_hi_ss(pr[r + 2][x], ky[l], dp2a_lo_ss(pr[r][x], ky[l], nl == 2 ? 0 : 2048));
+                    if (nl == 2) sum[r][x] = (l ? sum[r][x] : 0) + (int)(short)(v >> 6);
+                    else sum[r][x] = v;
+                }
+        }
+        uint8_t *outp = (p ? c.out[1] : c.out[0]) + (size_t)(rq * 4) * (p ? c.ostride[1] : c.ostride[0]) + cg * 4;
+        const int ostride = p ? c.ostride[1] : c.ostride[0];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            int o[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+                o[x] = nl == 2 ? (sum[r][x] + 64) >> 7 : sum[r][x] >> 12;
+            const uint32_t v = pack_sat_u8x4(o[0], o[1], o[2], o[3]);
+            uint8_t *q = outp + (size_t)r * ostride;
+            if (al4) *(uint32_t *)q = v;
+            else { q[0] = (uint8_t)v; q[1] = (uint8_t)(v >> 8); q[2] = (uint8_t)(v >> 16); q[3] = (uint8_t)(v >> 24); }
+        }
+    }
+}
+
 // copy / rounded average of np planes out of TMA-fetched tiles (pitch 48): plane p, list l at tiles + (p * 2 + l) * tile_bytes, sample (x, y) of the block at
 // tile row y + row0, byte am[l] + col0 + x.  8-byte items (block widths are multiples of 8 for luma; chroma widths 4 take the 4-byte form).
 __device__ __forceinline__ void mc_copy_tiles(const McClass &c, int nl, const uint8_t *tiles, int tile_bytes, const int (&am)[2], int row0, int col0)
 {
     const int lane = threadIdx.x & 31;
     const int tw = c.tw, th = c.th;
-    const bool wide = (tw & 7) == 0 && ((((uintptr_t)c.out[0] | (uintptr_t)c.ostride[0]) | (c.np == 2 ? ((uintptr_t)c.out[1] | (uintptr_t)c.ostride[1]) : 0)) & 7) == 0;
+    const uintptr_t al = ((uintptr_t)c.out[0] | (uintptr_t)c.ostride[0]) | (c.np == 2 ? ((uintptr_t)c.out[1] | (uintptr_t)c.ostride[1]) : 0);
+    if ((tw & 15) == 0 && (al & 15) == 0) {      // 16-byte items: five tile words, four funnel shifts, one 128-bit store
+        const int ipr = tw >> 4, lg = 31 - __clz(ipr), per_plane = th * ipr, total = c.np * per_plane;
+#pragma unroll 2
+        for (int i = lane; i < total; i += 32) {
+            const int p = i >= per_plane ? 1 : 0, j = i - p * per_plane;
+            const int y = j >> lg, g = j & (ipr - 1);
+            uint32_t v[2][4];
+#pragma unroll
+            for (int l = 0; l < 2; ++l) {
+                if (l >= nl) continue;
+                const int o = (l ? am[1] : am[0]) + col0 + g * 16;
+                const uint32_t *w = (const uint32_t *)(tiles + (p * 2 + l) * tile_bytes + (y + row0) * 48) + (o >> 2);
+                const uint32_t sh = (uint32_t)(o & 3) * 8;
+                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+                v[l][0] = __funnelshift_r(w0, w1, sh); v[l][1] = __funnelshift_r(w1, w2, sh); v[l][2] = __funnelshift_r(w2, w3, sh); v[l][3] = __funnelshift_r(w3, w4, sh);
+            }
+            if (nl == 2) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[0][k] = __vavgu4(v[0][k], v[1][k]);
+            }
+            *(uint4 *)((p ? c.out[1] : c.out[0]) + (size_t)y * (p ? c.ostride[1] : c.ostride[0]) + g * 16) = make_uint4(v[0][0], v[0][1], v[0][2], v[0][3]);
+        }
+        return;
+    }
+    const bool wide = (tw & 7) == 0 && (al & 7) == 0;
     const int ib = wide ? 8 : 4, ipr = tw / ib, lg = 31 - __clz(ipr), per_plane = th * ipr, total = c.np * per_plane;
 #pragma unroll 2
     for (int i = lane; i < total; i += 32) {
@@ -578,13 +662,15 @@ __global__ void __launch_bounds__(MC8_NT, TMA ? 3 : 4) mc_batch8_kernel(const __
                     for (int s = 0; s < 2; ++s) {
                         L.fx[s] = px[s] & 3; L.fy[s] = py[s] & 3; K.fx[s] = px[s] & 7; K.fy[s] = py[s] & 7;
                         if (s < nl) { lf |= L.fx[s] | L.fy[s]; kf |= K.fx[s] | K.fy[s]; }
-                        L.u[0][s].ref = r[s]->p[0] + ((size_t)((py[s] >> 2) + ty0) * r[s]->stride[0] + (px[s] >> 2) + tx0);
-                        L.u[0][s].rstride = r[s]->stride[0];
-                        L.u[1][s] = L.u[0][s];
+                        if (!TMA || phase == 1) {      // (the TMA warp path addresses its windows by tensor coordinates)
+                            L.u[0][s].ref = r[s]->p[0] + ((size_t)((py[s] >> 2) + ty0) * r[s]->stride[0] + (px[s] >> 2) + tx0);
+                            L.u[0][s].rstride = r[s]->stride[0];
+                            L.u[1][s] = L.u[0][s];
 #pragma unroll
-                        for (int pl = 1; pl < 3; ++pl) {
-                            K.u[pl - 1][s].ref = r[s]->p[pl] + ((size_t)((py[s] >> 3) + (ty0 >> 1)) * r[s]->stride[pl] + (px[s] >> 3) + (tx0 >> 1));
-                            K.u[pl - 1][s].rstride = r[s]->stride[pl];
+                            for (int pl = 1; pl < 3; ++pl) {
+                                K.u[pl - 1][s].ref = r[s]->p[pl] + ((size_t)((py[s] >> 3) + (ty0 >> 1)) * r[s]->stride[pl] + (px[s] >> 3) + (tx0 >> 1));
+                                K.u[pl - 1][s].rstride = r[s]->stride[pl];
+                            }
                         }
                     }
                     L.interp = lf != 0; K.interp = kf != 0;
@@ -617,7 +703,7 @@ __global__ void __launch_bounds__(MC8_NT, TMA ? 3 : 4) mc_batch8_kernel(const __
                                 __syncwarp();                                  // the luma copy has read its tiles
                                 mc_chroma_h_rows<true>(K, nl, s_ctmp, G::TMP_C, s_ct, MC8_CT, ac);
                                 __syncwarp();
-                                mc_stage_v<4, false, 32>(K, nl, s_ctmp, G::TMP_C);
+                                mc_chroma_v_warp(K, nl, s_ctmp, G::TMP_C);
                             }
                         } else {
                             int16_t *s_ctmp = (int16_t *)s_warp;
@@ -627,7 +713,7 @@ __global__ void __launch_bounds__(MC8_NT, TMA ? 3 : 4) mc_batch8_kernel(const __
                             else {
                                 mc_chroma_h_rows<false>(K, nl, s_ctmp, G::TMP_C, nullptr, 0, dummy);
                                 __syncwarp();
-                                mc_stage_v<4, false, 32>(K, nl, s_ctmp, G::TMP_C);
+                                mc_chroma_v_warp(K, nl, s_ctmp, G::TMP_C);
                                 __syncwarp();      // the next tile reuses the per-warp tile
                             }
                         }

@@ -10,7 +10,7 @@ python tools/ncu_summary.py /tmp/$tag.ncu-rep > gpurun_out/${tag}_summary.txt 2>
 python tools/ncu_lines.py /tmp/$tag.ncu-rep "me_picture:k12817me_picture_kernelILb0" me.cu 70 > gpurun_out/${tag}_lines_me0.txt 2>&1
 python tools/ncu_lines.py /tmp/$tag.ncu-rep "me_picture:k25617me_picture_kernelILb1" me.cu 50 > gpurun_out/${tag}_lines_me1.txt 2>&1
 python tools/ncu_lines.py /tmp/$tag.ncu-rep "tq_batch:tq_batch_kernelILb0" tq.cu 60 > gpurun_out/${tag}_lines_tq.txt 2>&1
-python tools/ncu_lines.py /tmp/$tag.ncu-rep "mc_batch8:mc_batch8_kernel" mc.cu 60 > gpurun_out/${tag}_lines_mc.txt 2>&1
+python tools/ncu_lines.py /tmp/$tag.ncu-rep "mc_batch8:mc_batch8_kernelILb1" mc.cu 400 > gpurun_out/${tag}_lines_mc.txt 2>&1
 python tools/ncu_lines.py /tmp/$tag.ncu-rep "sao_stats_kernel" sao.cu 30 > gpurun_out/${tag}_lines_sao.txt 2>&1
 python tools/ncu_lines.py /tmp/$tag.ncu-rep "ois_picture_kernel" intra.cu 30 > gpurun_out/${tag}_lines_ois.txt 2>&1
 ls -la /tmp/$tag.ncu-rep
