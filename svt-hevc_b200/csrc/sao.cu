@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(ST_NT) sao_stats16_kernel(const __grid_constan
         const int e0 = sgn(v, q[-1]) + sgn(v, q[1]) + 2, e1 = sgn(v, q[-rs]) + sgn(v, q[rs]) + 2;
         const int e2 = sgn(v, q[-rs - 1]) + sgn(v, q[rs + 1]) + 2, e3 = sgn(v, q[-rs + 1]) + sgn(v, q[rs - 1]) + 2;
         my[(0 + e0) * ST_NT] += add; my[(5 + e1) * ST_NT] += add; my[(10 + e2) * ST_NT] += add; my[(15 + e3) * ST_NT] += add;
-        my[(20 + (v >> 5)) * ST_NT] += add;
+        my[(20 + min(v >> 5, 31)) * ST_NT] += add;      // (samples above 10 bits -- a caller bug -- must not leave the histogram)
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256) sao_apply16_kernel(const __grid_constant_
     const uint16_t *q = (const uint16_t *)A.in[c].p + (size_t)y * is + x;
     int v = q[0];
     if (t == 5) {
-        const int b = (v >> 5) - p.band_position[c];
+        const int b = min(v >> 5, 31) - p.band_position[c];
         if (b >= 0 && b <= 3) v = min(max(v + p.offset[c][b], 0), 1023);
     } else if (t >= 1 && t <= 4) {
         const int dx = (t == 2) ? 0 : (t == 4 ? 1 : -1), dy = (t == 1) ? 0 : -1;

@@ -16,6 +16,8 @@
 // warp share the matrix row -> broadcast); the 16/32-point forward passes fold the first butterfly stage in 16 bits exactly
 // like PartialButterfly{16,32}Estimate.  Only the `active` low-frequency corner is computed for the N2 / N4 shapes, and
 // the inverse skips the zero rows/columns.  No tensor cores: operands are s16 x s8 with a rounding shift per pass.
+#include <mutex>
+
 #include "common.cuh"
 
 namespace svtb200 {
@@ -583,23 +585,31 @@ __global__ void __launch_bounds__(TQ_NT) tq_leaf_kernel(const LeafArgs L)
     }
 }
 
+// The transform matrices live in __constant__ / __device__ symbols of the CURRENT device: they are built into local buffers and uploaded once per device
+// under a lock (entry points are called concurrently from many EncDec threads), and the upload is complete -- cudaMemcpyToSymbol from pageable memory
+// followed by a device synchronisation -- before any thread launches on its own non-blocking stream.
 static int ensure_tables()
 {
-    static thread_local bool done = false;   // per thread: cheap and avoids a lock; the copy is idempotent
-    if (done) return SVTB200_OK;
+    static std::mutex mu;
+    static std::atomic<int> uploaded_dev{-1};
+    int dev = -1;
+    SVTB200_CUDA_TRY(cudaGetDevice(&dev));
+    if (uploaded_dev.load(std::memory_order_acquire) == dev) return SVTB200_OK;
+    std::lock_guard<std::mutex> lk(mu);
+    if (uploaded_dev.load(std::memory_order_relaxed) == dev) return SVTB200_OK;
     int8_t m[32][32];
     build_dct32(m);
-    SVTB200_CUDA_TRY(cudaMemcpyToSymbol(c_dct32, m, sizeof m));
-    SVTB200_CUDA_TRY(cudaMemcpyToSymbol(g_dct32, m, sizeof m));
-    static int8_t mt[4][32 * 32];
-    memset(mt, 0, sizeof mt);
+    std::vector<int8_t> mt(4 * 32 * 32, 0);
     for (int l = 0; l < 4; ++l) {
         const int N = 4 << l, ks = 32 / N;
         for (int k = 0; k < N; ++k)
-            for (int n = 0; n < N; ++n) mt[l][n * 32 + k] = m[k * ks][n];
+            for (int n = 0; n < N; ++n) mt[(size_t)l * 1024 + n * 32 + k] = m[k * ks][n];
     }
-    SVTB200_CUDA_TRY(cudaMemcpyToSymbol(g_dct_t, mt, sizeof mt));
-    done = true;
+    SVTB200_CUDA_TRY(cudaMemcpyToSymbol(c_dct32, m, sizeof m));
+    SVTB200_CUDA_TRY(cudaMemcpyToSymbol(g_dct32, m, sizeof m));
+    SVTB200_CUDA_TRY(cudaMemcpyToSymbol(g_dct_t, mt.data(), mt.size()));
+    SVTB200_CUDA_TRY(cudaDeviceSynchronize());
+    uploaded_dev.store(dev, std::memory_order_release);
     return SVTB200_OK;
 }
 
@@ -620,8 +630,8 @@ static int check_jobs(const svtb200_tq_job *jobs, int n, const svtb200_yuv_pictu
         const svtb200_plane &pl = t.plane == 0 ? pic.y : t.plane == 1 ? pic.cb : pic.cr;
         const bool ok = t.plane <= 2 && (t.size == 4 || t.size == 8 || t.size == 16 || t.size == 32) && t.shape <= 3 && t.qp <= 51 && t.slice_type <= 3 &&
                         (!t.dst4x4 || t.size == 4) && (t.size > 4 || t.shape == 0) && !(t.size == 8 && t.shape == SVTB200_SHAPE_N4) &&
-                        t.x + t.size <= pl.width + 2 * pl.origin_x && t.y + t.size <= pl.height + 2 * pl.origin_y;
-        if (!ok) { set_error("tq_batch: job %d malformed (size/shape/qp/plane out of range, or 8x8 with N4 which the reference leaves undefined)", j); return SVTB200_ERR_BAD_ARG; }
+                        t.x + t.size <= pl.width && t.y + t.size <= pl.height;      // TUs lie inside the picture: the coefficient planes are unpadded
+        if (!ok) { set_error("tq_batch: job %d malformed (size/shape/qp/plane out of range, TU outside the picture, or 8x8 with N4 which the reference leaves undefined)", j); return SVTB200_ERR_BAD_ARG; }
     }
     return SVTB200_OK;
 }
@@ -635,6 +645,11 @@ static int tq_batch_dev_impl(const svtb200_yuv_picture *src, const svtb200_yuv_p
                              const svtb200_coeff_picture *coeff, const svtb200_tq_job *jobs_dev, int n_jobs, uint32_t *nz_counts_dev, void *cuda_stream, bool hbd)
 {
     if (!src || !pred || !recon || !coeff || (!jobs_dev && n_jobs) || n_jobs < 0 || !nz_counts_dev) { set_error("tq_batch_dev: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    for (int k = 0; k < 3; ++k) {
+        const svtb200_plane *a[3] = {k == 0 ? &src->y : k == 1 ? &src->cb : &src->cr, k == 0 ? &pred->y : k == 1 ? &pred->cb : &pred->cr, k == 0 ? &recon->y : k == 1 ? &recon->cb : &recon->cr};
+        if (!a[0]->buf || !a[1]->buf || !a[2]->buf || !coeff->buf[k] || a[1]->width != a[0]->width || a[1]->height != a[0]->height || a[2]->width != a[0]->width ||
+            a[2]->height != a[0]->height || coeff->stride[k] < a[0]->width) { set_error("tq_batch_dev: plane %d: null buffer, or prediction / reconstruction / coefficient geometry differs from the source's", k); return SVTB200_ERR_BAD_ARG; }
+    }
     int rc = ensure_device();
     if (rc || (rc = ensure_tables())) return rc;
     if (n_jobs == 0) return SVTB200_OK;

@@ -102,9 +102,14 @@ class HostPaPicture:
 
 
 # ------------------------------------------------------------------------------------------------
-# preset -> ME parameters.  Mirror of SetMeHmeParamsOq / SignalDerivationMeKernelOq
-# (EbMotionEstimationProcess.c:53-124, :308-423) + the tables in EbDefinitions.h:1666-1806 for the
-# resolution classes / presets BASELINE.json names (4K and 1080p, M7 and M10).
+# preset -> ME / OIS parameters: restatement of the reference's per-picture signal derivation for the presets and resolution classes
+# BASELINE.json names (M7 and M10; 1080p and 4K-and-above), PINNED field by field against the reference's own functions by
+# tests/test_oracle_preset.py (oracle/refinc_meproc_harness.c):
+#   SignalDerivationPreAnalysisOq     EbResourceCoordinationProcess.c:239  (HME enables, tables EbDefinitions.h:1666-1806)
+#   SignalDerivationMultiProcessesOq  EbPictureDecisionProcess.c:376       (useSubpelFlag :334, limitOisToDcModeFlag, cu8x8Mode, skipOis8x8)
+#   SignalDerivationMeKernelOq        EbMotionEstimationProcess.c:308      (SetMeHmeParamsOq :53, oneQuadrantHME, fractionalSearchModel, ...)
+#   lambda / mvdBits                  EbMotionEstimationProcess.c:684-704
+# In the encoder the shim reads these values from the encoder's own contexts; this restatement serves bench.py and the tests.
 # ------------------------------------------------------------------------------------------------
 _ME_TABLE = {
     # (res_class, enc_mode): (l0_total_w, l0_total_h, l0_w, l0_h, en_l1, l1_w, l1_h, en_l2, l2_w, l2_h, sa_w, sa_h)
@@ -113,24 +118,62 @@ _ME_TABLE = {
     ("1080p", 10): (48, 40, 24, 20, 1, 4, 4, 0, 0, 0, 8, 7),
     ("1080p", 7): (64, 48, 32, 24, 1, 4, 4, 1, 4, 2, 16, 9),
 }
-# plausible CABAC bit-fraction estimates (1 bit = 32768) standing in for mdRateEstimationArray->mvdBits;
-# the same numbers are handed to the reference harness, the port and the CUDA path.
-DEFAULT_MVD_BITS = (24000, 43000, 26000, 40000, 21000, 47000, 30000, 36000, 33000, 33000, 29000, 38000)
-# lambdaModeDecisionRaSad{Base,RefNonBase,NonRef}[qp] are data tables of the encoder's rate control; tests only need a
-# the qp-32 entries
-DEFAULT_LAMBDA = {"base": 439162, "ref": 717148, "nonref": 824850}  # EbLambdaRateTables.h:249,280 at qp 32
+# initial MdRateEstimationContext_t::mvdBits (1 bit = 32768) at picture QP 32, the CQP setting of every BASELINE.json config
+# (EncodeCabacContextModelInit + MdRateEstimationContextInit, EbEncodeContext.c:138-143), by slice type; other QPs: pass mvd_bits
+MVD_BITS_QP32 = {
+    "B": (37716, 28388, 36028, 29856, 39963, 26612, 29856, 36028, 28388, 37716, 31523, 34297),
+    "P": (47445, 21645, 42538, 24752, 49833, 20310, 29856, 36028, 28388, 37716, 31523, 34297),
+}
+DEFAULT_MVD_BITS = MVD_BITS_QP32["B"]
+# lambdaModeDecisionRaSad{Base, RefNonBase, NonRef}[32] (EbLambdaRateTables.h:249,280,311); other QPs: pass lambda_
+DEFAULT_LAMBDA = {"base": 439162, "ref": 717148, "nonref": 994505}
+
+
+def resolution_class(width, height):
+    """DeriveInputResolution (EbSequenceControlSet.c:288) + the resolutionIndex of the preset tables: '4k' (INPUT_SIZE_4K_RANGE, also 8K) or '1080p'."""
+    n = width * height
+    if n >= 0x29F630:
+        return "4k"
+    if n >= 0x1AB3F0:
+        return "1080p"
+    raise Svtb200Error(f"preset tables are restated for 1080p and 4K-and-above pictures only ({width}x{height})")
+
+
+def picture_signals(width, height, enc_mode, temporal_layer, hierarchical_levels=3, is_reference=None, slice_type="B"):
+    """useSubpelFlag, limitOisToDcModeFlag, cu8x8Mode, skipOis8x8 of one picture (SignalDerivationMultiProcessesOq) for enc modes 7..10."""
+    if not 7 <= enc_mode <= 10:
+        raise Svtb200Error("picture signals are restated for enc modes 7..10")
+    res = resolution_class(width, height)
+    if is_reference is None:
+        is_reference = temporal_layer < hierarchical_levels
+    if enc_mode <= 8:
+        use_subpel = 1
+    elif enc_mode == 9:
+        use_subpel = int(temporal_layer == 0) if res == "4k" else 1
+    else:
+        use_subpel = int(temporal_layer == 0) if res == "4k" else int(bool(is_reference))
+    if enc_mode == 7:
+        cu8x8_mode = 1 if res == "4k" else (0 if temporal_layer == 0 else 1)
+    else:
+        cu8x8_mode = 1
+    intra = slice_type == "I"
+    return dict(use_subpel=use_subpel, limit_ois_to_dc_mode=int(enc_mode >= 10 and not intra), cu8x8_mode=cu8x8_mode, cu16x16_mode=0,
+                skip_ois_8x8=0 if intra else 1, is_reference=int(bool(is_reference)))
 
 
 def me_config(width, height, enc_mode=10, temporal_layer=0, num_lists=1, hierarchical_levels=3,
-              frame_rate=60, lambda_=None, mvd_bits=DEFAULT_MVD_BITS, ref_poc=(0, 16), rate_control_mode=0, use_subpel=None):
-    res = "4k" if width * height > 1920 * 1088 else "1080p"
+              frame_rate=60, lambda_=None, mvd_bits=None, ref_poc=(0, 16), rate_control_mode=0, use_subpel=None, is_reference=None, slice_type="B", qp=32):
+    res = resolution_class(width, height)
+    if (res, enc_mode) not in _ME_TABLE:
+        raise Svtb200Error(f"me_config: enc mode {enc_mode} is not restated (7 and 10 are)")
     t = _ME_TABLE[(res, enc_mode)]
+    sig = picture_signals(width, height, enc_mode, temporal_layer, hierarchical_levels, is_reference, slice_type)
     c = MeConfig()
     c.pic_width, c.pic_height = width, height
     c.num_lists, c.temporal_layer, c.hierarchical_levels = num_lists, temporal_layer, hierarchical_levels
     c.enable_hme, c.enable_hme_l0, c.enable_hme_l1, c.enable_hme_l2 = 1, 1, t[4], t[7]
     c.one_quadrant_hme = 1 if (enc_mode >= 8 and res == "4k") else 0
-    c.update_hme_search_center = 1
+    c.update_hme_search_center = 1       # resolution above 576p and tune 1 (SetMeHmeParamsOq :120)
     c.n_hme_regions_w = c.n_hme_regions_h = 2
     l0tw, l0th, l0w, l0h = t[0], t[1], t[2], t[3]
     if res == "4k" and frame_rate <= 30:   # low frame-rate bump, EbMotionEstimationProcess.c:98-117
@@ -144,17 +187,37 @@ def me_config(width, height, enc_mode=10, temporal_layer=0, num_lists=1, hierarc
         c.hme_l1_w[i], c.hme_l1_h[i] = t[5], t[6]
         c.hme_l2_w[i], c.hme_l2_h[i] = t[8], t[9]
     c.search_area_w, c.search_area_h = t[10], t[11]
-    if use_subpel is None:               # useSubpelFlag, EbPictureDecisionProcess.c:330-361: 4K: base layer only; below 4K: M<=9 all, M10 reference pictures
-        use_subpel = (temporal_layer == 0) if res == "4k" else (enc_mode <= 9 or temporal_layer < hierarchical_levels)
+    if use_subpel is None:
+        use_subpel = sig["use_subpel"]
     # fractionalSearchModel, EbMotionEstimationProcess.c:398-420: 0 all PUs (M<=5, M6 below 4K), 1 selective (SuPelEnable), 2 off
-    c.fractional_search_model = 2 if not use_subpel else (0 if (enc_mode <= 5 or (enc_mode == 6 and res != "4k")) else 1)
+    c.fractional_search_model = 2 if not use_subpel else 1
     c.fractional_search_method = 0       # SUB_SAD_SEARCH for M>=5 (:340-345)
-    c.cu8x8_mode, c.cu16x16_mode = 1, 0  # CU_8x8_MODE_1 at M>=? (EbPictureDecisionProcess.c:447-449)
+    c.cu8x8_mode, c.cu16x16_mode = sig["cu8x8_mode"], 0
     c.rate_control_mode = rate_control_mode
-    c.lambda_ = lambda_ if lambda_ is not None else DEFAULT_LAMBDA["base" if temporal_layer == 0 else "ref"]
+    if lambda_ is None:
+        if qp != 32:
+            raise Svtb200Error("me_config: lambda_ is tabulated for QP 32 only; pass lambda_ (lambdaModeDecisionRaSad*[qp])")
+        lambda_ = DEFAULT_LAMBDA["base" if temporal_layer == 0 else ("ref" if sig["is_reference"] else "nonref")]
+    c.lambda_ = lambda_
+    if mvd_bits is None:
+        if qp != 32:
+            raise Svtb200Error("me_config: mvd_bits are tabulated for QP 32 only; pass mvd_bits (mdRateEstimationArray->mvdBits)")
+        mvd_bits = MVD_BITS_QP32["P" if slice_type == "P" else "B"]
     for i, v in enumerate(mvd_bits):
         c.mvd_bits[i] = v
     c.ref_poc[0], c.ref_poc[1] = ref_poc
+    return c
+
+
+def ois_config(width, height, enc_mode=10, temporal_layer=0, hierarchical_levels=3, is_reference=None, slice_type="B"):
+    """OisConfig of one picture: oisKernelLevel / oisThSet (SignalDerivationMeKernelOq :352-392), limitOisToDcModeFlag, skipOis8x8, cu8x8Mode."""
+    sig = picture_signals(width, height, enc_mode, temporal_layer, hierarchical_levels, is_reference, slice_type)
+    c = OisConfig()
+    c.pic_width, c.pic_height = width, height
+    c.slice_type = {"B": 0, "P": 1, "I": 2}[slice_type]
+    c.temporal_layer = temporal_layer
+    c.ois_kernel_level, c.ois_th_set, c.set_best_ois_distortion_to_valid = 0, 1, 0      # enc modes >= 7 (:352-392)
+    c.limit_ois_to_dc_mode, c.skip_ois_8x8, c.cu8x8_mode = sig["limit_ois_to_dc_mode"], sig["skip_ois_8x8"], sig["cu8x8_mode"]
     return c
 
 
