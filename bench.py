@@ -42,15 +42,52 @@ PAD = 80
 METRIC = "4Kp60 8-bit preset-M10 hot-path CTUs/sec (fps = value / 2040)"
 WORKLOAD = ("configs[1]: 3840x2160 8-bit 4:2:0, preset M10 tool schedule, mini-GOP temporal layers [0,3,2,3,1,3,2,3], 2 reference lists, "
             "fixed 32x32 PU/TU mode-decision stand-in")
-STAGES = ["me_picture (+ sub-pel on layer 0)", "ois_picture", "mc_batch", "tq_batch", "sao_stats_picture", "dlf_picture (layer 0)", "sao_apply_picture (layer 0)"]
+STAGES = ["me_picture (+ sub-pel on layer 0)", "ois_picture", "mc_batch", "tq_batch", "sao_stats_picture (H3 state on layer 0: deblocked + unfiltered strips)",
+          "dlf_picture (layer 0)", "sao_apply_picture (layer 0)"]
 # algorithmic HBM bytes per CTU
 ALG = {"me": 9384 * 2, "ois": 4096 + 21 * 5, "mc_uni": 12288, "mc_bi": 18432, "tq": 30720, "dlf": 12864, "sao_stats": 12288 + 3 * 312, "sao_apply": 12288}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this command (profiles/r01_s4_summary.txt;
-# ME = 7/8 integer-pel launches + 1/8 sub-pel launches of the mini-GOP).  Writes mostly stay in the 126 MB L2 during a capture, so the figure is read-dominated.
-NCU_TRAFFIC = {"me": (7 * (27.699200 + 4.423424) + (18.488576 + 1.536256)) / 8 * 1e6, "ois": 8.636416e6, "mc": 13.201408e6, "tq": 27.947776e6, "sao_stats": 25.263616e6}
-NCU_TRAFFIC_SOURCE = "profiles/r01_s4_summary.txt"
+def kernel_sources_sha16():
+    """sha256 (first 16 hex digits) of the CUDA sources: stamps the ncu traffic file with the code it was captured from"""
+    import hashlib
+    m = hashlib.sha256()
+    d = os.path.join(ROOT, "svt-hevc_b200", "csrc")
+    for n in sorted(os.listdir(d)):
+        with open(os.path.join(d, n), "rb") as f:
+            m.update(n.encode()); m.update(f.read())
+    return m.hexdigest()[:16]
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of each stage's kernel from the committed `ncu --set full` capture of this command
+    (profiles/r02_traffic.json, written by tools/ncu_traffic.py on the GPU box).  The file is stamped with the hash of the kernel sources it was
+    captured from: a stale file yields null, never a number of other code."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        if t.get("sources_sha16") == kernel_sources_sha16():
+            return t["bytes_per_launch"], "profiles/r02_traffic.json"
+        return {}, "profiles/r02_traffic.json is stale (captured from other kernel sources)"
+    except Exception:
+        return {}, None
+
+
+# VABSDIFF4 issue rate measured on B200 by tools/ubench_pipes.cu (profiles/r02_ubench_pipes.txt): 0.49 warp-instructions / clock / SM sub-partition,
+# shared with SHF / PRMT / IADD3 / LOP3 / IMNMX (one half-rate ALU pipe)
+VABSDIFF4_PER_CLK_PER_SMSP = 0.49
+HME_MULT = {0: 200, 1: 140, 2: 100, 3: 70}          # HME_LEVEL_0_SEARCH_AREA_MULTIPLIER_X/_Y, 4 hierarchical levels (EbDefinitions.h:1322-1331)
+
+
+def me_sad_warp_instr(tl):
+    """VABSDIFF4 warp-instructions one M10 4K ME launch cannot avoid (two lists): HME level 0 (16 x 8-row block, every position of the
+    (64 x 32) * mult area, width floored to 16), the 8 x 7 full-pel search on 64 x 32 source rows, six + one LCU-sized centre tests, bi-prediction"""
+    saw, sah = (64 * HME_MULT[tl] // 100) & ~15, 32 * HME_MULT[tl] // 100
+    per_list = saw * sah * 32 + 56 * 512 + 7 * 512
+    bipred = 3 * 4096 // 2 // 4                         # 64x64 + 4 32x32 + 16 16x16 PUs, every other row, 4 samples per lane-op
+    full_rows = (ROWS - 1) * COLS                       # HME runs on full-height LCUs only
+    return ((2 * per_list + bipred) * full_rows + (2 * (56 * 512 + 7 * 384) + bipred) * COLS) / 32.0
 
 
 def peaks():
@@ -240,6 +277,7 @@ def run_b200(args):
         def __init__(self):
             self.pred_t, self.pred = dev_yuv()
             self.sao_t, self.sao_out = dev_yuv()
+            self.unf_t, self.unf = dev_yuv()                 # reconstruction before deblocking (H3 statistics of layer-0 pictures)
             self.in_t, self.in_yuv = dev_yuv()
             self.pa = S.DevPaPicture(W, H)
             self.coeff_t = [torch.zeros((H, W), dtype=torch.int16, device=dev), torch.zeros((H // 2, W // 2), dtype=torch.int16, device=dev),
@@ -288,7 +326,7 @@ def run_b200(args):
         mc_bytes.append(wl.mc_alg_bytes(jobs))
     torch.cuda.synchronize()
 
-    names = ["me", "ois", "mc", "tq", "dlf", "sao_stats", "sao_apply"]
+    names = ["me", "ois", "mc", "tq", "h3_copy", "dlf", "sao_stats", "sao_apply"]
     # per-frame constants hoisted out of the loops (the loops should cost the host as little as a C caller would spend)
     me_cfgs = {tl: S.me_config(W, H, enc_mode=10, temporal_layer=tl, num_lists=2, ref_poc=(0, 16)) for tl in set(TL_PATTERN)}
     ref_pairs = {}
@@ -318,10 +356,14 @@ def run_b200(args):
         timed("mc", lambda: S.mc_batch_dev(ref_pairs[(r0, r1)], d_mc_ptr[k][0], d_mc_ptr[k][1], pred, st))
         timed("tq", lambda: S.tq_batch_dev(src_yuv, pred, pred, sl.coeff, p_tq, n_tq, P["nz"], st))
         if tl0:
+            # H3 (EbCodingLoop.c:4604-4635, 4711-4748): the encoder gathers LCU n's statistics right after LCU n's own deblocking step, i.e. from the
+            # deblocked picture except the right / bottom 4-sample strips of every LCU, which are still unfiltered: keep the reconstruction before DLF
+            timed("h3_copy", lambda: S.yuv_picture_copy_dev(pred, sl.unf, st))
             timed("dlf", lambda: S.dlf_picture_dev(pred, p_vbs, p_hbs, p_qp, wl.dlf_prm, st))
-        timed("sao_stats", lambda: S.sao_stats_picture_dev(src_yuv, pred, P["stats"], st))
-        if tl0:
+            timed("sao_stats", lambda: S.sao_stats_picture_h3_dev(src_yuv, pred, sl.unf, P["stats"], st))
             timed("sao_apply", lambda: S.sao_apply_picture_dev(pred, sl.sao_out, p_sao_prm, (1, 1), st))
+        else:
+            timed("sao_stats", lambda: S.sao_stats_picture_dev(src_yuv, pred, P["stats"], st))
 
     # resident loop: frames are independent, so consecutive frames alternate between `--streams` compute streams (one output slot each);
     # kernels of different frames then share the SMs, which hides launch tails and lets the latency-bound kernels overlap the issue-bound ones
@@ -386,24 +428,27 @@ def run_b200(args):
 
     for i in range(args.warmup):
         step_resident(i)
-    launches0 = S.lib().svtb200_launch_count()
     sampler = ClockSampler(local); sampler.start()
-    ev = {n: [] for n in names}
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0.record(tstream)
-    for cs in cstreams[1:]:
-        cs.wait_event(t0)
-    for i in range(args.steps):
-        step_resident(args.warmup + i, ev)
-    for cs in cstreams[1:]:
-        e = torch.cuda.Event(); e.record(cs); tstream.wait_event(e)
-    t1.record(tstream)
-    barrier()
+    # the timed region (exactly --steps frames between two barriers) is run --repeats times; the MEDIAN run is the one reported
+    runs = []
+    for rep in range(max(1, args.repeats)):
+        launches0 = S.lib().svtb200_launch_count()
+        ev = {n: [] for n in names}
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0.record(tstream)
+        for cs in cstreams[1:]:
+            cs.wait_event(t0)
+        for i in range(args.steps):
+            step_resident(args.warmup + i, ev)
+        for cs in cstreams[1:]:
+            e = torch.cuda.Event(); e.record(cs); tstream.wait_event(e)
+        t1.record(tstream)
+        barrier()
+        runs.append((t0.elapsed_time(t1), {n: [a.elapsed_time(b) for a, b in ev[n]] for n in names}, S.lib().svtb200_launch_count() - launches0))
     sampler.stop_flag = True
-    launches = S.lib().svtb200_launch_count() - launches0
-    ms = t0.elapsed_time(t1)
-    stage_ms = {n: [a.elapsed_time(b) for a, b in ev[n]] for n in names}
+    runs_ms = [r[0] for r in runs]
+    ms, stage_ms, launches = sorted(runs, key=lambda r: r[0])[len(runs) // 2]
     # the same stages with nothing else on the GPU (one stream): what each kernel costs alone -- reported next to the timed-region numbers
     ev1 = {n: [] for n in names}
     for i in range(min(args.steps, 16)):
@@ -459,11 +504,19 @@ def run_b200(args):
         tot = {n: float(np.sum(v)) for n, v in stage_ms.items()}
         dom = max(tot, key=tot.get)
         alg = {"me": ALG["me"] * N_LCU, "ois": ALG["ois"] * N_LCU, "mc": float(np.mean(mc_bytes)), "tq": ALG["tq"] * N_LCU, "dlf": ALG["dlf"] * N_LCU,
-               "sao_stats": ALG["sao_stats"] * N_LCU, "sao_apply": ALG["sao_apply"] * N_LCU}
+               "h3_copy": 2 * 6144 * N_LCU, "sao_stats": ALG["sao_stats"] * N_LCU, "sao_apply": ALG["sao_apply"] * N_LCU}
         per_stage = {n: {"launch_ms_avg": float(np.mean(v)) if v else None, "launches": len(v), "share_of_step": tot[n] / sum(tot.values()),
                          "achieved_gbs": (alg[n] / (np.mean(v) * 1e-3) / 1e9) if v else None,
                          "frac_of_hbm_peak": (alg[n] / (np.mean(v) * 1e-3) / 1e9 / peak) if v else None} for n, v in stage_ms.items()}
         k_avg_s = float(np.mean(stage_ms[dom])) * 1e-3
+        traffic, traffic_src = ncu_traffic()
+        sm_clk = (sampler.summary().get("sm_mhz") or 1965.0) * 1e6
+        sad_peak = 148 * 4 * VABSDIFF4_PER_CLK_PER_SMSP * sm_clk
+        sad_avg = float(np.mean([me_sad_warp_instr(wl.tl(args.warmup + j)) for j in range(args.steps)]))
+        me_avg_s = float(np.mean(stage_ms["me"])) * 1e-3
+        me_issue = {"bound": "vabsdiff4_issue", "sad_warp_instr_per_launch": sad_avg, "peak_warp_instr_per_s": sad_peak,
+                    "floor_ms_per_launch": sad_avg / sad_peak * 1e3, "avg_launch_ms": me_avg_s * 1e3, "frac": sad_avg / sad_peak / me_avg_s,
+                    "source": "tools/ubench_pipes.cu: 0.49 VABSDIFF4 / clk / SM sub-partition (profiles/r02_ubench_pipes.txt)"}
         h2d = W * H * 3 // 2
         d2h = int(np.mean(d2h_bytes))
         out = {
@@ -477,12 +530,15 @@ def run_b200(args):
             "gpu_launches": int(launches),
             **({"diagnosis_only_e2e_skip": sorted(skip)} if skip else {}),
             "clocks": sampler.summary(),
-            "roofline": {"kernel": {"me": "me_picture_kernel", "ois": "ois_picture_kernel", "mc": "mc_batch_kernel", "tq": "tq_batch_kernel", "dlf": "dlf_pass_kernel",
+            "roofline": {"kernel": {"me": "me_picture_kernel", "ois": "ois_picture_kernel", "mc": "mc_batch8_kernel", "tq": "tq_batch_kernel", "dlf": "dlf_pass_kernel", "h3_copy": "cudaMemcpy2DAsync (device to device)",
                                     "sao_stats": "sao_stats_kernel", "sao_apply": "sao_apply_kernel"}[dom],
                          "bound": "hbm", "achieved": alg[dom] / k_avg_s / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg[dom] / k_avg_s / 1e9 / peak, "traffic": NCU_TRAFFIC.get(dom), "traffic_source": NCU_TRAFFIC_SOURCE if dom in NCU_TRAFFIC else None,
+                         "frac": alg[dom] / k_avg_s / 1e9 / peak, "traffic": traffic.get(dom), "traffic_source": traffic_src,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg[dom], "avg_launch_ms": k_avg_s * 1e3},
+            # SURVEY 8d's secondary bound for ME: the VABSDIFF4 instructions the search cannot avoid at the measured issue rate of their (half-rate) pipe
+            "me_issue_roofline": me_issue,
+            "timed_region_runs_ms": runs_ms,
             "stages": per_stage,
             "me_ms_by_temporal_layer": {str(tl): float(np.mean([t for j, t in enumerate(serial_ms["me"]) if wl.tl(args.warmup + j) == tl])) for tl in sorted(set(TL_PATTERN))
                                         if any(wl.tl(args.warmup + j) == tl for j in range(len(serial_ms["me"])))},
@@ -499,6 +555,27 @@ def run_b200(args):
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's own functions (oracle/_ref), one frame per host thread
 # ------------------------------------------------------------------------------------------------
+def host_info():
+    """What the CPU arm really has: affinity mask, cgroup CPU quota, load, CPU model -- so that a record can explain its own CPU number"""
+    info = {"os_cpu_count": os.cpu_count(), "affinity_threads": len(os.sched_getaffinity(0)), "loadavg_before": list(os.getloadavg())}
+    quota = None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            q, per = f.read().split()[:2]
+            info["cgroup_cpu_max"] = f"{q} {per}"
+            if q != "max":
+                quota = max(1, int(float(q) / float(per)))
+    except Exception:
+        info["cgroup_cpu_max"] = None
+    try:
+        with open("/proc/cpuinfo") as f:
+            info["cpu_model"] = next((l.split(":", 1)[1].strip() for l in f if l.startswith("model name")), None)
+    except Exception:
+        info["cpu_model"] = None
+    info["usable_threads"] = max(1, min(info["affinity_threads"], quota or info["affinity_threads"]))
+    return info
+
+
 def cpu_reference(frames):
     """The reference's own functions on every host thread.  Like the B200 arm, the timed region holds nothing but the stage calls: the
     mode-decision stand-in (MC job lists from one ME pass per ring frame) is computed beforehand, every worker thread owns its output buffers for
@@ -512,7 +589,9 @@ def cpu_reference(frames):
     if ref is None:
         raise RuntimeError("oracle/_ref missing: build it with oracle/build_ref.sh where /root/reference exists")
     refsao = C.CDLL(os.path.join(ROOT, "oracle", "_ref", f"libsvtref_sao_{variant}.so"))
-    nthreads = os.cpu_count() or 1
+    # the threads this process may actually run on (affinity mask, cgroup CPU quota), not the box's nominal core count
+    host = host_info()
+    nthreads = host["usable_threads"]
     per_thread = 4
     frames = frames or nthreads * per_thread
     nworkers = min(nthreads, frames)
@@ -521,7 +600,7 @@ def cpu_reference(frames):
     yuv = [S.HostYuvPicture(wl.luma[i], wl.chroma[i][0], wl.chroma[i][1]) for i in range(RING)]
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
     ois_cfg = wl.ois_cfg()
-    for f in (ref.svtref_me_picture_rows, ref.svtref_ois_picture, ref.svtref_mc_batch, ref.svtref_tq_batch, ref.svtref_dlf_picture, refsao.svtref_sao_stats_picture,
+    for f in (ref.svtref_me_picture_rows, ref.svtref_ois_picture, ref.svtref_mc_batch, ref.svtref_tq_batch, ref.svtref_dlf_picture, ref.svtref_dlf_sao_stats_picture, refsao.svtref_sao_stats_picture,
               refsao.svtref_sao_apply_picture):
         f.restype = C.c_int
     flags = (C.c_uint8 * 2)(1, 1)
@@ -563,10 +642,12 @@ def cpu_reference(frames):
             assert ref.svtref_tq_batch(C.byref(yuv[k].struct), C.byref(self.pred.struct), C.byref(self.pred.struct), C.byref(self.coeff.struct), vp(wl.tq_jobs),
                                        C.c_int(n_tq), vp(self.nz), C.c_int(1), C.c_int(0), C.c_int(n_tq)) == 0
             if wl.tl(i) == 0:
-                assert ref.svtref_dlf_picture(C.byref(self.pred.struct), vp(wl.vbs), vp(wl.hbs), vp(wl.qp_array), C.byref(wl.dlf_prm), C.c_int(1)) == 0
-            assert refsao.svtref_sao_stats_picture(C.byref(yuv[k].struct), C.byref(self.pred.struct), vp(self.stats), C.c_int(1)) == 0
-            if wl.tl(i) == 0:
+                # the encoder's own order: every LCU's deblocking step followed by that LCU's SAO statistics (EbCodingLoop.c:4604-4635, 4711-4748)
+                assert ref.svtref_dlf_sao_stats_picture(C.byref(self.pred.struct), C.byref(yuv[k].struct), vp(wl.vbs), vp(wl.hbs), vp(wl.qp_array), C.byref(wl.dlf_prm),
+                                                        vp(self.stats), None, C.c_int(1)) == 0
                 assert refsao.svtref_sao_apply_picture(C.byref(self.pred.struct), vp(wl.sao_prm), flags, C.c_int(1)) == 0
+            else:
+                assert refsao.svtref_sao_stats_picture(C.byref(yuv[k].struct), C.byref(self.pred.struct), vp(self.stats), C.c_int(1)) == 0
 
     gate = threading.Barrier(nworkers + 1)
     errors = []
@@ -605,7 +686,7 @@ def cpu_reference(frames):
     if errors or dt is None:
         raise errors[0] if errors else RuntimeError("cpu_reference: the worker barrier broke")
     v = N_LCU * frames / dt
-    return {"value": v, "unit": "CTU/s", "fps": v / N_LCU, "cores": nworkers, "kind": "reference",
+    return {"value": v, "unit": "CTU/s", "fps": v / N_LCU, "cores": nworkers, "kind": "reference", "host": host, "loadavg_after": list(os.getloadavg()),
             "sample": f"{frames} full 4K frames of the same stages and jobs through the reference's own functions (MotionEstimateLcu, OpenLoopIntraSearchLcu, "
                       f"EncodePassInterPrediction, EstimateTransform/UnifiedQuantizeInvQuantize/EncodeInvTransform, LCU DLF drivers, SAO gather/apply; "
                       f"{variant} rows), {nworkers} worker threads with their own buffers, {frames // nworkers} frame(s) each behind a barrier; job lists "
@@ -673,6 +754,7 @@ def main():
     ap.add_argument("--e2e-skip", default="", help="diagnosis only: comma list of e2e parts to leave out (h2d, d2h, pack, pa); a run with this set is not a bench value")
     ap.add_argument("--inflight", type=int, default=5, help="frames in flight in the end-to-end loop (device + pinned host buffers per frame)")
     ap.add_argument("--streams", type=int, default=2, help="compute streams the resident loop spreads consecutive frames over")
+    ap.add_argument("--repeats", type=int, default=5, help="the timed region (--steps frames) is run this many times; the median run is reported")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -360,7 +360,9 @@ int svtb200_sao_stats_picture(const svtb200_yuv_picture *src, const svtb200_yuv_
 int svtb200_sao_stats_picture_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out_dev, void *cuda_stream);
 /* H3: the statistics the encoder gathers on a picture WITH deblocking -- LCU n is gathered right after its own deblocking step
  * (Codec/EbCodingLoop.c:4600-4760), when its last 4 columns / rows still wait for the right / bottom neighbour: `deblocked` everywhere except those
- * strips, which are read from `unfiltered` (same geometry; the reconstruction before svtb200_dlf_picture).  Device pictures. */
+ * strips, which are read from `unfiltered` (same geometry; the reconstruction before svtb200_dlf_picture). */
+int svtb200_sao_stats_picture_h3(const svtb200_yuv_picture *src, const svtb200_yuv_picture *deblocked, const svtb200_yuv_picture *unfiltered,
+                                 svtb200_sao_stats *out);
 int svtb200_sao_stats_picture_h3_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *deblocked, const svtb200_yuv_picture *unfiltered,
                                      svtb200_sao_stats *out_dev, void *cuda_stream);
 
@@ -545,6 +547,10 @@ int svtb200_yuv_picture_upload(const svtb200_yuv_picture *dev, const void *host_
 /* b6: GeneratePadding (Codec/EbMcp.c:1017) on a device-resident reconstructed picture, in place, before it serves as a reference
  * (PadRefAndSetFlags, Codec/EbEncDecProcess.c): every padding sample takes the nearest interior sample.  8-bit planes. */
 int svtb200_yuv_picture_pad_dev(const svtb200_yuv_picture *dev, void *cuda_stream);
+/* Device picture -> device picture of the same geometry (whole padded planes, bytes_per_sample 1 or 2): keeps the reconstruction a later stage needs
+ * unmodified, e.g. the picture before svtb200_dlf_picture_dev for svtb200_sao_stats_picture_h3_dev (the reference keeps it implicitly: its LCU n is
+ * gathered before LCU n + 1 is deblocked, Codec/EbCodingLoop.c:4604-4748). */
+int svtb200_yuv_picture_copy_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *dst, uint32_t bytes_per_sample, void *cuda_stream);
 int svtb200_copy_async(void *dst, const void *src, size_t bytes, int device_to_host, void *cuda_stream);
 void svtb200_pa_picture_destroy(svtb200_pa_picture *dev);
 

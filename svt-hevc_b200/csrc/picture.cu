@@ -110,6 +110,25 @@ int svtb200_pa_picture_upload(const svtb200_pa_picture *dev, const uint8_t *host
     return build_planes(dev, st, f.buf, (int)f.stride, f.origin_x, true);
 }
 
+// Device picture -> device picture (same geometry), whole padded planes: the reconstruction a later stage needs unmodified (H3: the SAO statistics of a
+// deblocked picture read the strips that were still unfiltered at gather time from the picture before svtb200_dlf_picture_dev).
+int svtb200_yuv_picture_copy_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *dst, uint32_t bytes_per_sample, void *cuda_stream)
+{
+    if (!src || !dst || (bytes_per_sample != 1 && bytes_per_sample != 2)) { set_error("yuv_picture_copy_dev: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    int rc = ensure_device();
+    if (rc) return rc;
+    const svtb200_plane *sp[3] = {&src->y, &src->cb, &src->cr}, *dp[3] = {&dst->y, &dst->cb, &dst->cr};
+    for (int k = 0; k < 3; ++k) {
+        if (!sp[k]->buf || !dp[k]->buf || sp[k]->width != dp[k]->width || sp[k]->height != dp[k]->height || sp[k]->origin_x != dp[k]->origin_x || sp[k]->origin_y != dp[k]->origin_y) {
+            set_error("yuv_picture_copy_dev: plane %d: null buffer or different geometry", k); return SVTB200_ERR_BAD_ARG;
+        }
+        const size_t row = (size_t)(sp[k]->width + 2 * sp[k]->origin_x) * bytes_per_sample, rows = (size_t)sp[k]->height + 2 * sp[k]->origin_y;
+        SVTB200_CUDA_TRY(cudaMemcpy2DAsync(dp[k]->buf, (size_t)dp[k]->stride * bytes_per_sample, sp[k]->buf, (size_t)sp[k]->stride * bytes_per_sample, row, rows,
+                                           cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream));
+    }
+    return SVTB200_OK;
+}
+
 int svtb200_yuv_picture_upload(const svtb200_yuv_picture *dev, const void *host_y, uint32_t host_y_stride, const void *host_cb, uint32_t host_cb_stride,
                                const void *host_cr, uint32_t host_cr_stride, uint32_t bytes_per_sample, void *cuda_stream)
 {

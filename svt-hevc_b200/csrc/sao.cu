@@ -350,21 +350,23 @@ static int upload_pic(ThreadCtx *c, const svtb200_yuv_picture *h, svtb200_yuv_pi
 }
 static size_t pic_bytes(const svtb200_yuv_picture *p) { return align_up(pbytes(p->y), 256) + align_up(pbytes(p->cb), 256) + align_up(pbytes(p->cr), 256); }
 
-static int sao_stats_impl(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out, bool hbd)
+static int sao_stats_impl(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out, bool hbd, const svtb200_yuv_picture *unfiltered = nullptr)
 {
     const size_t bps = hbd ? 2 : 1;
     if (!src || !recon || !out) { set_error("sao_stats_picture: bad argument"); return SVTB200_ERR_BAD_ARG; }
     int rc = sao_check(src, recon, "sao_stats_picture");
+    if (!rc && unfiltered) rc = sao_check(recon, unfiltered, "sao_stats_picture_h3");
     if (rc) return rc;
     ThreadCtx *c = tls_ctx();
     if ((rc = c->init())) return rc;
     c->reset();
     const size_t n = (size_t)((recon->y.width + 63) / 64) * ((recon->y.height + 63) / 64) * 3, ob = n * sizeof(svtb200_sao_stats);
-    if ((rc = c->dev_reserve(bps * (pic_bytes(src) + pic_bytes(recon)) + ob + 8192))) return rc;
-    svtb200_yuv_picture ds, dr;
+    if ((rc = c->dev_reserve(bps * (pic_bytes(src) + pic_bytes(recon) + (unfiltered ? pic_bytes(unfiltered) : 0)) + ob + 12288))) return rc;
+    svtb200_yuv_picture ds, dr, du;
     void *d_out;
-    if ((rc = upload_pic(c, src, &ds, true, bps)) || (rc = upload_pic(c, recon, &dr, true, bps)) || (rc = c->dev_alloc(ob, &d_out))) return rc;
-    if ((rc = sao_stats_dev_impl(&ds, &dr, (svtb200_sao_stats *)d_out, c->stream, hbd))) return rc;
+    if ((rc = upload_pic(c, src, &ds, true, bps)) || (rc = upload_pic(c, recon, &dr, true, bps)) || (unfiltered && (rc = upload_pic(c, unfiltered, &du, true, bps))) ||
+        (rc = c->dev_alloc(ob, &d_out))) return rc;
+    if ((rc = sao_stats_dev_impl(&ds, &dr, (svtb200_sao_stats *)d_out, c->stream, hbd, unfiltered ? &du : nullptr))) return rc;
     SVTB200_CUDA_TRY(cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, c->stream));
     SVTB200_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return SVTB200_OK;
@@ -401,6 +403,11 @@ int svtb200_sao_stats_picture_h3_dev(const svtb200_yuv_picture *src, const svtb2
 {
     if (!unfiltered) { set_error("sao_stats_picture_h3_dev: bad argument"); return SVTB200_ERR_BAD_ARG; }
     return sao_stats_dev_impl(src, deblocked, out_dev, cuda_stream, false, unfiltered);
+}
+int svtb200_sao_stats_picture_h3(const svtb200_yuv_picture *src, const svtb200_yuv_picture *deblocked, const svtb200_yuv_picture *unfiltered, svtb200_sao_stats *out)
+{
+    if (!unfiltered) { set_error("sao_stats_picture_h3: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    return sao_stats_impl(src, deblocked, out, false, unfiltered);
 }
 int svtb200_sao_apply_picture_dev(const svtb200_yuv_picture *in, const svtb200_yuv_picture *out, const svtb200_sao_params *lcu_params_dev, const uint8_t sao_flag[2], void *cuda_stream)
 { return sao_apply_dev_impl(in, out, lcu_params_dev, sao_flag, cuda_stream, false); }

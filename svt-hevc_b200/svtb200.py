@@ -650,6 +650,10 @@ def yuv_picture_upload(dev_struct, y_ptr, y_stride, cb_ptr, cb_stride, cr_ptr, c
                                            C.c_void_p(cr_ptr), C.c_uint32(cr_stride), C.c_uint32(bps), C.c_void_p(stream)))
 
 
+def yuv_picture_copy_dev(src_struct, dst_struct, stream=0, bytes_per_sample=1):
+    check(lib().svtb200_yuv_picture_copy_dev(C.byref(src_struct), C.byref(dst_struct), C.c_uint32(bytes_per_sample), C.c_void_p(stream)))
+
+
 def copy_async(dst_ptr, src_ptr, nbytes, device_to_host, stream=0):
     check(lib().svtb200_copy_async(C.c_void_p(dst_ptr), C.c_void_p(src_ptr), C.c_size_t(nbytes), C.c_int(1 if device_to_host else 0), C.c_void_p(stream)))
 
@@ -672,6 +676,14 @@ def sao_decision_picture(stats, lcu_cols, lcu_rows, rates, full_lambda, full_chr
     C.memmove(C.byref(r), C.byref(rates), C.sizeof(r))
     check(lib().svtb200_sao_decision_picture(_u8p(stats), C.c_int(lcu_cols), C.c_int(lcu_rows), C.byref(r), C.c_uint64(full_lambda),
                                              C.c_uint64(full_chroma_lambda_sao), C.c_int(is10bit), _u8p(out)))
+    return out
+
+
+def sao_stats_picture_h3(src, deblocked, unfiltered):
+    """H3 statistics (host pictures, HostYuvPicture)"""
+    n = ((deblocked.width + 63) // 64) * ((deblocked.height + 63) // 64)
+    out = np.zeros((n, 3), dtype=SAO_STATS_DTYPE)
+    check(lib().svtb200_sao_stats_picture_h3(C.byref(src.struct), C.byref(deblocked.struct), C.byref(unfiltered.struct), _u8p(out)))
     return out
 
 

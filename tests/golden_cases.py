@@ -197,17 +197,20 @@ def _intra(case, backend):
     return _h(np.frombuffer("".join(digests).encode(), np.uint8))
 
 
-# ---- oracles whose device version is not on main yet (reference and port only) -------------------------------------------------------------
-NO_CUDA_YET = ("saodec/", "sao_h3/")
+# ---- SAO decision and H3 statistics ----------------------------------------------------------------------------------------------------------
+NO_CUDA_YET = ("none/",)      # (every golden case has a CUDA runner)
 
 
 def _saodec(case, backend):
     import test_oracle_saodec as T
     name, sao_case, rates, lam, lam_c = case
     stats, cols, rows = T.picture_stats(sao_case)
-    lib, fn = (T.refdec, "svtref_sao_decision_picture") if backend == "reference" else (T.port, "port_sao_decision_picture")
-    assert backend != "cuda" and lib is not None
-    d = T.run_decision(lib, fn, stats, cols, rows, T.rate_tables(rates), lam, lam_c)
+    if backend == "cuda":
+        d = S.sao_decision_picture(stats, cols, rows, T.rate_tables(rates), lam, lam_c)
+    else:
+        lib, fn = (T.refdec, "svtref_sao_decision_picture") if backend == "reference" else (T.port, "port_sao_decision_picture")
+        assert lib is not None
+        d = T.run_decision(lib, fn, stats, cols, rows, T.rate_tables(rates), lam, lam_c)
     return _h(*[d[f] for f in ("merge_left", "merge_up", "type", "band_position", "offset", "luma_cost", "chroma_cost")])
 
 
@@ -217,8 +220,12 @@ def _sao_h3(case, backend):
     name, w, h, kind, density = case
     pic, vbs, hbs, qp, prm = make_dlf_inputs(w, h, seed=w + h, density=density, kind=kind)
     src = T.noisy_source(pic, w * 7 + h)
-    assert backend != "cuda"
-    st = T.reference_interleaved(pic, src, vbs, hbs, qp, prm, asm_mode=0)[2] if backend == "reference" else T.port_h3(pic, src, vbs, hbs, qp, prm)[2]
+    if backend == "cuda":      # picture-order deblocking of a copy on the device, then the H3 statistics from (deblocked, unfiltered)
+        final = S.HostYuvPicture(*[a.copy() for a in pic.interior()], pad=pic.pad)
+        S.dlf_picture(final, vbs, hbs, qp, prm)
+        st = S.sao_stats_picture_h3(src, final, pic)
+    else:
+        st = T.reference_interleaved(pic, src, vbs, hbs, qp, prm, asm_mode=0)[2] if backend == "reference" else T.port_h3(pic, src, vbs, hbs, qp, prm)[2]
     return _h(st["bo_diff"], st["bo_count"], st["eo_diff"][..., :4], st["eo_count"][..., :4])
 
 
