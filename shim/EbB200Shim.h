@@ -25,11 +25,15 @@ extern "C" {
 extern int EbB200Init(void);
 /* 1 when motion estimation of this picture goes to the GPU (backend on, unrestricted motion vectors, one tile, a preset the library supports) */
 extern int EbB200MeActive(const SequenceControlSet_t *scs, const PictureParentControlSet_t *pcs, const MeContext_t *me);
-/* MotionEstimateLcu of EVERY LCU of the picture in one call: fills pcs->meResults[lcu][pu] and pcs->rcMEdistortion[lcu] (what
- * MotionEstimateLcu writes, Codec/EbMotionEstimation.c:4321-4438).  Called by every ME segment thread of the picture (Codec/EbMotionEstimationProcess.c:706);
- * the first caller runs the picture, the others wait for it -- the open-loop intra search that follows reads the ME results of its own segment. */
-extern void EbB200MePictureOnce(SequenceControlSet_t *scs, PictureParentControlSet_t *pcs, MeContext_t *me, EbPictureBufferDesc_t *inputPadded,
-                                EbPictureBufferDesc_t *quarter, EbPictureBufferDesc_t *sixteenth);
+/* The open-loop stages of one picture in one go -- MotionEstimateLcu of EVERY LCU (fills pcs->meResults[lcu][pu] and pcs->rcMEdistortion[lcu], what
+ * MotionEstimateLcu writes, Codec/EbMotionEstimation.c:4321-4438) and OpenLoopIntraSearchLcu of every LCU (pcs->oisCu32Cu16Results / oisCu8Results,
+ * :5053).  Called by every ME segment thread of the picture (Codec/EbMotionEstimationProcess.c:706); the first caller runs the picture, the others wait
+ * for it.  Returns a mask of what the GPU did: EB_B200_DID_ME, EB_B200_DID_OIS (0: backend off). */
+#define EB_B200_DID_ME  1
+#define EB_B200_DID_OIS 2
+struct MotionEstimationContext_s;
+extern int EbB200PictureOnce(SequenceControlSet_t *scs, PictureParentControlSet_t *pcs, struct MotionEstimationContext_s *ctx, EbPictureBufferDesc_t *inputPicture,
+                             EbPictureBufferDesc_t *inputPadded, EbPictureBufferDesc_t *quarter, EbPictureBufferDesc_t *sixteenth);
 /* statistics for the log at encoder shutdown */
 extern void EbB200Report(void);
 

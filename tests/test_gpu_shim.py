@@ -19,6 +19,13 @@ def test_bitstream_identical_with_gpu_motion_estimation(tmp_path, w, h, n, enc_m
     gpu = SC.encode(str(tmp_path), clip, w, h, n, "1", enc_mode, tag="_gpu")
     assert ref[0] == 0, ref[3][-600:]
     assert gpu[0] == 0, gpu[3][-600:]
-    assert "motion estimation ran on the GPU" in gpu[3] or "motion estimation runs on the GPU" in gpu[3], gpu[3][-600:]
-    assert ref[1] is not None and ref[1] == gpu[1], "bitstreams differ"
+    assert "on the GPU" in gpu[3], gpu[3][-600:]
+    assert ref[1] is not None and ref[1] == gpu[1], "bitstreams differ (GPU motion estimation + open-loop intra search)"
     assert ref[2] is not None and ref[2] == gpu[2], "reconstructions differ"
+    # motion estimation alone on the GPU, the intra search on the CPU: isolates the two stages when one of them ever differs
+    os.environ["SVT_HEVC_B200_OIS"] = "0"
+    try:
+        me_only = SC.encode(str(tmp_path), clip, w, h, n, "1", enc_mode, tag="_me")
+    finally:
+        os.environ.pop("SVT_HEVC_B200_OIS", None)
+    assert me_only[0] == 0 and me_only[1] == ref[1] and me_only[2] == ref[2], "bitstreams differ (GPU motion estimation only)"
