@@ -36,16 +36,101 @@ for p in (os.path.join(ROOT, "svt-hevc_b200"), os.path.join(ROOT, "tests")):
 W, H = 3840, 2160
 COLS, ROWS = 60, 34
 N_LCU = COLS * ROWS
+BITS, ENC_MODE, FPS, CFG_ID = 8, 10, 60, 2
 TL_PATTERN = [0, 3, 2, 3, 1, 3, 2, 3]
 RING = 16
 PAD = 80
-METRIC = "4Kp60 8-bit preset-M10 hot-path CTUs/sec (fps = value / 2040)"
-WORKLOAD = ("configs[1]: 3840x2160 8-bit 4:2:0, preset M10 tool schedule, mini-GOP temporal layers [0,3,2,3,1,3,2,3], 2 reference lists, "
-            "fixed 32x32 PU/TU mode-decision stand-in")
+# BASELINE.json configs (index in `configs`, 0-based = id - 1).  2 is the headline the driver runs; 3 / 4 / 5: --config N
+CONFIGS = {
+    2: dict(w=3840, h=2160, bits=8, enc_mode=10, fps=60, streams=2, gop_exchange=False,
+            metric="4Kp60 8-bit preset-M10 hot-path CTUs/sec (fps = value / 2040)",
+            workload="configs[1]: 3840x2160 8-bit 4:2:0, preset M10 tool schedule, mini-GOP temporal layers [0,3,2,3,1,3,2,3], 2 reference lists, "
+                     "fixed 32x32 PU/TU mode-decision stand-in"),
+    3: dict(w=3840, h=2160, bits=10, enc_mode=7, fps=60, streams=2, gop_exchange=False,
+            metric="4Kp60 10-bit preset-M7 hot-path CTUs/sec (fps = value / 2040)",
+            workload="configs[2]: 3840x2160 10-bit 4:2:0, preset M7 tool schedule (HME level 0 in 2x2 regions + level 1, 16x9 full-pel search, selective sub-pel "
+                     "refinement on every layer, full open-loop intra search), 8-bit + 2-bit input planes packed to 16-bit samples on the device, 16-bit MC / "
+                     "T-Q / DLF / SAO, mini-GOP temporal layers [0,3,2,3,1,3,2,3], 2 reference lists, fixed 32x32 PU/TU mode-decision stand-in"),
+    4: dict(w=7680, h=4320, bits=10, enc_mode=10, fps=50, streams=2, gop_exchange=True,
+            metric="8Kp50 10-bit preset-M10 hot-path CTUs/sec, closed GOPs round-robin over the GPUs (fps = value / 8160)",
+            workload="configs[3]: 7680x4320 10-bit 4:2:0, preset M10 tool schedule, closed GOPs of 16 pictures, GOP g on rank g % N, per-picture outputs "
+                     "(packed coefficients + offsets + nz + ME / OIS / SAO records) sent to rank 0 over NCCL at every GOP boundary inside the timed region"),
+    5: dict(w=1920, h=1080, bits=8, enc_mode=10, fps=60, streams=4, gop_exchange=False,
+            metric="1080p60 8-bit preset-M10 stream-density hot-path CTUs/sec, 4 concurrent streams per GPU (fps per stream = value / 510 / (4 * N))",
+            workload="configs[4]: 4 independent 1920x1080 8-bit streams per GPU (32 on 8 GPUs), preset M10 (the reference rejects M12 at 1080p, "
+                     "EbEncHandle.c:2304-2309), one compute stream per video stream, no communication"),
+}
+METRIC = CONFIGS[2]["metric"]
+WORKLOAD = CONFIGS[2]["workload"]
 STAGES = ["me_picture (+ sub-pel on layer 0)", "ois_picture", "mc_batch", "tq_batch", "sao_stats_picture (H3 state on layer 0: deblocked + unfiltered strips)",
           "dlf_picture (layer 0)", "sao_apply_picture (layer 0)"]
-# algorithmic HBM bytes per CTU
+# algorithmic HBM bytes per CTU of 8-bit samples; sample planes count twice at 10 bits (alg_per_ctu)
 ALG = {"me": 9384 * 2, "ois": 4096 + 21 * 5, "mc_uni": 12288, "mc_bi": 18432, "tq": 30720, "dlf": 12864, "sao_stats": 12288 + 3 * 312, "sao_apply": 12288}
+
+
+def set_config(cid):
+    global W, H, COLS, ROWS, N_LCU, BITS, ENC_MODE, FPS, CFG_ID, METRIC, WORKLOAD
+    c = CONFIGS[cid]
+    W, H, BITS, ENC_MODE, FPS, CFG_ID = c["w"], c["h"], c["bits"], c["enc_mode"], c["fps"], cid
+    COLS, ROWS = (W + 63) // 64, (H + 63) // 64
+    N_LCU = COLS * ROWS
+    METRIC, WORKLOAD = c["metric"], c["workload"]
+    return c
+
+
+def alg_per_ctu():
+    """algorithmic bytes per CTU of the current configuration: ME / OIS read the 8-bit planes at any bit depth, the EncDec stages move 16-bit samples at 10 bits"""
+    k = 2 if BITS == 10 else 1
+    a = dict(ALG)
+    if ENC_MODE == 7:
+        a["me"] = (9384 + 2048) * 2            # + the quarter-resolution planes of HME level 1
+    for n in ("mc_uni", "mc_bi", "dlf", "sao_apply"):
+        a[n] = ALG[n] * k
+    a["tq"] = (6144 + 6144) * k + 12288 + 6144 * k
+    a["sao_stats"] = 12288 * k + 3 * 312
+    a["pack"] = 6144 + 6144 + 12288
+    return a
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process (threads + first-touch of everything it pins afterwards) to the CPUs of the NUMA node its GPU hangs off (NVML's ideal CPU affinity),
+    intersected with the CPUs the process may use.  Returns a record for the JSON line."""
+    rec = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = sorted(cpus & allowed)
+        if use:
+            os.sched_setaffinity(0, use)
+            rec = {"bound": True, "cpus": f"{use[0]}-{use[-1]} ({len(use)})", "allowed_before": len(allowed)}
+            try:
+                nodes = [n for n in os.listdir("/sys/devices/system/node") if n.startswith("node")]
+                for n in nodes:
+                    with open(f"/sys/devices/system/node/{n}/cpulist") as f:
+                        lst = f.read().strip()
+                    first = int(lst.split(",")[0].split("-")[0])
+                    if first in use or use[0] in _cpulist(lst):
+                        rec["numa_node"] = n
+                        break
+            except Exception:
+                pass
+    except Exception as e:      # noqa: BLE001
+        rec["error"] = f"{type(e).__name__}: {e}"
+    return rec
+
+
+def _cpulist(s):
+    out = set()
+    for part in s.split(","):
+        if "-" in part:
+            a, b = part.split("-"); out.update(range(int(a), int(b) + 1))
+        elif part:
+            out.add(int(part))
+    return out
 
 
 def kernel_sources_sha16():
@@ -81,13 +166,21 @@ HME_MULT = {0: 200, 1: 140, 2: 100, 3: 70}          # HME_LEVEL_0_SEARCH_AREA_MU
 
 
 def me_sad_warp_instr(tl):
-    """VABSDIFF4 warp-instructions one M10 4K ME launch cannot avoid (two lists): HME level 0 (16 x 8-row block, every position of the
-    (64 x 32) * mult area, width floored to 16), the 8 x 7 full-pel search on 64 x 32 source rows, six + one LCU-sized centre tests, bi-prediction"""
-    saw, sah = (64 * HME_MULT[tl] // 100) & ~15, 32 * HME_MULT[tl] // 100
-    per_list = saw * sah * 32 + 56 * 512 + 7 * 512
+    """VABSDIFF4 warp-instructions one ME launch of the current configuration cannot avoid (two lists): HME level 0 (16 x 8-row block, every position of the
+    search area: one (64 x 32) * mult quadrant at M10 4K, 2 x 2 regions of (32 x 16) * mult at M7), [M7: HME level 1, 4 regions of 8 x 4 on a 32 x 16-row block],
+    the full-pel search (8 x 7 or 16 x 9 positions on 64 x 32 source rows), six + one LCU-sized centre tests, bi-prediction.  Sub-pel refinement is not counted."""
+    if ENC_MODE == 7:
+        hme = 4 * ((32 * HME_MULT[tl] // 100) * (16 * HME_MULT[tl] // 100)) * 32 + 4 * 32 * 128
+        fp = 144 * 512
+    else:
+        saw, sah = (64 * HME_MULT[tl] // 100) & ~15, 32 * HME_MULT[tl] // 100
+        hme, fp = saw * sah * 32, 56 * 512
+    per_list = hme + fp + 7 * 512
     bipred = 3 * 4096 // 2 // 4                         # 64x64 + 4 32x32 + 16 16x16 PUs, every other row, 4 samples per lane-op
-    full_rows = (ROWS - 1) * COLS                       # HME runs on full-height LCUs only
-    return ((2 * per_list + bipred) * full_rows + (2 * (56 * 512 + 7 * 384) + bipred) * COLS) / 32.0
+    last_full = (H % 64) == 0
+    full_rows = (ROWS if last_full else ROWS - 1) * COLS          # HME runs on full-height LCUs only
+    part = 0 if last_full else (2 * (fp + 7 * 384) + bipred) * COLS
+    return ((2 * per_list + bipred) * full_rows + part) / 32.0
 
 
 def peaks():
@@ -143,17 +236,29 @@ class Workload:
         import common
         import svtb200 as S
         self.S = S
-        v = common.SynthVideo(W, H, seed=seed)
-        self.luma = [v.luma(i) for i in range(n_frames)]
-        self.chroma = [v.chroma(i) for i in range(n_frames)]
+        if W > 4096:      # 8K: a 2 x 2 tiling of a 4K clip (same texture statistics and motion, a quarter of the generation time)
+            v = common.SynthVideo(W // 2, H // 2, seed=seed)
+            self.luma = [np.tile(v.luma(i), (2, 2)) for i in range(n_frames)]
+            self.chroma = [tuple(np.tile(c, (2, 2)) for c in v.chroma(i)) for i in range(n_frames)]
+        else:
+            v = common.SynthVideo(W, H, seed=seed)
+            self.luma = [v.luma(i) for i in range(n_frames)]
+            self.chroma = [v.chroma(i) for i in range(n_frames)]
         self.n = n_frames
         rng = np.random.default_rng(seed ^ 0xABCD)
-        # TU jobs: 32x32 luma + 16x16 chroma, 16x16 / 8x8 in the 48-row bottom LCUs
+        if BITS == 10:
+            # 10-bit = the 8-bit clip x 4 + 2 random LSBs, held as the encoder holds its input: 8-bit MSB planes + 2-bit planes (byte = lsb << 6)
+            self.lsb = [tuple(((rng.integers(0, 4, p.shape, dtype=np.uint8)) << 6).astype(np.uint8) for p in (self.luma[i],) + tuple(self.chroma[i]))
+                        for i in range(n_frames)]
+        # geometry of the last LCU row (4K: 48 samples, 8K: 32, 1080p: 56): the largest of 32 / 16 / 8 that tiles it
+        self.last_h = H - 64 * (ROWS - 1)
+        self.n_last = 32 if self.last_h % 32 == 0 else 16 if self.last_h % 16 == 0 else 8
+        # TU jobs: 32x32 luma + 16x16 chroma; n_last (/ 2) in the bottom LCUs
         jobs = []
         for plane, sh in ((0, 0), (1, 1), (2, 1)):
             for ly in range(ROWS):
-                n = (32 >> sh) if ly < ROWS - 1 else (16 >> sh)
-                lh = (64 if ly < ROWS - 1 else 48) >> sh
+                n = (32 >> sh) if ly < ROWS - 1 else (self.n_last >> sh)
+                lh = (64 if ly < ROWS - 1 else self.last_h) >> sh
                 for lx in range(COLS):
                     for yy in range(0, lh, n):
                         for xx in range(0, 64 >> sh, n):
@@ -164,11 +269,14 @@ class Workload:
         tq["qp"] = np.where(tq["plane"] == 0, 32, 31)
         tq["slice_type"] = 0
         self.tq_jobs = tq
-        # boundary strengths: 1 on every 32x32 (16x16 in the bottom row) PU/TU boundary, none on the picture border
+        # boundary strengths: 1 on every PU/TU boundary (32-sample grid; n_last grid in the bottom row), none on the picture border
         vbs = np.zeros((ROWS, COLS, 16, 16), np.uint8)
         hbs = np.zeros((ROWS, COLS, 16, 16), np.uint8)
         vbs[:, :, :, 0] = 1; vbs[:, :, :, 8] = 1; hbs[:, :, 0, :] = 1; hbs[:, :, 8, :] = 1
-        vbs[-1, :, :, 4] = 1; vbs[-1, :, :, 12] = 1; hbs[-1, :, 4, :] = 1
+        for k in range(0, 16, self.n_last // 4):
+            vbs[-1, :, :, k] = 1
+            if 4 * k < self.last_h:
+                hbs[-1, :, k, :] = 1
         vbs[:, 0, :, 0] = 0; hbs[0, :, 0, :] = 0
         self.vbs, self.hbs = vbs.reshape(N_LCU, 256), hbs.reshape(N_LCU, 256)
         self.qp_array = np.full(((H + 7) // 8, W // 8), 32, np.uint8)
@@ -183,29 +291,36 @@ class Workload:
         return TL_PATTERN[step % 8]
 
     def me_cfg(self, step):
-        return self.S.me_config(W, H, enc_mode=10, temporal_layer=self.tl(step), num_lists=2, ref_poc=(0, 16))
+        return self.me_cfg_tl(self.tl(step))
 
-    def ois_cfg(self):
-        """M10, non-I pictures: limitOisToDcModeFlag (EbPictureDecisionProcess.c:417-422), skipOis8x8 (:455), CU_8x8_MODE_1"""
-        c = self.S.OisConfig()
-        c.pic_width, c.pic_height, c.slice_type, c.temporal_layer = W, H, 0, 0
-        c.limit_ois_to_dc_mode, c.skip_ois_8x8, c.cu8x8_mode = 1, 1, 1
-        return c
+    def me_cfg_tl(self, tl):
+        return self.S.me_config(W, H, enc_mode=ENC_MODE, temporal_layer=tl, num_lists=2, ref_poc=(0, 16), frame_rate=FPS)
+
+    def ois_cfg(self, tl=1):
+        """non-I pictures (EbPictureDecisionProcess.c:417-455): M10 DC only; M7 the full open-loop search"""
+        return self.S.ois_config(W, H, enc_mode=ENC_MODE, temporal_layer=tl, slice_type="B")
+
+    def ois_cap(self):
+        return 1 if ENC_MODE >= 10 else 9
 
     def refs(self, step):
         d = {0: 8, 1: 4, 2: 2, 3: 1}[self.tl(step)]
         return (step - d) % self.n, (step + d) % self.n
 
     def mc_jobs(self, me_results):
-        """Mode-decision stand-in: each 32x32 (16x16 in the bottom LCU row) PU takes its best ME candidate."""
+        """Mode-decision stand-in: each 32x32 PU (n_last x n_last in the bottom LCU row) takes its best ME candidate."""
         S = self.S
         res = me_results.reshape(ROWS, COLS, 85)
         out = []
         for ly in range(ROWS):
             if ly < ROWS - 1:
                 pus = [(1 + k, (k & 1) * 32, (k >> 1) * 32, 32) for k in range(4)]
+            elif self.n_last == 32:
+                pus = [(1 + k, (k & 1) * 32, (k >> 1) * 32, 32) for k in range(4) if (k >> 1) * 32 < self.last_h]
+            elif self.n_last == 16:
+                pus = [(5 + by * 4 + bx, bx * 16, by * 16, 16) for by in range(self.last_h // 16) for bx in range(4)]
             else:
-                pus = [(5 + by * 4 + bx, bx * 16, by * 16, 16) for by in range(3) for bx in range(4)]
+                pus = [(21 + by * 8 + bx, bx * 8, by * 8, 8) for by in range(self.last_h // 8) for bx in range(8)]
             for (pu, px, py, sz) in pus:
                 r = res[ly, :, pu]
                 j = np.zeros(COLS, dtype=S.MC_JOB_DTYPE)
@@ -222,7 +337,13 @@ class Workload:
     @staticmethod
     def mc_alg_bytes(jobs):
         px = jobs["w"].astype(np.int64) * jobs["h"] * 3 // 2
-        return int((px * (np.where(jobs["dir"] == 2, 2, 1) + 1)).sum())
+        return int((px * (np.where(jobs["dir"] == 2, 2, 1) + 1)).sum()) * (2 if BITS == 10 else 1)
+
+    def luma16(self, i):
+        return (self.luma[i].astype(np.uint16) << 2) | (self.lsb[i][0] >> 6)
+
+    def chroma16(self, i):
+        return tuple((self.chroma[i][k].astype(np.uint16) << 2) | (self.lsb[i][1 + k] >> 6) for k in range(2))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -234,6 +355,8 @@ def run_b200(args):
     import svtb200 as S
 
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    cfg = CONFIGS[CFG_ID]
+    numa = bind_to_gpu_numa_node(local)      # before anything is pinned: first touch of the pinned buffers lands on the GPU's NUMA node
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -242,11 +365,20 @@ def run_b200(args):
     stream = tstream.cuda_stream
     wl = Workload(RING, seed=0x5F7C0001 + rank)
     dev = torch.device("cuda", local)
+    hbd = BITS == 10
+    bps = 2 if hbd else 1
+    sdt = torch.int16 if hbd else torch.uint8           # sample storage (16-bit samples are unsigned; torch only carries the bits)
+    alg_ctu = alg_per_ctu()
+    # 8-bit or 16-bit flavour of every EncDec-side entry point
+    F = dict(mc=S.mc_batch16_dev if hbd else S.mc_batch_dev, tq=S.tq_batch16_dev if hbd else S.tq_batch_dev, dlf=S.dlf_picture16_dev if hbd else S.dlf_picture_dev,
+             sao_stats=S.sao_stats_picture16_dev if hbd else S.sao_stats_picture_dev, sao_h3=S.sao_stats_picture16_h3_dev if hbd else S.sao_stats_picture_h3_dev,
+             sao_apply=S.sao_apply_picture16_dev if hbd else S.sao_apply_picture_dev)
 
-    def dev_yuv():
-        y = torch.zeros((H + 2 * PAD, W + 2 * PAD), dtype=torch.uint8, device=dev)
-        cb = torch.zeros((H // 2 + PAD, W // 2 + PAD), dtype=torch.uint8, device=dev)
-        cr = torch.zeros((H // 2 + PAD, W // 2 + PAD), dtype=torch.uint8, device=dev)
+    def dev_yuv(dtype=None):
+        dtype = dtype or sdt
+        y = torch.zeros((H + 2 * PAD, W + 2 * PAD), dtype=dtype, device=dev)
+        cb = torch.zeros((H // 2 + PAD, W // 2 + PAD), dtype=dtype, device=dev)
+        cr = torch.zeros((H // 2 + PAD, W // 2 + PAD), dtype=dtype, device=dev)
         st = S.make_yuv_struct((y.data_ptr(), cb.data_ptr(), cr.data_ptr()), (y.shape[1], cb.shape[1], cr.shape[1]), PAD, W, H)
         return (y, cb, cr), st
 
@@ -262,82 +394,106 @@ def run_b200(args):
                 pl[:p, :] = pl[p:p + 1, :]; pl[p + hh:, :] = pl[p + hh - 1:p + hh, :]
 
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    h_y = [pin(a) for a in wl.luma]
-    h_cb = [pin(c[0]) for c in wl.chroma]
-    h_cr = [pin(c[1]) for c in wl.chroma]
+    h_y = [pin(a) for a in wl.luma]                     # 8-bit luma: what PictureAnalysis / ME / OIS read at any bit depth
+    if hbd:
+        # e2e input = unpacked 10-bit planes (yuv420p10le); resident input = the encoder's own 8-bit + 2-bit input planes, packed on the device per picture
+        h_s = [tuple(pin(a.view(np.int16)) for a in (wl.luma16(i),) + wl.chroma16(i)) for i in range(RING)]
+        d_in8 = [tuple(torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (wl.luma[i],) + tuple(wl.chroma[i])) for i in range(RING)]
+        d_inn = [tuple(torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in wl.lsb[i]) for i in range(RING)]
+    else:
+        h_s = [(h_y[i], pin(wl.chroma[i][0]), pin(wl.chroma[i][1])) for i in range(RING)]
     ring_pa = [S.DevPaPicture(W, H) for _ in range(RING)]
-    ring_yuv = [dev_yuv() for _ in range(RING)]
+    ring_yuv = [dev_yuv() for _ in range(RING)]          # reconstructed references (16-bit samples at 10 bits) == the sources of the synthetic clip
     for i in range(RING):
         ring_pa[i].upload(h_y[i].data_ptr(), stream)
-        fill_yuv(ring_yuv[i][0], h_y[i], h_cb[i], h_cr[i], True)
-    sao_t, sao_out = dev_yuv()
+        fill_yuv(ring_yuv[i][0], h_s[i][0], h_s[i][1], h_s[i][2], True)
+
+    cap_ois = wl.ois_cap()
+    n_tq = len(wl.tq_jobs)
+    stream_cap = int(sum(int(j["size"]) ** 2 for j in wl.tq_jobs))       # elements of the packed coefficient stream when every TU is coded
+    small_sizes = [N_LCU * 85 * 24, (n_tq + 1) * 4, n_tq * 4, N_LCU * 3 * 312, N_LCU * 85, N_LCU * 85 * cap_ois * 4]
+    small_offs = np.concatenate([[0], np.cumsum([(b + 255) // 256 * 256 for b in small_sizes])]).astype(int)
+    small_total = int(small_offs[-1])
+    frame_capacity = small_total + 2 * stream_cap        # [small results | packed coefficient stream]: one contiguous span per picture
 
     class Slot:
-        """device + pinned host buffers of one frame in flight (the e2e loop keeps two in flight: copies of one overlap the kernels of the other)"""
-        def __init__(self):
+        """device + pinned host buffers of one frame in flight (the e2e loop keeps several in flight: copies of one overlap the kernels of the other)"""
+        def __init__(self, own_outputs=True):
             self.pred_t, self.pred = dev_yuv()
             self.sao_t, self.sao_out = dev_yuv()
             self.unf_t, self.unf = dev_yuv()                 # reconstruction before deblocking (H3 statistics of layer-0 pictures)
             self.in_t, self.in_yuv = dev_yuv()
+            if hbd:
+                self.in8 = torch.zeros((H, W), dtype=torch.uint8, device=dev)      # e2e: 8-bit luma of the uploaded 10-bit picture (UnPack8BitData)
+                self.src_t, self.src = dev_yuv()                                   # resident: the packed 16-bit source picture
             self.pa = S.DevPaPicture(W, H)
             self.coeff_t = [torch.zeros((H, W), dtype=torch.int16, device=dev), torch.zeros((H // 2, W // 2), dtype=torch.int16, device=dev),
                             torch.zeros((H // 2, W // 2), dtype=torch.int16, device=dev)]
             self.coeff = S.CoeffPicture()
             for k in range(3):
                 self.coeff.buf[k] = self.coeff_t[k].data_ptr(); self.coeff.stride[k] = self.coeff_t[k].shape[1]
-            # everything small the host consumes sits in ONE device buffer (one D2H): ME results, TU offsets, nz counts, SAO stats, OIS
-            sizes = [N_LCU * 85 * 24, (len(wl.tq_jobs) + 1) * 4, len(wl.tq_jobs) * 4, N_LCU * 3 * 312, N_LCU * 85, N_LCU * 85 * 4]
-            offs = np.concatenate([[0], np.cumsum([(b + 255) // 256 * 256 for b in sizes])]).astype(int)
-            self.d_small = torch.zeros(int(offs[-1]), dtype=torch.uint8, device=dev)
-            self.h_small = torch.zeros(int(offs[-1]), dtype=torch.uint8).pin_memory()
-            part = lambda k: self.d_small[offs[k]:offs[k] + sizes[k]]
-            self.d_res, self.d_nz, self.d_stats, self.d_ois_total = part(0), part(2).view(torch.int32), part(3), part(4)
-            self.d_off, self.d_ois_cand = part(1).view(torch.int32), part(5).view(torch.int32)
-            self.h_off_total = self.h_small[offs[1]:offs[1] + sizes[1]].view(torch.int32).numpy()      # [-1] = packed stream length
-            # quantised coefficients leave the device as a dense stream of the coded TUs (svtb200_tq_pack_coeffs_dev)
-            self.cap = int(sum(int(j["size"]) ** 2 for j in wl.tq_jobs))
-            self.d_stream = torch.zeros(self.cap, dtype=torch.int16, device=dev)
-            self.h_stream = torch.empty(self.cap, dtype=torch.int16).pin_memory()
-            self.small_bytes = int(sum(sizes))
+            self.cap = stream_cap
+            self.small_bytes = int(sum(small_sizes))
             self.pending = False
             self.ev_small = torch.cuda.Event()
             self.ev_in, self.ev_cmp, self.ev_out = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
-            # raw pointers used by the per-frame calls
-            self.p = dict(res=self.d_res.data_ptr(), nz=self.d_nz.data_ptr(), stats=self.d_stats.data_ptr(), ois_t=self.d_ois_total.data_ptr(),
-                          ois_c=self.d_ois_cand.data_ptr(), off=self.d_off.data_ptr(), stream=self.d_stream.data_ptr(), small=self.d_small.data_ptr(),
-                          h_small=self.h_small.data_ptr(), h_stream=self.h_stream.data_ptr(), yint=self.in_t[0][PAD:, PAD:].data_ptr())
+            if own_outputs:
+                # everything the host consumes sits in ONE device span per picture (small results, then the packed stream): ME results, TU offsets, nz counts,
+                # SAO stats, OIS; the coefficients leave as a dense stream of the coded TUs (svtb200_tq_pack_coeffs_dev)
+                self.d_out = torch.zeros(frame_capacity, dtype=torch.uint8, device=dev)
+                self.h_small = torch.zeros(small_total, dtype=torch.uint8).pin_memory()
+                self.h_stream = torch.empty(stream_cap, dtype=torch.int16).pin_memory()
+                self.h_off_total = self.h_small[small_offs[1]:small_offs[1] + small_sizes[1]].view(torch.int32).numpy()      # [-1] = packed stream length
+                self.bind(self.d_out)
+
+        def bind(self, span):
+            """point the per-picture outputs at `span` (frame_capacity bytes of device memory: this slot's own, or a picture's place in the GOP-exchange buffer)"""
+            base = span.data_ptr()
+            o = small_offs
+            self.p = dict(res=base + int(o[0]), off=base + int(o[1]), nz=base + int(o[2]), stats=base + int(o[3]), ois_t=base + int(o[4]), ois_c=base + int(o[5]),
+                          small=base, stream=base + small_total, yint=self.in_t[0][PAD:, PAD:].data_ptr())
+            if hasattr(self, "h_small"):
+                self.p.update(h_small=self.h_small.data_ptr(), h_stream=self.h_stream.data_ptr())
+            self.off_total = span[int(o[1]) + 4 * n_tq:int(o[1]) + 4 * n_tq + 4].view(torch.int32)
 
     NS = max(3, args.inflight)            # e2e: NS frames in flight (H2D / kernels / D2H of consecutive frames overlap, the host runs NS - 1 frames ahead)
+    if W > 4096:
+        NS = 3                            # 8K: 0.8 GB of device pictures per slot
     slots = [Slot() for _ in range(NS)]
-    d_res = slots[0].d_res
     d_tq = torch.from_numpy(wl.tq_jobs.view(np.uint8)).to(dev)
     d_vbs, d_hbs, d_qp = (torch.from_numpy(a.copy()).to(dev) for a in (wl.vbs, wl.hbs, wl.qp_array))
     d_sao_prm = torch.from_numpy(wl.sao_prm.view(np.uint8)).to(dev)
-    ois_cfg = wl.ois_cfg()
+    ois_cfgs = {tl: wl.ois_cfg(tl) for tl in set(TL_PATTERN)}
 
     # mode-decision stand-in: one ME pass per (ring frame, layer) pair fixes the MC job lists used by both timed loops
     d_mc, mc_bytes = [], []
+    d_res0 = torch.zeros(small_sizes[0], dtype=torch.uint8, device=dev)
     for i in range(RING):
         r0, r1 = wl.refs(i)
-        S.me_picture_dev(wl.me_cfg(i), ring_pa[i], ring_pa[r0], ring_pa[r1], d_res.data_ptr(), stream)
+        S.me_picture_dev(wl.me_cfg(i), ring_pa[i], ring_pa[r0], ring_pa[r1], d_res0.data_ptr(), stream)
         torch.cuda.synchronize()
-        jobs = wl.mc_jobs(d_res.cpu().numpy().view(S.ME_PU_RESULT_DTYPE).reshape(N_LCU, 85))
+        jobs = wl.mc_jobs(d_res0.cpu().numpy().view(S.ME_PU_RESULT_DTYPE).reshape(N_LCU, 85))
         d_mc.append((torch.from_numpy(jobs.view(np.uint8)).to(dev), len(jobs)))
         mc_bytes.append(wl.mc_alg_bytes(jobs))
     torch.cuda.synchronize()
 
-    names = ["me", "ois", "mc", "tq", "h3_copy", "dlf", "sao_stats", "sao_apply"]
+    names = (["pack"] if hbd else []) + ["me", "ois", "mc", "tq", "h3_copy", "dlf", "sao_stats", "sao_apply"] + (["pack_coeffs"] if cfg["gop_exchange"] else [])
     # per-frame constants hoisted out of the loops (the loops should cost the host as little as a C caller would spend)
-    me_cfgs = {tl: S.me_config(W, H, enc_mode=10, temporal_layer=tl, num_lists=2, ref_poc=(0, 16)) for tl in set(TL_PATTERN)}
+    me_cfgs = {tl: wl.me_cfg_tl(tl) for tl in set(TL_PATTERN)}
     ref_pairs = {}
     for i in range(RING):
         r0, r1 = wl.refs(i)
         ref_pairs[(r0, r1)] = S.yuv_struct_array([ring_yuv[r0][1], ring_yuv[r1][1]])
     d_mc_ptr = [(t.data_ptr(), n) for t, n in d_mc]
-    p_tq, n_tq, p_vbs, p_hbs, p_qp, p_sao_prm = d_tq.data_ptr(), len(wl.tq_jobs), d_vbs.data_ptr(), d_hbs.data_ptr(), d_qp.data_ptr(), d_sao_prm.data_ptr()
-    hp = [(h_y[k].data_ptr(), h_cb[k].data_ptr(), h_cr[k].data_ptr()) for k in range(RING)]
+    p_tq, p_vbs, p_hbs, p_qp, p_sao_prm = d_tq.data_ptr(), d_vbs.data_ptr(), d_hbs.data_ptr(), d_qp.data_ptr(), d_sao_prm.data_ptr()
+    hp = [tuple(t.data_ptr() for t in h_s[k]) for k in range(RING)]
 
-    def pipeline(i, src_pa, src_yuv, sl, ts, ev=None):
+    def pack_source(k, sl, st):
+        """10 bits: the encoder's 8-bit + 2-bit input planes -> the 16-bit source picture of the EncDec stages (Pack2D_SRC, EbPictureOperators.c:544), per plane"""
+        for pl, (w_, h_, pad) in enumerate(((W, H, PAD), (W // 2, H // 2, PAD // 2), (W // 2, H // 2, PAD // 2))):
+            S.pack_plane_dev(S.PACK_MSB, d_in8[k][pl].data_ptr(), w_, d_inn[k][pl].data_ptr(), w_, sl.src_t[pl][pad:, pad:].data_ptr(), sl.src_t[pl].shape[1], 0, 0, w_, h_, st)
+
+    def pipeline(i, src_pa, src_yuv, sl, ts, ev=None, resident=True):
         """All device stages of frame i into slot sl on torch stream ts.  ev: dict name -> list of (start, end) events."""
         st = ts.cuda_stream
         def timed(name, fn):
@@ -348,32 +504,72 @@ def run_b200(args):
             ev[name].append((a, b))
         r0, r1 = wl.refs(i)
         k = i % RING
-        tl0 = wl.tl(i) == 0
+        tl = wl.tl(i)
+        tl0 = tl == 0
         pred = sl.pred
         P = sl.p
-        timed("me", lambda: S.me_picture_dev(me_cfgs[wl.tl(i)], src_pa, ring_pa[r0], ring_pa[r1], P["res"], st))
-        timed("ois", lambda: S.ois_picture_dev(ois_cfg, src_pa.struct.full, P["res"], P["ois_t"], P["ois_c"], 1, st))
-        timed("mc", lambda: S.mc_batch_dev(ref_pairs[(r0, r1)], d_mc_ptr[k][0], d_mc_ptr[k][1], pred, st))
-        timed("tq", lambda: S.tq_batch_dev(src_yuv, pred, pred, sl.coeff, p_tq, n_tq, P["nz"], st))
+        if hbd and resident:
+            timed("pack", lambda: pack_source(k, sl, st))
+            src_yuv = sl.src
+        timed("me", lambda: S.me_picture_dev(me_cfgs[tl], src_pa, ring_pa[r0], ring_pa[r1], P["res"], st))
+        timed("ois", lambda: S.ois_picture_dev(ois_cfgs[tl], src_pa.struct.full, P["res"], P["ois_t"], P["ois_c"], cap_ois, st))
+        timed("mc", lambda: F["mc"](ref_pairs[(r0, r1)], d_mc_ptr[k][0], d_mc_ptr[k][1], pred, st))
+        timed("tq", lambda: F["tq"](src_yuv, pred, pred, sl.coeff, p_tq, n_tq, P["nz"], st))
         if tl0:
             # H3 (EbCodingLoop.c:4604-4635, 4711-4748): the encoder gathers LCU n's statistics right after LCU n's own deblocking step, i.e. from the
             # deblocked picture except the right / bottom 4-sample strips of every LCU, which are still unfiltered: keep the reconstruction before DLF
-            timed("h3_copy", lambda: S.yuv_picture_copy_dev(pred, sl.unf, st))
-            timed("dlf", lambda: S.dlf_picture_dev(pred, p_vbs, p_hbs, p_qp, wl.dlf_prm, st))
-            timed("sao_stats", lambda: S.sao_stats_picture_h3_dev(src_yuv, pred, sl.unf, P["stats"], st))
-            timed("sao_apply", lambda: S.sao_apply_picture_dev(pred, sl.sao_out, p_sao_prm, (1, 1), st))
+            timed("h3_copy", lambda: S.yuv_picture_copy_dev(pred, sl.unf, st, bps))
+            timed("dlf", lambda: F["dlf"](pred, p_vbs, p_hbs, p_qp, wl.dlf_prm, st))
+            timed("sao_stats", lambda: F["sao_h3"](src_yuv, pred, sl.unf, P["stats"], st))
+            timed("sao_apply", lambda: F["sao_apply"](pred, sl.sao_out, p_sao_prm, (1, 1), st))
         else:
-            timed("sao_stats", lambda: S.sao_stats_picture_dev(src_yuv, pred, P["stats"], st))
+            timed("sao_stats", lambda: F["sao_stats"](src_yuv, pred, P["stats"], st))
+        if cfg["gop_exchange"] and resident:
+            timed("pack_coeffs", lambda: S.tq_pack_coeffs_dev(sl.coeff, p_tq, P["nz"], n_tq, P["stream"], sl.cap, P["off"], st))
 
     # resident loop: frames are independent, so consecutive frames alternate between `--streams` compute streams (one output slot each);
-    # kernels of different frames then share the SMs, which hides launch tails and lets the latency-bound kernels overlap the issue-bound ones
+    # kernels of different frames then share the SMs, which hides launch tails and lets the latency-bound kernels overlap the issue-bound ones.
+    # config 5: the compute streams ARE the concurrent video streams of the density run (frame i belongs to video stream i % streams).
     cstreams = [tstream] + [torch.cuda.Stream(device=dev) for _ in range(args.streams - 1)]
     while len(slots) < len(cstreams):
         slots.append(Slot())
 
-    def step_resident(i, ev=None):
+    # config 4: closed GOPs round-robin over the ranks; the pictures of a GOP write their outputs straight into the GOP-exchange buffer
+    FPG = 16
+    ex = None
+    if cfg["gop_exchange"]:
+        from gop_exchange import GopExchange
+        ex = GopExchange(rank, world, dev, FPG, frame_capacity)
+        comm_stream = torch.cuda.Stream(device=dev)
+        ex_stats = {"rounds": 0, "bytes": 0, "ms": []}
+
+    ev_round = [None, None]              # per parity: the transfers that last read this half of the exchange buffer
+
+    def step_resident(i, ev=None, frame_in_gop=None, parity=0):
         k = i % len(cstreams)
-        pipeline(i, ring_pa[i % RING], ring_yuv[i % RING][1], slots[k], cstreams[k], ev)
+        sl = slots[k]
+        if ex is not None:
+            if frame_in_gop == 0 and ev_round[parity] is not None:
+                for cs in cstreams:
+                    cs.wait_event(ev_round[parity])                                          # GOP k - 2 has left this half of the buffer
+            sl.bind(ex.frame_view(parity, frame_in_gop))
+        pipeline(i, ring_pa[i % RING], ring_yuv[i % RING][1], sl, cstreams[k], ev)
+
+    def gop_boundary(round_index, gop_slots_totals):
+        """all pictures of this rank's GOP are done: their byte counts reach the host (one small D2H), the transfers to rank 0 are posted on the
+        communication stream and overlap the next GOP's kernels"""
+        for cs in cstreams:
+            e = torch.cuda.Event(); e.record(cs); comm_stream.wait_event(e)
+        with torch.cuda.stream(comm_stream):
+            totals = torch.stack(gop_slots_totals).flatten().cpu().tolist()                 # elements of each picture's packed stream
+            fb = [small_total + 2 * min(int(v), stream_cap) for v in totals]
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(comm_stream)
+            moved = ex.exchange(round_index, fb)
+            ex.wait_all()                                                                    # stream-ordered: the communication stream waits, the host does not
+            b.record(comm_stream)
+            ev_round[round_index & 1] = b
+        ex_stats["rounds"] += 1; ex_stats["bytes"] += moved; ex_stats["ms"].append((a, b))
 
     # copy-in, small-results copy-out and coefficient-stream copy-out each get a stream: a frame's stream copy is issued two frames later (its
     # length must reach the host first) and must not queue behind the next frame's kernels
@@ -387,7 +583,7 @@ def run_b200(args):
         if not sl.pending:
             return
         sl.ev_small.synchronize()
-        total = int(sl.h_off_total[-1])
+        total = min(int(sl.h_off_total[-1]), sl.cap)
         if "d2h" not in skip:
             S.copy_async(sl.p["h_stream"], sl.p["stream"], 2 * total, True, s_out.cuda_stream)
         sl.ev_out.record(s_out)
@@ -402,20 +598,24 @@ def run_b200(args):
         finish_slot(sl)                                                                    # frame i - NS (same slot) is completely out
         s_in.wait_event(sl.ev_cmp)                                                         # the kernels that read this slot's inputs are done
         if "h2d" not in skip:
-            S.yuv_picture_upload(sl.in_yuv, hp[k][0], W, hp[k][1], W // 2, hp[k][2], W // 2, 1, s_in.cuda_stream)    # H2D: Y + Cb + Cr
+            S.yuv_picture_upload(sl.in_yuv, hp[k][0], W, hp[k][1], W // 2, hp[k][2], W // 2, bps, s_in.cuda_stream)    # H2D: Y + Cb + Cr (2 bytes / sample at 10 bits)
         sl.ev_in.record(s_in)
         cs = cstreams[i % len(cstreams)]                                                   # consecutive frames alternate compute streams, as in the resident loop
         cs.wait_event(sl.ev_in)
         cs.wait_event(sl.ev_out)                                                           # this slot's previous results have left the device
         if "pa" not in skip:
-            sl.pa.build_from_device(sl.p["yint"], sl.in_t[0].shape[1], cs.cuda_stream)     # pad + decimate on the device
-        pipeline(i, sl.pa, sl.in_yuv, sl, cs)
+            if hbd:      # UnPack8BitData (EbPackUnPack_C.c:153): the 8-bit luma PictureAnalysis / ME / OIS work on
+                S.pack_plane_dev(S.PACK_UNPACK8, sl.p["yint"], sl.in_t[0].shape[1], 0, 0, sl.in8.data_ptr(), W, 0, 0, W, H, cs.cuda_stream)
+                sl.pa.build_from_device(sl.in8.data_ptr(), W, cs.cuda_stream)
+            else:
+                sl.pa.build_from_device(sl.p["yint"], sl.in_t[0].shape[1], cs.cuda_stream)     # pad + decimate on the device
+        pipeline(i, sl.pa, sl.in_yuv, sl, cs, resident=False)
         if "pack" not in skip:
             S.tq_pack_coeffs_dev(sl.coeff, p_tq, sl.p["nz"], n_tq, sl.p["stream"], sl.cap, sl.p["off"], cs.cuda_stream)
         sl.ev_cmp.record(cs)
         s_small.wait_event(sl.ev_cmp)
         if "d2h" not in skip:
-            S.copy_async(sl.p["h_small"], sl.p["small"], sl.d_small.numel(), True, s_small.cuda_stream)    # D2H: ME results, TU offsets, nz, SAO stats, OIS
+            S.copy_async(sl.p["h_small"], sl.p["small"], small_total, True, s_small.cuda_stream)    # D2H: ME results, TU offsets, nz, SAO stats, OIS
         sl.ev_small.record(s_small)
         sl.pending = True
         finish_slot(slots[(i + 1) % NS])                                                   # frame i - NS + 1: its offsets arrived long ago, its stream goes out now
@@ -426,11 +626,14 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if ex is not None:
+        args.steps = max(FPG, args.steps // FPG * FPG)                                     # whole GOPs
     for i in range(args.warmup):
-        step_resident(i)
+        step_resident(i, frame_in_gop=i % FPG, parity=0)
     sampler = ClockSampler(local); sampler.start()
     # the timed region (exactly --steps frames between two barriers) is run --repeats times; the MEDIAN run is the one reported
     runs = []
+    round_counter = 0
     for rep in range(max(1, args.repeats)):
         launches0 = S.lib().svtb200_launch_count()
         ev = {n: [] for n in names}
@@ -439,14 +642,25 @@ def run_b200(args):
         t0.record(tstream)
         for cs in cstreams[1:]:
             cs.wait_event(t0)
+        totals = []
         for i in range(args.steps):
-            step_resident(args.warmup + i, ev)
+            step_resident(args.warmup + i, ev, frame_in_gop=i % FPG, parity=round_counter & 1)
+            if ex is not None:
+                totals.append(slots[(args.warmup + i) % len(cstreams)].off_total)
+                if (i + 1) % FPG == 0:
+                    gop_boundary(round_counter, totals); round_counter += 1; totals = []
         for cs in cstreams[1:]:
             e = torch.cuda.Event(); e.record(cs); tstream.wait_event(e)
+        if ex is not None:
+            ex.wait_all()
+            e = torch.cuda.Event(); e.record(comm_stream); tstream.wait_event(e)
         t1.record(tstream)
         barrier()
         runs.append((t0.elapsed_time(t1), {n: [a.elapsed_time(b) for a, b in ev[n]] for n in names}, S.lib().svtb200_launch_count() - launches0))
     sampler.stop_flag = True
+    if ex is not None:
+        for sl in slots:
+            sl.bind(sl.d_out)                                                               # the e2e loop below uses the slots' own spans again
     runs_ms = [r[0] for r in runs]
     ms, stage_ms, launches = sorted(runs, key=lambda r: r[0])[len(runs) // 2]
     # the same stages with nothing else on the GPU (one stream): what each kernel costs alone -- reported next to the timed-region numbers
@@ -478,6 +692,8 @@ def run_b200(args):
         torch.cuda.synchronize()
         res["duplex_each_gbs"] = nbytes * reps / (time.perf_counter() - t0) / 1e9
         return res
+    if world > 1:
+        dist.barrier()                     # every rank probes at the same time: what the link gives when all GPUs of the node copy at once
     pcie = pcie_probe()
 
     for i in range(args.warmup):
@@ -495,21 +711,25 @@ def run_b200(args):
     e2e_s = time.perf_counter() - w0
 
     tms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    link = torch.tensor([pcie["h2d_gbs"], pcie["d2h_gbs"], pcie["duplex_each_gbs"]], dtype=torch.float64, device="cuda")
+    link_all = [link.clone() for _ in range(world)]
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        dist.all_gather(link_all, link)
     ms, e2e_ms = float(tms[0]), float(tms[1])
     if rank == 0:
         peak, peak_src = peaks()
         ctus = N_LCU * args.steps * world
         tot = {n: float(np.sum(v)) for n, v in stage_ms.items()}
-        dom = max(tot, key=tot.get)
-        alg = {"me": ALG["me"] * N_LCU, "ois": ALG["ois"] * N_LCU, "mc": float(np.mean(mc_bytes)), "tq": ALG["tq"] * N_LCU, "dlf": ALG["dlf"] * N_LCU,
-               "h3_copy": 2 * 6144 * N_LCU, "sao_stats": ALG["sao_stats"] * N_LCU, "sao_apply": ALG["sao_apply"] * N_LCU}
+        dom = max((n for n in tot if n not in ("h3_copy",)), key=tot.get)
+        alg = {"me": alg_ctu["me"] * N_LCU, "ois": alg_ctu["ois"] * N_LCU, "mc": float(np.mean(mc_bytes)), "tq": alg_ctu["tq"] * N_LCU, "dlf": alg_ctu["dlf"] * N_LCU,
+               "h3_copy": 2 * 6144 * bps * N_LCU, "sao_stats": alg_ctu["sao_stats"] * N_LCU, "sao_apply": alg_ctu["sao_apply"] * N_LCU, "pack": alg_ctu["pack"] * N_LCU,
+               "pack_coeffs": 2 * 12288 * N_LCU}
         per_stage = {n: {"launch_ms_avg": float(np.mean(v)) if v else None, "launches": len(v), "share_of_step": tot[n] / sum(tot.values()),
                          "achieved_gbs": (alg[n] / (np.mean(v) * 1e-3) / 1e9) if v else None,
                          "frac_of_hbm_peak": (alg[n] / (np.mean(v) * 1e-3) / 1e9 / peak) if v else None} for n, v in stage_ms.items()}
         k_avg_s = float(np.mean(stage_ms[dom])) * 1e-3
-        traffic, traffic_src = ncu_traffic()
+        traffic, traffic_src = ncu_traffic() if CFG_ID == 2 else ({}, None)
         sm_clk = (sampler.summary().get("sm_mhz") or 1965.0) * 1e6
         sad_peak = 148 * 4 * VABSDIFF4_PER_CLK_PER_SMSP * sm_clk
         sad_avg = float(np.mean([me_sad_warp_instr(wl.tl(args.warmup + j)) for j in range(args.steps)]))
@@ -517,21 +737,28 @@ def run_b200(args):
         me_issue = {"bound": "vabsdiff4_issue", "sad_warp_instr_per_launch": sad_avg, "peak_warp_instr_per_s": sad_peak,
                     "floor_ms_per_launch": sad_avg / sad_peak * 1e3, "avg_launch_ms": me_avg_s * 1e3, "frac": sad_avg / sad_peak / me_avg_s,
                     "source": "tools/ubench_pipes.cu: 0.49 VABSDIFF4 / clk / SM sub-partition (profiles/r02_ubench_pipes.txt)"}
-        h2d = W * H * 3 // 2
+        h2d = W * H * 3 // 2 * bps
         d2h = int(np.mean(d2h_bytes))
+        la = np.array([[float(x) for x in t.tolist()] for t in link_all])
+        kernel_names = {"me": "me_picture_kernel", "ois": "ois_picture_kernel", "mc": "mc_batch_kernel<1>" if hbd else "mc_batch8_kernel", "tq": "tq_batch_kernel",
+                        "dlf": "dlf_pass_kernel", "h3_copy": "cudaMemcpy2DAsync (device to device)", "sao_stats": "sao_stats16_kernel" if hbd else "sao_stats_kernel",
+                        "sao_apply": "sao_apply16_kernel" if hbd else "sao_apply_kernel", "pack": "pack_kernel", "pack_coeffs": "tq_pack_scan_kernel + tq_pack_copy_kernel"}
         out = {
             "metric": METRIC, "value": ctus / (ms * 1e-3), "unit": "CTU/s", "fps": ctus / (ms * 1e-3) / N_LCU,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16" if hbd else "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "stages": STAGES,
-                       "l2": "16-frame ring of resident 4K pictures (> 400 MB of planes) > 126 MB L2", "parallelism": f"{args.streams} compute stream(s) per GPU, {world} GPU(s)"},
+                       "l2": f"{RING}-frame ring of resident {W}x{H} pictures (> {RING * W * H * (1.33 + 1.5 * bps) / 1e6:.0f} MB of planes) > 126 MB L2",
+                       "parallelism": f"{args.streams} compute stream(s) per GPU, {world} GPU(s)"},
             "e2e": {"value": ctus / (e2e_ms * 1e-3), "unit": "CTU/s", "fps": ctus / (e2e_ms * 1e-3) / N_LCU,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_link": pcie},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_link": pcie,
+                    "host_link_all_ranks": {"h2d_gbs_min_max": [float(la[:, 0].min()), float(la[:, 0].max())], "d2h_gbs_min_max": [float(la[:, 1].min()), float(la[:, 1].max())],
+                                            "duplex_each_gbs_min_max": [float(la[:, 2].min()), float(la[:, 2].max())]},
+                    "numa_binding_rank0": numa},
             "gpu_launches": int(launches),
             **({"diagnosis_only_e2e_skip": sorted(skip)} if skip else {}),
             "clocks": sampler.summary(),
-            "roofline": {"kernel": {"me": "me_picture_kernel", "ois": "ois_picture_kernel", "mc": "mc_batch8_kernel", "tq": "tq_batch_kernel", "dlf": "dlf_pass_kernel", "h3_copy": "cudaMemcpy2DAsync (device to device)",
-                                    "sao_stats": "sao_stats_kernel", "sao_apply": "sao_apply_kernel"}[dom],
+            "roofline": {"kernel": kernel_names[dom],
                          "bound": "hbm", "achieved": alg[dom] / k_avg_s / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg[dom] / k_avg_s / 1e9 / peak, "traffic": traffic.get(dom), "traffic_source": traffic_src,
                          "peak_source": peak_src,
@@ -545,6 +772,22 @@ def run_b200(args):
             "stages_serial": {n: {"launch_ms_avg": float(np.mean(v)) if v else None, "frac_of_hbm_peak": (alg[n] / (np.mean(v) * 1e-3) / 1e9 / peak) if v else None}
                               for n, v in serial_ms.items()},
         }
+        if CFG_ID == 5:
+            out["density"] = {"streams_per_gpu": args.streams, "streams_total": args.streams * world, "fps_per_stream": out["fps"] / (args.streams * world),
+                              "realtime_streams_at_60fps": out["fps"] / 60.0}
+        if ex is not None:
+            xs = [a.elapsed_time(b) for a, b in ex_stats["ms"]]
+            recv_bytes = ex_stats["bytes"]
+            out["gop_exchange"] = {"frames_per_gop": FPG, "rounds": ex_stats["rounds"], "gops_total": ex_stats["rounds"] * world,
+                                   "bytes_received_by_rank0": int(recv_bytes), "bytes_per_gop_avg": (recv_bytes / max(1, ex_stats["rounds"] * max(1, world - 1))),
+                                   "transfer_ms_avg_on_comm_stream": float(np.mean(xs)) if xs else None,
+                                   "nvlink_gbs_during_transfers": (recv_bytes / 1e9) / (sum(xs) * 1e-3) if (recv_bytes and xs and sum(xs) > 0) else None,
+                                   "rank0_reassembled_coding_order": [g for g, _, _ in ex.assembled] == list(range(len(ex.assembled))),
+                                   "inside_timed_region": True,
+                                   "link_gbs_lower_bound": (recv_bytes / 1e9) / (sum(runs_ms) * 1e-3) if recv_bytes else None,
+                                   "note": "transfers are posted on a communication stream at every GOP boundary, overlap the next GOP's kernels and complete before the "
+                                           "timed region ends; nvlink_gbs_during_transfers = bytes rank 0 received / time between posting and completion on rank 0's "
+                                           "communication stream (includes waiting for the slowest sender's GOP); link_gbs_lower_bound = the same bytes / all timed time"}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_reference(frames=None)
         print(json.dumps(out))
@@ -592,23 +835,32 @@ def cpu_reference(frames):
     # the threads this process may actually run on (affinity mask, cgroup CPU quota), not the box's nominal core count
     host = host_info()
     nthreads = host["usable_threads"]
-    per_thread = 4
+    per_thread = 4 if W <= 4096 else 1
     frames = frames or nthreads * per_thread
     nworkers = min(nthreads, frames)
+    hbd = BITS == 10
+    sfx = "16" if hbd else ""
     wl = Workload(RING, seed=0x5F7C0001)
     pa = [S.HostPaPicture(l) for l in wl.luma]
-    yuv = [S.HostYuvPicture(wl.luma[i], wl.chroma[i][0], wl.chroma[i][1]) for i in range(RING)]
+    if hbd:
+        yuv = [S.HostYuvPicture(wl.luma16(i), *wl.chroma16(i), dtype=np.uint16) for i in range(RING)]
+    else:
+        yuv = [S.HostYuvPicture(wl.luma[i], wl.chroma[i][0], wl.chroma[i][1]) for i in range(RING)]
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    ois_cfg = wl.ois_cfg()
-    for f in (ref.svtref_me_picture_rows, ref.svtref_ois_picture, ref.svtref_mc_batch, ref.svtref_tq_batch, ref.svtref_dlf_picture, ref.svtref_dlf_sao_stats_picture, refsao.svtref_sao_stats_picture,
-              refsao.svtref_sao_apply_picture):
+    ois_cfgs = {tl: wl.ois_cfg(tl) for tl in set(TL_PATTERN)}
+    cap_ois = wl.ois_cap()
+    f_mc, f_tq = getattr(ref, "svtref_mc_batch" + sfx), getattr(ref, "svtref_tq_batch" + sfx)
+    f_dlfsao = getattr(ref, "svtref_dlf_sao_stats_picture" + sfx)
+    f_stats, f_apply = getattr(refsao, "svtref_sao_stats_picture" + sfx), getattr(refsao, "svtref_sao_apply_picture" + sfx)
+    for f in (ref.svtref_me_picture_rows, ref.svtref_ois_picture, f_mc, f_tq, f_dlfsao, f_stats, f_apply):
         f.restype = C.c_int
     flags = (C.c_uint8 * 2)(1, 1)
-    me_cfgs = {tl: S.me_config(W, H, enc_mode=10, temporal_layer=tl, num_lists=2, ref_poc=(0, 16)) for tl in set(TL_PATTERN)}
+    me_cfgs = {tl: wl.me_cfg_tl(tl) for tl in set(TL_PATTERN)}
     ref_pairs = {}
     for i in range(RING):
         ref_pairs[wl.refs(i)] = S.yuv_array([yuv[wl.refs(i)[0]], yuv[wl.refs(i)[1]]])
     n_tq = len(wl.tq_jobs)
+    sample_dt = np.uint16 if hbd else np.uint8
 
     def me(i, res):
         k = i % RING
@@ -627,27 +879,29 @@ def cpu_reference(frames):
     class Worker:
         def __init__(self):
             self.res = np.zeros((N_LCU, 85), dtype=S.ME_PU_RESULT_DTYPE)
-            self.ois_total, self.ois_cand = np.zeros((N_LCU, 85), np.uint8), np.zeros((N_LCU, 85, 1), np.uint32)
-            self.pred = S.HostYuvPicture(np.zeros((H, W), np.uint8), np.zeros((H // 2, W // 2), np.uint8), np.zeros((H // 2, W // 2), np.uint8), replicate=False)
+            self.ois_total, self.ois_cand = np.zeros((N_LCU, 85), np.uint8), np.zeros((N_LCU, 85, cap_ois), np.uint32)
+            self.pred = S.HostYuvPicture(np.zeros((H, W), sample_dt), np.zeros((H // 2, W // 2), sample_dt), np.zeros((H // 2, W // 2), sample_dt), replicate=False,
+                                         dtype=sample_dt)
             self.coeff = S.HostCoeffPicture(W, H)
             self.nz = np.zeros(n_tq, np.uint32)
             self.stats = np.zeros((N_LCU, 3), dtype=S.SAO_STATS_DTYPE)
 
         def frame(self, i):
             k = i % RING
+            tl = wl.tl(i)
             me(i, self.res)
-            assert ref.svtref_ois_picture(C.byref(ois_cfg), C.byref(pa[k].struct.full), vp(self.res), vp(self.ois_total), vp(self.ois_cand), C.c_uint32(1), C.c_int(1)) == 0
+            assert ref.svtref_ois_picture(C.byref(ois_cfgs[tl]), C.byref(pa[k].struct.full), vp(self.res), vp(self.ois_total), vp(self.ois_cand), C.c_uint32(cap_ois), C.c_int(1)) == 0
             jobs = mc_jobs[k]
-            assert ref.svtref_mc_batch(ref_pairs[wl.refs(i)], C.c_int(2), vp(jobs), C.c_int(len(jobs)), C.byref(self.pred.struct), C.c_int(1)) == 0
-            assert ref.svtref_tq_batch(C.byref(yuv[k].struct), C.byref(self.pred.struct), C.byref(self.pred.struct), C.byref(self.coeff.struct), vp(wl.tq_jobs),
-                                       C.c_int(n_tq), vp(self.nz), C.c_int(1), C.c_int(0), C.c_int(n_tq)) == 0
-            if wl.tl(i) == 0:
+            assert f_mc(ref_pairs[wl.refs(i)], C.c_int(2), vp(jobs), C.c_int(len(jobs)), C.byref(self.pred.struct), C.c_int(1)) == 0
+            assert f_tq(C.byref(yuv[k].struct), C.byref(self.pred.struct), C.byref(self.pred.struct), C.byref(self.coeff.struct), vp(wl.tq_jobs),
+                        C.c_int(n_tq), vp(self.nz), C.c_int(1), C.c_int(0), C.c_int(n_tq)) == 0
+            if tl == 0:
                 # the encoder's own order: every LCU's deblocking step followed by that LCU's SAO statistics (EbCodingLoop.c:4604-4635, 4711-4748)
-                assert ref.svtref_dlf_sao_stats_picture(C.byref(self.pred.struct), C.byref(yuv[k].struct), vp(wl.vbs), vp(wl.hbs), vp(wl.qp_array), C.byref(wl.dlf_prm),
-                                                        vp(self.stats), None, C.c_int(1)) == 0
-                assert refsao.svtref_sao_apply_picture(C.byref(self.pred.struct), vp(wl.sao_prm), flags, C.c_int(1)) == 0
+                assert f_dlfsao(C.byref(self.pred.struct), C.byref(yuv[k].struct), vp(wl.vbs), vp(wl.hbs), vp(wl.qp_array), C.byref(wl.dlf_prm),
+                                vp(self.stats), None, C.c_int(1)) == 0
+                assert f_apply(C.byref(self.pred.struct), vp(wl.sao_prm), flags, C.c_int(1)) == 0
             else:
-                assert refsao.svtref_sao_stats_picture(C.byref(yuv[k].struct), C.byref(self.pred.struct), vp(self.stats), C.c_int(1)) == 0
+                assert f_stats(C.byref(yuv[k].struct), C.byref(self.pred.struct), vp(self.stats), C.c_int(1)) == 0
 
     gate = threading.Barrier(nworkers + 1)
     errors = []
@@ -687,10 +941,10 @@ def cpu_reference(frames):
         raise errors[0] if errors else RuntimeError("cpu_reference: the worker barrier broke")
     v = N_LCU * frames / dt
     return {"value": v, "unit": "CTU/s", "fps": v / N_LCU, "cores": nworkers, "kind": "reference", "host": host, "loadavg_after": list(os.getloadavg()),
-            "sample": f"{frames} full 4K frames of the same stages and jobs through the reference's own functions (MotionEstimateLcu, OpenLoopIntraSearchLcu, "
-                      f"EncodePassInterPrediction, EstimateTransform/UnifiedQuantizeInvQuantize/EncodeInvTransform, LCU DLF drivers, SAO gather/apply; "
-                      f"{variant} rows), {nworkers} worker threads with their own buffers, {frames // nworkers} frame(s) each behind a barrier; job lists "
-                      f"prepared beforehand as on the B200 arm"}
+            "sample": f"{frames} full {W}x{H} frames of the same stages and jobs through the reference's own functions (MotionEstimateLcu, OpenLoopIntraSearchLcu, "
+                      f"EncodePassInterPrediction{sfx}, EstimateTransform/UnifiedQuantizeInvQuantize/EncodeInvTransform, the LCU DLF drivers interleaved with the SAO gather "
+                      f"on layer-0 pictures, SAO gather/apply; {variant} rows), {nworkers} worker threads with their own buffers, {frames // nworkers} frame(s) each behind a "
+                      f"barrier; job lists prepared beforehand as on the B200 arm"}
 
 
 def reference_encoder_app(n_frames=32, timeout_s=180):
@@ -705,6 +959,8 @@ def reference_encoder_app(n_frames=32, timeout_s=180):
         import common
         if not os.path.exists(app) or not common.cpu_has("avx512bw"):
             return {"unavailable": "oracle/_ref/SvtHevcEncApp_avx512 missing or no AVX-512 on this host"}
+        if BITS != 8:
+            return {"unavailable": "whole-encoder context run is wired for the 8-bit configurations only"}
         wl = Workload(RING, seed=0x5F7C0001)
         with tempfile.TemporaryDirectory() as d:      # -nb preloads the frames into RAM, so the file system does not matter
             yuv = os.path.join(d, "in.yuv")
@@ -712,7 +968,7 @@ def reference_encoder_app(n_frames=32, timeout_s=180):
                 for i in range(n_frames):
                     k = i % RING
                     f.write(wl.luma[k].tobytes()); f.write(wl.chroma[k][0].tobytes()); f.write(wl.chroma[k][1].tobytes())
-            cmd = [app, "-i", yuv, "-w", str(W), "-h", str(H), "-n", str(n_frames), "-nb", str(n_frames), "-encMode", "10", "-q", "32", "-fps", "60",
+            cmd = [app, "-i", yuv, "-w", str(W), "-h", str(H), "-n", str(n_frames), "-nb", str(n_frames), "-encMode", str(ENC_MODE), "-q", "32", "-fps", str(FPS),
                    "-intra-period", "55", "-irefresh-type", "1", "-b", os.path.join(d, "out.265")]
             t0 = time.perf_counter()
             out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s).stdout
@@ -722,7 +978,7 @@ def reference_encoder_app(n_frames=32, timeout_s=180):
             return {"unavailable": "no 'Average Speed' line in the encoder's output", "tail": out[-300:]}
         fps = float(m.group(1))
         return {"fps": fps, "ctu_per_s": fps * N_LCU, "frames": n_frames, "threads": os.cpu_count(), "wall_s": wall,
-                "what": "SvtHevcEncApp (reference, AVX-512 build) 3840x2160 8-bit, -encMode 10 -q 32 -intra-period 55, frames preloaded (-nb): whole encoder"}
+                "what": f"SvtHevcEncApp (reference, AVX-512 build) {W}x{H} 8-bit, -encMode {ENC_MODE} -q 32 -intra-period 55, frames preloaded (-nb): whole encoder"}
     except Exception as e:      # noqa: BLE001
         return {"unavailable": f"{type(e).__name__}: {e}"}
 
@@ -735,7 +991,7 @@ def run_reference(args):
     cb = cpu_reference(frames=None)
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "CTU/s", "fps": cb["fps"], "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * N_LCU / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "u8", "data": "synthetic", "config": {"workload": WORKLOAD, "stages": STAGES},
+           "dtype": "u16" if BITS == 10 else "u8", "data": "synthetic", "config": {"workload": WORKLOAD, "stages": STAGES},
            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "CTU/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "wall_s": time.perf_counter() - t0}
     if not args.no_encoder_app:
@@ -755,8 +1011,17 @@ def main():
     ap.add_argument("--inflight", type=int, default=5, help="frames in flight in the end-to-end loop (device + pinned host buffers per frame)")
     ap.add_argument("--streams", type=int, default=2, help="compute streams the resident loop spreads consecutive frames over")
     ap.add_argument("--repeats", type=int, default=5, help="the timed region (--steps frames) is run this many times; the median run is reported")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config (1-based index in `configs`): 2 headline (default), 3 10-bit M7 4K, "
+                    "4 8K 10-bit closed GOPs over the GPUs with the NCCL GOP-boundary exchange, 5 1080p stream density")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    c = set_config(args.config)
+    if "--streams" not in sys.argv:
+        args.streams = c["streams"]
+    if args.config == 4 and "--steps" not in sys.argv:
+        args.steps = 32
+    if args.config == 4 and "--repeats" not in sys.argv:
+        args.repeats = 3
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -196,17 +196,25 @@ __global__ void __launch_bounds__(ST_NT) sao_stats16_kernel(const __grid_constan
     const int lw = min(64, A.W - lx * 64) >> sh, lh = min(64, A.H - ly * 64) >> sh;
     const int rs = A.rec[c].stride, ss = A.src[c].stride;
     const uint16_t *r = (const uint16_t *)A.rec[c].p + (size_t)oy * rs + ox, *s = (const uint16_t *)A.src[c].p + (size_t)oy * ss + ox;
+    // H3 (same rule as the 8-bit kernel, pinned for 16-bit planes by port_sao_h3_compose16): the last 4 columns / rows of an LCU with a right / bottom
+    // neighbour are read from the unfiltered reconstruction
+    const int us = A.pre[c].stride;
+    const uint16_t *u = A.pre[c].p ? (const uint16_t *)A.pre[c].p + (size_t)oy * us + ox : nullptr;
+    const bool has_right = (lx + 1) * 64 < A.W, has_bottom = (ly + 1) * 64 < A.H;
+    auto at = [&](int x, int y) -> int {
+        const bool strip = u && ((has_right && x >= lw - 4) || (has_bottom && y >= lh - 4));
+        return strip ? u[(size_t)y * us + x] : r[(size_t)y * rs + x];
+    };
     int *my = s_h + threadIdx.x;
 #pragma unroll 4
     for (int k = 0; k < ST_ROWS; ++k) my[k * ST_NT] = 0;
     const int iw = lw - 2, n_items = (lh - 2) * iw;
     for (int i = threadIdx.x; i < n_items; i += ST_NT) {
         const int y = 1 + i / iw, x = 1 + i % iw;
-        const uint16_t *q = r + (size_t)y * rs + x;
-        const int v = q[0], d = (int)s[(size_t)y * ss + x] - v;
+        const int v = at(x, y), d = (int)s[(size_t)y * ss + x] - v;
         const int add = 65536 + d;       // |sum of <= 31 differences| < 2^15
-        const int e0 = sgn(v, q[-1]) + sgn(v, q[1]) + 2, e1 = sgn(v, q[-rs]) + sgn(v, q[rs]) + 2;
-        const int e2 = sgn(v, q[-rs - 1]) + sgn(v, q[rs + 1]) + 2, e3 = sgn(v, q[-rs + 1]) + sgn(v, q[rs - 1]) + 2;
+        const int e0 = sgn(v, at(x - 1, y)) + sgn(v, at(x + 1, y)) + 2, e1 = sgn(v, at(x, y - 1)) + sgn(v, at(x, y + 1)) + 2;
+        const int e2 = sgn(v, at(x - 1, y - 1)) + sgn(v, at(x + 1, y + 1)) + 2, e3 = sgn(v, at(x + 1, y - 1)) + sgn(v, at(x - 1, y + 1)) + 2;
         my[(0 + e0) * ST_NT] += add; my[(5 + e1) * ST_NT] += add; my[(10 + e2) * ST_NT] += add; my[(15 + e3) * ST_NT] += add;
         my[(20 + min(v >> 5, 31)) * ST_NT] += add;      // (samples above 10 bits -- a caller bug -- must not leave the histogram)
     }
@@ -289,7 +297,6 @@ static int sao_stats_dev_impl(const svtb200_yuv_picture *src, const svtb200_yuv_
     int rc = sao_check(src, recon, "sao_stats_picture");
     if (!rc && unfiltered) rc = sao_check(unfiltered, recon, "sao_stats_picture_h3");
     if (rc || (rc = ensure_device())) return rc;
-    if (unfiltered && hbd) { set_error("sao_stats_picture_h3: 16-bit planes not supported yet"); return SVTB200_ERR_UNSUPPORTED; }
     StatsArgs A;
     for (int k = 0; k < 3; ++k) {
         A.pre[k] = {nullptr, 0};
@@ -415,6 +422,17 @@ int svtb200_sao_apply_picture(const svtb200_yuv_picture *in, const svtb200_yuv_p
 { return sao_apply_impl(in, out, lcu_params, sao_flag, false); }
 int svtb200_sao_stats_picture16_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out_dev, void *cuda_stream)
 { return sao_stats_dev_impl(src, recon, out_dev, cuda_stream, true); }
+int svtb200_sao_stats_picture16_h3_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *deblocked, const svtb200_yuv_picture *unfiltered, svtb200_sao_stats *out_dev,
+                                       void *cuda_stream)
+{
+    if (!unfiltered) { set_error("sao_stats_picture16_h3_dev: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    return sao_stats_dev_impl(src, deblocked, out_dev, cuda_stream, true, unfiltered);
+}
+int svtb200_sao_stats_picture16_h3(const svtb200_yuv_picture *src, const svtb200_yuv_picture *deblocked, const svtb200_yuv_picture *unfiltered, svtb200_sao_stats *out)
+{
+    if (!unfiltered) { set_error("sao_stats_picture16_h3: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    return sao_stats_impl(src, deblocked, out, true, unfiltered);
+}
 int svtb200_sao_stats_picture16(const svtb200_yuv_picture *src, const svtb200_yuv_picture *recon, svtb200_sao_stats *out) { return sao_stats_impl(src, recon, out, true); }
 int svtb200_sao_apply_picture16_dev(const svtb200_yuv_picture *in, const svtb200_yuv_picture *out, const svtb200_sao_params *lcu_params_dev, const uint8_t sao_flag[2], void *cuda_stream)
 { return sao_apply_dev_impl(in, out, lcu_params_dev, sao_flag, cuda_stream, true); }

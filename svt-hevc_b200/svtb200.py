@@ -544,6 +544,40 @@ def sao_apply_picture_dev(inp, out, prm_ptr, flags=(1, 1), stream=0):
     check(lib().svtb200_sao_apply_picture_dev(C.byref(inp), C.byref(out), C.c_void_p(prm_ptr), (C.c_uint8 * 2)(*flags), C.c_void_p(stream)))
 
 
+# ---- 16-bit sample planes (10-bit video): device-picture entry points of configs 3 / 4 -----------------------------------------------------
+def mc_batch16_dev(ref_structs, jobs_ptr, n_jobs, dst_struct, stream=0):
+    arr = ref_structs if isinstance(ref_structs, C.Array) else yuv_struct_array(ref_structs)
+    check(lib().svtb200_mc_batch16_dev(arr, C.c_int(len(ref_structs)), C.c_void_p(jobs_ptr), C.c_int(n_jobs), C.byref(dst_struct), C.c_void_p(stream)))
+
+
+def tq_batch16_dev(src, pred, recon, coeff_struct, jobs_ptr, n_jobs, nz_ptr, stream=0):
+    check(lib().svtb200_tq_batch16_dev(C.byref(src), C.byref(pred), C.byref(recon), C.byref(coeff_struct), C.c_void_p(jobs_ptr), C.c_int(n_jobs),
+                                       C.c_void_p(nz_ptr), C.c_void_p(stream)))
+
+
+def dlf_picture16_dev(recon, vbs_ptr, hbs_ptr, qp_ptr, prm, stream=0):
+    check(lib().svtb200_dlf_picture16_dev(C.byref(recon), C.c_void_p(vbs_ptr), C.c_void_p(hbs_ptr), C.c_void_p(qp_ptr), C.byref(prm), C.c_void_p(stream)))
+
+
+def sao_stats_picture16_dev(src, recon, out_ptr, stream=0):
+    check(lib().svtb200_sao_stats_picture16_dev(C.byref(src), C.byref(recon), C.c_void_p(out_ptr), C.c_void_p(stream)))
+
+
+def sao_stats_picture16_h3_dev(src, deblocked, unfiltered, out_ptr, stream=0):
+    check(lib().svtb200_sao_stats_picture16_h3_dev(C.byref(src), C.byref(deblocked), C.byref(unfiltered), C.c_void_p(out_ptr), C.c_void_p(stream)))
+
+
+def sao_stats_picture16_h3(src, deblocked, unfiltered):
+    n = ((deblocked.width + 63) // 64) * ((deblocked.height + 63) // 64)
+    out = np.zeros((n, 3), dtype=SAO_STATS_DTYPE)
+    check(lib().svtb200_sao_stats_picture16_h3(C.byref(src.struct), C.byref(deblocked.struct), C.byref(unfiltered.struct), _u8p(out)))
+    return out
+
+
+def sao_apply_picture16_dev(inp, out, prm_ptr, flags=(1, 1), stream=0):
+    check(lib().svtb200_sao_apply_picture16_dev(C.byref(inp), C.byref(out), C.c_void_p(prm_ptr), (C.c_uint8 * 2)(*flags), C.c_void_p(stream)))
+
+
 # ---- 10-bit pack / unpack -----------------------------------------------------------
 PACK_MSB, PACK_COMPRESSED_MSB, PACK_CPACK, PACK_UNPACK, PACK_UNPACK8, PACK_UNPACK_AVG = range(6)
 
