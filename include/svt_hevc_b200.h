@@ -289,6 +289,38 @@ int svtb200_tq_batch16_dev(const svtb200_yuv_picture *src, const svtb200_yuv_pic
 int svtb200_tq_pack_coeffs_dev(const svtb200_coeff_picture *coeff_dev, const svtb200_tq_job *jobs_dev, const uint32_t *nz_counts_dev, int n_jobs,
                                int16_t *stream_dev, uint32_t stream_capacity, uint32_t *offsets_dev, void *cuda_stream);
 
+/* ---- distortion leaves of mode decision (the first bricks of row N2) ----------------------------------------------
+ * The full loop evaluates them per candidate block; here they are batched, one job per block, one result per job.
+ *   spatial_distortion   SpatialFullDistortionKernel (C_DEFAULT/EbPictureOperators_C.c:697; table Codec/EbPictureOperators.h:633; callers
+ *                        Codec/EbFullLoop.c:384-392,950-975 and the SSD refinement Codec/EbMotionEstimation.c:799-979): sum (input - recon)^2
+ *   full_distortion      FullDistortionKernel_32bit / ..Intra_32bit / ..CbfZero_32bit (C_DEFAULT/EbPictureOperators_C.c:385-475; table
+ *                        Codec/EbPictureOperators.h:520-606): out[2j] / out[2j+1] = distortionResult[0] / [1]; 32-bit wrapping sums like both rows
+ *   satd                 Compute8x8Satd / Compute4x4Satd summed over the block's 8x8 / 4x4 units (C_DEFAULT/EbPictureOperators_C.c:482,
+ *                        Codec/EbHmCode.c:41; drivers Codec/EbProductCodingLoop.c:2642) on the residual src - pred
+ * Blocks lie inside the picture; origin / dimensions are multiples of 4 (8 for SATD_8X8 jobs); coefficient jobs need even x. */
+#define SVTB200_FULLDIST_DEFAULT  0   /* [0] = sum (coeff - recon)^2, [1] = sum coeff^2 */
+#define SVTB200_FULLDIST_INTRA    1   /* [0] = [1] = sum (coeff - recon)^2              */
+#define SVTB200_FULLDIST_CBF_ZERO 2   /* [0] = [1] = sum coeff^2                        */
+#define SVTB200_SATD_8X8 0
+#define SVTB200_SATD_4X4 1
+typedef struct svtb200_dist_job {
+    uint16_t x, y;          /* block origin in samples of its own plane */
+    uint8_t  plane;         /* 0 = Y, 1 = Cb, 2 = Cr                     */
+    uint8_t  width, height; /* 4 .. 64                                   */
+    uint8_t  kind;          /* SVTB200_FULLDIST_* / SVTB200_SATD_* (ignored by spatial_distortion) */
+} svtb200_dist_job;         /* 8 bytes */
+int svtb200_spatial_distortion_batch(const svtb200_yuv_picture *input, const svtb200_yuv_picture *recon, const svtb200_dist_job *jobs, int n_jobs,
+                                     uint64_t *out);
+int svtb200_spatial_distortion_batch_dev(const svtb200_yuv_picture *input, const svtb200_yuv_picture *recon, const svtb200_dist_job *jobs_dev, int n_jobs,
+                                         uint64_t *out_dev, void *cuda_stream);
+int svtb200_full_distortion_batch(const svtb200_coeff_picture *coeff, const svtb200_coeff_picture *recon_coeff, uint32_t width, uint32_t height,
+                                  const svtb200_dist_job *jobs, int n_jobs, uint64_t *out);
+int svtb200_full_distortion_batch_dev(const svtb200_coeff_picture *coeff, const svtb200_coeff_picture *recon_coeff, const svtb200_dist_job *jobs_dev,
+                                      int n_jobs, uint64_t *out_dev, void *cuda_stream);
+int svtb200_satd_batch(const svtb200_yuv_picture *src, const svtb200_yuv_picture *pred, const svtb200_dist_job *jobs, int n_jobs, uint64_t *out);
+int svtb200_satd_batch_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *pred, const svtb200_dist_job *jobs_dev, int n_jobs,
+                           uint64_t *out_dev, void *cuda_stream);
+
 /* Leaf entry points (reference prototypes; host pointers). */
 /* EstimateTransform, Codec/EbTransforms.c:3268 (EB_TRANSFORM_FUNC tables EbTransforms.h:339-472) */
 int svtb200_EstimateTransform(const int16_t *residualBuffer, uint32_t residualStride, int16_t *coeffBuffer, uint32_t coeffStride,

@@ -471,6 +471,98 @@ static int intra_launch(const IntraArgs &A, cudaStream_t st, bool hbd = false)
     return SVTB200_OK;
 }
 
+// ---- DC-only open-loop search (OpenLoopIntraDC, EbMotionEstimation.c:4964): the path every non-I picture of M10 takes ---------------------------------
+// (limitOisToDcModeFlag, EbPictureDecisionProcess.c:417-422; 8x8 CUs skipped).  One CTA of four warps per LCU, a warp per 32x32 quadrant, a lane per
+// row: the row's eight source words feed the 32x32 CU (flat DC) and the two 16x16 CUs it crosses (DC with the [1 3] edge filter on their first row /
+// column, IntraModeDCLuma), neighbour sums and SADs reduced with shuffles.  Same availability rule as UpdateNeighborSamplesArrayOpenLoop (:5222):
+// neighbours outside the picture read 128, CUs crossing the picture edge are skipped.  Needs a padded plane (interior 4-byte aligned, >= 1 sample around).
+constexpr int DCK_P = 80;      // tile pitch: byte 15 = column -1, bytes 16..79 = columns 0..63; row 0 = picture row -1
+__global__ void __launch_bounds__(128) ois_dc_kernel(const __grid_constant__ OisArgs A)
+{
+    __shared__ __align__(16) uint8_t s_t[65 * DCK_P];
+    const int W = A.cfg.pic_width, H = A.cfg.pic_height;
+    const int lcu = blockIdx.x, ox = (lcu % A.lcu_cols) * 64, oy = (lcu / A.lcu_cols) * 64;
+    // stage rows -1..63: 16 interior words + the left apron byte per row (the plane is padded: every address exists)
+    for (int i = threadIdx.x; i < 65 * 17; i += 128) {
+        const int r = i / 17, c = i - r * 17;
+        const uint8_t *g = A.src + (ptrdiff_t)(oy + r - 1) * A.stride + ox;
+        if (c < 16) ((uint32_t *)(s_t + r * DCK_P + 16))[c] = __ldg((const uint32_t *)g + c);
+        else s_t[r * DCK_P + 15] = __ldg(g - 1);
+    }
+    uint8_t *total = A.total + (size_t)lcu * 85;
+    uint32_t *cand = A.cand + (size_t)lcu * 85 * A.cap;
+    for (int i = threadIdx.x; i < 85; i += 128) total[i] = 0;           // every slot of this LCU is defined: zero first, then the reference's writes
+    for (int i = threadIdx.x; i < 85 * A.cap; i += 128) cand[i] = 0;
+    __syncthreads();
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cx = (w & 1) * 32, cy = (w >> 1) * 32, x = ox + cx, y = oy + cy;
+    const uint8_t *rowp = s_t + (cy + lane + 1) * DCK_P + 16 + cx;
+    const uint4 wa = *(const uint4 *)rowp, wb = *(const uint4 *)(rowp + 16);
+    const uint32_t sw[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+    // ---- 32x32 CU ----
+    {
+        const int top = (y != 0 && x + lane < W) ? s_t[cy * DCK_P + 16 + cx + lane] : 128;
+        const int left = (x != 0 && y + lane < H) ? s_t[(cy + lane + 1) * DCK_P + 15 + cx] : 128;
+        const int dc = (int)((warp_sum((uint32_t)(top + left)) + 32) >> 6);
+        const uint32_t dc4 = (uint32_t)dc * 0x01010101u;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc = vsad4_acc(sw[k], dc4, acc);
+        acc = warp_sum(acc);
+        if (lane == 0 && x + 32 <= W && y + 32 <= H) { const int cu = 1 + w; cand[(size_t)cu * A.cap] = ois_pack(acc, true, 1); total[cu] = 1; }
+    }
+    // ---- the four 16x16 CUs of the quadrant: lanes 0-15 rows of the upper pair, 16-31 of the lower pair; words 0-3 -> left CU, 4-7 -> right CU ----
+    {
+        const int qy = lane >> 4, cr = lane & 15, y16 = y + 16 * qy;
+        uint32_t sad[2];
+#pragma unroll
+        for (int qx = 0; qx < 2; ++qx) {
+            const int x16 = x + 16 * qx;
+            const int tcol = 16 + cx + 16 * qx, trow = cy + 16 * qy;                       // tile coordinates of the CU's sample (0, 0): row trow + 1
+            const int top = (y16 != 0 && x16 + cr < W) ? s_t[trow * DCK_P + tcol + cr] : 128;
+            const int left = (x16 != 0 && y16 + cr < H) ? s_t[(trow + cr + 1) * DCK_P + tcol - 1] : 128;
+            uint32_t ssum = (uint32_t)(top + left);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);      // over the 16 lanes of the CU
+            const int dc = (int)((ssum + 16) >> 5);
+            const uint32_t dc4 = (uint32_t)dc * 0x01010101u;
+            uint32_t p[4] = {dc4, dc4, dc4, dc4};
+            if (cr == 0) {      // first row: (top[x] + 3 dc + 2) >> 2, corner (left[0] + top[0] + 2 dc + 2) >> 2 (IntraModeDCLuma edge filter, N < 32)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t wv = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int xx = 4 * k + b;
+                        const int t = (y16 != 0 && x16 + xx < W) ? s_t[trow * DCK_P + tcol + xx] : 128;
+                        const int v = xx == 0 ? (left + t + 2 * dc + 2) >> 2 : (t + 3 * dc + 2) >> 2;
+                        wv |= (uint32_t)v << (8 * b);
+                    }
+                    p[k] = wv;
+                }
+            } else {
+                p[0] = (dc4 & 0xffffff00u) | (uint32_t)((left + 3 * dc + 2) >> 2);       // first column
+            }
+            uint32_t acc = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc = vsad4_acc(sw[4 * qx + k], p[k], acc);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            sad[qx] = acc;
+        }
+        if (cr == 0) {
+#pragma unroll
+            for (int qx = 0; qx < 2; ++qx) {
+                const int x16 = x + 16 * qx;
+                if (x16 + 16 <= W && y16 + 16 <= H) {
+                    const int cu = 5 + ((cy >> 4) + qy) * 4 + (cx >> 4) + qx;
+                    cand[(size_t)cu * A.cap] = ois_pack(sad[qx], true, 1); total[cu] = 1;
+                }
+            }
+        }
+    }
+}
+
 static int ois_check(const svtb200_ois_config *cfg, const svtb200_plane *src, const void *me, const void *total, const void *cand, uint32_t cap, const char *who)
 {
     if (!cfg || !src || !src->buf || !total || !cand) { set_error("%s: null argument", who); return SVTB200_ERR_BAD_ARG; }
@@ -493,7 +585,10 @@ static int ois_launch(const svtb200_ois_config &cfg, const uint8_t *src00, int s
     A.lcu_cols = (cfg.pic_width + 63) / 64;
     A.padded = padded;
     const int n_lcu = A.lcu_cols * ((cfg.pic_height + 63) / 64);
-    ois_picture_kernel<<<n_lcu, OIS_NT, 0, st>>>(A);
+    // non-I pictures limited to DC without 8x8 CUs (every inter picture of M10) on a padded, word-aligned plane: the dedicated kernel
+    const bool dc_only = cfg.slice_type != 2 && !cfg.ois_kernel_level && cfg.limit_ois_to_dc_mode && (cfg.skip_ois_8x8 || cfg.cu8x8_mode == 1);
+    if (dc_only && padded && (((uintptr_t)src00 | (uintptr_t)stride) & 3) == 0) ois_dc_kernel<<<n_lcu, 128, 0, st>>>(A);
+    else ois_picture_kernel<<<n_lcu, OIS_NT, 0, st>>>(A);
     SVTB200_COUNT_LAUNCH();
     SVTB200_CUDA_TRY(cudaGetLastError());
     return SVTB200_OK;

@@ -124,6 +124,178 @@ __global__ void __launch_bounds__(ST_NT) sao_stats_kernel(const __grid_constant_
     }
 }
 
+// ---- round-2 statistics kernel (8-bit): ONE CTA PER LCU, all three components; a thread owns a 4-sample-wide, 8-row-tall strip ----------------------------
+// The per-sample work of GatherSaoStatisticsLcuLossy_62x62 is five histogram updates (four edge types + the band).  Here the edge-type updates never touch
+// memory: a thread keeps, per edge type and category, a packed byte counter (<= 8 rows: no carry between bytes) and a 32-bit difference sum, fed by 0/1
+// byte masks -- the category masks are LOP3 combinations of the byte compare masks (v < a, v > a, v < b, v > b), the difference sums one DP4A each.  The
+// vertical compares of a row serve the next row (sign(v[y] - v[y+1]) = -sign(v[y+1] - v[y])), and the three rows a sample needs live in registers as the
+// strip walks down.  Only the band-offset bins keep the thread-private shared-memory histogram.  Warps 0-3: luma (16 word columns x 8 strips), warp 4: Cb,
+// warp 5: Cr (8 word columns x 4 strips).  Same 62 x 62 interior rule, same H3 composition, same output layout as sao_stats_kernel.
+constexpr int ST2_NT = 192;
+// 0xff where the byte's top bit is set, else 0: PRMT with the sign-replicate bit of every selector nibble (__byte_perm() masks that bit off, hence the PTX)
+__device__ __forceinline__ uint32_t msb_mask(uint32_t w)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, 0, 0xba98;" : "=r"(d) : "r"(w));
+    return d;
+}
+// byte masks (0xff / 0x00) of a > b and a < b for unsigned bytes: the carry-free per-byte difference trick, both directions from shared terms
+__device__ __forceinline__ void cmp4(uint32_t a, uint32_t b, uint32_t &gt, uint32_t &lt)
+{
+    // a > b  <=>  msb of ((b & ~a) | (~(b ^ a) & (b - a per byte, 7-bit))) ...: compute the 7-bit differences without inter-byte borrow
+    const uint32_t al = a | 0x80808080u, bl = b | 0x80808080u, ah = a & 0x7f7f7f7fu, bh = b & 0x7f7f7f7fu;
+    const uint32_t dab = al - bh, dba = bl - ah;              // per byte: bit 7 = (a7 >= b7) / (b7 >= a7) on the low 7 bits
+    // a < b: msb(a) < msb(b), or equal msbs and low7(a) < low7(b) (bit 7 of dab clear)
+    const uint32_t x = a ^ b;
+    lt = msb_mask(((~a & b) & x) | (~x & ~dab));
+    gt = msb_mask(((a & ~b) & x) | (~x & ~dba));
+}
+struct EoAcc { uint32_t cnt[4]; int sum[4]; };      // categories 0, 1, 3, 4 of one edge type
+__device__ __forceinline__ void eo_accumulate(EoAcc &A, uint32_t la, uint32_t ga, uint32_t lb, uint32_t gb, uint32_t valid01, uint32_t d)
+{
+    // category masks as 0/1 bytes: 0: v < a & v < b; 4: v > a & v > b; 1: exactly one '<' and no '>'; 3: exactly one '>' and no '<'
+    const uint32_t k0 = la & lb & valid01, k4 = ga & gb & valid01;
+    const uint32_t k1 = (la ^ lb) & ~(ga | gb) & valid01, k3 = (ga ^ gb) & ~(la | lb) & valid01;
+    A.cnt[0] += k0; A.cnt[1] += k1; A.cnt[2] += k3; A.cnt[3] += k4;
+    A.sum[0] = dp4a_ss(d, k0, A.sum[0]); A.sum[1] = dp4a_ss(d, k1, A.sum[1]); A.sum[2] = dp4a_ss(d, k3, A.sum[2]); A.sum[3] = dp4a_ss(d, k4, A.sum[3]);
+}
+
+__global__ void __launch_bounds__(ST2_NT) sao_stats2_kernel(const __grid_constant__ StatsArgs A)
+{
+    // reconstructed blocks of the three components with a one-word margin on every side: luma 66 rows x 72 bytes, chroma 34 rows x 40 bytes each
+    __shared__ __align__(16) uint8_t s_y[66 * 72];
+    __shared__ __align__(16) uint8_t s_c[2][34 * 40];
+    __shared__ int s_bo[32 * ST2_NT];            // thread-private band histograms, word = (count << 16) + sum(diff)
+    __shared__ int s_eo[3][32];                  // per component: 4 types x (4 counts, 4 sums)
+    const int lcu = blockIdx.x, lx = lcu % A.cols, ly = lcu / A.cols;
+    const int wid = threadIdx.x >> 5;
+    // ---- stage the three blocks (H3 composition included) ----
+    for (int c = 0; c < 3; ++c) {
+        const int sh = c ? 1 : 0;
+        const int ox = (lx * 64) >> sh, oy = (ly * 64) >> sh;
+        const int lw = min(64, A.W - lx * 64) >> sh, lh = min(64, A.H - ly * 64) >> sh;
+        const int pitch = c ? 40 : 72;
+        uint8_t *dst = c ? s_c[c - 1] : s_y;
+        const uint8_t *r = A.rec[c].p + (size_t)oy * A.rec[c].stride + ox;
+        const uint8_t *u = A.pre[c].p ? A.pre[c].p + (size_t)oy * A.pre[c].stride + ox : nullptr;
+        const bool has_right = (lx + 1) * 64 < A.W, has_bottom = (ly + 1) * 64 < A.H;
+        const int wpr = lw >> 2;
+        const SmallDiv d_wpr = mk_div(wpr);
+        for (int i = threadIdx.x; i < lh * wpr; i += ST2_NT) {
+            const int y = udiv(i, d_wpr), x4 = i - y * wpr;
+            const bool strip = u && ((has_right && 4 * x4 >= lw - 4) || (has_bottom && y >= lh - 4));
+            ((uint32_t *)(dst + (y + 1) * pitch))[1 + x4] = strip ? *(const uint32_t *)(u + (size_t)y * A.pre[c].stride + 4 * x4)
+                                                                : *(const uint32_t *)(r + (size_t)y * A.rec[c].stride + 4 * x4);
+        }
+    }
+    int *mybo = s_bo + threadIdx.x;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) mybo[k * ST2_NT] = 0;
+    if (threadIdx.x < 96) s_eo[threadIdx.x >> 5][threadIdx.x & 31] = 0;
+    __syncthreads();
+    // ---- strips ----
+    const int c = wid < 4 ? 0 : wid - 3, sh = c ? 1 : 0;
+    const int ox = (lx * 64) >> sh, oy = (ly * 64) >> sh;
+    const int lw = min(64, A.W - lx * 64) >> sh, lh = min(64, A.H - ly * 64) >> sh;
+    const int pitch = c ? 40 : 72, wpr = lw >> 2;
+    const uint8_t *blk = c ? s_c[c - 1] : s_y;
+    const int t = c ? (int)(threadIdx.x & 31) : (int)threadIdx.x;          // thread index within the component
+    const int xw = c ? (t & 7) : (t & 15), sy = c ? (t >> 3) : (t >> 4);   // word column, strip index (8 rows each)
+    EoAcc E[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { E[k].cnt[q] = 0; E[k].sum[q] = 0; }
+    if (xw < wpr && sy * 8 < lh) {
+        const uint8_t *src = A.src[c].p + (size_t)oy * A.src[c].stride + ox;
+        const int y0 = sy * 8, y1 = min(lh, y0 + 8);
+        // rolling window: (left, centre, right) words of rows y - 1, y, y + 1 (tile row index = y + 1, word index = xw + 1)
+        const uint32_t *row = (const uint32_t *)(blk + y0 * pitch) + xw;             // row y0 - 1
+        const int p4 = pitch >> 2;
+        uint32_t uL = row[0], uC = row[1], uR = row[2];
+        uint32_t cL = row[p4], cC = row[p4 + 1], cR = row[p4 + 2];
+        // compares of row y against its upper neighbours come from the previous row's compares against ITS lower neighbours
+        uint32_t gU, lU, gUL, lUL, gUR, lUR;
+        {
+            const uint32_t UL = __funnelshift_r(uL, uC, 24), UR = __funnelshift_r(uC, uR, 8);
+            cmp4(cC, uC, gU, lU); cmp4(cC, UL, gUL, lUL); cmp4(cC, UR, gUR, lUR);
+        }
+        uint32_t colmask = 0xffffffffu;                                               // 62 x 62 interior: the first / last sample of a row never counts
+        if (xw == 0) colmask &= 0xffffff00u;
+        if (xw == wpr - 1) colmask &= 0x00ffffffu;
+        for (int y = y0; y < y1; ++y) {
+            const uint32_t *nr = (const uint32_t *)(blk + (y + 2) * pitch) + xw;      // row y + 1
+            const uint32_t dL = nr[0], dC = nr[1], dR = nr[2];
+            const uint32_t v = cC;
+            const uint32_t Lw = __funnelshift_r(cL, cC, 24), Rw = __funnelshift_r(cC, cR, 8);
+            const uint32_t DL = __funnelshift_r(dL, dC, 24), DR = __funnelshift_r(dC, dR, 8);
+            uint32_t gL, lL, gR, lR, gD, lD, gDL, lDL, gDR, lDR;
+            cmp4(v, Lw, gL, lL); cmp4(v, Rw, gR, lR); cmp4(v, dC, gD, lD); cmp4(v, DL, gDL, lDL); cmp4(v, DR, gDR, lDR);
+            if (y >= 1 && y < lh - 1) {
+                const uint32_t valid01 = colmask & 0x01010101u;
+                const uint32_t sv = *(const uint32_t *)(src + (size_t)y * A.src[c].stride + 4 * xw);
+                // diff = clipToSigned8Bit(src - rec), packed s8
+                const uint32_t dpos = __vminu4(__vsubus4(sv, v), 0x7f7f7f7fu), dneg = __vminu4(__vsubus4(v, sv), 0x80808080u);
+                const uint32_t d = __vsub4(dpos, dneg);
+                eo_accumulate(E[0], lL, gL, lR, gR, valid01, d);         // EO-0: left / right
+                eo_accumulate(E[1], lU, gU, lD, gD, valid01, d);         // EO-90: up / down
+                eo_accumulate(E[2], lUL, gUL, lDR, gDR, valid01, d);     // EO-135: up-left / down-right
+                eo_accumulate(E[3], lUR, gUR, lDL, gDL, valid01, d);     // EO-45: up-right / down-left
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    if (!((colmask >> (8 * b)) & 1)) continue;
+                    mybo[((v >> (8 * b + 3)) & 31) * ST2_NT] += 65536 + (int)(signed char)(d >> (8 * b));
+                }
+            }
+            // next row: its upper compares are this row's lower compares mirrored (v[y+1] > v[y] <=> v[y] < v[y+1]); the diagonals swap sides with the
+            // one-sample shift: (y+1, x) vs (y, x-1) [its UL] is the DR compare of (y, x-1), which lives in the left neighbour's word -- recomputed below
+            gU = lD; lU = gD;
+            uL = cL; uC = cC; uR = cR; cL = dL; cC = dC; cR = dR;
+            {
+                const uint32_t UL = __funnelshift_r(uL, uC, 24), UR = __funnelshift_r(uC, uR, 8);
+                cmp4(cC, UL, gUL, lUL); cmp4(cC, UR, gUR, lUR);
+            }
+        }
+    }
+    // ---- reduce: byte counters -> counts, warp sums, one shared-memory atomic per (warp, bin) ----
+    {
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int cn = __reduce_add_sync(0xffffffffu, dp4a_ss(E[k].cnt[q], 0x01010101u, 0));
+                const int sm = __reduce_add_sync(0xffffffffu, E[k].sum[q]);
+                if (lane == 0) { atomicAdd(&s_eo[c][k * 8 + q], cn); atomicAdd(&s_eo[c][k * 8 + 4 + q], sm); }
+            }
+    }
+    __syncthreads();
+    // ---- outputs: per component, EO slots 0..3 <- categories 0, 1, 3, 4 (slot 4 = 0), then the 32 bands ----
+    if (threadIdx.x < 96) {
+        const int cc = threadIdx.x >> 5, k = threadIdx.x & 31;
+        svtb200_sao_stats *o = A.out + (size_t)lcu * 3 + cc;
+        const int tt = k >> 3, q = k & 7;
+        if (q < 4) o->eo_count[tt][q] = (uint16_t)s_eo[cc][k]; else o->eo_diff[tt][q - 4] = s_eo[cc][k];
+        if (k < 4) { o->eo_diff[k][4] = 0; o->eo_count[k][4] = 0; }
+    }
+    {
+        // band histograms: component cc owns the thread columns [first, first + n): luma 0..127, Cb 128..159, Cr 160..191
+        const int lane = threadIdx.x & 31;
+        for (int item = wid; item < 96; item += ST2_NT / 32) {
+            const int cc = item >> 5, band = item & 31;
+            const int first = cc == 0 ? 0 : 96 + 32 * cc, n = cc == 0 ? 128 : 32;
+            int dsum = 0, csum = 0;
+            for (int q = lane; q < n; q += 32) {
+                const int w = s_bo[band * ST2_NT + first + q], dd = (int)(short)(w & 0xffff);
+                dsum += dd; csum += (w - dd) >> 16;
+            }
+            dsum = __reduce_add_sync(0xffffffffu, dsum);
+            csum = __reduce_add_sync(0xffffffffu, csum);
+            if (lane == 0) { svtb200_sao_stats *o = A.out + (size_t)lcu * 3 + cc; o->bo_diff[band] = dsum; o->bo_count[band] = (uint16_t)csum; }
+        }
+    }
+}
+
 struct ApplyArgs {
     PlaneRO in[3];
     uint8_t *out[3];
@@ -139,20 +311,23 @@ __global__ void __launch_bounds__(256) sao_apply_kernel(const __grid_constant__ 
     const int c = blockIdx.z, sh = c ? 1 : 0, pw = A.W >> sh, ph = A.H >> sh;
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
     if (x0 >= pw || y >= ph) return;
-    const svtb200_sao_params p = A.prm[(size_t)((y << sh) >> 6) * A.cols + ((x0 << sh) >> 6)];   // 4 samples never straddle an LCU
-    const int t = A.flag[c ? 1 : 0] ? p.type[c ? 1 : 0] : 0;
+    const svtb200_sao_params *pp = A.prm + (size_t)((y << sh) >> 6) * A.cols + ((x0 << sh) >> 6);   // 4 samples never straddle an LCU
+    const int t = A.flag[c ? 1 : 0] ? pp->type[c ? 1 : 0] : 0;
+    // the four offsets of this plane in registers (a struct copy indexed by the class would live in local memory)
+    const int8_t *po = pp->offset[c];
+    const int o0 = po[0], o1 = po[1], o2 = po[2], o3 = po[3];
     const int is = A.in[c].stride;
     const uint8_t *row = A.in[c].p + (size_t)y * is + x0;
     const uint32_t cur = *(const uint32_t *)row;
     uint32_t res = cur;
     if (t == 5) {
-        const int pos = p.band_position[c];
+        const int pos = pp->band_position[c];
         res = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             int v = (cur >> (8 * k)) & 255;
             const int b = (v >> 3) - pos;
-            if (b >= 0 && b <= 3) v = min(max(v + p.offset[c][b], 0), 255);
+            if (b >= 0 && b <= 3) v = min(max(v + (b == 0 ? o0 : b == 1 ? o1 : b == 2 ? o2 : o3), 0), 255);
             res |= (uint32_t)v << (8 * k);
         }
     } else if (t >= 1 && t <= 4) {
@@ -173,7 +348,7 @@ __global__ void __launch_bounds__(256) sao_apply_kernel(const __grid_constant__ 
                 const int x = x0 + k;
                 if (!((t != 2) && (x == 0 || x == pw - 1))) {
                     const int idx = sgn(v, (int)((na >> (8 * k)) & 255)) + sgn(v, (int)((nb >> (8 * k)) & 255)) + 2;
-                    const int off = idx == 0 ? p.offset[c][0] : idx == 1 ? p.offset[c][1] : idx == 3 ? p.offset[c][2] : idx == 4 ? p.offset[c][3] : 0;
+                    const int off = idx == 0 ? o0 : idx == 1 ? o1 : idx == 3 ? o2 : idx == 4 ? o3 : 0;
                     v = min(max(v + off, 0), 255);
                 }
                 res |= (uint32_t)v << (8 * k);
@@ -247,20 +422,23 @@ __global__ void __launch_bounds__(256) sao_apply16_kernel(const __grid_constant_
     const int c = blockIdx.z, sh = c ? 1 : 0, pw = A.W >> sh, ph = A.H >> sh;
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= pw || y >= ph) return;
-    const svtb200_sao_params p = A.prm[(size_t)((y << sh) >> 6) * A.cols + ((x << sh) >> 6)];
-    const int t = A.flag[c ? 1 : 0] ? p.type[c ? 1 : 0] : 0;
+    const svtb200_sao_params *pp = A.prm + (size_t)((y << sh) >> 6) * A.cols + ((x << sh) >> 6);
+    const int t = A.flag[c ? 1 : 0] ? pp->type[c ? 1 : 0] : 0;
+    // the four offsets of this plane in registers (a struct copy indexed by the class would live in local memory)
+    const int8_t *po = pp->offset[c];
+    const int o0 = po[0], o1 = po[1], o2 = po[2], o3 = po[3];
     const int is = A.in[c].stride;
     const uint16_t *q = (const uint16_t *)A.in[c].p + (size_t)y * is + x;
     int v = q[0];
     if (t == 5) {
-        const int b = min(v >> 5, 31) - p.band_position[c];
-        if (b >= 0 && b <= 3) v = min(max(v + p.offset[c][b], 0), 1023);
+        const int b = min(v >> 5, 31) - pp->band_position[c];
+        if (b >= 0 && b <= 3) v = min(max(v + (b == 0 ? o0 : b == 1 ? o1 : b == 2 ? o2 : o3), 0), 1023);
     } else if (t >= 1 && t <= 4) {
         const int dx = (t == 2) ? 0 : (t == 4 ? 1 : -1), dy = (t == 1) ? 0 : -1;
         const bool skip = ((t != 1) && (y == 0 || y == ph - 1)) || ((t != 2) && (x == 0 || x == pw - 1));
         if (!skip) {
             const int idx = sgn(v, (int)q[(ptrdiff_t)dy * is + dx]) + sgn(v, (int)q[-(ptrdiff_t)dy * is - dx]) + 2;
-            const int off = idx == 0 ? p.offset[c][0] : idx == 1 ? p.offset[c][1] : idx == 3 ? p.offset[c][2] : idx == 4 ? p.offset[c][3] : 0;
+            const int off = idx == 0 ? o0 : idx == 1 ? o1 : idx == 3 ? o2 : idx == 4 ? o3 : 0;
             v = min(max(v + off, 0), 1023);
         }
     }
@@ -312,7 +490,7 @@ static int sao_stats_dev_impl(const svtb200_yuv_picture *src, const svtb200_yuv_
     }
     A.out = out_dev; A.W = recon->y.width; A.H = recon->y.height; A.cols = (A.W + 63) / 64;
     const int n = A.cols * ((A.H + 63) / 64) * 3;
-    if (hbd) sao_stats16_kernel<<<n, ST_NT, 0, (cudaStream_t)cuda_stream>>>(A); else sao_stats_kernel<<<n, ST_NT, 0, (cudaStream_t)cuda_stream>>>(A);
+    if (hbd) sao_stats16_kernel<<<n, ST_NT, 0, (cudaStream_t)cuda_stream>>>(A); else sao_stats2_kernel<<<n / 3, ST2_NT, 0, (cudaStream_t)cuda_stream>>>(A);
     SVTB200_COUNT_LAUNCH();
     SVTB200_CUDA_TRY(cudaGetLastError());
     return SVTB200_OK;

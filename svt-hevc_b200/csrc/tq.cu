@@ -49,6 +49,7 @@ __device__ __align__(16) int8_t g_dct_t[4][32 * 32];   // [log2 N - 2]
 __constant__ int8_t c_dst4[4][4] = {{29, 55, 74, 84}, {74, 74, 0, -74}, {84, -29, -74, 55}, {55, -84, 74, -29}};
 __constant__ uint32_t c_qfunc[6] = {26214, 23302, 20560, 18396, 16384, 14564};   // QFunc, Codec/EbTransforms.h:26
 __constant__ uint32_t c_ffunc[6] = {40, 45, 51, 57, 64, 72};                      // FFunc, :27
+#include "tq_tables.inc"
 
 static void build_dct32(int8_t m[32][32])
 {
@@ -355,15 +356,11 @@ template <bool HBD>
 __device__ __forceinline__ int ld1(const uint8_t *base, size_t i) { return HBD ? (int)((const uint16_t *)base)[i] : (int)base[i]; }
 
 // HBD: 16-bit sample planes (10-bit video): EncodeLoop16bit / EncodeGenerateRecon16bit (Codec/EbCodingLoop.c:1240,1640); strides stay in samples
+// The general path: the whole CTA (TQ_NT threads) on one TU, every size / shape / flag.
 template <bool HBD>
-__global__ void __launch_bounds__(TQ_NT, 1024 / TQ_NT > 32 ? 32 : 1024 / TQ_NT) tq_batch_kernel(const __grid_constant__ TqArgs A)
+__device__ void tq_cta_path(const TqArgs &A, const int j, int16_t *s_a, int16_t *s_b, int16_t *s_q, uint32_t &s_cnt, int8_t *s_m, int8_t *s_mt)
 {
     constexpr int BPS = HBD ? 2 : 1, BIT_INC = HBD ? 2 : 0, MAXV = HBD ? 1023 : 255;
-    __shared__ __align__(16) int16_t s_a[32 * TP], s_b[32 * TP], s_q[32 * TP];
-    __shared__ uint32_t s_cnt;
-    __shared__ __align__(16) int8_t s_m[32 * 32], s_mt[32 * 32];
-    const int j = blockIdx.x;
-    if (j >= A.n_jobs) return;
     const svtb200_tq_job t = A.jobs[j];
     const int N = t.size, pl = t.plane, lg = ilog2d(N);
     // core matrix and the transpose of this TU size: 64 + 64 128-bit loads
@@ -449,6 +446,272 @@ __global__ void __launch_bounds__(TQ_NT, 1024 / TQ_NT > 32 ? 32 : 1024 / TQ_NT) 
     }
 }
 
+
+
+// =====================================================================================================================================
+// Warp-level fast path (round 2): ONE WARP PER TU for the TUs that make up a picture -- 16x16 / 32x32, full (DEFAULT) shape, DCT, no post-quantisation
+// flags -- with no block barrier anywhere.  Lane r owns row r (forward pass 1: residual row -> folded -> N outputs into a transposed s16 tile), then row u
+// of that tile (forward pass 2 -> the N coefficients of column u, quantised and dequantised in registers), then column u of the inverse pass 1 (even /
+// odd partial butterflies: out[n] = E[n] + O[n], out[N-1-n] = E[n] - O[n], half the multiplies of the dense product and exact in integers) into the same
+// tile, then row y of the inverse pass 2, the prediction row and the reconstruction.  Every tap is a compile-time-indexed word of the static
+// __constant__ tables (tq_tables.inc): a constant operand, not a load.  Two shared-memory transposes (2 x N x N s16) are all the data exchange there is.
+// Arithmetic identical to tq_chain (same shifts, offsets, 16-bit wraps and clips); the general path above keeps every other size / shape / flag.
+// =====================================================================================================================================
+__device__ __forceinline__ uint32_t swap16(uint32_t w) { return __byte_perm(w, w, 0x1032); }
+__device__ __forceinline__ uint32_t cw(const int8_t *tab, int word) { return ((const uint32_t *)tab)[word]; }
+
+// out[k] for k < N from the folded row (fs: sums, fd: differences; N/4 words each): taps M_N[k][0 .. N/2)
+template <int N>
+__device__ __forceinline__ int fwd_dot(const uint32_t (&fs)[N / 4], const uint32_t (&fd)[N / 4], int k)
+{
+    // (k is a compile-time constant at every call site: the loops over k are fully unrolled)
+    const int row = (N == 32 ? k : 2 * k) * 8;
+    int acc = 0;
+#pragma unroll
+    for (int q = 0; q < N / 8; ++q) {
+        const uint32_t w = cw(c_fw32, row + q);
+        acc = (k & 1) ? dp2a_hi(fd[2 * q + 1], w, dp2a_lo(fd[2 * q], w, acc)) : dp2a_hi(fs[2 * q + 1], w, dp2a_lo(fs[2 * q], w, acc));
+    }
+    return acc;
+}
+// E[n], O[n] of the inverse butterflies from the even- / odd-index input words (we[2q] = (in[8q], in[8q+2]), we[2q+1] = (in[8q+4], in[8q+6]); wo likewise + 1)
+template <int N>
+__device__ __forceinline__ void inv_eo(const uint32_t (&we)[N / 4], const uint32_t (&wo)[N / 4], int n, int &E, int &O)
+{
+    const int8_t *te = N == 32 ? c_te32 : c_te16, *to = N == 32 ? c_to32 : c_to16;
+    int e = 0, o = 0;
+#pragma unroll
+    for (int q = 0; q < N / 8; ++q) {
+        const uint32_t a = cw(te, n * (N / 8) + q), b = cw(to, n * (N / 8) + q);
+        e = dp2a_hi(we[2 * q + 1], a, dp2a_lo(we[2 * q], a, e));
+        o = dp2a_hi(wo[2 * q + 1], b, dp2a_lo(wo[2 * q], b, o));
+    }
+    E = e; O = o;
+}
+// a row of N s16 (natural order, N/2 words) -> even / odd index words for inv_eo
+template <int N>
+__device__ __forceinline__ void split_eo(const uint32_t (&x)[N / 2], uint32_t (&we)[N / 4], uint32_t (&wo)[N / 4])
+{
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) {
+        we[i] = __byte_perm(x[2 * i], x[2 * i + 1], 0x5410);      // (x[4i], x[4i+2])
+        wo[i] = __byte_perm(x[2 * i], x[2 * i + 1], 0x7632);      // (x[4i+1], x[4i+3])
+    }
+}
+// first butterfly stage in 16 bits (wrapping, like PartialButterfly{16,32}Estimate): x = N/2 words of s16 pairs in natural order
+template <int N>
+__device__ __forceinline__ void fold16(const uint32_t (&x)[N / 2], uint32_t (&fs)[N / 4], uint32_t (&fd)[N / 4])
+{
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) {
+        const uint32_t m = swap16(x[N / 2 - 1 - i]);              // (X[N-1-2i], X[N-2-2i])
+        fs[i] = __vadd2(x[i], m);
+        fd[i] = __vsub2(x[i], m);
+    }
+}
+
+template <int N, bool HBD>
+__device__ void tq_warp_fast(const TqArgs &A, const svtb200_tq_job &t, const int j, int16_t *T)
+{
+    constexpr int BPS = HBD ? 2 : 1, BIT_INC = HBD ? 2 : 0, MAXV = HBD ? 1023 : 255, LG = N == 32 ? 5 : 4;
+    const int lane = threadIdx.x & 31, pl = t.plane;
+    const bool on = lane < N;
+    const int ss = A.src.stride[pl], ps = A.pred.stride[pl], rs = A.recon.stride[pl], cs = A.cstride[pl];
+    const uint8_t *s = A.src.p[pl] + ((size_t)(A.src.oy[pl] + t.y) * ss + A.src.ox[pl] + t.x) * BPS;
+    const uint8_t *p = A.pred.p[pl] + ((size_t)(A.pred.oy[pl] + t.y) * ps + A.pred.ox[pl] + t.x) * BPS;
+    uint8_t *r = A.recon.p[pl] + ((size_t)(A.recon.oy[pl] + t.y) * rs + A.recon.ox[pl] + t.x) * BPS;
+    int16_t *co = A.coeff[pl] + (size_t)t.y * cs + t.x;
+    const bool want_recon = !(t.flags & SVTB200_TQ_SKIP_RECON);
+    const int s1 = (N == 32 ? 6 : 4) + BIT_INC, s2 = 9;
+    uint32_t x[N / 2];
+    // ---- residual row `lane` as s16 pairs ----
+    if (on) {
+        const uint8_t *sr = s + (size_t)lane * ss * BPS, *pr = p + (size_t)lane * ps * BPS;
+        if (HBD) {
+#pragma unroll
+            for (int c = 0; c < N / 8; ++c) {
+                const uint4 a = ((const uint4 *)sr)[c], b = ((const uint4 *)pr)[c];
+                x[4 * c] = __vsub2(a.x, b.x); x[4 * c + 1] = __vsub2(a.y, b.y); x[4 * c + 2] = __vsub2(a.z, b.z); x[4 * c + 3] = __vsub2(a.w, b.w);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < N / 16; ++c) {
+                const uint4 a = ((const uint4 *)sr)[c], b = ((const uint4 *)pr)[c];
+                const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {      // bytes -> u16 pairs, then the 16-bit difference (|difference| <= 255)
+                    x[8 * c + 2 * q] = __vsub2(__byte_perm(aw[q], 0, 0x4140), __byte_perm(bw[q], 0, 0x4140));
+                    x[8 * c + 2 * q + 1] = __vsub2(__byte_perm(aw[q], 0, 0x4342), __byte_perm(bw[q], 0, 0x4342));
+                }
+            }
+        }
+    }
+    // ---- forward pass 1: T[k][lane] ----
+    {
+        uint32_t fs[N / 4], fd[N / 4];
+        fold16<N>(x, fs, fd);
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const int v = (fwd_dot<N>(fs, fd, k) + (1 << (s1 - 1))) >> s1;
+            if (on) T[k * TP + lane] = (int16_t)v;
+        }
+    }
+    __syncwarp();
+    // ---- forward pass 2 on row `lane` of T: coefficient column u = lane ----
+    if (on) {
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) x[i] = ((const uint32_t *)(T + lane * TP))[i];
+    }
+    __syncwarp();                       // every lane holds its row: the tile is free for the inverse pass
+    // quantiser parameters (UnifiedQuantizeInvQuantize, Codec/EbTransforms.c:3094-3110; same derivation as tq_chain)
+    const int qp = t.qp + (BIT_INC ? 12 : 0);
+    const int qpRem = qp % 6, qpPer = qp / 6;
+    const int tshift = 15 - (8 + BIT_INC) - LG;
+    const int shiftedQBits = 14 + qpPer + tshift;
+    const uint32_t qoff_ip = (uint32_t)(t.slice_type >= 2 ? 171 : 85) << (shiftedQBits - 9);
+    const uint32_t qoff = t.dz_offset ? (uint32_t)(t.dz_offset * (1u << shiftedQBits) / 20) : qoff_ip;
+    const int shiftedFFunc = qpPer > 8 ? (int)c_ffunc[qpRem] << (qpPer - 2) : (int)c_ffunc[qpRem] << qpPer;
+    const int shiftNum = qpPer > 8 ? 20 - 14 - tshift - 2 : 20 - 14 - tshift;
+    const int iqoff = 1 << (shiftNum - 1);
+    const uint32_t qf = c_qfunc[qpRem];
+    uint32_t mynz = 0;
+    uint32_t d[N / 2];                  // dequantised column, natural order
+    {
+        uint32_t fs[N / 4], fd[N / 4];
+        fold16<N>(x, fs, fd);
+#pragma unroll
+        for (int v = 0; v < N; ++v) {
+            const int c = (int)(short)((fwd_dot<N>(fs, fd, v) + (1 << (s2 - 1))) >> s2);
+            int a = (int)((uint32_t)abs(c) * qf + qoff);
+            a >>= shiftedQBits;
+            const int qv = clip16i(c < 0 ? -a : a);
+            const int rv = clip16i((qv * shiftedFFunc + iqoff) >> shiftNum);
+            mynz += (on && qv != 0);
+            if (on) co[(size_t)v * cs + lane] = (int16_t)qv;
+            if (v & 1) d[v >> 1] = (d[v >> 1] & 0xffffu) | ((uint32_t)(uint16_t)rv << 16); else d[v >> 1] = (uint32_t)(uint16_t)rv;
+        }
+    }
+    const uint32_t nz = __reduce_add_sync(0xffffffffu, mynz);
+    if (lane == 0) A.nz[j] = nz;
+    if (!want_recon) return;
+    if (nz == 0) {                      // prediction = reconstruction (copied when the two pictures differ)
+        if (on && r != p) {
+            const uint4 *pr = (const uint4 *)(p + (size_t)lane * ps * BPS);
+            uint4 *rr = (uint4 *)(r + (size_t)lane * rs * BPS);
+#pragma unroll
+            for (int c = 0; c < N * BPS / 16; ++c) rr[c] = pr[c];
+        }
+        return;
+    }
+    // ---- inverse pass 1 (along v): T[y][lane] = clip16((sum_v M[v][y] d[v] + 64) >> 7) ----
+    {
+        uint32_t we[N / 4], wo[N / 4];
+        split_eo<N>(d, we, wo);
+#pragma unroll
+        for (int y = 0; y < N / 2; ++y) {
+            int E, O;
+            inv_eo<N>(we, wo, y, E, O);
+            if (on) {
+                T[y * TP + lane] = (int16_t)clip16i((E + O + 64) >> 7);
+                T[(N - 1 - y) * TP + lane] = (int16_t)clip16i((E - O + 64) >> 7);
+            }
+        }
+    }
+    __syncwarp();
+    // ---- inverse pass 2 (along u) on row y = lane, prediction, reconstruction ----
+    if (on) {
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) x[i] = ((const uint32_t *)(T + lane * TP))[i];
+        uint32_t we[N / 4], wo[N / 4];
+        split_eo<N>(x, we, wo);
+        uint32_t rw[N / 2];              // the residual row as s16 pairs (32 registers less than one int per sample)
+        constexpr int off2 = 2048 >> BIT_INC, sh2 = 12 - BIT_INC;
+#pragma unroll
+        for (int n = 0; n < N / 2; ++n) {
+            int E, O;
+            inv_eo<N>(we, wo, n, E, O);
+            const uint32_t a = (uint32_t)(uint16_t)clip16i((E + O + off2) >> sh2), b = (uint32_t)(uint16_t)clip16i((E - O + off2) >> sh2);
+            const int m = N - 1 - n;
+            if (n & 1) rw[n >> 1] = (rw[n >> 1] & 0xffffu) | (a << 16); else rw[n >> 1] = a;
+            if (m & 1) rw[m >> 1] = b << 16; else rw[m >> 1] = (rw[m >> 1] & 0xffff0000u) | b;      // (m runs downwards: the odd half of a word comes first)
+        }
+        const uint8_t *pr = p + (size_t)lane * ps * BPS;
+        uint8_t *rr = r + (size_t)lane * rs * BPS;
+        if (HBD) {
+#pragma unroll
+            for (int c = 0; c < N / 8; ++c) {
+                const uint4 b = ((const uint4 *)pr)[c];
+                const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+                uint32_t o[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t e = rw[4 * c + q];
+                    const int v0 = min(max((int)(bw[q] & 0xffff) + (int)(short)(e & 0xffff), 0), MAXV), v1 = min(max((int)(bw[q] >> 16) + (int)(short)(e >> 16), 0), MAXV);
+                    o[q] = (uint32_t)v0 | ((uint32_t)v1 << 16);
+                }
+                ((uint4 *)rr)[c] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < N / 16; ++c) {
+                const uint4 b = ((const uint4 *)pr)[c];
+                const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+                uint32_t o[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    int v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t w = rw[8 * c + 2 * q + (e >> 1)];
+                        v[e] = min(max((int)((bw[q] >> (8 * e)) & 0xff) + (int)(short)((e & 1) ? (w >> 16) : (w & 0xffff)), 0), 255);
+                    }
+                    o[q] = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+                }
+                ((uint4 *)rr)[c] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+}
+
+// eligibility of the warp path (uniform per TU): a full-shape 16x16 / 32x32 DCT TU without post-quantisation flags whose rows are 16-byte accessible
+template <bool HBD>
+__device__ __forceinline__ bool tq_fast_ok(const TqArgs &A, const svtb200_tq_job &t)
+{
+    constexpr int BPS = HBD ? 2 : 1;
+    if (!(t.size == 16 || t.size == 32) || t.shape != SVTB200_SHAPE_DEFAULT || t.dst4x4 || (t.flags & ~SVTB200_TQ_SKIP_RECON)) return false;
+    const int pl = t.plane;
+    const uintptr_t a = (uintptr_t)(A.src.p[pl] + ((size_t)(A.src.oy[pl] + t.y) * A.src.stride[pl] + A.src.ox[pl] + t.x) * BPS) | (uintptr_t)(A.src.stride[pl] * BPS) |
+                        (uintptr_t)(A.pred.p[pl] + ((size_t)(A.pred.oy[pl] + t.y) * A.pred.stride[pl] + A.pred.ox[pl] + t.x) * BPS) | (uintptr_t)(A.pred.stride[pl] * BPS) |
+                        (uintptr_t)(A.recon.p[pl] + ((size_t)(A.recon.oy[pl] + t.y) * A.recon.stride[pl] + A.recon.ox[pl] + t.x) * BPS) | (uintptr_t)(A.recon.stride[pl] * BPS);
+    return (a & 15) == 0;
+}
+
+// Batch kernel: a CTA of two warps takes two consecutive TUs; each warp runs its TU alone when the warp path applies, the rest go through the general
+// path afterwards with the whole CTA.
+template <bool HBD>
+__global__ void __launch_bounds__(TQ_NT, 8) tq_batch_kernel(const __grid_constant__ TqArgs A)
+{
+    static_assert(TQ_NT == 64, "two warps, two TUs");
+    __shared__ __align__(16) int16_t s_a[32 * TP], s_b[32 * TP], s_q[32 * TP];
+    __shared__ uint32_t s_cnt;
+    __shared__ __align__(16) int8_t s_m[32 * 32], s_mt[32 * 32];
+    __shared__ int s_slow[2];
+    const int wid = threadIdx.x >> 5, j = 2 * blockIdx.x + wid;
+    bool fast = false;
+    if (j < A.n_jobs) {
+        const svtb200_tq_job t = A.jobs[j];
+        fast = tq_fast_ok<HBD>(A, t);
+        if (fast) {
+            int16_t *T = wid ? s_b : s_a;
+            if (t.size == 32) tq_warp_fast<32, HBD>(A, t, j, T); else tq_warp_fast<16, HBD>(A, t, j, T);
+        }
+    }
+    if ((threadIdx.x & 31) == 0) s_slow[wid] = (j < A.n_jobs && !fast) ? 1 : 0;
+    __syncthreads();
+    const int slow0 = s_slow[0], slow1 = s_slow[1];
+    if (slow0) { tq_cta_path<HBD>(A, 2 * blockIdx.x, s_a, s_b, s_q, s_cnt, s_m, s_mt); __syncthreads(); }
+    if (slow1) tq_cta_path<HBD>(A, 2 * blockIdx.x + 1, s_a, s_b, s_q, s_cnt, s_m, s_mt);
+}
 
 // ---- coefficient hand-off: only coded TUs cross PCIe -------------------------------------------------------------------
 // The entropy coder reads coeffSamplesTB of TUs whose cbf is set (EbCodingLoop.c:745, EbEntropyCoding.c) and nothing else, so the coefficient
@@ -659,7 +922,7 @@ static int tq_batch_dev_impl(const svtb200_yuv_picture *src, const svtb200_yuv_p
     A.recon = to_yuvw(*recon, recon->y.buf, recon->cb.buf, recon->cr.buf);
     for (int k = 0; k < 3; ++k) { A.coeff[k] = coeff->buf[k]; A.cstride[k] = (int)coeff->stride[k]; }
     A.jobs = jobs_dev; A.n_jobs = n_jobs; A.nz = nz_counts_dev;
-    if (hbd) tq_batch_kernel<true><<<n_jobs, TQ_NT, 0, (cudaStream_t)cuda_stream>>>(A); else tq_batch_kernel<false><<<n_jobs, TQ_NT, 0, (cudaStream_t)cuda_stream>>>(A);
+    if (hbd) tq_batch_kernel<true><<<(n_jobs + 1) / 2, TQ_NT, 0, (cudaStream_t)cuda_stream>>>(A); else tq_batch_kernel<false><<<(n_jobs + 1) / 2, TQ_NT, 0, (cudaStream_t)cuda_stream>>>(A);
     SVTB200_COUNT_LAUNCH();
     SVTB200_CUDA_TRY(cudaGetLastError());
     return SVTB200_OK;
