@@ -208,6 +208,15 @@ int svtb200_mc_batch16(const svtb200_yuv_picture *refs, int n_refs, const svtb20
 int svtb200_mc_batch16_dev(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs_dev, int n_jobs,
                            const svtb200_yuv_picture *dst, void *cuda_stream);
 
+/* b6: the mode-decision fast loop's interpolation-free prediction (INTERPOLATION_FREE_PATH, Codec/EbEncDecProcess.c:2728, pictures with
+ * useSubpelFlag == 0): UniPredIFreeRef8Bit / BiPredIFreeRef8Bit (Codec/EbAvcStyleMcp.c:172,321) behind Inter2Nx2NPuPredictionInterpolationFree
+ * (Codec/EbInterPrediction.c:60-400) -- the copy at the integer position the vector's fraction maps to, bi-prediction = rounded average of the
+ * two copies.  Same job record, same position clamp, same destination convention as svtb200_mc_batch (the fast loop writes the candidate's
+ * prediction buffer; here every PU lands at its own position of `dst`). */
+int svtb200_mc_ifree_batch(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs, int n_jobs, const svtb200_yuv_picture *dst);
+int svtb200_mc_ifree_batch_dev(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs_dev, int n_jobs,
+                               const svtb200_yuv_picture *dst, void *cuda_stream);
+
 /* Leaf entry points with the reference's kernel prototypes.  The reference selects one of 16 (luma) / 64
  * (chroma) functions by fractional position (uniPredLumaIFFunctionPtrArrayNew[2][16], EbMcpTables.c:28;
  * uniPredChromaIFFunctionPtrArrayNew[2][64], :195); here the position is an argument.

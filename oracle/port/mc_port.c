@@ -125,6 +125,46 @@ int port_mc_batch(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_
     return 0;
 }
 
+/* ---- interpolation-free prediction of the mode-decision fast loop ---------------------------------------------------
+ * UniPredIFreeRef8Bit / BiPredIFreeRef8Bit (Codec/EbAvcStyleMcp.c:172,321): function [0] of AvcStyleUniPredLumaIFFunctionPtrArray (the copy) at the
+ * integer position the fraction maps to (IntegerPosoffsetTabX/Y :19-27; chroma: +1 where the 1/8 fraction exceeds 4), bi-prediction =
+ * (a + b + 1) >> 1 of the two copies (BiPredAverageKernel_C :269).  Position clamp of the caller, Codec/EbInterPrediction.c:100-115. */
+int port_mc_ifree_batch(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs, int n_jobs, const svtb200_yuv_picture *dst)
+{
+    static const uint8_t offx[16] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0 }, offy[16] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1 };
+    for (int j = 0; j < n_jobs; ++j) {
+        const svtb200_mc_job *q = &jobs[j];
+        const uint8_t *src[2][3] = { { 0 } };
+        int stride[2][3] = { { 0 } };
+        for (int l = 0; l < 2; ++l) {
+            if (!(q->dir == l || q->dir == 2)) continue;
+            if (q->ref_idx[l] >= n_refs) return -1;
+            const svtb200_yuv_picture *r = &refs[q->ref_idx[l]];
+            const int px = (uint16_t)clamp_i((r->y.origin_x - 71) << 2, (r->y.width + r->y.origin_x + 7) << 2, ((q->x + r->y.origin_x) << 2) + q->mv[l][0]);
+            const int py = (uint16_t)clamp_i((r->y.origin_y - 71) << 2, (r->y.height + r->y.origin_y + 7) << 2, ((q->y + r->y.origin_y) << 2) + q->mv[l][1]);
+            const int f = (px & 3) + ((py & 3) << 2);
+            src[l][0] = r->y.buf + (size_t)((py >> 2) + offy[f]) * r->y.stride + (px >> 2) + offx[f];
+            const int cx = (px >> 3) + ((px & 7) > 4), cy = (py >> 3) + ((py & 7) > 4);
+            src[l][1] = r->cb.buf + (size_t)cy * r->cb.stride + cx;
+            src[l][2] = r->cr.buf + (size_t)cy * r->cr.stride + cx;
+            stride[l][0] = (int)r->y.stride; stride[l][1] = (int)r->cb.stride; stride[l][2] = (int)r->cr.stride;
+        }
+        uint8_t *d[3] = { dst->y.buf + (size_t)(dst->y.origin_y + q->y) * dst->y.stride + dst->y.origin_x + q->x, NULL, NULL };
+        const size_t cidx = (((size_t)(dst->y.origin_y + q->y) * dst->cb.stride) >> 1) + ((dst->y.origin_x + q->x) >> 1);
+        d[1] = dst->cb.buf + cidx; d[2] = dst->cr.buf + cidx;
+        const int ds[3] = { (int)dst->y.stride, (int)dst->cb.stride, (int)dst->cr.stride };
+        for (int c = 0; c < 3; ++c) {
+            const int w = c ? q->w >> 1 : q->w, h = c ? q->h >> 1 : q->h;
+            for (int y = 0; y < h; ++y)
+                for (int x = 0; x < w; ++x) {
+                    if (q->dir == 2) d[c][(size_t)y * ds[c] + x] = (uint8_t)((src[0][c][(size_t)y * stride[0][c] + x] + src[1][c][(size_t)y * stride[1][c] + x] + 1) >> 1);
+                    else d[c][(size_t)y * ds[c] + x] = src[q->dir][c][(size_t)y * stride[q->dir][c] + x];
+                }
+        }
+    }
+    return 0;
+}
+
 /* ---- 16-bit samples (10-bit video): SURVEY §8 row b5 -------------------------------------------------------------------
  * uniPred / biPred ...New16bit / ...OutRaw16bit (C_DEFAULT/EbMcp_C.c:3121-4861), BiPredClipping16bit :3265, integer/integer
  * shortcut BiPredClippingOnTheFly16bit (Codec/EbMcp.c:847), drivers UniPredInterpolation16bit / BiPredInterpolation16bit

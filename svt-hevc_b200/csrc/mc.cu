@@ -766,6 +766,63 @@ __global__ void __launch_bounds__(MC_NT) mc_leaf_kernel(const uint8_t *r0, int s
         }
 }
 
+// ---- interpolation-free prediction of the mode-decision fast loop (INTERPOLATION_FREE_PATH, Codec/EbEncDecProcess.c:2728: pictures without sub-pel) ----
+// UniPredIFreeRef8Bit / BiPredIFreeRef8Bit (Codec/EbAvcStyleMcp.c:172,321): whatever the vector's fraction, function [0] of the AVC-style table (the
+// copy) runs at the integer position the fraction maps to -- luma: position >> 2 plus IntegerPosoffsetTab{X,Y} (:19-27: +1 in x for fraction (3,2), +1
+// in y for (1..3,3)); chroma: position >> 3, +1 where the 1/8 fraction exceeds 4 -- and bi-prediction is the rounded average of the two copies
+// (BiPredAverageKernel / PictureAverage, :269).  Same position clamp as every PU-level wrapper (Inter2Nx2NPuPredictionInterpolationFree,
+// Codec/EbInterPrediction.c:100-115).  One warp per PU, 4 samples per lane and step: a copy kernel, HBM / L2 bound.
+__global__ void __launch_bounds__(256) mc_ifree_kernel(const __grid_constant__ McArgs A)
+{
+    const int job = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (job >= A.n_jobs) return;
+    const svtb200_mc_job q = A.jobs[job];
+    const bool bi = q.dir == 2;
+    int px[2], py[2];
+    const YuvD *r[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int l = bi ? s : (q.dir == 1 ? 1 : 0);
+        const int ri = l ? q.ref_idx[1] : q.ref_idx[0], mvx = l ? q.mv[1][0] : q.mv[0][0], mvy = l ? q.mv[1][1] : q.mv[0][1];
+        r[s] = &A.refs[min(ri, A.n_refs - 1)];
+        px[s] = (uint16_t)clampi((r[s]->ox - 71) << 2, (r[s]->w + r[s]->ox + 7) << 2, ((q.x + r[s]->ox) << 2) + mvx);
+        py[s] = (uint16_t)clampi((r[s]->oy - 71) << 2, (r[s]->h + r[s]->oy + 7) << 2, ((q.y + r[s]->oy) << 2) + mvy);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int w4 = (c ? q.w >> 1 : q.w) >> 2, h = c ? q.h >> 1 : q.h;
+        const uint8_t *s0, *s1;
+        {
+            const uint8_t *sp[2];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                int ix, iy;
+                if (c == 0) {
+                    const int fx = px[s] & 3, fy = py[s] & 3;
+                    ix = (px[s] >> 2) + (fx == 3 && fy == 2); iy = (py[s] >> 2) + (fy == 3 && fx != 0);
+                } else {
+                    ix = (px[s] >> 3) + ((px[s] & 7) > 4); iy = (py[s] >> 3) + ((py[s] & 7) > 4);
+                }
+                sp[s] = r[s]->p[c] + (ptrdiff_t)iy * r[s]->stride[c] + ix;
+            }
+            s0 = sp[0]; s1 = sp[1];
+        }
+        const int st0 = r[0]->stride[c], st1 = r[1]->stride[c];
+        // the destination index exactly as the callers form it: luma origin + PU position, chroma = half of both
+        uint8_t *d = c == 0 ? A.dst[0] + (size_t)(A.doy + q.y) * A.dstride[0] + A.dox + q.x
+                            : A.dst[c] + (size_t)((A.doy + q.y) >> 1) * A.dstride[c] + ((A.dox + q.x) >> 1);
+        const int lg = 31 - __clz(w4), n = h << lg;                   // w4 is 1, 2, 4, 8 or 16
+        for (int i = lane; i < n; i += 32) {
+            const int y = i >> lg, x = i & (w4 - 1);
+            uint32_t v = ld_u32_unaligned(s0 + (ptrdiff_t)y * st0 + 4 * x);
+            if (bi) v = __vavgu4(v, ld_u32_unaligned(s1 + (ptrdiff_t)y * st1 + 4 * x));
+            uint8_t *o = d + (size_t)y * A.dstride[c] + 4 * x;
+            if (((uintptr_t)o & 3) == 0) *(uint32_t *)o = v;
+            else { o[0] = (uint8_t)v; o[1] = (uint8_t)(v >> 8); o[2] = (uint8_t)(v >> 16); o[3] = (uint8_t)(v >> 24); }
+        }
+    }
+}
+
 static YuvD to_yuvd(const svtb200_yuv_picture &p, const uint8_t *y, const uint8_t *cb, const uint8_t *cr)
 {
     YuvD d;
@@ -786,7 +843,7 @@ static int check_pic(const svtb200_yuv_picture &p, const char *what)
 }
 
 static int launch_mc(const YuvD *h_refs, int n_refs, const svtb200_mc_job *d_jobs, int n_jobs, const svtb200_yuv_picture &dst,
-                     uint8_t *dy, uint8_t *dcb, uint8_t *dcr, cudaStream_t st, bool hbd = false)
+                     uint8_t *dy, uint8_t *dcb, uint8_t *dcr, cudaStream_t st, bool hbd = false, bool ifree = false)
 {
     McArgs A;
     for (int i = 0; i < 16; ++i) A.refs[i] = h_refs[i < n_refs ? i : 0];
@@ -795,7 +852,8 @@ static int launch_mc(const YuvD *h_refs, int n_refs, const svtb200_mc_job *d_job
     A.dstride[0] = (int)dst.y.stride; A.dstride[1] = (int)dst.cb.stride; A.dstride[2] = (int)dst.cr.stride;
     A.dox = dst.y.origin_x; A.doy = dst.y.origin_y;
     if (n_jobs == 0) return SVTB200_OK;
-    if (hbd) mc_batch_kernel<true><<<n_jobs, MC_NT, 0, st>>>(A);
+    if (ifree) { A.tma = 0; mc_ifree_kernel<<<(n_jobs + 7) / 8, 256, 0, st>>>(A); }
+    else if (hbd) mc_batch_kernel<true><<<n_jobs, MC_NT, 0, st>>>(A);
     else {
         // TMA path: at most four references, every plane 16-byte aligned with a 16-byte pitch (device pictures of svtb200_yuv_picture_create)
         A.tma = n_refs <= 4;
@@ -830,7 +888,7 @@ using namespace svtb200;
 
 extern "C" {
 
-static int mc_batch_dev_impl(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs_dev, int n_jobs, const svtb200_yuv_picture *dst, void *cuda_stream, bool hbd)
+static int mc_batch_dev_impl(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs_dev, int n_jobs, const svtb200_yuv_picture *dst, void *cuda_stream, bool hbd, bool ifree = false)
 {
     if (!refs || n_refs <= 0 || n_refs > 16 || (!jobs_dev && n_jobs) || n_jobs < 0 || !dst) { set_error("mc_batch_dev: bad argument"); return SVTB200_ERR_BAD_ARG; }
     int rc = check_pic(*dst, "destination");
@@ -840,10 +898,10 @@ static int mc_batch_dev_impl(const svtb200_yuv_picture *refs, int n_refs, const 
     YuvD tab[16];
     for (int i = 0; i < n_refs; ++i) tab[i] = to_yuvd(refs[i], refs[i].y.buf, refs[i].cb.buf, refs[i].cr.buf);
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    return launch_mc(tab, n_refs, jobs_dev, n_jobs, *dst, dst->y.buf, dst->cb.buf, dst->cr.buf, st, hbd);
+    return launch_mc(tab, n_refs, jobs_dev, n_jobs, *dst, dst->y.buf, dst->cb.buf, dst->cr.buf, st, hbd, ifree);
 }
 
-static int mc_batch_impl(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs, int n_jobs, const svtb200_yuv_picture *dst, bool hbd)
+static int mc_batch_impl(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs, int n_jobs, const svtb200_yuv_picture *dst, bool hbd, bool ifree = false)
 {
     const size_t bps = hbd ? 2 : 1;
     if (!refs || n_refs <= 0 || n_refs > 16 || (!jobs && n_jobs) || n_jobs < 0 || !dst) { set_error("mc_batch: bad argument"); return SVTB200_ERR_BAD_ARG; }
@@ -884,7 +942,7 @@ static int mc_batch_impl(const svtb200_yuv_picture *refs, int n_refs, const svtb
         SVTB200_CUDA_TRY(cudaMemcpyAsync(dp[k], dpl[k]->buf, bps * pbytes(*dpl[k]), cudaMemcpyHostToDevice, c->stream));
     }
     if (n_jobs) SVTB200_CUDA_TRY(cudaMemcpyAsync(d_jobs, jobs, sizeof(svtb200_mc_job) * (size_t)n_jobs, cudaMemcpyHostToDevice, c->stream));
-    if ((rc = launch_mc((const YuvD *)h_tab, n_refs, (const svtb200_mc_job *)d_jobs, n_jobs, *dst, (uint8_t *)dp[0], (uint8_t *)dp[1], (uint8_t *)dp[2], c->stream, hbd))) return rc;
+    if ((rc = launch_mc((const YuvD *)h_tab, n_refs, (const svtb200_mc_job *)d_jobs, n_jobs, *dst, (uint8_t *)dp[0], (uint8_t *)dp[1], (uint8_t *)dp[2], c->stream, hbd, ifree))) return rc;
     for (int k = 0; k < 3; ++k) SVTB200_CUDA_TRY(cudaMemcpyAsync(dpl[k]->buf, dp[k], bps * pbytes(*dpl[k]), cudaMemcpyDeviceToHost, c->stream));
     SVTB200_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return SVTB200_OK;
@@ -896,6 +954,10 @@ int svtb200_mc_batch(const svtb200_yuv_picture *refs, int n_refs, const svtb200_
 { return mc_batch_impl(refs, n_refs, jobs, n_jobs, dst, false); }
 int svtb200_mc_batch16_dev(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs_dev, int n_jobs, const svtb200_yuv_picture *dst, void *cuda_stream)
 { return mc_batch_dev_impl(refs, n_refs, jobs_dev, n_jobs, dst, cuda_stream, true); }
+int svtb200_mc_ifree_batch_dev(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs_dev, int n_jobs, const svtb200_yuv_picture *dst, void *cuda_stream)
+{ return mc_batch_dev_impl(refs, n_refs, jobs_dev, n_jobs, dst, cuda_stream, false, true); }
+int svtb200_mc_ifree_batch(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs, int n_jobs, const svtb200_yuv_picture *dst)
+{ return mc_batch_impl(refs, n_refs, jobs, n_jobs, dst, false, true); }
 int svtb200_mc_batch16(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs, int n_jobs, const svtb200_yuv_picture *dst)
 { return mc_batch_impl(refs, n_refs, jobs, n_jobs, dst, true); }
 

@@ -366,6 +366,12 @@ def mc_batch(refs, jobs, dst):
     check(lib().svtb200_mc_batch(yuv_array(refs), C.c_int(len(refs)), _u8p(jobs), C.c_int(len(jobs)), C.byref(dst.struct)))
 
 
+def mc_ifree_batch(refs, jobs, dst):
+    """the mode-decision fast loop's interpolation-free prediction (UniPredIFreeRef8Bit / BiPredIFreeRef8Bit); same arguments as mc_batch"""
+    jobs = np.ascontiguousarray(jobs)
+    check(lib().svtb200_mc_ifree_batch(yuv_array(refs), C.c_int(len(refs)), _u8p(jobs), C.c_int(len(jobs)), C.byref(dst.struct)))
+
+
 def mc_batch16(refs, jobs, dst):
     """16-bit sample planes (HostYuvPicture(dtype=np.uint16)), 10-bit video"""
     jobs = np.ascontiguousarray(jobs)
@@ -432,6 +438,38 @@ def tq_batch(src, pred, recon, coeff, jobs, hbd=False):
     check((lib().svtb200_tq_batch16 if hbd else lib().svtb200_tq_batch)(C.byref(src.struct), C.byref(pred.struct), C.byref(recon.struct), C.byref(coeff.struct), _u8p(jobs),
                                  C.c_int(len(jobs)), _u8p(nz)))
     return nz
+
+
+# ---- distortion leaves of mode decision --------------------------------------------------------------------------
+DIST_JOB_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("plane", "u1"), ("width", "u1"), ("height", "u1"), ("kind", "u1")])
+assert DIST_JOB_DTYPE.itemsize == 8
+FULLDIST_DEFAULT, FULLDIST_INTRA, FULLDIST_CBF_ZERO = 0, 1, 2
+SATD_8X8, SATD_4X4 = 0, 1
+
+
+def spatial_distortion_batch(inp, recon, jobs):
+    """SpatialFullDistortionKernel per job: sum (input - recon)^2 -> uint64[n]"""
+    jobs = np.ascontiguousarray(jobs)
+    out = np.zeros(len(jobs), np.uint64)
+    check(lib().svtb200_spatial_distortion_batch(C.byref(inp.struct), C.byref(recon.struct), _u8p(jobs), C.c_int(len(jobs)), _u8p(out)))
+    return out
+
+
+def full_distortion_batch(coeff, recon_coeff, width, height, jobs):
+    """FullDistortionKernel{,Intra,CbfZero}_32bit per job -> uint64[n][2] (distortionResult[0], [1])"""
+    jobs = np.ascontiguousarray(jobs)
+    out = np.zeros((len(jobs), 2), np.uint64)
+    check(lib().svtb200_full_distortion_batch(C.byref(coeff.struct), C.byref(recon_coeff.struct), C.c_uint32(width), C.c_uint32(height), _u8p(jobs),
+                                              C.c_int(len(jobs)), _u8p(out)))
+    return out
+
+
+def satd_batch(src, pred, jobs):
+    """Compute8x8Satd / Compute4x4Satd of the residual src - pred summed over the block's units -> uint64[n]"""
+    jobs = np.ascontiguousarray(jobs)
+    out = np.zeros(len(jobs), np.uint64)
+    check(lib().svtb200_satd_batch(C.byref(src.struct), C.byref(pred.struct), _u8p(jobs), C.c_int(len(jobs)), _u8p(out)))
+    return out
 
 
 def estimate_transform(res, N, bit_inc=0, dst=0, shape=0):

@@ -131,3 +131,19 @@ def test_mc_batch16_integer_mvs_and_alignment():
     want = run_oracle16(port, "port_mc_batch16", refs, jobs, w, h)
     for a, b in zip(dst.interior(), want.interior()):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("case", MC_CASES + [("uhd_3840x2160", 3840, 2160, "synth", True, False)], ids=lambda c: c[0])
+def test_mc_ifree_cuda_vs_oracle(case):
+    """row b6: the interpolation-free prediction of the mode-decision fast loop (UniPredIFreeRef8Bit / BiPredIFreeRef8Bit)"""
+    name, w, h, kind, all_fracs, big = case
+    refs = make_pictures(w, h, seed=13, kind=kind)
+    jobs = make_jobs(w, h, len(refs), seed=6, all_fracs=all_fracs, big_mv=big)
+    if ref is not None:
+        want = run_oracle(ref, "svtref_mc_ifree_batch", refs, jobs, w, h, asm_mode=1 if common.ref_asm_simd_ok() else 0)
+    else:
+        want = run_oracle(port, "port_mc_ifree_batch", refs, jobs, w, h)
+    got = S.HostYuvPicture(np.zeros((h, w), np.uint8), np.zeros((h // 2, w // 2), np.uint8), np.zeros((h // 2, w // 2), np.uint8))
+    S.mc_ifree_batch(refs, jobs, got)
+    for a, b, nm in zip(got.interior(), want.interior(), "Y Cb Cr".split()):
+        assert np.array_equal(a, b), f"{name}: {nm} differs: {np.argwhere(a != b)[:5]}"

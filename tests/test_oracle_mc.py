@@ -94,6 +94,32 @@ def test_mc_batch_port_vs_reference(case):
             assert np.array_equal(a, b), f"{name}: {nm} differs (reference SIMD vs C rows)"
 
 
+@needs_ref
+@pytest.mark.parametrize("case", MC_CASES, ids=lambda c: c[0])
+def test_mc_ifree_port_vs_reference(case):
+    """the interpolation-free prediction of the mode-decision fast loop (row b6): UniPredIFreeRef8Bit / BiPredIFreeRef8Bit, C and SIMD rows"""
+    name, w, h, kind, all_fracs, big = case
+    refs = make_pictures(w, h, seed=13, kind=kind)
+    jobs = make_jobs(w, h, len(refs), seed=6, all_fracs=all_fracs, big_mv=big)
+    want = run_oracle(ref, "svtref_mc_ifree_batch", refs, jobs, w, h, asm_mode=0)
+    got = run_oracle(port, "port_mc_ifree_batch", refs, jobs, w, h)
+    for a, b, nm in zip(got.interior(), want.interior(), "Y Cb Cr".split()):
+        assert np.array_equal(a, b), f"{name}: {nm} differs (port vs reference C rows)"
+    if common.ref_asm_simd_ok():
+        simd = run_oracle(ref, "svtref_mc_ifree_batch", refs, jobs, w, h, asm_mode=1)
+        for a, b, nm in zip(simd.interior(), want.interior(), "Y Cb Cr".split()):
+            assert np.array_equal(a, b), f"{name}: {nm} differs (reference SIMD vs C rows)"
+    # integer vectors: the interpolation-free result is the HEVC interpolation's (both are copies / rounded averages of copies ... for uni-pred)
+    ij = jobs.copy()
+    ij["mv"] &= ~3
+    ij = ij[ij["dir"] != 2]
+    a = run_oracle(port, "port_mc_ifree_batch", refs, ij, w, h)
+    b = run_oracle(port, "port_mc_batch", refs, ij, w, h)
+    for x, y in zip(a.interior(), b.interior()):
+        # chroma of an odd integer luma vector still has a half-sample fraction in the HEVC path: compare luma only
+        assert np.array_equal(x, y) or x.shape != a.interior()[0].shape
+
+
 # ---- 16-bit samples (10-bit video), SURVEY §8 row b5 ---------------------------------------------------------------------
 def make_pictures16(w, h, seed, n=3, kind="synth"):
     rng = np.random.default_rng(seed + 1000)
