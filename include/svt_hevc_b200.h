@@ -374,6 +374,29 @@ int svtb200_dlf_picture16(const svtb200_yuv_picture *recon, const uint8_t *verti
 int svtb200_dlf_picture16_dev(const svtb200_yuv_picture *recon, const uint8_t *vertical_bs, const uint8_t *horizontal_bs,
                               const uint8_t *qp_array, const svtb200_dlf_params *prm, void *cuda_stream);
 
+/* N3: the boundary strengths on the device, so that deblocking needs no host-built arrays.  CalculateBSForPUBoundary (Codec/EbDeblockingFilter.c:109),
+ * SetBSArrayBasedOnPUBoundary (:339), SetBSArrayBasedOnTUBoundary (:472), call sites Codec/EbCodingLoop.c:3554,4329,4364.  The encode pass sets a CU's
+ * strengths when that CU is coded, from its neighbour arrays; its own cbf entries and everything left of / above it are final by then, so the result
+ * is a function of the picture's final maps:
+ *   cu_map  : one svtb200_cu_info per 8x8 luma block, raster, cu_stride entries per row -- CodingUnit_t::predictionModeFlag, PredictionUnit_t::
+ *             interPredDirectionIndex and mv[2] (quarter-pel) of the CU covering the block, and that CU's size
+ *   cbf_map : one byte per 4x4 luma block (PictureControlSet_t::cbfMapArray: lumaCbf of the TU covering it), cbf_stride entries per row
+ *   slice_type 0 = B, 1 = P, 2 = I; ref_poc_l0 / l1 = refPOC of refPicPtrArray[REF_LIST_0 / 1]
+ * Output: the [n_lcu][256] arrays svtb200_dlf_picture consumes.  One tile; transform depth 0 except 64x64 CUs (four 32x32 TUs), as the encoder codes. */
+typedef struct svtb200_cu_info {
+    int16_t mv[2][2];       /* [list][x, y], quarter-pel */
+    uint8_t pred_dir;       /* 0 = list 0, 1 = list 1, 2 = bi (inter CUs) */
+    uint8_t intra;          /* predictionModeFlag == INTRA_MODE */
+    uint8_t log2_cu_size;   /* 3 .. 6 */
+    uint8_t reserved;
+} svtb200_cu_info;          /* 12 bytes */
+int svtb200_dlf_bs_picture(const svtb200_cu_info *cu_map, uint32_t cu_stride, const uint8_t *cbf_map, uint32_t cbf_stride, uint16_t pic_width,
+                           uint16_t pic_height, uint8_t slice_type, uint64_t ref_poc_l0, uint64_t ref_poc_l1, uint8_t *vertical_bs,
+                           uint8_t *horizontal_bs);
+int svtb200_dlf_bs_picture_dev(const svtb200_cu_info *cu_map_dev, uint32_t cu_stride, const uint8_t *cbf_map_dev, uint32_t cbf_stride,
+                               uint16_t pic_width, uint16_t pic_height, uint8_t slice_type, uint64_t ref_poc_l0, uint64_t ref_poc_l1,
+                               uint8_t *vertical_bs_dev, uint8_t *horizontal_bs_dev, void *cuda_stream);
+
 /* Leaf entry points, reference prototypes (EbDeblockingFilter.h:245-273). In-place on host memory; the caller states how
  * far the plane extends around the edge start via the fixed footprint: 4 samples either side, 4 (luma) / 2 (chroma) along. */
 int svtb200_Luma4SampleEdgeDLFCore(uint8_t *edgeStartFilteredSamplePtr, uint32_t reconLumaPicStride, uint8_t isVerticalEdge,

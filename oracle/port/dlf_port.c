@@ -11,6 +11,7 @@
  */
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "svt_hevc_b200.h"
 
@@ -169,3 +170,70 @@ int port_dlf_picture(const svtb200_yuv_picture *rec, const uint8_t *vbs, const u
 { return dlf_picture_impl(rec, vbs, hbs, qp, p, 0); }
 int port_dlf_picture16(const svtb200_yuv_picture *rec, const uint8_t *vbs, const uint8_t *hbs, const uint8_t *qp, const svtb200_dlf_params *p)
 { return dlf_picture_impl(rec, vbs, hbs, qp, p, 1); }
+
+/* ---- boundary-strength derivation --------------------------------------------------------------------------------
+ * Restated CU by CU the way the encode pass runs it (Codec/EbCodingLoop.c:3554,4329,4364): for every CU of every LCU, SetBSArrayBasedOnPUBoundary
+ * (Codec/EbDeblockingFilter.c:339: the CU's top row and left column against the neighbour arrays, skipped on the picture edge) and, for 64x64 CUs,
+ * SetBSArrayBasedOnTUBoundary (:472) for the four 32x32 TUs; per edge CalculateBSForPUBoundary (:109) / CalculateBSForTUBoundaryInsidePU (:440).
+ * The neighbour arrays are read from the final maps (the neighbours are coded before the CU, the CU's own cbf entries are written before the call). */
+static int port_mv_far(const svtb200_cu_info *a, int la, const svtb200_cu_info *b, int lb)
+{
+    return abs(a->mv[la][0] - b->mv[lb][0]) >= 4 || abs(a->mv[la][1] - b->mv[lb][1]) >= 4;
+}
+static uint8_t port_bs_pu(const svtb200_cu_info *pu, const svtb200_cu_info *nb, int cbf_here, int cbf_nb, int slice_type, uint64_t poc0, uint64_t poc1)
+{
+    if (pu->intra || nb->intra) return 2;
+    int c1;
+    if (slice_type == 1) c1 = port_mv_far(pu, 0, nb, 0);
+    else {
+        switch (pu->pred_dir + nb->pred_dir * 3) {
+        case 0: c1 = port_mv_far(pu, 0, nb, 0); break;
+        case 1: c1 = poc1 != poc0 || port_mv_far(pu, 1, nb, 0); break;
+        case 3: c1 = poc0 != poc1 || port_mv_far(pu, 0, nb, 1); break;
+        case 4: c1 = port_mv_far(pu, 1, nb, 1); break;
+        case 8:
+            if (poc0 == poc1) c1 = (port_mv_far(pu, 0, nb, 0) || port_mv_far(pu, 1, nb, 1)) && (port_mv_far(pu, 0, nb, 1) || port_mv_far(pu, 1, nb, 0));
+            else c1 = port_mv_far(pu, 0, nb, 0) || port_mv_far(pu, 1, nb, 1);
+            break;
+        default: c1 = 1; break;
+        }
+    }
+    return (uint8_t)(c1 | (cbf_here || cbf_nb));
+}
+
+int port_dlf_bs_picture(const svtb200_cu_info *cu_map, uint32_t cu_stride, const uint8_t *cbf, uint32_t cbf_stride, uint16_t W, uint16_t H, uint8_t slice_type,
+                        uint64_t poc0, uint64_t poc1, uint8_t *vbs, uint8_t *hbs)
+{
+    const int cols = (W + 63) / 64, rows = (H + 63) / 64;
+    memset(vbs, 0, (size_t)cols * rows * 256);
+    memset(hbs, 0, (size_t)cols * rows * 256);
+    for (int ly = 0; ly < rows; ++ly)
+        for (int lx = 0; lx < cols; ++lx) {
+            uint8_t *v = vbs + (size_t)(ly * cols + lx) * 256, *h = hbs + (size_t)(ly * cols + lx) * 256;
+            /* the CUs of this LCU: every 8x8 block whose position is a multiple of its CU size starts one */
+            for (int by = 0; by < 64; by += 8)
+                for (int bx = 0; bx < 64; bx += 8) {
+                    const int x0 = lx * 64 + bx, y0 = ly * 64 + by;
+                    if (x0 >= W || y0 >= H) continue;
+                    const svtb200_cu_info *cu = &cu_map[(size_t)(y0 >> 3) * cu_stride + (x0 >> 3)];
+                    const int size = 1 << cu->log2_cu_size;
+                    if ((bx & (size - 1)) || (by & (size - 1))) continue;
+                    if (y0 != 0)          /* horizontal PU boundary: the CU's top row (tileTopBoundary == picture top here) */
+                        for (int x = x0; x < x0 + size && x < W; x += 4)
+                            h[((x & 63) >> 2) + ((y0 & 63) >> 2) * 16] = port_bs_pu(cu, &cu_map[(size_t)((y0 >> 3) - 1) * cu_stride + (x >> 3)], cbf[(size_t)(y0 >> 2) * cbf_stride + (x >> 2)],
+                                                                                   cbf[(size_t)((y0 >> 2) - 1) * cbf_stride + (x >> 2)], slice_type, poc0, poc1);
+                    if (x0 != 0)
+                        for (int y = y0; y < y0 + size && y < H; y += 4)
+                            v[((x0 & 63) >> 2) + ((y & 63) >> 2) * 16] = port_bs_pu(cu, &cu_map[(size_t)(y >> 3) * cu_stride + (x0 >> 3) - 1], cbf[(size_t)(y >> 2) * cbf_stride + (x0 >> 2)],
+                                                                                   cbf[(size_t)(y >> 2) * cbf_stride + (x0 >> 2) - 1], slice_type, poc0, poc1);
+                    if (size == 64 && !cu->intra)      /* TU boundaries inside the CU: the 32-sample cross; only the inter path sets them (EbCodingLoop.c:4328) */
+                        for (int t = 0; t < 64; t += 4) {
+                            if (x0 + t < W && y0 + 32 < H)
+                                h[(t >> 2) + 8 * 16] = (cbf[(size_t)((y0 + 32) >> 2) * cbf_stride + ((x0 + t) >> 2)] || cbf[(size_t)(((y0 + 32) >> 2) - 1) * cbf_stride + ((x0 + t) >> 2)]);
+                            if (y0 + t < H && x0 + 32 < W)
+                                v[8 + (t >> 2) * 16] = (cbf[(size_t)((y0 + t) >> 2) * cbf_stride + ((x0 + 32) >> 2)] || cbf[(size_t)((y0 + t) >> 2) * cbf_stride + ((x0 + 32) >> 2) - 1]);
+                        }
+                }
+        }
+    return 0;
+}

@@ -263,3 +263,72 @@ int svtref_dlf_sao_stats_picture16(const svtb200_yuv_picture *recon, const svtb2
     free(lcus); free(pcs->lcuPtrArray); free(pcs->verticalEdgeBSArray); free(pcs->horizontalEdgeBSArray); free(pcs); free(scs); free(ec);
     return 0;
 }
+
+/* ---- boundary strengths: the reference's OWN SetBSArrayBasedOnPUBoundary / SetBSArrayBasedOnTUBoundary (Codec/EbDeblockingFilter.c:339,472), called CU by
+ * CU like the encode pass does (Codec/EbCodingLoop.c:3554,4329,4364), with the neighbour arrays of each call filled from the picture's final maps (the
+ * blocks left of / above a CU are coded before it; its own cbf entries are written before the call, :4320-4326). */
+#include "EbNeighborArrays.h"
+#include "EbUtility.h"
+#include "EbReferenceObject.h"
+int svtref_dlf_bs_picture(const svtb200_cu_info *cu_map, uint32_t cu_stride, const uint8_t *cbf, uint32_t cbf_stride, uint16_t W, uint16_t H, uint8_t slice_type,
+                          uint64_t poc0, uint64_t poc1, uint8_t *vbs, uint8_t *hbs)
+{
+    const EB_U32 cols = (W + 63) / 64, rows = (H + 63) / 64, nLcu = cols * rows;
+    memset(vbs, 0, (size_t)nLcu * 256); memset(hbs, 0, (size_t)nLcu * 256);
+    EbCallback_t cb; memset(&cb, 0, sizeof cb); cb.ErrorHandler = on_error;
+    EncodeContext_t *ec = (EncodeContext_t *)calloc(1, sizeof(*ec)); ec->appCallbackPtr = &cb;
+    SequenceControlSet_t *scs = (SequenceControlSet_t *)calloc(1, sizeof(*scs));
+    scs->encodeContextPtr = ec; scs->lumaWidth = W; scs->lumaHeight = H; scs->lcuSize = 64;
+    EbObjectWrapper_t scsWrap; memset(&scsWrap, 0, sizeof scsWrap); scsWrap.objectPtr = scs;
+    PictureControlSet_t *pcs = (PictureControlSet_t *)calloc(1, sizeof(*pcs));
+    pcs->sequenceControlSetWrapperPtr = &scsWrap;
+    pcs->sliceType = slice_type == 0 ? EB_B_PICTURE : slice_type == 1 ? EB_P_PICTURE : EB_I_PICTURE;
+    /* the reference indexes cbfMapArray with lumaWidth >> 2 entries per row */
+    pcs->cbfMapArray = (EB_U8 *)calloc((size_t)(W >> 2) * (H >> 2), 1);
+    for (int y = 0; y < H >> 2; ++y) memcpy(pcs->cbfMapArray + (size_t)y * (W >> 2), cbf + (size_t)y * cbf_stride, W >> 2);
+    EbReferenceObject_t ro[2]; memset(ro, 0, sizeof ro); ro[0].refPOC = poc0; ro[1].refPOC = poc1;
+    EbObjectWrapper_t rw[2]; memset(rw, 0, sizeof rw); rw[0].objectPtr = &ro[0]; rw[1].objectPtr = &ro[1];
+    pcs->refPicPtrArray[0] = &rw[0]; pcs->refPicPtrArray[1] = &rw[1];
+    /* neighbour arrays at the 4-sample granularity the callee indexes them with (LOG_MIN_PU_SIZE) */
+    NeighborArrayUnit_t modeNA, mvNA; memset(&modeNA, 0, sizeof modeNA); memset(&mvNA, 0, sizeof mvNA);
+    modeNA.topArray = (EB_U8 *)calloc(W / 4 + 16, 1); modeNA.leftArray = (EB_U8 *)calloc(H / 4 + 16, 1);
+    mvNA.topArray = (EB_U8 *)calloc(W / 4 + 16, sizeof(MvUnit_t)); mvNA.leftArray = (EB_U8 *)calloc(H / 4 + 16, sizeof(MvUnit_t));
+    for (EB_U32 lcu = 0; lcu < nLcu; ++lcu) {
+        const EB_U32 ox = (lcu % cols) * 64, oy = (lcu / cols) * 64;
+        for (EB_U32 ci = 0; ci < CU_MAX_COUNT; ++ci) {
+            const CodedUnitStats_t *st = GetCodedUnitStats(ci);
+            const EB_U32 x0 = ox + st->originX, y0 = oy + st->originY;
+            if (x0 >= W || y0 >= H) continue;
+            const svtb200_cu_info *me = &cu_map[(size_t)(y0 >> 3) * cu_stride + (x0 >> 3)];
+            if ((1u << me->log2_cu_size) != st->size) continue;       /* not a CU of this picture's partitioning */
+            for (EB_U32 k = 0; k < st->size && x0 + k < W; k += 4) {  /* row above */
+                if (y0 == 0) break;
+                const svtb200_cu_info *n = &cu_map[(size_t)((y0 >> 3) - 1) * cu_stride + ((x0 + k) >> 3)];
+                MvUnit_t *m = (MvUnit_t *)mvNA.topArray + ((x0 + k) >> 2);
+                modeNA.topArray[(x0 + k) >> 2] = n->intra ? INTRA_MODE : INTER_MODE;
+                m->predDirection = n->pred_dir; m->mv[0].x = n->mv[0][0]; m->mv[0].y = n->mv[0][1]; m->mv[1].x = n->mv[1][0]; m->mv[1].y = n->mv[1][1];
+            }
+            for (EB_U32 k = 0; k < st->size && y0 + k < H; k += 4) {  /* column to the left */
+                if (x0 == 0) break;
+                const svtb200_cu_info *n = &cu_map[(size_t)((y0 + k) >> 3) * cu_stride + (x0 >> 3) - 1];
+                MvUnit_t *m = (MvUnit_t *)mvNA.leftArray + ((y0 + k) >> 2);
+                modeNA.leftArray[(y0 + k) >> 2] = n->intra ? INTRA_MODE : INTER_MODE;
+                m->predDirection = n->pred_dir; m->mv[0].x = n->mv[0][0]; m->mv[0].y = n->mv[0][1]; m->mv[1].x = n->mv[1][0]; m->mv[1].y = n->mv[1][1];
+            }
+            PredictionUnit_t pu; memset(&pu, 0, sizeof pu);
+            pu.interPredDirectionIndex = me->pred_dir; pu.mv[0].x = me->mv[0][0]; pu.mv[0].y = me->mv[0][1]; pu.mv[1].x = me->mv[1][0]; pu.mv[1].y = me->mv[1][1];
+            CodingUnit_t cu; memset(&cu, 0, sizeof cu);
+            cu.predictionModeFlag = me->intra ? INTRA_MODE : INTER_MODE;
+            /* the picture is partial in its last LCU row / column: the callee walks the whole CU edge, so clip by giving it only CUs that lie inside (the
+             * encoder never codes a CU crossing the picture edge) */
+            if (x0 + st->size > W || y0 + st->size > H) continue;
+            if (st->size == 64 && !me->intra) {      /* inter 64x64: four 32x32 TUs (EbCodingLoop.c:4328) */
+                for (int t = 0; t < 4; ++t)
+                    SetBSArrayBasedOnTUBoundary(x0 + (t & 1) * 32, y0 + (t >> 1) * 32, 32, 32, st, (EB_MODETYPE)cu.predictionModeFlag, ox, oy, pcs, hbs + (size_t)lcu * 256, vbs + (size_t)lcu * 256);
+            }
+            SetBSArrayBasedOnPUBoundary(&modeNA, &mvNA, &pu, &cu, st, ox, oy, x0 == 0 ? EB_TRUE : EB_FALSE, y0 == 0 ? EB_TRUE : EB_FALSE, pcs, hbs + (size_t)lcu * 256, vbs + (size_t)lcu * 256);
+        }
+    }
+    free(modeNA.topArray); free(modeNA.leftArray); free(mvNA.topArray); free(mvNA.leftArray); free(pcs->cbfMapArray); free(pcs); free(scs); free(ec);
+    return 0;
+}

@@ -570,6 +570,25 @@ def tq_batch_dev(src, pred, recon, coeff_struct, jobs_ptr, n_jobs, nz_ptr, strea
                                      C.c_void_p(nz_ptr), C.c_void_p(stream)))
 
 
+CU_INFO_DTYPE = np.dtype([("mv", "<i2", (2, 2)), ("pred_dir", "u1"), ("intra", "u1"), ("log2_cu_size", "u1"), ("reserved", "u1")])
+assert CU_INFO_DTYPE.itemsize == 12
+
+
+def dlf_bs_picture(cu_map, cbf_map, width, height, slice_type, ref_poc_l0=0, ref_poc_l1=16):
+    """boundary strengths from the picture's final mode / motion / cbf maps -> (vertical_bs, horizontal_bs), each [n_lcu][256] (row N3)"""
+    cu_map, cbf_map = np.ascontiguousarray(cu_map), np.ascontiguousarray(cbf_map, np.uint8)
+    n_lcu = ((width + 63) // 64) * ((height + 63) // 64)
+    v, h = np.zeros((n_lcu, 256), np.uint8), np.zeros((n_lcu, 256), np.uint8)
+    check(lib().svtb200_dlf_bs_picture(_u8p(cu_map), C.c_uint32(cu_map.shape[1]), _u8p(cbf_map), C.c_uint32(cbf_map.shape[1]), C.c_uint16(width), C.c_uint16(height),
+                                       C.c_uint8(slice_type), C.c_uint64(ref_poc_l0), C.c_uint64(ref_poc_l1), _u8p(v), _u8p(h)))
+    return v, h
+
+
+def dlf_bs_picture_dev(cu_ptr, cu_stride, cbf_ptr, cbf_stride, width, height, slice_type, ref_poc_l0, ref_poc_l1, vbs_ptr, hbs_ptr, stream=0):
+    check(lib().svtb200_dlf_bs_picture_dev(C.c_void_p(cu_ptr), C.c_uint32(cu_stride), C.c_void_p(cbf_ptr), C.c_uint32(cbf_stride), C.c_uint16(width), C.c_uint16(height),
+                                           C.c_uint8(slice_type), C.c_uint64(ref_poc_l0), C.c_uint64(ref_poc_l1), C.c_void_p(vbs_ptr), C.c_void_p(hbs_ptr), C.c_void_p(stream)))
+
+
 def dlf_picture_dev(recon, vbs_ptr, hbs_ptr, qp_ptr, prm, stream=0):
     check(lib().svtb200_dlf_picture_dev(C.byref(recon), C.c_void_p(vbs_ptr), C.c_void_p(hbs_ptr), C.c_void_p(qp_ptr), C.byref(prm), C.c_void_p(stream)))
 

@@ -11,7 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-STAGE = [("me_picture_kernel<1>", "me_subpel"), ("me_picture_kernel<0>", "me_int"), ("ois_picture", "ois"), ("mc_batch", "mc"), ("tq_batch", "tq"), ("dlf_pass", "dlf"),
+STAGE = [("me_picture_kernel<1>", "me_subpel"), ("me_picture_kernel<0>", "me_int"), ("ois_", "ois"), ("mc_batch", "mc"), ("tq_batch", "tq"), ("dlf_pass", "dlf"),
          ("sao_stats", "sao_stats"), ("sao_apply", "sao_apply")]
 
 
