@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(ST_NT) sao_stats_kernel(const __grid_constant_
 // vertical compares of a row serve the next row (sign(v[y] - v[y+1]) = -sign(v[y+1] - v[y])), and the three rows a sample needs live in registers as the
 // strip walks down.  Only the band-offset bins keep the thread-private shared-memory histogram.  Warps 0-3: luma (16 word columns x 8 strips), warp 4: Cb,
 // warp 5: Cr (8 word columns x 4 strips).  Same 62 x 62 interior rule, same H3 composition, same output layout as sao_stats_kernel.
-constexpr int ST2_NT = 192;
+constexpr int ST2_NT = 192, ST2_P = ST2_NT + 1;
 // 0xff where the byte's top bit is set, else 0: PRMT with the sign-replicate bit of every selector nibble (__byte_perm() masks that bit off, hence the PTX)
 __device__ __forceinline__ uint32_t msb_mask(uint32_t w)
 {
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(ST2_NT) sao_stats2_kernel(const __grid_constan
     // reconstructed blocks of the three components with a one-word margin on every side: luma 66 rows x 72 bytes, chroma 34 rows x 40 bytes each
     __shared__ __align__(16) uint8_t s_y[66 * 72];
     __shared__ __align__(16) uint8_t s_c[2][34 * 40];
-    __shared__ int s_bo[32 * ST2_NT];            // thread-private band histograms, word = (count << 16) + sum(diff)
+    __shared__ int s_bo[32 * ST2_P];             // thread-private band histograms [band][thread], word = (count << 16) + sum(diff); odd pitch: see the reduction
     __shared__ int s_eo[3][32];                  // per component: 4 types x (4 counts, 4 sums)
     const int lcu = blockIdx.x, lx = lcu % A.cols, ly = lcu / A.cols;
     const int wid = threadIdx.x >> 5;
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(ST2_NT) sao_stats2_kernel(const __grid_constan
     }
     int *mybo = s_bo + threadIdx.x;
 #pragma unroll 8
-    for (int k = 0; k < 32; ++k) mybo[k * ST2_NT] = 0;
+    for (int k = 0; k < 32; ++k) mybo[k * ST2_P] = 0;
     if (threadIdx.x < 96) s_eo[threadIdx.x >> 5][threadIdx.x & 31] = 0;
     __syncthreads();
     // ---- strips ----
@@ -223,7 +223,11 @@ __global__ void __launch_bounds__(ST2_NT) sao_stats2_kernel(const __grid_constan
         uint32_t colmask = 0xffffffffu;                                               // 62 x 62 interior: the first / last sample of a row never counts
         if (xw == 0) colmask &= 0xffffff00u;
         if (xw == wpr - 1) colmask &= 0x00ffffffu;
+        const uint8_t *srow = src + (size_t)y0 * A.src[c].stride + 4 * xw;
+        uint32_t sv_next = *(const uint32_t *)srow;                                   // the source word of a row is fetched one row ahead
         for (int y = y0; y < y1; ++y) {
+            const uint32_t sv = sv_next;
+            if (y + 1 < y1) sv_next = *(const uint32_t *)(srow + (size_t)(y + 1 - y0) * A.src[c].stride);
             const uint32_t *nr = (const uint32_t *)(blk + (y + 2) * pitch) + xw;      // row y + 1
             const uint32_t dL = nr[0], dC = nr[1], dR = nr[2];
             const uint32_t v = cC;
@@ -233,7 +237,6 @@ __global__ void __launch_bounds__(ST2_NT) sao_stats2_kernel(const __grid_constan
             cmp4(v, Lw, gL, lL); cmp4(v, Rw, gR, lR); cmp4(v, dC, gD, lD); cmp4(v, DL, gDL, lDL); cmp4(v, DR, gDR, lDR);
             if (y >= 1 && y < lh - 1) {
                 const uint32_t valid01 = colmask & 0x01010101u;
-                const uint32_t sv = *(const uint32_t *)(src + (size_t)y * A.src[c].stride + 4 * xw);
                 // diff = clipToSigned8Bit(src - rec), packed s8
                 const uint32_t dpos = __vminu4(__vsubus4(sv, v), 0x7f7f7f7fu), dneg = __vminu4(__vsubus4(v, sv), 0x80808080u);
                 const uint32_t d = __vsub4(dpos, dneg);
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(ST2_NT) sao_stats2_kernel(const __grid_constan
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
                     if (!((colmask >> (8 * b)) & 1)) continue;
-                    mybo[((v >> (8 * b + 3)) & 31) * ST2_NT] += 65536 + (int)(signed char)(d >> (8 * b));
+                    mybo[((v >> (8 * b + 3)) & 31) * ST2_P] += 65536 + (int)(signed char)(d >> (8 * b));
                 }
             }
             // next row: its upper compares are this row's lower compares mirrored (v[y+1] > v[y] <=> v[y] < v[y+1]); the diagonals swap sides with the
@@ -278,21 +281,20 @@ __global__ void __launch_bounds__(ST2_NT) sao_stats2_kernel(const __grid_constan
         if (q < 4) o->eo_count[tt][q] = (uint16_t)s_eo[cc][k]; else o->eo_diff[tt][q - 4] = s_eo[cc][k];
         if (k < 4) { o->eo_diff[k][4] = 0; o->eo_count[k][4] = 0; }
     }
-    {
-        // band histograms: component cc owns the thread columns [first, first + n): luma 0..127, Cb 128..159, Cr 160..191
-        const int lane = threadIdx.x & 31;
-        for (int item = wid; item < 96; item += ST2_NT / 32) {
-            const int cc = item >> 5, band = item & 31;
-            const int first = cc == 0 ? 0 : 96 + 32 * cc, n = cc == 0 ? 128 : 32;
-            int dsum = 0, csum = 0;
-            for (int q = lane; q < n; q += 32) {
-                const int w = s_bo[band * ST2_NT + first + q], dd = (int)(short)(w & 0xffff);
-                dsum += dd; csum += (w - dd) >> 16;
-            }
-            dsum = __reduce_add_sync(0xffffffffu, dsum);
-            csum = __reduce_add_sync(0xffffffffu, csum);
-            if (lane == 0) { svtb200_sao_stats *o = A.out + (size_t)lcu * 3 + cc; o->bo_diff[band] = dsum; o->bo_count[band] = (uint16_t)csum; }
+    // band histograms: component cc owns the thread columns [first, first + n): luma 0..127, Cb 128..159, Cr 160..191.  One thread per (component,
+    // band) walks its row of the [band][thread] table -- the odd pitch puts the 32 rows a warp reads at the same column into 32 different banks -- and
+    // adds four packed words at a time before unpacking (4 x 32 samples: count <= 128, |sum of differences| <= 16 256, both inside their half word).
+    if (threadIdx.x < 96) {
+        const int cc = threadIdx.x >> 5, band = threadIdx.x & 31;
+        const int first = cc == 0 ? 0 : 96 + 32 * cc, n = cc == 0 ? 128 : 32;
+        const int *row = s_bo + band * ST2_P + first;
+        int dsum = 0, csum = 0;
+        for (int q = 0; q < n; q += 4) {
+            const int w = row[q] + row[q + 1] + row[q + 2] + row[q + 3], dd = (int)(short)(w & 0xffff);
+            dsum += dd; csum += (w - dd) >> 16;
         }
+        svtb200_sao_stats *o = A.out + (size_t)lcu * 3 + cc;
+        o->bo_diff[band] = dsum; o->bo_count[band] = (uint16_t)csum;
     }
 }
 

@@ -535,13 +535,13 @@ __device__ void tq_warp_fast(const TqArgs &A, const svtb200_tq_job &t, const int
             }
         } else {
 #pragma unroll
-            for (int c = 0; c < N / 16; ++c) {
-                const uint4 a = ((const uint4 *)sr)[c], b = ((const uint4 *)pr)[c];
-                const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+            for (int c = 0; c < N / 8; ++c) {      // 8-byte vectors: the chroma planes of a picture padded by 40 samples are 8-, not 16-byte aligned
+                const uint2 a = ((const uint2 *)sr)[c], b = ((const uint2 *)pr)[c];
+                const uint32_t aw[2] = {a.x, a.y}, bw[2] = {b.x, b.y};
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {      // bytes -> u16 pairs, then the 16-bit difference (|difference| <= 255)
-                    x[8 * c + 2 * q] = __vsub2(__byte_perm(aw[q], 0, 0x4140), __byte_perm(bw[q], 0, 0x4140));
-                    x[8 * c + 2 * q + 1] = __vsub2(__byte_perm(aw[q], 0, 0x4342), __byte_perm(bw[q], 0, 0x4342));
+                for (int q = 0; q < 2; ++q) {      // bytes -> u16 pairs, then the 16-bit difference (|difference| <= 255)
+                    x[4 * c + 2 * q] = __vsub2(__byte_perm(aw[q], 0, 0x4140), __byte_perm(bw[q], 0, 0x4140));
+                    x[4 * c + 2 * q + 1] = __vsub2(__byte_perm(aw[q], 0, 0x4342), __byte_perm(bw[q], 0, 0x4342));
                 }
             }
         }
@@ -596,10 +596,10 @@ __device__ void tq_warp_fast(const TqArgs &A, const svtb200_tq_job &t, const int
     if (!want_recon) return;
     if (nz == 0) {                      // prediction = reconstruction (copied when the two pictures differ)
         if (on && r != p) {
-            const uint4 *pr = (const uint4 *)(p + (size_t)lane * ps * BPS);
-            uint4 *rr = (uint4 *)(r + (size_t)lane * rs * BPS);
+            const uint2 *pr = (const uint2 *)(p + (size_t)lane * ps * BPS);
+            uint2 *rr = (uint2 *)(r + (size_t)lane * rs * BPS);
 #pragma unroll
-            for (int c = 0; c < N * BPS / 16; ++c) rr[c] = pr[c];
+            for (int c = 0; c < N * BPS / 8; ++c) rr[c] = pr[c];
         }
         return;
     }
@@ -653,27 +653,27 @@ __device__ void tq_warp_fast(const TqArgs &A, const svtb200_tq_job &t, const int
             }
         } else {
 #pragma unroll
-            for (int c = 0; c < N / 16; ++c) {
-                const uint4 b = ((const uint4 *)pr)[c];
-                const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
-                uint32_t o[4];
+            for (int c = 0; c < N / 8; ++c) {
+                const uint2 b = ((const uint2 *)pr)[c];
+                const uint32_t bw[2] = {b.x, b.y};
+                uint32_t o[2];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < 2; ++q) {
                     int v[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const uint32_t w = rw[8 * c + 2 * q + (e >> 1)];
+                        const uint32_t w = rw[4 * c + 2 * q + (e >> 1)];
                         v[e] = min(max((int)((bw[q] >> (8 * e)) & 0xff) + (int)(short)((e & 1) ? (w >> 16) : (w & 0xffff)), 0), 255);
                     }
                     o[q] = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
                 }
-                ((uint4 *)rr)[c] = make_uint4(o[0], o[1], o[2], o[3]);
+                ((uint2 *)rr)[c] = make_uint2(o[0], o[1]);
             }
         }
     }
 }
 
-// eligibility of the warp path (uniform per TU): a full-shape 16x16 / 32x32 DCT TU without post-quantisation flags whose rows are 16-byte accessible
+// eligibility of the warp path (uniform per TU): a full-shape 16x16 / 32x32 DCT TU without post-quantisation flags whose rows are vector accessible
 template <bool HBD>
 __device__ __forceinline__ bool tq_fast_ok(const TqArgs &A, const svtb200_tq_job &t)
 {
@@ -683,7 +683,7 @@ __device__ __forceinline__ bool tq_fast_ok(const TqArgs &A, const svtb200_tq_job
     const uintptr_t a = (uintptr_t)(A.src.p[pl] + ((size_t)(A.src.oy[pl] + t.y) * A.src.stride[pl] + A.src.ox[pl] + t.x) * BPS) | (uintptr_t)(A.src.stride[pl] * BPS) |
                         (uintptr_t)(A.pred.p[pl] + ((size_t)(A.pred.oy[pl] + t.y) * A.pred.stride[pl] + A.pred.ox[pl] + t.x) * BPS) | (uintptr_t)(A.pred.stride[pl] * BPS) |
                         (uintptr_t)(A.recon.p[pl] + ((size_t)(A.recon.oy[pl] + t.y) * A.recon.stride[pl] + A.recon.ox[pl] + t.x) * BPS) | (uintptr_t)(A.recon.stride[pl] * BPS);
-    return (a & 15) == 0;
+    return (a & (HBD ? 15 : 7)) == 0;      // 8-bit rows move as 8-byte vectors, 16-bit rows as 16-byte vectors
 }
 
 // Batch kernel: a CTA of two warps takes two consecutive TUs; each warp runs its TU alone when the warp path applies, the rest go through the general
