@@ -510,17 +510,41 @@ __device__ __forceinline__ void fold16(const uint32_t (&x)[N / 2], uint32_t (&fs
     }
 }
 
-template <int N, bool HBD>
-__device__ void tq_warp_fast(const TqArgs &A, const svtb200_tq_job &t, const int j, int16_t *T)
+// PAIR (N = 16 only): the two half-warps run two TUs at once -- lanes 0-15 the TU `t` / `j` / `T` they were handed, lanes 16-31 theirs; every
+// per-TU quantity below is per lane, the tile exchanges stay inside a half-warp's own tile, and what used to be an early return is a predicate.
+// The function is a real call (three instantiations inlined into the job loop of the kernel spilled at the 128-register budget): what it needs of the
+// kernel's parameter block travels by value in TuPtrs, the tiles are namespace-scope __shared__ arrays, and the picture pointers are declared global
+// to the compiler -- a callee would otherwise reach all of them through generic addresses.
+struct TuPtrs { const uint8_t *s, *p; uint8_t *r; int16_t *co; uint32_t *nz; int ss, ps, rs, cs; };
+template <bool HBD>
+__device__ __forceinline__ TuPtrs tu_ptrs(const TqArgs &A, const svtb200_tq_job &t, int j)
 {
+    constexpr int BPS = HBD ? 2 : 1;
+    const int pl = t.plane;
+    TuPtrs P;
+    P.ss = A.src.stride[pl]; P.ps = A.pred.stride[pl]; P.rs = A.recon.stride[pl]; P.cs = A.cstride[pl];
+    P.s = A.src.p[pl] + ((size_t)(A.src.oy[pl] + t.y) * P.ss + A.src.ox[pl] + t.x) * BPS;
+    P.p = A.pred.p[pl] + ((size_t)(A.pred.oy[pl] + t.y) * P.ps + A.pred.ox[pl] + t.x) * BPS;
+    P.r = A.recon.p[pl] + ((size_t)(A.recon.oy[pl] + t.y) * P.rs + A.recon.ox[pl] + t.x) * BPS;
+    P.co = A.coeff[pl] + (size_t)t.y * P.cs + t.x;
+    P.nz = A.nz + j;
+    return P;
+}
+__shared__ __align__(16) int16_t s_tile[2][32 * TP];      // one 32x32 (or two 16x16) s16 tile per warp of the batch kernel
+
+template <int N, bool HBD, bool PAIR = false>
+__device__ __noinline__ void tq_warp_fast(const TuPtrs P, const svtb200_tq_job t, const int tile_off, const bool live = true)
+{
+    static_assert(!PAIR || N == 16, "two TUs per warp: 16x16 only");
     constexpr int BPS = HBD ? 2 : 1, BIT_INC = HBD ? 2 : 0, MAXV = HBD ? 1023 : 255, LG = N == 32 ? 5 : 4;
-    const int lane = threadIdx.x & 31, pl = t.plane;
-    const bool on = lane < N;
-    const int ss = A.src.stride[pl], ps = A.pred.stride[pl], rs = A.recon.stride[pl], cs = A.cstride[pl];
-    const uint8_t *s = A.src.p[pl] + ((size_t)(A.src.oy[pl] + t.y) * ss + A.src.ox[pl] + t.x) * BPS;
-    const uint8_t *p = A.pred.p[pl] + ((size_t)(A.pred.oy[pl] + t.y) * ps + A.pred.ox[pl] + t.x) * BPS;
-    uint8_t *r = A.recon.p[pl] + ((size_t)(A.recon.oy[pl] + t.y) * rs + A.recon.ox[pl] + t.x) * BPS;
-    int16_t *co = A.coeff[pl] + (size_t)t.y * cs + t.x;
+    const int lane = PAIR ? (int)(threadIdx.x & 15) : (int)(threadIdx.x & 31);      // the lane's row / column inside its TU
+    const bool on = live && lane < N;
+    int16_t *T = &s_tile[0][0] + tile_off;
+    const int ss = P.ss, ps = P.ps, rs = P.rs, cs = P.cs;
+    const uint8_t *s = P.s, *p = P.p;
+    uint8_t *r = P.r;
+    int16_t *co = P.co;
+    __builtin_assume(__isGlobal(s)); __builtin_assume(__isGlobal(p)); __builtin_assume(__isGlobal(r)); __builtin_assume(__isGlobal(co)); __builtin_assume(__isGlobal(P.nz));
     const bool want_recon = !(t.flags & SVTB200_TQ_SKIP_RECON);
     const int s1 = (N == 32 ? 6 : 4) + BIT_INC, s2 = 9;
     uint32_t x[N / 2];
@@ -591,18 +615,21 @@ __device__ void tq_warp_fast(const TqArgs &A, const svtb200_tq_job &t, const int
             if (v & 1) d[v >> 1] = (d[v >> 1] & 0xffffu) | ((uint32_t)(uint16_t)rv << 16); else d[v >> 1] = (uint32_t)(uint16_t)rv;
         }
     }
-    const uint32_t nz = __reduce_add_sync(0xffffffffu, mynz);
-    if (lane == 0) A.nz[j] = nz;
-    if (!want_recon) return;
-    if (nz == 0) {                      // prediction = reconstruction (copied when the two pictures differ)
-        if (on && r != p) {
-            const uint2 *pr = (const uint2 *)(p + (size_t)lane * ps * BPS);
-            uint2 *rr = (uint2 *)(r + (size_t)lane * rs * BPS);
+    uint32_t nz;
+    if (PAIR) {
+        nz = mynz;
 #pragma unroll
-            for (int c = 0; c < N * BPS / 8; ++c) rr[c] = pr[c];
-        }
-        return;
+        for (int o = 8; o > 0; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);      // stays inside the half-warp
+    } else nz = __reduce_add_sync(0xffffffffu, mynz);
+    if (lane == 0 && live) *P.nz = nz;
+    if (want_recon && nz == 0 && on && r != p) {      // prediction = reconstruction (copied when the two pictures differ)
+        const uint2 *pr = (const uint2 *)(p + (size_t)lane * ps * BPS);
+        uint2 *rr = (uint2 *)(r + (size_t)lane * rs * BPS);
+#pragma unroll
+        for (int c = 0; c < N * BPS / 8; ++c) rr[c] = pr[c];
     }
+    const bool inv = on && want_recon && nz != 0;
+    if (!__any_sync(0xffffffffu, inv)) return;
     // ---- inverse pass 1 (along v): T[y][lane] = clip16((sum_v M[v][y] d[v] + 64) >> 7) ----
     {
         uint32_t we[N / 4], wo[N / 4];
@@ -611,7 +638,7 @@ __device__ void tq_warp_fast(const TqArgs &A, const svtb200_tq_job &t, const int
         for (int y = 0; y < N / 2; ++y) {
             int E, O;
             inv_eo<N>(we, wo, y, E, O);
-            if (on) {
+            if (inv) {
                 T[y * TP + lane] = (int16_t)clip16i((E + O + 64) >> 7);
                 T[(N - 1 - y) * TP + lane] = (int16_t)clip16i((E - O + 64) >> 7);
             }
@@ -619,7 +646,7 @@ __device__ void tq_warp_fast(const TqArgs &A, const svtb200_tq_job &t, const int
     }
     __syncwarp();
     // ---- inverse pass 2 (along u) on row y = lane, prediction, reconstruction ----
-    if (on) {
+    if (inv) {
 #pragma unroll
         for (int i = 0; i < N / 2; ++i) x[i] = ((const uint32_t *)(T + lane * TP))[i];
         uint32_t we[N / 4], wo[N / 4];
@@ -686,31 +713,40 @@ __device__ __forceinline__ bool tq_fast_ok(const TqArgs &A, const svtb200_tq_job
     return (a & (HBD ? 15 : 7)) == 0;      // 8-bit rows move as 8-byte vectors, 16-bit rows as 16-byte vectors
 }
 
-// Batch kernel: a CTA of two warps takes two consecutive TUs; each warp runs its TU alone when the warp path applies, the rest go through the general
-// path afterwards with the whole CTA.
+// Batch kernel: a CTA of two warps takes 2 x TQ_CHUNK consecutive TUs; each warp runs its TUs alone when the warp path applies, the rest go through the
+// general path afterwards with the whole CTA.
+constexpr int TQ_CHUNK = 3;
 template <bool HBD>
 __global__ void __launch_bounds__(TQ_NT, 8) tq_batch_kernel(const __grid_constant__ TqArgs A)
 {
     static_assert(TQ_NT == 64, "two warps, two TUs");
-    __shared__ __align__(16) int16_t s_a[32 * TP], s_b[32 * TP], s_q[32 * TP];
+    int16_t *s_a = s_tile[0], *s_b = s_tile[1];
+    __shared__ __align__(16) int16_t s_q[32 * TP];
     __shared__ uint32_t s_cnt;
     __shared__ __align__(16) int8_t s_m[32 * 32], s_mt[32 * 32];
     __shared__ int s_slow[2];
-    const int wid = threadIdx.x >> 5, j = 2 * blockIdx.x + wid;
-    bool fast = false;
-    if (j < A.n_jobs) {
+    // a warp takes TQ_CHUNK consecutive jobs (a 32x32 CU's luma TU and its two chroma TUs in the usual job order) one after the other; two neighbouring
+    // 16x16 TUs run side by side in its half-warps
+    const int wid = threadIdx.x >> 5, j0 = TQ_CHUNK * (2 * blockIdx.x + wid), half = (threadIdx.x >> 4) & 1;
+    const int tile = wid * 32 * TP;
+    uint32_t slow = 0;
+    for (int i = 0; i < TQ_CHUNK && j0 + i < A.n_jobs; ++i) {
+        const int j = j0 + i;
         const svtb200_tq_job t = A.jobs[j];
-        fast = tq_fast_ok<HBD>(A, t);
-        if (fast) {
-            int16_t *T = wid ? s_b : s_a;
-            if (t.size == 32) tq_warp_fast<32, HBD>(A, t, j, T); else tq_warp_fast<16, HBD>(A, t, j, T);
-        }
+        if (!tq_fast_ok<HBD>(A, t)) { slow |= 1u << i; continue; }
+        if (t.size == 32) { tq_warp_fast<32, HBD>(tu_ptrs<HBD>(A, t, j), t, tile); __syncwarp(); continue; }
+        bool pair = false;
+        svtb200_tq_job t2 = t;
+        if (i + 1 < TQ_CHUNK && j + 1 < A.n_jobs) { t2 = A.jobs[j + 1]; pair = t2.size == 16 && tq_fast_ok<HBD>(A, t2); }
+        if (pair) { const svtb200_tq_job th = half ? t2 : t; tq_warp_fast<16, HBD, true>(tu_ptrs<HBD>(A, th, j + half), th, tile + half * 16 * TP); ++i; }
+        else tq_warp_fast<16, HBD>(tu_ptrs<HBD>(A, t, j), t, tile);
+        __syncwarp();
     }
-    if ((threadIdx.x & 31) == 0) s_slow[wid] = (j < A.n_jobs && !fast) ? 1 : 0;
+    if ((threadIdx.x & 31) == 0) s_slow[wid] = (int)slow;
     __syncthreads();
-    const int slow0 = s_slow[0], slow1 = s_slow[1];
-    if (slow0) { tq_cta_path<HBD>(A, 2 * blockIdx.x, s_a, s_b, s_q, s_cnt, s_m, s_mt); __syncthreads(); }
-    if (slow1) tq_cta_path<HBD>(A, 2 * blockIdx.x + 1, s_a, s_b, s_q, s_cnt, s_m, s_mt);
+    const uint32_t all_slow = (uint32_t)s_slow[0] | ((uint32_t)s_slow[1] << TQ_CHUNK);
+    for (int k = 0; k < 2 * TQ_CHUNK; ++k)
+        if ((all_slow >> k) & 1) { tq_cta_path<HBD>(A, TQ_CHUNK * 2 * blockIdx.x + k, s_a, s_b, s_q, s_cnt, s_m, s_mt); __syncthreads(); }
 }
 
 // ---- coefficient hand-off: only coded TUs cross PCIe -------------------------------------------------------------------
@@ -922,7 +958,7 @@ static int tq_batch_dev_impl(const svtb200_yuv_picture *src, const svtb200_yuv_p
     A.recon = to_yuvw(*recon, recon->y.buf, recon->cb.buf, recon->cr.buf);
     for (int k = 0; k < 3; ++k) { A.coeff[k] = coeff->buf[k]; A.cstride[k] = (int)coeff->stride[k]; }
     A.jobs = jobs_dev; A.n_jobs = n_jobs; A.nz = nz_counts_dev;
-    if (hbd) tq_batch_kernel<true><<<(n_jobs + 1) / 2, TQ_NT, 0, (cudaStream_t)cuda_stream>>>(A); else tq_batch_kernel<false><<<(n_jobs + 1) / 2, TQ_NT, 0, (cudaStream_t)cuda_stream>>>(A);
+    if (hbd) tq_batch_kernel<true><<<(n_jobs + 2 * TQ_CHUNK - 1) / (2 * TQ_CHUNK), TQ_NT, 0, (cudaStream_t)cuda_stream>>>(A); else tq_batch_kernel<false><<<(n_jobs + 2 * TQ_CHUNK - 1) / (2 * TQ_CHUNK), TQ_NT, 0, (cudaStream_t)cuda_stream>>>(A);
     SVTB200_COUNT_LAUNCH();
     SVTB200_CUDA_TRY(cudaGetLastError());
     return SVTB200_OK;
