@@ -63,9 +63,9 @@ CONFIGS = {
 METRIC = CONFIGS[2]["metric"]
 WORKLOAD = CONFIGS[2]["workload"]
 STAGES = ["me_picture (+ sub-pel on layer 0)", "ois_picture", "mc_batch", "tq_batch", "sao_stats_picture (H3 state on layer 0: deblocked + unfiltered strips)",
-          "dlf_picture (layer 0)", "sao_apply_picture (layer 0)"]
+          "sao_decision_picture (SaoGenerationDecision; its offsets feed sao_apply on layer 0)", "dlf_picture (layer 0)", "sao_apply_picture (layer 0)"]
 # algorithmic HBM bytes per CTU of 8-bit samples; sample planes count twice at 10 bits (alg_per_ctu)
-ALG = {"me": 9384 * 2, "ois": 4096 + 21 * 5, "mc_uni": 12288, "mc_bi": 18432, "tq": 30720, "dlf": 12864, "sao_stats": 12288 + 3 * 312, "sao_apply": 12288}
+ALG = {"me": 9384 * 2, "ois": 4096 + 21 * 5, "mc_uni": 12288, "mc_bi": 18432, "tq": 30720, "dlf": 12864, "sao_stats": 12288 + 3 * 312, "sao_dec": 3 * 312 + 40 + 20, "sao_apply": 12288}
 
 
 def set_config(cid):
@@ -76,6 +76,20 @@ def set_config(cid):
     N_LCU = COLS * ROWS
     METRIC, WORKLOAD = c["metric"], c["workload"]
     return c
+
+
+# SAO decision inputs: CABAC bit estimates (1 bit = 32768) of the magnitudes MdRateEstimationContext_t holds for saoMergeFlagBits / saoTypeIndexBits /
+# saoOffsetTrunUnaryBits, and fullLambda / fullChromaLambdaSao of a QP-32 picture (lambdaModeDecision* tables, EbLambdaRateTables.h): the same values on both arms
+SAO_LAMBDA = (439162, 350000)
+
+
+def sao_rates():
+    import svtb200 as S
+    t = S.SaoRateTables()
+    t.merge_flag_bits[:] = [9000, 70000]
+    t.type_index_bits[:] = [14000, 80000, 80000, 80000, 80000, 81000]
+    t.offset_trun_unary_bits[:] = [32768 * (k + 1) if k < 7 else 32768 * 7 for k in range(8)]
+    return t
 
 
 def alg_per_ctu():
@@ -411,7 +425,9 @@ def run_b200(args):
     cap_ois = wl.ois_cap()
     n_tq = len(wl.tq_jobs)
     stream_cap = int(sum(int(j["size"]) ** 2 for j in wl.tq_jobs))       # elements of the packed coefficient stream when every TU is coded
-    small_sizes = [N_LCU * 85 * 24, (n_tq + 1) * 4, n_tq * 4, N_LCU * 3 * 312, N_LCU * 85, N_LCU * 85 * cap_ois * 4]
+    # what the host consumes of a picture: ME records, TU offsets, nz counts, SAO decisions (the statistics stay on the device: the RD decision runs there),
+    # OIS totals and candidates
+    small_sizes = [N_LCU * 85 * 24, (n_tq + 1) * 4, n_tq * 4, N_LCU * 40, N_LCU * 85, N_LCU * 85 * cap_ois * 4]
     small_offs = np.concatenate([[0], np.cumsum([(b + 255) // 256 * 256 for b in small_sizes])]).astype(int)
     small_total = int(small_offs[-1])
     frame_capacity = small_total + 2 * stream_cap        # [small results | packed coefficient stream]: one contiguous span per picture
@@ -422,6 +438,8 @@ def run_b200(args):
             self.pred_t, self.pred = dev_yuv()
             self.sao_t, self.sao_out = dev_yuv()
             self.unf_t, self.unf = dev_yuv()                 # reconstruction before deblocking (H3 statistics of layer-0 pictures)
+            self.stats_t = torch.zeros(N_LCU * 3 * 312, dtype=torch.uint8, device=dev)       # SAO statistics: consumed by the decision on the device
+            self.sao_prm_t = torch.zeros(N_LCU * 20, dtype=torch.uint8, device=dev)          # the decision in the form sao_apply reads
             self.in_t, self.in_yuv = dev_yuv()
             if hbd:
                 self.in8 = torch.zeros((H, W), dtype=torch.uint8, device=dev)      # e2e: 8-bit luma of the uploaded 10-bit picture (UnPack8BitData)
@@ -450,7 +468,8 @@ def run_b200(args):
             """point the per-picture outputs at `span` (frame_capacity bytes of device memory: this slot's own, or a picture's place in the GOP-exchange buffer)"""
             base = span.data_ptr()
             o = small_offs
-            self.p = dict(res=base + int(o[0]), off=base + int(o[1]), nz=base + int(o[2]), stats=base + int(o[3]), ois_t=base + int(o[4]), ois_c=base + int(o[5]),
+            self.p = dict(res=base + int(o[0]), off=base + int(o[1]), nz=base + int(o[2]), dec=base + int(o[3]), stats=self.stats_t.data_ptr(), sao_prm=self.sao_prm_t.data_ptr(),
+                          ois_t=base + int(o[4]), ois_c=base + int(o[5]),
                           small=base, stream=base + small_total, yint=self.in_t[0][PAD:, PAD:].data_ptr())
             if hasattr(self, "h_small"):
                 self.p.update(h_small=self.h_small.data_ptr(), h_stream=self.h_stream.data_ptr())
@@ -477,7 +496,7 @@ def run_b200(args):
         mc_bytes.append(wl.mc_alg_bytes(jobs))
     torch.cuda.synchronize()
 
-    names = (["pack"] if hbd else []) + ["me", "ois", "mc", "tq", "h3_copy", "dlf", "sao_stats", "sao_apply"] + (["pack_coeffs"] if cfg["gop_exchange"] else [])
+    names = (["pack"] if hbd else []) + ["me", "ois", "mc", "tq", "h3_copy", "dlf", "sao_stats", "sao_dec", "sao_apply"] + (["pack_coeffs"] if cfg["gop_exchange"] else [])
     # per-frame constants hoisted out of the loops (the loops should cost the host as little as a C caller would spend)
     me_cfgs = {tl: wl.me_cfg_tl(tl) for tl in set(TL_PATTERN)}
     ref_pairs = {}
@@ -486,6 +505,7 @@ def run_b200(args):
         ref_pairs[(r0, r1)] = S.yuv_struct_array([ring_yuv[r0][1], ring_yuv[r1][1]])
     d_mc_ptr = [(t.data_ptr(), n) for t, n in d_mc]
     p_tq, p_vbs, p_hbs, p_qp, p_sao_prm = d_tq.data_ptr(), d_vbs.data_ptr(), d_hbs.data_ptr(), d_qp.data_ptr(), d_sao_prm.data_ptr()
+    rates_b = sao_rates()
     hp = [tuple(t.data_ptr() for t in h_s[k]) for k in range(RING)]
 
     def pack_source(k, sl, st):
@@ -521,9 +541,11 @@ def run_b200(args):
             timed("h3_copy", lambda: S.yuv_picture_copy_dev(pred, sl.unf, st, bps))
             timed("dlf", lambda: F["dlf"](pred, p_vbs, p_hbs, p_qp, wl.dlf_prm, st))
             timed("sao_stats", lambda: F["sao_h3"](src_yuv, pred, sl.unf, P["stats"], st))
-            timed("sao_apply", lambda: F["sao_apply"](pred, sl.sao_out, p_sao_prm, (1, 1), st))
+            timed("sao_dec", lambda: S.sao_decision_picture_dev(P["stats"], COLS, ROWS, rates_b, SAO_LAMBDA[0], SAO_LAMBDA[1], 1 if hbd else 0, P["dec"], P["sao_prm"], st))
+            timed("sao_apply", lambda: F["sao_apply"](pred, sl.sao_out, P["sao_prm"], (1, 1), st))
         else:
             timed("sao_stats", lambda: F["sao_stats"](src_yuv, pred, P["stats"], st))
+            timed("sao_dec", lambda: S.sao_decision_picture_dev(P["stats"], COLS, ROWS, rates_b, SAO_LAMBDA[0], SAO_LAMBDA[1], 1 if hbd else 0, P["dec"], P["sao_prm"], st))
         if cfg["gop_exchange"] and resident:
             timed("pack_coeffs", lambda: S.tq_pack_coeffs_dev(sl.coeff, p_tq, P["nz"], n_tq, P["stream"], sl.cap, P["off"], st))
 
@@ -615,7 +637,7 @@ def run_b200(args):
         sl.ev_cmp.record(cs)
         s_small.wait_event(sl.ev_cmp)
         if "d2h" not in skip:
-            S.copy_async(sl.p["h_small"], sl.p["small"], small_total, True, s_small.cuda_stream)    # D2H: ME results, TU offsets, nz, SAO stats, OIS
+            S.copy_async(sl.p["h_small"], sl.p["small"], small_total, True, s_small.cuda_stream)    # D2H: ME results, TU offsets, nz, SAO decisions, OIS
         sl.ev_small.record(s_small)
         sl.pending = True
         finish_slot(slots[(i + 1) % NS])                                                   # frame i - NS + 1: its offsets arrived long ago, its stream goes out now
@@ -723,7 +745,7 @@ def run_b200(args):
         tot = {n: float(np.sum(v)) for n, v in stage_ms.items()}
         dom = max((n for n in tot if n not in ("h3_copy",)), key=tot.get)
         alg = {"me": alg_ctu["me"] * N_LCU, "ois": alg_ctu["ois"] * N_LCU, "mc": float(np.mean(mc_bytes)), "tq": alg_ctu["tq"] * N_LCU, "dlf": alg_ctu["dlf"] * N_LCU,
-               "h3_copy": 2 * 6144 * bps * N_LCU, "sao_stats": alg_ctu["sao_stats"] * N_LCU, "sao_apply": alg_ctu["sao_apply"] * N_LCU, "pack": alg_ctu["pack"] * N_LCU,
+               "h3_copy": 2 * 6144 * bps * N_LCU, "sao_stats": alg_ctu["sao_stats"] * N_LCU, "sao_dec": ALG["sao_dec"] * N_LCU, "sao_apply": alg_ctu["sao_apply"] * N_LCU, "pack": alg_ctu["pack"] * N_LCU,
                "pack_coeffs": 2 * 12288 * N_LCU}
         per_stage = {n: {"launch_ms_avg": float(np.mean(v)) if v else None, "launches": len(v), "share_of_step": tot[n] / sum(tot.values()),
                          "achieved_gbs": (alg[n] / (np.mean(v) * 1e-3) / 1e9) if v else None,
@@ -741,7 +763,7 @@ def run_b200(args):
         d2h = int(np.mean(d2h_bytes))
         la = np.array([[float(x) for x in t.tolist()] for t in link_all])
         kernel_names = {"me": "me_picture_kernel", "ois": "ois_picture_kernel", "mc": "mc_batch_kernel<1>" if hbd else "mc_batch8_kernel", "tq": "tq_batch_kernel",
-                        "dlf": "dlf_pass_kernel", "h3_copy": "cudaMemcpy2DAsync (device to device)", "sao_stats": "sao_stats16_kernel" if hbd else "sao_stats_kernel",
+                        "dlf": "dlf_pass_kernel", "h3_copy": "cudaMemcpy2DAsync (device to device)", "sao_stats": "sao_stats16_kernel" if hbd else "sao_stats2_kernel", "sao_dec": "sao_offsets_kernel + sao_merge_kernel",
                         "sao_apply": "sao_apply16_kernel" if hbd else "sao_apply_kernel", "pack": "pack_kernel", "pack_coeffs": "tq_pack_scan_kernel + tq_pack_copy_kernel"}
         out = {
             "metric": METRIC, "value": ctus / (ms * 1e-3), "unit": "CTU/s", "fps": ctus / (ms * 1e-3) / N_LCU,
@@ -852,7 +874,10 @@ def cpu_reference(frames):
     f_mc, f_tq = getattr(ref, "svtref_mc_batch" + sfx), getattr(ref, "svtref_tq_batch" + sfx)
     f_dlfsao = getattr(ref, "svtref_dlf_sao_stats_picture" + sfx)
     f_stats, f_apply = getattr(refsao, "svtref_sao_stats_picture" + sfx), getattr(refsao, "svtref_sao_apply_picture" + sfx)
-    for f in (ref.svtref_me_picture_rows, ref.svtref_ois_picture, f_mc, f_tq, f_dlfsao, f_stats, f_apply):
+    refdec = C.CDLL(os.path.join(ROOT, "oracle", "_ref", f"libsvtref_saodec_{variant}.so"))
+    f_dec = refdec.svtref_sao_decision_picture      # the reference's own DetermineSao*ModeOffsets / TestSaoCopyModes sequence (oracle/refinc_saodec_harness.c)
+    rates = sao_rates()
+    for f in (ref.svtref_me_picture_rows, ref.svtref_ois_picture, f_mc, f_tq, f_dlfsao, f_stats, f_apply, f_dec):
         f.restype = C.c_int
     flags = (C.c_uint8 * 2)(1, 1)
     me_cfgs = {tl: wl.me_cfg_tl(tl) for tl in set(TL_PATTERN)}
@@ -885,6 +910,8 @@ def cpu_reference(frames):
             self.coeff = S.HostCoeffPicture(W, H)
             self.nz = np.zeros(n_tq, np.uint32)
             self.stats = np.zeros((N_LCU, 3), dtype=S.SAO_STATS_DTYPE)
+            self.dec = np.zeros(N_LCU, dtype=S.SAO_DECISION_DTYPE)
+            self.prm = np.zeros(N_LCU, dtype=S.SAO_PARAMS_DTYPE)
 
         def frame(self, i):
             k = i % RING
@@ -899,9 +926,15 @@ def cpu_reference(frames):
                 # the encoder's own order: every LCU's deblocking step followed by that LCU's SAO statistics (EbCodingLoop.c:4604-4635, 4711-4748)
                 assert f_dlfsao(C.byref(self.pred.struct), C.byref(yuv[k].struct), vp(wl.vbs), vp(wl.hbs), vp(wl.qp_array), C.byref(wl.dlf_prm),
                                 vp(self.stats), None, C.c_int(1)) == 0
-                assert f_apply(C.byref(self.pred.struct), vp(wl.sao_prm), flags, C.c_int(1)) == 0
+                self.decide()
+                self.prm["type"], self.prm["band_position"], self.prm["offset"] = self.dec["type"], self.dec["band_position"], self.dec["offset"]
+                assert f_apply(C.byref(self.pred.struct), vp(self.prm), flags, C.c_int(1)) == 0
             else:
                 assert f_stats(C.byref(yuv[k].struct), C.byref(self.pred.struct), vp(self.stats), C.c_int(1)) == 0
+                self.decide()
+
+        def decide(self):
+            assert f_dec(vp(self.stats), C.c_int(COLS), C.c_int(ROWS), C.byref(rates), C.c_uint64(SAO_LAMBDA[0]), C.c_uint64(SAO_LAMBDA[1]), C.c_int(1 if hbd else 0), vp(self.dec)) == 0
 
     gate = threading.Barrier(nworkers + 1)
     errors = []

@@ -4,8 +4,9 @@
 // Replaces: DetermineSaoLumaModeOffsets / DetermineSaoChromaModeOffsets / TestSaoCopyModes (static, Codec/EbSampleAdaptiveOffsetGenerationDecision.c:44,182,437)
 // in the order SaoGenerationDecision :647-767 calls them for saoMode = 1 (presets <= M10), GetSaoOffsetsFractionBits Codec/EbMdRateEstimation.c:250.
 //
-// Design: the offsets / type of an LCU depend on that LCU's statistics only -> one thread per LCU (sao_offsets_kernel).  The merge test reads the FINAL
-// parameters of the left and top neighbours -> anti-diagonal wavefront inside ONE CTA (sao_merge_kernel: cols + rows - 1 steps, a barrier between steps).
+// Design: the offsets / type of an LCU depend on that LCU's statistics only -> one warp per LCU, lanes over bands / (type, category) pairs
+// (sao_offsets_kernel).  The merge test reads the FINAL parameters of the left and top neighbours -> anti-diagonal wavefront inside ONE CTA working out of
+// shared memory (sao_merge_kernel: cols + rows - 1 steps, a barrier between steps).
 // Scalar 64-bit integer arithmetic with the reference's own conversions (see oracle/port/sao_decision_port.c for the quirks that are kept).
 #include "common.cuh"
 
@@ -23,116 +24,6 @@ __constant__ int32_t kMinBO[2] = {-7, -31};
 
 __device__ __forceinline__ int32_t clip3(int32_t lo, int32_t hi, int32_t v) { return v < lo ? lo : (v > hi ? hi : v); }
 __device__ __forceinline__ uint32_t absu(int32_t v) { return (uint32_t)(v < 0 ? -v : v); }
-
-__device__ uint64_t offsets_fraction_bits(uint32_t sao_type, const int32_t *offset, const svtb200_sao_rate_tables *r)
-{
-    uint64_t bits = 0;
-    if (sao_type != 0) {
-        uint32_t o[4];
-        for (int k = 0; k < 4; ++k) { o[k] = absu(offset[k]); if (o[k] > 7) o[k] = 7; }
-        if (sao_type == 5) {
-            bits += 163840;                                     /* band position: 5 bits */
-            for (int k = 0; k < 4; ++k) bits += r->offset_trun_unary_bits[o[k]];
-            for (int k = 0; k < 4; ++k) bits += o[k] != 0 ? 32768 : 0;
-        } else {
-            for (int k = 0; k < 4; ++k) bits += r->offset_trun_unary_bits[o[k]];
-        }
-    }
-    return bits;
-}
-
-__device__ void luma_mode_offsets(const svtb200_sao_stats *st /* component 0 */, svtb200_sao_decision *p, uint64_t lambda, const svtb200_sao_rate_tables *r, int is10bit)
-{
-    const uint64_t maxCost = ~(uint64_t)0;
-    const uint32_t dshift = is10bit ? 4 : 0;
-    int32_t boOffset[32];
-    int64_t boIntervalDistortion[32], boBestCost = (int64_t)(maxCost >> 1), eoBestCost = (int64_t)(maxCost >> 1);
-    uint32_t bestBand = 0, bestEo = 0;
-    int32_t eoOffset[4][4];
-    const int64_t saoOffRate = r->type_index_bits[0];
-    const int64_t saoOffCost = (int64_t)(((saoOffRate * lambda) + MD_OFFSET) >> MD_SHIFT);
-
-    for (int b = 0; b < 32; ++b) {
-        boOffset[b] = st->bo_count[b] == 0 ? 0 : st->bo_diff[b] / (int32_t)st->bo_count[b];
-        boOffset[b] = clip3(kMinBO[is10bit], kMaxBO[is10bit], boOffset[b]);
-        boIntervalDistortion[b] = (-(2 * boOffset[b] * st->bo_diff[b]) + ((int32_t)st->bo_count[b] * SQR(boOffset[b]))) >> dshift;
-    }
-    for (uint32_t iv = 0; iv < 32 - 4 + 1; ++iv) {
-        int64_t d = 0;
-        for (uint32_t b = iv; b < iv + 4; ++b) d += boIntervalDistortion[b];
-        const int64_t rate = (int64_t)offsets_fraction_bits(5, &boOffset[iv], r);
-        const int64_t cost = (d << COST_PRECISION) + (((rate * lambda) + MD_OFFSET) >> MD_SHIFT);
-        if (cost < boBestCost) { boBestCost = cost; bestBand = iv; }
-    }
-    for (uint32_t t = 0; t < 4; ++t) {
-        int64_t dist = 0;
-        for (uint32_t k = 0; k < 4; ++k) {
-            eoOffset[t][k] = st->eo_count[t][k] == 0 ? 0 : st->eo_diff[t][k] / (int32_t)st->eo_count[t][k];
-            eoOffset[t][k] = clip3(kMinEO[is10bit][k], kMaxEO[is10bit][k], eoOffset[t][k]);
-            dist += (int64_t)((-(2 * eoOffset[t][k] * st->eo_diff[t][k]) + ((int32_t)st->eo_count[t][k] * SQR(eoOffset[t][k]))) >> dshift);
-        }
-        const int64_t rate = (int64_t)offsets_fraction_bits(t + 1, eoOffset[t], r);
-        const int64_t cost = (dist << COST_PRECISION) + (((rate * lambda) + MD_OFFSET) >> MD_SHIFT);
-        if (cost < eoBestCost) { eoBestCost = cost; bestEo = t; }
-    }
-    boBestCost += (((r->type_index_bits[5] * lambda) + MD_OFFSET) >> MD_SHIFT);
-    eoBestCost += (((r->type_index_bits[bestEo + 1] * lambda) + MD_OFFSET) >> MD_SHIFT);
-    if (boBestCost < saoOffCost || eoBestCost < saoOffCost) {
-        p->luma_cost = boBestCost < eoBestCost ? boBestCost : eoBestCost;
-        if (p->luma_cost == boBestCost) {
-            p->type[0] = 5; p->band_position[0] = (uint8_t)bestBand;
-            for (int k = 0; k < 4; ++k) p->offset[0][k] = boOffset[bestBand + k];
-        } else if (p->luma_cost == eoBestCost) {
-            p->type[0] = (uint8_t)(bestEo + 1);
-            for (int k = 0; k < 4; ++k) p->offset[0][k] = eoOffset[bestEo][k];
-        }
-    } else {
-        p->type[0] = 0;
-        p->luma_cost = saoOffCost;
-    }
-}
-
-__device__ void chroma_mode_offsets(const svtb200_sao_stats *st /* components 0..2 of the LCU */, svtb200_sao_decision *p, uint64_t lambda, const svtb200_sao_rate_tables *r, int is10bit)
-{
-    const uint64_t maxCost = ~(uint64_t)0;
-    const uint32_t dshift = is10bit ? 4 : 0;
-    const int64_t boChromaBestCost = (int64_t)(maxCost >> 1);          /* BO for chroma is compiled out in the reference */
-    int64_t eoChromaBestCost = (int64_t)(maxCost >> 1);
-    uint32_t bestEo = 1;
-    int32_t eoOffset[2][4][4];
-    int64_t eoTypeDistortion[4] = {0, 0, 0, 0}, eoTypeCost[4] = {0, 0, 0, 0};
-    const int64_t saoOffRate = r->type_index_bits[0];
-    const int64_t saoOffCost = (int64_t)(((saoOffRate * lambda) + MD_OFFSET) >> MD_SHIFT);
-
-    for (uint32_t t = 0; t < 4; ++t) {
-        for (uint32_t c = 1; c < 3; ++c) {
-            const svtb200_sao_stats *s = st + c;
-            for (uint32_t k = 0; k < 4; ++k) {
-                int32_t o = s->eo_count[t][k] == 0 ? 0 : s->eo_diff[t][k] / (int32_t)s->eo_count[t][k];
-                o = clip3(kMinEO[is10bit][k], kMaxEO[is10bit][k], o);
-                eoOffset[c - 1][t][k] = o;
-                eoTypeDistortion[t] += (int64_t)((-(2 * o * s->eo_diff[t][k]) + ((int32_t)s->eo_count[t][k] * SQR(o))) >> dshift);   /* never reset between Cb and Cr */
-            }
-            const int64_t rate = (int64_t)offsets_fraction_bits(t + 1, eoOffset[c - 1][t], r);
-            eoTypeCost[t] += (eoTypeDistortion[t] << COST_PRECISION) + (((rate * lambda) + MD_OFFSET) >> MD_SHIFT);
-        }
-        if (eoTypeCost[t] < eoChromaBestCost) { eoChromaBestCost = eoTypeCost[t]; bestEo = t; }
-    }
-    eoChromaBestCost += (((r->type_index_bits[bestEo + 1] * lambda) + MD_OFFSET) >> MD_SHIFT);
-    if (boChromaBestCost < saoOffCost || eoChromaBestCost < saoOffCost) {
-        p->chroma_cost = boChromaBestCost < eoChromaBestCost ? boChromaBestCost : eoChromaBestCost;
-        if (p->chroma_cost == boChromaBestCost) {
-            p->type[1] = 5;                                             /* unreachable: band positions / offsets would be 0 */
-            for (int c = 1; c < 3; ++c) { p->band_position[c] = 0; for (int k = 0; k < 4; ++k) p->offset[c][k] = 0; }
-        } else {
-            p->type[1] = (uint8_t)(bestEo + 1);
-            for (int c = 1; c < 3; ++c) for (int k = 0; k < 4; ++k) p->offset[c][k] = eoOffset[c - 1][bestEo][k];
-        }
-    } else {
-        p->type[1] = 0;
-        p->chroma_cost = saoOffCost;
-    }
-}
 
 /* distortion of re-using a neighbour's parameters on this LCU's statistics */
 __device__ void merge_distortion(const svtb200_sao_stats *st, const svtb200_sao_decision *n, int64_t *luma, int64_t *chroma)
@@ -202,30 +93,168 @@ __device__ void copy_modes(const svtb200_sao_stats *st, svtb200_sao_decision *p,
 }
 
 
-__global__ void __launch_bounds__(128) sao_offsets_kernel(const svtb200_sao_stats *stats, int n_lcu, svtb200_sao_rate_tables rates, uint64_t lambda, uint64_t lambda_c,
-                                                          int is10bit, svtb200_sao_decision *out)
+// ---- offsets / type of an LCU: one WARP per LCU --------------------------------------------------------------------------------------------
+// DetermineSaoLumaModeOffsets / DetermineSaoChromaModeOffsets / GetSaoOffsetsFractionBits with their arithmetic spread over the lanes: a lane per band for the band offsets (interval sums, rates and the
+// first-minimum search by shuffles), a lane per (type, category) for the luma edge offsets, a lane per (component, type, category) for the chroma ones.
+// Every expression keeps the reference's operand widths (32-bit products, 64-bit costs), so the results are the scalar path's bit for bit.
+__device__ __forceinline__ int64_t shfl_down64(int64_t v, int d) { return (int64_t)__shfl_down_sync(0xffffffffu, (unsigned long long)v, d); }
+__device__ __forceinline__ int64_t shfl_xor64(int64_t v, int d) { return (int64_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)v, d); }
+__device__ __forceinline__ int64_t shfl64(int64_t v, int l) { return (int64_t)__shfl_sync(0xffffffffu, (unsigned long long)v, l); }
+// (cost, index) of the first minimum among the lanes with valid set: smaller cost wins, equal costs keep the smaller index (the reference scans upwards with <)
+__device__ __forceinline__ void first_min(int64_t &cost, int &idx, bool valid)
 {
-    const int lcu = blockIdx.x * 128 + threadIdx.x;
+    if (!valid) { cost = INT64_MAX; idx = 1 << 20; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int64_t c2 = shfl_xor64(cost, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (c2 < cost || (c2 == cost && i2 < idx)) { cost = c2; idx = i2; }
+    }
+}
+__device__ __forceinline__ int64_t rate_cost(int64_t rate, uint64_t lambda) { return (int64_t)(((rate * lambda) + MD_OFFSET) >> MD_SHIFT); }
+
+__global__ void __launch_bounds__(128) sao_offsets_kernel(const svtb200_sao_stats *stats, int n_lcu, const __grid_constant__ svtb200_sao_rate_tables rates, uint64_t lambda,
+                                                          uint64_t lambda_c, int is10bit, svtb200_sao_decision *out)
+{
+    const int lcu = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (lcu >= n_lcu) return;
-    svtb200_sao_decision p;
-    memset(&p, 0, sizeof p);                                                    // SaoGenerationDecision :683-694
-    luma_mode_offsets(stats + (size_t)lcu * 3, &p, lambda, &rates, is10bit);
-    chroma_mode_offsets(stats + (size_t)lcu * 3, &p, lambda_c, &rates, is10bit);
-    out[lcu] = p;
+    const svtb200_sao_stats *st = stats + (size_t)lcu * 3;
+    const uint32_t dshift = is10bit ? 4 : 0;
+    const int64_t huge = (int64_t)((~(uint64_t)0) >> 1);
+    const int64_t offCostL = rate_cost(rates.type_index_bits[0], lambda), offCostC = rate_cost(rates.type_index_bits[0], lambda_c);
+    // ---- luma band offsets: lane = band ----
+    int32_t boOff;
+    int64_t boDist;
+    {
+        const int32_t cnt = (int32_t)st[0].bo_count[lane], diff = st[0].bo_diff[lane];
+        boOff = clip3(kMinBO[is10bit], kMaxBO[is10bit], cnt == 0 ? 0 : diff / cnt);
+        boDist = (int64_t)((-(2 * boOff * diff) + (cnt * SQR(boOff))) >> dshift);
+    }
+    int64_t boCost;
+    int bestBand;
+    {
+        int64_t d = boDist;
+        uint32_t o = min(absu(boOff), 7u);
+        int64_t rate = 163840 + (int64_t)rates.offset_trun_unary_bits[o] + (o != 0 ? 32768 : 0);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+            d += shfl_down64(boDist, k);
+            const uint32_t ok = min(absu(__shfl_down_sync(0xffffffffu, boOff, k)), 7u);
+            rate += (int64_t)rates.offset_trun_unary_bits[ok] + (ok != 0 ? 32768 : 0);
+        }
+        boCost = (d << COST_PRECISION) + rate_cost(rate, lambda);
+        bestBand = lane;
+        first_min(boCost, bestBand, lane < 32 - 4 + 1);
+    }
+    // ---- luma edge offsets: lane = type * 4 + category (lanes 16-31 idle) ----
+    int32_t eoOff = 0;
+    int64_t eoCost;
+    int bestEo;
+    {
+        const int t = (lane >> 2) & 3, k = lane & 3;
+        const int32_t cnt = (int32_t)st[0].eo_count[t][k], diff = st[0].eo_diff[t][k];
+        eoOff = clip3(kMinEO[is10bit][k], kMaxEO[is10bit][k], cnt == 0 ? 0 : diff / cnt);
+        int64_t dist = (int64_t)((-(2 * eoOff * diff) + (cnt * SQR(eoOff))) >> dshift);
+        int64_t rate = (int64_t)rates.offset_trun_unary_bits[min(absu(eoOff), 7u)];
+        dist += shfl_xor64(dist, 1); dist += shfl_xor64(dist, 2);
+        rate += shfl_xor64(rate, 1); rate += shfl_xor64(rate, 2);
+        eoCost = (dist << COST_PRECISION) + rate_cost(rate, lambda);
+        bestEo = t;
+        first_min(eoCost, bestEo, lane < 16 && k == 0);
+    }
+    // ---- chroma edge offsets: lane = component * 16 + type * 4 + category ----
+    int32_t ceOff;
+    int64_t ceCost;
+    int bestCe;
+    {
+        const int c = lane >> 4, t = (lane >> 2) & 3, k = lane & 3;
+        const int32_t cnt = (int32_t)st[1 + c].eo_count[t][k], diff = st[1 + c].eo_diff[t][k];
+        ceOff = clip3(kMinEO[is10bit][k], kMaxEO[is10bit][k], cnt == 0 ? 0 : diff / cnt);
+        int64_t dist = (int64_t)((-(2 * ceOff * diff) + (cnt * SQR(ceOff))) >> dshift);
+        int64_t rate = (int64_t)rates.offset_trun_unary_bits[min(absu(ceOff), 7u)];
+        dist += shfl_xor64(dist, 1); dist += shfl_xor64(dist, 2);
+        rate += shfl_xor64(rate, 1); rate += shfl_xor64(rate, 2);
+        // the reference never resets the type's distortion between Cb and Cr: cost(t) = cost(D_cb, R_cb) + cost(D_cb + D_cr, R_cr)
+        const int64_t dOther = shfl_xor64(dist, 16), rOther = shfl_xor64(rate, 16);
+        const int64_t dCb = c ? dOther : dist, dCr = c ? dist : dOther, rCb = c ? rOther : rate, rCr = c ? rate : rOther;
+        ceCost = (dCb << COST_PRECISION) + rate_cost(rCb, lambda_c) + ((dCb + dCr) << COST_PRECISION) + rate_cost(rCr, lambda_c);
+        bestCe = t;
+        first_min(ceCost, bestCe, lane < 16 && k == 0);
+    }
+    // ---- selection (DetermineSaoLumaModeOffsets / ...ChromaModeOffsets tails); the chosen offsets come from the lanes that hold them ----
+    boCost += rate_cost(rates.type_index_bits[5], lambda);
+    eoCost += rate_cost(rates.type_index_bits[bestEo + 1], lambda);
+    ceCost += rate_cost(rates.type_index_bits[bestCe + 1], lambda_c);
+    int32_t lumaBo[4], lumaEo[4], cb[4], cr[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        lumaBo[k] = __shfl_sync(0xffffffffu, boOff, (bestBand + k) & 31);
+        lumaEo[k] = __shfl_sync(0xffffffffu, eoOff, (bestEo * 4 + k) & 31);
+        cb[k] = __shfl_sync(0xffffffffu, ceOff, (bestCe * 4 + k) & 31);
+        cr[k] = __shfl_sync(0xffffffffu, ceOff, (16 + bestCe * 4 + k) & 31);
+    }
+    if (lane == 0) {
+        svtb200_sao_decision p;
+        memset(&p, 0, sizeof p);                                                    // SaoGenerationDecision :683-694
+        if (boCost < offCostL || eoCost < offCostL) {
+            p.luma_cost = boCost < eoCost ? boCost : eoCost;
+            if (p.luma_cost == boCost) {
+                p.type[0] = 5; p.band_position[0] = (uint8_t)bestBand;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) p.offset[0][k] = lumaBo[k];
+            } else {
+                p.type[0] = (uint8_t)(bestEo + 1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) p.offset[0][k] = lumaEo[k];
+            }
+        } else { p.type[0] = 0; p.luma_cost = offCostL; }
+        // chroma: band offsets are compiled out in the reference (their cost stays at the maximum)
+        if (huge < offCostC || ceCost < offCostC) {
+            p.chroma_cost = huge < ceCost ? huge : ceCost;
+            if (p.chroma_cost == huge) p.type[1] = 5;                                // unreachable: band positions / offsets would be 0
+            else {
+                p.type[1] = (uint8_t)(bestCe + 1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { p.offset[1][k] = cb[k]; p.offset[2][k] = cr[k]; }
+            }
+        } else { p.type[1] = 0; p.chroma_cost = offCostC; }
+        out[lcu] = p;
+    }
 }
 
-__global__ void __launch_bounds__(256) sao_merge_kernel(const svtb200_sao_stats *stats, int cols, int rows, svtb200_sao_rate_tables rates, uint64_t lambda, int is10bit,
-                                                        svtb200_sao_decision *out, svtb200_sao_params *params)
+// The merge step of LCU (x, y) needs the FINAL decisions of (x - 1, y) and (x, y - 1): both lie on the previous anti-diagonal.  One CTA walks the
+// diagonals; everything a step touches sits in shared memory -- the decisions of the previous diagonal (indexed by row) and the statistics of the current
+// one, fetched cooperatively one diagonal ahead -- so a step costs a barrier and a few hundred dependent instructions instead of dependent L2 round trips.
+constexpr int SAOM_NT = 256;
+constexpr int SAO_STAT_WORDS = 3 * (int)sizeof(svtb200_sao_stats) / 4;       // 234 words per LCU
+__global__ void __launch_bounds__(SAOM_NT) sao_merge_kernel(const svtb200_sao_stats *stats, int cols, int rows, const __grid_constant__ svtb200_sao_rate_tables rates,
+                                                            uint64_t lambda, int is10bit, svtb200_sao_decision *out, svtb200_sao_params *params)
 {
+    extern __shared__ __align__(16) uint8_t saom_smem[];
+    uint32_t *s_stats = (uint32_t *)saom_smem;                                               // [2][rows][SAO_STAT_WORDS]
+    svtb200_sao_decision *s_dec = (svtb200_sao_decision *)(s_stats + 2 * rows * SAO_STAT_WORDS);   // [2][rows]
+    auto fetch = [&](int d) {      // statistics and first-phase decisions of diagonal d -> buffer d & 1
+        if (d >= cols + rows - 1) return;
+        const int y0 = max(0, d - (cols - 1)), y1 = min(rows - 1, d);
+        uint32_t *dst = s_stats + (d & 1) * rows * SAO_STAT_WORDS;
+        for (int i = threadIdx.x; i < (y1 - y0 + 1) * SAO_STAT_WORDS; i += SAOM_NT) {
+            const int y = y0 + i / SAO_STAT_WORDS, w = i - (y - y0) * SAO_STAT_WORDS;
+            dst[y * SAO_STAT_WORDS + w] = ((const uint32_t *)(stats + (size_t)(y * cols + d - y) * 3))[w];
+        }
+    };
+    fetch(0);
+    __syncthreads();
     for (int d = 0; d < cols + rows - 1; ++d) {
         const int y0 = max(0, d - (cols - 1)), y1 = min(rows - 1, d);
-        for (int y = y0 + threadIdx.x; y <= y1; y += 256) {
+        fetch(d + 1);
+        const int y = y0 + (int)threadIdx.x;
+        if (y <= y1) {
             const int x = d - y, lcu = y * cols + x;
             svtb200_sao_decision p = out[lcu];
-            svtb200_sao_decision l, u;
-            if (x) l = out[lcu - 1];
-            if (y) u = out[lcu - cols];
-            copy_modes(stats + (size_t)lcu * 3, &p, x ? &l : nullptr, y ? &u : nullptr, lambda, &rates, is10bit);
+            const svtb200_sao_decision *prev = s_dec + ((d + 1) & 1) * rows;
+            const svtb200_sao_stats *st = (const svtb200_sao_stats *)(s_stats + ((d & 1) * rows + y) * SAO_STAT_WORDS);
+            copy_modes(st, &p, x ? &prev[y] : nullptr, y ? &prev[y - 1] : nullptr, lambda, &rates, is10bit);
+            s_dec[(d & 1) * rows + y] = p;
             out[lcu] = p;
             if (params) {
                 svtb200_sao_params q;
@@ -235,7 +264,7 @@ __global__ void __launch_bounds__(256) sao_merge_kernel(const svtb200_sao_stats 
                 params[lcu] = q;
             }
         }
-        __syncthreads();      // the next diagonal reads what this one wrote (same CTA: the barrier orders the global accesses)
+        __syncthreads();      // the next diagonal reads what this one wrote, and its statistics have landed
     }
 }
 
@@ -252,9 +281,12 @@ int svtb200_sao_decision_picture_dev(const svtb200_sao_stats *stats_dev, int lcu
     if (rc) return rc;
     const int n = lcu_cols * lcu_rows;
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    sao_offsets_kernel<<<(n + 127) / 128, 128, 0, st>>>(stats_dev, n, *rates, full_lambda, full_chroma_lambda_sao, is10bit != 0, out_dev);
+    if (lcu_rows > SAOM_NT) { set_error("sao_decision_picture_dev: more than %d LCU rows", SAOM_NT); return SVTB200_ERR_UNSUPPORTED; }
+    sao_offsets_kernel<<<(n + 3) / 4, 128, 0, st>>>(stats_dev, n, *rates, full_lambda, full_chroma_lambda_sao, is10bit != 0, out_dev);
     SVTB200_COUNT_LAUNCH();
-    sao_merge_kernel<<<1, 256, 0, st>>>(stats_dev, lcu_cols, lcu_rows, *rates, full_lambda, is10bit != 0, out_dev, params_out_dev);
+    const size_t smem = (size_t)2 * lcu_rows * (SAO_STAT_WORDS * 4 + sizeof(svtb200_sao_decision));
+    if (smem > 48 * 1024) SVTB200_CUDA_TRY(cudaFuncSetAttribute(sao_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sao_merge_kernel<<<1, SAOM_NT, smem, st>>>(stats_dev, lcu_cols, lcu_rows, *rates, full_lambda, is10bit != 0, out_dev, params_out_dev);
     SVTB200_COUNT_LAUNCH();
     SVTB200_CUDA_TRY(cudaGetLastError());
     return SVTB200_OK;

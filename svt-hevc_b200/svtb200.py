@@ -770,6 +770,14 @@ def sao_decision_picture(stats, lcu_cols, lcu_rows, rates, full_lambda, full_chr
     return out
 
 
+def sao_decision_picture_dev(stats_ptr, lcu_cols, lcu_rows, rates, full_lambda, full_chroma_lambda_sao, is10bit, out_ptr, params_ptr=0, stream=0):
+    """SAO decision of a picture on device buffers: stats -> svtb200_sao_decision records (+ optionally the svtb200_sao_params sao_apply consumes)"""
+    r = SaoRateTables()
+    C.memmove(C.byref(r), C.byref(rates), C.sizeof(r))
+    check(lib().svtb200_sao_decision_picture_dev(C.c_void_p(stats_ptr), C.c_int(lcu_cols), C.c_int(lcu_rows), C.byref(r), C.c_uint64(full_lambda),
+                                                 C.c_uint64(full_chroma_lambda_sao), C.c_int(is10bit), C.c_void_p(out_ptr), C.c_void_p(params_ptr or None), C.c_void_p(stream)))
+
+
 def sao_stats_picture_h3(src, deblocked, unfiltered):
     """H3 statistics (host pictures, HostYuvPicture)"""
     n = ((deblocked.width + 63) // 64) * ((deblocked.height + 63) // 64)
