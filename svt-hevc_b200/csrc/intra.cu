@@ -294,11 +294,27 @@ __device__ __forceinline__ uint32_t warp_mode_sad(const uint8_t *line, const Mod
     return warp_sum(acc);
 }
 
+// how many of the nine stage-1 modes the inter-picture search evaluates for a CU: 0 when the DC distortion is close enough to the ME distortion (or
+// either is 0), else 1 + 2 * point with point from the thresholds of the picture's set and layer (OpenLoopIntraSearchLcu, EbMotionEstimation.c:5117-5160)
+__device__ __forceinline__ int ois_stage1_count(const svtb200_ois_config &cfg, uint32_t dc_sad, uint32_t me_sad)
+{
+    const int32_t diff = (int32_t)(me_sad - dc_sad) * 100;
+    const int32_t dist = dc_sad ? diff / (int32_t)dc_sad : 0;
+    const int16_t *th = c_ois_th[cfg.ois_th_set][cfg.temporal_layer];
+    int point = 4;
+    if (dc_sad == 0 || me_sad == 0 || dist <= th[0]) point = 0;
+    else if (dist <= th[1]) point = 1;
+    else if (dist <= th[2]) point = 2;
+    else if (dist <= th[3]) point = 3;
+    return point == 0 ? 0 : 1 + 2 * point;
+}
+
 __global__ void __launch_bounds__(OIS_NT) ois_picture_kernel(const __grid_constant__ OisArgs A)
 {
     __shared__ __align__(16) uint8_t s_raw[SRC_R * SRC_P];
     __shared__ uint8_t s_line[OIS_NW][4 * 32 + 4];
     __shared__ uint32_t s_sad[85][SAD_SLOTS];
+    __shared__ uint32_t s_sort[84][37];            // [CU][18 distortions, 18 modes]; odd pitch: a warp's CUs fall into different banks
     __shared__ int s_next;
     const svtb200_ois_config &cfg = A.cfg;
     const int W = cfg.pic_width, H = cfg.pic_height;
@@ -350,6 +366,9 @@ __global__ void __launch_bounds__(OIS_NT) ois_picture_kernel(const __grid_consta
             if (path == 0) mode = c_islice_modes[k]; else if (path == 1) mode = k; else if (path == 2) mode = 1; else mode = k == 0 ? 1 : c_stage1_modes[k - 1];
             const uint32_t sad = warp_mode_sad(line, mode_setup(mode, N, true, dc), s_src, cx, cy);
             if (lane == 0) s_sad[cu][k] = sad;
+            // the "OIS point" path evaluates only the 1 + 2 * point stage-1 modes its DC-vs-ME test asks for (OpenLoopIntraSearchLcu :5117-5160): most CUs
+            // of an inter picture stop at the DC
+            if (path == 3 && k == 0) n_modes = 1 + ois_stage1_count(cfg, sad, A.me[(size_t)lcu * 85 + cu].distortion[0]);
         }
         __syncwarp();
     }
@@ -370,7 +389,7 @@ __global__ void __launch_bounds__(OIS_NT) ois_picture_kernel(const __grid_consta
             uint32_t *c = cand + (size_t)cu * A.cap;
             if (path == 2) { c[0] = ois_pack(s_sad[cu][0], true, 1); total[cu] = 1; continue; }    // OpenLoopIntraDC :4964
             // SortIntraModesOpenLoop :4871 (keep the best 18 of 35) then SortOisCandidateOpenLoop :4843
-            uint32_t d[18], md[18];
+            uint32_t *d = s_sort[cu - 1], *md = d + 18;      // per-CU scratch in shared memory (dynamically indexed: registers would spill to local memory)
             for (int m = 0; m < 18; ++m) { d[m] = s_sad[cu][m]; md[m] = m; }
             for (int m = 18; m < 35; ++m) {
                 const uint32_t sad = s_sad[cu][m];
@@ -389,7 +408,7 @@ __global__ void __launch_bounds__(OIS_NT) ois_picture_kernel(const __grid_consta
     if (threadIdx.x != 0) return;
     // I slices and the inter/intra "OIS point" path: stage1SadArray and bestMode live across the CUs of the LCU (:5069,5073), so the
     // reference's loop is replayed in order on the SAD table
-    uint32_t stage1[11];
+    uint32_t *stage1 = s_sort[0], *modes = s_sort[1];      // (the sort scratch is free on these paths)
     for (int k = 0; k < 11; ++k) stage1[k] = 0;
     int best_mode = 0;
     for (int cu = 1; cu <= max_cu; ++cu) {
@@ -405,7 +424,7 @@ __global__ void __launch_bounds__(OIS_NT) ois_picture_kernel(const __grid_consta
                 if (stage1[m] < best_sad) { best_mode = c_islice_modes[m]; best_sad = stage1[m]; }
             }
             int cnt = 2;
-            uint32_t modes[5] = {0, 1, 0, 0, 0};
+            modes[0] = 0; modes[1] = 1; modes[2] = modes[3] = modes[4] = 0;
             if (best_mode != 0 && best_mode != 1) {
                 const int r = best_mode == 2 ? 0 : best_mode == 10 ? 1 : best_mode == 18 ? 2 : best_mode == 26 ? 3 : 4;
                 for (int q = 0; q < 3; ++q) modes[cnt++] = c_islice_inject[r][q];
@@ -417,16 +436,8 @@ __global__ void __launch_bounds__(OIS_NT) ois_picture_kernel(const __grid_consta
         }
         const uint32_t me_sad = A.me[(size_t)lcu * 85 + cu].distortion[0];
         stage1[0] = s_sad[cu][0];
-        const int32_t diff = (int32_t)(me_sad - stage1[0]) * 100;
-        const int32_t dist = stage1[0] ? diff / (int32_t)stage1[0] : 0;
-        const int16_t *th = c_ois_th[cfg.ois_th_set][cfg.temporal_layer];
-        int point = 4;
-        if (stage1[0] == 0 || me_sad == 0 || dist <= th[0]) point = 0;
-        else if (dist <= th[1]) point = 1;
-        else if (dist <= th[2]) point = 2;
-        else if (dist <= th[3]) point = 3;
-        if (point == 0) { c[0] = ois_pack(stage1[0], false, 1); total[cu] = 1; continue; }
-        const int n = 1 + 2 * point;
+        const int n = ois_stage1_count(cfg, stage1[0], me_sad);
+        if (n == 0) { c[0] = ois_pack(stage1[0], false, 1); total[cu] = 1; continue; }
         uint32_t best_sad = 32 * 32 * 255;
         for (int m = 0; m < n; ++m) {
             stage1[m] = s_sad[cu][1 + m];
