@@ -455,6 +455,7 @@ def run_b200(args):
             self.pending = False
             self.ev_small = torch.cuda.Event()
             self.ev_in, self.ev_cmp, self.ev_out = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+            self.ev_dec, self.dec_pending = torch.cuda.Event(), False      # the SAO decision of the slot's last picture, when it ran on the side stream
             if own_outputs:
                 # everything the host consumes sits in ONE device span per picture (small results, then the packed stream): ME results, TU offsets, nz counts,
                 # SAO stats, OIS; the coefficients leave as a dense stream of the coded TUs (svtb200_tq_pack_coeffs_dev)
@@ -516,12 +517,14 @@ def run_b200(args):
     def pipeline(i, src_pa, src_yuv, sl, ts, ev=None, resident=True):
         """All device stages of frame i into slot sl on torch stream ts.  ev: dict name -> list of (start, end) events."""
         st = ts.cuda_stream
-        def timed(name, fn):
+        def timed(name, fn, on=None):
             if ev is None:
                 fn(); return
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(ts); fn(); b.record(ts)
+            a.record(on or ts); fn(); b.record(on or ts)
             ev[name].append((a, b))
+        if sl.dec_pending:                      # this slot's statistics buffer is still being read by the previous picture's decision
+            ts.wait_event(sl.ev_dec); sl.dec_pending = False
         r0, r1 = wl.refs(i)
         k = i % RING
         tl = wl.tl(i)
@@ -545,7 +548,12 @@ def run_b200(args):
             timed("sao_apply", lambda: F["sao_apply"](pred, sl.sao_out, P["sao_prm"], (1, 1), st))
         else:
             timed("sao_stats", lambda: F["sao_stats"](src_yuv, pred, P["stats"], st))
-            timed("sao_dec", lambda: S.sao_decision_picture_dev(P["stats"], COLS, ROWS, rates_b, SAO_LAMBDA[0], SAO_LAMBDA[1], 1 if hbd else 0, P["dec"], P["sao_prm"], st))
+            # no picture stage of this frame waits for the decision (SAO is not applied on this layer): its dependency chain (an anti-diagonal wavefront in one
+            # CTA) runs on a side stream next to the following frame's kernels; whoever consumes the decisions (the copy-out, the GOP exchange) waits for ev_dec
+            side = dstreams[ts]
+            e = torch.cuda.Event(); e.record(ts); side.wait_event(e)
+            timed("sao_dec", lambda: S.sao_decision_picture_dev(P["stats"], COLS, ROWS, rates_b, SAO_LAMBDA[0], SAO_LAMBDA[1], 1 if hbd else 0, P["dec"], P["sao_prm"], side.cuda_stream), on=side)
+            sl.ev_dec.record(side); sl.dec_pending = True
         if cfg["gop_exchange"] and resident:
             timed("pack_coeffs", lambda: S.tq_pack_coeffs_dev(sl.coeff, p_tq, P["nz"], n_tq, P["stream"], sl.cap, P["off"], st))
 
@@ -553,6 +561,7 @@ def run_b200(args):
     # kernels of different frames then share the SMs, which hides launch tails and lets the latency-bound kernels overlap the issue-bound ones.
     # config 5: the compute streams ARE the concurrent video streams of the density run (frame i belongs to video stream i % streams).
     cstreams = [tstream] + [torch.cuda.Stream(device=dev) for _ in range(args.streams - 1)]
+    dstreams = {cs: torch.cuda.Stream(device=dev) for cs in cstreams}      # one side stream per compute stream: SAO decisions off the critical path
     while len(slots) < len(cstreams):
         slots.append(Slot())
 
@@ -580,7 +589,7 @@ def run_b200(args):
     def gop_boundary(round_index, gop_slots_totals):
         """all pictures of this rank's GOP are done: their byte counts reach the host (one small D2H), the transfers to rank 0 are posted on the
         communication stream and overlap the next GOP's kernels"""
-        for cs in cstreams:
+        for cs in list(cstreams) + list(dstreams.values()):
             e = torch.cuda.Event(); e.record(cs); comm_stream.wait_event(e)
         with torch.cuda.stream(comm_stream):
             totals = torch.stack(gop_slots_totals).flatten().cpu().tolist()                 # elements of each picture's packed stream
@@ -636,6 +645,8 @@ def run_b200(args):
             S.tq_pack_coeffs_dev(sl.coeff, p_tq, sl.p["nz"], n_tq, sl.p["stream"], sl.cap, sl.p["off"], cs.cuda_stream)
         sl.ev_cmp.record(cs)
         s_small.wait_event(sl.ev_cmp)
+        if sl.dec_pending:
+            s_small.wait_event(sl.ev_dec)
         if "d2h" not in skip:
             S.copy_async(sl.p["h_small"], sl.p["small"], small_total, True, s_small.cuda_stream)    # D2H: ME results, TU offsets, nz, SAO decisions, OIS
         sl.ev_small.record(s_small)

@@ -25,31 +25,9 @@ __constant__ int32_t kMinBO[2] = {-7, -31};
 __device__ __forceinline__ int32_t clip3(int32_t lo, int32_t hi, int32_t v) { return v < lo ? lo : (v > hi ? hi : v); }
 __device__ __forceinline__ uint32_t absu(int32_t v) { return (uint32_t)(v < 0 ? -v : v); }
 
-/* distortion of re-using a neighbour's parameters on this LCU's statistics */
-__device__ void merge_distortion(const svtb200_sao_stats *st, const svtb200_sao_decision *n, int64_t *luma, int64_t *chroma)
-{
-    *luma = 0; *chroma = 0;
-    if (n->type[0] > 0) {
-        for (int k = 0; k < 4; ++k) {
-            if (n->type[0] == 5)
-                *luma += -(2 * n->offset[0][k] * st[0].bo_diff[n->band_position[0] + k]) + ((int32_t)st[0].bo_count[n->band_position[0] + k] * SQR(n->offset[0][k]));
-            else
-                *luma += -(2 * n->offset[0][k] * st[0].eo_diff[n->type[0] - 1][k]) + ((int32_t)st[0].eo_count[n->type[0] - 1][k] * SQR(n->offset[0][k]));
-        }
-    }
-    if (n->type[1] > 0) {
-        for (int c = 1; c < 3; ++c)
-            for (int k = 0; k < 4; ++k) {
-                if (n->type[1] == 5)
-                    *chroma += -(2 * n->offset[c][k] * st[c].bo_diff[n->band_position[c] + k]) + ((int32_t)st[c].bo_count[n->band_position[c] + k] * SQR(n->offset[c][k]));
-                else
-                    *chroma += -(2 * n->offset[c][k] * st[c].eo_diff[n->type[1] - 1][k]) + ((int32_t)st[c].eo_count[n->type[1] - 1][k] * SQR(n->offset[c][k]));
-            }
-    }
-}
-
-__device__ void copy_modes(const svtb200_sao_stats *st, svtb200_sao_decision *p, const svtb200_sao_decision *left, const svtb200_sao_decision *up, uint64_t lambda,
-                       const svtb200_sao_rate_tables *r, int is10bit)
+// TestSaoCopyModes with the four merge distortions already summed (the group of lanes that owns the LCU computed them, see sao_merge_kernel)
+__device__ void copy_modes(svtb200_sao_decision *p, const svtb200_sao_decision *left, const svtb200_sao_decision *up, int64_t dlL, int64_t dcL, int64_t dlU, int64_t dcU,
+                           uint64_t lambda, const svtb200_sao_rate_tables *r, int is10bit)
 {
     const uint64_t maxCost = ~(uint64_t)0;
     const uint32_t dshift = is10bit ? 4 : 0;
@@ -61,8 +39,7 @@ __device__ void copy_modes(const svtb200_sao_stats *st, svtb200_sao_decision *p,
     p->luma_cost = p->luma_cost + ((((leftFlagBits + upFlagBits) * lambda) + MD_OFFSET) >> MD_SHIFT);
     p->chroma_cost = p->chroma_cost + ((((leftFlagBits + upFlagBits) * lambda) + MD_OFFSET) >> MD_SHIFT);
     if (left) {
-        int64_t dl, dc;
-        merge_distortion(st, left, &dl, &dc);
+        int64_t dl = dlL, dc = dcL;
         const int64_t rate = r->merge_flag_bits[1];
         dl >>= dshift; dc >>= dshift;
         lumaLeftCost = (dl << COST_PRECISION) + (((rate * lambda) + MD_OFFSET) >> MD_SHIFT);
@@ -70,8 +47,7 @@ __device__ void copy_modes(const svtb200_sao_stats *st, svtb200_sao_decision *p,
         leftCost = (dl << COST_PRECISION) + (dc << COST_PRECISION) + (((rate * lambda) + MD_OFFSET) >> MD_SHIFT);
     }
     if (up) {
-        int64_t dl, dc;
-        merge_distortion(st, up, &dl, &dc);
+        int64_t dl = dlU, dc = dcU;
         dl >>= dshift; dc >>= dshift;
         upFlagBits = r->merge_flag_bits[1];
         const int64_t rate = (int64_t)(leftFlagBits + upFlagBits);
@@ -91,7 +67,16 @@ __device__ void copy_modes(const svtb200_sao_stats *st, svtb200_sao_decision *p,
         }
     }
 }
-
+// one of the 12 terms of the distortion of re-using neighbour n's parameters on this LCU's statistics: term 0-3 luma category k, 4-7 Cb, 8-11 Cr
+// (the reference sums -(2 * offset * diff) + count * offset^2 in 32 bits per term)
+__device__ __forceinline__ int32_t merge_term(const svtb200_sao_stats *st, const svtb200_sao_decision *n, int term)
+{
+    const int c = term < 4 ? 0 : 1 + ((term - 4) >> 2), k = term & 3, ty = n->type[c ? 1 : 0];
+    if (ty == 0) return 0;
+    const int32_t o = n->offset[c][k];
+    if (ty == 5) { const int b = n->band_position[c] + k; return -(2 * o * st[c].bo_diff[b]) + ((int32_t)st[c].bo_count[b] * SQR(o)); }
+    return -(2 * o * st[c].eo_diff[ty - 1][k]) + ((int32_t)st[c].eo_count[ty - 1][k] * SQR(o));
+}
 
 // ---- offsets / type of an LCU: one WARP per LCU --------------------------------------------------------------------------------------------
 // DetermineSaoLumaModeOffsets / DetermineSaoChromaModeOffsets / GetSaoOffsetsFractionBits with their arithmetic spread over the lanes: a lane per band for the band offsets (interval sums, rates and the
@@ -225,35 +210,66 @@ __global__ void __launch_bounds__(128) sao_offsets_kernel(const svtb200_sao_stat
 // The merge step of LCU (x, y) needs the FINAL decisions of (x - 1, y) and (x, y - 1): both lie on the previous anti-diagonal.  One CTA walks the
 // diagonals; everything a step touches sits in shared memory -- the decisions of the previous diagonal (indexed by row) and the statistics of the current
 // one, fetched cooperatively one diagonal ahead -- so a step costs a barrier and a few hundred dependent instructions instead of dependent L2 round trips.
-constexpr int SAOM_NT = 256;
-constexpr int SAO_STAT_WORDS = 3 * (int)sizeof(svtb200_sao_stats) / 4;       // 234 words per LCU
-__global__ void __launch_bounds__(SAOM_NT) sao_merge_kernel(const svtb200_sao_stats *stats, int cols, int rows, const __grid_constant__ svtb200_sao_rate_tables rates,
-                                                            uint64_t lambda, int is10bit, svtb200_sao_decision *out, svtb200_sao_params *params)
+constexpr int SAOM_G = 8;                  // lanes per LCU in the merge step
+constexpr int SAO_STAT_CHUNKS = 3 * (int)sizeof(svtb200_sao_stats) / 8;      // 117 eight-byte chunks per LCU (936 bytes)
+constexpr int SAO_DEC_CHUNKS = (int)sizeof(svtb200_sao_decision) / 8;         // 5
+static_assert(3 * sizeof(svtb200_sao_stats) % 8 == 0 && sizeof(svtb200_sao_decision) % 8 == 0, "8-byte asynchronous copies");
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// blockDim.x = SAOM_G * rows rounded up to whole warps: the LCU of row y0 + t / SAOM_G of the diagonal belongs to the SAOM_G lanes t, t + 1, ...: each
+// computes 3 of the 24 distortion terms (12 per neighbour), the four sums are formed by shuffles, the group's first lane finishes TestSaoCopyModes
+__global__ void __launch_bounds__(1024) sao_merge_kernel(const svtb200_sao_stats *stats, int cols, int rows, const __grid_constant__ svtb200_sao_rate_tables rates,
+                                                         uint64_t lambda, int is10bit, svtb200_sao_decision *out, svtb200_sao_params *params)
 {
     extern __shared__ __align__(16) uint8_t saom_smem[];
-    uint32_t *s_stats = (uint32_t *)saom_smem;                                               // [2][rows][SAO_STAT_WORDS]
-    svtb200_sao_decision *s_dec = (svtb200_sao_decision *)(s_stats + 2 * rows * SAO_STAT_WORDS);   // [2][rows]
-    auto fetch = [&](int d) {      // statistics and first-phase decisions of diagonal d -> buffer d & 1
-        if (d >= cols + rows - 1) return;
-        const int y0 = max(0, d - (cols - 1)), y1 = min(rows - 1, d);
-        uint32_t *dst = s_stats + (d & 1) * rows * SAO_STAT_WORDS;
-        for (int i = threadIdx.x; i < (y1 - y0 + 1) * SAO_STAT_WORDS; i += SAOM_NT) {
-            const int y = y0 + i / SAO_STAT_WORDS, w = i - (y - y0) * SAO_STAT_WORDS;
-            dst[y * SAO_STAT_WORDS + w] = ((const uint32_t *)(stats + (size_t)(y * cols + d - y) * 3))[w];
+    // [3][rows] statistics of the current and the next two diagonals (fetched two steps ahead: a global -> shared copy takes longer than a step), [3][rows]
+    // first-phase decisions of the same, [2][rows] final decisions of the previous / current diagonal
+    uint8_t *s_stats = saom_smem;
+    svtb200_sao_decision *s_in = (svtb200_sao_decision *)(s_stats + (size_t)3 * rows * SAO_STAT_CHUNKS * 8);
+    svtb200_sao_decision *s_dec = s_in + 3 * rows;
+    const int NT = blockDim.x;
+    auto fetch = [&](int d) {      // statistics and first-phase decisions of diagonal d -> buffer d % 3, asynchronously (LDGSTS: no register round trip, all in flight)
+        if (d < cols + rows - 1) {
+        const int y0 = max(0, d - (cols - 1)), y1 = min(rows - 1, d), per = SAO_STAT_CHUNKS + SAO_DEC_CHUNKS;
+        for (int i = threadIdx.x; i < (y1 - y0 + 1) * per; i += NT) {
+            const int y = y0 + i / per, c = i - (y - y0) * per, lcu = y * cols + d - y;
+            if (c < SAO_STAT_CHUNKS) cp_async8(s_stats + ((size_t)((d % 3) * rows + y) * SAO_STAT_CHUNKS + c) * 8, (const uint8_t *)(stats + (size_t)lcu * 3) + 8 * c);
+            else cp_async8((uint8_t *)(s_in + (d % 3) * rows + y) + 8 * (c - SAO_STAT_CHUNKS), (const uint8_t *)(out + lcu) + 8 * (c - SAO_STAT_CHUNKS));
         }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");      // (an empty group past the last diagonal keeps the wait arithmetic uniform)
     };
     fetch(0);
+    fetch(1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncthreads();
+    const int g = threadIdx.x & (SAOM_G - 1);
     for (int d = 0; d < cols + rows - 1; ++d) {
         const int y0 = max(0, d - (cols - 1)), y1 = min(rows - 1, d);
-        fetch(d + 1);
-        const int y = y0 + (int)threadIdx.x;
-        if (y <= y1) {
-            const int x = d - y, lcu = y * cols + x;
-            svtb200_sao_decision p = out[lcu];
-            const svtb200_sao_decision *prev = s_dec + ((d + 1) & 1) * rows;
-            const svtb200_sao_stats *st = (const svtb200_sao_stats *)(s_stats + ((d & 1) * rows + y) * SAO_STAT_WORDS);
-            copy_modes(st, &p, x ? &prev[y] : nullptr, y ? &prev[y - 1] : nullptr, lambda, &rates, is10bit);
+        fetch(d + 2);
+        const int y = y0 + (int)(threadIdx.x / SAOM_G);
+        const bool on = y <= y1;
+        const int x = d - y;
+        const svtb200_sao_decision *prev = s_dec + ((d + 1) & 1) * rows;
+        const svtb200_sao_decision *left = on && x ? &prev[y] : nullptr, *up = on && y ? &prev[y - 1] : nullptr;
+        const svtb200_sao_stats *st = (const svtb200_sao_stats *)(s_stats + (size_t)((d % 3) * rows + (on ? y : 0)) * SAO_STAT_CHUNKS * 8);
+        int64_t sLL = 0, sLC = 0, sUL = 0, sUC = 0;      // left luma, left chroma, up luma, up chroma
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int t = g + SAOM_G * q, nb = t >= 12, term = t - 12 * nb;
+            const svtb200_sao_decision *n = nb ? up : left;
+            const int64_t v = n ? (int64_t)merge_term(st, n, term) : 0;
+            const bool chroma = term >= 4;
+            sLL += (!nb && !chroma) ? v : 0; sLC += (!nb && chroma) ? v : 0; sUL += (nb && !chroma) ? v : 0; sUC += (nb && chroma) ? v : 0;
+        }
+#pragma unroll
+        for (int o = SAOM_G / 2; o > 0; o >>= 1) { sLL += shfl_xor64(sLL, o); sLC += shfl_xor64(sLC, o); sUL += shfl_xor64(sUL, o); sUC += shfl_xor64(sUC, o); }
+        if (on && g == 0) {
+            const int lcu = y * cols + x;
+            svtb200_sao_decision p = s_in[(d % 3) * rows + y];
+            copy_modes(&p, left, up, sLL, sLC, sUL, sUC, lambda, &rates, is10bit);
             s_dec[(d & 1) * rows + y] = p;
             out[lcu] = p;
             if (params) {
@@ -264,7 +280,8 @@ __global__ void __launch_bounds__(SAOM_NT) sao_merge_kernel(const svtb200_sao_st
                 params[lcu] = q;
             }
         }
-        __syncthreads();      // the next diagonal reads what this one wrote, and its statistics have landed
+        asm volatile("cp.async.wait_group 1;" ::: "memory");      // everything but the newest group: diagonal d + 1 has landed
+        __syncthreads();      // the next diagonal reads what this one wrote
     }
 }
 
@@ -281,12 +298,19 @@ int svtb200_sao_decision_picture_dev(const svtb200_sao_stats *stats_dev, int lcu
     if (rc) return rc;
     const int n = lcu_cols * lcu_rows;
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    if (lcu_rows > SAOM_NT) { set_error("sao_decision_picture_dev: more than %d LCU rows", SAOM_NT); return SVTB200_ERR_UNSUPPORTED; }
+    if (lcu_rows * SAOM_G > 1024) { set_error("sao_decision_picture_dev: more than %d LCU rows", 1024 / SAOM_G); return SVTB200_ERR_UNSUPPORTED; }
     sao_offsets_kernel<<<(n + 3) / 4, 128, 0, st>>>(stats_dev, n, *rates, full_lambda, full_chroma_lambda_sao, is10bit != 0, out_dev);
     SVTB200_COUNT_LAUNCH();
-    const size_t smem = (size_t)2 * lcu_rows * (SAO_STAT_WORDS * 4 + sizeof(svtb200_sao_decision));
-    if (smem > 48 * 1024) SVTB200_CUDA_TRY(cudaFuncSetAttribute(sao_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sao_merge_kernel<<<1, SAOM_NT, smem, st>>>(stats_dev, lcu_cols, lcu_rows, *rates, full_lambda, is10bit != 0, out_dev, params_out_dev);
+    const size_t smem = (size_t)lcu_rows * (3 * SAO_STAT_CHUNKS * 8 + 5 * sizeof(svtb200_sao_decision));
+    // opt in to more than 48 KB of dynamic shared memory once per device and size (the attribute call is a context-level operation: not per launch)
+    static std::atomic<size_t> opted[64];
+    int dev = 0;
+    SVTB200_CUDA_TRY(cudaGetDevice(&dev));
+    if (smem > 48 * 1024 && opted[dev & 63].load(std::memory_order_relaxed) < smem) {
+        SVTB200_CUDA_TRY(cudaFuncSetAttribute(sao_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        opted[dev & 63].store(smem, std::memory_order_relaxed);
+    }
+    sao_merge_kernel<<<1, (lcu_rows * SAOM_G + 31) / 32 * 32, smem, st>>>(stats_dev, lcu_cols, lcu_rows, *rates, full_lambda, is10bit != 0, out_dev, params_out_dev);
     SVTB200_COUNT_LAUNCH();
     SVTB200_CUDA_TRY(cudaGetLastError());
     return SVTB200_OK;
