@@ -523,8 +523,6 @@ def run_b200(args):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(on or ts); fn(); b.record(on or ts)
             ev[name].append((a, b))
-        if sl.dec_pending:                      # this slot's statistics buffer is still being read by the previous picture's decision
-            ts.wait_event(sl.ev_dec); sl.dec_pending = False
         r0, r1 = wl.refs(i)
         k = i % RING
         tl = wl.tl(i)
@@ -538,6 +536,8 @@ def run_b200(args):
         timed("ois", lambda: S.ois_picture_dev(ois_cfgs[tl], src_pa.struct.full, P["res"], P["ois_t"], P["ois_c"], cap_ois, st))
         timed("mc", lambda: F["mc"](ref_pairs[(r0, r1)], d_mc_ptr[k][0], d_mc_ptr[k][1], pred, st))
         timed("tq", lambda: F["tq"](src_yuv, pred, pred, sl.coeff, p_tq, n_tq, P["nz"], st))
+        if sl.dec_pending:                      # the slot's statistics buffer may still be read by its previous picture's decision (side stream): the writer waits
+            ts.wait_event(sl.ev_dec); sl.dec_pending = False
         if tl0:
             # H3 (EbCodingLoop.c:4604-4635, 4711-4748): the encoder gathers LCU n's statistics right after LCU n's own deblocking step, i.e. from the
             # deblocked picture except the right / bottom 4-sample strips of every LCU, which are still unfiltered: keep the reconstruction before DLF
@@ -570,7 +570,7 @@ def run_b200(args):
     ex = None
     if cfg["gop_exchange"]:
         from gop_exchange import GopExchange
-        ex = GopExchange(rank, world, dev, FPG, frame_capacity)
+        ex = GopExchange(rank, world, dev, FPG, frame_capacity, peer=(args.exchange == "peer"))
         comm_stream = torch.cuda.Stream(device=dev)
         ex_stats = {"rounds": 0, "bytes": 0, "ms": []}
 
@@ -691,7 +691,24 @@ def run_b200(args):
         barrier()
         runs.append((t0.elapsed_time(t1), {n: [a.elapsed_time(b) for a, b in ev[n]] for n in names}, S.lib().svtb200_launch_count() - launches0))
     sampler.stop_flag = True
+    ex_report = None
     if ex is not None:
+        # what moved, seen from the producers (in peer mode rank 0 runs no transfer of its own): per rank the bytes and the time its copies spent on the
+        # communication stream, and a check that rank 0 holds what the producers sent (byte sum of the first picture of every rank's last GOP)
+        mine = {"bytes": int(ex_stats["bytes"]), "ms": [a.elapsed_time(b) for a, b in ex_stats["ms"]]}
+        last_parity = (round_counter - 1) & 1
+        mine["sum0"] = int(ex.send[last_parity][:small_total].to(torch.int64).sum().item())
+        allr = [None] * world
+        if world > 1:
+            dist.all_gather_object(allr, mine)
+        else:
+            allr = [mine]
+        if rank == 0:
+            ok = True
+            for src in range(1, world):
+                got = ex.payload_on_rank0((round_counter - 1) * world + src, 0)[:small_total].to(torch.int64).sum().item()
+                ok = ok and int(got) == allr[src]["sum0"]
+            ex_report = {"per_rank": allr, "payload_verified": bool(ok)}
         for sl in slots:
             sl.bind(sl.d_out)                                                               # the e2e loop below uses the slots' own spans again
     runs_ms = [r[0] for r in runs]
@@ -811,11 +828,17 @@ def run_b200(args):
         if ex is not None:
             xs = [a.elapsed_time(b) for a, b in ex_stats["ms"]]
             recv_bytes = ex_stats["bytes"]
+            if ex.peer and ex_report:      # producers' view: every round the slowest producer's copies bound the round
+                per = ex_report["per_rank"][1:]
+                xs = [max(p["ms"][r] for p in per) for r in range(len(per[0]["ms"]))] if per and per[0]["ms"] else xs
             out["gop_exchange"] = {"frames_per_gop": FPG, "rounds": ex_stats["rounds"], "gops_total": ex_stats["rounds"] * world,
                                    "bytes_received_by_rank0": int(recv_bytes), "bytes_per_gop_avg": (recv_bytes / max(1, ex_stats["rounds"] * max(1, world - 1))),
                                    "transfer_ms_avg_on_comm_stream": float(np.mean(xs)) if xs else None,
                                    "nvlink_gbs_during_transfers": (recv_bytes / 1e9) / (sum(xs) * 1e-3) if (recv_bytes and xs and sum(xs) > 0) else None,
                                    "rank0_reassembled_coding_order": [g for g, _, _ in ex.assembled] == list(range(len(ex.assembled))),
+                                   "transport": "peer memory (CUDA IPC mapping of rank 0's buffers, device-to-device copies over NVLink by the copy engines; torch.distributed carries the byte counts)"
+                                                if ex.peer else "torch.distributed point-to-point send / recv",
+                                   "payload_verified_on_rank0": ex_report["payload_verified"] if ex_report else None,
                                    "inside_timed_region": True,
                                    "link_gbs_lower_bound": (recv_bytes / 1e9) / (sum(runs_ms) * 1e-3) if recv_bytes else None,
                                    "note": "transfers are posted on a communication stream at every GOP boundary, overlap the next GOP's kernels and complete before the "
@@ -1055,6 +1078,7 @@ def main():
     ap.add_argument("--inflight", type=int, default=5, help="frames in flight in the end-to-end loop (device + pinned host buffers per frame)")
     ap.add_argument("--streams", type=int, default=2, help="compute streams the resident loop spreads consecutive frames over")
     ap.add_argument("--repeats", type=int, default=5, help="the timed region (--steps frames) is run this many times; the median run is reported")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "p2p"], help="config 4, N > 1: GOP hand-off by peer-memory copies over NVLink (default) or by send / recv")
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config (1-based index in `configs`): 2 headline (default), 3 10-bit M7 4K, "
                     "4 8K 10-bit closed GOPs over the GPUs with the NCCL GOP-boundary exchange, 5 1080p stream density")
     args = ap.parse_args()

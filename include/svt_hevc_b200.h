@@ -621,6 +621,15 @@ int svtb200_yuv_picture_pad_dev(const svtb200_yuv_picture *dev, void *cuda_strea
  * gathered before LCU n + 1 is deblocked, Codec/EbCodingLoop.c:4604-4748). */
 int svtb200_yuv_picture_copy_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *dst, uint32_t bytes_per_sample, void *cuda_stream);
 int svtb200_copy_async(void *dst, const void *src, size_t bytes, int device_to_host, void *cuda_stream);
+/* Peer memory for the GOP-boundary hand-off to the entropy-coding rank (one process per GPU): the receiver allocates and exports its buffers,
+ * every producer opens them (CUDA IPC, peer access enabled lazily) and moves a finished picture's outputs device to device over NVLink with the copy
+ * engines.  The 64-byte handle travels between the processes by whatever the host uses (torch.distributed in bench.py). */
+int svtb200_peer_alloc(size_t bytes, void **dev_ptr);
+int svtb200_peer_free(void *dev_ptr);
+int svtb200_peer_export(const void *dev_ptr, uint8_t handle[64]);
+int svtb200_peer_open(const uint8_t handle[64], void **dev_ptr);
+int svtb200_peer_close(void *dev_ptr);
+int svtb200_peer_copy_async(void *dst_dev, const void *src_dev, size_t bytes, void *cuda_stream);
 void svtb200_pa_picture_destroy(svtb200_pa_picture *dev);
 
 #ifdef __cplusplus

@@ -180,6 +180,58 @@ int svtb200_copy_async(void *dst, const void *src, size_t bytes, int device_to_h
     return SVTB200_OK;
 }
 
+// ---- peer memory for the GOP-boundary hand-off: one process per GPU, the entropy-coding rank's receive buffers mapped into every
+// producer's address space (CUDA IPC) so that a finished picture's outputs move GPU to GPU over NVLink by the copy engines -- no SM, no staging, no
+// collective in the data path.  Exportable memory comes from cudaMalloc directly (pool allocators hand out sub-ranges an IPC handle cannot name).
+int svtb200_peer_alloc(size_t bytes, void **dev_ptr)
+{
+    if (!dev_ptr || !bytes) { set_error("peer_alloc: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    int rc = ensure_device();
+    if (rc) return rc;
+    SVTB200_CUDA_TRY(cudaMalloc(dev_ptr, bytes));
+    SVTB200_CUDA_TRY(cudaMemset(*dev_ptr, 0, bytes));
+    return SVTB200_OK;
+}
+int svtb200_peer_free(void *dev_ptr)
+{
+    if (dev_ptr) SVTB200_CUDA_TRY(cudaFree(dev_ptr));
+    return SVTB200_OK;
+}
+int svtb200_peer_export(const void *dev_ptr, uint8_t handle[64])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    if (!dev_ptr || !handle) { set_error("peer_export: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    int rc = ensure_device();
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    SVTB200_CUDA_TRY(cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)));
+    memcpy(handle, &h, 64);
+    return SVTB200_OK;
+}
+int svtb200_peer_open(const uint8_t handle[64], void **dev_ptr)
+{
+    if (!dev_ptr || !handle) { set_error("peer_open: bad argument"); return SVTB200_ERR_BAD_ARG; }
+    int rc = ensure_device();
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    SVTB200_CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SVTB200_OK;
+}
+int svtb200_peer_close(void *dev_ptr)
+{
+    if (dev_ptr) SVTB200_CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+    return SVTB200_OK;
+}
+int svtb200_peer_copy_async(void *dst_dev, const void *src_dev, size_t bytes, void *cuda_stream)
+{
+    if ((!dst_dev || !src_dev) && bytes) { set_error("peer_copy_async: null pointer"); return SVTB200_ERR_BAD_ARG; }
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (bytes) SVTB200_CUDA_TRY(cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream));      // unified addressing: the peer mapping routes it over NVLink
+    return SVTB200_OK;
+}
+
 int svtb200_pa_picture_download(const svtb200_pa_picture *dev, const svtb200_pa_picture *host)
 {
     if (!dev || !host) { set_error("pa_picture_download: bad argument"); return SVTB200_ERR_BAD_ARG; }

@@ -26,6 +26,9 @@ namespace svtb200 {
 #define TQ_NT_V 64
 #endif
 constexpr int TQ_NT = TQ_NT_V;     // threads per TU
+#ifndef TQ_MIN_CTAS
+#define TQ_MIN_CTAS 8
+#endif
 constexpr int TP = 34;   // s16 pitch of the 32x32 tiles: 17 words -> conflict-free column walks
 
 struct YuvW {
@@ -717,7 +720,7 @@ __device__ __forceinline__ bool tq_fast_ok(const TqArgs &A, const svtb200_tq_job
 // general path afterwards with the whole CTA.
 constexpr int TQ_CHUNK = 3;
 template <bool HBD>
-__global__ void __launch_bounds__(TQ_NT, 8) tq_batch_kernel(const __grid_constant__ TqArgs A)
+__global__ void __launch_bounds__(TQ_NT, TQ_MIN_CTAS) tq_batch_kernel(const __grid_constant__ TqArgs A)
 {
     static_assert(TQ_NT == 64, "two warps, two TUs");
     int16_t *s_a = s_tile[0], *s_b = s_tile[1];

@@ -24,12 +24,33 @@ class GopExchange:
     """frames_per_gop pictures per GOP; every rank owns a send buffer laid out [frame][frame_capacity bytes] per parity (double buffered: GOP k + 1 is
     produced while GOP k is in flight); rank 0 owns one receive buffer per (source rank, parity)."""
 
-    def __init__(self, rank, world, device, frames_per_gop, frame_capacity, comm_stream=None):
+    def __init__(self, rank, world, device, frames_per_gop, frame_capacity, comm_stream=None, peer=False):
+        """peer=True (GPUs of one node): rank 0's receive buffers are mapped into every producer's address space (CUDA IPC through the C ABI's
+        svtb200_peer_* entry points) and a GOP's pictures move by device-to-device copies over NVLink on the copy engines; torch.distributed then only
+        carries the byte counts.  peer=False: point-to-point send / recv of the same bytes (NCCL on GPUs, gloo in the CPU tests)."""
         self.rank, self.world, self.device = rank, world, device
         self.fpg, self.cap = frames_per_gop, int(frame_capacity)
         self.send = [torch.zeros(self.fpg * self.cap, dtype=torch.uint8, device=device) for _ in range(2)]
         self.recv = {}
-        if rank == 0:
+        self.peer = bool(peer) and world > 1
+        self.remote = [None, None]          # producers: rank 0's buffer for this rank, per parity (device pointers valid in this process)
+        self.recv_ptr = {}                  # rank 0: (source rank, parity) -> device pointer of the exported buffer
+        if self.peer:
+            import svtb200 as S
+            self.S = S
+            handles = [None]
+            if rank == 0:
+                table = {}
+                for src in range(1, world):
+                    for parity in range(2):
+                        ptr = S.peer_alloc(self.fpg * self.cap)
+                        self.recv_ptr[(src, parity)] = ptr
+                        table[(src, parity)] = S.peer_export(ptr)
+                handles = [table]
+            dist.broadcast_object_list(handles, src=0)
+            if rank != 0:
+                self.remote = [S.peer_open(handles[0][(rank, parity)]) for parity in range(2)]
+        elif rank == 0:
             for src in range(1, world):
                 self.recv[src] = [torch.zeros(self.fpg * self.cap, dtype=torch.uint8, device=device) for _ in range(2)]
         self.comm_stream = comm_stream
@@ -53,7 +74,18 @@ class GopExchange:
             sizes.copy_(mine)
         sizes = sizes.cpu().view(self.world, self.fpg).tolist()
         ops, moved = [], 0
-        if self.world > 1:
+        if self.peer:
+            # the data plane: this rank's pictures straight into rank 0's memory, on the caller's current stream (stream-ordered after the kernels that
+            # produced them); rank 0 only learns the sizes
+            if self.rank == 0:
+                moved = sum(sum(sizes[src]) for src in range(1, self.world))
+            else:
+                st = torch.cuda.current_stream().cuda_stream
+                for f, nb in enumerate(sizes[self.rank]):
+                    if nb:
+                        self.S.peer_copy_async(self.remote[parity] + f * self.cap, self.send[parity].data_ptr() + f * self.cap, nb, st)
+                        moved += nb
+        elif self.world > 1:
             if self.rank == 0:
                 for src in range(1, self.world):
                     for f, nb in enumerate(sizes[src]):
@@ -83,6 +115,10 @@ class GopExchange:
         for g, src, sizes in self.assembled:
             if g == gop_index:
                 parity = (gop_index // self.world) & 1
+                if src != 0 and self.peer:      # the exported buffer is raw device memory: hand out a copy
+                    out = torch.empty(sizes[frame], dtype=torch.uint8, device=self.device)
+                    self.S.peer_copy_async(out.data_ptr(), self.recv_ptr[(src, parity)] + frame * self.cap, sizes[frame], torch.cuda.current_stream().cuda_stream)
+                    return out
                 buf = self.send[parity] if src == 0 else self.recv[src][parity]
                 return buf[frame * self.cap:frame * self.cap + sizes[frame]]
         raise KeyError(gop_index)

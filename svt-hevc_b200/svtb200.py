@@ -574,6 +574,38 @@ CU_INFO_DTYPE = np.dtype([("mv", "<i2", (2, 2)), ("pred_dir", "u1"), ("intra", "
 assert CU_INFO_DTYPE.itemsize == 12
 
 
+# ---- peer memory (GOP-boundary hand-off over NVLink) ------------------------------------------------------------------------------------
+def peer_alloc(nbytes):
+    p = C.c_void_p()
+    check(lib().svtb200_peer_alloc(C.c_size_t(nbytes), C.byref(p)))
+    return p.value
+
+
+def peer_free(ptr):
+    check(lib().svtb200_peer_free(C.c_void_p(ptr)))
+
+
+def peer_export(ptr):
+    h = (C.c_uint8 * 64)()
+    check(lib().svtb200_peer_export(C.c_void_p(ptr), h))
+    return bytes(h)
+
+
+def peer_open(handle):
+    h = (C.c_uint8 * 64).from_buffer_copy(handle)
+    p = C.c_void_p()
+    check(lib().svtb200_peer_open(h, C.byref(p)))
+    return p.value
+
+
+def peer_close(ptr):
+    check(lib().svtb200_peer_close(C.c_void_p(ptr)))
+
+
+def peer_copy_async(dst_ptr, src_ptr, nbytes, stream=0):
+    check(lib().svtb200_peer_copy_async(C.c_void_p(dst_ptr), C.c_void_p(src_ptr), C.c_size_t(nbytes), C.c_void_p(stream)))
+
+
 def dlf_bs_picture(cu_map, cbf_map, width, height, slice_type, ref_poc_l0=0, ref_poc_l1=16):
     """boundary strengths from the picture's final mode / motion / cbf maps -> (vertical_bs, horizontal_bs), each [n_lcu][256] (row N3)"""
     cu_map, cbf_map = np.ascontiguousarray(cu_map), np.ascontiguousarray(cbf_map, np.uint8)
