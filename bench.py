@@ -514,7 +514,7 @@ def run_b200(args):
         for pl, (w_, h_, pad) in enumerate(((W, H, PAD), (W // 2, H // 2, PAD // 2), (W // 2, H // 2, PAD // 2))):
             S.pack_plane_dev(S.PACK_MSB, d_in8[k][pl].data_ptr(), w_, d_inn[k][pl].data_ptr(), w_, sl.src_t[pl][pad:, pad:].data_ptr(), sl.src_t[pl].shape[1], 0, 0, w_, h_, st)
 
-    def pipeline(i, src_pa, src_yuv, sl, ts, ev=None, resident=True):
+    def pipeline(i, src_pa, src_yuv, sl, ts, ev=None, resident=True, inline_dec=False):
         """All device stages of frame i into slot sl on torch stream ts.  ev: dict name -> list of (start, end) events."""
         st = ts.cuda_stream
         def timed(name, fn, on=None):
@@ -548,6 +548,9 @@ def run_b200(args):
             timed("sao_apply", lambda: F["sao_apply"](pred, sl.sao_out, P["sao_prm"], (1, 1), st))
         else:
             timed("sao_stats", lambda: F["sao_stats"](src_yuv, pred, P["stats"], st))
+            if inline_dec:      # (a captured frame graph is one stream: the decision stays in it)
+                timed("sao_dec", lambda: S.sao_decision_picture_dev(P["stats"], COLS, ROWS, rates_b, SAO_LAMBDA[0], SAO_LAMBDA[1], 1 if hbd else 0, P["dec"], P["sao_prm"], st))
+                return
             # no picture stage of this frame waits for the decision (SAO is not applied on this layer): its dependency chain (an anti-diagonal wavefront in one
             # CTA) runs on a side stream next to the following frame's kernels; whoever consumes the decisions (the copy-out, the GOP exchange) waits for ev_dec
             side = dstreams[ts]
@@ -621,6 +624,38 @@ def run_b200(args):
         d2h_bytes.append(2 * total + sl.small_bytes)
         sl.pending = False
 
+    def frame_kernels(i, sl, cs, inline_dec):
+        """the device stages of e2e frame i on compute stream cs"""
+        if "pa" not in skip:
+            if hbd:      # UnPack8BitData (EbPackUnPack_C.c:153): the 8-bit luma PictureAnalysis / ME / OIS work on
+                S.pack_plane_dev(S.PACK_UNPACK8, sl.p["yint"], sl.in_t[0].shape[1], 0, 0, sl.in8.data_ptr(), W, 0, 0, W, H, cs.cuda_stream)
+                sl.pa.build_from_device(sl.in8.data_ptr(), W, cs.cuda_stream)
+            else:
+                sl.pa.build_from_device(sl.p["yint"], sl.in_t[0].shape[1], cs.cuda_stream)     # pad + decimate on the device
+        pipeline(i, sl.pa, sl.in_yuv, sl, cs, resident=False, inline_dec=inline_dec)
+        if "pack" not in skip:
+            S.tq_pack_coeffs_dev(sl.coeff, p_tq, sl.p["nz"], n_tq, sl.p["stream"], sl.cap, sl.p["off"], cs.cuda_stream)
+
+    # The e2e loop is bound by the HOST when every stage is a separate call (about 20 library calls and as many stream / event operations per frame from
+    # Python): the frame's kernels are captured once per (slot, ring picture, stream) combination into a CUDA graph and replayed -- one launch per frame.
+    # Pointers and per-layer parameters are baked in, so the combinations must repeat: 4 slots and 4 streams against the 16-picture ring = 16 graphs.
+    GRAPH_PERIOD = RING
+    frame_graphs = {}
+    e2e_streams = cstreams
+    if not args.no_graphs and RING % 4 == 0:
+        NS = 4
+        while len(slots) < NS:
+            slots.append(Slot())
+        e2e_streams = (cstreams + [torch.cuda.Stream(device=dev) for _ in range(4)])[:4]
+
+    def capture_frame_graphs():
+        for i in range(GRAPH_PERIOD):
+            sl, cs = slots[i % NS], e2e_streams[i % len(e2e_streams)]
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=cs):
+                frame_kernels(i, sl, cs, inline_dec=True)
+            frame_graphs[i] = g
+
     def step_e2e(i):
         """Frame i from pinned host buffers: H2D on the copy-in stream, kernels on the compute stream, D2H of everything the host-side
         encoder consumes on the copy-out stream; NS frames in flight, every copy inside the timed region."""
@@ -631,18 +666,15 @@ def run_b200(args):
         if "h2d" not in skip:
             S.yuv_picture_upload(sl.in_yuv, hp[k][0], W, hp[k][1], W // 2, hp[k][2], W // 2, bps, s_in.cuda_stream)    # H2D: Y + Cb + Cr (2 bytes / sample at 10 bits)
         sl.ev_in.record(s_in)
-        cs = cstreams[i % len(cstreams)]                                                   # consecutive frames alternate compute streams, as in the resident loop
+        cs = e2e_streams[i % len(e2e_streams)]                                             # consecutive frames alternate compute streams, as in the resident loop
         cs.wait_event(sl.ev_in)
         cs.wait_event(sl.ev_out)                                                           # this slot's previous results have left the device
-        if "pa" not in skip:
-            if hbd:      # UnPack8BitData (EbPackUnPack_C.c:153): the 8-bit luma PictureAnalysis / ME / OIS work on
-                S.pack_plane_dev(S.PACK_UNPACK8, sl.p["yint"], sl.in_t[0].shape[1], 0, 0, sl.in8.data_ptr(), W, 0, 0, W, H, cs.cuda_stream)
-                sl.pa.build_from_device(sl.in8.data_ptr(), W, cs.cuda_stream)
-            else:
-                sl.pa.build_from_device(sl.p["yint"], sl.in_t[0].shape[1], cs.cuda_stream)     # pad + decimate on the device
-        pipeline(i, sl.pa, sl.in_yuv, sl, cs, resident=False)
-        if "pack" not in skip:
-            S.tq_pack_coeffs_dev(sl.coeff, p_tq, sl.p["nz"], n_tq, sl.p["stream"], sl.cap, sl.p["off"], cs.cuda_stream)
+        g = frame_graphs.get(i % GRAPH_PERIOD) if frame_graphs else None
+        if g is not None:
+            with torch.cuda.stream(cs):
+                g.replay()                                                                 # the frame's kernels as one captured graph: one launch from the host
+        else:
+            frame_kernels(i, sl, cs, inline_dec=False)
         sl.ev_cmp.record(cs)
         s_small.wait_event(sl.ev_cmp)
         if sl.dec_pending:
@@ -751,6 +783,21 @@ def run_b200(args):
     for sl in slots[:NS]:
         finish_slot(sl)
     barrier()
+    graph_note = "off (--no-graphs)"
+    if not args.no_graphs and RING % 4 == 0:
+        try:
+            capture_frame_graphs()
+            barrier()
+            for i in range(GRAPH_PERIOD):      # first replay of every graph outside the timed region
+                step_e2e(args.warmup + i)
+            for sl in slots[:NS]:
+                finish_slot(sl)
+            barrier()
+            graph_note = f"{len(frame_graphs)} frame graphs (pa build + pipeline + coefficient pack per frame), {NS} slots, {len(e2e_streams)} streams"
+        except Exception as exc:      # capture refused on this driver / torch: fall back to call-by-call launches and say so
+            frame_graphs.clear()
+            torch.cuda.synchronize()
+            graph_note = f"capture failed, call-by-call launches: {type(exc).__name__}: {str(exc)[:160]}"
     w0 = time.perf_counter()
     d2h_bytes.clear()
     for i in range(args.steps):
@@ -804,7 +851,7 @@ def run_b200(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_link": pcie,
                     "host_link_all_ranks": {"h2d_gbs_min_max": [float(la[:, 0].min()), float(la[:, 0].max())], "d2h_gbs_min_max": [float(la[:, 1].min()), float(la[:, 1].max())],
                                             "duplex_each_gbs_min_max": [float(la[:, 2].min()), float(la[:, 2].max())]},
-                    "numa_binding_rank0": numa},
+                    "numa_binding_rank0": numa, "kernel_launch": graph_note, "frames_in_flight": NS},
             "gpu_launches": int(launches),
             **({"diagnosis_only_e2e_skip": sorted(skip)} if skip else {}),
             "clocks": sampler.summary(),
@@ -1078,6 +1125,7 @@ def main():
     ap.add_argument("--inflight", type=int, default=5, help="frames in flight in the end-to-end loop (device + pinned host buffers per frame)")
     ap.add_argument("--streams", type=int, default=2, help="compute streams the resident loop spreads consecutive frames over")
     ap.add_argument("--repeats", type=int, default=5, help="the timed region (--steps frames) is run this many times; the median run is reported")
+    ap.add_argument("--no-graphs", action="store_true", help="e2e loop: launch every stage call by call instead of replaying one captured CUDA graph per frame")
     ap.add_argument("--exchange", default="peer", choices=["peer", "p2p"], help="config 4, N > 1: GOP hand-off by peer-memory copies over NVLink (default) or by send / recv")
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config (1-based index in `configs`): 2 headline (default), 3 10-bit M7 4K, "
                     "4 8K 10-bit closed GOPs over the GPUs with the NCCL GOP-boundary exchange, 5 1080p stream density")
