@@ -1123,7 +1123,7 @@ def main():
     ap.add_argument("--no-encoder-app", action="store_true", help="reference arm: skip the whole-encoder run of the reference's own CLI")
     ap.add_argument("--e2e-skip", default="", help="diagnosis only: comma list of e2e parts to leave out (h2d, d2h, pack, pa); a run with this set is not a bench value")
     ap.add_argument("--inflight", type=int, default=5, help="frames in flight in the end-to-end loop (device + pinned host buffers per frame)")
-    ap.add_argument("--streams", type=int, default=2, help="compute streams the resident loop spreads consecutive frames over")
+    ap.add_argument("--streams", type=int, default=3, help="compute streams the resident loop spreads consecutive frames over")
     ap.add_argument("--repeats", type=int, default=5, help="the timed region (--steps frames) is run this many times; the median run is reported")
     ap.add_argument("--no-graphs", action="store_true", help="e2e loop: launch every stage call by call instead of replaying one captured CUDA graph per frame")
     ap.add_argument("--exchange", default="peer", choices=["peer", "p2p"], help="config 4, N > 1: GOP hand-off by peer-memory copies over NVLink (default) or by send / recv")
