@@ -42,16 +42,16 @@ RING = 16
 PAD = 80
 # BASELINE.json configs (index in `configs`, 0-based = id - 1).  2 is the headline the driver runs; 3 / 4 / 5: --config N
 CONFIGS = {
-    2: dict(w=3840, h=2160, bits=8, enc_mode=10, fps=60, streams=2, gop_exchange=False,
+    2: dict(w=3840, h=2160, bits=8, enc_mode=10, fps=60, streams=3, gop_exchange=False,
             metric="4Kp60 8-bit preset-M10 hot-path CTUs/sec (fps = value / 2040)",
             workload="configs[1]: 3840x2160 8-bit 4:2:0, preset M10 tool schedule, mini-GOP temporal layers [0,3,2,3,1,3,2,3], 2 reference lists, "
                      "fixed 32x32 PU/TU mode-decision stand-in"),
-    3: dict(w=3840, h=2160, bits=10, enc_mode=7, fps=60, streams=2, gop_exchange=False,
+    3: dict(w=3840, h=2160, bits=10, enc_mode=7, fps=60, streams=3, gop_exchange=False,
             metric="4Kp60 10-bit preset-M7 hot-path CTUs/sec (fps = value / 2040)",
             workload="configs[2]: 3840x2160 10-bit 4:2:0, preset M7 tool schedule (HME level 0 in 2x2 regions + level 1, 16x9 full-pel search, selective sub-pel "
                      "refinement on every layer, full open-loop intra search), 8-bit + 2-bit input planes packed to 16-bit samples on the device, 16-bit MC / "
                      "T-Q / DLF / SAO, mini-GOP temporal layers [0,3,2,3,1,3,2,3], 2 reference lists, fixed 32x32 PU/TU mode-decision stand-in"),
-    4: dict(w=7680, h=4320, bits=10, enc_mode=10, fps=50, streams=2, gop_exchange=True,
+    4: dict(w=7680, h=4320, bits=10, enc_mode=10, fps=50, streams=3, gop_exchange=True,
             metric="8Kp50 10-bit preset-M10 hot-path CTUs/sec, closed GOPs round-robin over the GPUs (fps = value / 8160)",
             workload="configs[3]: 7680x4320 10-bit 4:2:0, preset M10 tool schedule, closed GOPs of 16 pictures, GOP g on rank g % N, per-picture outputs "
                      "(packed coefficients + offsets + nz + ME / OIS / SAO records) sent to rank 0 over NCCL at every GOP boundary inside the timed region"),
