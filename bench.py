@@ -646,7 +646,9 @@ def run_b200(args):
         NS = 4
         while len(slots) < NS:
             slots.append(Slot())
-        e2e_streams = (cstreams + [torch.cuda.Stream(device=dev) for _ in range(4)])[:4]
+        e2e_streams = [torch.cuda.Stream(device=dev) for _ in range(4)]      # (capture needs non-default streams)
+        for cs in e2e_streams:
+            dstreams[cs] = torch.cuda.Stream(device=dev)
 
     def capture_frame_graphs():
         for i in range(GRAPH_PERIOD):
@@ -786,6 +788,8 @@ def run_b200(args):
     graph_note = "off (--no-graphs)"
     if not args.no_graphs and RING % 4 == 0:
         try:
+            for sl in slots:
+                sl.dec_pending = False      # (everything has completed at the barrier: no event of the call-by-call frames may enter a capture)
             capture_frame_graphs()
             barrier()
             for i in range(GRAPH_PERIOD):      # first replay of every graph outside the timed region
