@@ -514,6 +514,19 @@ def run_b200(args):
         for pl, (w_, h_, pad) in enumerate(((W, H, PAD), (W // 2, H // 2, PAD // 2), (W // 2, H // 2, PAD // 2))):
             S.pack_plane_dev(S.PACK_MSB, d_in8[k][pl].data_ptr(), w_, d_inn[k][pl].data_ptr(), w_, sl.src_t[pl][pad:, pad:].data_ptr(), sl.src_t[pl].shape[1], 0, 0, w_, h_, st)
 
+    def side_decision(sl, ts, timed=None):
+        """No picture stage of a frame outside layer 0 waits for its SAO decision (SAO is not applied there): the decision's dependency chain (an anti-diagonal
+        wavefront in one CTA) runs on a side stream next to the following frame's kernels; whoever consumes the decisions (the copy-out, the GOP exchange)
+        waits for ev_dec."""
+        P, side = sl.p, dstreams[ts]
+        e = torch.cuda.Event(); e.record(ts); side.wait_event(e)
+        fn = lambda: S.sao_decision_picture_dev(P["stats"], COLS, ROWS, rates_b, SAO_LAMBDA[0], SAO_LAMBDA[1], 1 if hbd else 0, P["dec"], P["sao_prm"], side.cuda_stream)
+        if timed is not None:
+            timed("sao_dec", fn, on=side)
+        else:
+            fn()
+        sl.ev_dec.record(side); sl.dec_pending = True
+
     def pipeline(i, src_pa, src_yuv, sl, ts, ev=None, resident=True, inline_dec=False):
         """All device stages of frame i into slot sl on torch stream ts.  ev: dict name -> list of (start, end) events."""
         st = ts.cuda_stream
@@ -548,15 +561,9 @@ def run_b200(args):
             timed("sao_apply", lambda: F["sao_apply"](pred, sl.sao_out, P["sao_prm"], (1, 1), st))
         else:
             timed("sao_stats", lambda: F["sao_stats"](src_yuv, pred, P["stats"], st))
-            if inline_dec:      # (a captured frame graph is one stream: the decision stays in it)
-                timed("sao_dec", lambda: S.sao_decision_picture_dev(P["stats"], COLS, ROWS, rates_b, SAO_LAMBDA[0], SAO_LAMBDA[1], 1 if hbd else 0, P["dec"], P["sao_prm"], st))
+            if inline_dec:      # (a captured frame graph is one stream: the caller runs this frame's decision after the replay, see side_decision)
                 return
-            # no picture stage of this frame waits for the decision (SAO is not applied on this layer): its dependency chain (an anti-diagonal wavefront in one
-            # CTA) runs on a side stream next to the following frame's kernels; whoever consumes the decisions (the copy-out, the GOP exchange) waits for ev_dec
-            side = dstreams[ts]
-            e = torch.cuda.Event(); e.record(ts); side.wait_event(e)
-            timed("sao_dec", lambda: S.sao_decision_picture_dev(P["stats"], COLS, ROWS, rates_b, SAO_LAMBDA[0], SAO_LAMBDA[1], 1 if hbd else 0, P["dec"], P["sao_prm"], side.cuda_stream), on=side)
-            sl.ev_dec.record(side); sl.dec_pending = True
+            side_decision(sl, ts, timed)
         if cfg["gop_exchange"] and resident:
             timed("pack_coeffs", lambda: S.tq_pack_coeffs_dev(sl.coeff, p_tq, P["nz"], n_tq, P["stream"], sl.cap, P["off"], st))
 
@@ -673,8 +680,12 @@ def run_b200(args):
         cs.wait_event(sl.ev_out)                                                           # this slot's previous results have left the device
         g = frame_graphs.get(i % GRAPH_PERIOD) if frame_graphs else None
         if g is not None:
+            if sl.dec_pending:                                                             # (the wait the call-by-call pipeline issues before its statistics kernel)
+                cs.wait_event(sl.ev_dec); sl.dec_pending = False
             with torch.cuda.stream(cs):
                 g.replay()                                                                 # the frame's kernels as one captured graph: one launch from the host
+            if wl.tl(i) != 0:
+                side_decision(sl, cs)
         else:
             frame_kernels(i, sl, cs, inline_dec=False)
         sl.ev_cmp.record(cs)
