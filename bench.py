@@ -42,20 +42,20 @@ RING = 16
 PAD = 80
 # BASELINE.json configs (index in `configs`, 0-based = id - 1).  2 is the headline the driver runs; 3 / 4 / 5: --config N
 CONFIGS = {
-    2: dict(w=3840, h=2160, bits=8, enc_mode=10, fps=60, streams=3, gop_exchange=False,
+    2: dict(w=3840, h=2160, bits=8, enc_mode=10, fps=60, streams=3, gop_exchange=False, graphs=False,
             metric="4Kp60 8-bit preset-M10 hot-path CTUs/sec (fps = value / 2040)",
             workload="configs[1]: 3840x2160 8-bit 4:2:0, preset M10 tool schedule, mini-GOP temporal layers [0,3,2,3,1,3,2,3], 2 reference lists, "
                      "fixed 32x32 PU/TU mode-decision stand-in"),
-    3: dict(w=3840, h=2160, bits=10, enc_mode=7, fps=60, streams=3, gop_exchange=False,
+    3: dict(w=3840, h=2160, bits=10, enc_mode=7, fps=60, streams=3, gop_exchange=False, graphs=True,
             metric="4Kp60 10-bit preset-M7 hot-path CTUs/sec (fps = value / 2040)",
             workload="configs[2]: 3840x2160 10-bit 4:2:0, preset M7 tool schedule (HME level 0 in 2x2 regions + level 1, 16x9 full-pel search, selective sub-pel "
                      "refinement on every layer, full open-loop intra search), 8-bit + 2-bit input planes packed to 16-bit samples on the device, 16-bit MC / "
                      "T-Q / DLF / SAO, mini-GOP temporal layers [0,3,2,3,1,3,2,3], 2 reference lists, fixed 32x32 PU/TU mode-decision stand-in"),
-    4: dict(w=7680, h=4320, bits=10, enc_mode=10, fps=50, streams=3, gop_exchange=True,
+    4: dict(w=7680, h=4320, bits=10, enc_mode=10, fps=50, streams=3, gop_exchange=True, graphs=False,
             metric="8Kp50 10-bit preset-M10 hot-path CTUs/sec, closed GOPs round-robin over the GPUs (fps = value / 8160)",
             workload="configs[3]: 7680x4320 10-bit 4:2:0, preset M10 tool schedule, closed GOPs of 16 pictures, GOP g on rank g % N, per-picture outputs "
                      "(packed coefficients + offsets + nz + ME / OIS / SAO records) sent to rank 0 over NCCL at every GOP boundary inside the timed region"),
-    5: dict(w=1920, h=1080, bits=8, enc_mode=10, fps=60, streams=4, gop_exchange=False,
+    5: dict(w=1920, h=1080, bits=8, enc_mode=10, fps=60, streams=4, gop_exchange=False, graphs=True,
             metric="1080p60 8-bit preset-M10 stream-density hot-path CTUs/sec, 4 concurrent streams per GPU (fps per stream = value / 510 / (4 * N))",
             workload="configs[4]: 4 independent 1920x1080 8-bit streams per GPU (32 on 8 GPUs), preset M10 (the reference rejects M12 at 1080p, "
                      "EbEncHandle.c:2304-2309), one compute stream per video stream, no communication"),
@@ -1141,6 +1141,8 @@ def main():
     ap.add_argument("--streams", type=int, default=3, help="compute streams the resident loop spreads consecutive frames over")
     ap.add_argument("--repeats", type=int, default=5, help="the timed region (--steps frames) is run this many times; the median run is reported")
     ap.add_argument("--no-graphs", action="store_true", help="e2e loop: launch every stage call by call instead of replaying one captured CUDA graph per frame")
+    ap.add_argument("--graphs", action="store_true", help="e2e loop: replay captured frame graphs even where the configuration's default is call by call (measured per "
+                    "configuration: the 1080p and the 10-bit 4K loops are host-bound and gain 6-18 %, the 8-bit 4K loop is not and loses 7 %)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "p2p"], help="config 4, N > 1: GOP hand-off by peer-memory copies over NVLink (default) or by send / recv")
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config (1-based index in `configs`): 2 headline (default), 3 10-bit M7 4K, "
                     "4 8K 10-bit closed GOPs over the GPUs with the NCCL GOP-boundary exchange, 5 1080p stream density")
@@ -1149,6 +1151,8 @@ def main():
     c = set_config(args.config)
     if "--streams" not in sys.argv:
         args.streams = c["streams"]
+    if not args.graphs and not c["graphs"]:
+        args.no_graphs = True
     if args.config == 4 and "--steps" not in sys.argv:
         args.steps = 32
     if args.config == 4 and "--repeats" not in sys.argv:
