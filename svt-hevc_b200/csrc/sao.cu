@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(ST_NT) sao_stats_kernel(const __grid_constant_
 // vertical compares of a row serve the next row (sign(v[y] - v[y+1]) = -sign(v[y+1] - v[y])), and the three rows a sample needs live in registers as the
 // strip walks down.  Only the band-offset bins keep the thread-private shared-memory histogram.  Warps 0-3: luma (16 word columns x 8 strips), warp 4: Cb,
 // warp 5: Cr (8 word columns x 4 strips).  Same 62 x 62 interior rule, same H3 composition, same output layout as sao_stats_kernel.
-constexpr int ST2_NT = 192, ST2_P = ST2_NT + 1;
+constexpr int ST2_NT = 192, ST2_P = ST2_NT;      // pitch a multiple of 32: a thread's column stays in ITS bank whatever band a sample falls into
 // 0xff where the byte's top bit is set, else 0: PRMT with the sign-replicate bit of every selector nibble (__byte_perm() masks that bit off, hence the PTX)
 __device__ __forceinline__ uint32_t msb_mask(uint32_t w)
 {
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(ST2_NT) sao_stats2_kernel(const __grid_constan
     // reconstructed blocks of the three components with a one-word margin on every side: luma 66 rows x 72 bytes, chroma 34 rows x 40 bytes each
     __shared__ __align__(16) uint8_t s_y[66 * 72];
     __shared__ __align__(16) uint8_t s_c[2][34 * 40];
-    __shared__ int s_bo[32 * ST2_P];             // thread-private band histograms [band][thread], word = (count << 16) + sum(diff); odd pitch: see the reduction
+    __shared__ int s_bo[32 * ST2_P];             // thread-private band histograms [band][thread], word = (count << 16) + sum(diff)
     __shared__ int s_eo[3][32];                  // per component: 4 types x (4 counts, 4 sums)
     const int lcu = blockIdx.x, lx = lcu % A.cols, ly = lcu / A.cols;
     const int wid = threadIdx.x >> 5;
@@ -282,15 +282,16 @@ __global__ void __launch_bounds__(ST2_NT) sao_stats2_kernel(const __grid_constan
         if (k < 4) { o->eo_diff[k][4] = 0; o->eo_count[k][4] = 0; }
     }
     // band histograms: component cc owns the thread columns [first, first + n): luma 0..127, Cb 128..159, Cr 160..191.  One thread per (component,
-    // band) walks its row of the [band][thread] table -- the odd pitch puts the 32 rows a warp reads at the same column into 32 different banks -- and
-    // adds four packed words at a time before unpacking (4 x 32 samples: count <= 128, |sum of differences| <= 16 256, both inside their half word).
+    // band) walks its row of the [band][thread] table, starting at a column skewed by its band so that the 32 rows a warp reads fall into 32 different
+    // banks, and adds four packed words at a time before unpacking (4 x 32 samples: count <= 128, |sum of differences| <= 16 256, inside their half word).
     if (threadIdx.x < 96) {
         const int cc = threadIdx.x >> 5, band = threadIdx.x & 31;
         const int first = cc == 0 ? 0 : 96 + 32 * cc, n = cc == 0 ? 128 : 32;
         const int *row = s_bo + band * ST2_P + first;
         int dsum = 0, csum = 0;
-        for (int q = 0; q < n; q += 4) {
-            const int w = row[q] + row[q + 1] + row[q + 2] + row[q + 3], dd = (int)(short)(w & 0xffff);
+        for (int q0 = 0; q0 < n; q0 += 4) {
+            const int q = (q0 + band) & (n - 1);      // n is 32 or 128
+            const int w = row[q] + row[(q + 1) & (n - 1)] + row[(q + 2) & (n - 1)] + row[(q + 3) & (n - 1)], dd = (int)(short)(w & 0xffff);
             dsum += dd; csum += (w - dd) >> 16;
         }
         svtb200_sao_stats *o = A.out + (size_t)lcu * 3 + cc;
