@@ -875,7 +875,11 @@ def run_b200(args):
                          "bound": "hbm", "achieved": alg[dom] / k_avg_s / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg[dom] / k_avg_s / 1e9 / peak, "traffic": traffic.get(dom), "traffic_source": traffic_src,
                          "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg[dom], "avg_launch_ms": k_avg_s * 1e3},
+                         "algorithmic_bytes_per_launch": alg[dom], "avg_launch_ms": k_avg_s * 1e3,
+                         # achieved / frac above follow the contract: launch durations taken INSIDE the timed region, where the frames of several streams share the
+                         # SMs (a launch lasts longer than the kernel's own time, the more streams the longer).  The same kernel alone on the GPU:
+                         "alone": {"avg_launch_ms": float(np.mean(serial_ms[dom])), "achieved": alg[dom] / (float(np.mean(serial_ms[dom])) * 1e-3) / 1e9,
+                                   "frac": alg[dom] / (float(np.mean(serial_ms[dom])) * 1e-3) / 1e9 / peak, "streams_in_timed_region": args.streams}},
             # SURVEY 8d's secondary bound for ME: the VABSDIFF4 instructions the search cannot avoid at the measured issue rate of their (half-rate) pipe
             "me_issue_roofline": me_issue,
             "timed_region_runs_ms": runs_ms,
