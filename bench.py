@@ -879,7 +879,10 @@ def run_b200(args):
                          # achieved / frac above follow the contract: launch durations taken INSIDE the timed region, where the frames of several streams share the
                          # SMs (a launch lasts longer than the kernel's own time, the more streams the longer).  The same kernel alone on the GPU:
                          "alone": {"avg_launch_ms": float(np.mean(serial_ms[dom])), "achieved": alg[dom] / (float(np.mean(serial_ms[dom])) * 1e-3) / 1e9,
-                                   "frac": alg[dom] / (float(np.mean(serial_ms[dom])) * 1e-3) / 1e9 / peak, "streams_in_timed_region": args.streams}},
+                                   "frac": alg[dom] / (float(np.mean(serial_ms[dom])) * 1e-3) / 1e9 / peak, "streams_in_timed_region": args.streams},
+                         "note": "achieved / frac use launch durations inside the timed region, where the frames of several compute streams share the SMs: a launch lasts longer "
+                                 "than the kernel's own time (round 1 ran 2 streams, this run --streams above: more streams raise `value` and lower this fraction); "
+                                 "`alone` is the same kernel with nothing else on the GPU"},
             # SURVEY 8d's secondary bound for ME: the VABSDIFF4 instructions the search cannot avoid at the measured issue rate of their (half-rate) pipe
             "me_issue_roofline": me_issue,
             "timed_region_runs_ms": runs_ms,
