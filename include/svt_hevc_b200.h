@@ -620,6 +620,11 @@ int svtb200_yuv_picture_pad_dev(const svtb200_yuv_picture *dev, void *cuda_strea
  * unmodified, e.g. the picture before svtb200_dlf_picture_dev for svtb200_sao_stats_picture_h3_dev (the reference keeps it implicitly: its LCU n is
  * gathered before LCU n + 1 is deblocked, Codec/EbCodingLoop.c:4604-4748). */
 int svtb200_yuv_picture_copy_dev(const svtb200_yuv_picture *src, const svtb200_yuv_picture *dst, uint32_t bytes_per_sample, void *cuda_stream);
+/* N1: the per-LCU mean / variance pyramid of PictureAnalysis (ComputeBlockMeanComputeVariance, Codec/EbPictureAnalysisProcess.c:1646; 8x8 figures of
+ * ComputeSubMean8x8 / ComputeSubdMeanOfSquaredValues8x8, ASM_SSE2/EbComputeMean_Intrinsic_SSE2.c:53,10) of the padded input luma:
+ * y_mean[lcu][85] = PictureParentControlSet_t::yMean, variance[lcu][85] = ::variance, PU order of ME_TIER_ZERO_PU_* (64x64, 32x32 x 4, 16x16 x 16, 8x8 x 64). */
+int svtb200_variance_picture(const svtb200_plane *luma_padded, uint8_t *y_mean, uint16_t *variance);
+int svtb200_variance_picture_dev(const svtb200_plane *luma_padded_dev, uint8_t *y_mean_dev, uint16_t *variance_dev, void *cuda_stream);
 int svtb200_copy_async(void *dst, const void *src, size_t bytes, int device_to_host, void *cuda_stream);
 /* Peer memory for the GOP-boundary hand-off to the entropy-coding rank (one process per GPU): the receiver allocates and exports its buffers,
  * every producer opens them (CUDA IPC, peer access enabled lazily) and moves a finished picture's outputs device to device over NVLink with the copy

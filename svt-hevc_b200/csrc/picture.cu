@@ -180,6 +180,93 @@ int svtb200_copy_async(void *dst, const void *src, size_t bytes, int device_to_h
     return SVTB200_OK;
 }
 
+// ---- PictureAnalysis feeder: the per-LCU mean / variance pyramid -------------------------------------------------------------
+// ComputeBlockMeanComputeVariance (Codec/EbPictureAnalysisProcess.c:1646-2400) with the 8x8 figures of ComputeSubMean8x8_SSE2_INTRIN /
+// ComputeSubdMeanOfSquaredValues8x8_SSE2_INTRIN (ASM_SSE2/EbComputeMean_Intrinsic_SSE2.c:53,10: rows 0, 2, 4, 6 of the block; sum << 3, sum of squares
+// << 11) -- the AVX2 row (ComputeIntermVarFour8x8_AVX2_INTRIN) is arithmetically the same.  One CTA of 64 threads per LCU, a thread per 8x8 block
+// (VABSDIFF4 against 0 for the sums, DP4A(w, w) for the squares), the 16x16 / 32x32 / 64x64 levels ((sum of four children) >> 2) through shared memory.
+// Outputs in the order of ME_TIER_ZERO_PU_*: 64x64, 4 x 32x32, 16 x 16x16, 64 x 8x8 (raster each): yMean = mean >> 8 (EB_U8), variance =
+// (mean of squares - mean^2) >> 16 (EB_U16).  A partial last LCU reads the picture's padding like the reference.
+__global__ void __launch_bounds__(64) variance_kernel(const uint8_t *luma00, int stride, int cols, uint8_t *y_mean, uint16_t *variance)
+{
+    __shared__ unsigned long long s_m[64 + 16 + 4 + 1], s_s[64 + 16 + 4 + 1];
+    const int lcu = blockIdx.x, b = threadIdx.x;
+    const uint8_t *q = luma00 + (size_t)((lcu / cols) * 64 + (b >> 3) * 8) * stride + (lcu % cols) * 64 + (b & 7) * 8;
+    uint32_t sum = 0, sq = 0;
+#pragma unroll
+    for (int r = 0; r < 8; r += 2) {
+        const uint32_t w0 = ld_u32_unaligned(q + (size_t)r * stride), w1 = ld_u32_unaligned(q + (size_t)r * stride + 4);
+        sum = vsad4_acc(w0, 0u, sum); sum = vsad4_acc(w1, 0u, sum);
+        asm("dp4a.u32.u32 %0, %1, %1, %0;" : "+r"(sq) : "r"(w0));
+        asm("dp4a.u32.u32 %0, %1, %1, %0;" : "+r"(sq) : "r"(w1));
+    }
+    s_m[21 + b] = (unsigned long long)sum << 3;
+    s_s[21 + b] = (unsigned long long)sq << 11;
+    __syncthreads();
+    if (b < 16) {
+        const int i = 21 + (b >> 2) * 16 + (b & 3) * 2;
+        s_m[5 + b] = (s_m[i] + s_m[i + 1] + s_m[i + 8] + s_m[i + 9]) >> 2;
+        s_s[5 + b] = (s_s[i] + s_s[i + 1] + s_s[i + 8] + s_s[i + 9]) >> 2;
+    }
+    __syncthreads();
+    if (b < 4) {
+        const int i = 5 + (b >> 1) * 8 + (b & 1) * 2;
+        s_m[1 + b] = (s_m[i] + s_m[i + 1] + s_m[i + 4] + s_m[i + 5]) >> 2;
+        s_s[1 + b] = (s_s[i] + s_s[i + 1] + s_s[i + 4] + s_s[i + 5]) >> 2;
+    }
+    __syncthreads();
+    if (b == 0) { s_m[0] = (s_m[1] + s_m[2] + s_m[3] + s_m[4]) >> 2; s_s[0] = (s_s[1] + s_s[2] + s_s[3] + s_s[4]) >> 2; }
+    __syncthreads();
+    for (int k = b; k < 85; k += 64) {
+        const unsigned long long m = s_m[k];
+        y_mean[(size_t)lcu * 85 + k] = (uint8_t)(m >> 8);
+        variance[(size_t)lcu * 85 + k] = (uint16_t)((s_s[k] - m * m) >> 16);
+    }
+}
+
+static int variance_check(const svtb200_plane *p, const void *a, const void *b, const char *who)
+{
+    if (!p || !p->buf || !a || !b || !p->width || !p->height) { set_error("%s: bad argument", who); return SVTB200_ERR_BAD_ARG; }
+    const uint32_t cols = (p->width + 63) / 64, rows = (p->height + 63) / 64;
+    // the last LCU row / column is read in full: the padding has to hold it (it does for the encoder's 68-sample padding and any picture size it accepts)
+    if (p->stride < p->origin_x + cols * 64 || (uint32_t)p->height + 2 * p->origin_y < p->origin_y + rows * 64) {
+        set_error("%s: the plane's padding does not cover the last (partial) LCU row / column", who); return SVTB200_ERR_BAD_ARG;
+    }
+    return SVTB200_OK;
+}
+
+int svtb200_variance_picture_dev(const svtb200_plane *luma_dev, uint8_t *y_mean_dev, uint16_t *variance_dev, void *cuda_stream)
+{
+    int rc = variance_check(luma_dev, y_mean_dev, variance_dev, "variance_picture_dev");
+    if (rc || (rc = ensure_device())) return rc;
+    const int cols = (luma_dev->width + 63) / 64, rows = (luma_dev->height + 63) / 64;
+    variance_kernel<<<cols * rows, 64, 0, (cudaStream_t)cuda_stream>>>(luma_dev->buf + (size_t)luma_dev->origin_y * luma_dev->stride + luma_dev->origin_x, (int)luma_dev->stride, cols,
+                                                                       y_mean_dev, variance_dev);
+    SVTB200_COUNT_LAUNCH();
+    SVTB200_CUDA_TRY(cudaGetLastError());
+    return SVTB200_OK;
+}
+
+int svtb200_variance_picture(const svtb200_plane *luma, uint8_t *y_mean, uint16_t *variance)
+{
+    int rc = variance_check(luma, y_mean, variance, "variance_picture");
+    if (rc) return rc;
+    ThreadCtx *c = tls_ctx();
+    if ((rc = c->init())) return rc;
+    c->reset();
+    const size_t pb = (size_t)luma->stride * (luma->height + 2 * luma->origin_y), n = (size_t)((luma->width + 63) / 64) * ((luma->height + 63) / 64);
+    void *d_p, *d_m, *d_v;
+    if ((rc = c->dev_reserve(pb + n * 85 * 3 + 4096)) || (rc = c->dev_alloc(pb, &d_p)) || (rc = c->dev_alloc(n * 85, &d_m)) || (rc = c->dev_alloc(n * 85 * 2, &d_v))) return rc;
+    SVTB200_CUDA_TRY(cudaMemcpyAsync(d_p, luma->buf, pb, cudaMemcpyHostToDevice, c->stream));
+    svtb200_plane dp = *luma;
+    dp.buf = (uint8_t *)d_p;
+    if ((rc = svtb200_variance_picture_dev(&dp, (uint8_t *)d_m, (uint16_t *)d_v, c->stream))) return rc;
+    SVTB200_CUDA_TRY(cudaMemcpyAsync(y_mean, d_m, n * 85, cudaMemcpyDeviceToHost, c->stream));
+    SVTB200_CUDA_TRY(cudaMemcpyAsync(variance, d_v, n * 85 * 2, cudaMemcpyDeviceToHost, c->stream));
+    SVTB200_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SVTB200_OK;
+}
+
 // ---- peer memory for the GOP-boundary hand-off: one process per GPU, the entropy-coding rank's receive buffers mapped into every
 // producer's address space (CUDA IPC) so that a finished picture's outputs move GPU to GPU over NVLink by the copy engines -- no SM, no staging, no
 // collective in the data path.  Exportable memory comes from cudaMalloc directly (pool allocators hand out sub-ranges an IPC handle cannot name).

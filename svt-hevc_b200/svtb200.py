@@ -574,6 +574,14 @@ CU_INFO_DTYPE = np.dtype([("mv", "<i2", (2, 2)), ("pred_dir", "u1"), ("intra", "
 assert CU_INFO_DTYPE.itemsize == 12
 
 
+def variance_picture(plane):
+    """PictureAnalysis' per-LCU mean / variance pyramid of a padded host luma plane (Plane) -> (y_mean[n_lcu][85] u8, variance[n_lcu][85] u16)"""
+    n = ((plane.width + 63) // 64) * ((plane.height + 63) // 64)
+    ym, vr = np.zeros((n, 85), np.uint8), np.zeros((n, 85), np.uint16)
+    check(lib().svtb200_variance_picture(C.byref(plane), _u8p(ym), _u8p(vr)))
+    return ym, vr
+
+
 # ---- peer memory (GOP-boundary hand-off over NVLink) ------------------------------------------------------------------------------------
 def peer_alloc(nbytes):
     p = C.c_void_p()
