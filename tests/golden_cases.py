@@ -229,6 +229,97 @@ def _sao_h3(case, backend):
     return _h(st["bo_diff"], st["bo_count"], st["eo_diff"][..., :4], st["eo_count"][..., :4])
 
 
+# ---- round-2 rows: boundary strengths, distortion leaves, interpolation-free prediction, mean / variance pyramid --------------------------------------
+def _bs(case, backend):
+    import test_oracle_bs as T
+    name, w, h, st, p0, p1 = case
+    cu, cbf = T.make_md_maps(w, h, seed=w + h + st, slice_type=st)
+    if backend == "cuda":
+        v, hh = S.dlf_bs_picture(cu, cbf, w, h, st, p0, p1)
+    else:
+        lib, fn = (T.ref, "svtref_dlf_bs_picture") if backend == "reference" else (T.port, "port_dlf_bs_picture")
+        assert lib is not None
+        v, hh = T.run_bs(lib, fn, cu, cbf, w, h, st, p0, p1)
+    return _h(v, hh)
+
+
+def _dist(case, backend):
+    """spatial SSD + SATD of one picture pair and the coefficient-domain distortion of one coefficient pair; the reference side calls the leaf kernels block by block"""
+    import test_oracle_dist as T
+    from test_oracle_mc import make_pictures
+    name, w, h, kind = case
+    a, b = make_pictures(w, h, seed=w + 1, n=2, kind=kind)
+    c, r = T.make_coeff_pictures(w, h, seed=h + 2)
+    js = T.make_dist_jobs(w, h, seed=3, n=120)
+    jt = T.make_dist_jobs(w, h, seed=4, n=120, kinds=(S.SATD_8X8, S.SATD_4X4), unit_of=lambda k: 8 if k == S.SATD_8X8 else 4)
+    jf = T.make_dist_jobs(w, h, seed=5, n=120, kinds=(S.FULLDIST_DEFAULT, S.FULLDIST_INTRA, S.FULLDIST_CBF_ZERO))
+    jf = jf[jf["width"] <= 32]
+    if backend == "cuda":
+        return _h(S.spatial_distortion_batch(a, b, js), S.satd_batch(a, b, jt), S.full_distortion_batch(c, r, w, h, jf))
+    if backend == "port":
+        return _h(T.run_port_batch("port_spatial_distortion_batch", a, b, js), T.run_port_batch("port_satd_batch", a, b, jt),
+                  T.run_port_batch("port_full_distortion_batch", c, r, jf, per_job=2))
+    ref = T.ref
+    assert ref is not None
+    vp = lambda arr, off=0: C.c_void_p(arr.ctypes.data + off)
+    ref.SpatialFullDistortionKernel.restype = ref.Compute8x8Satd.restype = ref.Compute4x4Satd.restype = C.c_uint64
+    ssd = np.zeros(len(js), np.uint64)
+    for j, t in enumerate(js):
+        pa, pb = a.interior()[t["plane"]], b.interior()[t["plane"]]
+        ssd[j] = ref.SpatialFullDistortionKernel(vp(pa, int(t["y"]) * pa.strides[0] + int(t["x"])), C.c_uint32(pa.strides[0]), vp(pb, int(t["y"]) * pb.strides[0] + int(t["x"])),
+                                                 C.c_uint32(pb.strides[0]), C.c_uint32(int(t["width"])), C.c_uint32(int(t["height"])))
+    satd = np.zeros(len(jt), np.uint64)
+    for j, t in enumerate(jt):
+        pa, pb = a.interior()[t["plane"]], b.interior()[t["plane"]]
+        u = 8 if t["kind"] == S.SATD_8X8 else 4
+        fn = ref.Compute8x8Satd if u == 8 else ref.Compute4x4Satd
+        tot = 0
+        for uy in range(int(t["height"]) // u):
+            for ux in range(int(t["width"]) // u):
+                y0, x0 = int(t["y"]) + uy * u, int(t["x"]) + ux * u
+                d = np.ascontiguousarray(pa[y0:y0 + u, x0:x0 + u].astype(np.int16) - pb[y0:y0 + u, x0:x0 + u].astype(np.int16))
+                tot += fn(vp(d))
+        satd[j] = tot
+    names = {S.FULLDIST_DEFAULT: "FullDistortionKernel_32bit", S.FULLDIST_INTRA: "FullDistortionKernelIntra_32bit", S.FULLDIST_CBF_ZERO: "FullDistortionKernelCbfZero_32bit"}
+    full = np.zeros((len(jf), 2), np.uint64)
+    for j, t in enumerate(jf):
+        pc, pr = c.planes[t["plane"]], r.planes[t["plane"]]
+        out = (C.c_uint64 * 2)()
+        off = (int(t["y"]) * pc.shape[1] + int(t["x"])) * 2
+        getattr(ref, names[int(t["kind"])])(vp(pc, off), C.c_uint32(pc.shape[1]), vp(pr, off), C.c_uint32(pr.shape[1]), out, C.c_uint32(int(t["width"])), C.c_uint32(int(t["height"])))
+        full[j] = (out[0], out[1])
+    return _h(ssd, satd, full)
+
+
+def _mc_ifree(case, backend):
+    from test_oracle_mc import make_jobs, make_pictures, run_oracle
+    name, w, h, kind, all_fracs, big = case
+    refs = make_pictures(w, h, seed=13, kind=kind)
+    jobs = make_jobs(w, h, len(refs), seed=6, all_fracs=all_fracs, big_mv=big)
+    if backend == "reference":
+        out = run_oracle(common.load_ref(), "svtref_mc_ifree_batch", refs, jobs, w, h, asm_mode=0)
+    elif backend == "port":
+        out = run_oracle(common.load_port(), "port_mc_ifree_batch", refs, jobs, w, h)
+    else:
+        out = S.HostYuvPicture(np.zeros((h, w), np.uint8), np.zeros((h // 2, w // 2), np.uint8), np.zeros((h // 2, w // 2), np.uint8))
+        S.mc_ifree_batch(refs, jobs, out)
+    return _h(*_planes(out))
+
+
+def _variance(case, backend):
+    import test_oracle_pa as T
+    name, w, h, kind = case
+    pl, _keep = T.padded_luma(w, h, seed=w + h, kind=kind)
+    if backend == "reference":
+        assert T.refpa is not None
+        ym, vr = T.run_variance(T.refpa, "svtref_variance_picture", pl, C.c_int(0))
+    elif backend == "port":
+        ym, vr = T.run_variance(T.port, "port_variance_picture", pl)
+    else:
+        ym, vr = S.variance_picture(pl)
+    return _h(ym, vr)
+
+
 def cases():
     """[(key, runner, case)] -- small, seeded, a few seconds for all of them on any backend"""
     from test_oracle_dlf import DLF_CASES
@@ -261,4 +352,14 @@ def cases():
     out.append(("sao_h3/synth_partial_lcu_200x136", _sao_h3, DLF_CASES[1]))
     out.append(("ois/islice_256x192", _ois, ("islice", 256, 192, dict(slice_type=2), 9)))
     out.append(("ois/dc_only_448x256", _ois, ("dc_only", 448, 256, dict(slice_type=0, limit_ois_to_dc_mode=1, skip_ois_8x8=1), 1)))
+    from test_oracle_bs import BS_CASES
+    from test_oracle_pa import PA_CASES
+    for c in BS_CASES[:3] + BS_CASES[4:5]:
+        out.append((f"bs/{c[0]}", _bs, c))
+    out.append(("dist/synth_192x128", _dist, ("synth", 192, 128, "synth")))
+    out.append(("dist/random_128x64", _dist, ("random", 128, 64, "random")))
+    for c in MC_CASES[:1] + MC_CASES[3:4]:
+        out.append((f"mc_ifree/{c[0]}", _mc_ifree, c))
+    for c in PA_CASES[:1] + PA_CASES[2:3]:
+        out.append((f"variance/{c[0]}", _variance, c))
     return out
