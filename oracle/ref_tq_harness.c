@@ -168,3 +168,42 @@ int svtref_tq_batch16(const svtb200_yuv_picture *src, const svtb200_yuv_picture 
     free(res); free(tr); free(q); free(scratch); free(ctx); free(md); free(pcs); free(ppcs); free(scs);
     return 0;
 }
+
+/* The mode-decision full loop's quantiser: the reference's OWN ProductUnifiedQuantizeInvQuantizeMd (Codec/EbFullLoop.c:77) after EstimateTransform, per TU of
+ * the job list -- at enc modes >= 5 (rdoqPmCoreMethod == EB_NO_RDOQ, Codec/EbEncDecProcess.c:2201) it is QuantizeInvQuantize + UpdateQiQCoef with the I / P
+ * rounding offset, no dead-zone offset and enableCbflag = 0, i.e. what svtb200_tq_batch computes for a job with SVTB200_TQ_SKIP_RECON, dz_offset = 0 and no
+ * ENABLE_CBF / CLEAN_SPARSE flag.  Outputs: quantised coefficients (active area) and nz counts, like svtref_tq_batch. */
+#include "EbFullLoop.h"
+int svtref_tq_md_batch(const svtb200_yuv_picture *src, const svtb200_yuv_picture *pred, const svtb200_coeff_picture *coeff, const svtb200_tq_job *jobs, int n_jobs,
+                       uint32_t *nz_counts, int asm_mode)
+{
+    ASM_TYPES = asm_mode ? EbHevcGetCpuAsmType() : 0;
+    PictureParentControlSet_t *ppcs = (PictureParentControlSet_t *)calloc(1, sizeof(*ppcs));
+    PictureControlSet_t *pcs = (PictureControlSet_t *)calloc(1, sizeof(*pcs));
+    pcs->ParentPcsPtr = ppcs;
+    EB_S16 *res = (EB_S16 *)calloc(64 * 64, sizeof(EB_S16)), *tr = (EB_S16 *)calloc(64 * 64, sizeof(EB_S16));
+    EB_S16 *q = (EB_S16 *)calloc(64 * 64, sizeof(EB_S16)), *rc = (EB_S16 *)calloc(64 * 64, sizeof(EB_S16)), *scratch = (EB_S16 *)calloc(64 * 64, sizeof(EB_S16));
+    for (int j = 0; j < n_jobs; ++j) {
+        const svtb200_tq_job *t = &jobs[j];
+        if (t->shape == SVTB200_SHAPE_ONLY_DC) { nz_counts[j] = 0; continue; }      /* (the full loop has no ONLY_DC shape) */
+        const svtb200_plane *sp = pl(src, t->plane), *pp = pl(pred, t->plane);
+        const EB_U32 N = t->size;
+        EB_U8 *s = sp->buf + (size_t)(sp->origin_y + t->y) * sp->stride + sp->origin_x + t->x;
+        EB_U8 *p = pp->buf + (size_t)(pp->origin_y + t->y) * pp->stride + pp->origin_x + t->x;
+        memset(q, 0, 64 * 64 * sizeof(EB_S16));
+        PictureResidual(s, sp->stride, p, pp->stride, res, 64, N, N);
+        EstimateTransform(res, 64, tr, 64, N, scratch, BIT_INCREMENT_8BIT, (EB_BOOL)t->dst4x4, (EB_TRANS_COEFF_SHAPE)t->shape);
+        pcs->sliceType = t->slice_type == 3 ? EB_IDR_PICTURE : (EB_PICTURE)t->slice_type;
+        pcs->temporalLayerIndex = t->temporal_layer;
+        EB_U32 nz = 0;
+        ProductUnifiedQuantizeInvQuantizeMd(pcs, tr, 64, q, rc, t->qp, N, &nz, t->shape == SVTB200_SHAPE_N2 ? PF_N2 : t->shape == SVTB200_SHAPE_N4 ? PF_N4 : PF_OFF,
+                                            (t->flags & SVTB200_TQ_CONTOURING) ? 1 : 0, t->plane ? 1 : 0, EB_NO_RDOQ, NULL, 0, INTER_MODE, 0, 0, NULL);
+        nz_counts[j] = nz;
+        const EB_U32 act = N >> t->shape;
+        int16_t *co = coeff->buf[t->plane] + (size_t)t->y * coeff->stride[t->plane] + t->x;
+        for (EB_U32 y = 0; y < N; ++y)
+            for (EB_U32 x = 0; x < N; ++x) co[(size_t)y * coeff->stride[t->plane] + x] = (y < act && x < act) ? q[y * 64 + x] : 0;
+    }
+    free(res); free(tr); free(q); free(rc); free(scratch); free(pcs); free(ppcs);
+    return 0;
+}

@@ -146,6 +146,27 @@ TQ_CASES = [("default_synth", 256, 192, "synth", (0,), (0,)), ("default_random",
 
 
 @needs_ref
+@pytest.mark.parametrize("kind,shapes", [("synth", (0,)), ("random", (0, 1, 2)), ("extremes", (0, 1))], ids=["synth", "random_shapes", "extremes"])
+def test_md_quantiser_is_the_skip_recon_chain(kind, shapes):
+    """ProductUnifiedQuantizeInvQuantizeMd (Codec/EbFullLoop.c:77), the quantiser of the mode-decision full loop, at enc modes >= 5 (no RDOQ / PM core):
+    its coefficients and non-zero counts are those of the encode-pass chain run with SKIP_RECON, no dead-zone offset and no cbf / sparse flags -- so the
+    entry point that is parity-tested on the GPU (svtb200_tq_batch, golden case tq/skip_recon) covers it"""
+    w, h = 256, 128
+    src, pred = make_src_pred(w, h, 23, kind)
+    jobs = make_tq_jobs(w, h, seed=12, shapes=shapes, flags=(8, 8 | 4))      # SKIP_RECON, with and without the contouring update
+    jobs["dz_offset"] = 0
+    want_c = S.HostCoeffPicture(w, h)
+    want_nz = np.zeros(len(jobs), np.uint32)
+    fn = ref.svtref_tq_md_batch; fn.restype = C.c_int
+    for asm in ((0, 1) if common.ref_asm_simd_ok() else (0,)):
+        assert fn(C.byref(src.struct), C.byref(pred.struct), C.byref(want_c.struct), vp(jobs), C.c_int(len(jobs)), vp(want_nz), C.c_int(asm)) == 0
+        _, got_c, got_nz = run_tq_oracle(port, "port_tq_batch", src, pred, jobs, w, h)
+        assert np.array_equal(got_nz, want_nz), (asm, np.argwhere(got_nz != want_nz)[:5])
+        for a, b in zip(got_c.planes, want_c.planes):
+            assert np.array_equal(a, b), asm
+
+
+@needs_ref
 @pytest.mark.parametrize("case", TQ_CASES, ids=lambda c: c[0])
 def test_tq_batch_port_vs_reference(case):
     name, w, h, kind, shapes, flags = case
