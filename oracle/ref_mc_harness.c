@@ -166,3 +166,37 @@ int svtref_mc_ifree_batch(const svtb200_yuv_picture *refs, int n_refs, const svt
     free(t0); free(t1); free(t2); free(refDesc);
     return 0;
 }
+
+/* The mode-decision side of HEVC interpolation: the reference's OWN UniPredHevcInterpolationMd / BiPredHevcInterpolationMd (Source/Lib/Codec/EbMcp.c:99,321)
+ * with the position arithmetic of their caller Inter2Nx2NPuPredictionHevc (Codec/EbInterPrediction.c:469-760; 8-bit path).  They are the same table-dispatched
+ * kernels the encode pass runs, writing the candidate's prediction buffer; here every PU lands at its own position of `dst`, so the result must equal
+ * svtref_mc_batch's (and through it svtb200_mc_batch's). */
+int svtref_mc_md_batch(const svtb200_yuv_picture *refs, int n_refs, const svtb200_mc_job *jobs, int n_jobs, const svtb200_yuv_picture *dst, int asm_mode)
+{
+    ASM_TYPES = asm_mode ? EbHevcGetCpuAsmType() : 0;
+    EbPictureBufferDesc_t *refDesc = (EbPictureBufferDesc_t *)calloc((size_t)n_refs, sizeof(*refDesc)), dstDesc;
+    for (int i = 0; i < n_refs; ++i) {
+        if (refs[i].y.origin_x != 80 || refs[i].y.origin_y != 80) { free(refDesc); return -2; }
+        fill_yuv(&refDesc[i], &refs[i]);
+    }
+    fill_yuv(&dstDesc, dst);
+    EB_S16 *t0 = (EB_S16 *)malloc(64 * 64 * 8), *t1 = (EB_S16 *)malloc(64 * 64 * 8), *t2 = (EB_S16 *)malloc(72 * 72 * 8);
+    for (int j = 0; j < n_jobs; ++j) {
+        const svtb200_mc_job *q = &jobs[j];
+        EB_U32 pos[2][2];
+        EbPictureBufferDesc_t *rp[2];
+        for (int l = 0; l < 2; ++l) {
+            rp[l] = &refDesc[q->ref_idx[l] < n_refs ? q->ref_idx[l] : 0];
+            pos[l][0] = (EB_U32)CLIP3((EB_S32)MVBOUNDLOW, (EB_S32)((rp[l]->width << 2) + MVBOUNDHIGH), (EB_S32)((q->x << 2) + REFPADD_QPEL + q->mv[l][0]));
+            pos[l][1] = (EB_U32)CLIP3((EB_S32)MVBOUNDLOW, (EB_S32)((rp[l]->height << 2) + MVBOUNDHIGH), (EB_S32)((q->y << 2) + REFPADD_QPEL + q->mv[l][1]));
+        }
+        const EB_U32 li = (EB_U32)(dstDesc.originX + q->x + (dstDesc.originY + q->y) * dstDesc.strideY);
+        const EB_U32 ci = (EB_U32)(((dstDesc.originX + q->x) >> 1) + ((dstDesc.originY + q->y) >> 1) * dstDesc.strideCb);
+        if (q->dir == 2)
+            BiPredHevcInterpolationMd(rp[0], rp[1], pos[0][0], pos[0][1], pos[1][0], pos[1][1], q->w, q->h, &dstDesc, li, ci, t0, t1, t2, EB_FALSE, PICTURE_BUFFER_DESC_FULL_MASK);
+        else
+            UniPredHevcInterpolationMd(rp[q->dir], pos[q->dir][0], pos[q->dir][1], q->w, q->h, &dstDesc, li, ci, t0, t2, EB_FALSE, PICTURE_BUFFER_DESC_FULL_MASK);
+    }
+    free(t0); free(t1); free(t2); free(refDesc);
+    return 0;
+}

@@ -120,6 +120,21 @@ def test_mc_ifree_port_vs_reference(case):
         assert np.array_equal(x, y) or x.shape != a.interior()[0].shape
 
 
+@needs_ref
+@pytest.mark.parametrize("case", MC_CASES, ids=lambda c: c[0])
+def test_md_interpolation_is_the_encode_pass_interpolation(case):
+    """UniPredHevcInterpolationMd / BiPredHevcInterpolationMd (Codec/EbMcp.c:99,321), the mode-decision wrappers of row b6: same kernels, same positions as the
+    encode pass -- so the entry point that is parity-tested on the GPU (svtb200_mc_batch) covers them"""
+    name, w, h, kind, all_fracs, big = case
+    refs = make_pictures(w, h, seed=17, kind=kind)
+    jobs = make_jobs(w, h, len(refs), seed=9, all_fracs=all_fracs, big_mv=big)
+    want = run_oracle(port, "port_mc_batch", refs, jobs, w, h)
+    for asm in ((0, 1) if common.ref_asm_simd_ok() else (0,)):
+        got = run_oracle(ref, "svtref_mc_md_batch", refs, jobs, w, h, asm_mode=asm)
+        for a, b, nm in zip(got.interior(), want.interior(), "Y Cb Cr".split()):
+            assert np.array_equal(a, b), f"{name}: {nm} differs (MD wrappers, asm {asm})"
+
+
 # ---- 16-bit samples (10-bit video), SURVEY §8 row b5 ---------------------------------------------------------------------
 def make_pictures16(w, h, seed, n=3, kind="synth"):
     rng = np.random.default_rng(seed + 1000)
